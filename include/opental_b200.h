@@ -68,17 +68,25 @@ OTAL_API int otal_bmp_backward_f64(const double* grad_out, const double* in, con
  * wide, which is how inception branches write straight into the concat buffer.
  * Weights: [kt*kh*kw][Cout][Cin] bf16 planes (tap-major, K-major rows).
  * y = relu?( conv(x, w) * scale[co] + shift[co] ), written as bf16 planes (y_hi/y_lo) and/or fp32 (y_f32).
- * Output extent equals input extent (pad front = pt/ph/pw, the rest of the "same" padding is implicit zero).
+ * Output extent = ceil(input extent / stride) (pad front = pt/ph/pw, the rest of the "same" padding is implicit
+ * zero: TMA out-of-bounds fill).  With accumulate = 1 the fp32 destination is read-modify-written, which is how the
+ * data-gradient of several consumers of one tensor is summed (dgrad = this same entry point run on the
+ * output-gradient with tap-flipped, channel-transposed weights).
  * (tT,tH,tW) is the 128-position tile box, tT*tH*tW == 128.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct otal_conv_desc {
-    int N, T, H, W;          /* batch and spatial extent (output == input extent) */
+    int N, T, H, W;          /* batch and INPUT spatial extent */
     int Cin, Cout;           /* channels read / written by this launch */
     int kt, kh, kw;          /* filter taps */
     int pt, ph, pw;          /* front padding */
     int tT, tH, tW;          /* tile box */
+    int sT, sH, sW;          /* conv stride per dim: 1 or 2 (0 = 1).  Output extent = ceil(input extent / stride) */
     int nsplit;              /* 1 = bf16, 3 = bf16x3 */
     int relu;
+    int accumulate;          /* y_f32 += result instead of y_f32 = result (dgrad into a shared gradient buffer) */
+    int dgrad;               /* data-gradient mode: x = output gradient planes [.., Cin = forward Cout], w = the
+                                FORWARD weights [taps][Cin][Cout] read transposed with flipped taps, pt/ph/pw =
+                                k-1-forward pad, Cout = forward Cin.  Stride 1 only. */
     int in_cstride, in_coff;   /* input row width and slice offset, in channels */
     int out_cstride, out_coff; /* output row width and slice offset, in channels (bf16 planes and fp32 alike) */
     const uint16_t* x_hi; const uint16_t* x_lo;   /* bf16 bit patterns */
@@ -89,6 +97,93 @@ typedef struct otal_conv_desc {
 } otal_conv_desc;
 
 OTAL_API int otal_conv_igemm_fwd(const otal_conv_desc* desc, void* stream);
+
+/* Conv3d_1a_7x7: 7x7x7, stride 2, 3 input channels -> Cout, + folded BN + ReLU
+ *   AFSD/common/i3d_backbone.py:196-199 (end point), :51-87 (Unit3D.forward incl. the (2,3) "same" padding)
+ * x: the clip as written by otal_clip_ingest, [N,T,H,Wp,8] bf16 planes (2 zero columns left of the image, >= 4
+ * right, channels 3..7 zero).  w: [49 (dt,dh)][Cout][64] planes, element dw*8 + c of a row = W[co,c,dt,dh,dw]
+ * (zero for dw == 7 or c >= 3).  y: [N,ceil(T/2),ceil(H/2),W/2,out_cstride] planes at channel offset out_coff. */
+typedef struct otal_conv1a_desc {
+    int N, T, H, W, Wp;
+    int Cout;
+    int tT, tH, tW;
+    int nsplit, relu;
+    int out_cstride, out_coff;
+    const uint16_t* x_hi; const uint16_t* x_lo;
+    const uint16_t* w_hi; const uint16_t* w_lo;
+    const float* scale; const float* shift;
+    uint16_t* y_hi; uint16_t* y_lo;
+} otal_conv1a_desc;
+OTAL_API int otal_conv1a_fwd(const otal_conv1a_desc* desc, void* stream);
+
+/* Weight gradient — replaces the weight part of torch's convolution_backward for Unit3D / Unit1D
+ *   AFSD/common/i3d_backbone.py:82 (conv3d), AFSD/common/layers.py:211 (conv1d)
+ * dw[tap][co][ci] += sum_{n,p} d[n,p,co] * x[n, s*p + tap - pad, ci]; x = saved conv input planes [N,T,H,W,x_cstride],
+ * d = output-gradient planes [N,ceil(T/s),..,d_cstride] (see otal_relu_bn_bwd_split).  dw is fp32, same layout as
+ * the forward weights, and is accumulated with float reductions: zero it (or keep the running gradient in it).
+ * (tT,tH,tW) is the 64-position K tile box. */
+typedef struct otal_wgrad_desc {
+    int N, T, H, W;          /* batch and INPUT (x) extent */
+    int Cin, Cout;
+    int kt, kh, kw;
+    int pt, ph, pw;
+    int sT, sH, sW;
+    int tT, tH, tW;
+    int nsplit;
+    int x_cstride, x_coff, d_cstride, d_coff;
+    const uint16_t* x_hi; const uint16_t* x_lo;
+    const uint16_t* d_hi; const uint16_t* d_lo;
+    float* dw;
+} otal_wgrad_desc;
+OTAL_API int otal_conv_wgrad(const otal_wgrad_desc* desc, void* stream);
+
+/* Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][64] fp32. */
+typedef struct otal_conv1a_wgrad_desc {
+    int N, T, H, W, Wp;
+    int Cout;
+    int tT, tH, tW;
+    int nsplit;
+    int d_cstride, d_coff;
+    const uint16_t* x_hi; const uint16_t* x_lo;
+    const uint16_t* d_hi; const uint16_t* d_lo;
+    float* dw;
+} otal_conv1a_wgrad_desc;
+OTAL_API int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* desc, void* stream);
+
+/* MaxPool3dSamePadding on NDHWC planes — replaces AFSD/common/layers.py:9-35 (zero pad + nn.MaxPool3d).
+ * Output extent = ceil(input / stride); (pt,ph,pw) = front padding of the "same" rule; padding competes as 0.
+ * forward: x planes -> y planes.  backward: g_in[argmax] += g_out (fp32, float reductions; zero g_in first unless it
+ * already holds the other consumers' gradient); x planes are the saved forward input. */
+typedef struct otal_pool_desc {
+    int N, T, H, W, C;
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int in_cstride, in_coff, out_cstride, out_coff;
+    int gout_cstride, gout_coff, gin_cstride, gin_coff;
+    const uint16_t* x_hi; const uint16_t* x_lo;
+    uint16_t* y_hi; uint16_t* y_lo;
+    const float* g_out; float* g_in;
+} otal_pool_desc;
+OTAL_API int otal_maxpool_fwd(const otal_pool_desc* desc, void* stream);
+OTAL_API int otal_maxpool_bwd(const otal_pool_desc* desc, void* stream);
+
+/* Clip ingest for Conv3d_1a — replaces `clips.cuda()` + the first F.pad (AFSD/thumos14/train.py:165,
+ * AFSD/common/i3d_backbone.py:59-79): NCDHW fp32 [N,C<=8,T,H,W] -> [N,T,H,Wp,8] bf16 planes, image column w at
+ * padded column w + pad_left, everything else zero.  lo may be NULL. */
+OTAL_API int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, int Wp,
+                              int pad_left, void* stream);
+
+/* Backward of relu(conv*scale+shift) w.r.t. the conv output, fused with the hi/lo split the tensor-core kernels read:
+ * d = g * [y > 0] * scale[c]   (torch relu backward + frozen BatchNorm3d, AFSD/thumos14/BDNet.py:39-49).
+ * g fp32 [npos, g_cstride] at g_coff, y_hi bf16 plane of the forward output, d planes.  relu = 0 skips the mask,
+ * scale may be NULL (=1), d_lo may be NULL. */
+OTAL_API int otal_relu_bn_bwd_split(const float* g, const uint16_t* y_hi, const float* scale, uint16_t* d_hi, uint16_t* d_lo,
+                                    long long npos, int C, int g_cstride, int g_coff, int y_cstride, int y_coff,
+                                    int d_cstride, int d_coff, int relu, void* stream);
+
+/* Adam with L2-in-gradient weight decay over a flat fp32 buffer — replaces torch.optim.Adam.step as configured by
+ * AFSD/thumos14/train.py:321-323.  g is multiplied by grad_scale first (1/world_size after a summing all-reduce). */
+OTAL_API int otal_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                            float eps, float weight_decay, float grad_scale, int step, void* stream);
 
 /* fp32 -> (hi, lo) bf16 planes, elementwise over n values (layout preserving). lo may be NULL. */
 OTAL_API int otal_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_int, c_longlong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libopental_b200.so")
@@ -17,24 +17,52 @@ OTAL_OK = 0
 ERR_NAMES = {-1: "OTAL_ERR_BAD_ARG", -2: "OTAL_ERR_CUDA", -3: "OTAL_ERR_DRIVER", -4: "OTAL_ERR_UNSUPPORTED"}
 
 
+def _ints(*names):
+    return [(n, c_int) for n in names]
+
+
+def _ptrs(*names):
+    return [(n, c_void_p) for n in names]
+
+
 class ConvDesc(Structure):
     """Mirror of `otal_conv_desc` (include/opental_b200.h)."""
 
-    _fields_ = [
-        ("N", c_int), ("T", c_int), ("H", c_int), ("W", c_int),
-        ("Cin", c_int), ("Cout", c_int),
-        ("kt", c_int), ("kh", c_int), ("kw", c_int),
-        ("pt", c_int), ("ph", c_int), ("pw", c_int),
-        ("tT", c_int), ("tH", c_int), ("tW", c_int),
-        ("nsplit", c_int), ("relu", c_int),
-        ("in_cstride", c_int), ("in_coff", c_int),
-        ("out_cstride", c_int), ("out_coff", c_int),
-        ("x_hi", c_void_p), ("x_lo", c_void_p),
-        ("w_hi", c_void_p), ("w_lo", c_void_p),
-        ("scale", c_void_p), ("shift", c_void_p),
-        ("y_hi", c_void_p), ("y_lo", c_void_p),
-        ("y_f32", c_void_p),
-    ]
+    _fields_ = (_ints("N", "T", "H", "W", "Cin", "Cout", "kt", "kh", "kw", "pt", "ph", "pw", "tT", "tH", "tW",
+                      "sT", "sH", "sW", "nsplit", "relu", "accumulate", "dgrad",
+                      "in_cstride", "in_coff", "out_cstride", "out_coff")
+                + _ptrs("x_hi", "x_lo", "w_hi", "w_lo", "scale", "shift", "y_hi", "y_lo", "y_f32"))
+
+
+class Conv1aDesc(Structure):
+    """Mirror of `otal_conv1a_desc`."""
+
+    _fields_ = (_ints("N", "T", "H", "W", "Wp", "Cout", "tT", "tH", "tW", "nsplit", "relu", "out_cstride", "out_coff")
+                + _ptrs("x_hi", "x_lo", "w_hi", "w_lo", "scale", "shift", "y_hi", "y_lo"))
+
+
+class WgradDesc(Structure):
+    """Mirror of `otal_wgrad_desc`."""
+
+    _fields_ = (_ints("N", "T", "H", "W", "Cin", "Cout", "kt", "kh", "kw", "pt", "ph", "pw", "sT", "sH", "sW",
+                      "tT", "tH", "tW", "nsplit", "x_cstride", "x_coff", "d_cstride", "d_coff")
+                + _ptrs("x_hi", "x_lo", "d_hi", "d_lo", "dw"))
+
+
+class Conv1aWgradDesc(Structure):
+    """Mirror of `otal_conv1a_wgrad_desc`."""
+
+    _fields_ = (_ints("N", "T", "H", "W", "Wp", "Cout", "tT", "tH", "tW", "nsplit", "d_cstride", "d_coff")
+                + _ptrs("x_hi", "x_lo", "d_hi", "d_lo", "dw"))
+
+
+class PoolDesc(Structure):
+    """Mirror of `otal_pool_desc`."""
+
+    _fields_ = (_ints("N", "T", "H", "W", "C", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw",
+                      "in_cstride", "in_coff", "out_cstride", "out_coff",
+                      "gout_cstride", "gout_coff", "gin_cstride", "gin_coff")
+                + _ptrs("x_hi", "x_lo", "y_hi", "y_lo", "g_out", "g_in"))
 
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/opental_b200.h.
@@ -46,6 +74,16 @@ SIGNATURES = {
     "otal_bmp_forward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_bmp_backward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_conv_igemm_fwd": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "otal_conv1a_fwd": (c_int, [POINTER(Conv1aDesc), c_void_p]),
+    "otal_conv_wgrad": (c_int, [POINTER(WgradDesc), c_void_p]),
+    "otal_conv1a_wgrad": (c_int, [POINTER(Conv1aWgradDesc), c_void_p]),
+    "otal_maxpool_fwd": (c_int, [POINTER(PoolDesc), c_void_p]),
+    "otal_maxpool_bwd": (c_int, [POINTER(PoolDesc), c_void_p]),
+    "otal_clip_ingest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_relu_bn_bwd_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,
+                               c_float, c_float, c_int, c_void_p]),
     "otal_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_merge_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_ncdhw_to_ndhwc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -42,6 +42,7 @@ struct ConvParams {
     int N, T, H, W;
     int Cin, Cout;
     int kt, kh, kw, pt, ph, pw;
+    int st, sh, sw;  // conv stride per dim (1 or 2); stride-2 dims read parity-split views of the input
     int tT, tH, tW;
     int tilesT, tilesH, tilesW;
     int BN, n_blocks, kchunks;
@@ -53,6 +54,8 @@ struct ConvParams {
     int total_tiles;
     int out_cstride; // fp32 output: channel stride (elements) of one position and channel offset of the slice
     int out_coff;
+    int accumulate;  // fp32 destination: y += result (dgrad into a shared gradient buffer)
+    int b_mn;        // dgrad mode: weights are read as [tap][K][N] (N contiguous, "MN-major" B) and taps are flipped
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
     float* out_f32;      // optional NDHWC fp32 destination (nullptr = skip)
@@ -64,11 +67,13 @@ struct ConvSmem {
     uint32_t staging_off, bar_off, total;
 };
 
-__host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nstages, int nbuf) {
+__host__ __device__ inline uint32_t conv_b_rows(int BN, int b_mn) { return b_mn ? (uint32_t)((BN + 63) / 64) * 64u : (uint32_t)BN; }
+
+__host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nstages, int nbuf, int b_mn) {
     ConvSmem s;
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
     s.a_bytes = kATileBytes * planes;
-    s.b_bytes = (uint32_t)BN * 128u * planes;
+    s.b_bytes = conv_b_rows(BN, b_mn) * 128u * planes;
     s.stage_bytes = s.a_bytes + s.b_bytes;
     s.staging_off = s.stage_bytes * (uint32_t)nstages;
     uint32_t staging = (uint32_t)nbuf * planes * kATileBytes;      // nbuf (0, 1 or 2) buffers x planes x 16 KB
@@ -77,15 +82,28 @@ __host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nst
     return s;
 }
 
+// All TMA descriptors of one launch.  A has one map per input parity class (pt*4 + ph*2 + pw) so that a
+// stride-2 conv reads the (even|odd) sub-lattice of the input as a dense tensor; stride-1 convs use A[0] only.
+struct alignas(64) ConvMaps {
+    CUtensorMap A_hi[8], A_lo[8];
+    CUtensorMap B_hi, B_lo, O_hi, O_lo;
+};
+
+// d = tap offset - front pad along one dim with stride s: input index = s*o + d = s*(o + q) + par
+__device__ __forceinline__ void split_parity(int d, int s, int& q, int& par) {
+    if (s == 1) { q = d; par = 0; }
+    else { par = d & 1; q = (d - par) >> 1; }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
-                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
-                  const __grid_constant__ CUtensorMap mapO_hi, const __grid_constant__ CUtensorMap mapO_lo,
-                  const ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+    const CUtensorMap& mapB_hi = maps.B_hi; const CUtensorMap& mapB_lo = maps.B_lo;
+    const CUtensorMap& mapO_hi = maps.O_hi; const CUtensorMap& mapO_lo = maps.O_lo;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment is required by the 128B swizzle pattern (pattern repeats every 8 rows x 128 B)
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, p.nstages, p.nbuf);
+    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, p.nstages, p.nbuf, p.b_mn);
+    const uint32_t b_plane = conv_b_rows(p.BN, p.b_mn) * 128u;   // bytes of one B plane per stage
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
@@ -97,9 +115,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     const bool split = p.nsplit == 3;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&mapA_hi);
+        tma_prefetch_desc(&maps.A_hi[0]);
         tma_prefetch_desc(&mapB_hi);
-        if (split) { tma_prefetch_desc(&mapA_lo); tma_prefetch_desc(&mapB_lo); }
+        if (split) { tma_prefetch_desc(&maps.A_lo[0]); tma_prefetch_desc(&mapB_lo); }
         if (p.store_bf16) { tma_prefetch_desc(&mapO_hi); if (split) tma_prefetch_desc(&mapO_lo); }
     }
     if (warp == 1 && lane == 0) {
@@ -129,19 +147,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 const int n = m;
                 for (int tap = 0; tap < ntaps; ++tap) {
                     const int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
+                    int qt, qh, qw, rt, rh, rw;
+                    split_parity(dt - p.pt, p.st, qt, rt);
+                    split_parity(dh - p.ph, p.sh, qh, rh);
+                    split_parity(dw - p.pw, p.sw, qw, rw);
+                    const int mi = rt * 4 + rh * 2 + rw;
+                    const CUtensorMap* mapA_hi = &maps.A_hi[mi];
+                    const CUtensorMap* mapA_lo = &maps.A_lo[mi];
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
                         unsigned char* sB = sA + L.a_bytes;
                         mbar_expect_tx(&full_bar[stage], L.stage_bytes);
                         const int c0 = kc * kChunkK;
-                        tma_load_5d(&mapA_hi, &full_bar[stage], sA, c0, w0 + dw - p.pw, h0 + dh - p.ph,
-                                    t0 + dt - p.pt, n);
-                        tma_load_3d(&mapB_hi, &full_bar[stage], sB, c0, nb * p.BN, tap);
+                        tma_load_5d(mapA_hi, &full_bar[stage], sA, c0, w0 + qw, h0 + qh, t0 + qt, n);
+                        if (!p.b_mn) {
+                            tma_load_3d(&mapB_hi, &full_bar[stage], sB, c0, nb * p.BN, tap);
+                            if (split) tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane, c0, nb * p.BN, tap);
+                        } else {
+                            // [64 K rows x 64 N] boxes of the flipped tap: N contiguous = MN-major B
+                            const int nbx = (p.BN + 63) / 64;
+                            for (int j = 0; j < nbx; ++j) {
+                                tma_load_3d(&mapB_hi, &full_bar[stage], sB + j * 8192, nb * p.BN + j * 64, c0, ntaps - 1 - tap);
+                                if (split)
+                                    tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane + j * 8192, nb * p.BN + j * 64, c0,
+                                                ntaps - 1 - tap);
+                            }
+                        }
                         if (split) {
-                            tma_load_5d(&mapA_lo, &full_bar[stage], sA + kATileBytes, c0, w0 + dw - p.pw,
-                                        h0 + dh - p.ph, t0 + dt - p.pt, n);
-                            tma_load_3d(&mapB_lo, &full_bar[stage], sB + (size_t)p.BN * 128, c0, nb * p.BN, tap);
+                            tma_load_5d(mapA_lo, &full_bar[stage], sA + kATileBytes, c0, w0 + qw, h0 + qh, t0 + qt, n);
                         }
                         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                     }
@@ -151,7 +185,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, 0, 0);
+            const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, 0, p.b_mn ? 1 : 0);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -166,11 +200,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t a_hi = umma_smem_desc_sw128(sA + k * 32, 16, 1024);
-                        const uint64_t b_hi = umma_smem_desc_sw128(sB + k * 32, 16, 1024);
+                        // K-major B: 32 bytes per K=16 step inside the swizzled row.  MN-major B (dgrad): 16 K rows =
+                        // 2048 bytes per step, LBO = 8 KB between 64-wide N boxes, SBO = 1 KB between 8-row groups.
+                        const uint64_t b_hi = p.b_mn ? umma_smem_desc_sw128(sB + k * 2048, 8192, 1024)
+                                                     : umma_smem_desc_sw128(sB + k * 32, 16, 1024);
                         umma_f16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
                         if (split) {
                             const uint64_t a_lo = umma_smem_desc_sw128(sA + kATileBytes + k * 32, 16, 1024);
-                            const uint64_t b_lo = umma_smem_desc_sw128(sB + p.BN * 128 + k * 32, 16, 1024);
+                            const uint64_t b_lo = p.b_mn ? umma_smem_desc_sw128(sB + b_plane + k * 2048, 8192, 1024)
+                                                         : umma_smem_desc_sw128(sB + b_plane + k * 32, 16, 1024);
                             umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
                             umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
                         }
@@ -244,8 +282,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         // Cout, out_coff and out_cstride are multiples of 8: groups of 4 are all-in or all-out
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
-                            if (cbase + j < p.Cout)
-                                *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            if (cbase + j < p.Cout) {
+                                float4* dst = reinterpret_cast<float4*>(orow + cbase + j);
+                                float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                                if (p.accumulate) { const float4 o = *dst; v4.x += o.x; v4.y += o.y; v4.z += o.z; v4.w += o.w; }
+                                *dst = v4;
+                            }
                     }
                     if (p.store_bf16) {
 #pragma unroll
@@ -305,6 +347,77 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// Everything the launcher needs besides the A maps (which differ between the generic and the folded conv1a path).
+struct ConvLaunch {
+    ConvParams p;
+    const uint16_t *w_hi, *w_lo;      // [taps][Cout][KW] bf16 planes, KW = weight row width (Cin or 64 for conv1a);
+                                      // dgrad (b_mn): [taps][K = w_k][N = Cout]
+    int w_k;                          // reduction width in elements
+    uint16_t *y_hi, *y_lo;
+    int To, Ho, Wo;                   // output extent
+};
+
+static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream) {
+    ConvParams& p = L.p;
+    const bool split = p.nsplit == 3;
+    p.T = L.To; p.H = L.Ho; p.W = L.Wo;      // the kernel tiles OUTPUT positions
+    p.tilesT = (p.T + p.tT - 1) / p.tT; p.tilesH = (p.H + p.tH - 1) / p.tH; p.tilesW = (p.W + p.tW - 1) / p.tW;
+    if (p.Cout <= 256) { p.n_blocks = 1; p.BN = (p.Cout + 15) / 16 * 16; }
+    else {
+        int best = 256, best_pad = 1 << 30;
+        for (int bn = 256; bn >= 64; bn -= 64) {
+            int pad = (p.Cout + bn - 1) / bn * bn;
+            if (pad < best_pad) { best_pad = pad; best = bn; }
+        }
+        p.BN = best; p.n_blocks = (p.Cout + best - 1) / best;
+    }
+    p.kchunks = (L.w_k + kChunkK - 1) / kChunkK;
+    p.store_bf16 = L.y_hi != nullptr;
+    p.total_tiles = p.N * p.tilesT * p.tilesH * p.tilesW * p.n_blocks;
+
+    const uint32_t smem_cap = 227 * 1024 - 1024;  // minus alignment slack
+    // prefer (>= 3 stages, double-buffered staging), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
+    int nst = 0, nbuf = p.store_bf16 ? 2 : 0;
+    for (int s = kMaxStages; s >= 3 && !nst; --s)
+        if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn).total <= smem_cap) nst = s;
+    if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn).total <= smem_cap) nst = 2;
+    if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn).total <= smem_cap) { nst = 2; nbuf = 1; }
+    if (!nst) { set_last_error_msg("conv: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
+    p.nstages = nst; p.nbuf = nbuf;
+    const ConvSmem SL = conv_smem_layout(p.BN, p.nsplit, nst, nbuf, p.b_mn);
+
+    int rc;
+    const int ntaps = p.kt * p.kh * p.kw;
+    // forward: rows of w_k reduction elements per output channel; dgrad: rows of Cout (N) elements per reduction index
+    const uint64_t brow = p.b_mn ? (uint64_t)p.Cout : (uint64_t)L.w_k;
+    const uint64_t bcol = p.b_mn ? (uint64_t)L.w_k : (uint64_t)p.Cout;
+    const uint64_t bdims[3] = {brow, bcol, (uint64_t)ntaps};
+    const uint64_t bst[2] = {brow * 2, brow * 2 * bcol};
+    const uint32_t bbox[3] = {64, p.b_mn ? 64u : (uint32_t)p.BN, 1};
+    if ((rc = make_tensor_map_bf16(&maps.B_hi, L.w_hi, 3, bdims, bst, bbox, 1))) return rc;
+    if (split && (rc = make_tensor_map_bf16(&maps.B_lo, L.w_lo, 3, bdims, bst, bbox, 1))) return rc;
+    if (p.store_bf16) {
+        const uint32_t obox[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+        const uint64_t odims[5] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.N};
+        const uint64_t cs = (uint64_t)p.out_cstride * 2;
+        const uint64_t ost[4] = {cs, cs * p.W, cs * p.W * p.H, cs * p.W * p.H * p.T};
+        if ((rc = make_tensor_map_bf16(&maps.O_hi, L.y_hi + p.out_coff, 5, odims, ost, obox, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.O_lo, L.y_lo + p.out_coff, 5, odims, ost, obox, 1))) return rc;
+    }
+
+    const size_t smem_bytes = SL.total + 1024;
+    static bool configured = false;
+    if (!configured) {
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+        configured = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
 }  // namespace otal
 
 using namespace otal;
@@ -324,81 +437,100 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
     }
     if (d->tT * d->tH * d->tW != kTileM) { set_last_error_msg("conv: tile box must hold 128 positions"); return OTAL_ERR_BAD_ARG; }
     if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("conv: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
+    const int st = d->sT ? d->sT : 1, sh = d->sH ? d->sH : 1, sw = d->sW ? d->sW : 1;
+    if ((st != 1 && st != 2) || (sh != 1 && sh != 2) || (sw != 1 && sw != 2)) {
+        set_last_error_msg("conv: stride must be 1 or 2"); return OTAL_ERR_BAD_ARG;
+    }
     const bool split = d->nsplit == 3;
     if (!d->x_hi || !d->w_hi || (split && (!d->x_lo || !d->w_lo))) { set_last_error_msg("conv: null operand plane"); return OTAL_ERR_BAD_ARG; }
-    const int store_bf16 = d->y_hi != nullptr;
-    if (store_bf16 && split && !d->y_lo) { set_last_error_msg("conv: y_lo missing"); return OTAL_ERR_BAD_ARG; }
-    if (!store_bf16 && !d->y_f32) { set_last_error_msg("conv: no destination"); return OTAL_ERR_BAD_ARG; }
+    if (d->y_hi && split && !d->y_lo) { set_last_error_msg("conv: y_lo missing"); return OTAL_ERR_BAD_ARG; }
+    if (!d->y_hi && !d->y_f32) { set_last_error_msg("conv: no destination"); return OTAL_ERR_BAD_ARG; }
+    if (d->dgrad && (st != 1 || sh != 1 || sw != 1)) { set_last_error_msg("conv: dgrad mode is stride-1 only"); return OTAL_ERR_BAD_ARG; }
+    if (d->accumulate && !d->y_f32) { set_last_error_msg("conv: accumulate needs the fp32 destination"); return OTAL_ERR_BAD_ARG; }
 
-    ConvParams p{};
-    p.N = d->N; p.T = d->T; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    ConvLaunch L{};
+    ConvParams& p = L.p;
+    p.N = d->N; p.Cin = d->Cin; p.Cout = d->Cout;
     p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+    p.st = st; p.sh = sh; p.sw = sw;
     p.tT = d->tT; p.tH = d->tH; p.tW = d->tW;
-    p.tilesT = (p.T + p.tT - 1) / p.tT; p.tilesH = (p.H + p.tH - 1) / p.tH; p.tilesW = (p.W + p.tW - 1) / p.tW;
-    if (p.Cout <= 256) { p.n_blocks = 1; p.BN = (p.Cout + 15) / 16 * 16; }
-    else {
-        int best = 256, best_pad = 1 << 30;
-        for (int bn = 256; bn >= 64; bn -= 64) {
-            int pad = (p.Cout + bn - 1) / bn * bn;
-            if (pad < best_pad) { best_pad = pad; best = bn; }
-        }
-        p.BN = best; p.n_blocks = (p.Cout + best - 1) / best;
-    }
-    p.kchunks = (p.Cin + kChunkK - 1) / kChunkK;
-    p.nsplit = d->nsplit; p.relu = d->relu; p.store_bf16 = store_bf16;
-    p.total_tiles = p.N * p.tilesT * p.tilesH * p.tilesW * p.n_blocks;
+    p.nsplit = d->nsplit; p.relu = d->relu; p.accumulate = d->accumulate; p.b_mn = d->dgrad ? 1 : 0;
     p.scale = d->scale; p.shift = d->shift; p.out_f32 = d->y_f32;
     p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+    L.w_hi = d->w_hi; L.w_lo = d->w_lo; L.w_k = d->Cin; L.y_hi = d->y_hi; L.y_lo = d->y_lo;
+    L.To = (d->T + st - 1) / st; L.Ho = (d->H + sh - 1) / sh; L.Wo = (d->W + sw - 1) / sw;
 
-    const uint32_t smem_cap = 227 * 1024 - 1024;  // minus alignment slack
-    // prefer (>= 3 stages, double-buffered staging), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
-    int nst = 0, nbuf = store_bf16 ? 2 : 0;
-    for (int s = kMaxStages; s >= 3 && !nst; --s)
-        if (conv_smem_layout(p.BN, p.nsplit, s, nbuf).total <= smem_cap) nst = s;
-    if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf).total <= smem_cap) nst = 2;
-    if (!nst && store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1).total <= smem_cap) { nst = 2; nbuf = 1; }
-    if (!nst) { set_last_error_msg("conv: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
-    p.nstages = nst; p.nbuf = nbuf;
-    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, nst, nbuf);
-
-    CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mO_hi, mO_lo;
-    memset(&mA_lo, 0, sizeof(mA_lo)); memset(&mB_lo, 0, sizeof(mB_lo));
-    memset(&mO_hi, 0, sizeof(mO_hi)); memset(&mO_lo, 0, sizeof(mO_lo));
+    ConvMaps maps;
+    memset(&maps, 0, sizeof(maps));
     int rc;
-    // activations: dims (C, W, H, T, N), channel slice [in_coff, in_coff+Cin) of rows of in_cstride channels
-    const uint64_t adims[5] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.N};
-    const uint64_t ast[4] = {(uint64_t)d->in_cstride * 2, (uint64_t)d->in_cstride * 2 * p.W,
-                             (uint64_t)d->in_cstride * 2 * p.W * p.H, (uint64_t)d->in_cstride * 2 * p.W * p.H * p.T};
+    // activations: dims (C, W, H, T, N), channel slice [in_coff, in_coff+Cin) of rows of in_cstride channels; one
+    // dense view per parity class of the strided dims
+    const uint64_t cs = (uint64_t)d->in_cstride * 2;
+    const uint64_t sW_ = cs, sH_ = cs * d->W, sT_ = cs * d->W * d->H, sN_ = cs * d->W * d->H * d->T;
     const uint32_t abox[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
-    if ((rc = make_tensor_map_bf16(&mA_hi, d->x_hi + d->in_coff, 5, adims, ast, abox, /*swizzle128=*/1))) return rc;
-    if (split && (rc = make_tensor_map_bf16(&mA_lo, d->x_lo + d->in_coff, 5, adims, ast, abox, 1))) return rc;
-    // weights: dims (Cin, Cout, taps)
-    const int ntaps = p.kt * p.kh * p.kw;
-    const uint64_t bdims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)ntaps};
-    const uint64_t bst[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cin * 2 * p.Cout};
-    const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
-    if ((rc = make_tensor_map_bf16(&mB_hi, d->w_hi, 3, bdims, bst, bbox, 1))) return rc;
-    if (split && (rc = make_tensor_map_bf16(&mB_lo, d->w_lo, 3, bdims, bst, bbox, 1))) return rc;
-    if (store_bf16) {
-        const uint64_t odims[5] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.N};
-        const uint64_t ost[4] = {(uint64_t)d->out_cstride * 2, (uint64_t)d->out_cstride * 2 * p.W,
-                                 (uint64_t)d->out_cstride * 2 * p.W * p.H,
-                                 (uint64_t)d->out_cstride * 2 * p.W * p.H * p.T};
-        if ((rc = make_tensor_map_bf16(&mO_hi, d->y_hi + d->out_coff, 5, odims, ost, abox, 1))) return rc;
-        if (split && (rc = make_tensor_map_bf16(&mO_lo, d->y_lo + d->out_coff, 5, odims, ost, abox, 1))) return rc;
+    for (int rt = 0; rt < st; ++rt) for (int rh = 0; rh < sh; ++rh) for (int rw = 0; rw < sw; ++rw) {
+        const int eT = (d->T - rt + st - 1) / st, eH = (d->H - rh + sh - 1) / sh, eW = (d->W - rw + sw - 1) / sw;
+        if (eT <= 0 || eH <= 0 || eW <= 0) continue;
+        const uint64_t adims[5] = {(uint64_t)p.Cin, (uint64_t)eW, (uint64_t)eH, (uint64_t)eT, (uint64_t)p.N};
+        const uint64_t ast[4] = {sW_ * sw, sH_ * sh, sT_ * st, sN_};
+        const size_t off = (size_t)d->in_coff + ((size_t)rt * d->H * d->W + (size_t)rh * d->W + rw) * d->in_cstride;
+        const int mi = rt * 4 + rh * 2 + rw;
+        if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 1))) return rc;
     }
+    return finish_and_launch(L, maps, stream);
+}
 
-    const size_t smem_bytes = L.total + 1024;
-    static size_t configured = 0;
-    if (smem_bytes > configured) {
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024));
-        configured = 227 * 1024;
+// Conv3d_1a_7x7 (AFSD/common/i3d_backbone.py:196-199): 7x7x7, stride 2, 3 input channels.
+// The clip is stored W-padded and channel-padded, [N,T,H,Wp,8] (otal_clip_ingest), so that the 7 W-taps x 8
+// channels of one (dt,dh) tap are 56 contiguous values: the A operand row of output column w' is the 64-element
+// window starting at padded column 2*w' (8th W-tap and channels 3..7 carry zero weights).  T and H use the
+// stride-2 parity views with TMA zero fill as padding; W padding is physical.
+int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!d) { set_last_error_msg("conv1a: null descriptor"); return OTAL_ERR_BAD_ARG; }
+    if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cout <= 0 || d->Cout % 8 || d->out_cstride % 8 || d->out_coff % 8) {
+        set_last_error_msg("conv1a: bad dimension"); return OTAL_ERR_BAD_ARG;
     }
-    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mO_hi, mO_lo, p);
-    OTAL_CUDA_TRY(cudaGetLastError());
-    return OTAL_OK;
+    if (d->W % 2 || d->Wp < d->W + 6) { set_last_error_msg("conv1a: W must be even and Wp >= W + 6"); return OTAL_ERR_BAD_ARG; }
+    if (d->tT * d->tH * d->tW != kTileM) { set_last_error_msg("conv1a: tile box must hold 128 positions"); return OTAL_ERR_BAD_ARG; }
+    if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("conv1a: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
+    const bool split = d->nsplit == 3;
+    if (!d->x_hi || !d->w_hi || (split && (!d->x_lo || !d->w_lo)) || !d->y_hi || (split && !d->y_lo)) {
+        set_last_error_msg("conv1a: null plane"); return OTAL_ERR_BAD_ARG;
+    }
+    ConvLaunch L{};
+    ConvParams& p = L.p;
+    p.N = d->N; p.Cin = 64; p.Cout = d->Cout;
+    p.kt = 7; p.kh = 7; p.kw = 1;
+    // "same" padding of k=7, s=2 on an even extent: total 5, front 2 (i3d_backbone.py:45-69)
+    p.pt = (d->T % 2 == 0) ? 2 : 3; p.ph = (d->H % 2 == 0) ? 2 : 3; p.pw = 0;
+    p.st = 2; p.sh = 2; p.sw = 1;
+    p.tT = d->tT; p.tH = d->tH; p.tW = d->tW;
+    p.nsplit = d->nsplit; p.relu = d->relu; p.accumulate = 0;
+    p.scale = d->scale; p.shift = d->shift; p.out_f32 = nullptr;
+    p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+    L.w_hi = d->w_hi; L.w_lo = d->w_lo; L.w_k = 64; L.y_hi = d->y_hi; L.y_lo = d->y_lo;
+    L.To = (d->T + 1) / 2; L.Ho = (d->H + 1) / 2; L.Wo = d->W / 2;
+
+    ConvMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    const uint64_t px = 8 * 2;                                  // bytes per padded pixel (8 channels)
+    const uint64_t sH_ = px * d->Wp, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
+    const uint32_t abox[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+    for (int rt = 0; rt < 2; ++rt) for (int rh = 0; rh < 2; ++rh) {
+        const int eT = (d->T - rt + 1) / 2, eH = (d->H - rh + 1) / 2;
+        if (eT <= 0 || eH <= 0) continue;
+        // dim0 = 64-element window, dim1 = output column (window origin advances 2 pixels = 16 elements)
+        const uint64_t adims[5] = {64, (uint64_t)L.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)p.N};
+        const uint64_t ast[4] = {2 * px, sH_ * 2, sT_ * 2, sN_};
+        const size_t off = ((size_t)rt * d->H + rh) * d->Wp * 8;
+        const int mi = rt * 4 + rh * 2;
+        if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 1))) return rc;
+    }
+    return finish_and_launch(L, maps, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,384 @@
+// Weight gradient of the implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces torch's convolution_backward (weight part) for Unit3D / Unit1D
+// (AFSD/common/i3d_backbone.py:82, AFSD/common/layers.py:211):
+//   dW[tap][co][ci] = sum_{n, p}  D[n, p, co] * X[n, s*p + tap - pad, ci]
+// with D = gradient w.r.t. the conv output (already multiplied by the ReLU mask and the folded-BN scale,
+// see relu_bn_bwd_split) and X the saved conv input, both NDHWC bf16 hi/lo planes.
+//
+// GEMM view per tap:  M = Cout (tile 128), N = Cin (tile <= 256), K = output positions.  In NDHWC both operands
+// have the *channel* (M resp. N) dimension contiguous, i.e. they are "MN-major" for the tensor core: the TMA boxes
+// [64 positions x 64 channels] land in shared memory as 128-byte-swizzled rows indexed by K, which is exactly the
+// canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units — no transposition
+// anywhere.  Padding is the TMA zero fill of the shifted X box; stride-2 convs read parity-split views of X.
+//
+// One work item = (tap, 128-row block of Cout, N block of Cin, K split).  The K split exists because K (positions,
+// up to 2.4 M at batch 8) is the long dimension while M x N x taps can be as small as 64 x 64 x 49; partial sums
+// are added to dW with fp32 reductions (red.global.add.f32), dW must be zeroed (or hold the running gradient) on
+// entry.  bf16x3: D_hi*X_hi + D_lo*X_hi + D_hi*X_lo with fp32 accumulation in TMEM.
+//
+// Warp roles (256 threads, persistent over work items): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 epilogue (tcgen05.ld -> red.add).
+#include "common.cuh"
+#include "tensormap.h"
+
+namespace otal {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgKP = 64;                 // positions per pipeline stage
+constexpr int kWgBox = kWgKP * 128;       // bytes of one [64 positions x 64 channels] bf16 box = 8 KB
+constexpr int kWgMaxStages = 6;
+
+struct WgParams {
+    int N, To, Ho, Wo;        // output (D) extent
+    int Cin, Cout;            // Cin = weight row width actually accumulated (64 for the folded conv1a)
+    int kt, kh, kw, pt, ph, pw, st, sh, sw;
+    int tT, tH, tW, tilesT, tilesH, tilesW;
+    int BN, n_blocks, m_blocks, ksplit, ktiles;   // ktiles = N * tilesT*tilesH*tilesW
+    int nsplit, nstages;
+    int total_items;
+    float* dw;
+};
+
+struct alignas(64) WgMaps {
+    CUtensorMap X_hi[8], X_lo[8];     // per parity class, as in the forward kernel
+    CUtensorMap D_hi, D_lo;
+};
+
+__device__ __forceinline__ void wg_split_parity(int d, int s, int& q, int& par) {
+    if (s == 1) { q = d; par = 0; }
+    else { par = d & 1; q = (d - par) >> 1; }
+}
+
+struct WgSmem { uint32_t a_bytes, b_bytes, stage_bytes, bar_off, total; };
+__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages) {
+    WgSmem s;
+    const uint32_t planes = nsplit == 3 ? 2u : 1u;
+    s.a_bytes = 2u * kWgBox * planes;                         // 128 rows of Cout = 2 boxes
+    s.b_bytes = (uint32_t)((BN + 63) / 64) * kWgBox * planes;
+    s.stage_bytes = s.a_bytes + s.b_bytes;
+    s.bar_off = s.stage_bytes * (uint32_t)nstages;
+    s.total = s.bar_off + 256;
+    return s;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* empty_bar = full_bar + kWgMaxStages;
+    uint64_t* tmem_full = empty_bar + kWgMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool split = p.nsplit == 3;
+    const uint32_t planes = split ? 2u : 1u;
+    const int nboxes_b = (p.BN + 63) / 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.X_hi[0]);
+        tma_prefetch_desc(&maps.D_hi);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // item -> (ks, nb, mb, tap); K tiles [k_begin, k_end) of the item's split
+    auto decode = [&](int item, int& tap, int& mb, int& nb, int& k_begin, int& k_end) {
+        const int ks = item % p.ksplit; item /= p.ksplit;
+        nb = item % p.n_blocks; item /= p.n_blocks;
+        mb = item % p.m_blocks; item /= p.m_blocks;
+        tap = item;
+        const long long kt_ = p.ktiles;
+        k_begin = (int)(kt_ * ks / p.ksplit);
+        k_end = (int)(kt_ * (ks + 1) / p.ksplit);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int tap, mb, nb, k0, k1;
+                decode(item, tap, mb, nb, k0, k1);
+                const int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
+                int qt, qh, qw, rt, rh, rw;
+                wg_split_parity(dt - p.pt, p.st, qt, rt);
+                wg_split_parity(dh - p.ph, p.sh, qh, rh);
+                wg_split_parity(dw - p.pw, p.sw, qw, rw);
+                const int mi = rt * 4 + rh * 2 + rw;
+                const int m_valid = min(128, p.Cout - mb * 128);
+                const int a_boxes = m_valid > 64 ? 2 : 1;     // rows 64..127 of a short block are never read back
+                const uint32_t tx = (uint32_t)(a_boxes + nboxes_b) * kWgBox * planes;
+                for (int k = k0; k < k1; ++k) {
+                    int m = k;
+                    const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
+                    const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
+                    const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
+                    const int n = m;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
+                    unsigned char* sB = sA + L.a_bytes;
+                    mbar_expect_tx(&full_bar[stage], tx);
+                    for (int j = 0; j < a_boxes; ++j) {
+                        tma_load_5d(&maps.D_hi, &full_bar[stage], sA + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n);
+                        if (split)
+                            tma_load_5d(&maps.D_lo, &full_bar[stage], sA + 2 * kWgBox + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n);
+                    }
+                    for (int j = 0; j < nboxes_b; ++j) {
+                        tma_load_5d(&maps.X_hi[mi], &full_bar[stage], sB + j * kWgBox, nb * p.BN + j * 64, w0 + qw, h0 + qh, t0 + qt, n);
+                        if (split)
+                            tma_load_5d(&maps.X_lo[mi], &full_bar[stage], sB + (nboxes_b + j) * kWgBox, nb * p.BN + j * 64,
+                                        w0 + qw, h0 + qh, t0 + qt, n);
+                    }
+                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);   // both operands MN-major
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int tap, mb, nb, k0, k1;
+                decode(item, tap, mb, nb, k0, k1);
+                if (k1 <= k0) continue;                       // empty split: nothing to add (producer/epilogue skip too)
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
+                for (int k = k0; k < k1; ++k) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
+                    const uint32_t sB = sA + L.a_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < kWgKP / 16; ++ks) {
+                        // 16 K rows = 2048 bytes; LBO = distance between 64-channel boxes, SBO = 8 K-rows
+                        const uint64_t a_hi = umma_smem_desc_sw128(sA + ks * 2048, kWgBox, 1024);
+                        const uint64_t b_hi = umma_smem_desc_sw128(sB + ks * 2048, kWgBox, 1024);
+                        umma_f16(d_tmem, a_hi, b_hi, idesc, (k != k0 || ks != 0));
+                        if (split) {
+                            const uint64_t a_lo = umma_smem_desc_sw128(sA + 2 * kWgBox + ks * 2048, kWgBox, 1024);
+                            const uint64_t b_lo = umma_smem_desc_sw128(sB + nboxes_b * kWgBox + ks * 2048, kWgBox, 1024);
+                            umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
+                            umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int tap, mb, nb, k0, k1;
+            decode(item, tap, mb, nb, k0, k1);
+            if (k1 <= k0) continue;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + (uint32_t)acc * 256 + ((uint32_t)(q * 32) << 16);
+            const int co = mb * 128 + row;
+            float* dst = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + nb * p.BN;
+            for (int col0 = 0; col0 < p.BN; col0 += 32) {
+                uint32_t v[32];
+                if (p.BN - col0 >= 32) tmem_ld32(t_acc + col0, v);
+                else {
+                    uint32_t v16[16];
+                    tmem_ld16(t_acc + col0, v16);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
+                }
+                tmem_ld_wait();
+                if (co < p.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ci = nb * p.BN + col0 + j;
+                        if (col0 + j < p.BN && ci < p.Cin) atomicAdd(dst + col0 + j, __uint_as_float(v[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int wg_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi, const uint16_t* d_lo, int d_cstride,
+                                int d_coff, cudaStream_t stream) {
+    const bool split = p.nsplit == 3;
+    p.tilesT = (p.To + p.tT - 1) / p.tT; p.tilesH = (p.Ho + p.tH - 1) / p.tH; p.tilesW = (p.Wo + p.tW - 1) / p.tW;
+    p.ktiles = p.N * p.tilesT * p.tilesH * p.tilesW;
+    p.m_blocks = (p.Cout + 127) / 128;
+    // N block: whole Cin when it fits 256 accumulator columns, else the multiple of 64 that wastes least
+    if (p.Cin <= 256) { p.BN = (p.Cin + 15) / 16 * 16; p.n_blocks = 1; }
+    else {
+        int best = 256, best_pad = 1 << 30;
+        for (int bn = 256; bn >= 64; bn -= 64) {
+            int pad = (p.Cin + bn - 1) / bn * bn;
+            if (pad < best_pad) { best_pad = pad; best = bn; }
+        }
+        p.BN = best; p.n_blocks = (p.Cin + best - 1) / best;
+    }
+    const int ntaps = p.kt * p.kh * p.kw;
+    const int base_items = ntaps * p.m_blocks * p.n_blocks;
+    int ks = (2 * wg_num_sms() + base_items - 1) / base_items;
+    if (ks > p.ktiles) ks = p.ktiles;
+    if (ks < 1) ks = 1;
+    p.ksplit = ks;
+    p.total_items = base_items * ks;
+
+    const uint32_t smem_cap = 227 * 1024 - 1024;
+    int nst = 0;
+    for (int s = kWgMaxStages; s >= 2 && !nst; --s)
+        if (wg_smem_layout(p.BN, p.nsplit, s).total <= smem_cap) nst = s;
+    if (!nst) { set_last_error_msg("wgrad: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
+    p.nstages = nst;
+    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst);
+
+    int rc;
+    const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+    const uint64_t ddims[5] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.To, (uint64_t)p.N};
+    const uint64_t cs = (uint64_t)d_cstride * 2;
+    const uint64_t dst_[4] = {cs, cs * p.Wo, cs * p.Wo * p.Ho, cs * p.Wo * p.Ho * p.To};
+    if ((rc = make_tensor_map_bf16(&maps.D_hi, d_hi + d_coff, 5, ddims, dst_, box, 1))) return rc;
+    if (split && (rc = make_tensor_map_bf16(&maps.D_lo, d_lo + d_coff, 5, ddims, dst_, box, 1))) return rc;
+
+    static bool configured = false;
+    if (!configured) {
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int grid = p.total_items < wg_num_sms() ? p.total_items : wg_num_sms();
+    conv_wgrad_kernel<<<grid, kWgThreads, SL.total + 1024, stream>>>(maps, p);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+}  // namespace otal
+
+using namespace otal;
+
+extern "C" {
+
+int otal_conv_wgrad(const otal_wgrad_desc* d, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!d) { set_last_error_msg("wgrad: null descriptor"); return OTAL_ERR_BAD_ARG; }
+    if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) {
+        set_last_error_msg("wgrad: non-positive dimension"); return OTAL_ERR_BAD_ARG;
+    }
+    if (d->Cin % 8 || d->Cout % 8 || d->x_cstride % 8 || d->x_coff % 8 || d->d_cstride % 8 || d->d_coff % 8) {
+        set_last_error_msg("wgrad: channel counts / strides / offsets must be multiples of 8"); return OTAL_ERR_BAD_ARG;
+    }
+    if (d->tT * d->tH * d->tW != kWgKP) { set_last_error_msg("wgrad: K tile box must hold 64 positions"); return OTAL_ERR_BAD_ARG; }
+    if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("wgrad: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
+    const int st = d->sT ? d->sT : 1, sh = d->sH ? d->sH : 1, sw = d->sW ? d->sW : 1;
+    if ((st != 1 && st != 2) || (sh != 1 && sh != 2) || (sw != 1 && sw != 2)) {
+        set_last_error_msg("wgrad: stride must be 1 or 2"); return OTAL_ERR_BAD_ARG;
+    }
+    const bool split = d->nsplit == 3;
+    if (!d->x_hi || !d->d_hi || !d->dw || (split && (!d->x_lo || !d->d_lo))) { set_last_error_msg("wgrad: null pointer"); return OTAL_ERR_BAD_ARG; }
+
+    WgParams p{};
+    p.N = d->N; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.To = (d->T + st - 1) / st; p.Ho = (d->H + sh - 1) / sh; p.Wo = (d->W + sw - 1) / sw;
+    p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+    p.st = st; p.sh = sh; p.sw = sw;
+    p.tT = d->tT; p.tH = d->tH; p.tW = d->tW;
+    p.nsplit = d->nsplit; p.dw = d->dw;
+
+    WgMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    const uint64_t cs = (uint64_t)d->x_cstride * 2;
+    const uint64_t sW_ = cs, sH_ = cs * d->W, sT_ = cs * d->W * d->H, sN_ = cs * d->W * d->H * d->T;
+    const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+    for (int rt = 0; rt < st; ++rt) for (int rh = 0; rh < sh; ++rh) for (int rw = 0; rw < sw; ++rw) {
+        const int eT = (d->T - rt + st - 1) / st, eH = (d->H - rh + sh - 1) / sh, eW = (d->W - rw + sw - 1) / sw;
+        if (eT <= 0 || eH <= 0 || eW <= 0) continue;
+        const uint64_t xdims[5] = {(uint64_t)d->Cin, (uint64_t)eW, (uint64_t)eH, (uint64_t)eT, (uint64_t)d->N};
+        const uint64_t xst[4] = {sW_ * sw, sH_ * sh, sT_ * st, sN_};
+        const size_t off = (size_t)d->x_coff + ((size_t)rt * d->H * d->W + (size_t)rh * d->W + rw) * d->x_cstride;
+        const int mi = rt * 4 + rh * 2 + rw;
+        if ((rc = make_tensor_map_bf16(&maps.X_hi[mi], d->x_hi + off, 5, xdims, xst, box, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 1))) return rc;
+    }
+    return wg_finish_and_launch(p, maps, d->d_hi, d->d_lo, d->d_cstride, d->d_coff, stream);
+}
+
+// Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][64] fp32.
+int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!d) { set_last_error_msg("conv1a_wgrad: null descriptor"); return OTAL_ERR_BAD_ARG; }
+    if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->W % 2 || d->Wp < d->W + 6 || d->Cout <= 0 || d->Cout % 8 ||
+        d->d_cstride % 8 || d->d_coff % 8) {
+        set_last_error_msg("conv1a_wgrad: bad dimension"); return OTAL_ERR_BAD_ARG;
+    }
+    if (d->tT * d->tH * d->tW != kWgKP) { set_last_error_msg("conv1a_wgrad: K tile box must hold 64 positions"); return OTAL_ERR_BAD_ARG; }
+    if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("conv1a_wgrad: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
+    const bool split = d->nsplit == 3;
+    if (!d->x_hi || !d->d_hi || !d->dw || (split && (!d->x_lo || !d->d_lo))) { set_last_error_msg("conv1a_wgrad: null pointer"); return OTAL_ERR_BAD_ARG; }
+
+    WgParams p{};
+    p.N = d->N; p.Cin = 64; p.Cout = d->Cout;
+    p.To = (d->T + 1) / 2; p.Ho = (d->H + 1) / 2; p.Wo = d->W / 2;
+    p.kt = 7; p.kh = 7; p.kw = 1;
+    p.pt = (d->T % 2 == 0) ? 2 : 3; p.ph = (d->H % 2 == 0) ? 2 : 3; p.pw = 0;
+    p.st = 2; p.sh = 2; p.sw = 1;
+    p.tT = d->tT; p.tH = d->tH; p.tW = d->tW;
+    p.nsplit = d->nsplit; p.dw = d->dw;
+
+    WgMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    const uint64_t px = 8 * 2;
+    const uint64_t sH_ = px * d->Wp, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
+    const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+    for (int rt = 0; rt < 2; ++rt) for (int rh = 0; rh < 2; ++rh) {
+        const int eT = (d->T - rt + 1) / 2, eH = (d->H - rh + 1) / 2;
+        if (eT <= 0 || eH <= 0) continue;
+        const uint64_t xdims[5] = {64, (uint64_t)p.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)d->N};
+        const uint64_t xst[4] = {2 * px, sH_ * 2, sT_ * 2, sN_};
+        const size_t off = ((size_t)rt * d->H + rh) * d->Wp * 8;
+        const int mi = rt * 4 + rh * 2;
+        if ((rc = make_tensor_map_bf16(&maps.X_hi[mi], d->x_hi + off, 5, xdims, xst, box, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 1))) return rc;
+    }
+    return wg_finish_and_launch(p, maps, d->d_hi, d->d_lo, d->d_cstride, d->d_coff, stream);
+}
+
+}  // extern "C"

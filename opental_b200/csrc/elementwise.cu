@@ -50,6 +50,97 @@ __global__ void ncdhw_to_ndhwc_split_kernel(const float* __restrict__ x, uint16_
     }
 }
 
+
+// Clip ingest for Conv3d_1a: NCDHW fp32 [N,C,T,H,W] -> [N,T,H,Wp,8] bf16 planes; image column w lands at padded
+// column w + pad_left, every other element (pad columns, channels >= C) is zero.  One thread per padded pixel:
+// reads are coalesced along w per channel plane, the 16-byte pixel is written with one vector store per plane.
+__global__ void clip_ingest_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                   int N, int C, int T, int H, int W, int Wp, int pad_left) {
+    const long long total = (long long)N * T * H * Wp;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long THW = (long long)T * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int wp = (int)(i % Wp);
+        const long long row = i / Wp;                 // (n*T + t)*H + h
+        const int w = wp - pad_left;
+        uint32_t h32[4] = {0, 0, 0, 0}, l32[4] = {0, 0, 0, 0};
+        if (w >= 0 && w < W) {
+            const long long n = row / ((long long)T * H);
+            const long long th = row - n * (long long)T * H;
+            const float* src = x + n * C * THW + th * W + w;
+            for (int c = 0; c < C && c < 8; ++c) {
+                __nv_bfloat16 hb, lb;
+                split_bf16(src[c * THW], hb, lb);
+                h32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
+                l32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
+            }
+        }
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h32[0], h32[1], h32[2], h32[3]);
+        if (lo) reinterpret_cast<uint4*>(lo)[i] = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+    }
+}
+
+// Backward of  y = relu(conv * scale + shift)  w.r.t. the conv output, fused with the bf16 hi/lo split that the
+// dgrad / wgrad tensor-core kernels consume:  d = g * [y > 0] * scale[c].   (ReLU backward of torch is
+// grad * (result > 0); frozen BN contributes only its scale, AFSD/thumos14/BDNet.py:39-49.)
+// One thread per (position, 8 channels): 32 B of g + 16 B of y_hi in, 2 x 16 B out.
+__global__ void relu_bn_bwd_split_kernel(const float* __restrict__ g, const uint16_t* __restrict__ y_hi,
+                                         const float* __restrict__ scale, uint16_t* __restrict__ d_hi,
+                                         uint16_t* __restrict__ d_lo, long long npos, int C, int g_cs, int g_co,
+                                         int y_cs, int y_co, int d_cs, int d_co, int relu) {
+    const int cgs = C >> 3;
+    const long long total = npos * cgs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cg = (int)(i % cgs);
+        const long long pos = i / cgs;
+        const float* gp = g + pos * g_cs + g_co + cg * 8;
+        const float4 a = *reinterpret_cast<const float4*>(gp), b = *reinterpret_cast<const float4*>(gp + 4);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t yw[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
+        if (relu) {
+            const uint4 yv = *reinterpret_cast<const uint4*>(y_hi + pos * y_cs + y_co + cg * 8);
+            yw[0] = yv.x; yw[1] = yv.y; yw[2] = yv.z; yw[3] = yv.w;
+        }
+        uint32_t ho[4], lo_[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x0 = v[2 * j], x1 = v[2 * j + 1];
+            // y > 0  <=>  bf16 bits: sign clear and magnitude non-zero
+            const uint32_t y0 = yw[j] & 0xffffu, y1 = yw[j] >> 16;
+            if (!(y0 != 0 && y0 < 0x8000u)) x0 = 0.f;
+            if (!(y1 != 0 && y1 < 0x8000u)) x1 = 0.f;
+            if (scale) { x0 *= __ldg(scale + cg * 8 + 2 * j); x1 *= __ldg(scale + cg * 8 + 2 * j + 1); }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(x0, h0, l0); split_bf16(x1, h1, l1);
+            ho[j] = pack_bf16x2(h0, h1); lo_[j] = pack_bf16x2(l0, l1);
+        }
+        const size_t off = (size_t)pos * d_cs + d_co + cg * 8;
+        *reinterpret_cast<uint4*>(d_hi + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        if (d_lo) *reinterpret_cast<uint4*>(d_lo + off) = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+    }
+}
+
+// Adam with classic L2 weight decay (grad += wd * p before the moments; torch.optim.Adam as used by
+// AFSD/thumos14/train.py:321-323) over one flat fp32 parameter buffer, optional 1/world gradient
+// scaling fused in (data-parallel all-reduce epilogue).  step_size = lr / (1 - beta1^t), bc2 = 1 - beta2^t.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                            float wd, float grad_scale, float bc1, float bc2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pi = p[i];
+        float gi = g[i] * grad_scale + wd * pi;
+        float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
 static inline int grid_for(long long work_items, int threads) {
     long long b = (work_items + threads - 1) / threads;
     const long long cap = 148LL * 8;
@@ -92,6 +183,43 @@ int otal_ncdhw_to_ndhwc_split(const float* x, uint16_t* hi, uint16_t* lo, int N,
     const long long THW = (long long)T * H * W;
     ncdhw_to_ndhwc_split_kernel<<<grid_for((long long)N * THW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, hi, lo, N, C, THW, Cpad);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, int Wp,
+                     int pad_left, void* stream) {
+    if (N < 0 || C <= 0 || C > 8 || T <= 0 || H <= 0 || W <= 0 || pad_left < 0 || Wp < W + pad_left || !x || !hi) {
+        set_last_error_msg("clip_ingest: bad argument"); return OTAL_ERR_BAD_ARG;
+    }
+    if (N == 0) return OTAL_OK;
+    clip_ingest_kernel<<<grid_for((long long)N * T * H * Wp, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, hi, lo, N, C, T, H, W, Wp, pad_left);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+int otal_relu_bn_bwd_split(const float* g, const uint16_t* y_hi, const float* scale, uint16_t* d_hi, uint16_t* d_lo,
+                           long long npos, int C, int g_cstride, int g_coff, int y_cstride, int y_coff,
+                           int d_cstride, int d_coff, int relu, void* stream) {
+    if (npos < 0 || C <= 0 || C % 8 || g_cstride % 4 || g_coff % 4 || y_cstride % 8 || y_coff % 8 || d_cstride % 8 ||
+        d_coff % 8 || !g || !d_hi || (relu && !y_hi)) {
+        set_last_error_msg("relu_bn_bwd_split: bad argument"); return OTAL_ERR_BAD_ARG;
+    }
+    if (npos == 0) return OTAL_OK;
+    relu_bn_bwd_split_kernel<<<grid_for(npos * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        g, y_hi, scale, d_hi, d_lo, npos, C, g_cstride, g_coff, y_cstride, y_coff, d_cstride, d_coff, relu);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+int otal_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_scale, int step, void* stream) {
+    if (n < 0 || step < 1 || (n > 0 && (!p || !g || !m || !v))) { set_last_error_msg("adam: bad argument"); return OTAL_ERR_BAD_ARG; }
+    if (n == 0) return OTAL_OK;
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+    adam_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                             weight_decay, grad_scale, bc1, bc2);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

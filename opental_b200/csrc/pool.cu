@@ -1,0 +1,182 @@
+// MaxPool3dSamePadding on NDHWC bf16 hi/lo planes (forward) and its gradient routing (backward).
+//
+// Reference: AFSD/common/layers.py:9-35 — F.pad with constant ZERO ("same" rule, front = pad//2) followed by
+// nn.MaxPool3d; used by the four stage pools of I3D and the b3a branch of every inception module
+// (AFSD/common/i3d_backbone.py:104-105, :204, :224, :242, :279).  A window that reaches into the padding therefore
+// competes against 0, which we reproduce exactly (inputs are post-ReLU, so it never changes the result).
+//
+// HBM-bound: one thread owns 8 channels (one 16-byte vector per plane) of one output position; a warp covers
+// 256 consecutive channels, i.e. fully coalesced 512-byte rows in NDHWC.  Values are compared as hi + lo, which is
+// exact in fp32 (8 + 8 significant bits), and the winning (hi, lo) pair is forwarded unchanged, so the pool is
+// bit-exact on the represented values.
+//
+// Backward: the argmax of each window is recomputed (first maximum in (t,h,w) window order, strict '>', like
+// ATen's max_pool3d) and the fp32 gradient is added to the fp32 input-gradient buffer with red.global.add.f32.
+// Overlapping windows (k3 s1 / k3 s2) make the adds collide; sums have at most 27 terms.
+#include "common.cuh"
+
+namespace otal {
+
+struct PoolParams {
+    int N, T, H, W, C;
+    int To, Ho, Wo;
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int in_cstride, in_coff, out_cstride, out_coff;
+    int gout_cstride, gout_coff, gin_cstride, gin_coff;
+    const uint16_t *x_hi, *x_lo;
+    uint16_t *y_hi, *y_lo;
+    const float* g_out;
+    float* g_in;
+};
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4* l, float (&v)[8]) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = bf16_bits_to_float(hw[i] & 0xffffu);
+        v[2 * i + 1] = bf16_bits_to_float(hw[i] >> 16);
+    }
+    if (l) {
+        const uint32_t lw[4] = {l->x, l->y, l->z, l->w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] += bf16_bits_to_float(lw[i] & 0xffffu);
+            v[2 * i + 1] += bf16_bits_to_float(lw[i] >> 16);
+        }
+    }
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const PoolParams p) {
+    const int cgs = p.C >> 3;
+    const long long total = (long long)p.N * p.To * p.Ho * p.Wo * cgs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int cg = (int)(idx % cgs);
+        long long pos = idx / cgs;
+        const int wo = (int)(pos % p.Wo); pos /= p.Wo;
+        const int ho = (int)(pos % p.Ho); pos /= p.Ho;
+        const int to = (int)(pos % p.To);
+        const int n = (int)(pos / p.To);
+        const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
+        const bool touches_pad = t0 < 0 || h0 < 0 || w0 < 0 || t0 + p.kt > p.T || h0 + p.kh > p.H || w0 + p.kw > p.W;
+
+        float best[8];
+        uint32_t bh[8], bl[8];
+        long long barg[8];
+        bool have = false;
+        if (touches_pad) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { best[j] = 0.f; bh[j] = 0; bl[j] = 0; barg[j] = -1; }
+            have = true;
+        }
+        for (int dt = 0; dt < p.kt; ++dt) {
+            const int t = t0 + dt;
+            if (t < 0 || t >= p.T) continue;
+            for (int dh = 0; dh < p.kh; ++dh) {
+                const int h = h0 + dh;
+                if (h < 0 || h >= p.H) continue;
+                for (int dw = 0; dw < p.kw; ++dw) {
+                    const int w = w0 + dw;
+                    if (w < 0 || w >= p.W) continue;
+                    const long long ipos = (((long long)n * p.T + t) * p.H + h) * p.W + w;
+                    const size_t off = (size_t)ipos * p.in_cstride + p.in_coff + cg * 8;
+                    const uint4 hv = *reinterpret_cast<const uint4*>(p.x_hi + off);
+                    uint4 lv = make_uint4(0, 0, 0, 0);
+                    if (p.x_lo) lv = *reinterpret_cast<const uint4*>(p.x_lo + off);
+                    float v[8];
+                    unpack8(hv, p.x_lo ? &lv : nullptr, v);
+                    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!have || v[j] > best[j]) {
+                            best[j] = v[j];
+                            bh[j] = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xffffu);
+                            bl[j] = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xffffu);
+                            barg[j] = ipos;
+                        }
+                    }
+                    have = true;
+                }
+            }
+        }
+        const long long opos = (((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo;
+        if (!kBackward) {
+            const size_t off = (size_t)opos * p.out_cstride + p.out_coff + cg * 8;
+            *reinterpret_cast<uint4*>(p.y_hi + off) =
+                make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
+            if (p.y_lo)
+                *reinterpret_cast<uint4*>(p.y_lo + off) =
+                    make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
+        } else {
+            const float* g = p.g_out + (size_t)opos * p.gout_cstride + p.gout_coff + cg * 8;
+            const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (barg[j] >= 0 && gv[j] != 0.f)
+                    atomicAdd(p.g_in + (size_t)barg[j] * p.gin_cstride + p.gin_coff + cg * 8 + j, gv[j]);
+        }
+    }
+}
+
+static int fill_pool(const otal_pool_desc* d, PoolParams& p, bool backward) {
+    if (!d) { set_last_error_msg("pool: null descriptor"); return OTAL_ERR_BAD_ARG; }
+    if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->C % 8 || d->in_cstride % 8 || d->in_coff % 8) {
+        set_last_error_msg("pool: bad dimension (channels / strides / offsets must be multiples of 8)"); return OTAL_ERR_BAD_ARG;
+    }
+    if (d->kt < 1 || d->kh < 1 || d->kw < 1 || d->st < 1 || d->sh < 1 || d->sw < 1) {
+        set_last_error_msg("pool: bad window"); return OTAL_ERR_BAD_ARG;
+    }
+    if (!d->x_hi) { set_last_error_msg("pool: null input"); return OTAL_ERR_BAD_ARG; }
+    if (!backward && (!d->y_hi || d->out_cstride % 8 || d->out_coff % 8 || (d->x_lo && !d->y_lo))) {
+        set_last_error_msg("pool: bad output"); return OTAL_ERR_BAD_ARG;
+    }
+    if (backward && (!d->g_out || !d->g_in || d->gout_cstride % 4 || d->gout_coff % 4)) {
+        set_last_error_msg("pool: bad gradient buffers"); return OTAL_ERR_BAD_ARG;
+    }
+    p.N = d->N; p.T = d->T; p.H = d->H; p.W = d->W; p.C = d->C;
+    p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw;
+    p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+    p.To = (d->T + d->st - 1) / d->st; p.Ho = (d->H + d->sh - 1) / d->sh; p.Wo = (d->W + d->sw - 1) / d->sw;
+    p.in_cstride = d->in_cstride; p.in_coff = d->in_coff; p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+    p.gout_cstride = d->gout_cstride; p.gout_coff = d->gout_coff; p.gin_cstride = d->gin_cstride; p.gin_coff = d->gin_coff;
+    p.x_hi = d->x_hi; p.x_lo = d->x_lo; p.y_hi = d->y_hi; p.y_lo = d->y_lo; p.g_out = d->g_out; p.g_in = d->g_in;
+    return OTAL_OK;
+}
+
+static int pool_grid(const PoolParams& p) {
+    const long long total = (long long)p.N * p.To * p.Ho * p.Wo * (p.C >> 3);
+    long long b = (total + 255) / 256;
+    const long long cap = 148LL * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace otal
+
+using namespace otal;
+
+extern "C" {
+
+int otal_maxpool_fwd(const otal_pool_desc* d, void* stream) {
+    PoolParams p{};
+    int rc = fill_pool(d, p, false);
+    if (rc) return rc;
+    maxpool_kernel<false><<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+int otal_maxpool_bwd(const otal_pool_desc* d, void* stream) {
+    PoolParams p{};
+    int rc = fill_pool(d, p, true);
+    if (rc) return rc;
+    maxpool_kernel<true><<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+}  // extern "C"

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import ConvDesc
+from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, PoolDesc, WgradDesc
 
 
 def _require_cuda(*tensors: torch.Tensor) -> None:
@@ -116,14 +116,16 @@ def clip_to_ndhwc(x: torch.Tensor, cpad: int = 8, with_lo: bool = True) -> Plane
 
 
 # ----------------------------------------------------------------------------------------------------------
-# implicit-GEMM convolution
+# implicit-GEMM convolution (forward / dgrad / wgrad)
 # ----------------------------------------------------------------------------------------------------------
-def pick_tile_box(T: int, H: int, W: int) -> tuple[int, int, int]:
-    """128-position tile box (tT, tH, tW), powers of two, minimising padded positions; ties -> wider W."""
+def pick_tile_box(T: int, H: int, W: int, log2_positions: int = 7) -> tuple[int, int, int]:
+    """Tile box (tT, tH, tW) of 2**log2_positions positions, powers of two, minimising padded positions; ties ->
+    wider W.  128 positions for the forward/dgrad M tile, 64 for the wgrad K tile."""
     best = None
-    for lw in range(8):
-        for lh in range(8 - lw):
-            lt = 7 - lw - lh
+    n = log2_positions
+    for lw in range(n + 1):
+        for lh in range(n + 1 - lw):
+            lt = n - lw - lh
             tw, th, tt = 1 << lw, 1 << lh, 1 << lt
             padded = (-(-T // tt) * tt) * (-(-H // th) * th) * (-(-W // tw) * tw)
             key = (padded, -tw, -th)
@@ -141,42 +143,56 @@ def pack_conv_weight(w: torch.Tensor, with_lo: bool = True) -> Planes:
     return split_bf16(wt, with_lo)
 
 
+def _out_extent(size: int, stride: int) -> int:
+    return -(-size // stride)
+
+
 def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front: tuple[int, int, int],
+               stride: tuple[int, int, int] = (1, 1, 1),
                scale: torch.Tensor | None = None, shift: torch.Tensor | None = None, relu: bool = False,
                in_slice: tuple[int, int] | None = None, out: Planes | None = None,
                out_slice: tuple[int, int] | None = None, out_f32: torch.Tensor | None = None,
-               want_planes: bool = True, tile: tuple[int, int, int] | None = None) -> Planes | None:
+               want_planes: bool = True, tile: tuple[int, int, int] | None = None,
+               accumulate: bool = False, dgrad: bool = False) -> Planes | None:
     """y = relu?(conv(x, w) * scale + shift).  x: NDHWC planes [N,T,H,W,Cx]; w: [taps,Cout,Cin] planes.
 
     in_slice = (offset, Cin) reads a channel slice of x; out/out_slice = write into a slice of an existing buffer.
+    dgrad=True: x is the output gradient [.., forward Cout], w the FORWARD weights [taps, fwd Cout, fwd Cin]; the
+    result is the input gradient [.., fwd Cin] (pad_front must be k-1-forward pad).
     """
     _require_cuda(x.hi, w.hi)
     N, T, H, W, Cx = x.hi.shape
-    taps, Cout, Cin = w.hi.shape
     kt, kh, kw = kernel
+    if dgrad:
+        taps, Cin, Cout = w.hi.shape
+    else:
+        taps, Cout, Cin = w.hi.shape
     assert taps == kt * kh * kw
     in_coff, cin_used = in_slice if in_slice is not None else (0, Cx)
     assert cin_used == Cin, f"weight Cin {Cin} != input slice {cin_used}"
     nsplit = 3 if (x.lo is not None and w.lo is not None) else 1
+    To, Ho, Wo = (_out_extent(a, s) for a, s in zip((T, H, W), stride))
     if out is None and want_planes:
-        hi = torch.empty((N, T, H, W, Cout), dtype=torch.bfloat16, device=x.hi.device)
+        hi = torch.empty((N, To, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.hi.device)
         out = Planes(hi, torch.empty_like(hi) if nsplit == 3 else None)
     if out is not None:
         out_cstride = out.hi.shape[-1]
-        out_coff = out_slice[0] if out_slice is not None else 0
-        if out_slice is not None:
-            assert out_slice[1] == Cout
+        assert tuple(out.hi.shape[:4]) == (N, To, Ho, Wo)
     else:
         assert out_f32 is not None
         out_cstride = out_f32.shape[-1]
-        out_coff = out_slice[0] if out_slice is not None else 0
+    out_coff = out_slice[0] if out_slice is not None else 0
+    if out_slice is not None:
+        assert out_slice[1] == Cout
     if out_f32 is not None:
-        assert out_f32.shape[-1] == out_cstride and out_f32.dtype == torch.float32
-    tT, tH, tW = tile if tile is not None else pick_tile_box(T, H, W)
+        assert out_f32.shape[-1] == out_cstride and out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+        assert tuple(out_f32.shape[:4]) == (N, To, Ho, Wo)
+    tT, tH, tW = tile if tile is not None else pick_tile_box(To, Ho, Wo)
     d = ConvDesc(N=N, T=T, H=H, W=W, Cin=Cin, Cout=Cout, kt=kt, kh=kh, kw=kw,
                  pt=pad_front[0], ph=pad_front[1], pw=pad_front[2], tT=tT, tH=tH, tW=tW,
-                 nsplit=nsplit, relu=int(relu), in_cstride=Cx, in_coff=in_coff,
-                 out_cstride=out_cstride, out_coff=out_coff,
+                 sT=stride[0], sH=stride[1], sW=stride[2],
+                 nsplit=nsplit, relu=int(relu), accumulate=int(accumulate), dgrad=int(dgrad),
+                 in_cstride=Cx, in_coff=in_coff, out_cstride=out_cstride, out_coff=out_coff,
                  x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                  w_hi=w.hi.data_ptr(), w_lo=_ptr(w.lo) if nsplit == 3 else None,
                  scale=_ptr(scale), shift=_ptr(shift),
@@ -185,3 +201,176 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                  y_f32=_ptr(out_f32))
     _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
     return out
+
+
+def conv_wgrad(x: Planes, d: Planes, dw: torch.Tensor, *, kernel: tuple[int, int, int],
+               pad_front: tuple[int, int, int], stride: tuple[int, int, int] = (1, 1, 1),
+               in_slice: tuple[int, int] | None = None, d_slice: tuple[int, int] | None = None) -> None:
+    """dw[tap, co, ci] += sum_p d[p, co] * x[s*p + tap - pad, ci]  (fp32, [taps, Cout, Cin], contiguous)."""
+    _require_cuda(x.hi, d.hi, dw)
+    N, T, H, W, Cx = x.hi.shape
+    taps, Cout, Cin = dw.shape
+    kt, kh, kw = kernel
+    assert taps == kt * kh * kw and dw.dtype == torch.float32 and dw.is_contiguous()
+    x_coff, cin_used = in_slice if in_slice is not None else (0, Cx)
+    d_coff, cout_used = d_slice if d_slice is not None else (0, d.hi.shape[-1])
+    assert cin_used == Cin and cout_used == Cout
+    To, Ho, Wo = (_out_extent(a, s) for a, s in zip((T, H, W), stride))
+    assert tuple(d.hi.shape[:4]) == (N, To, Ho, Wo)
+    nsplit = 3 if (x.lo is not None and d.lo is not None) else 1
+    tT, tH, tW = pick_tile_box(To, Ho, Wo, 6)
+    desc = WgradDesc(N=N, T=T, H=H, W=W, Cin=Cin, Cout=Cout, kt=kt, kh=kh, kw=kw,
+                     pt=pad_front[0], ph=pad_front[1], pw=pad_front[2], sT=stride[0], sH=stride[1], sW=stride[2],
+                     tT=tT, tH=tH, tW=tW, nsplit=nsplit, x_cstride=Cx, x_coff=x_coff,
+                     d_cstride=d.hi.shape[-1], d_coff=d_coff,
+                     x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
+                     d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
+    _lib.call("otal_conv_wgrad", ctypes.byref(desc), _stream())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Conv3d_1a_7x7 (stride 2, 3 channels) in the folded layout
+# ----------------------------------------------------------------------------------------------------------
+CLIP_CPAD = 8
+CLIP_PAD_LEFT = 2
+
+
+def clip_padded_width(W: int) -> int:
+    return W + 8          # 2 zero columns left, 6 right (>= 4 needed by the 8-tap window)
+
+
+def clip_ingest(x: torch.Tensor, with_lo: bool = True) -> Planes:
+    """NCDHW fp32 clip [N,3,T,H,W] -> [N,T,H,Wp,8] bf16 planes (W- and channel-padded), the input of conv1a_fwd."""
+    _require_cuda(x)
+    x = x.contiguous().float()
+    N, C, T, H, W = x.shape
+    Wp = clip_padded_width(W)
+    hi = torch.empty((N, T, H, Wp, CLIP_CPAD), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if with_lo else None
+    _lib.call("otal_clip_ingest", x.data_ptr(), hi.data_ptr(), _ptr(lo), N, C, T, H, W, Wp, CLIP_PAD_LEFT, _stream())
+    return Planes(hi, lo)
+
+
+def pack_conv1a_weight(w: torch.Tensor, with_lo: bool = True) -> Planes:
+    """[Cout, 3, 7, 7, 7] fp32 -> [49 (dt,dh), Cout, 64] planes, row element dw*8 + c (zero for dw == 7, c >= 3)."""
+    Cout, C, kt, kh, kw = w.shape
+    assert (kt, kh, kw) == (7, 7, 7) and C <= CLIP_CPAD
+    f = torch.zeros((kt, kh, Cout, 8, CLIP_CPAD), dtype=torch.float32, device=w.device)
+    f[:, :, :, :kw, :C] = w.detach().float().permute(2, 3, 0, 4, 1)
+    return split_bf16(f.reshape(kt * kh, Cout, 64), with_lo)
+
+
+def unpack_conv1a_wgrad(dw: torch.Tensor, C: int = 3) -> torch.Tensor:
+    """[49, Cout, 64] folded weight gradient -> [Cout, C, 7, 7, 7]."""
+    Cout = dw.shape[1]
+    return dw.reshape(7, 7, Cout, 8, CLIP_CPAD)[:, :, :, :7, :C].permute(2, 4, 0, 1, 3).contiguous()
+
+
+def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shift: torch.Tensor | None,
+               relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None) -> Planes:
+    N, T, H, Wp, C8 = x.hi.shape
+    taps, Cout, K = w.hi.shape
+    assert C8 == CLIP_CPAD and taps == 49 and K == 64
+    nsplit = 3 if (x.lo is not None and w.lo is not None) else 1
+    To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
+    if out is None:
+        hi = torch.empty((N, To, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.hi.device)
+        out = Planes(hi, torch.empty_like(hi) if nsplit == 3 else None)
+    tT, tH, tW = pick_tile_box(To, Ho, Wo)
+    d = Conv1aDesc(N=N, T=T, H=H, W=W, Wp=Wp, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit, relu=int(relu),
+                   out_cstride=out.hi.shape[-1], out_coff=out_slice[0] if out_slice else 0,
+                   x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
+                   w_hi=w.hi.data_ptr(), w_lo=_ptr(w.lo) if nsplit == 3 else None,
+                   scale=_ptr(scale), shift=_ptr(shift), y_hi=out.hi.data_ptr(),
+                   y_lo=_ptr(out.lo) if nsplit == 3 else None)
+    _lib.call("otal_conv1a_fwd", ctypes.byref(d), _stream())
+    return out
+
+
+def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[int, int] | None = None) -> None:
+    """dw [49, Cout, 64] fp32 += folded weight gradient of Conv3d_1a."""
+    N, T, H, Wp, C8 = x.hi.shape
+    taps, Cout, K = dw.shape
+    assert taps == 49 and K == 64 and dw.dtype == torch.float32 and dw.is_contiguous()
+    nsplit = 3 if (x.lo is not None and d.lo is not None) else 1
+    To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
+    assert tuple(d.hi.shape[:4]) == (N, To, Ho, Wo)
+    tT, tH, tW = pick_tile_box(To, Ho, Wo, 6)
+    desc = Conv1aWgradDesc(N=N, T=T, H=H, W=W, Wp=Wp, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit,
+                           d_cstride=d.hi.shape[-1], d_coff=d_slice[0] if d_slice else 0,
+                           x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
+                           d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
+    _lib.call("otal_conv1a_wgrad", ctypes.byref(desc), _stream())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# max pooling, ReLU/BN backward, Adam
+# ----------------------------------------------------------------------------------------------------------
+def _pool_desc(x: Planes, kernel, stride, pad_front, in_slice) -> tuple[PoolDesc, tuple[int, int, int, int], int]:
+    N, T, H, W, Cx = x.hi.shape
+    coff, C = in_slice if in_slice is not None else (0, Cx)
+    d = PoolDesc(N=N, T=T, H=H, W=W, C=C, kt=kernel[0], kh=kernel[1], kw=kernel[2], st=stride[0], sh=stride[1],
+                 sw=stride[2], pt=pad_front[0], ph=pad_front[1], pw=pad_front[2], in_cstride=Cx, in_coff=coff,
+                 x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo))
+    out_shape = (N, _out_extent(T, stride[0]), _out_extent(H, stride[1]), _out_extent(W, stride[2]))
+    return d, out_shape, C
+
+
+def maxpool_fwd(x: Planes, *, kernel, stride, pad_front, in_slice=None, out: Planes | None = None,
+                out_slice=None) -> Planes:
+    _require_cuda(x.hi)
+    d, oshape, C = _pool_desc(x, kernel, stride, pad_front, in_slice)
+    if out is None:
+        hi = torch.empty((*oshape, C), dtype=torch.bfloat16, device=x.hi.device)
+        out = Planes(hi, torch.empty_like(hi) if x.lo is not None else None)
+    assert tuple(out.hi.shape[:4]) == oshape
+    d.out_cstride = out.hi.shape[-1]
+    d.out_coff = out_slice[0] if out_slice else 0
+    d.y_hi = out.hi.data_ptr()
+    d.y_lo = _ptr(out.lo) if x.lo is not None else None
+    _lib.call("otal_maxpool_fwd", ctypes.byref(d), _stream())
+    return out
+
+
+def maxpool_bwd(x: Planes, g_out: torch.Tensor, g_in: torch.Tensor, *, kernel, stride, pad_front, in_slice=None,
+                gout_slice=None, gin_slice=None) -> None:
+    """g_in[argmax window] += g_out  (fp32 NDHWC buffers; x = saved forward input planes)."""
+    _require_cuda(x.hi, g_out, g_in)
+    d, oshape, C = _pool_desc(x, kernel, stride, pad_front, in_slice)
+    assert tuple(g_out.shape[:4]) == oshape and tuple(g_in.shape[:4]) == tuple(x.hi.shape[:4])
+    assert g_out.dtype == torch.float32 and g_in.dtype == torch.float32 and g_out.is_contiguous() and g_in.is_contiguous()
+    d.gout_cstride = g_out.shape[-1]
+    d.gout_coff = gout_slice[0] if gout_slice else 0
+    d.gin_cstride = g_in.shape[-1]
+    d.gin_coff = gin_slice[0] if gin_slice else 0
+    d.g_out = g_out.data_ptr()
+    d.g_in = g_in.data_ptr()
+    _lib.call("otal_maxpool_bwd", ctypes.byref(d), _stream())
+
+
+def relu_bn_bwd_split(g: torch.Tensor, y: Planes | None, scale: torch.Tensor | None, *, C: int | None = None,
+                      g_slice=None, y_slice=None, relu: bool = True, with_lo: bool = True) -> Planes:
+    """d = g * [y > 0] * scale  as bf16 planes [.., C] (dense)."""
+    _require_cuda(g)
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    Cg = g.shape[-1]
+    g_coff, C_ = g_slice if g_slice is not None else (0, Cg)
+    C = C or C_
+    npos = g.numel() // Cg
+    hi = torch.empty((*g.shape[:-1], C), dtype=torch.bfloat16, device=g.device)
+    lo = torch.empty_like(hi) if with_lo else None
+    y_cs = y.hi.shape[-1] if y is not None else 8
+    y_co = y_slice[0] if y_slice else 0
+    _lib.call("otal_relu_bn_bwd_split", g.data_ptr(), _ptr(y.hi) if y is not None else None, _ptr(scale), hi.data_ptr(),
+              _ptr(lo), npos, C, Cg, g_coff, y_cs, y_co, C, 0, int(relu and y is not None), _stream())
+    return Planes(hi, lo)
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas=(0.9, 0.999),
+              eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, step: int = 1) -> None:
+    """In-place fused Adam (L2-in-gradient weight decay) over flat fp32 buffers."""
+    _require_cuda(p, g, m, v)
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    _lib.call("otal_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1],
+              eps, weight_decay, grad_scale, step, _stream())
