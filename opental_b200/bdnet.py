@@ -1,0 +1,341 @@
+"""BDNet (THUMOS14 flavour) with the reference's module API and state_dict, on the sm_100a kernels.
+
+Call-compatible with `AFSD/thumos14/BDNet.py:435-535`:
+    BDNet(in_channels=3, backbone_model=None, training=True, use_edl=False, use_rpl=False)
+    .forward(x, proposals=None, ssl=False, get_feat=False) -> dict(loc, conf, priors, prop_loc, prop_conf, center,
+        start, end, start_loc_prop, end_loc_prop, start_conf_prop, end_conf_prop, act, prop_act[, unct, prop_unct])
+The reference reads num_classes / os_head / evidence / ... from a global config evaluated at import time
+(BDNet.py:12-18); here they are keyword arguments, and `BDNet.from_config(cfg_dict, ...)` maps the same yaml keys.
+
+Backbone: `I3DBackbone` (opental_b200/backbone.py) — every Unit3D, max-pool, their gradients and the concat are
+hand-written sm_100a kernels.  BoundaryMaxPooling: the native operator (opental_b200/prop_pooling.py).  The 1-D
+pyramid / towers / heads (CoarsePyramid, BDNet.py:117-432; 5 GFLOP of 168, launch-bound) currently run as torch ops
+on the same stream; the duplicated frame-level pooling of the two proposal branches (BDNet.py:109 called from :386
+and :388 with identical arguments) is computed once per level.
+
+`use_rpl`, `get_feat`, the TransformerHead and dropout > 0 are baseline / ablation variants that are off in every
+OpenTAL config: NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .backbone import I3DBackbone, same_pad_front
+from .prop_pooling import BoundaryMaxPooling
+
+LAYER_NUM = 6        # BDNet.py:20
+CONV_CHANNELS = 512  # BDNet.py:21
+
+
+class Unit1D(nn.Module):
+    """conv1d with TF-style "same" padding and bias, no activation (AFSD/common/layers.py:178-214)."""
+
+    def __init__(self, in_channels, output_channels, kernel_shape=1, stride=1):
+        super().__init__()
+        self.conv1d = nn.Conv1d(in_channels, output_channels, kernel_shape, stride, padding=0, bias=True)
+        self._k, self._s = kernel_shape, stride
+
+    def forward(self, x):
+        t = x.shape[2]
+        total = max(self._k - self._s, 0) if t % self._s == 0 else max(self._k - t % self._s, 0)
+        if total:
+            x = F.pad(x, [total // 2, total - total // 2])
+        return self.conv1d(x)
+
+
+class Unit3DValid(nn.Module):
+    """Head-side Unit3D, padding='spatial_valid' with a full-extent spatial kernel (layers.py:143-175): a GEMM that
+    collapses H x W."""
+
+    def __init__(self, in_channels, output_channels, kernel_shape):
+        super().__init__()
+        assert kernel_shape[0] == 1
+        self.conv3d = nn.Conv3d(in_channels, output_channels, kernel_shape, bias=True)
+
+    def forward(self, x):
+        return self.conv3d(x)
+
+
+def _unit_gn(unit, channels):
+    return nn.Sequential(unit, nn.GroupNorm(32, channels), nn.ReLU(inplace=True))
+
+
+class ScaleExp(nn.Module):
+    """exp(x * scale) (BDNet.py:55-61)."""
+
+    def __init__(self, init_value=1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.FloatTensor([init_value]))
+
+    def forward(self, x):
+        return torch.exp(x * self.scale)
+
+
+class ProposalBranch(nn.Module):
+    """BDNet.py:64-113.  forward takes the already pooled frame-level feature (shared by both branches)."""
+
+    def __init__(self, in_channels, proposal_channels):
+        super().__init__()
+        self.cur_point_conv = _unit_gn(Unit1D(in_channels, proposal_channels, 1), proposal_channels)
+        self.lr_conv = _unit_gn(Unit1D(in_channels, proposal_channels * 2, 1), proposal_channels * 2)
+        self.boundary_max_pooling = BoundaryMaxPooling()
+        self.roi_conv = _unit_gn(Unit1D(proposal_channels, proposal_channels, 1), proposal_channels)
+        self.proposal_conv = _unit_gn(Unit1D(proposal_channels * 4, in_channels, 1), in_channels)
+
+    def forward(self, feature, pooled_frame_feature, segments):
+        fm_short = self.cur_point_conv(feature)
+        feature = self.lr_conv(feature)
+        prop_feature = self.boundary_max_pooling(feature, segments)
+        prop_roi_feature = self.roi_conv(pooled_frame_feature)
+        prop_feature = torch.cat([prop_roi_feature, prop_feature, fm_short], dim=1)
+        return self.proposal_conv(prop_feature), feature
+
+
+class CoarsePyramid(nn.Module):
+    """BDNet.py:117-432 (OpenTAL configuration: no RPL head, no transformer, dropout 0)."""
+
+    def __init__(self, feat_channels, num_classes, frame_num=256, os_head=False):
+        super().__init__()
+        out_channels = CONV_CHANNELS
+        self.num_classes = num_classes
+        self.frame_num = frame_num
+        self.os_head = os_head
+        self.layer_num = LAYER_NUM
+        feat_t = frame_num // 4
+        s4, s5 = frame_num // 4, frame_num // 8      # temporal extents of Mixed_4f / Mixed_5c
+        assert feat_t == s4 and s5 * 2 == s4
+        self.pyramids = nn.ModuleList()
+        self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[0], out_channels, [1, 6, 6]), out_channels))
+        self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[1], out_channels, [1, 3, 3]), out_channels))
+        for _ in range(2, LAYER_NUM):
+            self.pyramids.append(_unit_gn(Unit1D(out_channels, out_channels, 3, stride=2), out_channels))
+        self.loc_heads = nn.ModuleList([ScaleExp() for _ in range(LAYER_NUM)])
+
+        def tower():
+            return nn.Sequential(*[_unit_gn(Unit1D(out_channels, out_channels, 3), out_channels) for _ in range(2)])
+
+        self.loc_tower, self.conf_tower = tower(), tower()
+        self.loc_head = Unit1D(out_channels, 2, 3)
+        self.conf_head = Unit1D(out_channels, num_classes, 3)
+        if os_head:
+            self.actionness_head = Unit1D(out_channels, 1, 3)
+        self.loc_proposal_branch = ProposalBranch(out_channels, 512)
+        self.conf_proposal_branch = ProposalBranch(out_channels, 512)
+        self.prop_loc_head = Unit1D(out_channels, 2, 1)
+        self.prop_conf_head = Unit1D(out_channels, num_classes, 1)
+        if os_head:
+            self.prop_actionness_head = Unit1D(out_channels, 1, 1)
+        self.center_head = Unit1D(out_channels, 1, 3)
+        self.deconv = nn.Sequential(
+            Unit1D(out_channels, out_channels, 3), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True),
+            Unit1D(out_channels, out_channels, 3), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True),
+            Unit1D(out_channels, out_channels, 1), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True))
+        self.boundary_max_pooling = BoundaryMaxPooling()
+        self.priors = []
+        t = feat_t
+        for _ in range(LAYER_NUM):
+            self.priors.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32).view(-1, 1))
+            t = t // 2
+        self._prior_cache = {}
+
+    def _priors_on(self, device):
+        if device not in self._prior_cache:
+            self._prior_cache[device] = [p.to(device) for p in self.priors]
+        return self._prior_cache[device]
+
+    def _segments(self, loc, prior, t):
+        """Window generation under no_grad (BDNet.py:355-384); torch.round is half-to-even."""
+        with torch.no_grad():
+            B = loc.shape[0]
+            seg = loc / self.frame_num * t
+            pri = prior.view(1, t, 1).expand(B, t, 1)
+            centre = torch.round(pri * t - 0.5)
+            plen = seg[:, :, :1] + seg[:, :, 1:]
+            inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
+            ls, rs = centre - seg[:, :, :1], centre + seg[:, :, 1:]
+            segments = torch.cat([torch.round(ls - outl), torch.round(ls + inl),
+                                  torch.round(rs - inl), torch.round(rs + outl)], dim=-1)
+            dl = pri * self.frame_num - loc[:, :, :1]
+            dr = pri * self.frame_num + loc[:, :, 1:]
+            plen = dr - dl + 1.0
+            inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
+            frame_segments = torch.cat([torch.round(dl - outl), torch.round(dl + inl),
+                                        torch.round(dr - inl), torch.round(dr + outl)], dim=-1)
+        return segments.contiguous(), frame_segments.contiguous()
+
+    def forward(self, feat_dict, ssl=False, get_feat=False, forced_segments=None):
+        if get_feat:
+            raise NotImplementedError("get_feat is an analysis-only path (SURVEY D10)")
+        x1, x2 = feat_dict["Mixed_4f"], feat_dict["Mixed_5c"]
+        B = x1.size(0)
+        K = self.num_classes
+        feats = []
+        for i, conv in enumerate(self.pyramids):
+            if i == 0:
+                x = conv(x1).squeeze(-1).squeeze(-1)
+            elif i == 1:
+                x = conv(x2).squeeze(-1).squeeze(-1)
+                feats[-1] = feats[-1] + F.interpolate(x, feats[-1].shape[2:], mode="nearest")
+            else:
+                x = conv(x)
+            feats.append(x)
+        frame = F.interpolate(feats[0].unsqueeze(-1), [self.frame_num, 1]).squeeze(-1)
+        frame = self.deconv(frame).contiguous()
+        trip = [frame.clone()] if ssl else None
+        start = frame[:, :256].permute(0, 2, 1).contiguous()
+        end = frame[:, 256:].permute(0, 2, 1).contiguous()
+
+        priors = self._priors_on(x1.device)
+        locs, confs, acts, centers, plocs, pconfs, pacts = [], [], [], [], [], [], []
+        extra = {}
+        for i, feat in enumerate(feats):
+            loc_feat = self.loc_tower(feat)
+            conf_feat = self.conf_tower(feat)
+            t = feat.size(2)
+            loc = self.loc_heads[i](self.loc_head(loc_feat)).view(B, 2, -1).permute(0, 2, 1).contiguous()
+            locs.append(loc)
+            confs.append(self.conf_head(conf_feat).view(B, K, -1).permute(0, 2, 1).contiguous())
+            if self.os_head:
+                acts.append(self.actionness_head(conf_feat).view(B, 1, -1).permute(0, 2, 1).contiguous())
+            if forced_segments is not None:
+                segments, frame_segments = forced_segments[i]
+            else:
+                segments, frame_segments = self._segments(loc, priors[i], t)
+            pooled_frame = self.boundary_max_pooling(frame, frame_segments)      # shared by both branches (F5)
+            loc_prop, loc_lr = self.loc_proposal_branch(loc_feat, pooled_frame, segments)
+            conf_prop, conf_lr = self.conf_proposal_branch(conf_feat, pooled_frame, segments)
+            if i == 0:
+                if ssl:
+                    trip.extend([loc_lr.clone(), conf_lr.clone()])
+                    return trip
+                nd = loc_lr.size(1) // 2
+                extra = dict(start_loc_prop=loc_lr[:, :nd].permute(0, 2, 1).contiguous(),
+                             end_loc_prop=loc_lr[:, nd:].permute(0, 2, 1).contiguous(),
+                             start_conf_prop=conf_lr[:, :nd].permute(0, 2, 1).contiguous(),
+                             end_conf_prop=conf_lr[:, nd:].permute(0, 2, 1).contiguous())
+            plocs.append(self.prop_loc_head(loc_prop).view(B, 2, -1).permute(0, 2, 1).contiguous())
+            pconfs.append(self.prop_conf_head(conf_prop).view(B, K, -1).permute(0, 2, 1).contiguous())
+            if self.os_head:
+                pacts.append(self.prop_actionness_head(conf_prop).view(B, 1, -1).permute(0, 2, 1).contiguous())
+            centers.append(self.center_head(loc_prop).view(B, 1, -1).permute(0, 2, 1).contiguous())
+        out = dict(loc=torch.cat(locs, 1), conf=torch.cat(confs, 1), priors=torch.cat(priors, 0),
+                   prop_loc=torch.cat(plocs, 1), prop_conf=torch.cat(pconfs, 1), center=torch.cat(centers, 1),
+                   start=start, end=end, **extra,
+                   act=torch.cat(acts, 1) if self.os_head else None,
+                   prop_act=torch.cat(pacts, 1) if self.os_head else None)
+        return out
+
+
+class DirichletLayer(nn.Module):
+    """BDNet.py:538-561."""
+
+    def __init__(self, evidence="exp", dim=-1):
+        super().__init__()
+        assert evidence in ("relu", "exp", "softplus")
+        self.evidence, self.dim = evidence, dim
+
+    def evidence_func(self, logit):
+        if self.evidence == "relu":
+            return F.relu(logit)
+        if self.evidence == "exp":
+            return torch.exp(torch.clamp(logit, -10, 10))
+        return F.softplus(logit)
+
+    def compute_uncertainty(self, logit):
+        num_classes = logit.size(-1)
+        alpha = self.evidence_func(logit) + 1
+        return num_classes / alpha.sum(dim=self.dim)
+
+    def forward(self, logit):
+        alpha = self.evidence_func(logit) + 1
+        return alpha / alpha.sum(dim=self.dim, keepdim=True)
+
+
+class BDNet(nn.Module):
+    def __init__(self, in_channels=3, backbone_model=None, training=True, use_edl=False, use_rpl=False, *,
+                 num_classes=21, os_head=False, frame_num=256, evidence="exp", dropout=0.0, precision="bf16x3",
+                 freeze_bn=True, freeze_bn_affine=True):
+        super().__init__()
+        if use_rpl:
+            raise NotImplementedError("the RPL head is a competing baseline, off in every OpenTAL config (SURVEY D10)")
+        if dropout:
+            raise NotImplementedError("dropout is 0 in every OpenTAL config (SURVEY D6)")
+        # The head's library convolutions must not silently drop to TF32 (torch's default for cuDNN convs): single-pass
+        # TF32 alone costs ~1e-3 relative at the outputs, the whole error budget of the path.
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        self.os_head = os_head
+        self.num_classes = num_classes - 1 if os_head else num_classes       # BDNet.py:440
+        self.coarse_pyramid_detection = CoarsePyramid([832, 1024], self.num_classes, frame_num, os_head)
+        self.reset_params()
+        self.backbone = I3DBackbone(in_channels, precision=precision, freeze_bn=freeze_bn,
+                                    freeze_bn_affine=freeze_bn_affine)
+        self.boundary_max_pooling = BoundaryMaxPooling()
+        self._training = training
+        if training and backbone_model is not None:
+            self.load_pretrained_weight(backbone_model)
+        self.scales = [1, 4, 4]
+        self.use_edl = use_edl
+        self.evidence = evidence
+        if use_edl:
+            self.out_layer = DirichletLayer(evidence, dim=-1)
+        self.use_rpl = False
+
+    @classmethod
+    def from_config(cls, config: dict, **kw):
+        """Map the reference's yaml keys (AFSD/common/config.py, BDNet.py:12-18) to constructor arguments."""
+        m = config.get("model", {})
+        return cls(in_channels=m.get("in_channels", 3), backbone_model=kw.pop("backbone_model", m.get("backbone_model")),
+                   num_classes=config["dataset"]["num_classes"], os_head=m.get("os_head", False),
+                   evidence=m.get("evidence", "exp"), dropout=m.get("dropout", 0.0),
+                   frame_num=config["dataset"]["training"]["clip_length"],
+                   freeze_bn=m.get("freeze_bn", True), freeze_bn_affine=m.get("freeze_bn_affine", True), **kw)
+
+    def load_pretrained_weight(self, model_path):
+        """I3D_BackBone.load_pretrained_weight (BDNet.py:35-37): Kinetics I3D state_dict, strict=False."""
+        sd = torch.load(model_path, map_location="cpu")
+        self.backbone._model.load_state_dict(sd, strict=False)
+
+    @staticmethod
+    def weight_init(m):
+        """Glorot-uniform conv weights, zero bias (BDNet.py:460-473)."""
+        if isinstance(m, (nn.Conv1d, nn.Conv2d, nn.Conv3d)):
+            fan_in, fan_out = nn.init._calculate_fan_in_and_fan_out(m.weight)
+            limit = math.sqrt(3.0 / max(1.0, (fan_in + fan_out) / 2.0))
+            nn.init.uniform_(m.weight, -limit, limit)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def reset_params(self):
+        for m in self.modules():
+            self.weight_init(m)
+
+    def forward(self, x, proposals=None, ssl=False, get_feat=False, forced_segments=None):
+        feat_dict = self.backbone(x)
+        if ssl:
+            top_feat = self.coarse_pyramid_detection(feat_dict, ssl=True)
+            # BDNet.py:482-503.  The reference indexes segments of sample 0 for every sample (only defined for batch 1,
+            # SURVEY D11); here the proposals of sample 0 are broadcast explicitly.
+            dec = proposals[0].unsqueeze(0)
+            plen = dec[:, :, 1:] - dec[:, :, :1] + 1.0
+            inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
+            fs = torch.cat([torch.round(dec[:, :, :1] - outl), torch.round(dec[:, :, :1] + inl),
+                            torch.round(dec[:, :, 1:] - inl), torch.round(dec[:, :, 1:] + outl)], dim=-1)
+            anchor, positive, negative = [], [], []
+            for i in range(3):
+                seg = (fs / self.scales[i]).expand(top_feat[i].size(0), -1, -1).contiguous()
+                bound = self.boundary_max_pooling(top_feat[i].contiguous(), seg)
+                nd = bound.size(1) // 2
+                anchor.append(bound[:, nd:, 0])
+                positive.append(bound[:, :nd, 1])
+                negative.append(bound[:, :nd, 2])
+            return anchor, positive, negative
+        out = self.coarse_pyramid_detection(feat_dict, get_feat=get_feat, forced_segments=forced_segments)
+        if self.use_edl:
+            out["unct"] = self.out_layer.compute_uncertainty(out["conf"])
+            out["prop_unct"] = self.out_layer.compute_uncertainty(out["prop_conf"])
+        return out

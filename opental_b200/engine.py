@@ -1,0 +1,191 @@
+"""Training step of the OpenTAL hot path on one B200 per process: forward -> MultiSegmentLoss + boundary BCE ->
+backward -> (data-parallel gradient all-reduce over NCCL) -> fused Adam.
+
+Replaces the body of `run_one_epoch` / `forward_one_epoch` (AFSD/thumos14/train.py:164-252) for the non-SSL pass:
+the cost is `lw*loss_l + cw*loss_c + lw*loss_prop_l + cw*loss_prop_c + ctw*loss_ct + loss_start + loss_end
+(+ actw*loss_act + actw*loss_prop_act)` (train.py:226-235), the optimizer is Adam with L2-in-gradient weight decay
+over every trainable parameter (train.py:321-323; frozen BN affine parameters are skipped, BDNet.py:47-49).
+
+All trainable parameters live in two flat fp32 buffers (backbone conv weights in kernel layout, head parameters in
+registration order); their gradients live in two matching flat buffers that the parameters' .grad alias.  A step is
+therefore: zero two buffers, forward/backward, at most two all-reduces, two fused Adam launches.  The head's
+all-reduce is launched when the backbone's backward starts, so the 130 MB of head gradients cross NVLink while
+the tensor cores work through the backbone; the backbone's 49 MB follow at the end.  No value is read back to the
+host inside a step; losses are returned as device tensors.
+
+Data-parallel semantics: clips shard across ranks, gradients are summed by NCCL and divided by the
+world size inside the Adam kernel.  Loss normalisers (N, PN, AN), the actionness top-M selection and the IBM EMA are
+per-rank, which differs from "the reference at batch 8*W on one GPU" exactly as documented in DESIGN.md.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .bdnet import BDNet
+from .multisegment_loss import MultiSegmentLoss, pad_targets, training_cost
+
+
+class FlatParams:
+    """Re-homes a list of parameters into one flat fp32 buffer (+ a flat gradient buffer their .grad alias)."""
+
+    def __init__(self, params: list[nn.Parameter]):
+        self.params = params
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4            # 16-byte alignment of every block
+        self.offsets, self.total = offs, total
+        self.w = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(params, offs):
+            view = self.w[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.g[o:o + p.numel()].view(p.shape)
+
+    def rebind(self) -> None:
+        """Undo a zero_grad(set_to_none=True) or a foreign .grad assignment."""
+        for p, o in zip(self.params, self.offsets):
+            want = self.g.data_ptr() + 4 * o
+            if p.grad is None or p.grad.data_ptr() != want:
+                view = self.g[o:o + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+
+
+class Trainer:
+    def __init__(self, net: BDNet, criterion: MultiSegmentLoss, *, lr=1e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, process_group=None):
+        self.net, self.criterion = net, criterion
+        self.lw, self.cw, self.ctw, self.actw = lw, cw, ctw, actw
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        dev = next(net.coarse_pyramid_detection.parameters()).device
+        assert dev.type == "cuda", "the training step runs on a CUDA device (no CPU fallback)"
+        self.device = dev
+        bb = net.backbone
+        self.bb_w, self.bb_g = bb.flat_parameters(dev)
+        bb._bind_grads()
+        bb_ids = {id(p) for p in bb.parameters()}
+        head = [p for p in net.parameters() if p.requires_grad and id(p) not in bb_ids]
+        self.head = FlatParams(head)
+        self.state = [dict(m=torch.zeros_like(t), v=torch.zeros_like(t)) for t in (self.bb_w, self.head.w)]
+        self.step_count = 0
+        self._head_work = None
+        bb.on_backward_start = self._launch_head_allreduce if self.world > 1 else None
+
+    # ---------------------------------------------------------------------------------------------- data parallel
+    def _launch_head_allreduce(self) -> None:
+        self._head_work = dist.all_reduce(self.head.g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        if self.world > 1:
+            for t in (self.bb_w, self.head.w, self.net.backbone.flat_bn):
+                dist.broadcast(t, src, group=self.pg)
+
+    # ---------------------------------------------------------------------------------------------- one step
+    def zero_grad(self) -> None:
+        self.net.backbone._bind_grads()
+        self.head.rebind()
+        self.bb_g.zero_()
+        self.head.g.zero_()
+
+    def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor):
+        out = self.net(clips)
+        losses = self.criterion(out, targets)
+        cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw)
+        cost.backward()
+        return cost.detach(), losses, ls.detach(), le.detach()
+
+    def step(self, clips: torch.Tensor, targets, scores: torch.Tensor):
+        """clips [B,3,T,H,W] fp32 on the device, targets: list of [N_i,3] or padded (tensor, mask), scores [B,2,T]."""
+        self.zero_grad()
+        cost, losses, ls, le = self.forward_backward(clips, targets, scores)
+        if self.world > 1:
+            if self._head_work is None:
+                self._launch_head_allreduce()
+            dist.all_reduce(self.bb_g, op=dist.ReduceOp.SUM, group=self.pg)
+            self._head_work.wait()
+            self._head_work = None
+        self.step_count += 1
+        for (w, g), st in zip(((self.bb_w, self.bb_g), (self.head.w, self.head.g)), self.state):
+            ops.adam_step(w, g, st["m"], st["v"], lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
+                          grad_scale=1.0 / self.world, step=self.step_count)
+        return cost, losses, ls, le
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic workload (SURVEY §8d conventions) — shared by bench.py, smoke() and the tests
+# ----------------------------------------------------------------------------------------------------------
+def synthetic_clip_u8(index: int, rank: int = 0, frames: int = 256) -> torch.Tensor:
+    """uint8 [T,112,112,3] i.i.d. uniform pixels, the npy format of AFSD/common/video2npy.py:61-74."""
+    g = torch.Generator().manual_seed(1000 * rank + index)
+    return torch.randint(0, 256, (frames, 112, 112, 3), generator=g, dtype=torch.uint8)
+
+
+def normalise_clip(px: torch.Tensor, crop: int = 96) -> torch.Tensor:
+    """centre crop + (x/255)*2-1 -> fp32 [3,T,crop,crop] (thumos_dataset.py:261-263)."""
+    o = (112 - crop) // 2
+    px = px[:, o:o + crop, o:o + crop, :]
+    return (px.permute(3, 0, 1, 2).float() / 255.0) * 2.0 - 1.0
+
+
+def synthetic_targets(index: int, rank: int = 0, num_classes: int = 15) -> torch.Tensor:
+    g = torch.Generator().manual_seed(7_000_000 + 1000 * rank + index)
+    rows = []
+    for j in range(2):
+        s = 0.10 + 0.45 * j + (torch.rand((), generator=g).item() * 0.06 - 0.03)
+        e = s + 0.25 + (torch.rand((), generator=g).item() * 0.06 - 0.03)
+        lab = int(torch.randint(1, num_classes + 1, (), generator=g).item())
+        rows.append([s, e, float(lab)])
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+def synthetic_scores(targets: torch.Tensor, frames: int = 256) -> torch.Tensor:
+    """start/end score maps [2,T] (thumos_dataset.py:110-120)."""
+    scores = torch.zeros(2, frames)
+    for s, e, _ in targets.tolist():
+        s_f, e_f = s * frames, e * frames
+        half = max((e_f - s_f) / 10.0, 2.0)
+        for row, centre in ((0, s_f), (1, e_f)):
+            lo = max(int(round(centre - half)), 0)
+            hi = min(int(round(centre + half)), frames - 1)
+            scores[row, lo:hi + 1] = 1.0
+    return scores
+
+
+OPENTAL_EDL_CONFIG = dict(evidence="exp", loss_type="log", with_ibm=True, ibm_start=10, momentum=0.99, num_bins=50,
+                          iou_aware=True)          # configs/thumos14_opental_final.yaml:38-49
+OPENTAL_ACT_CONFIG = dict(weight=0.0, margin=1.0)  # :50-52
+
+
+def build_opental(device="cuda", precision="bf16x3", frame_num=256, epoch=1):
+    """BDNet + MultiSegmentLoss as constructed for configs/thumos14_opental_final.yaml --open_set."""
+    net = BDNet(in_channels=3, training=True, use_edl=True, num_classes=16, os_head=True, frame_num=frame_num,
+                precision=precision).to(device)
+    crit = MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True,
+                            act_config=OPENTAL_ACT_CONFIG, clip_length=frame_num).to(device)
+    crit.cls_loss.epoch = epoch
+    net.train()
+    return net, crit
+
+
+def smoke_step() -> None:
+    """One tiny BDNet training step on cuda:0 (short 64-frame clip would break the 256-frame head, so: one full clip)."""
+    torch.manual_seed(0)
+    net, crit = build_opental()
+    tr = Trainer(net, crit)
+    clip = normalise_clip(synthetic_clip_u8(0)).unsqueeze(0).cuda()
+    tgt = [synthetic_targets(0).cuda()]
+    sc = synthetic_scores(tgt[0].cpu()).unsqueeze(0).cuda()
+    cost, losses, ls, le = tr.step(clip, tgt, sc)
+    torch.cuda.synchronize()
+    vals = [float(cost)] + [float(v) for v in losses]
+    assert all(v == v and abs(v) < 1e6 for v in vals), vals
+    print("smoke training step ok: cost %.4f, losses %s" % (vals[0], ["%.4f" % v for v in vals[1:]]))

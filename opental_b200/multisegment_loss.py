@@ -1,0 +1,327 @@
+"""MultiSegmentLoss / EvidenceLoss / ActionnessLoss / FocalLoss with the reference's API, restructured for the GPU.
+
+Reference: AFSD/thumos14/multisegment_loss.py:70-259 and AFSD/thumos14/cls_loss.py (FocalLoss_Ori :6-78, EvidenceLoss
+:81-285, ActionnessLoss :288-339).  Same constructor arguments, same 7-tuple, same mutable `cls_loss.epoch` /
+`cls_loss.total_epoch` / `cls_loss.weight_accum` state — but a different execution model:
+
+  * the reference loops over the batch in Python, gathers positives with boolean masks (dynamic shapes -> a
+    device->host sync per gather), and walks the 50 IBM bins with `.item()` (about 100 syncs per step);
+  * here every term is a fixed-shape masked reduction over all B x 126 priors: prior<->GT matching is one batched
+    op over zero-padded targets, the IBM per-bin EMA is a one-hot segmented mean, the actionness top-M selection is
+    a rank comparison against a device scalar.  Nothing reads a value back to the host, so the whole loss can be
+    enqueued behind the head (and captured in a CUDA graph).
+The arithmetic per element follows the reference line by line (cited inline); summation order differs, which is
+fp32 rounding noise (tests/ check 1e-5 relative against the oracle and the reference-generated golden values).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_EPS = torch.finfo(torch.float32).eps
+
+
+def _iou(pred, target):
+    """1-D IoU of (left, right) offset pairs, last dim 2 (multisegment_loss.py:20-36)."""
+    inter = torch.min(pred[..., 0], target[..., 0]) + torch.min(pred[..., 1], target[..., 1])
+    union = (target[..., 0] + target[..., 1]) + (pred[..., 0] + pred[..., 1]) - inter
+    return inter / union.clamp(min=_EPS), union
+
+
+def _giou_loss(pred, target):
+    """1 - GIoU (multisegment_loss.py:40-43)."""
+    iou, union = _iou(pred, target)
+    hull = torch.max(pred[..., 0], target[..., 0]) + torch.max(pred[..., 1], target[..., 1])
+    return 1.0 - (iou - (hull - union) / hull.clamp(min=_EPS))
+
+
+def pad_targets(targets, device=None):
+    """list of B tensors [N_i,3] (start, end, label; normalised) -> ([B,G,3] zero padded, [B,G] valid mask)."""
+    if isinstance(targets, (tuple, list)) and len(targets) == 2 and torch.is_tensor(targets[0]) and targets[0].dim() == 3:
+        return targets
+    B = len(targets)
+    G = max(1, max(int(t.shape[0]) for t in targets))
+    device = device or targets[0].device
+    padded = torch.zeros(B, G, 3, dtype=torch.float32)
+    valid = torch.zeros(B, G, dtype=torch.bool)
+    for b, t in enumerate(targets):
+        n = int(t.shape[0])
+        if n:
+            padded[b, :n] = t.detach().to("cpu", torch.float32)
+            valid[b, :n] = True
+    return padded.to(device, non_blocking=True), valid.to(device, non_blocking=True)
+
+
+class FocalLoss_Ori(nn.Module):
+    """Focal loss on softmax probabilities with per-class alpha (cls_loss.py:6-78).  `weight` masks samples."""
+
+    def __init__(self, num_class, alpha=None, gamma=2, balance_index=-1, size_average=True):
+        super().__init__()
+        self.num_class, self.gamma, self.size_average, self.eps = num_class, gamma, size_average, 1e-6
+        if alpha is None:
+            alpha = [0.25, 0.75]
+        if isinstance(alpha, (list, tuple)):
+            assert len(alpha) == num_class
+            a = torch.tensor(list(alpha), dtype=torch.float32)
+        elif isinstance(alpha, (float, int)):
+            assert 0 < alpha < 1.0 and balance_index > -1
+            a = torch.ones(num_class) * (1 - alpha)
+            a[balance_index] = alpha
+        else:
+            a = alpha
+        self.register_buffer("alpha", a, persistent=False)
+        self.epoch, self.total_epoch = 0, 25
+
+    def forward(self, prob, target, weight=None):
+        target = target.view(-1, 1)
+        pt = prob.gather(1, target).view(-1) + self.eps
+        alpha = self.alpha.to(prob.device).gather(0, target.view(-1))
+        loss = -1 * torch.pow(1.0 - pt, self.gamma) * (alpha * pt.log())
+        if weight is not None:
+            loss = torch.where(weight, loss, torch.zeros_like(loss))
+        return loss.mean() if self.size_average else loss.sum()
+
+
+class EvidenceLoss(nn.Module):
+    """EDL classification loss, loss_type 'log' / 'digamma', evidence exp / relu / softplus, optional IBM
+    re-weighting and IoU-aware calibration (cls_loss.py:81-285).  The GHM / IB / focal-EDL / mse branches are ablations
+    outside the OpenTAL configs: NotImplementedError."""
+
+    def __init__(self, num_cls, cfg, size_average=False):
+        super().__init__()
+        self.num_cls = num_cls
+        self.loss_type = cfg["loss_type"]
+        self.evidence = cfg["evidence"]
+        if self.loss_type not in ("log", "digamma"):
+            raise NotImplementedError(f"loss_type {self.loss_type}")
+        for k in ("with_focal", "with_ghm", "with_ibloss"):
+            if cfg.get(k, False):
+                raise NotImplementedError(f"{k} is an ablation branch outside the OpenTAL configs")
+        self.soft_label = cfg.get("soft_label", 0.0)
+        self.iou_aware = cfg.get("iou_aware", False)
+        self.with_ibm = cfg.get("with_ibm", False)
+        if self.with_ibm:
+            self.ibm_start = cfg.get("ibm_start", 0)
+            self.num_bins = cfg.get("num_bins", 50)
+            self.momentum = cfg.get("momentum", 0.99)
+            # explicit buffer (the reference keeps it outside the state_dict); persistent so it is saved
+            self.register_buffer("weight_accum", torch.ones(self.num_bins))
+        self.epoch, self.total_epoch = 0, 25
+        self.size_average = size_average
+
+    def evidence_func(self, logit):
+        if self.evidence == "relu":
+            return F.relu(logit)
+        if self.evidence == "exp":
+            return torch.exp(torch.clamp(logit, -10, 10))
+        return F.softplus(logit)
+
+    def iou_calib(self, logits, ious, mean=False):
+        """cls_loss.py:120-129 (the reference patches `ious` in place; a functional where() is equivalent)."""
+        ious = torch.where(ious < 0, torch.full_like(ious, 1e-3), ious)
+        unc = self.num_cls / (self.evidence_func(logits) + 1).sum(dim=-1)
+        reg = -ious * torch.log(1 - unc) - (1 - ious) * torch.log(unc)
+        return reg.mean() if mean else reg.sum()
+
+    def forward(self, logit, target, weight=None):
+        """logit [M,K]; target [M] in 0..K-1; weight [M] bool = which rows are real samples (masked formulation of the
+        reference's boolean gather).  Returns the summed (or mean) loss."""
+        func = torch.log if self.loss_type == "log" else torch.digamma
+        target = target.view(-1)
+        M = logit.shape[0]
+        if weight is None:
+            weight = torch.ones(M, dtype=torch.bool, device=logit.device)
+        y = F.one_hot(target, self.num_cls).to(logit.dtype)
+        if self.soft_label:
+            y = torch.where(y == 1, torch.full_like(y, 1 - self.soft_label), torch.full_like(y, self.soft_label / (self.num_cls - 1)))
+        alpha = self.evidence_func(logit) + 1
+        S = alpha.sum(dim=1, keepdim=True)
+        per = (y * (func(S) - func(alpha))).sum(dim=1)
+        if self.with_ibm and self.epoch >= self.ibm_start:
+            with torch.no_grad():       # cls_loss.py:257-270
+                feat_norm = logit.abs().sum(1)
+                a = alpha.detach()
+                unc = self.num_cls / a.sum(dim=-1, keepdim=True)
+                grad_norm = ((1 / a - unc).abs() * y).sum(dim=1)
+                grad_hat = grad_norm * feat_norm
+                bins = torch.ceil(grad_norm * self.num_bins).long()                 # 1..num_bins (0 if grad_norm == 0)
+                onehot = F.one_hot(bins.clamp(0, self.num_bins), self.num_bins + 1)[:, 1:].to(logit.dtype)
+                onehot = onehot * weight.to(logit.dtype).unsqueeze(1)
+                cnt = onehot.sum(0)
+                mean = (onehot * grad_hat.unsqueeze(1)).sum(0) / cnt.clamp(min=1)
+                acc = self.weight_accum.to(logit.device)
+                acc = torch.where(cnt > 0, self.momentum * acc + (1 - self.momentum) * mean, acc)
+                self.weight_accum = acc
+                w = acc[(bins - 1) % self.num_bins]                                 # bin 0 -> index -1 (python wrap)
+            per = w * per
+        per = torch.where(weight, per, torch.zeros_like(per))
+        if self.size_average:
+            return per.sum() / weight.sum().clamp(min=1)
+        return per.sum()
+
+
+class ActionnessLoss(nn.Module):
+    """Positive-unlabeled actionness loss (cls_loss.py:288-339): BCE over the positives and the top-M lowest-scoring
+    negatives, M = min(#pos, #neg) - 1, plus a rank term.  Returns (loss, #pos + #kept negatives) as tensors."""
+
+    def __init__(self, size_average=False, cfg=None):
+        super().__init__()
+        self.size_average = size_average
+        self.weight = cfg.get("weight", 0.1) if cfg is not None else 0.1
+        self.margin = cfg.get("margin", 1.0) if cfg is not None else 1.0
+
+    def forward(self, logit, target):
+        pred = logit.reshape(-1)
+        label = target.reshape(-1).to(pred.dtype)
+        pos = label > 0
+        neg = ~pos
+        npos = pos.sum()
+        nneg = neg.sum()
+        top_m = torch.minimum(npos, nneg) - 1
+        use_top = top_m > 0
+        # rank of every negative among the negatives, ascending by score (positives pushed to the end)
+        key = torch.where(neg, pred.detach(), torch.full_like(pred, float("inf")))
+        order = key.argsort()
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(order.numel(), device=order.device)
+        kept_neg = neg & (rank < top_m)
+        sel = torch.where(use_top, pos | kept_neg, torch.ones_like(pos))
+        bce = F.binary_cross_entropy_with_logits(pred, label, reduction="none")
+        bce = torch.where(sel, bce, torch.zeros_like(bce))
+        count = sel.sum()
+        loss = bce.sum() / count.clamp(min=1) if self.size_average else bce.sum()
+        if self.weight:
+            neg_max = torch.where(neg, pred, torch.full_like(pred, -1e30)).max()
+            pos_max = torch.where(pos, pred, torch.full_like(pred, -1e30)).max().detach()
+            rank_loss = torch.clamp(self.margin - neg_max + pos_max, min=0.0)
+            loss = loss + self.weight * torch.where(use_top, rank_loss, torch.zeros_like(rank_loss))
+        return loss, count
+
+
+class MultiSegmentLoss(nn.Module):
+    def __init__(self, num_classes, overlap_thresh, negpos_ratio, use_gpu=True, cls_loss_type="focal", edl_config=None,
+                 rpl_config=None, os_head=False, act_config=None, size_average=False, *, clip_length=256):
+        super().__init__()
+        self.num_classes = num_classes
+        self.overlap_thresh = overlap_thresh
+        self.negpos_ratio = negpos_ratio
+        self.use_gpu = use_gpu
+        self.cls_loss_type = cls_loss_type
+        self.clip_length = clip_length          # the reference reads config['dataset']['training']['clip_length'] (:110)
+        if cls_loss_type == "focal":
+            self.cls_loss = FocalLoss_Ori(num_classes, balance_index=0, size_average=size_average, alpha=0.25)
+        elif cls_loss_type == "edl":
+            self.cls_loss = EvidenceLoss(num_classes, edl_config, size_average=size_average)
+        else:
+            raise NotImplementedError("RPLoss is a competing baseline outside the OpenTAL configs (SURVEY §2 row 6)")
+        self.iou_aware = cls_loss_type == "edl" and self.cls_loss.iou_aware
+        self.os_head = os_head
+        if os_head:
+            self.act_loss = ActionnessLoss(size_average=size_average, cfg=act_config)
+        self.size_average = size_average
+
+    @torch.no_grad()
+    def match(self, loc, priors, tgt, valid):
+        """Prior <-> ground-truth matching for the whole batch (multisegment_loss.py:120-153)."""
+        clip = float(self.clip_length)
+        c = priors[:, 0].view(1, -1, 1)                                   # [1,P,1]
+        left = (c - tgt[:, None, :, 0]) * clip                           # [B,P,G]
+        right = (tgt[:, None, :, 1] - c) * clip
+        big = clip * 2
+        area = left + right
+        area = torch.where((left < 0) | (right < 0), torch.full_like(area, big), area)
+        area = torch.where(valid[:, None, :], area, torch.full_like(area, big * 2))   # padding never wins a tie
+        best, idx = area.min(dim=2)                                      # first minimum, like the reference
+        sel = idx.unsqueeze(-1)
+        t_start = tgt[:, :, 0].gather(1, idx)
+        t_end = tgt[:, :, 1].gather(1, idx)
+        lab = tgt[:, :, 2].long().gather(1, idx)
+        cc = priors[:, 0].view(1, -1)
+        loc_t = torch.stack([(cc - t_start) * clip, (t_end - cc) * clip], dim=-1)      # [B,P,2]
+        conf_t = torch.where(best >= big, torch.zeros_like(lab), lab)
+        iou, _ = _iou(loc, loc_t)
+        prop_conf_t = torch.where(iou < self.overlap_thresh, torch.zeros_like(conf_t), conf_t)
+        w = (loc[..., 0] + loc[..., 1]).unsqueeze(-1)
+        prop_loc_t = (loc_t - loc) / (0.5 * w)
+        del sel
+        return loc_t, conf_t, prop_loc_t, prop_conf_t, iou
+
+    def forward(self, output_dict, targets, pre_locs=None):
+        loc, conf, ploc, pconf, center, priors = (output_dict[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))
+        act, pact = output_dict.get("act"), output_dict.get("prop_act")
+        B, P = loc.shape[:2]
+        K = self.num_classes
+        tgt, valid = pad_targets(targets, loc.device)
+        loc_t, conf_t, prop_loc_t, prop_conf_t, iou = self.match(loc.detach(), priors, tgt, valid)
+        pos, ppos = conf_t > 0, prop_conf_t > 0
+        zero = loc.new_zeros(())
+
+        # localisation: GIoU on positives, L1 on refined positives, IoU-quality BCE (:155-189)
+        loss_l = torch.where(pos, _giou_loss(loc, loc_t), zero).sum()
+        loss_prop_l = torch.where(ppos.unsqueeze(-1), (ploc - prop_loc_t).abs(), zero).sum()
+        cur = 0.5 * (loc[..., 0] + loc[..., 1]).unsqueeze(-1) * ploc + loc
+        q = _iou(cur, loc_t)[0].clamp(min=0)
+        ct = F.binary_cross_entropy_with_logits(center.reshape(B, P), q, reduction="none")
+        loss_ct = torch.where(pos, ct, zero).sum()
+        if self.size_average:
+            loss_l = loss_l / pos.sum().clamp(min=1)
+            loss_prop_l = loss_prop_l / (2 * ppos.sum()).clamp(min=1)
+            loss_ct = loss_ct / pos.sum().clamp(min=1)
+
+        # classification, coarse and refined (:191-232)
+        def cls(logits, labels, mask):
+            logits = logits.reshape(-1, K)
+            labels, mask = labels.reshape(-1), mask.reshape(-1)
+            if self.cls_loss_type == "focal":
+                logits = F.softmax(logits, dim=1)
+            if self.os_head:
+                return self.cls_loss(logits, (labels - 1).clamp(min=0), mask)
+            return self.cls_loss(logits, labels, None)
+
+        loss_c = cls(conf, conf_t, pos)
+        loss_act = loss_prop_act = None
+        if self.os_head:
+            loss_act, AN = self.act_loss(act.reshape(-1, 1), pos.reshape(-1, 1).float())
+        loss_prop_c = cls(pconf, prop_conf_t, ppos)
+        if self.iou_aware:
+            # The reference flattens its [P,B] iou buffer against [B*P] logits (:116,:146,:236): identical for B == 1,
+            # a mis-pairing for B > 1 that is reproduced here for parity.
+            loss_iouc = self.cls_loss.iou_calib(pconf.reshape(-1, K), iou.t().reshape(-1), mean=True)
+        if self.os_head:
+            loss_prop_act, PAN = self.act_loss(pact.reshape(-1, 1), ppos.reshape(-1, 1).float())
+
+        N = pos.sum().clamp(min=1)
+        PN = ppos.sum().clamp(min=1)
+        if not self.size_average:
+            loss_l, loss_c, loss_ct = loss_l / N, loss_c / N, loss_ct / N
+            loss_prop_l, loss_prop_c = loss_prop_l / PN, loss_prop_c / PN
+        if self.iou_aware:
+            loss_prop_c = loss_prop_c + loss_iouc
+        if self.os_head and not self.size_average:
+            loss_act = loss_act / AN.clamp(min=1)
+            loss_prop_act = loss_prop_act / PAN.clamp(min=1)
+        return loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act
+
+
+def calc_bce_loss(start, end, scores):
+    """tanh -> mean over channels -> BCE (AFSD/thumos14/train.py:152-161)."""
+    s = torch.tanh(start).mean(-1)
+    e = torch.tanh(end).mean(-1)
+    return (F.binary_cross_entropy(s.view(-1), scores[:, 0].contiguous().view(-1), reduction="mean"),
+            F.binary_cross_entropy(e.view(-1), scores[:, 1].contiguous().view(-1), reduction="mean"))
+
+
+def training_cost(output_dict, losses, scores, *, lw=1.0, cw=10.0, ctw=1.0, actw=1.0):
+    """Total cost of one (non-SSL) THUMOS14 training step (train.py:186-200, 226-235)."""
+    loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act = losses
+    ls, le = calc_bce_loss(output_dict["start"], output_dict["end"], scores)
+    sc = F.interpolate(scores, scale_factor=1.0 / 4)
+    a, b = calc_bce_loss(output_dict["start_loc_prop"], output_dict["end_loc_prop"], sc)
+    c, d = calc_bce_loss(output_dict["start_conf_prop"], output_dict["end_conf_prop"], sc)
+    ls = ls + 0.1 * (a + c)
+    le = le + 0.1 * (b + d)
+    cost = lw * loss_l + cw * loss_c + lw * loss_prop_l + cw * loss_prop_c + ctw * loss_ct + ls + le
+    if loss_act is not None:
+        cost = cost + actw * loss_act + actw * loss_prop_act
+    return cost, ls, le

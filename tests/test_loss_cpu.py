@@ -1,0 +1,99 @@
+"""CPU: the product's fixed-shape, sync-free MultiSegmentLoss (opental_b200/multisegment_loss.py; plain torch ops, so it
+runs on CPU tensors too) against the oracle restatement of the reference loss, which itself is pinned to the
+reference-generated golden values (tests/test_oracle_golden.py).  Tolerance 1e-5 relative: only summation order differs."""
+import math
+
+import pytest
+import torch
+
+import opental_oracle as O
+from opental_b200.multisegment_loss import MultiSegmentLoss, training_cost
+from opental_b200.engine import OPENTAL_ACT_CONFIG, OPENTAL_EDL_CONFIG
+
+
+def fake_outputs(B, seed, loc_scale=30.0):
+    g = torch.Generator().manual_seed(seed)
+    P = 126
+    cfg = O.OracleConfig()
+    out = dict(loc=(torch.rand(B, P, 2, generator=g) * loc_scale + 1).requires_grad_(True),
+               conf=torch.randn(B, P, 15, generator=g).requires_grad_(True),
+               prop_loc=(0.3 * torch.randn(B, P, 2, generator=g)).requires_grad_(True),
+               prop_conf=torch.randn(B, P, 15, generator=g).requires_grad_(True),
+               center=torch.randn(B, P, 1, generator=g).requires_grad_(True),
+               priors=torch.cat(O.level_priors(cfg), 0),
+               act=torch.randn(B, P, 1, generator=g).requires_grad_(True),
+               prop_act=torch.randn(B, P, 1, generator=g).requires_grad_(True))
+    return out, cfg
+
+
+def make_crit(epoch, act_weight=0.0):
+    crit = MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True,
+                            act_config=dict(weight=act_weight, margin=1.0))
+    crit.cls_loss.epoch = epoch
+    return crit
+
+
+@pytest.mark.parametrize("B,epoch,act_weight", [(1, 1, 0.0), (1, 11, 0.0), (3, 11, 0.0), (2, 11, 0.1), (4, 1, 0.1)])
+def test_loss_matches_oracle(B, epoch, act_weight):
+    out, cfg = fake_outputs(B, seed=10 * B + epoch)
+    cfg.act_weight = act_weight
+    targets = [O.synthetic_targets(i, num_classes=15) for i in range(B)]
+    if B >= 3:
+        targets[1] = targets[1][:1]                      # ragged number of ground-truth segments
+    state = O.LossState(epoch=epoch)
+    ref = O.multisegment_loss(out, targets, state, cfg)
+    crit = make_crit(epoch, act_weight)
+    got = crit(out, targets)
+    for a, b in zip(got, ref):
+        assert abs(float(a) - float(b)) <= 1e-5 * max(1.0, abs(float(b))), (float(a), float(b))
+    assert torch.allclose(crit.cls_loss.weight_accum, state.weight_accum, atol=1e-6)
+    # gradients of the weighted cost w.r.t. every head output
+    keys = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
+    w = (1, 10, 1, 10, 1, 1, 1)
+    g_ref = torch.autograd.grad(sum(wi * li for wi, li in zip(w, ref)), [out[k] for k in keys], allow_unused=True)
+    g_got = torch.autograd.grad(sum(wi * li for wi, li in zip(w, got)), [out[k] for k in keys], allow_unused=True)
+    for k, a, b in zip(keys, g_got, g_ref):
+        assert torch.allclose(a, b, atol=1e-6, rtol=1e-4), k
+
+
+def test_no_positive_priors():
+    out, cfg = fake_outputs(2, seed=3)
+    targets = [torch.tensor([[1.2, 1.4, 3.0]]), torch.tensor([[1.5, 1.9, 4.0]])]     # outside [0,1]: no prior inside
+    got = make_crit(11)(out, targets)
+    ref = O.multisegment_loss(out, targets, O.LossState(epoch=11), cfg)
+    assert float(got[0]) == 0 and float(got[1]) == 0 and float(got[2]) == 0
+    for a, b in zip(got, ref):
+        assert math.isfinite(float(a)) and abs(float(a) - float(b)) <= 1e-5 * max(1.0, abs(float(b)))
+
+
+def test_training_cost_matches_oracle():
+    out, cfg = fake_outputs(2, seed=5)
+    g = torch.Generator().manual_seed(6)
+    for k, shp in (("start", (2, 256, 256)), ("end", (2, 256, 256)), ("start_loc_prop", (2, 64, 512)),
+                   ("end_loc_prop", (2, 64, 512)), ("start_conf_prop", (2, 64, 512)), ("end_conf_prop", (2, 64, 512))):
+        out[k] = torch.randn(*shp, generator=g).relu()
+    targets = [O.synthetic_targets(i, num_classes=15) for i in range(2)]
+    scores = torch.stack([O.synthetic_scores(t) for t in targets])
+    ref_cost, _ = O.training_cost(out, targets, scores, O.LossState(epoch=1), cfg)
+    crit = make_crit(1)
+    cost, ls, le = training_cost(out, crit(out, targets), scores)
+    assert abs(float(cost) - float(ref_cost)) < 1e-5 * abs(float(ref_cost))
+
+
+def test_focal_configuration():
+    """configs/thumos14.yaml flavour (config 1): 21 classes incl. background, softmax focal loss on every prior."""
+    g = torch.Generator().manual_seed(9)
+    P = 126
+    cfg = O.OracleConfig()
+    out = dict(loc=torch.rand(1, P, 2, generator=g) * 30 + 1, conf=torch.randn(1, P, 21, generator=g),
+               prop_loc=0.3 * torch.randn(1, P, 2, generator=g), prop_conf=torch.randn(1, P, 21, generator=g),
+               center=torch.randn(1, P, 1, generator=g), priors=torch.cat(O.level_priors(cfg), 0), act=None, prop_act=None)
+    crit = MultiSegmentLoss(21, 0.5, 1.0, cls_loss_type="focal")
+    l = crit(out, [O.synthetic_targets(0, num_classes=20)])
+    assert l[5] is None and l[6] is None and all(math.isfinite(float(v)) for v in l[:5])
+    # hand check of the focal term on the coarse logits
+    loc_t, conf_t, *_ = crit.match(out["loc"], out["priors"], *__import__("opental_b200.multisegment_loss", fromlist=["pad_targets"]).pad_targets([O.synthetic_targets(0, num_classes=20)]))
+    p = torch.softmax(out["conf"].view(-1, 21), 1).gather(1, conf_t.view(-1, 1)).view(-1) + 1e-6
+    alpha = torch.where(conf_t.view(-1) == 0, torch.tensor(0.25), torch.tensor(0.75))
+    want = (-(1 - p) ** 2 * alpha * p.log()).sum() / max(int((conf_t > 0).sum()), 1)
+    assert abs(float(l[1]) - float(want)) < 1e-5 * abs(float(want))
