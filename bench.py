@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: THUMOS14 OpenTAL training clips/s on N B200s (one process per GPU, NCCL over NVLink).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16x3|bf16] [--impl reference]
+
+A step = one full training pass over one batch of synthetic clips: BDNet forward (native I3D backbone + head), the
+MultiSegmentLoss (EDL + actionness + regression terms) and the boundary BCE of train.py, backward, gradient all-reduce
+(N > 1) and the fused Adam update.  Workload = BASELINE.json configs[1]/[2]: configs/thumos14_opental_final.yaml
+--open_set, clips 3x256x96x96, batch 8 per GPU, keyed synthetic weights, synthetic uint8 clips/targets/score maps
+(SURVEY §8d).  Prints ONE JSON line (rank 0) — contract in the round prompt; `--impl reference` times the CPU
+restatement of the reference (oracle/) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training clips/sec (THUMOS14 OpenTAL, 3x256x96x96 clips)"
+UNIT = "clips/s"
+FLOP_TRAIN_PER_CLIP = 466.45e9      # fwd + dgrad + wgrad conv FLOPs, fp32 semantics
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="clips per GPU per step")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.3:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle restatement of the reference training step on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_training_steps(steps: int, warmup: int, batch: int = 1):
+    """Times `steps` full training steps (forward, loss, backward; batch `batch`) of the CPU restatement of the
+    reference (oracle/opental_oracle.py: torch CPU fp32 ops, all host threads).  Returns (clips/s, ms/step, cores)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import opental_oracle as O          # bench.py's cpu_baseline / reference arm is allowed to execute oracle/
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(cfg)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and ".bn." not in k else v)
+          for k, v in sd.items()}
+    state = O.LossState(epoch=11)
+    x = torch.stack([O.synthetic_clip(i) for i in range(batch)])
+    targets = [O.synthetic_targets(i, num_classes=cfg.num_classes) for i in range(batch)]
+    scores = torch.stack([O.synthetic_scores(t) for t in targets])
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.bdnet_forward(x, sd, cfg, compat=True)
+        cost, _ = O.training_cost(out, targets, scores, state, cfg)
+        cost.backward()
+        for v in sd.values():
+            if v.is_floating_point() and v.grad is not None:
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    return batch * 1000.0 / ms, ms, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    val, ms, cores = cpu_training_steps(steps, warm, batch=1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "THUMOS14 OpenTAL (configs/thumos14_opental_final.yaml --open_set) training step, clips 3x256x96x96, "
+                               "CPU restatement of the reference (oracle/), batch 1 per step", "batch_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} training steps of 1 clip after {warm} warm-up (forward + loss + backward, torch CPU fp32)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from opental_b200 import _lib, engine, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the native path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    torch.manual_seed(0)
+    net, crit = engine.build_opental(device=dev, precision=args.precision, epoch=11)
+    # keyed synthetic weights would need the oracle; the bench uses the module's own deterministic init (same shapes)
+    tr = engine.Trainer(net, crit, lr=1e-5, weight_decay=1e-3)
+    tr.broadcast_parameters(0)
+
+    # two distinct synthetic batches per rank, host (pinned) and device copies
+    def make_batch(j):
+        idx = [rank * 1000 + j * B + i for i in range(B)]
+        clips = torch.stack([engine.normalise_clip(engine.synthetic_clip_u8(i, rank)) for i in idx])
+        tg = [engine.synthetic_targets(i, rank) for i in idx]
+        sc = torch.stack([engine.synthetic_scores(t) for t in tg])
+        from opental_b200.multisegment_loss import pad_targets
+        tp, tv = pad_targets(tg, device="cpu")
+        return clips.pin_memory(), tp.pin_memory(), tv.pin_memory(), sc.pin_memory()
+
+    host = [make_batch(j) for j in range(2)]
+    devb = [tuple(t.to(dev) for t in hb) for hb in host]
+
+    def step_dev(j):
+        c, tp, tv, sc = devb[j % 2]
+        return tr.step(c, (tp, tv), sc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for j in range(args.warmup):
+        step_dev(j)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    with ops.PROFILE.enabled() as prof:
+        e0.record()
+        for j in range(args.steps):
+            step_dev(j)
+        e1.record()
+        barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    ksum = prof.summary()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = world * B * 1000.0 / ms
+
+    # ---- end to end: pinned host buffers -> H2D every step (prefetched on a copy stream) -> step -> loss read back
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(j):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[j % 2])
+                for d, h in zip(bufs[j % 2], host[j % 2]):
+                    d.copy_(h, non_blocking=True)
+                ready[j % 2].record(copy_stream)
+
+        for ev in consumed:
+            ev.record()
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        barrier()
+        t0 = time.perf_counter()
+        prefetch(0)
+        for j in range(args.steps):
+            if j + 1 < args.steps:
+                prefetch(j + 1)
+            torch.cuda.current_stream().wait_event(ready[j % 2])
+            c, tp, tv, sc = bufs[j % 2]
+            cost, losses, ls, le = tr.step(c, (tp, tv), sc)
+            consumed[j % 2].record()
+            _ = float(cost)                                   # device -> host read of the step's result (4 bytes)
+        barrier()
+        ms_e2e = (time.perf_counter() - t0) * 1000.0 / args.steps
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
+        e2e = {"value": world * B * 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e, "api": "opental_b200.engine.Trainer.step on pinned host fp32 clips (prefetched H2D) + float(cost)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks.get("bf16_tflops_sustained") else "fallback 1.4 PFLOP/s sustained"
+    roof = {}
+    for k, d in ksum.items():
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        hw = 3.0 if args.precision == "bf16x3" else 1.0
+        roof[k] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                   "traffic": None, "launches_per_step": d["launches"] / args.steps,
+                   "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / args.steps / ms,
+                   "executed_tflops": ach * hw, "executed_frac": ach * hw / peak_tf,
+                   "note": f"achieved = algorithmic fp32-semantic conv FLOPs / event-timed kernel time; {args.precision} executes {hw:.0f}x "
+                           f"those FLOPs on the bf16 pipe; peak = {peak_src}"}
+    dominant = max(roof, key=lambda k: roof[k]["ms_per_step"]) if roof else None
+
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        v, cms, cores = cpu_training_steps(2, 1, batch=1)
+        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "2 training steps of 1 clip after 1 warm-up (forward + loss + backward, torch CPU fp32 restatement in oracle/)",
+                    "ms_per_step": cms}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (3 bf16 tensor-core passes, fp32 accumulate; fp32-equivalent ~1e-5)" if args.precision == "bf16x3" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": "THUMOS14 OpenTAL (configs/thumos14_opental_final.yaml --open_set) training step: BDNet fwd + MultiSegmentLoss(edl, "
+                               "IBM, actionness) + boundary BCE + bwd + Adam; clips 3x256x96x96",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "precision": args.precision,
+                   "l2": "per-step inputs (226 MB of clips) and activations (GBs) exceed the 126 MB L2; two alternating batches",
+                   "ssl_pass": False},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "gpu_launches_by_entry_point": dict(_lib.LAUNCHES),
+        "roofline": roof.get(dominant),
+        "roofline_kernel": dominant,
+        "roofline_all": roof,
+        "model_tflops_per_gpu": value / world * FLOP_TRAIN_PER_CLIP / 1e12,
+        "cpu_baseline": cpu_base,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

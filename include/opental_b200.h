@@ -87,6 +87,8 @@ typedef struct otal_conv_desc {
     int dgrad;               /* data-gradient mode: x = output gradient planes [.., Cin = forward Cout], w = the
                                 FORWARD weights [taps][Cin][Cout] read transposed with flipped taps, pt/ph/pw =
                                 k-1-forward pad, Cout = forward Cin.  Stride 1 only. */
+    int y_f32_ncdhw;         /* fp32 destination layout: 0 = NDHWC (out_cstride channels per position), 1 = NCDHW
+                                ([N, out_cstride, To, Ho, Wo], any Cout) — the reference's layout, used by the 1-D head */
     int in_cstride, in_coff;   /* input row width and slice offset, in channels */
     int out_cstride, out_coff; /* output row width and slice offset, in channels (bf16 planes and fp32 alike) */
     const uint16_t* x_hi; const uint16_t* x_lo;   /* bf16 bit patterns */
@@ -184,6 +186,12 @@ OTAL_API int otal_relu_bn_bwd_split(const float* g, const uint16_t* y_hi, const 
  * AFSD/thumos14/train.py:321-323.  g is multiplied by grad_scale first (1/world_size after a summing all-reduce). */
 OTAL_API int otal_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                             float eps, float weight_decay, float grad_scale, int step, void* stream);
+
+/* [B,C,T] fp32 (the reference's conv1d layout) -> channels-last bf16 planes [B,Ttot,Cpad]: element (b,c,t) lands at
+ * position offset + t*dilate, channel c.  With dilate > 1 or Cpad > C the caller zero-fills the planes first (this is
+ * the zero-upsampled output gradient a stride-2 conv's dgrad reads).  lo may be NULL. */
+OTAL_API int otal_ncl_to_nlc_split(const float* x, uint16_t* hi, uint16_t* lo, int B, int C, int T, int Cpad, int Ttot,
+                                   int dilate, int offset, void* stream);
 
 /* fp32 -> (hi, lo) bf16 planes, elementwise over n values (layout preserving). lo may be NULL. */
 OTAL_API int otal_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);

@@ -29,7 +29,7 @@ class ConvDesc(Structure):
     """Mirror of `otal_conv_desc` (include/opental_b200.h)."""
 
     _fields_ = (_ints("N", "T", "H", "W", "Cin", "Cout", "kt", "kh", "kw", "pt", "ph", "pw", "tT", "tH", "tW",
-                      "sT", "sH", "sW", "nsplit", "relu", "accumulate", "dgrad",
+                      "sT", "sH", "sW", "nsplit", "relu", "accumulate", "dgrad", "y_f32_ncdhw",
                       "in_cstride", "in_coff", "out_cstride", "out_coff")
                 + _ptrs("x_hi", "x_lo", "w_hi", "w_lo", "scale", "shift", "y_hi", "y_lo", "y_f32"))
 
@@ -84,6 +84,7 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,
                                c_float, c_float, c_int, c_void_p]),
+    "otal_ncl_to_nlc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_merge_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_ncdhw_to_ndhwc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -121,6 +122,14 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed: {ERR_NAMES.get(rc, rc)}: {last_error()}")
 
 
+LAUNCHES = {}      # entry point -> number of successful calls (each launches at least one CUDA kernel of this library)
+
+
 def call(name: str, *args) -> None:
     """Call an int-returning entry point and raise RuntimeError on a non-zero code."""
     check(getattr(load(), name)(*args), name)
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
+
+
+def launch_count() -> int:
+    return sum(LAUNCHES.values())

@@ -24,7 +24,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .backbone import I3DBackbone, same_pad_front
+from .backbone import I3DBackbone
+from .headconv import HeadConvStore, head_conv
 from .prop_pooling import BoundaryMaxPooling
 
 LAYER_NUM = 6        # BDNet.py:20
@@ -38,8 +39,12 @@ class Unit1D(nn.Module):
         super().__init__()
         self.conv1d = nn.Conv1d(in_channels, output_channels, kernel_shape, stride, padding=0, bias=True)
         self._k, self._s = kernel_shape, stride
+        self._native = None      # (HeadConvStore, record) once CoarsePyramid has registered this conv
 
     def forward(self, x):
+        if self._native is not None:
+            store, rec = self._native
+            return head_conv(x, self.conv1d.weight, self.conv1d.bias, store, rec, self._s)
         t = x.shape[2]
         total = max(self._k - self._s, 0) if t % self._s == 0 else max(self._k - t % self._s, 0)
         if total:
@@ -55,9 +60,14 @@ class Unit3DValid(nn.Module):
         super().__init__()
         assert kernel_shape[0] == 1
         self.conv3d = nn.Conv3d(in_channels, output_channels, kernel_shape, bias=True)
+        self._native = None
 
     def forward(self, x):
-        return self.conv3d(x)
+        """x: NCDHW view of the backbone's channels-last feature map; returns [B,Cout,T] (H, W collapsed)."""
+        if self._native is not None:
+            store, rec = self._native
+            return head_conv(x.permute(0, 2, 3, 4, 1), self.conv3d.weight, self.conv3d.bias, store, rec, 1)
+        return self.conv3d(x).squeeze(-1).squeeze(-1)
 
 
 def _unit_gn(unit, channels):
@@ -98,7 +108,7 @@ class ProposalBranch(nn.Module):
 class CoarsePyramid(nn.Module):
     """BDNet.py:117-432 (OpenTAL configuration: no RPL head, no transformer, dropout 0)."""
 
-    def __init__(self, feat_channels, num_classes, frame_num=256, os_head=False):
+    def __init__(self, feat_channels, num_classes, frame_num=256, os_head=False, precision="bf16x3", native_convs=True):
         super().__init__()
         out_channels = CONV_CHANNELS
         self.num_classes = num_classes
@@ -141,6 +151,16 @@ class CoarsePyramid(nn.Module):
             self.priors.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32).view(-1, 1))
             t = t // 2
         self._prior_cache = {}
+        # every head conv on the tensor-core kernels, weights re-homed into one packed flat buffer (headconv.py);
+        # native_convs=False keeps torch's library convs (debugging aid, never selected implicitly)
+        self.conv_store = None
+        if native_convs:
+            self.conv_store = HeadConvStore(precision)
+            for m in self.modules():
+                if isinstance(m, Unit1D):
+                    m._native = (self.conv_store, self.conv_store.register(m.conv1d.weight, m.conv1d.bias, "conv1d"))
+                elif isinstance(m, Unit3DValid):
+                    m._native = (self.conv_store, self.conv_store.register(m.conv3d.weight, m.conv3d.bias, "valid3d"))
 
     def _priors_on(self, device):
         if device not in self._prior_cache:
@@ -171,14 +191,16 @@ class CoarsePyramid(nn.Module):
         if get_feat:
             raise NotImplementedError("get_feat is an analysis-only path (SURVEY D10)")
         x1, x2 = feat_dict["Mixed_4f"], feat_dict["Mixed_5c"]
+        if self.conv_store is not None:
+            self.conv_store.prepare(x1.device)
         B = x1.size(0)
         K = self.num_classes
         feats = []
         for i, conv in enumerate(self.pyramids):
             if i == 0:
-                x = conv(x1).squeeze(-1).squeeze(-1)
+                x = conv(x1)
             elif i == 1:
-                x = conv(x2).squeeze(-1).squeeze(-1)
+                x = conv(x2)
                 feats[-1] = feats[-1] + F.interpolate(x, feats[-1].shape[2:], mode="nearest")
             else:
                 x = conv(x)
@@ -258,7 +280,7 @@ class DirichletLayer(nn.Module):
 class BDNet(nn.Module):
     def __init__(self, in_channels=3, backbone_model=None, training=True, use_edl=False, use_rpl=False, *,
                  num_classes=21, os_head=False, frame_num=256, evidence="exp", dropout=0.0, precision="bf16x3",
-                 freeze_bn=True, freeze_bn_affine=True):
+                 freeze_bn=True, freeze_bn_affine=True, native_head_convs=True):
         super().__init__()
         if use_rpl:
             raise NotImplementedError("the RPL head is a competing baseline, off in every OpenTAL config (SURVEY D10)")
@@ -270,7 +292,8 @@ class BDNet(nn.Module):
         torch.backends.cuda.matmul.allow_tf32 = False
         self.os_head = os_head
         self.num_classes = num_classes - 1 if os_head else num_classes       # BDNet.py:440
-        self.coarse_pyramid_detection = CoarsePyramid([832, 1024], self.num_classes, frame_num, os_head)
+        self.coarse_pyramid_detection = CoarsePyramid([832, 1024], self.num_classes, frame_num, os_head, precision,
+                                                      native_head_convs)
         self.reset_params()
         self.backbone = I3DBackbone(in_channels, precision=precision, freeze_bn=freeze_bn,
                                     freeze_bn_affine=freeze_bn_affine)

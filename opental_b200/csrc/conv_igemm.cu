@@ -55,6 +55,7 @@ struct ConvParams {
     int out_cstride; // fp32 output: channel stride (elements) of one position and channel offset of the slice
     int out_coff;
     int accumulate;  // fp32 destination: y += result (dgrad into a shared gradient buffer)
+    int out_ncdhw;   // fp32 destination is channel-major [N, out_cstride, T, H, W] instead of channels-last
     int b_mn;        // dgrad mode: weights are read as [tap][K][N] (N contiguous, "MN-major" B) and taps are flipped
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
@@ -241,8 +242,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             const bool row_ok = (w0 + rw < p.W) && (h0 + rh < p.H) && (t0 + rt < p.T);
             float* orow = nullptr;
             if (p.out_f32 && row_ok) {
-                size_t pos = (((size_t)n * p.T + (t0 + rt)) * p.H + (h0 + rh)) * p.W + (w0 + rw);
-                orow = p.out_f32 + pos * p.out_cstride + p.out_coff;
+                const size_t pos = ((size_t)(t0 + rt) * p.H + (h0 + rh)) * p.W + (w0 + rw);
+                if (p.out_ncdhw)   // element (n, c, pos): channel stride = T*H*W, consecutive rows -> consecutive addresses
+                    orow = p.out_f32 + ((size_t)n * p.out_cstride + p.out_coff) * ((size_t)p.T * p.H * p.W) + pos;
+                else
+                    orow = p.out_f32 + ((size_t)n * p.T * p.H * p.W + pos) * p.out_cstride + p.out_coff;
             }
 
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -278,7 +282,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         if (p.relu) x = fmaxf(x, 0.f);
                         f[j] = x;
                     }
-                    if (orow) {
+                    if (orow && !p.out_ncdhw) {
                         // Cout, out_coff and out_cstride are multiples of 8: groups of 4 are all-in or all-out
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -287,6 +291,15 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                                 float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                                 if (p.accumulate) { const float4 o = *dst; v4.x += o.x; v4.y += o.y; v4.z += o.z; v4.w += o.w; }
                                 *dst = v4;
+                            }
+                    } else if (orow) {
+                        // channel-major: for a fixed channel the 32 rows of a warp are 32 consecutive floats
+                        const size_t cs = (size_t)p.T * p.H * p.W;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (cbase + j < p.Cout) {
+                                float* dst = orow + (size_t)(cbase + j) * cs;
+                                *dst = p.accumulate ? *dst + f[j] : f[j];
                             }
                     }
                     if (p.store_bf16) {
@@ -431,7 +444,10 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
     if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) {
         set_last_error_msg("conv: non-positive dimension"); return OTAL_ERR_BAD_ARG;
     }
-    if (d->Cin % 8 || d->in_cstride % 8 || d->in_coff % 8 || d->out_cstride % 8 || d->out_coff % 8 || d->Cout % 8) {
+    const bool ncdhw = d->y_f32_ncdhw != 0;   // channel-major fp32 output: no vector stores, no alignment constraint
+    if (ncdhw && d->y_hi) { set_last_error_msg("conv: NCDHW output is fp32 only"); return OTAL_ERR_BAD_ARG; }
+    if (d->Cin % 8 || d->in_cstride % 8 || d->in_coff % 8 ||
+        (!ncdhw && (d->out_cstride % 8 || d->out_coff % 8 || d->Cout % 8))) {
         set_last_error_msg("conv: channel counts / strides / offsets must be multiples of 8 (16-byte TMA rows)");
         return OTAL_ERR_BAD_ARG;
     }
@@ -455,6 +471,7 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
     p.st = st; p.sh = sh; p.sw = sw;
     p.tT = d->tT; p.tH = d->tH; p.tW = d->tW;
     p.nsplit = d->nsplit; p.relu = d->relu; p.accumulate = d->accumulate; p.b_mn = d->dgrad ? 1 : 0;
+    p.out_ncdhw = d->y_f32_ncdhw ? 1 : 0;
     p.scale = d->scale; p.shift = d->shift; p.out_f32 = d->y_f32;
     p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
     L.w_hi = d->w_hi; L.w_lo = d->w_lo; L.w_k = d->Cin; L.y_hi = d->y_hi; L.y_lo = d->y_lo;

@@ -141,6 +141,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// [B,C,T] fp32 -> channels-last planes [B,Ttot,Cpad]; thread = (b, t, 8-channel group).  Reads are strided by T
+// (tiny head tensors, L2 resident), writes are 16-byte vectors.
+__global__ void ncl_to_nlc_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                        int B, int C, int T, int Cpad, int Ttot, int dilate, int offset) {
+    const int cgs = Cpad >> 3;
+    const long long total = (long long)B * T * cgs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int t = (int)(i % T);
+        const long long r = i / T;
+        const int cg = (int)(r % cgs);
+        const int b = (int)(r / cgs);
+        uint32_t h32[4] = {0, 0, 0, 0}, l32[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            if (c < C) {
+                __nv_bfloat16 hb, lb;
+                split_bf16(x[((size_t)b * C + c) * T + t], hb, lb);
+                h32[j >> 1] |= (uint32_t)__bfloat16_as_ushort(hb) << ((j & 1) * 16);
+                l32[j >> 1] |= (uint32_t)__bfloat16_as_ushort(lb) << ((j & 1) * 16);
+            }
+        }
+        const size_t off = ((size_t)b * Ttot + offset + (size_t)t * dilate) * Cpad + cg * 8;
+        *reinterpret_cast<uint4*>(hi + off) = make_uint4(h32[0], h32[1], h32[2], h32[3]);
+        if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+    }
+}
+
 static inline int grid_for(long long work_items, int threads) {
     long long b = (work_items + threads - 1) / threads;
     const long long cap = 148LL * 8;
@@ -220,6 +249,19 @@ int otal_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                                              weight_decay, grad_scale, bc1, bc2);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+int otal_ncl_to_nlc_split(const float* x, uint16_t* hi, uint16_t* lo, int B, int C, int T, int Cpad, int Ttot, int dilate,
+                          int offset, void* stream) {
+    if (B < 0 || C <= 0 || T <= 0 || Cpad < C || Cpad % 8 || dilate < 1 || offset < 0 || offset + (T - 1) * dilate >= Ttot ||
+        !x || !hi) {
+        set_last_error_msg("ncl_to_nlc_split: bad argument"); return OTAL_ERR_BAD_ARG;
+    }
+    if (B == 0) return OTAL_OK;
+    ncl_to_nlc_split_kernel<<<grid_for((long long)B * T * (Cpad / 8), 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, hi, lo, B, C, T, Cpad, Ttot, dilate, offset);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

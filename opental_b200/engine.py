@@ -72,29 +72,41 @@ class Trainer:
         bb = net.backbone
         self.bb_w, self.bb_g = bb.flat_parameters(dev)
         bb._bind_grads()
-        bb_ids = {id(p) for p in bb.parameters()}
-        head = [p for p in net.parameters() if p.requires_grad and id(p) not in bb_ids]
+        skip = {id(p) for p in bb.parameters()}
+        # head conv weights live in the head's packed store (kernel layout), everything else (biases, GroupNorm,
+        # ScaleExp) in a plain flat buffer
+        self.hc = net.coarse_pyramid_detection.conv_store
+        self.groups = [(self.bb_w, self.bb_g)]
+        if self.hc is not None:
+            self.hc.ensure(dev)
+            self.hc.bind_grads()
+            skip |= {id(r.weight) for r in self.hc.recs}
+            self.groups.append((self.hc.flat_w, self.hc.flat_g))
+        head = [p for p in net.parameters() if p.requires_grad and id(p) not in skip]
         self.head = FlatParams(head)
-        self.state = [dict(m=torch.zeros_like(t), v=torch.zeros_like(t)) for t in (self.bb_w, self.head.w)]
+        self.groups.append((self.head.w, self.head.g))
+        self.state = [dict(m=torch.zeros_like(w), v=torch.zeros_like(w)) for w, _ in self.groups]
         self.step_count = 0
         self._head_work = None
         bb.on_backward_start = self._launch_head_allreduce if self.world > 1 else None
 
     # ---------------------------------------------------------------------------------------------- data parallel
     def _launch_head_allreduce(self) -> None:
-        self._head_work = dist.all_reduce(self.head.g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self._head_work = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for _, g in self.groups[1:]]
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
-            for t in (self.bb_w, self.head.w, self.net.backbone.flat_bn):
+            for t in [w for w, _ in self.groups] + [self.net.backbone.flat_bn]:
                 dist.broadcast(t, src, group=self.pg)
 
     # ---------------------------------------------------------------------------------------------- one step
     def zero_grad(self) -> None:
         self.net.backbone._bind_grads()
+        if self.hc is not None:
+            self.hc.bind_grads()
         self.head.rebind()
-        self.bb_g.zero_()
-        self.head.g.zero_()
+        for _, g in self.groups:
+            g.zero_()
 
     def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor):
         out = self.net(clips)
@@ -111,10 +123,11 @@ class Trainer:
             if self._head_work is None:
                 self._launch_head_allreduce()
             dist.all_reduce(self.bb_g, op=dist.ReduceOp.SUM, group=self.pg)
-            self._head_work.wait()
+            for wk in self._head_work:
+                wk.wait()
             self._head_work = None
         self.step_count += 1
-        for (w, g), st in zip(((self.bb_w, self.bb_g), (self.head.w, self.head.g)), self.state):
+        for (w, g), st in zip(self.groups, self.state):
             ops.adam_step(w, g, st["m"], st["v"], lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
                           grad_scale=1.0 / self.world, step=self.step_count)
         return cost, losses, ls, le

@@ -13,6 +13,57 @@ from . import _lib
 from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, PoolDesc, WgradDesc
 
 
+class KernelProfile:
+    """Optional per-kernel timing with CUDA events on the launching stream (bench.py's live roofline measurement).
+    Disabled by default: `with ops.PROFILE.enabled(): ...` brackets every tensor-core conv launch with two events and
+    records its algorithmic FLOPs (2 * output positions * Cout * Cin * taps, fp32 semantics — bf16x3 executes 3x that)."""
+
+    def __init__(self):
+        self.on = False
+        self.records = []      # (kernel, start_event, end_event, flops)
+
+    def enabled(self):
+        prof = self
+
+        class _Ctx:
+            def __enter__(self_):
+                prof.on = True
+                prof.records = []
+                return prof
+
+            def __exit__(self_, *a):
+                prof.on = False
+
+        return _Ctx()
+
+    def begin(self):
+        if not self.on:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def end(self, kernel: str, start, flops: float):
+        if start is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.records.append((kernel, start, ev, flops))
+
+    def summary(self) -> dict:
+        """kernel -> dict(launches, ms, flops); call after torch.cuda.synchronize()."""
+        out = {}
+        for k, s, e, f in self.records:
+            d = out.setdefault(k, dict(launches=0, ms=0.0, flops=0.0))
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += f
+        return out
+
+
+PROFILE = KernelProfile()
+
+
 def _require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -153,7 +204,7 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                in_slice: tuple[int, int] | None = None, out: Planes | None = None,
                out_slice: tuple[int, int] | None = None, out_f32: torch.Tensor | None = None,
                want_planes: bool = True, tile: tuple[int, int, int] | None = None,
-               accumulate: bool = False, dgrad: bool = False) -> Planes | None:
+               accumulate: bool = False, dgrad: bool = False, f32_ncdhw: bool = False) -> Planes | None:
     """y = relu?(conv(x, w) * scale + shift).  x: NDHWC planes [N,T,H,W,Cx]; w: [taps,Cout,Cin] planes.
 
     in_slice = (offset, Cin) reads a channel slice of x; out/out_slice = write into a slice of an existing buffer.
@@ -180,11 +231,15 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
         assert tuple(out.hi.shape[:4]) == (N, To, Ho, Wo)
     else:
         assert out_f32 is not None
-        out_cstride = out_f32.shape[-1]
+        out_cstride = out_f32.shape[1] if f32_ncdhw else out_f32.shape[-1]
     out_coff = out_slice[0] if out_slice is not None else 0
     if out_slice is not None:
         assert out_slice[1] == Cout
-    if out_f32 is not None:
+    if out_f32 is not None and f32_ncdhw:
+        # channel-major destination [N, Ctot, To, Ho, Wo] (1-D head: [B, C, T] viewed as [B, C, T, 1, 1])
+        assert out is None and out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+        assert out_f32.shape[0] == N and out_f32.numel() == N * out_cstride * To * Ho * Wo
+    elif out_f32 is not None:
         assert out_f32.shape[-1] == out_cstride and out_f32.dtype == torch.float32 and out_f32.is_contiguous()
         assert tuple(out_f32.shape[:4]) == (N, To, Ho, Wo)
     tT, tH, tW = tile if tile is not None else pick_tile_box(To, Ho, Wo)
@@ -192,14 +247,16 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                  pt=pad_front[0], ph=pad_front[1], pw=pad_front[2], tT=tT, tH=tH, tW=tW,
                  sT=stride[0], sH=stride[1], sW=stride[2],
                  nsplit=nsplit, relu=int(relu), accumulate=int(accumulate), dgrad=int(dgrad),
-                 in_cstride=Cx, in_coff=in_coff, out_cstride=out_cstride, out_coff=out_coff,
+                 y_f32_ncdhw=int(f32_ncdhw), in_cstride=Cx, in_coff=in_coff, out_cstride=out_cstride, out_coff=out_coff,
                  x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                  w_hi=w.hi.data_ptr(), w_lo=_ptr(w.lo) if nsplit == 3 else None,
                  scale=_ptr(scale), shift=_ptr(shift),
                  y_hi=_ptr(out.hi) if out is not None else None,
                  y_lo=_ptr(out.lo) if (out is not None and nsplit == 3) else None,
                  y_f32=_ptr(out_f32))
+    t0 = PROFILE.begin()
     _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
+    PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps)
     return out
 
 
@@ -225,7 +282,9 @@ def conv_wgrad(x: Planes, d: Planes, dw: torch.Tensor, *, kernel: tuple[int, int
                      d_cstride=d.hi.shape[-1], d_coff=d_coff,
                      x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                      d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
+    t0 = PROFILE.begin()
     _lib.call("otal_conv_wgrad", ctypes.byref(desc), _stream())
+    PROFILE.end("conv_wgrad_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -283,7 +342,9 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
                    w_hi=w.hi.data_ptr(), w_lo=_ptr(w.lo) if nsplit == 3 else None,
                    scale=_ptr(scale), shift=_ptr(shift), y_hi=out.hi.data_ptr(),
                    y_lo=_ptr(out.lo) if nsplit == 3 else None)
+    t0 = PROFILE.begin()
     _lib.call("otal_conv1a_fwd", ctypes.byref(d), _stream())
+    PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)   # algorithmic: 3 channels, 7^3 taps
     return out
 
 
@@ -300,7 +361,25 @@ def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[
                            d_cstride=d.hi.shape[-1], d_coff=d_slice[0] if d_slice else 0,
                            x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                            d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
+    t0 = PROFILE.begin()
     _lib.call("otal_conv1a_wgrad", ctypes.byref(desc), _stream())
+    PROFILE.end("conv_wgrad_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
+
+
+def ncl_to_nlc_planes(x: torch.Tensor, cpad: int | None = None, *, ttot: int | None = None, dilate: int = 1,
+                      offset: int = 0, with_lo: bool = True) -> Planes:
+    """[B,C,T] fp32 -> channels-last planes [B,Ttot,1,1,Cpad]; element (b,c,t) at position offset + t*dilate."""
+    _require_cuda(x)
+    x = x.contiguous().float()
+    B, C, T = x.shape
+    cpad = cpad or (C + 7) // 8 * 8
+    ttot = ttot or T
+    dense = cpad == C and dilate == 1 and ttot == T
+    mk = torch.empty if dense else torch.zeros
+    hi = mk((B, ttot, 1, 1, cpad), dtype=torch.bfloat16, device=x.device)
+    lo = mk((B, ttot, 1, 1, cpad), dtype=torch.bfloat16, device=x.device) if with_lo else None
+    _lib.call("otal_ncl_to_nlc_split", x.data_ptr(), hi.data_ptr(), _ptr(lo), B, C, T, cpad, ttot, dilate, offset, _stream())
+    return Planes(hi, lo)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -210,3 +210,82 @@ def test_fused_adam_matches_torch():
         opt.step()
         ops.adam_step(p, (grad * 4).cuda(), m, v, lr=1e-3, weight_decay=1e-3, grad_scale=0.25, step=step)
     assert torch.allclose(p.cpu(), p_ref.detach(), atol=1e-6, rtol=1e-5)
+
+
+HEAD_CONVS = [
+    # B, Cin, Cout, T, k, stride
+    (2, 512, 512, 64, 3, 1),       # tower conv
+    (2, 512, 2, 16, 3, 1),         # loc_head: Cout padded to 8
+    (3, 512, 15, 8, 1, 1),         # prop_conf_head
+    (2, 512, 1, 2, 3, 1),          # actionness head on the shortest level
+    (2, 512, 512, 32, 3, 2),       # pyramid Unit1D k3 s2 (pads (0,1)), strided wgrad + upsampled dgrad
+    (1, 512, 512, 4, 3, 2),
+    (2, 2048, 512, 16, 1, 1),      # proposal_conv
+    (1, 512, 1024, 64, 1, 1),      # lr_conv: 4 N blocks
+]
+
+
+@pytest.mark.parametrize("case", HEAD_CONVS)
+def test_head_conv1d_fwd_bwd(case):
+    """Unit1D on the tensor-core kernels (headconv.py) vs torch's fp32 conv1d + autograd (the oracle's unit1d)."""
+    from opental_b200.headconv import HeadConvStore, head_conv
+    B, Cin, Cout, T, k, s = case
+    g = torch.Generator().manual_seed(11)
+    conv = torch.nn.Conv1d(Cin, Cout, k, s).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(Cout, Cin, k, generator=g) * (2.0 / (Cin * k)) ** 0.5)
+        conv.bias.copy_(0.1 * torch.randn(Cout, generator=g))
+    w_ref = conv.weight.detach().cpu().clone().requires_grad_(True)
+    b_ref = conv.bias.detach().cpu().clone().requires_grad_(True)
+    x = torch.randn(B, Cin, T, generator=g)
+    x_ref = x.clone().requires_grad_(True)
+    y_ref = O.unit1d(x_ref, {"u.conv1d.weight": w_ref, "u.conv1d.bias": b_ref}, "u.", stride=s)
+    gy = torch.randn(y_ref.shape, generator=g)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(y_ref, (x_ref, w_ref, b_ref), gy)
+
+    store = HeadConvStore()
+    rec = store.register(conv.weight, conv.bias, "conv1d")
+    store.prepare(torch.device("cuda", torch.cuda.current_device()))
+    store.bind_grads()
+    xg = x.cuda().requires_grad_(True)
+    y = head_conv(xg, conv.weight, conv.bias, store, rec, s)
+    assert tuple(y.shape) == tuple(y_ref.shape)
+    assert rel(y.detach().cpu(), y_ref.detach()) < TOL
+    y.backward(gy.cuda())
+    assert rel(xg.grad.cpu(), gx_ref) < TOL
+    assert rel(conv.weight.grad.cpu(), gw_ref) < TOL
+    assert rel(conv.bias.grad.cpu(), gb_ref) < TOL
+    # parameters still have the reference's shapes and alias the packed store
+    assert tuple(conv.weight.shape) == (Cout, Cin, k)
+    assert torch.equal(conv.weight.detach().cpu(), w_ref.detach())
+
+
+def test_head_valid3d_conv():
+    """pyramids.0: Conv3d [512,832,1,6,6] 'spatial_valid' on the backbone's channels-last feature map."""
+    from opental_b200.headconv import HeadConvStore, head_conv
+    g = torch.Generator().manual_seed(12)
+    B, C, T, Hh = 2, 832, 8, 6
+    conv = torch.nn.Conv3d(C, 512, (1, Hh, Hh)).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(512, C, 1, Hh, Hh, generator=g) * (2.0 / (C * Hh * Hh)) ** 0.5)
+        conv.bias.copy_(0.1 * torch.randn(512, generator=g))
+    w_ref = conv.weight.detach().cpu().clone().requires_grad_(True)
+    b_ref = conv.bias.detach().cpu().clone().requires_grad_(True)
+    x = torch.randn(B, C, T, Hh, Hh, generator=g).relu()
+    x_ref = x.clone().requires_grad_(True)
+    y_ref = O.head_unit3d_valid(x_ref, {"u.conv3d.weight": w_ref, "u.conv3d.bias": b_ref}, "u.").squeeze(-1).squeeze(-1)
+    gy = torch.randn(y_ref.shape, generator=g)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(y_ref, (x_ref, w_ref, b_ref), gy)
+    store = HeadConvStore()
+    rec = store.register(conv.weight, conv.bias, "valid3d")
+    store.prepare(torch.device("cuda", torch.cuda.current_device()))
+    store.bind_grads()
+    xl = x.permute(0, 2, 3, 4, 1).contiguous().cuda().requires_grad_(True)        # NDHWC storage
+    y = head_conv(xl, conv.weight, conv.bias, store, rec, 1)
+    # reduction length 29 952: bf16x3 drops the lo*lo products (2^-16 each, random-walk ~1e-4 of the max) and the
+    # fp32 CPU reference carries its own summation error of the same order; 3e-4 is still 3x inside the budget
+    assert rel(y.detach().cpu(), y_ref.detach()) < 3e-4
+    y.backward(gy.cuda())
+    assert rel(xl.grad.permute(0, 4, 1, 2, 3).cpu(), gx_ref) < TOL
+    assert rel(conv.weight.grad.cpu(), gw_ref) < TOL
+    assert rel(conv.bias.grad.cpu(), gb_ref) < TOL
