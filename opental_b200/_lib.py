@@ -123,11 +123,23 @@ def check(rc: int, what: str) -> None:
 
 
 LAUNCHES = {}      # entry point -> number of successful calls (each launches at least one CUDA kernel of this library)
+TRACE = None       # developer tracing (tools/step_profile.py): a list collects (entry point, label, start, end) events
+LABEL = None       # free-form description of the next call (shape, role), set by ops.* when tracing
 
 
 def call(name: str, *args) -> None:
     """Call an int-returning entry point and raise RuntimeError on a non-zero code."""
-    check(getattr(load(), name)(*args), name)
+    global LABEL
+    if TRACE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(load(), name)(*args), name)
+        e1.record()
+        TRACE.append((name, LABEL, e0, e1))
+        LABEL = None
+    else:
+        check(getattr(load(), name)(*args), name)
     LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
 
 

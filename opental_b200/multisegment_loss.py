@@ -150,9 +150,10 @@ class EvidenceLoss(nn.Module):
                 onehot = onehot * weight.to(logit.dtype).unsqueeze(1)
                 cnt = onehot.sum(0)
                 mean = (onehot * grad_hat.unsqueeze(1)).sum(0) / cnt.clamp(min=1)
-                acc = self.weight_accum.to(logit.device)
-                acc = torch.where(cnt > 0, self.momentum * acc + (1 - self.momentum) * mean, acc)
-                self.weight_accum = acc
+                if self.weight_accum.device != logit.device:
+                    self.weight_accum = self.weight_accum.to(logit.device)
+                acc = torch.where(cnt > 0, self.momentum * self.weight_accum + (1 - self.momentum) * mean, self.weight_accum)
+                self.weight_accum.copy_(acc)     # in place: the buffer keeps its address (CUDA-graph replays update it)
                 w = acc[(bins - 1) % self.num_bins]                                 # bin 0 -> index -1 (python wrap)
             per = w * per
         per = torch.where(weight, per, torch.zeros_like(per))

@@ -255,6 +255,10 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                  y_lo=_ptr(out.lo) if (out is not None and nsplit == 3) else None,
                  y_f32=_ptr(out_f32))
     t0 = PROFILE.begin()
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"{'dgrad' if dgrad else 'fwd'} N{N} {T}x{H}x{W} Cin{Cin} Cout{Cout} k{kt}{kh}{kw} s{stride[0]}{stride[1]}{stride[2]} "
+                      f"x{nsplit} tile{tT}x{tH}x{tW}{' f32' if out_f32 is not None else ''}{' acc' if accumulate else ''}",
+                      2.0 * N * To * Ho * Wo * Cout * Cin * taps)
     _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
     PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps)
     return out
@@ -283,6 +287,9 @@ def conv_wgrad(x: Planes, d: Planes, dw: torch.Tensor, *, kernel: tuple[int, int
                      x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                      d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
     t0 = PROFILE.begin()
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"wgrad N{N} {T}x{H}x{W} Cin{Cin} Cout{Cout} k{kt}{kh}{kw} s{stride[0]}{stride[1]}{stride[2]} x{nsplit}",
+                      2.0 * N * To * Ho * Wo * Cout * Cin * taps)
     _lib.call("otal_conv_wgrad", ctypes.byref(desc), _stream())
     PROFILE.end("conv_wgrad_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps)
 
@@ -343,6 +350,8 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
                    scale=_ptr(scale), shift=_ptr(shift), y_hi=out.hi.data_ptr(),
                    y_lo=_ptr(out.lo) if nsplit == 3 else None)
     t0 = PROFILE.begin()
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"conv1a fwd N{N} {T}x{H}x{W} Cout{Cout} x{nsplit}", 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
     _lib.call("otal_conv1a_fwd", ctypes.byref(d), _stream())
     PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)   # algorithmic: 3 channels, 7^3 taps
     return out
@@ -362,6 +371,8 @@ def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[
                            x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                            d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
     t0 = PROFILE.begin()
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"conv1a wgrad N{N} {T}x{H}x{W} Cout{Cout} x{nsplit}", 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
     _lib.call("otal_conv1a_wgrad", ctypes.byref(desc), _stream())
     PROFILE.end("conv_wgrad_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
 
@@ -407,6 +418,8 @@ def maxpool_fwd(x: Planes, *, kernel, stride, pad_front, in_slice=None, out: Pla
     d.out_coff = out_slice[0] if out_slice else 0
     d.y_hi = out.hi.data_ptr()
     d.y_lo = _ptr(out.lo) if x.lo is not None else None
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"pool fwd {tuple(x.hi.shape)} C{C} k{kernel} s{stride}", 0.0)
     _lib.call("otal_maxpool_fwd", ctypes.byref(d), _stream())
     return out
 
@@ -424,6 +437,8 @@ def maxpool_bwd(x: Planes, g_out: torch.Tensor, g_in: torch.Tensor, *, kernel, s
     d.gin_coff = gin_slice[0] if gin_slice else 0
     d.g_out = g_out.data_ptr()
     d.g_in = g_in.data_ptr()
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"pool bwd {tuple(x.hi.shape)} C{C} k{kernel} s{stride}", 0.0)
     _lib.call("otal_maxpool_bwd", ctypes.byref(d), _stream())
 
 
@@ -440,6 +455,8 @@ def relu_bn_bwd_split(g: torch.Tensor, y: Planes | None, scale: torch.Tensor | N
     lo = torch.empty_like(hi) if with_lo else None
     y_cs = y.hi.shape[-1] if y is not None else 8
     y_co = y_slice[0] if y_slice else 0
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"relu_bn_bwd {tuple(g.shape)} C{C}", 0.0)
     _lib.call("otal_relu_bn_bwd_split", g.data_ptr(), _ptr(y.hi) if y is not None else None, _ptr(scale), hi.data_ptr(),
               _ptr(lo), npos, C, Cg, g_coff, y_cs, y_co, C, 0, int(relu and y is not None), _stream())
     return Planes(hi, lo)
