@@ -202,6 +202,43 @@ OTAL_API int otal_merge_bf16(const uint16_t* hi, const uint16_t* lo, float* x, l
 OTAL_API int otal_ncdhw_to_ndhwc_split(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W,
                               int Cpad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * MultiSegmentLoss (THUMOS14 OpenTAL configuration: cls_loss_type 'edl' with loss_type 'log', evidence 'exp', os_head)
+ * — replaces MultiSegmentLoss.forward            AFSD/thumos14/multisegment_loss.py:92-259 (iou_loss :20-53)
+ *            EvidenceLoss.forward/edl_loss/iou_calib  AFSD/thumos14/cls_loss.py:120-168, :212-278
+ *            ActionnessLoss.forward                   AFSD/thumos14/cls_loss.py:299-339
+ * and their autograd backward.  One single-CTA launch computes the 7 losses and the gradient of each loss w.r.t. each
+ * head output ("unit gradients", stored in `workspace`); otal_msl_backward scales them by the 7 upstream gradients.
+ *
+ * Inputs are the reference's tensors, contiguous fp32: loc/prop_loc [B,P,2], conf/prop_conf [B,P,K], center/act/
+ * prop_act [B,P] (act / prop_act may be NULL: no os_head), priors element p at priors[p*prior_stride], targets
+ * [B,G,3] = (start, end, label 1..K) normalised to the clip, zero padded, valid [B,G] bytes (1 = real row).
+ * weight_accum [num_bins] is the IBM EMA state (cls_loss.py:114), updated in place when use_ibm != 0 (the caller sets
+ * use_ibm = epoch >= ibm_start).  losses [16]: loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act,
+ * loss_prop_act, then N, PN, AN, PAN, loss_iouc.  workspace: otal_msl_workspace_floats(B,P,K) floats.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct otal_msl_desc {
+    int B, P, K, G;
+    float clip_length, overlap_thresh;
+    int use_ibm, num_bins;
+    float momentum;
+    int iou_aware;
+    float act_weight, act_margin;
+    int prior_stride;
+    const float* loc; const float* conf; const float* prop_loc; const float* prop_conf;
+    const float* center; const float* act; const float* prop_act;
+    const float* priors; const float* targets; const unsigned char* valid;
+    float* weight_accum;
+    float* losses;
+    float* workspace;
+} otal_msl_desc;
+OTAL_API long long otal_msl_workspace_floats(int B, int P, int K);
+OTAL_API int otal_msl_forward(const otal_msl_desc* desc, void* stream);
+/* grad_losses [7] (device): upstream gradients of the 7 losses.  g_act / g_prop_act may be NULL. */
+OTAL_API int otal_msl_backward(int B, int P, int K, const float* workspace, const float* grad_losses, float* g_loc,
+                               float* g_conf, float* g_prop_loc, float* g_prop_conf, float* g_center, float* g_act,
+                               float* g_prop_act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,16 @@ class PoolDesc(Structure):
                 + _ptrs("x_hi", "x_lo", "y_hi", "y_lo", "g_out", "g_in"))
 
 
+class MslDesc(Structure):
+    """Mirror of `otal_msl_desc`."""
+
+    _fields_ = (_ints("B", "P", "K", "G") + [("clip_length", c_float), ("overlap_thresh", c_float)] + _ints("use_ibm", "num_bins")
+                + [("momentum", c_float)] + _ints("iou_aware") + [("act_weight", c_float), ("act_margin", c_float)]
+                + _ints("prior_stride")
+                + _ptrs("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "priors", "targets", "valid",
+                        "weight_accum", "losses", "workspace"))
+
+
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/opental_b200.h.
 SIGNATURES = {
     "otal_last_error": (c_char_p, []),
@@ -87,6 +97,10 @@ SIGNATURES = {
     "otal_ncl_to_nlc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_merge_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "otal_msl_workspace_floats": (c_longlong, [c_int, c_int, c_int]),
+    "otal_msl_forward": (c_int, [POINTER(MslDesc), c_void_p]),
+    "otal_msl_backward": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "otal_ncdhw_to_ndhwc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

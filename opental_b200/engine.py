@@ -88,9 +88,15 @@ class Trainer:
         self.state = [dict(m=torch.zeros_like(w), v=torch.zeros_like(w)) for w, _ in self.groups]
         self.step_count = 0
         self._head_work = None
-        bb.on_backward_start = self._launch_head_allreduce if self.world > 1 else None
+        self._graph = None
+        self._static = None
+        bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
 
     # ---------------------------------------------------------------------------------------------- data parallel
+    def _on_backbone_backward(self) -> None:
+        if not torch.cuda.is_current_stream_capturing():      # inside a graph capture the all-reduce stays outside
+            self._launch_head_allreduce()
+
     def _launch_head_allreduce(self) -> None:
         self._head_work = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for _, g in self.groups[1:]]
 
@@ -113,12 +119,57 @@ class Trainer:
         losses = self.criterion(out, targets)
         cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw)
         cost.backward()
-        return cost.detach(), losses, ls.detach(), le.detach()
+        # detached: a caller holding a non-detached loss would keep this step's autograd graph (and its AccumulateGrad
+        # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture
+        return cost.detach(), tuple(l.detach() if l is not None else None for l in losses), ls.detach(), le.detach()
+
+    # ---------------------------------------------------------------------------------------------- CUDA graph
+    def capture(self, clips: torch.Tensor, targets, scores: torch.Tensor) -> None:
+        """Capture zero_grad + forward + loss + backward for this input geometry into ONE CUDA graph.  The head and the
+        loss are ~2500 small launches whose host-side enqueue cost (~75 ms per step at batch 8) exceeds the GPU work; a
+        graph replay removes it.  Inputs are copied into static buffers before every replay; the gradient all-reduce and
+        the Adam launches stay outside the graph (Adam's bias correction depends on the host step counter).
+        The graph bakes in `criterion.cls_loss.epoch >= ibm_start`: re-capture when the epoch crosses ibm_start."""
+        import gc
+        gc.collect()                                 # drop dead autograd graphs of earlier eager steps (see forward_backward)
+        tgt, valid = pad_targets(targets, clips.device)
+        self._static = [torch.empty_like(t) for t in (clips, tgt, valid, scores)]
+        for d, s in zip(self._static, (clips, tgt, valid, scores)):
+            d.copy_(s)
+        c, t, v, sc = self._static
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            for _ in range(2):                       # warm-up on the capture stream (lazy initialisations, allocator)
+                self.zero_grad()
+                self.forward_backward(c, (t, v), sc)
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=stream):
+            self.zero_grad()
+            self._graph_out = self.forward_backward(c, (t, v), sc)
+        self._graph_epoch_flag = self._ibm_flag()
+
+    def _ibm_flag(self):
+        c = self.criterion.cls_loss
+        return bool(getattr(c, "with_ibm", False) and c.epoch >= getattr(c, "ibm_start", 0))
 
     def step(self, clips: torch.Tensor, targets, scores: torch.Tensor):
         """clips [B,3,T,H,W] fp32 on the device, targets: list of [N_i,3] or padded (tensor, mask), scores [B,2,T]."""
-        self.zero_grad()
-        cost, losses, ls, le = self.forward_backward(clips, targets, scores)
+        if self._graph is not None:
+            tgt, valid = pad_targets(targets, clips.device)
+            if (tuple(clips.shape) != tuple(self._static[0].shape) or tuple(tgt.shape) != tuple(self._static[1].shape)
+                    or self._ibm_flag() != self._graph_epoch_flag):
+                raise RuntimeError("captured training graph does not match this batch geometry / epoch: call capture() again")
+            for d, s in zip(self._static, (clips, tgt, valid, scores)):
+                if d.data_ptr() != s.data_ptr():
+                    d.copy_(s, non_blocking=True)
+            self._graph.replay()
+            cost, losses, ls, le = self._graph_out
+        else:
+            self.zero_grad()
+            cost, losses, ls, le = self.forward_backward(clips, targets, scores)
         if self.world > 1:
             if self._head_work is None:
                 self._launch_head_allreduce()

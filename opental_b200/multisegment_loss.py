@@ -200,6 +200,25 @@ class ActionnessLoss(nn.Module):
         return loss, count
 
 
+class _FusedMSLFn(torch.autograd.Function):
+    """Autograd boundary of the single-CTA loss kernel (opental_b200/csrc/msl.cu): returns the loss vector [7]."""
+
+    @staticmethod
+    def forward(ctx, loc, conf, ploc, pconf, center, act, pact, priors, tgt, valid, weight_accum, cfg):
+        from . import ops
+        losses, ws = ops.msl_forward(loc, conf, ploc, pconf, center, act, pact, priors, tgt, valid, weight_accum, **cfg)
+        ctx.ws, ctx.dims, ctx.with_act = ws, tuple(conf.shape), act is not None
+        ctx.mark_non_differentiable(losses)
+        return losses[:7].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _g_stats):
+        from . import ops
+        B, P, K = ctx.dims
+        gl, gc, gpl, gpc, gct, ga, gpa = ops.msl_backward(ctx.ws, g, B, P, K, ctx.with_act)
+        return gl, gc, gpl, gpc, gct, ga, gpa, None, None, None, None, None
+
+
 class MultiSegmentLoss(nn.Module):
     def __init__(self, num_classes, overlap_thresh, negpos_ratio, use_gpu=True, cls_loss_type="focal", edl_config=None,
                  rpl_config=None, os_head=False, act_config=None, size_average=False, *, clip_length=256):
@@ -221,6 +240,7 @@ class MultiSegmentLoss(nn.Module):
         if os_head:
             self.act_loss = ActionnessLoss(size_average=size_average, cfg=act_config)
         self.size_average = size_average
+        self.fused = True       # use the single-CTA CUDA kernel when the configuration allows it (see _fused_ok)
 
     @torch.no_grad()
     def match(self, loc, priors, tgt, valid):
@@ -248,12 +268,32 @@ class MultiSegmentLoss(nn.Module):
         del sel
         return loc_t, conf_t, prop_loc_t, prop_conf_t, iou
 
+    def _fused_ok(self, loc) -> bool:
+        """The single-CTA CUDA kernel covers the OpenTAL configuration; every other variant (focal, digamma, relu /
+        softplus evidence, soft labels, size_average, closed-set head) runs the masked torch formulation below."""
+        c = self.cls_loss
+        return (self.fused and loc.is_cuda and loc.dtype == torch.float32 and self.cls_loss_type == "edl" and self.os_head
+                and not self.size_average and c.loss_type == "log" and c.evidence == "exp" and not c.soft_label
+                and loc.shape[0] * loc.shape[1] <= 4096)
+
     def forward(self, output_dict, targets, pre_locs=None):
         loc, conf, ploc, pconf, center, priors = (output_dict[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))
         act, pact = output_dict.get("act"), output_dict.get("prop_act")
         B, P = loc.shape[:2]
         K = self.num_classes
         tgt, valid = pad_targets(targets, loc.device)
+        if self._fused_ok(loc):
+            c = self.cls_loss
+            use_ibm = bool(c.with_ibm and c.epoch >= c.ibm_start)
+            if c.with_ibm and c.weight_accum.device != loc.device:
+                c.weight_accum = c.weight_accum.to(loc.device)
+            cfg = dict(clip_length=float(self.clip_length), overlap_thresh=float(self.overlap_thresh), use_ibm=use_ibm,
+                       momentum=float(c.momentum) if c.with_ibm else 0.0, iou_aware=bool(self.iou_aware),
+                       act_weight=float(self.act_loss.weight), act_margin=float(self.act_loss.margin))
+            vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P), pact.reshape(B, P),
+                                           priors, tgt, valid, c.weight_accum if c.with_ibm else None, cfg)
+            self.last_stats = stats        # N, PN, AN, PAN, loss_iouc at [7:12] (device; for logging)
+            return tuple(vec.unbind(0))
         loc_t, conf_t, prop_loc_t, prop_conf_t, iou = self.match(loc.detach(), priors, tgt, valid)
         pos, ppos = conf_t > 0, prop_conf_t > 0
         zero = loc.new_zeros(())

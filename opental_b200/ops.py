@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, PoolDesc, WgradDesc
+from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, MslDesc, PoolDesc, WgradDesc
 
 
 class KernelProfile:
@@ -470,3 +470,49 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
     _lib.call("otal_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1],
               eps, weight_decay, grad_scale, step, _stream())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# MultiSegmentLoss (single-CTA fused kernel)
+# ----------------------------------------------------------------------------------------------------------
+def msl_forward(loc, conf, prop_loc, prop_conf, center, act, prop_act, priors, targets, valid, weight_accum, *,
+                clip_length: float, overlap_thresh: float, use_ibm: bool, momentum: float, iou_aware: bool,
+                act_weight: float, act_margin: float) -> tuple[torch.Tensor, torch.Tensor]:
+    """All 7 losses (+ N, PN, AN, PAN, loss_iouc) and the unit-gradient workspace.  See include/opental_b200.h."""
+    _require_cuda(loc, conf, prop_loc, prop_conf, center, priors, targets, valid)
+    B, P, K = conf.shape
+    G = targets.shape[1]
+    ts = [t.contiguous() if t is not None else None for t in (loc, conf, prop_loc, prop_conf, center, act, prop_act)]
+    for t in ts:
+        assert t is None or t.dtype == torch.float32
+    targets = targets.contiguous().float()
+    valid = valid.contiguous()
+    assert valid.element_size() == 1 and priors.dtype == torch.float32
+    losses = torch.empty(16, dtype=torch.float32, device=loc.device)
+    ws = torch.empty(int(_lib.load().otal_msl_workspace_floats(B, P, K)), dtype=torch.float32, device=loc.device)
+    d = MslDesc(B=B, P=P, K=K, G=G, clip_length=clip_length, overlap_thresh=overlap_thresh, use_ibm=int(use_ibm),
+                num_bins=weight_accum.numel() if weight_accum is not None else 0, momentum=momentum, iou_aware=int(iou_aware),
+                act_weight=act_weight, act_margin=act_margin, prior_stride=priors.stride(0),
+                loc=ts[0].data_ptr(), conf=ts[1].data_ptr(), prop_loc=ts[2].data_ptr(), prop_conf=ts[3].data_ptr(),
+                center=ts[4].data_ptr(), act=_ptr(ts[5]), prop_act=_ptr(ts[6]), priors=priors.data_ptr(),
+                targets=targets.data_ptr(), valid=valid.data_ptr(), weight_accum=_ptr(weight_accum),
+                losses=losses.data_ptr(), workspace=ws.data_ptr())
+    _lib.call("otal_msl_forward", ctypes.byref(d), _stream())
+    return losses, ws
+
+
+def msl_backward(ws: torch.Tensor, grad_losses: torch.Tensor, B: int, P: int, K: int, with_act: bool):
+    """Input gradients (loc, conf, prop_loc, prop_conf, center, act, prop_act) from the workspace of msl_forward."""
+    dev = ws.device
+    grad_losses = grad_losses.contiguous().float()
+    assert grad_losses.numel() >= 7
+    g_loc = torch.empty(B, P, 2, dtype=torch.float32, device=dev)
+    g_ploc = torch.empty_like(g_loc)
+    g_conf = torch.empty(B, P, K, dtype=torch.float32, device=dev)
+    g_pconf = torch.empty_like(g_conf)
+    g_center = torch.empty(B, P, dtype=torch.float32, device=dev)
+    g_act = torch.empty(B, P, dtype=torch.float32, device=dev) if with_act else None
+    g_pact = torch.empty(B, P, dtype=torch.float32, device=dev) if with_act else None
+    _lib.call("otal_msl_backward", B, P, K, ws.data_ptr(), grad_losses.data_ptr(), g_loc.data_ptr(), g_conf.data_ptr(),
+              g_ploc.data_ptr(), g_pconf.data_ptr(), g_center.data_ptr(), _ptr(g_act), _ptr(g_pact), _stream())
+    return g_loc, g_conf, g_ploc, g_pconf, g_center, g_act, g_pact

@@ -1,0 +1,139 @@
+"""GPU parity of the single-CTA MultiSegmentLoss kernel (opental_b200/csrc/msl.cu, through the C ABI) against the CPU
+oracle restatement of the reference loss (oracle/opental_oracle.py, pinned to reference-generated golden values by
+tests/test_oracle_golden.py): the 7 losses, the IBM EMA buffer and the gradient of the weighted cost w.r.t. every head
+output.  Tolerance: 2e-5 relative on the losses (fp32 summation order and expf/logf rounding), 1e-4 relative / 2e-6
+absolute on the gradients."""
+import math
+
+import pytest
+import torch
+
+import opental_oracle as O
+from opental_b200.engine import OPENTAL_EDL_CONFIG
+from opental_b200.multisegment_loss import MultiSegmentLoss
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
+W = (1.0, 10.0, 1.0, 10.0, 1.0, 1.0, 1.0)
+
+
+def fake_outputs(B, seed, loc_scale=30.0, P=126):
+    g = torch.Generator().manual_seed(seed)
+    cfg = O.OracleConfig()
+    out = dict(loc=(torch.rand(B, P, 2, generator=g) * loc_scale + 1), conf=2 * torch.randn(B, P, 15, generator=g),
+               prop_loc=0.3 * torch.randn(B, P, 2, generator=g), prop_conf=2 * torch.randn(B, P, 15, generator=g),
+               center=torch.randn(B, P, 1, generator=g), act=torch.randn(B, P, 1, generator=g),
+               prop_act=torch.randn(B, P, 1, generator=g))
+    return out, torch.cat(O.level_priors(cfg), 0), cfg
+
+
+def make_crit(epoch, act_weight=0.0):
+    crit = MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True,
+                            act_config=dict(weight=act_weight, margin=1.0)).cuda()
+    crit.cls_loss.epoch = epoch
+    return crit
+
+
+def run_both(B, epoch, act_weight, seed, targets=None, loc_scale=30.0, mutate=None):
+    out, priors, cfg = fake_outputs(B, seed, loc_scale)
+    if mutate:
+        mutate(out)
+    cfg.act_weight = act_weight
+    targets = targets or [O.synthetic_targets(i, num_classes=15) for i in range(B)]
+    # oracle (CPU)
+    ref_in = {k: v.clone().requires_grad_(True) for k, v in out.items()}
+    ref_in["priors"] = priors
+    state = O.LossState(epoch=epoch)
+    ref = O.multisegment_loss(ref_in, targets, state, cfg)
+    g_ref = torch.autograd.grad(sum(w * l for w, l in zip(W, ref)), [ref_in[k] for k in KEYS], allow_unused=True)
+    # fused CUDA kernel
+    dev_in = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+    dev_in["priors"] = priors.cuda()
+    crit = make_crit(epoch, act_weight)
+    assert crit._fused_ok(dev_in["loc"])
+    got = crit(dev_in, [t.cuda() for t in targets])
+    g_got = torch.autograd.grad(sum(w * l for w, l in zip(W, got)), [dev_in[k] for k in KEYS], allow_unused=True)
+    return ref, g_ref, state, got, g_got, crit
+
+
+def check(ref, g_ref, state, got, g_got, crit):
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (i, float(a), float(b))
+    assert torch.allclose(crit.cls_loss.weight_accum.cpu(), state.weight_accum, atol=1e-6)
+    for k, a, b in zip(KEYS, g_got, g_ref):
+        b = torch.zeros_like(a.cpu()) if b is None else b
+        assert torch.allclose(a.cpu(), b, atol=2e-6, rtol=1e-4), (k, float((a.cpu() - b).abs().max()))
+
+
+@pytest.mark.parametrize("B,epoch,act_weight", [(1, 1, 0.0), (1, 11, 0.0), (3, 11, 0.0), (2, 11, 0.1), (8, 11, 0.0), (8, 1, 0.1),
+                                                (16, 11, 0.1)])
+def test_fused_loss_matches_oracle(B, epoch, act_weight):
+    targets = [O.synthetic_targets(i, num_classes=15) for i in range(B)]
+    if B >= 3:
+        targets[1] = targets[1][:1]                       # ragged number of ground-truth segments
+    check(*run_both(B, epoch, act_weight, seed=10 * B + epoch, targets=targets))
+
+
+def test_fused_loss_small_extents_few_refined_positives():
+    # random-init-like loc (extent ~2 frames): IoU with the GT below piou almost everywhere -> PN tiny or zero
+    check(*run_both(2, 11, 0.0, seed=77, loc_scale=1.0))
+
+
+def test_fused_loss_no_positive_priors():
+    targets = [torch.tensor([[1.2, 1.4, 3.0]]), torch.tensor([[1.5, 1.9, 4.0]])]     # outside [0,1]: no prior inside
+    ref, g_ref, state, got, g_got, crit = run_both(2, 11, 0.1, seed=3, targets=targets)
+    assert float(got[0]) == 0 and float(got[1]) == 0 and float(got[2]) == 0 and float(got[4]) == 0
+    check(ref, g_ref, state, got, g_got, crit)
+
+
+def test_fused_loss_clamped_logits():
+    # logits beyond +-10 hit the clamp of the exp evidence: zero gradient there (cls_loss.py:182-190)
+    def mutate(out):
+        out["conf"][:, ::3, 2] = 14.0
+        out["prop_conf"][:, ::4, 5] = -13.0
+    check(*run_both(2, 11, 0.0, seed=5, mutate=mutate))
+
+
+def test_fused_matches_masked_torch_formulation_on_device():
+    """Same inputs through the torch formulation of the same module (fused = False), all on the GPU."""
+    out, priors, _ = fake_outputs(8, 123)
+    targets = [O.synthetic_targets(i, num_classes=15).cuda() for i in range(8)]
+    res = []
+    for fused in (True, False):
+        crit = make_crit(11)
+        crit.fused = fused
+        d = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+        d["priors"] = priors.cuda()
+        l = crit(d, targets)
+        g = torch.autograd.grad(sum(w * x for w, x in zip(W, l)), [d[k] for k in KEYS])
+        res.append((l, g, crit.cls_loss.weight_accum.clone()))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b)))
+    for k, a, b in zip(KEYS, res[0][1], res[1][1]):
+        assert torch.allclose(a, b, atol=2e-6, rtol=1e-4), k
+    assert torch.allclose(res[0][2], res[1][2], atol=1e-6)
+
+
+def test_fused_loss_is_deterministic_and_sync_free():
+    out, priors, _ = fake_outputs(8, 9)
+    targets = [O.synthetic_targets(i, num_classes=15) for i in range(8)]
+    from opental_b200.multisegment_loss import pad_targets
+    tp, tv = pad_targets(targets, device="cpu")
+    tp, tv = tp.cuda(), tv.cuda()
+    d = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+    d["priors"] = priors.cuda()
+    vals = []
+    torch.cuda.synchronize()
+    for _ in range(2):
+        crit = make_crit(11)
+        torch.cuda.set_sync_debug_mode("error")          # any host<->device synchronisation raises
+        try:
+            l = crit(d, (tp, tv))
+            cost = sum(w * x for w, x in zip(W, l))
+            g = torch.autograd.grad(cost, [d[k] for k in KEYS])
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+        vals.append(torch.cat([torch.stack(list(l))] + [x.reshape(-1) for x in g]))
+    assert torch.equal(vals[0], vals[1])
+    assert all(math.isfinite(v) for v in vals[0][:7].tolist())

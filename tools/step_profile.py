@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--syncs", action="store_true")
     ap.add_argument("--top", type=int, default=70)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -106,30 +107,42 @@ def main():
         tf = r[2] / (r[1] * 1e-3) / 1e12 if r[1] > 0 and r[2] > 0 else 0.0
         print(f"  {r[1]:8.3f} {r[0]:4d} {tf:7.1f}  {name[5:]:22s} {label}")
 
+    if args.syncs:
+        import traceback
+        import warnings
+        seen = collections.Counter()
+
+        def show(message, category, filename, lineno, file=None, line=None):
+            if "synchroniz" in str(message):
+                st = [f for f in traceback.extract_stack() if "opental_b200" in f.filename or "bench" in f.filename]
+                seen[" <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in st[-3:])] += 1
+
+        warnings.showwarning = show
+        warnings.simplefilter("always")
+        torch.cuda.set_sync_debug_mode("warn")
+        tr.step(clips, (tp, tv), sc)
+        torch.cuda.set_sync_debug_mode("default")
+        torch.cuda.synchronize()
+        print("host<->device synchronisations inside one eager step:", sum(seen.values()))
+        for k, v in seen.most_common(20):
+            print(f"  {v:4d}  {k}")
+
     if args.graph:
         try:
-            crit.cls_loss.epoch = 11
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                tr.zero_grad()
-                tr.forward_backward(clips, (tp, tv), sc)
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                tr.zero_grad()
-                cost, losses, ls, le = tr.forward_backward(clips, (tp, tv), sc)
-            torch.cuda.synchronize()
+            del cost, losses, out, feat
+            tr.capture(clips, (tp, tv), sc)
             for _ in range(2):
-                g.replay()
+                tr.step(clips, (tp, tv), sc)
             torch.cuda.synchronize()
             e0 = ev()
             for _ in range(5):
-                g.replay()
+                cost, losses, ls, le = tr.step(clips, (tp, tv), sc)
             e1 = ev(); torch.cuda.synchronize()
-            print(f"CUDA-graph replay of zero_grad+fwd+loss+bwd: {e0.elapsed_time(e1) / 5:.2f} ms, cost {float(cost):.4f}")
+            print(f"CUDA-graph step (replay + Adam): {e0.elapsed_time(e1) / 5:.2f} ms, cost {float(cost):.4f}, "
+                  f"losses {[round(float(v), 4) for v in losses]}")
         except Exception as ex:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
             print("graph capture failed:", repr(ex)[:1500])
 
 
