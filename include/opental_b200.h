@@ -239,6 +239,17 @@ OTAL_API int otal_msl_backward(int B, int P, int K, const float* workspace, cons
                                float* g_conf, float* g_prop_loc, float* g_prop_conf, float* g_center, float* g_act,
                                float* g_prop_act, void* stream);
 
+/* GroupNorm(groups, C) + ReLU on [B,C,T] fp32 — replaces nn.GroupNorm(32, C) + nn.ReLU(inplace=True) after every
+ * pyramid / tower / proposal-branch / deconv conv (AFSD/thumos14/BDNet.py:72-73, :139-140, :166-167, :176-177, :276-283).
+ * forward also writes the per-(sample, group) mean and 1/sqrt(var + eps) ([B*groups] each) that backward consumes.
+ * backward: gx [B,C,T]; dgamma_dbeta [B,2,C] = per-sample partial sums of (d gamma, d beta) — sum over B for the
+ * parameter gradients.  relu = 0 gives plain GroupNorm. */
+OTAL_API int otal_groupnorm_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                                     int B, int C, int T, int groups, float eps, int relu, void* stream);
+OTAL_API int otal_groupnorm_relu_bwd(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                                     const float* rstd, float* gx, float* dgamma_dbeta, int B, int C, int T, int groups,
+                                     int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .backbone import I3DBackbone
 from .headconv import HeadConvStore, head_conv
 from .prop_pooling import BoundaryMaxPooling
@@ -70,8 +71,17 @@ class Unit3DValid(nn.Module):
         return self.conv3d(x).squeeze(-1).squeeze(-1)
 
 
+class GroupNormReLU(nn.GroupNorm):
+    """nn.GroupNorm(32, C) fused with the ReLU that follows it everywhere in CoarsePyramid (BDNet.py:72-73 etc.): one
+    native launch (opental_b200/csrc/gn.cu).  Same parameters / state_dict keys as nn.GroupNorm."""
+
+    def forward(self, x):
+        return ops.groupnorm_relu(x, self.weight, self.bias, self.num_groups, self.eps, relu=True)
+
+
 def _unit_gn(unit, channels):
-    return nn.Sequential(unit, nn.GroupNorm(32, channels), nn.ReLU(inplace=True))
+    # index 1 keeps the reference's state_dict keys ('<seq>.1.weight/bias'); index 2 was the in-place ReLU
+    return nn.Sequential(unit, GroupNormReLU(32, channels), nn.Identity())
 
 
 class ScaleExp(nn.Module):
@@ -141,9 +151,9 @@ class CoarsePyramid(nn.Module):
             self.prop_actionness_head = Unit1D(out_channels, 1, 1)
         self.center_head = Unit1D(out_channels, 1, 3)
         self.deconv = nn.Sequential(
-            Unit1D(out_channels, out_channels, 3), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True),
-            Unit1D(out_channels, out_channels, 3), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True),
-            Unit1D(out_channels, out_channels, 1), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True))
+            Unit1D(out_channels, out_channels, 3), GroupNormReLU(32, out_channels), nn.Identity(),
+            Unit1D(out_channels, out_channels, 3), GroupNormReLU(32, out_channels), nn.Identity(),
+            Unit1D(out_channels, out_channels, 1), GroupNormReLU(32, out_channels), nn.Identity())
         self.boundary_max_pooling = BoundaryMaxPooling()
         self.priors = []
         t = feat_t

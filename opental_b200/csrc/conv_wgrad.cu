@@ -94,12 +94,16 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // item -> (ks, nb, mb, tap); K tiles [k_begin, k_end) of the item's split
+    // item -> (tap, nb, mb, ks), tap fastest: the CTAs that run concurrently work on the SAME K chunk (range of output
+    // positions) for different taps / channel blocks, so the chunk of D and X is fetched from HBM once and re-read by
+    // the other taps from L2.  (With ks fastest every tap streamed the whole D and X tensors from HBM again: taps x
+    // (|D| + |X|) of DRAM traffic, e.g. 16 GB for Conv3d_2c at batch 8.)
     auto decode = [&](int item, int& tap, int& mb, int& nb, int& k_begin, int& k_end) {
-        const int ks = item % p.ksplit; item /= p.ksplit;
+        const int ntaps_ = p.kt * p.kh * p.kw;
+        tap = item % ntaps_; item /= ntaps_;
         nb = item % p.n_blocks; item /= p.n_blocks;
         mb = item % p.m_blocks; item /= p.m_blocks;
-        tap = item;
+        const int ks = item;
         const long long kt_ = p.ktiles;
         k_begin = (int)(kt_ * ks / p.ksplit);
         k_end = (int)(kt_ * (ks + 1) / p.ksplit);
@@ -256,7 +260,18 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     }
     const int ntaps = p.kt * p.kh * p.kw;
     const int base_items = ntaps * p.m_blocks * p.n_blocks;
-    int ks = (2 * wg_num_sms() + base_items - 1) / base_items;
+    int ks = (2 * wg_num_sms() + base_items - 1) / base_items;       // at least two waves of work items
+    {
+        // K chunk sized so that the chunks in flight (concurrent CTAs / items per chunk, + 1 for the transition) stay
+        // L2-resident: bytes per 64-position K tile = 64 x (Cout + Cin) channels x 2 B x planes
+        const double tile_bytes = 64.0 * (p.Cout + p.Cin) * 2.0 * (split ? 2.0 : 1.0);
+        const int in_flight = (wg_num_sms() + base_items - 1) / base_items + 1;
+        const double budget = 40.0 * 1024 * 1024 / in_flight;
+        long long chunk_tiles = (long long)(budget / tile_bytes);
+        if (chunk_tiles < 16) chunk_tiles = 16;                      // keep the accumulation long enough to amortise the epilogue
+        const long long ks_l2 = (p.ktiles + chunk_tiles - 1) / chunk_tiles;
+        if (ks_l2 > ks) ks = (int)(ks_l2 > 4096 ? 4096 : ks_l2);
+    }
     if (ks > p.ktiles) ks = p.ktiles;
     if (ks < 1) ks = 1;
     p.ksplit = ks;

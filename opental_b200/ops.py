@@ -516,3 +516,41 @@ def msl_backward(ws: torch.Tensor, grad_losses: torch.Tensor, B: int, P: int, K:
     _lib.call("otal_msl_backward", B, P, K, ws.data_ptr(), grad_losses.data_ptr(), g_loc.data_ptr(), g_conf.data_ptr(),
               g_ploc.data_ptr(), g_pconf.data_ptr(), g_center.data_ptr(), _ptr(g_act), _ptr(g_pact), _stream())
     return g_loc, g_conf, g_ploc, g_pconf, g_center, g_act, g_pact
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GroupNorm + ReLU
+# ----------------------------------------------------------------------------------------------------------
+class _GroupNormReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups: int, eps: float, relu: bool):
+        _require_cuda(x, gamma, beta)
+        x = x.contiguous()
+        assert x.dtype == torch.float32 and x.dim() == 3
+        B, C, T = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(2, B * groups, dtype=torch.float32, device=x.device)
+        _lib.call("otal_groupnorm_relu_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), stats[0].data_ptr(),
+                  stats[1].data_ptr(), B, C, T, groups, eps, int(relu), _stream())
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.cfg = (groups, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        groups, relu = ctx.cfg
+        B, C, T = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        dgb = torch.empty(B, 2, C, dtype=torch.float32, device=x.device)
+        _lib.call("otal_groupnorm_relu_bwd", gy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats[0].data_ptr(),
+                  stats[1].data_ptr(), gx.data_ptr(), dgb.data_ptr(), B, C, T, groups, int(relu), _stream())
+        d = dgb.sum(0) if B > 1 else dgb[0]
+        return gx, d[0], d[1], None, None, None
+
+
+def groupnorm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32, eps: float = 1e-5,
+                   relu: bool = True) -> torch.Tensor:
+    """relu(group_norm(x)) on [B,C,T] fp32 in one launch (forward) / one launch + a [B,2,C] batch reduction (backward)."""
+    return _GroupNormReLUFn.apply(x, gamma, beta, groups, eps, relu)
