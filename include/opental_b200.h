@@ -241,14 +241,33 @@ OTAL_API int otal_msl_backward(int B, int P, int K, const float* workspace, cons
 
 /* GroupNorm(groups, C) + ReLU on [B,C,T] fp32 — replaces nn.GroupNorm(32, C) + nn.ReLU(inplace=True) after every
  * pyramid / tower / proposal-branch / deconv conv (AFSD/thumos14/BDNet.py:72-73, :139-140, :166-167, :176-177, :276-283).
- * forward also writes the per-(sample, group) mean and 1/sqrt(var + eps) ([B*groups] each) that backward consumes.
- * backward: gx [B,C,T]; dgamma_dbeta [B,2,C] = per-sample partial sums of (d gamma, d beta) — sum over B for the
- * parameter gradients.  relu = 0 gives plain GroupNorm. */
+ * Segments: nseg (0..8) column ranges [seg_off[s], seg_off[s] + seg_len[s]) along T (HOST int arrays) are normalised
+ * independently — the 6 pyramid levels laid side by side, which share these modules' weights (BDNet.py:333-412) — and
+ * every column outside the ranges is written as 0 (forward) / receives gradient 0 (backward).  nseg = 0: one segment
+ * [0,T), i.e. plain GroupNorm.
+ * forward also writes the per-(sample, group, segment) mean and 1/sqrt(var + eps) ([B*groups*max(nseg,1)] each) that
+ * backward consumes.  backward: gx [B,C,T]; dgamma_dbeta [B,2,C] = per-sample partial sums of (d gamma, d beta) — sum
+ * over B for the parameter gradients.  relu = 0 gives plain GroupNorm. */
 OTAL_API int otal_groupnorm_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                                     int B, int C, int T, int groups, float eps, int relu, void* stream);
+                                     int B, int C, int T, int groups, float eps, int relu, int nseg, const int* seg_off,
+                                     const int* seg_len, void* stream);
 OTAL_API int otal_groupnorm_relu_bwd(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
                                      const float* rstd, float* gx, float* dgamma_dbeta, int B, int C, int T, int groups,
-                                     int relu, void* stream);
+                                     int relu, int nseg, const int* seg_off, const int* seg_len, void* stream);
+
+/* Proposal window generation for all pyramid levels at once — replaces the no_grad block AFSD/thumos14/BDNet.py:355-384.
+ * loc [B,P,2] (frames) over the P = sum of level lengths priors; per-prior tables prior [P] ((c+0.5)/t), level_len [P]
+ * (t of the prior's level), level_off [P] (first column of that level in the level-concatenated feature).
+ *   seg_level  [B,P,4] (optional, may be NULL): the reference's `segments` in level units, bit-identical to torch
+ *   seg_concat [B,P,4]: the same windows truncated + clamped to [0, t-1] (what boundary_max_pooling_kernel.cu:33-38 does
+ *                       with them) + level_off: windows into the level-concatenated feature
+ *   frame_seg  [B,P,4]: the reference's `frame_segments` (frame units), bit-identical to torch */
+OTAL_API int otal_make_segments(const float* loc, const float* prior, const int* level_len, const int* level_off,
+                                float* seg_level, float* seg_concat, float* frame_seg, int B, int P, float frame_num, void* stream);
+
+/* DirichletLayer.compute_uncertainty, 'exp' evidence (AFSD/thumos14/BDNet.py:544-556): unct[m] = K / sum_k(exp(clamp(
+ * logit[m,k], -10, 10)) + 1).  logit [M,K] contiguous. */
+OTAL_API int otal_dirichlet_uncertainty(const float* logit, float* unct, long long M, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,9 +102,12 @@ SIGNATURES = {
     "otal_msl_backward": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "otal_groupnorm_relu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                        c_float, c_int, c_void_p]),
+                                        c_float, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
     "otal_groupnorm_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                        c_int, c_int, c_int, c_int, c_void_p]),
+                                        c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
+    "otal_make_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                   c_void_p]),
+    "otal_dirichlet_uncertainty": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "otal_ncdhw_to_ndhwc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

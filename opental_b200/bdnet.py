@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from . import ops
 from .backbone import I3DBackbone
 from .headconv import HeadConvStore, head_conv
-from .prop_pooling import BoundaryMaxPooling
+from .prop_pooling import BoundaryMaxPooling, BoundaryMaxPoolingFunction
 
 LAYER_NUM = 6        # BDNet.py:20
 CONV_CHANNELS = 512  # BDNet.py:21
@@ -75,8 +75,13 @@ class GroupNormReLU(nn.GroupNorm):
     """nn.GroupNorm(32, C) fused with the ReLU that follows it everywhere in CoarsePyramid (BDNet.py:72-73 etc.): one
     native launch (opental_b200/csrc/gn.cu).  Same parameters / state_dict keys as nn.GroupNorm."""
 
-    def forward(self, x):
-        return ops.groupnorm_relu(x, self.weight, self.bias, self.num_groups, self.eps, relu=True)
+    def forward(self, x, segments=None):
+        return ops.groupnorm_relu(x, self.weight, self.bias, self.num_groups, self.eps, relu=True, segments=segments)
+
+
+def _conv_gn(seq, x, segments=None):
+    """Apply a `_unit_gn` block; `segments` = per-level column ranges when x holds several pyramid levels side by side."""
+    return seq[1](seq[0](x), segments)
 
 
 def _unit_gn(unit, channels):
@@ -96,7 +101,10 @@ class ScaleExp(nn.Module):
 
 
 class ProposalBranch(nn.Module):
-    """BDNet.py:64-113.  forward takes the already pooled frame-level feature (shared by both branches)."""
+    """BDNet.py:64-113, level-batched: `feature` [B,C,P] holds all pyramid levels side by side (P = 126 priors), every
+    conv here is 1x1, GroupNorm statistics stay per level (`level_segments`), `segments` are windows into that
+    concatenated axis (already clamped to their level).  Takes the pooled frame-level feature, which both branches
+    share (the reference pools it twice with identical arguments, BDNet.py:109 called from :386 and :388)."""
 
     def __init__(self, in_channels, proposal_channels):
         super().__init__()
@@ -106,13 +114,37 @@ class ProposalBranch(nn.Module):
         self.roi_conv = _unit_gn(Unit1D(proposal_channels, proposal_channels, 1), proposal_channels)
         self.proposal_conv = _unit_gn(Unit1D(proposal_channels * 4, in_channels, 1), in_channels)
 
-    def forward(self, feature, pooled_frame_feature, segments):
-        fm_short = self.cur_point_conv(feature)
-        feature = self.lr_conv(feature)
+    def forward(self, feature, pooled_frame_feature, segments, level_segments=None):
+        fm_short = _conv_gn(self.cur_point_conv, feature, level_segments)
+        feature = _conv_gn(self.lr_conv, feature, level_segments)
         prop_feature = self.boundary_max_pooling(feature, segments)
-        prop_roi_feature = self.roi_conv(pooled_frame_feature)
+        prop_roi_feature = _conv_gn(self.roi_conv, pooled_frame_feature, level_segments)
         prop_feature = torch.cat([prop_roi_feature, prop_feature, fm_short], dim=1)
-        return self.proposal_conv(prop_feature), feature
+        return _conv_gn(self.proposal_conv, prop_feature, level_segments), feature
+
+
+class _FramePoolFn(torch.autograd.Function):
+    """BoundaryMaxPooling of the frame-level feature for the windows of ALL levels in one launch.  In the parity mode
+    that reproduces the reference backward's tscale quirk (boundary_max_pooling_kernel.cu:121) the quirk depends on the
+    per-level call shape (K = t of the level), so that mode falls back to one backward launch per level."""
+
+    @staticmethod
+    def forward(ctx, frame, frame_segments, level_segments):
+        ctx.save_for_backward(frame, frame_segments)
+        ctx.level_segments = level_segments
+        return ops.bmp_forward(frame, frame_segments)
+
+    @staticmethod
+    def backward(ctx, g):
+        frame, fs = ctx.saved_tensors
+        g = g.contiguous()
+        if not BoundaryMaxPoolingFunction.compat_tscale_bug:
+            return ops.bmp_backward(g, frame, fs, False), None, None
+        total = None
+        for off, t in ctx.level_segments:
+            gi = ops.bmp_backward(g[:, :, off:off + t].contiguous(), frame, fs[:, off:off + t].contiguous(), True)
+            total = gi if total is None else total + gi
+        return total, None, None
 
 
 class CoarsePyramid(nn.Module):
@@ -160,7 +192,22 @@ class CoarsePyramid(nn.Module):
         for _ in range(LAYER_NUM):
             self.priors.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32).view(-1, 1))
             t = t // 2
-        self._prior_cache = {}
+        # Level-batched layouts.  The towers / heads / proposal branches share their weights across the 6 levels
+        # (BDNet.py:333-412), so they run ONCE on all levels laid side by side along T:
+        #   "sep" layout  [B,C,S]: [0 | L0 | 0 | L1 | 0 | ... | L5 | 0 ...] — one zero column between levels gives every
+        #                 k=3 "same" convolution its per-level zero padding; S is padded to a multiple of 8
+        #   "cat" layout  [B,C,P]: the 126 priors back to back (1x1 convs, pooling windows, outputs)
+        self.level_t = [feat_t >> i for i in range(LAYER_NUM)]
+        self.num_priors = sum(self.level_t)
+        sep_off, pos = [], 1
+        for t in self.level_t:
+            sep_off.append(pos)
+            pos += t + 1
+        self.sep_len = (pos + 7) // 8 * 8
+        self.sep_segments = tuple(zip(sep_off, self.level_t))
+        cat_off = [sum(self.level_t[:i]) for i in range(LAYER_NUM)]
+        self.cat_segments = tuple(zip(cat_off, self.level_t))
+        self._tables = {}
         # every head conv on the tensor-core kernels, weights re-homed into one packed flat buffer (headconv.py);
         # native_convs=False keeps torch's library convs (debugging aid, never selected implicitly)
         self.conv_store = None
@@ -172,30 +219,31 @@ class CoarsePyramid(nn.Module):
                 elif isinstance(m, Unit3DValid):
                     m._native = (self.conv_store, self.conv_store.register(m.conv3d.weight, m.conv3d.bias, "valid3d"))
 
-    def _priors_on(self, device):
-        if device not in self._prior_cache:
-            self._prior_cache[device] = [p.to(device) for p in self.priors]
-        return self._prior_cache[device]
+    def _tables_on(self, device):
+        """Per-prior lookup tables on `device`: prior position, level length, level offset (cat layout), level id, and
+        the column of every prior in the sep layout."""
+        if device not in self._tables:
+            lens = torch.tensor([t for t in self.level_t for _ in range(t)], dtype=torch.int32)
+            offs = torch.tensor([o for (o, t) in self.cat_segments for _ in range(t)], dtype=torch.int32)
+            lid = torch.tensor([i for i, t in enumerate(self.level_t) for _ in range(t)], dtype=torch.long)
+            sep = torch.cat([torch.arange(o, o + t) for o, t in self.sep_segments])
+            self._tables[device] = dict(priors=[p.to(device) for p in self.priors],
+                                        prior=torch.cat(self.priors, 0).to(device), level_len=lens.to(device),
+                                        level_off=offs.to(device), level_id=lid.to(device), sep_idx=sep.to(device))
+        return self._tables[device]
 
-    def _segments(self, loc, prior, t):
-        """Window generation under no_grad (BDNet.py:355-384); torch.round is half-to-even."""
-        with torch.no_grad():
-            B = loc.shape[0]
-            seg = loc / self.frame_num * t
-            pri = prior.view(1, t, 1).expand(B, t, 1)
-            centre = torch.round(pri * t - 0.5)
-            plen = seg[:, :, :1] + seg[:, :, 1:]
-            inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
-            ls, rs = centre - seg[:, :, :1], centre + seg[:, :, 1:]
-            segments = torch.cat([torch.round(ls - outl), torch.round(ls + inl),
-                                  torch.round(rs - inl), torch.round(rs + outl)], dim=-1)
-            dl = pri * self.frame_num - loc[:, :, :1]
-            dr = pri * self.frame_num + loc[:, :, 1:]
-            plen = dr - dl + 1.0
-            inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
-            frame_segments = torch.cat([torch.round(dl - outl), torch.round(dl + inl),
-                                        torch.round(dr - inl), torch.round(dr + outl)], dim=-1)
-        return segments.contiguous(), frame_segments.contiguous()
+    def _segments(self, loc, tb):
+        """Window generation (no_grad, BDNet.py:355-384) for all levels: one native launch."""
+        _, seg_cat, frame_seg = ops.make_segments(loc, tb["prior"].view(-1), tb["level_len"], tb["level_off"], self.frame_num)
+        return seg_cat, frame_seg
+
+    def _forced(self, forced_segments):
+        """Per-level (segments, frame_segments) as the reference produces them -> the level-concatenated form."""
+        segs, fsegs = [], []
+        for (seg, fseg), (off, t) in zip(forced_segments, self.cat_segments):
+            segs.append(torch.trunc(seg).clamp(0, t - 1) + off)
+            fsegs.append(fseg)
+        return torch.cat(segs, 1).contiguous(), torch.cat(fsegs, 1).contiguous()
 
     def forward(self, feat_dict, ssl=False, get_feat=False, forced_segments=None):
         if get_feat:
@@ -205,6 +253,8 @@ class CoarsePyramid(nn.Module):
             self.conv_store.prepare(x1.device)
         B = x1.size(0)
         K = self.num_classes
+        tb = self._tables_on(x1.device)
+        # ---- pyramid (BDNet.py:311-322) and frame-level feature (:324-331)
         feats = []
         for i, conv in enumerate(self.pyramids):
             if i == 0:
@@ -217,49 +267,59 @@ class CoarsePyramid(nn.Module):
             feats.append(x)
         frame = F.interpolate(feats[0].unsqueeze(-1), [self.frame_num, 1]).squeeze(-1)
         frame = self.deconv(frame).contiguous()
-        trip = [frame.clone()] if ssl else None
         start = frame[:, :256].permute(0, 2, 1).contiguous()
         end = frame[:, 256:].permute(0, 2, 1).contiguous()
 
-        priors = self._priors_on(x1.device)
-        locs, confs, acts, centers, plocs, pconfs, pacts = [], [], [], [], [], [], []
-        extra = {}
-        for i, feat in enumerate(feats):
-            loc_feat = self.loc_tower(feat)
-            conf_feat = self.conf_tower(feat)
-            t = feat.size(2)
-            loc = self.loc_heads[i](self.loc_head(loc_feat)).view(B, 2, -1).permute(0, 2, 1).contiguous()
-            locs.append(loc)
-            confs.append(self.conf_head(conf_feat).view(B, K, -1).permute(0, 2, 1).contiguous())
-            if self.os_head:
-                acts.append(self.actionness_head(conf_feat).view(B, 1, -1).permute(0, 2, 1).contiguous())
-            if forced_segments is not None:
-                segments, frame_segments = forced_segments[i]
-            else:
-                segments, frame_segments = self._segments(loc, priors[i], t)
-            pooled_frame = self.boundary_max_pooling(frame, frame_segments)      # shared by both branches (F5)
-            loc_prop, loc_lr = self.loc_proposal_branch(loc_feat, pooled_frame, segments)
-            conf_prop, conf_lr = self.conf_proposal_branch(conf_feat, pooled_frame, segments)
-            if i == 0:
-                if ssl:
-                    trip.extend([loc_lr.clone(), conf_lr.clone()])
-                    return trip
-                nd = loc_lr.size(1) // 2
-                extra = dict(start_loc_prop=loc_lr[:, :nd].permute(0, 2, 1).contiguous(),
-                             end_loc_prop=loc_lr[:, nd:].permute(0, 2, 1).contiguous(),
-                             start_conf_prop=conf_lr[:, :nd].permute(0, 2, 1).contiguous(),
-                             end_conf_prop=conf_lr[:, nd:].permute(0, 2, 1).contiguous())
-            plocs.append(self.prop_loc_head(loc_prop).view(B, 2, -1).permute(0, 2, 1).contiguous())
-            pconfs.append(self.prop_conf_head(conf_prop).view(B, K, -1).permute(0, 2, 1).contiguous())
-            if self.os_head:
-                pacts.append(self.prop_actionness_head(conf_prop).view(B, 1, -1).permute(0, 2, 1).contiguous())
-            centers.append(self.center_head(loc_prop).view(B, 1, -1).permute(0, 2, 1).contiguous())
-        out = dict(loc=torch.cat(locs, 1), conf=torch.cat(confs, 1), priors=torch.cat(priors, 0),
-                   prop_loc=torch.cat(plocs, 1), prop_conf=torch.cat(pconfs, 1), center=torch.cat(centers, 1),
-                   start=start, end=end, **extra,
-                   act=torch.cat(acts, 1) if self.os_head else None,
-                   prop_act=torch.cat(pacts, 1) if self.os_head else None)
-        return out
+        # ---- towers and coarse heads on all levels at once (sep layout), BDNet.py:333-353
+        z = feats[0].new_zeros(B, feats[0].shape[1], 1)
+        parts = [z]
+        for f in feats:
+            parts += [f, z]
+        tail = self.sep_len - (self.num_priors + LAYER_NUM + 1)
+        if tail:
+            parts.append(feats[0].new_zeros(B, feats[0].shape[1], tail))
+        x_sep = torch.cat(parts, dim=2)
+        loc_feat, conf_feat = x_sep, x_sep
+        for blk in self.loc_tower:
+            loc_feat = _conv_gn(blk, loc_feat, self.sep_segments)
+        for blk in self.conf_tower:
+            conf_feat = _conv_gn(blk, conf_feat, self.sep_segments)
+        sep_idx = tb["sep_idx"]
+
+        def to_out(y):                                  # [B,c,P] -> the reference's [B,P,c]
+            return y.permute(0, 2, 1).contiguous()
+
+        scale = torch.cat([h.scale for h in self.loc_heads])[tb["level_id"]]            # ScaleExp of the prior's level
+        loc = to_out(torch.exp(self.loc_head(loc_feat).index_select(2, sep_idx) * scale))
+        conf = to_out(self.conf_head(conf_feat).index_select(2, sep_idx))
+        act = to_out(self.actionness_head(conf_feat).index_select(2, sep_idx)) if self.os_head else None
+
+        # ---- proposal windows and the two proposal branches (cat layout), BDNet.py:355-397
+        if forced_segments is not None:
+            segments, frame_segments = self._forced(forced_segments)
+        else:
+            segments, frame_segments = self._segments(loc, tb)
+        pooled_frame = _FramePoolFn.apply(frame, frame_segments, self.cat_segments)     # shared by both branches (F5)
+        loc_cat = loc_feat.index_select(2, sep_idx)
+        conf_cat = conf_feat.index_select(2, sep_idx)
+        loc_prop, loc_lr = self.loc_proposal_branch(loc_cat, pooled_frame, segments, self.cat_segments)
+        conf_prop, conf_lr = self.conf_proposal_branch(conf_cat, pooled_frame, segments, self.cat_segments)
+        t0 = self.level_t[0]
+        if ssl:
+            return [frame.clone(), loc_lr[:, :, :t0].clone(), conf_lr[:, :, :t0].clone()]
+        nd = loc_lr.size(1) // 2
+        extra = dict(start_loc_prop=loc_lr[:, :nd, :t0].permute(0, 2, 1).contiguous(),
+                     end_loc_prop=loc_lr[:, nd:, :t0].permute(0, 2, 1).contiguous(),
+                     start_conf_prop=conf_lr[:, :nd, :t0].permute(0, 2, 1).contiguous(),
+                     end_conf_prop=conf_lr[:, nd:, :t0].permute(0, 2, 1).contiguous())
+        # ---- refined heads (BDNet.py:399-412): 1x1 heads on the cat layout; the k=3 centre head needs the separators
+        prop_loc = to_out(self.prop_loc_head(loc_prop))
+        prop_conf = to_out(self.prop_conf_head(conf_prop))
+        prop_act = to_out(self.prop_actionness_head(conf_prop)) if self.os_head else None
+        lp_sep = loc_prop.new_zeros(B, loc_prop.shape[1], self.sep_len).index_copy(2, sep_idx, loc_prop)
+        center = to_out(self.center_head(lp_sep).index_select(2, sep_idx))
+        return dict(loc=loc, conf=conf, priors=tb["prior"], prop_loc=prop_loc, prop_conf=prop_conf, center=center,
+                    start=start, end=end, **extra, act=act, prop_act=prop_act)
 
 
 class DirichletLayer(nn.Module):
@@ -369,6 +429,10 @@ class BDNet(nn.Module):
             return anchor, positive, negative
         out = self.coarse_pyramid_detection(feat_dict, get_feat=get_feat, forced_segments=forced_segments)
         if self.use_edl:
-            out["unct"] = self.out_layer.compute_uncertainty(out["conf"])
-            out["prop_unct"] = self.out_layer.compute_uncertainty(out["prop_conf"])
+            if self.evidence == "exp":        # native kernel (no autograd graph: these are inference-side scores)
+                out["unct"] = ops.dirichlet_uncertainty(out["conf"])
+                out["prop_unct"] = ops.dirichlet_uncertainty(out["prop_conf"])
+            else:
+                out["unct"] = self.out_layer.compute_uncertainty(out["conf"])
+                out["prop_unct"] = self.out_layer.compute_uncertainty(out["prop_conf"])
         return out

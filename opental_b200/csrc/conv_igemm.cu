@@ -384,6 +384,18 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         }
         p.BN = best; p.n_blocks = (p.Cout + best - 1) / best;
     }
+    // Small problems (the 1-D head: 16..512 positions, 512 channels) are bound by ONE SM streaming its weight block
+    // from L2 (~42 B/clk per SM): narrow the N block so that more CTAs share the weight traffic.
+    {
+        const int m_tiles = p.N * p.tilesT * p.tilesH * p.tilesW;
+        while (p.BN > 64 && p.BN % 64 == 0 && m_tiles * p.n_blocks < num_sms() / 2) {
+            p.BN -= 64;
+            p.n_blocks = (p.Cout + p.BN - 1) / p.BN;
+        }
+        if (p.BN > 64 && p.BN % 64 != 0 && p.Cout > 64 && m_tiles * p.n_blocks < num_sms() / 2) {
+            p.BN = 64; p.n_blocks = (p.Cout + 63) / 64;
+        }
+    }
     p.kchunks = (L.w_k + kChunkK - 1) / kChunkK;
     p.store_bf16 = L.y_hi != nullptr;
     p.total_tiles = p.N * p.tilesT * p.tilesH * p.tilesW * p.n_blocks;

@@ -259,6 +259,12 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
         p.BN = best; p.n_blocks = (p.Cin + best - 1) / best;
     }
     const int ntaps = p.kt * p.kh * p.kw;
+    // short reductions (the 1-D head: K = 16..512 positions) cannot be split along K: narrow the N block instead so
+    // that enough CTAs share the epilogue's reductions into dW
+    while (p.BN > 64 && p.BN % 64 == 0 && (long long)ntaps * p.m_blocks * p.n_blocks * p.ktiles < wg_num_sms()) {
+        p.BN -= 64;
+        p.n_blocks = (p.Cin + p.BN - 1) / p.BN;
+    }
     const int base_items = ntaps * p.m_blocks * p.n_blocks;
     int ks = (2 * wg_num_sms() + base_items - 1) / base_items;       // at least two waves of work items
     {

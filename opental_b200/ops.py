@@ -521,36 +521,74 @@ def msl_backward(ws: torch.Tensor, grad_losses: torch.Tensor, B: int, P: int, K:
 # ----------------------------------------------------------------------------------------------------------
 # GroupNorm + ReLU
 # ----------------------------------------------------------------------------------------------------------
+def _seg_arrays(segments):
+    if not segments:
+        return 0, None, None
+    n = len(segments)
+    return n, (ctypes.c_int * n)(*[int(o) for o, _ in segments]), (ctypes.c_int * n)(*[int(l) for _, l in segments])
+
+
 class _GroupNormReLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups: int, eps: float, relu: bool):
+    def forward(ctx, x, gamma, beta, groups: int, eps: float, relu: bool, segments):
         _require_cuda(x, gamma, beta)
         x = x.contiguous()
         assert x.dtype == torch.float32 and x.dim() == 3
         B, C, T = x.shape
         y = torch.empty_like(x)
-        stats = torch.empty(2, B * groups, dtype=torch.float32, device=x.device)
+        nseg, so, sl = _seg_arrays(segments)
+        stats = torch.empty(2, B * groups * max(nseg, 1), dtype=torch.float32, device=x.device)
         _lib.call("otal_groupnorm_relu_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), stats[0].data_ptr(),
-                  stats[1].data_ptr(), B, C, T, groups, eps, int(relu), _stream())
+                  stats[1].data_ptr(), B, C, T, groups, eps, int(relu), nseg, so, sl, _stream())
         ctx.save_for_backward(x, gamma, beta, stats)
-        ctx.cfg = (groups, relu)
+        ctx.cfg = (groups, relu, segments)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, gamma, beta, stats = ctx.saved_tensors
-        groups, relu = ctx.cfg
+        groups, relu, segments = ctx.cfg
         B, C, T = x.shape
         gy = gy.contiguous()
         gx = torch.empty_like(x)
         dgb = torch.empty(B, 2, C, dtype=torch.float32, device=x.device)
+        nseg, so, sl = _seg_arrays(segments)
         _lib.call("otal_groupnorm_relu_bwd", gy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats[0].data_ptr(),
-                  stats[1].data_ptr(), gx.data_ptr(), dgb.data_ptr(), B, C, T, groups, int(relu), _stream())
+                  stats[1].data_ptr(), gx.data_ptr(), dgb.data_ptr(), B, C, T, groups, int(relu), nseg, so, sl, _stream())
         d = dgb.sum(0) if B > 1 else dgb[0]
-        return gx, d[0], d[1], None, None, None
+        return gx, d[0], d[1], None, None, None, None
 
 
 def groupnorm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32, eps: float = 1e-5,
-                   relu: bool = True) -> torch.Tensor:
-    """relu(group_norm(x)) on [B,C,T] fp32 in one launch (forward) / one launch + a [B,2,C] batch reduction (backward)."""
-    return _GroupNormReLUFn.apply(x, gamma, beta, groups, eps, relu)
+                   relu: bool = True, segments=None) -> torch.Tensor:
+    """relu(group_norm(x)) on [B,C,T] fp32 in one launch (forward) / one launch + a [B,2,C] batch reduction (backward).
+    segments: optional tuple of (offset, length) column ranges normalised independently; other columns become 0."""
+    return _GroupNormReLUFn.apply(x, gamma, beta, groups, eps, relu, tuple(segments) if segments else None)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# detection-head helpers
+# ----------------------------------------------------------------------------------------------------------
+def make_segments(loc: torch.Tensor, prior: torch.Tensor, level_len: torch.Tensor, level_off: torch.Tensor, frame_num: float,
+                  want_level: bool = False):
+    """(seg_level | None, seg_concat, frame_seg), each [B,P,4] — see otal_make_segments in include/opental_b200.h."""
+    _require_cuda(loc, prior, level_len, level_off)
+    loc = loc.detach().contiguous()
+    B, P, _ = loc.shape
+    assert loc.dtype == torch.float32 and prior.numel() == P and level_len.dtype == torch.int32 and level_off.dtype == torch.int32
+    seg_c = torch.empty(B, P, 4, dtype=torch.float32, device=loc.device)
+    fseg = torch.empty_like(seg_c)
+    seg_l = torch.empty_like(seg_c) if want_level else None
+    _lib.call("otal_make_segments", loc.data_ptr(), prior.data_ptr(), level_len.data_ptr(), level_off.data_ptr(), _ptr(seg_l),
+              seg_c.data_ptr(), fseg.data_ptr(), B, P, float(frame_num), _stream())
+    return seg_l, seg_c, fseg
+
+
+def dirichlet_uncertainty(logit: torch.Tensor) -> torch.Tensor:
+    """K / sum(exp(clamp(logit, -10, 10)) + 1) over the last dim (no gradient: an inference-side score)."""
+    _require_cuda(logit)
+    x = logit.detach().contiguous().float()
+    K = x.shape[-1]
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    _lib.call("otal_dirichlet_uncertainty", x.data_ptr(), out.data_ptr(), x.numel() // K, K, _stream())
+    return out

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(8, 512, 64), (2, 1024, 32), (8, 512, 256), (3, 512, 2), (1, 1024, 4), (2, 64, 7), (1, 512, 2048)]
+SHAPES = [(8, 512, 64), (2, 1024, 32), (8, 512, 256), (3, 512, 2), (1, 1024, 4), (2, 64, 7), (1, 512, 1024)]
 
 
 @pytest.mark.parametrize("B,C,T", SHAPES)
