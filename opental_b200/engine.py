@@ -58,6 +58,40 @@ class FlatParams:
                 p.grad = view
 
 
+class GradReducer:
+    """Data-parallel exchange step: sum the flat gradient buffers over the ranks of `process_group` (NCCL over NVLink on
+    the GPUs; the same host logic runs over gloo in the CPU tests).  The 1/world scaling is NOT applied here — it is
+    folded into the optimizer kernel (`grad_scale`)."""
+
+    def __init__(self, buffers: list[torch.Tensor], process_group=None):
+        self.buffers = buffers
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self._work = []
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / self.world
+
+    def launch(self, which=None) -> None:
+        """Start the all-reduce of buffers[i] for i in `which` (default: all) without waiting."""
+        if self.world == 1:
+            return
+        for i in (range(len(self.buffers)) if which is None else which):
+            self._work.append(dist.all_reduce(self.buffers[i], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def wait(self) -> None:
+        for w in self._work:
+            w.wait()
+        self._work = []
+
+
+def shard_indices(num_items: int, rank: int, world: int) -> range:
+    """Clip indices of `rank`: contiguous, disjoint, equal-sized shards (the remainder is dropped like drop_last)."""
+    per = num_items // world
+    return range(rank * per, (rank + 1) * per)
+
+
 class Trainer:
     def __init__(self, net: BDNet, criterion: MultiSegmentLoss, *, lr=1e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  lw=1.0, cw=10.0, ctw=1.0, actw=1.0, process_group=None):
@@ -86,8 +120,9 @@ class Trainer:
         self.head = FlatParams(head)
         self.groups.append((self.head.w, self.head.g))
         self.state = [dict(m=torch.zeros_like(w), v=torch.zeros_like(w)) for w, _ in self.groups]
+        self.reducer = GradReducer([g for _, g in self.groups], process_group)
         self.step_count = 0
-        self._head_work = None
+        self._head_launched = False
         self._graph = None
         self._static = None
         bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
@@ -98,7 +133,8 @@ class Trainer:
             self._launch_head_allreduce()
 
     def _launch_head_allreduce(self) -> None:
-        self._head_work = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for _, g in self.groups[1:]]
+        self.reducer.launch(range(1, len(self.groups)))        # head buffers: complete once the backbone backward starts
+        self._head_launched = True
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
@@ -171,16 +207,15 @@ class Trainer:
             self.zero_grad()
             cost, losses, ls, le = self.forward_backward(clips, targets, scores)
         if self.world > 1:
-            if self._head_work is None:
+            if not self._head_launched:
                 self._launch_head_allreduce()
-            dist.all_reduce(self.bb_g, op=dist.ReduceOp.SUM, group=self.pg)
-            for wk in self._head_work:
-                wk.wait()
-            self._head_work = None
+            self.reducer.launch([0])
+            self.reducer.wait()
+            self._head_launched = False
         self.step_count += 1
         for (w, g), st in zip(self.groups, self.state):
             ops.adam_step(w, g, st["m"], st["v"], lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
-                          grad_scale=1.0 / self.world, step=self.step_count)
+                          grad_scale=self.reducer.grad_scale, step=self.step_count)
         return cost, losses, ls, le
 
 
