@@ -111,7 +111,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (addresses, UMMA /
+    // TMA descriptors, barrier addresses) in uniform registers; only the issue instructions sit behind elect_one().
+    // (With the loops inside `if (lane == 0)` every tcgen05.mma paid a ~15-instruction R2UR waterfall: issue-bound at N <= 64.)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const bool split = p.nsplit == 3;
 
@@ -136,27 +139,27 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     const int kiters = ntaps * p.kchunks;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nb = tile % p.n_blocks;
-                int m = tile / p.n_blocks;
-                const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
-                const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
-                const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
-                const int n = m;
-                for (int tap = 0; tap < ntaps; ++tap) {
-                    const int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
-                    int qt, qh, qw, rt, rh, rw;
-                    split_parity(dt - p.pt, p.st, qt, rt);
-                    split_parity(dh - p.ph, p.sh, qh, rh);
-                    split_parity(dw - p.pw, p.sw, qw, rw);
-                    const int mi = rt * 4 + rh * 2 + rw;
-                    const CUtensorMap* mapA_hi = &maps.A_hi[mi];
-                    const CUtensorMap* mapA_lo = &maps.A_lo[mi];
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ------------------------------------------------------------------ TMA producer (whole warp runs the loop)
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nb = tile % p.n_blocks;
+            int m = tile / p.n_blocks;
+            const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
+            const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
+            const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
+            const int n = m;
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
+                int qt, qh, qw, rt, rh, rw;
+                split_parity(dt - p.pt, p.st, qt, rt);
+                split_parity(dh - p.ph, p.sh, qh, rh);
+                split_parity(dw - p.pw, p.sw, qw, rw);
+                const int mi = rt * 4 + rh * 2 + rw;
+                const CUtensorMap* mapA_hi = &maps.A_hi[mi];
+                const CUtensorMap* mapA_lo = &maps.A_lo[mi];
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
                         unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
                         unsigned char* sB = sA + L.a_bytes;
                         mbar_expect_tx(&full_bar[stage], L.stage_bytes);
@@ -178,48 +181,54 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         if (split) {
                             tma_load_5d(mapA_lo, &full_bar[stage], sA + kATileBytes, c0, w0 + qw, h0 + qh, t0 + qt, n);
                         }
-                        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, 0, p.b_mn ? 1 : 0);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop)
+        const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, 0, p.b_mn ? 1 : 0);
+        // descriptor templates: everything but the start address.  K-major: 32 bytes per K=16 step inside the swizzled
+        // row.  MN-major B (dgrad): 16 K rows = 2048 bytes per step, LBO = 8 KB between 64-wide N boxes, SBO = 1 KB.
+        const uint64_t tmpl_k = umma_smem_desc_sw128(0, 16, 1024);
+        const uint64_t tmpl_b = p.b_mn ? umma_smem_desc_sw128(0, 8192, 1024) : tmpl_k;
+        const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+            for (int it = 0; it < kiters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
-                for (int it = 0; it < kiters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
-                    const uint32_t sB = sA + L.a_bytes;
+                const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
+                const uint32_t sB = sA + L.a_bytes;
+                const uint64_t a_hi0 = tmpl_k + (uint64_t)(sA >> 4);
+                const uint64_t a_lo0 = tmpl_k + (uint64_t)((sA + kATileBytes) >> 4);
+                const uint64_t b_hi0 = tmpl_b + (uint64_t)(sB >> 4);
+                const uint64_t b_lo0 = tmpl_b + (uint64_t)((sB + b_plane) >> 4);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t a_hi = umma_smem_desc_sw128(sA + k * 32, 16, 1024);
-                        // K-major B: 32 bytes per K=16 step inside the swizzled row.  MN-major B (dgrad): 16 K rows =
-                        // 2048 bytes per step, LBO = 8 KB between 64-wide N boxes, SBO = 1 KB between 8-row groups.
-                        const uint64_t b_hi = p.b_mn ? umma_smem_desc_sw128(sB + k * 2048, 8192, 1024)
-                                                     : umma_smem_desc_sw128(sB + k * 32, 16, 1024);
+                        const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2);
+                        const uint64_t b_hi = b_hi0 + (uint64_t)(k * b_step);
                         umma_f16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
                         if (split) {
-                            const uint64_t a_lo = umma_smem_desc_sw128(sA + kATileBytes + k * 32, 16, 1024);
-                            const uint64_t b_lo = p.b_mn ? umma_smem_desc_sw128(sB + b_plane + k * 2048, 8192, 1024)
-                                                         : umma_smem_desc_sw128(sB + b_plane + k * 32, 16, 1024);
-                            umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-                            umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                            umma_f16(d_tmem, a_lo0 + (uint64_t)(k * 2), b_hi, idesc, 1);
+                            umma_f16(d_tmem, a_hi, b_lo0 + (uint64_t)(k * b_step), idesc, 1);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(&tmem_full[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (128 threads)

@@ -35,6 +35,8 @@ struct WgParams {
     int kt, kh, kw, pt, ph, pw, st, sh, sw;
     int tT, tH, tW, tilesT, tilesH, tilesW;
     int BN, n_blocks, m_blocks, ksplit, ktiles;   // ktiles = N * tilesT*tilesH*tilesW
+    int G, ngroups, cstride;  // taps per work item (they share the D tile in shared memory), number of tap groups, TMEM
+                              // column stride between the accumulators of consecutive taps (BN rounded up to 32)
     int nsplit, nstages;
     int total_items;
     float* dw;
@@ -50,12 +52,13 @@ __device__ __forceinline__ void wg_split_parity(int d, int s, int& q, int& par) 
     else { par = d & 1; q = (d - par) >> 1; }
 }
 
-struct WgSmem { uint32_t a_bytes, b_bytes, stage_bytes, bar_off, total; };
-__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages) {
+struct WgSmem { uint32_t a_bytes, b_bytes, tap_bytes, stage_bytes, bar_off, total; };
+__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages, int G) {
     WgSmem s;
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
     s.a_bytes = 2u * kWgBox * planes;                         // 128 rows of Cout = 2 boxes
-    s.b_bytes = (uint32_t)((BN + 63) / 64) * kWgBox * planes;
+    s.tap_bytes = (uint32_t)((BN + 63) / 64) * kWgBox * planes;   // X boxes of ONE tap
+    s.b_bytes = s.tap_bytes * (uint32_t)G;
     s.stage_bytes = s.a_bytes + s.b_bytes;
     s.bar_off = s.stage_bytes * (uint32_t)nstages;
     s.total = s.bar_off + 256;
@@ -66,14 +69,14 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages);
+    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages, p.G);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + kWgMaxStages;
     uint64_t* tmem_full = empty_bar + kWgMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (see conv_igemm.cu)
     const int lane = threadIdx.x & 31;
     const bool split = p.nsplit == 3;
     const uint32_t planes = split ? 2u : 1u;
@@ -94,126 +97,159 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // item -> (tap, nb, mb, ks), tap fastest: the CTAs that run concurrently work on the SAME K chunk (range of output
-    // positions) for different taps / channel blocks, so the chunk of D and X is fetched from HBM once and re-read by
-    // the other taps from L2.  (With ks fastest every tap streamed the whole D and X tensors from HBM again: taps x
-    // (|D| + |X|) of DRAM traffic, e.g. 16 GB for Conv3d_2c at batch 8.)
-    auto decode = [&](int item, int& tap, int& mb, int& nb, int& k_begin, int& k_end) {
-        const int ntaps_ = p.kt * p.kh * p.kw;
-        tap = item % ntaps_; item /= ntaps_;
+    // item -> (tap group, nb, mb, ks), tap group fastest: the CTAs that run concurrently work on the SAME K chunk (range
+    // of output positions) for different taps / channel blocks, so the chunk of D and X is fetched from HBM once and
+    // re-read by the other taps from L2.  (With ks fastest every tap streamed the whole D and X tensors from HBM again:
+    // taps x (|D| + |X|) of DRAM traffic, e.g. 16 GB for Conv3d_2c at batch 8.)
+    // A work item covers G consecutive taps: the D tile of a stage is loaded once and multiplied against the G shifted X
+    // tiles into G accumulators (TMEM columns [j*cstride, j*cstride + BN)), which cuts the L2->SMEM operand traffic per tap from
+    // |D tile| + |X tile| to |D tile|/G + |X tile| — these kernels are bound by that traffic (~43 B/clk/SM), not by the MMA.
+    const int ntaps_ = p.kt * p.kh * p.kw;
+    auto decode = [&](int item, int& tap0, int& gsz, int& mb, int& nb, int& k_begin, int& k_end) {
+        const int tg = item % p.ngroups; item /= p.ngroups;
         nb = item % p.n_blocks; item /= p.n_blocks;
         mb = item % p.m_blocks; item /= p.m_blocks;
         const int ks = item;
+        tap0 = tg * p.G;
+        gsz = min(p.G, ntaps_ - tap0);
         const long long kt_ = p.ktiles;
         k_begin = (int)(kt_ * ks / p.ksplit);
         k_end = (int)(kt_ * (ks + 1) / p.ksplit);
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int tap, mb, nb, k0, k1;
-                decode(item, tap, mb, nb, k0, k1);
+        // ---- TMA producer: the whole warp runs the loop (uniform registers), one elected lane issues
+        int stage = 0; uint32_t phase = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int tap0, gsz, mb, nb, k0, k1;
+            decode(item, tap0, gsz, mb, nb, k0, k1);
+            int qt[4], qh[4], qw[4], mi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int tap = min(tap0 + j, ntaps_ - 1);
                 const int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
-                int qt, qh, qw, rt, rh, rw;
-                wg_split_parity(dt - p.pt, p.st, qt, rt);
-                wg_split_parity(dh - p.ph, p.sh, qh, rh);
-                wg_split_parity(dw - p.pw, p.sw, qw, rw);
-                const int mi = rt * 4 + rh * 2 + rw;
-                const int m_valid = min(128, p.Cout - mb * 128);
-                const int a_boxes = m_valid > 64 ? 2 : 1;     // rows 64..127 of a short block are never read back
-                const uint32_t tx = (uint32_t)(a_boxes + nboxes_b) * kWgBox * planes;
-                for (int k = k0; k < k1; ++k) {
-                    int m = k;
-                    const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
-                    const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
-                    const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
-                    const int n = m;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                int rt, rh, rw;
+                wg_split_parity(dt - p.pt, p.st, qt[j], rt);
+                wg_split_parity(dh - p.ph, p.sh, qh[j], rh);
+                wg_split_parity(dw - p.pw, p.sw, qw[j], rw);
+                mi[j] = rt * 4 + rh * 2 + rw;
+            }
+            const int m_valid = min(128, p.Cout - mb * 128);
+            const int a_boxes = m_valid > 64 ? 2 : 1;     // rows 64..127 of a short block are never read back
+            const uint32_t tx = (uint32_t)(a_boxes + gsz * nboxes_b) * kWgBox * planes;
+            for (int k = k0; k < k1; ++k) {
+                int m = k;
+                const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
+                const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
+                const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
+                const int n = m;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
-                    unsigned char* sB = sA + L.a_bytes;
                     mbar_expect_tx(&full_bar[stage], tx);
                     for (int j = 0; j < a_boxes; ++j) {
                         tma_load_5d(&maps.D_hi, &full_bar[stage], sA + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n);
                         if (split)
                             tma_load_5d(&maps.D_lo, &full_bar[stage], sA + 2 * kWgBox + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n);
                     }
-                    for (int j = 0; j < nboxes_b; ++j) {
-                        tma_load_5d(&maps.X_hi[mi], &full_bar[stage], sB + j * kWgBox, nb * p.BN + j * 64, w0 + qw, h0 + qh, t0 + qt, n);
-                        if (split)
-                            tma_load_5d(&maps.X_lo[mi], &full_bar[stage], sB + (nboxes_b + j) * kWgBox, nb * p.BN + j * 64,
-                                        w0 + qw, h0 + qh, t0 + qt, n);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < gsz) {
+                            unsigned char* sB = sA + L.a_bytes + (size_t)g * L.tap_bytes;
+                            for (int j = 0; j < nboxes_b; ++j) {
+                                tma_load_5d(&maps.X_hi[mi[g]], &full_bar[stage], sB + j * kWgBox, nb * p.BN + j * 64, w0 + qw[g],
+                                            h0 + qh[g], t0 + qt[g], n);
+                                if (split)
+                                    tma_load_5d(&maps.X_lo[mi[g]], &full_bar[stage], sB + (nboxes_b + j) * kWgBox, nb * p.BN + j * 64,
+                                                w0 + qw[g], h0 + qh[g], t0 + qt[g], n);
+                            }
+                        }
                     }
-                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);   // both operands MN-major
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int tap, mb, nb, k0, k1;
-                decode(item, tap, mb, nb, k0, k1);
-                if (k1 <= k0) continue;                       // empty split: nothing to add (producer/epilogue skip too)
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        // ---- MMA issuer: whole warp runs the loop, one elected lane issues
+        const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);   // both operands MN-major
+        // descriptor template: 16 K rows = 2048 bytes per K step; LBO = distance between 64-channel boxes, SBO = 8 K rows
+        const uint64_t tmpl = umma_smem_desc_sw128(0, kWgBox, 1024);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int tap0, gsz, mb, nb, k0, k1;
+            decode(item, tap0, gsz, mb, nb, k0, k1);
+            if (k1 <= k0) continue;                       // empty split: nothing to add (producer/epilogue skip too)
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
+            for (int k = k0; k < k1; ++k) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
-                for (int k = k0; k < k1; ++k) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
-                    const uint32_t sB = sA + L.a_bytes;
+                const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
+                const uint64_t a_hi0 = tmpl + (uint64_t)(sA >> 4);
+                const uint64_t a_lo0 = tmpl + (uint64_t)((sA + 2 * kWgBox) >> 4);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < kWgKP / 16; ++ks) {
-                        // 16 K rows = 2048 bytes; LBO = distance between 64-channel boxes, SBO = 8 K-rows
-                        const uint64_t a_hi = umma_smem_desc_sw128(sA + ks * 2048, kWgBox, 1024);
-                        const uint64_t b_hi = umma_smem_desc_sw128(sB + ks * 2048, kWgBox, 1024);
-                        umma_f16(d_tmem, a_hi, b_hi, idesc, (k != k0 || ks != 0));
-                        if (split) {
-                            const uint64_t a_lo = umma_smem_desc_sw128(sA + 2 * kWgBox + ks * 2048, kWgBox, 1024);
-                            const uint64_t b_lo = umma_smem_desc_sw128(sB + nboxes_b * kWgBox + ks * 2048, kWgBox, 1024);
-                            umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-                            umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                        const uint64_t a_hi = a_hi0 + (uint64_t)(ks * (2048 >> 4));
+                        const uint64_t a_lo = a_lo0 + (uint64_t)(ks * (2048 >> 4));
+                        const uint32_t accum = (k != k0 || ks != 0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (g < gsz) {
+                                const uint32_t sB = sA + L.a_bytes + (uint32_t)g * L.tap_bytes;
+                                const uint32_t dg = d_tmem + (uint32_t)(g * p.cstride);
+                                const uint64_t b_hi = tmpl + (uint64_t)((sB + ks * 2048) >> 4);
+                                umma_f16(dg, a_hi, b_hi, idesc, accum);
+                                if (split) {
+                                    const uint64_t b_lo = tmpl + (uint64_t)((sB + nboxes_b * kWgBox + ks * 2048) >> 4);
+                                    umma_f16(dg, a_lo, b_hi, idesc, 1);
+                                    umma_f16(dg, a_hi, b_lo, idesc, 1);
+                                }
+                            }
                         }
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(&tmem_full[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            int tap, mb, nb, k0, k1;
-            decode(item, tap, mb, nb, k0, k1);
+            int tap0, gsz, mb, nb, k0, k1;
+            decode(item, tap0, gsz, mb, nb, k0, k1);
             if (k1 <= k0) continue;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256 + ((uint32_t)(q * 32) << 16);
             const int co = mb * 128 + row;
-            float* dst = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + nb * p.BN;
-            for (int col0 = 0; col0 < p.BN; col0 += 32) {
-                uint32_t v[32];
-                if (p.BN - col0 >= 32) tmem_ld32(t_acc + col0, v);
-                else {
-                    uint32_t v16[16];
-                    tmem_ld16(t_acc + col0, v16);
+            for (int g = 0; g < gsz; ++g) {
+                float* dst = p.dw + ((size_t)(tap0 + g) * p.Cout + co) * p.Cin + nb * p.BN;
+                for (int col0 = 0; col0 < p.BN; col0 += 32) {
+                    uint32_t v[32];
+                    if (p.BN - col0 >= 32) tmem_ld32(t_acc + g * p.cstride + col0, v);
+                    else {
+                        uint32_t v16[16];
+                        tmem_ld16(t_acc + g * p.cstride + col0, v16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
-                }
-                tmem_ld_wait();
-                if (co < p.Cout) {
+                        for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
+                    }
+                    tmem_ld_wait();
+                    if (co < p.Cout) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int ci = nb * p.BN + col0 + j;
-                        if (col0 + j < p.BN && ci < p.Cin) atomicAdd(dst + col0 + j, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j) {
+                            const int ci = nb * p.BN + col0 + j;
+                            if (col0 + j < p.BN && ci < p.Cin) atomicAdd(dst + col0 + j, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -265,7 +301,19 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
         p.BN -= 64;
         p.n_blocks = (p.Cin + p.BN - 1) / p.BN;
     }
-    const int base_items = ntaps * p.m_blocks * p.n_blocks;
+    // taps per work item: as many accumulators as fit 256 TMEM columns (double buffered) and two pipeline stages of
+    // shared memory (D tile + G X tiles, 16 KB per box pair in bf16x3)
+    {
+        const int nbx = (p.BN + 63) / 64;
+        p.cstride = (p.BN + 31) / 32 * 32;
+        int G = 256 / p.cstride;
+        if (G > 4 / nbx) G = 4 / nbx;
+        if (G > ntaps) G = ntaps;
+        if (G < 1) G = 1;
+        p.G = G;
+        p.ngroups = (ntaps + G - 1) / G;
+    }
+    const int base_items = p.ngroups * p.m_blocks * p.n_blocks;
     int ks = (2 * wg_num_sms() + base_items - 1) / base_items;       // at least two waves of work items
     {
         // K chunk sized so that the chunks in flight (concurrent CTAs / items per chunk, + 1 for the transition) stay
@@ -286,10 +334,10 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     const uint32_t smem_cap = 227 * 1024 - 1024;
     int nst = 0;
     for (int s = kWgMaxStages; s >= 2 && !nst; --s)
-        if (wg_smem_layout(p.BN, p.nsplit, s).total <= smem_cap) nst = s;
+        if (wg_smem_layout(p.BN, p.nsplit, s, p.G).total <= smem_cap) nst = s;
     if (!nst) { set_last_error_msg("wgrad: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
     p.nstages = nst;
-    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst);
+    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst, p.G);
 
     int rc;
     const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
