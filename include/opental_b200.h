@@ -155,7 +155,8 @@ OTAL_API int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* desc, void* stream)
 /* MaxPool3dSamePadding on NDHWC planes — replaces AFSD/common/layers.py:9-35 (zero pad + nn.MaxPool3d).
  * Output extent = ceil(input / stride); (pt,ph,pw) = front padding of the "same" rule; padding competes as 0.
  * forward: x planes -> y planes.  backward: g_in[argmax] += g_out (fp32, float reductions; zero g_in first unless it
- * already holds the other consumers' gradient); x planes are the saved forward input. */
+ * already holds the other consumers' gradient); x planes are the saved forward input, or `argmax` as recorded by the
+ * forward pass.  Inputs are compared through order-preserving integer keys of the (hi, lo) pairs: exact for any sign. */
 typedef struct otal_pool_desc {
     int N, T, H, W, C;
     int kt, kh, kw, st, sh, sw, pt, ph, pw;
@@ -164,6 +165,8 @@ typedef struct otal_pool_desc {
     const uint16_t* x_hi; const uint16_t* x_lo;
     uint16_t* y_hi; uint16_t* y_lo;
     const float* g_out; float* g_in;
+    unsigned char* argmax;   /* optional [N,To,Ho,Wo,C] bytes: forward records the window-relative arg-max (255 = the zero
+                                padding won), backward then scatters without re-reading x (x_hi may be NULL in that case) */
 } otal_pool_desc;
 OTAL_API int otal_maxpool_fwd(const otal_pool_desc* desc, void* stream);
 OTAL_API int otal_maxpool_bwd(const otal_pool_desc* desc, void* stream);

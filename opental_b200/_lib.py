@@ -62,7 +62,7 @@ class PoolDesc(Structure):
     _fields_ = (_ints("N", "T", "H", "W", "C", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw",
                       "in_cstride", "in_coff", "out_cstride", "out_coff",
                       "gout_cstride", "gout_coff", "gin_cstride", "gin_coff")
-                + _ptrs("x_hi", "x_lo", "y_hi", "y_lo", "g_out", "g_in"))
+                + _ptrs("x_hi", "x_lo", "y_hi", "y_lo", "g_out", "g_in", "argmax"))
 
 
 class MslDesc(Structure):

@@ -252,7 +252,8 @@ class I3DBackbone(nn.Module):
         y = self._new((*shape, ctot), x)
         mid = self._new((*shape, c["b1a"].cout + c["b2a"].cout), x)
         f32 = torch.empty((*shape, ctot), dtype=torch.float32, device=x.hi.device) if out_f32 else None
-        pooled = ops.maxpool_fwd(x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)))
+        pooled, parg = ops.maxpool_fwd(x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)),
+                                       save_argmax=True)
         o1, o2, o3 = c["b0"].cout, c["b0"].cout + c["b1b"].cout, c["b0"].cout + c["b1b"].cout + c["b2b"].cout
         self._conv(x, c["b0"], y, 0, out_f32=f32)
         self._conv(x, c["b1a"], mid, 0)
@@ -260,7 +261,7 @@ class I3DBackbone(nn.Module):
         self._conv(mid, c["b1b"], y, o1, in_slice=(0, c["b1a"].cout), out_f32=f32)
         self._conv(mid, c["b2b"], y, o2, in_slice=(c["b1a"].cout, c["b2a"].cout), out_f32=f32)
         self._conv(pooled, c["b3b"], y, o3, out_f32=f32)
-        saved[name] = (x, y, mid, pooled)
+        saved[name] = (x, y, mid, pooled, parg)
         if out_f32:
             saved[name + ".f32"] = f32
         return y
@@ -280,8 +281,9 @@ class I3DBackbone(nn.Module):
         saved["Conv3d_1a_7x7"] = cur
         for name, kind, arg in ENDPOINTS[1:]:
             if kind == "pool":
-                nxt = ops.maxpool_fwd(cur, kernel=arg["k"], stride=arg["s"], pad_front=_pads(cur.hi.shape[1:4], arg["k"], arg["s"]))
-                saved[name] = (cur, nxt)
+                nxt, parg = ops.maxpool_fwd(cur, kernel=arg["k"], stride=arg["s"],
+                                            pad_front=_pads(cur.hi.shape[1:4], arg["k"], arg["s"]), save_argmax=True)
+                saved[name] = (cur, nxt, parg)
             elif kind == "conv":
                 r = self.convs[name]
                 nxt = self._new((*cur.hi.shape[:4], r.cout), cur)
@@ -311,7 +313,7 @@ class I3DBackbone(nn.Module):
 
     def _mixed_bwd(self, name: str, saved: dict, g_y: torch.Tensor) -> torch.Tensor:
         c = {b: self.convs[f"{name}.{b}"] for b in BRANCHES}
-        x, y, mid, pooled = saved.pop(name)
+        x, y, mid, pooled, parg = saved.pop(name)
         with_lo = self.precision == "bf16x3"
         ctot = y.hi.shape[-1]
         o1, o2, o3 = c["b0"].cout, c["b0"].cout + c["b1b"].cout, c["b0"].cout + c["b1b"].cout + c["b2b"].cout
@@ -332,7 +334,7 @@ class I3DBackbone(nn.Module):
         d_m = ops.relu_bn_bwd_split(g_mid, mid, sc_m, with_lo=with_lo)
         self._conv_bwd(c["b1a"], x, d_m, g_x, d_slice=(0, w1a), accumulate=True)
         self._conv_bwd(c["b2a"], x, d_m, g_x, d_slice=(w1a, c["b2a"].cout), accumulate=True)
-        ops.maxpool_bwd(x, g_pool, g_x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)))
+        ops.maxpool_bwd(x, g_pool, g_x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)), argmax=parg)
         return g_x
 
     def backward_planes(self, saved: dict, g4: torch.Tensor | None, g5: torch.Tensor | None) -> None:
@@ -350,12 +352,13 @@ class I3DBackbone(nn.Module):
                     g = g4                                   # head gradient + pool5a routing, accumulated below
                 g = self._mixed_bwd(name, saved, g)
             elif kind == "pool":
-                x, _ = saved.pop(name)
+                x, _, parg = saved.pop(name)
                 if name == "MaxPool3d_5a_2x2":
                     g_in = g4
                 else:
                     g_in = torch.zeros(x.hi.shape, dtype=torch.float32, device=dev)
-                ops.maxpool_bwd(x, g, g_in, kernel=arg["k"], stride=arg["s"], pad_front=_pads(x.hi.shape[1:4], arg["k"], arg["s"]))
+                ops.maxpool_bwd(x, g, g_in, kernel=arg["k"], stride=arg["s"], pad_front=_pads(x.hi.shape[1:4], arg["k"], arg["s"]),
+                                argmax=parg)
                 g = g_in
             elif kind == "conv":
                 r = self.convs[name]

@@ -123,6 +123,154 @@ maxpool_kernel(const PoolParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path (the five window shapes of I3D).  Two ideas on top of the generic kernel above:
+//  * order-preserving integer keys: a value is the pair (hi, lo) of bf16 with |lo| <= ulp(hi)/2, so the order of the
+//    represented values hi + lo is the lexicographic order of (hi, lo).  Mapping each 16-bit pattern b to
+//    T(b) = b ^ 0xffff (negative) / b ^ 0x8000 (non-negative) makes that an unsigned 32-bit compare of
+//    (T(hi) << 16) | T(lo): one max per candidate instead of unpack + add + compare + three selects, and the winning key
+//    converts back to the exact (hi, lo) pair.
+//  * WB consecutive outputs along W per thread share the loaded input columns ((WB-1)*SW + KW columns instead of
+//    WB*KW), and the forward optionally records the arg-max (window-relative index, one byte per element; 255 = the
+//    zero padding won) so that the backward is a pure scatter: read 8 gradients + 8 bytes, issue <= 8 red.add.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t key_fwd2(uint32_t w) {          // T() on both 16-bit halves
+    const uint32_t s = (w >> 15) & 0x00010001u;
+    return w ^ ((s * 0xffffu) | 0x80008000u);
+}
+__device__ __forceinline__ uint32_t key_inv2(uint32_t w) {
+    const uint32_t m = ((w >> 15) & 0x00010001u) ^ 0x00010001u;
+    return w ^ ((m * 0xffffu) | 0x80008000u);
+}
+
+template <int KT, int KH, int KW, int ST, int SH, int SW, int WB>
+__global__ void __launch_bounds__(128)
+maxpool_fwd_fast_kernel(const PoolParams p, unsigned char* __restrict__ argmax) {
+    constexpr int NCOL = (WB - 1) * SW + KW;
+    constexpr uint32_t KEY_ZERO = 0x80008000u;                       // key of +0.0 (hi = lo = +0)
+    const int cgs = p.C >> 3;
+    const int wblocks = (p.Wo + WB - 1) / WB;
+    const long long total = (long long)p.N * p.To * p.Ho * wblocks * cgs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int cg = (int)(idx % cgs);
+        long long r = idx / cgs;
+        const int wbk = (int)(r % wblocks); r /= wblocks;
+        const int ho = (int)(r % p.Ho); r /= p.Ho;
+        const int to = (int)(r % p.To);
+        const int n = (int)(r / p.To);
+        const int t0 = to * ST - p.pt, h0 = ho * SH - p.ph, wi0 = wbk * WB * SW - p.pw;
+        const bool th_pad = t0 < 0 || h0 < 0 || t0 + KT > p.T || h0 + KH > p.H;
+        uint32_t best[WB][8];
+        uint32_t arg[WB][8];
+#pragma unroll
+        for (int o = 0; o < WB; ++o) {
+            const int w0 = wi0 + o * SW;
+            const bool pad = th_pad || w0 < 0 || w0 + KW > p.W;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { best[o][j] = pad ? KEY_ZERO : 0u; arg[o][j] = 255u; }
+        }
+#pragma unroll
+        for (int dt = 0; dt < KT; ++dt) {
+            const int t = t0 + dt;
+            if (t < 0 || t >= p.T) continue;
+#pragma unroll
+            for (int dh = 0; dh < KH; ++dh) {
+                const int h = h0 + dh;
+                if (h < 0 || h >= p.H) continue;
+                const long long rowpos = (((long long)n * p.T + t) * p.H + h) * p.W;
+#pragma unroll
+                for (int c = 0; c < NCOL; ++c) {
+                    const int w = wi0 + c;
+                    if (w < 0 || w >= p.W) continue;
+                    const size_t off = (size_t)(rowpos + w) * p.in_cstride + p.in_coff + cg * 8;
+                    const uint4 hv = *reinterpret_cast<const uint4*>(p.x_hi + off);
+                    uint4 lv = make_uint4(0, 0, 0, 0);
+                    if (p.x_lo) lv = *reinterpret_cast<const uint4*>(p.x_lo + off);
+                    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+                    uint32_t key[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t th = key_fwd2(hw[i]), tl = key_fwd2(lw[i]);
+                        key[2 * i] = __byte_perm(tl, th, 0x5410);
+                        key[2 * i + 1] = __byte_perm(tl, th, 0x7632);
+                    }
+#pragma unroll
+                    for (int o = 0; o < WB; ++o) {
+                        const int dw = c - o * SW;                   // compile-time after unrolling
+                        if (dw < 0 || dw >= KW) continue;
+                        const uint32_t code = (uint32_t)((dt * KH + dh) * KW + dw);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (key[j] > best[o][j]) { best[o][j] = key[j]; arg[o][j] = code; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < WB; ++o) {
+            const int wo = wbk * WB + o;
+            if (wo >= p.Wo) continue;
+            const long long opos = (((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo;
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t ka = best[o][2 * i] ? best[o][2 * i] : KEY_ZERO, kb = best[o][2 * i + 1] ? best[o][2 * i + 1] : KEY_ZERO;
+                oh[i] = key_inv2(__byte_perm(ka, kb, 0x7632));
+                ol[i] = key_inv2(__byte_perm(ka, kb, 0x5410));
+            }
+            const size_t off = (size_t)opos * p.out_cstride + p.out_coff + cg * 8;
+            *reinterpret_cast<uint4*>(p.y_hi + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            if (argmax) {
+                const uint32_t a0 = arg[o][0] | (arg[o][1] << 8) | (arg[o][2] << 16) | (arg[o][3] << 24);
+                const uint32_t a1 = arg[o][4] | (arg[o][5] << 8) | (arg[o][6] << 16) | (arg[o][7] << 24);
+                *reinterpret_cast<uint2*>(argmax + (size_t)opos * p.C + cg * 8) = make_uint2(a0, a1);
+            }
+        }
+    }
+}
+
+// Backward from the recorded arg-max: pure scatter.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_argmax_kernel(const PoolParams p, const unsigned char* __restrict__ argmax) {
+    const int cgs = p.C >> 3;
+    const long long total = (long long)p.N * p.To * p.Ho * p.Wo * cgs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int khw = p.kh * p.kw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int cg = (int)(idx % cgs);
+        long long pos = idx / cgs;
+        const long long opos = pos;
+        const int wo = (int)(pos % p.Wo); pos /= p.Wo;
+        const int ho = (int)(pos % p.Ho); pos /= p.Ho;
+        const int to = (int)(pos % p.To);
+        const int n = (int)(pos / p.To);
+        const uint2 a = *reinterpret_cast<const uint2*>(argmax + (size_t)opos * p.C + cg * 8);
+        const float* g = p.g_out + (size_t)opos * p.gout_cstride + p.gout_coff + cg * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t code = ((j < 4 ? a.x : a.y) >> ((j & 3) * 8)) & 0xffu;
+            if (code == 255u || gv[j] == 0.f) continue;
+            const int dt = (int)code / khw, rem = (int)code - dt * khw, dh = rem / p.kw, dw = rem - dh * p.kw;
+            const long long ipos = (((long long)n * p.T + (t0 + dt)) * p.H + (h0 + dh)) * p.W + (w0 + dw);
+            atomicAdd(p.g_in + (size_t)ipos * p.gin_cstride + p.gin_coff + cg * 8 + j, gv[j]);
+        }
+    }
+}
+
+template <int KT, int KH, int KW, int ST, int SH, int SW, int WB>
+static void launch_pool_fast(const PoolParams& p, unsigned char* argmax, cudaStream_t s) {
+    const int wblocks = (p.Wo + WB - 1) / WB;
+    const long long total = (long long)p.N * p.To * p.Ho * wblocks * (p.C >> 3);
+    long long b = (total + 127) / 128;
+    const long long cap = 148LL * 32;
+    maxpool_fwd_fast_kernel<KT, KH, KW, ST, SH, SW, WB><<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 128, 0, s>>>(p, argmax);
+}
+
 static int fill_pool(const otal_pool_desc* d, PoolParams& p, bool backward) {
     if (!d) { set_last_error_msg("pool: null descriptor"); return OTAL_ERR_BAD_ARG; }
     if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->C % 8 || d->in_cstride % 8 || d->in_coff % 8) {
@@ -131,7 +279,7 @@ static int fill_pool(const otal_pool_desc* d, PoolParams& p, bool backward) {
     if (d->kt < 1 || d->kh < 1 || d->kw < 1 || d->st < 1 || d->sh < 1 || d->sw < 1) {
         set_last_error_msg("pool: bad window"); return OTAL_ERR_BAD_ARG;
     }
-    if (!d->x_hi) { set_last_error_msg("pool: null input"); return OTAL_ERR_BAD_ARG; }
+    if (!d->x_hi && !(backward && d->argmax)) { set_last_error_msg("pool: null input"); return OTAL_ERR_BAD_ARG; }
     if (!backward && (!d->y_hi || d->out_cstride % 8 || d->out_coff % 8 || (d->x_lo && !d->y_lo))) {
         set_last_error_msg("pool: bad output"); return OTAL_ERR_BAD_ARG;
     }
@@ -165,7 +313,20 @@ int otal_maxpool_fwd(const otal_pool_desc* d, void* stream) {
     PoolParams p{};
     int rc = fill_pool(d, p, false);
     if (rc) return rc;
-    maxpool_kernel<false><<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto is = [&](int kt, int kh, int kw, int st, int sh, int sw) {
+        return p.kt == kt && p.kh == kh && p.kw == kw && p.st == st && p.sh == sh && p.sw == sw;
+    };
+    // WB = 2 measured best at batch 8 (profiles/r01_pool_bench.txt): these launches are bound by L2 re-reads of the
+    // 27 window positions, WB = 4 shares more columns but halves the warps in flight
+    if (is(3, 3, 3, 1, 1, 1)) launch_pool_fast<3, 3, 3, 1, 1, 1, 2>(p, d->argmax, s);
+    else if (is(1, 3, 3, 1, 2, 2)) launch_pool_fast<1, 3, 3, 1, 2, 2, 2>(p, d->argmax, s);
+    else if (is(3, 3, 3, 2, 2, 2)) launch_pool_fast<3, 3, 3, 2, 2, 2, 2>(p, d->argmax, s);
+    else if (is(2, 2, 2, 2, 2, 2)) launch_pool_fast<2, 2, 2, 2, 2, 2, 2>(p, d->argmax, s);
+    else {
+        if (d->argmax) { set_last_error_msg("pool: arg-max recording is implemented for the I3D window shapes only"); return OTAL_ERR_UNSUPPORTED; }
+        maxpool_kernel<false><<<pool_grid(p), 256, 0, s>>>(p);
+    }
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }
@@ -174,7 +335,8 @@ int otal_maxpool_bwd(const otal_pool_desc* d, void* stream) {
     PoolParams p{};
     int rc = fill_pool(d, p, true);
     if (rc) return rc;
-    maxpool_kernel<true><<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (d->argmax) maxpool_bwd_argmax_kernel<<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, d->argmax);
+    else maxpool_kernel<true><<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

@@ -407,7 +407,9 @@ def _pool_desc(x: Planes, kernel, stride, pad_front, in_slice) -> tuple[PoolDesc
 
 
 def maxpool_fwd(x: Planes, *, kernel, stride, pad_front, in_slice=None, out: Planes | None = None,
-                out_slice=None) -> Planes:
+                out_slice=None, save_argmax: bool = False):
+    """MaxPool3dSamePadding forward on planes.  save_argmax=True additionally returns the recorded arg-max bytes
+    [N,To,Ho,Wo,C] that let maxpool_bwd scatter without re-reading the input."""
     _require_cuda(x.hi)
     d, oshape, C = _pool_desc(x, kernel, stride, pad_front, in_slice)
     if out is None:
@@ -418,15 +420,18 @@ def maxpool_fwd(x: Planes, *, kernel, stride, pad_front, in_slice=None, out: Pla
     d.out_coff = out_slice[0] if out_slice else 0
     d.y_hi = out.hi.data_ptr()
     d.y_lo = _ptr(out.lo) if x.lo is not None else None
+    arg = torch.empty((*oshape, C), dtype=torch.uint8, device=x.hi.device) if save_argmax else None
+    d.argmax = _ptr(arg)
     if _lib.TRACE is not None:
         _lib.LABEL = (f"pool fwd {tuple(x.hi.shape)} C{C} k{kernel} s{stride}", 0.0)
     _lib.call("otal_maxpool_fwd", ctypes.byref(d), _stream())
-    return out
+    return (out, arg) if save_argmax else out
 
 
 def maxpool_bwd(x: Planes, g_out: torch.Tensor, g_in: torch.Tensor, *, kernel, stride, pad_front, in_slice=None,
-                gout_slice=None, gin_slice=None) -> None:
-    """g_in[argmax window] += g_out  (fp32 NDHWC buffers; x = saved forward input planes)."""
+                gout_slice=None, gin_slice=None, argmax: torch.Tensor | None = None) -> None:
+    """g_in[argmax window] += g_out  (fp32 NDHWC buffers; x = saved forward input planes, only read when `argmax`
+    — the bytes recorded by maxpool_fwd(save_argmax=True) — is not given)."""
     _require_cuda(x.hi, g_out, g_in)
     d, oshape, C = _pool_desc(x, kernel, stride, pad_front, in_slice)
     assert tuple(g_out.shape[:4]) == oshape and tuple(g_in.shape[:4]) == tuple(x.hi.shape[:4])
@@ -437,6 +442,9 @@ def maxpool_bwd(x: Planes, g_out: torch.Tensor, g_in: torch.Tensor, *, kernel, s
     d.gin_coff = gin_slice[0] if gin_slice else 0
     d.g_out = g_out.data_ptr()
     d.g_in = g_in.data_ptr()
+    if argmax is not None:
+        assert argmax.dtype == torch.uint8 and argmax.is_contiguous() and tuple(argmax.shape) == (*oshape, C)
+        d.argmax = argmax.data_ptr()
     if _lib.TRACE is not None:
         _lib.LABEL = (f"pool bwd {tuple(x.hi.shape)} C{C} k{kernel} s{stride}", 0.0)
     _lib.call("otal_maxpool_bwd", ctypes.byref(d), _stream())

@@ -182,6 +182,26 @@ def test_maxpool_fwd_bwd(case):
     pos = xr.detach() > 0
     assert torch.allclose(got[pos], gx_ref[pos], atol=1e-5, rtol=1e-5)
     # (an all-zero window may hand its gradient to the zero padding instead of a zero input: same effect)
+    # recorded arg-max path: same output, and a pure-scatter backward that does not read x
+    y2, arg = ops.maxpool_fwd(xp, kernel=k, stride=s, pad_front=pads, save_argmax=True)
+    assert torch.equal(y2.hi, y.hi) and torch.equal(y2.lo, y.lo) and arg.dtype == torch.uint8
+    gin2 = torch.zeros(2, T, H, W, C, device="cuda")
+    ops.maxpool_bwd(xp, gy.permute(0, 2, 3, 4, 1).contiguous().cuda(), gin2, kernel=k, stride=s, pad_front=pads, argmax=arg)
+    assert torch.allclose(from_ndhwc(gin2)[pos], gx_ref[pos], atol=1e-5, rtol=1e-5)
+    assert abs(float(gin2.sum()) - float(gin.sum())) <= 1e-3 * float(gin.abs().sum())
+
+
+def test_maxpool_signed_inputs_exact():
+    """The integer-key comparison is exact for any sign (the I3D pools only ever see post-ReLU inputs)."""
+    from opental_b200 import ops
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(1, 16, 4, 6, 6, generator=g) * 3
+    xp = to_planes(x)
+    xr = from_ndhwc(xp.float())
+    for k, s in (((3, 3, 3), (1, 1, 1)), ((2, 2, 2), (2, 2, 2))):
+        pads = tuple(O.same_pad(sz, kk, ss)[0] for sz, kk, ss in zip((4, 6, 6), k, s))
+        y = ops.maxpool_fwd(xp, kernel=k, stride=s, pad_front=pads)
+        assert torch.equal(from_ndhwc(y.float()), O.maxpool3d_same(xr, k, s))
 
 
 def test_relu_bn_bwd_split():
