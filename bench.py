@@ -255,22 +255,31 @@ def run_native(args):
         e2e = {"value": world * B * 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e, "api": "opental_b200.engine.Trainer.step on pinned host fp32 clips (prefetched H2D) + float(cost)"}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     # ---- per-kernel roofline: the same step enqueued eagerly with every tensor-core conv launch bracketed by CUDA events
     # on the launching stream (a graph replay cannot be bracketed per kernel); same process, same buffers, after the timed
-    # region.  FLOPs are algorithmic (fp32 semantics).
+    # region, on every rank (the step contains the gradient all-reduce).  FLOPs are algorithmic (fp32 semantics).
     graph, tr._graph = tr._graph, None
     n_prof = max(1, min(args.steps, 3))
     with ops.PROFILE.enabled() as prof:
         for j in range(n_prof):
             step_dev(j)
-        torch.cuda.synchronize()
+        barrier()
     ksum = prof.summary()
     tr._graph = graph
+
+    # data-parallel sanity: after identical updates every rank must hold bit-identical parameters
+    in_sync = None
+    if world > 1:
+        chk = torch.stack([w.double().sum() for w, _ in tr.groups] + [w.double().abs().sum() for w, _ in tr.groups])
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        in_sync = bool(torch.equal(hi, lo))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     peaks = {}
     try:
@@ -290,7 +299,8 @@ def run_native(args):
                    "executed_tflops": ach * hw, "executed_frac": ach * hw / peak_tf,
                    "note": f"achieved = algorithmic fp32-semantic conv FLOPs / event-timed kernel time; {args.precision} executes {hw:.0f}x "
                            f"those FLOPs on the bf16 pipe; peak = {peak_src}"}
-    dominant = max(roof, key=lambda k: roof[k]["ms_per_step"]) if roof else None
+    big = [k for k in roof if "head" not in k]
+    dominant = max(big, key=lambda k: roof[k]["ms_per_step"]) if big else None
 
     cpu_base = None
     if not args.no_cpu_baseline:
@@ -312,6 +322,7 @@ def run_native(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
+        "dp_params_in_sync": in_sync,
         "gpu_launches_by_entry_point": dict(_lib.LAUNCHES),
         "roofline": roof.get(dominant),
         "roofline_kernel": dominant,

@@ -125,11 +125,13 @@ class Trainer:
         self._head_launched = False
         self._graph = None
         self._static = None
+        self._capturing = False
         bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
 
     # ---------------------------------------------------------------------------------------------- data parallel
     def _on_backbone_backward(self) -> None:
-        if not torch.cuda.is_current_stream_capturing():      # inside a graph capture the all-reduce stays outside
+        # while a graph is being captured (or warmed up for capture) the all-reduce stays outside the graph
+        if not self._capturing and not torch.cuda.is_current_stream_capturing():
             self._launch_head_allreduce()
 
     def _launch_head_allreduce(self) -> None:
@@ -175,16 +177,21 @@ class Trainer:
         c, t, v, sc = self._static
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(stream):
-            for _ in range(2):                       # warm-up on the capture stream (lazy initialisations, allocator)
+        self._capturing = True
+        try:
+            with torch.cuda.stream(stream):
+                for _ in range(2):                   # warm-up on the capture stream (lazy initialisations, allocator)
+                    self.zero_grad()
+                    self.forward_backward(c, (t, v), sc)
+            torch.cuda.current_stream().wait_stream(stream)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread may query events while this thread captures
+            with torch.cuda.graph(self._graph, stream=stream, capture_error_mode="thread_local"):
                 self.zero_grad()
-                self.forward_backward(c, (t, v), sc)
-        torch.cuda.current_stream().wait_stream(stream)
-        torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=stream):
-            self.zero_grad()
-            self._graph_out = self.forward_backward(c, (t, v), sc)
+                self._graph_out = self.forward_backward(c, (t, v), sc)
+        finally:
+            self._capturing = False
         self._graph_epoch_flag = self._ibm_flag()
 
     def _ibm_flag(self):

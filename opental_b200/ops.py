@@ -54,6 +54,8 @@ class KernelProfile:
         """kernel -> dict(launches, ms, flops); call after torch.cuda.synchronize()."""
         out = {}
         for k, s, e, f in self.records:
+            if f < 2e9:     # head-sized launches: their event brackets measure host enqueue gaps in eager mode, not the kernel
+                k = k + " (launches < 2 GFLOP: 1-D head)"
             d = out.setdefault(k, dict(launches=0, ms=0.0, flops=0.0))
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
