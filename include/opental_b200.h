@@ -102,11 +102,12 @@ OTAL_API int otal_conv_igemm_fwd(const otal_conv_desc* desc, void* stream);
 
 /* Conv3d_1a_7x7: 7x7x7, stride 2, 3 input channels -> Cout, + folded BN + ReLU
  *   AFSD/common/i3d_backbone.py:196-199 (end point), :51-87 (Unit3D.forward incl. the (2,3) "same" padding)
- * x: the clip as written by otal_clip_ingest, [N,T,H,Wp,8] bf16 planes (2 zero columns left of the image, >= 4
- * right, channels 3..7 zero).  w: [49 (dt,dh)][Cout][64] planes, element dw*8 + c of a row = W[co,c,dt,dh,dw]
- * (zero for dw == 7 or c >= 3).  y: [N,ceil(T/2),ceil(H/2),W/2,out_cstride] planes at channel offset out_coff. */
+ * x: the clip as written by otal_clip_ingest, [N,T,H,W/2,32] bf16 planes: for every output column w' the 8-pixel x
+ * 4-channel window that starts 2 pixels left of image column 2*w' (zero outside the image, channel 3 zero).
+ * w: [49 (dt,dh)][Cout][32] planes, element dw*4 + c of a row = W[co,c,dt,dh,dw] (zero for dw == 7 or c == 3).
+ * y: [N,ceil(T/2),ceil(H/2),W/2,out_cstride] planes at channel offset out_coff. */
 typedef struct otal_conv1a_desc {
-    int N, T, H, W, Wp;
+    int N, T, H, W;
     int Cout;
     int tT, tH, tW;
     int nsplit, relu;
@@ -139,9 +140,9 @@ typedef struct otal_wgrad_desc {
 } otal_wgrad_desc;
 OTAL_API int otal_conv_wgrad(const otal_wgrad_desc* desc, void* stream);
 
-/* Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][64] fp32. */
+/* Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][32] fp32. */
 typedef struct otal_conv1a_wgrad_desc {
-    int N, T, H, W, Wp;
+    int N, T, H, W;
     int Cout;
     int tT, tH, tW;
     int nsplit;
@@ -172,10 +173,12 @@ OTAL_API int otal_maxpool_fwd(const otal_pool_desc* desc, void* stream);
 OTAL_API int otal_maxpool_bwd(const otal_pool_desc* desc, void* stream);
 
 /* Clip ingest for Conv3d_1a — replaces `clips.cuda()` + the first F.pad (AFSD/thumos14/train.py:165,
- * AFSD/common/i3d_backbone.py:59-79): NCDHW fp32 [N,C<=8,T,H,W] -> [N,T,H,Wp,8] bf16 planes, image column w at
- * padded column w + pad_left, everything else zero.  lo may be NULL. */
-OTAL_API int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, int Wp,
-                              int pad_left, void* stream);
+ * AFSD/common/i3d_backbone.py:59-79): NCDHW fp32 [N,C<=4,T,H,W] (W even) -> [N,T,H,W/2,8,4] bf16 planes: window w' holds
+ * image columns 2*w' - 2 .. 2*w' + 5 (the 7 W taps of the stride-2 conv with its "same" front padding of 2, plus one
+ * zero-weight column), 4 channel slots per pixel, zero outside the image / for channels >= C.  The 4x expansion along
+ * W makes every TMA box row of Conv3d_1a a dense 64-byte run (overlapping windows read through a strided tensor map
+ * are bound by the TMA request rate, not by bytes).  lo may be NULL. */
+OTAL_API int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, void* stream);
 
 /* Backward of relu(conv*scale+shift) w.r.t. the conv output, fused with the hi/lo split the tensor-core kernels read:
  * d = g * [y > 0] * scale[c]   (torch relu backward + frozen BatchNorm3d, AFSD/thumos14/BDNet.py:39-49).

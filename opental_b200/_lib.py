@@ -37,7 +37,7 @@ class ConvDesc(Structure):
 class Conv1aDesc(Structure):
     """Mirror of `otal_conv1a_desc`."""
 
-    _fields_ = (_ints("N", "T", "H", "W", "Wp", "Cout", "tT", "tH", "tW", "nsplit", "relu", "out_cstride", "out_coff")
+    _fields_ = (_ints("N", "T", "H", "W", "Cout", "tT", "tH", "tW", "nsplit", "relu", "out_cstride", "out_coff")
                 + _ptrs("x_hi", "x_lo", "w_hi", "w_lo", "scale", "shift", "y_hi", "y_lo"))
 
 
@@ -52,7 +52,7 @@ class WgradDesc(Structure):
 class Conv1aWgradDesc(Structure):
     """Mirror of `otal_conv1a_wgrad_desc`."""
 
-    _fields_ = (_ints("N", "T", "H", "W", "Wp", "Cout", "tT", "tH", "tW", "nsplit", "d_cstride", "d_coff")
+    _fields_ = (_ints("N", "T", "H", "W", "Cout", "tT", "tH", "tW", "nsplit", "d_cstride", "d_coff")
                 + _ptrs("x_hi", "x_lo", "d_hi", "d_lo", "dw"))
 
 
@@ -89,7 +89,7 @@ SIGNATURES = {
     "otal_conv1a_wgrad": (c_int, [POINTER(Conv1aWgradDesc), c_void_p]),
     "otal_maxpool_fwd": (c_int, [POINTER(PoolDesc), c_void_p]),
     "otal_maxpool_bwd": (c_int, [POINTER(PoolDesc), c_void_p]),
-    "otal_clip_ingest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_clip_ingest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_relu_bn_bwd_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,

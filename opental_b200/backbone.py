@@ -373,7 +373,7 @@ class I3DBackbone(nn.Module):
                 a, W = saved.pop("clip")
                 sc, _ = self._ss(r)
                 d = ops.relu_bn_bwd_split(g, y, sc, with_lo=with_lo)
-                dw = torch.zeros(49, r.cout, 64, dtype=torch.float32, device=dev)
+                dw = torch.zeros(49, r.cout, 8 * ops.CLIP_CPAD, dtype=torch.float32, device=dev)
                 ops.conv1a_wgrad(a, d, dw, W)
                 # packed layout of this block is [kt,kh,kw,Cout,Cin]; the parameter's .grad is its strided view
                 r.unit.conv3d.weight.grad.add_(ops.unpack_conv1a_wgrad(dw, r.cin))

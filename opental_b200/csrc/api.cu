@@ -58,7 +58,8 @@ int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, const void* base, 
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
     return make_tensor_map(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, nullptr,
-                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+                           swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 }  // namespace otal

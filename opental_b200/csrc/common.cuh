@@ -208,6 +208,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// Same with an explicit layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 0 = none (cute/arch/mma_sm100_desc.hpp).
+// SWIZZLE_64B, K-major: rows of 64 bytes, 8-row groups SBO = 512 bytes apart; MN-major: 32 contiguous elements per K row.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout & 7) << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4

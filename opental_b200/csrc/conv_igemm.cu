@@ -57,6 +57,7 @@ struct ConvParams {
     int accumulate;  // fp32 destination: y += result (dgrad into a shared gradient buffer)
     int out_ncdhw;   // fp32 destination is channel-major [N, out_cstride, T, H, W] instead of channels-last
     int b_mn;        // dgrad mode: weights are read as [tap][K][N] (N contiguous, "MN-major" B) and taps are flipped
+    int k32;         // K chunk of 32 elements = 64-byte rows, SWIZZLE_64B operands (the folded Conv3d_1a: 8 W taps x 4 channels)
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
     float* out_f32;      // optional NDHWC fp32 destination (nullptr = skip)
@@ -70,11 +71,12 @@ struct ConvSmem {
 
 __host__ __device__ inline uint32_t conv_b_rows(int BN, int b_mn) { return b_mn ? (uint32_t)((BN + 63) / 64) * 64u : (uint32_t)BN; }
 
-__host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nstages, int nbuf, int b_mn) {
+__host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nstages, int nbuf, int b_mn, int k32 = 0) {
     ConvSmem s;
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
-    s.a_bytes = kATileBytes * planes;
-    s.b_bytes = conv_b_rows(BN, b_mn) * 128u * planes;
+    const uint32_t rowb = k32 ? 64u : 128u;                        // operand row pitch in shared memory
+    s.a_bytes = kTileM * rowb * planes;
+    s.b_bytes = ((conv_b_rows(BN, b_mn) * rowb + 1023u) & ~1023u) * planes;
     s.stage_bytes = s.a_bytes + s.b_bytes;
     s.staging_off = s.stage_bytes * (uint32_t)nstages;
     uint32_t staging = (uint32_t)nbuf * planes * kATileBytes;      // nbuf (0, 1 or 2) buffers x planes x 16 KB
@@ -103,8 +105,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment is required by the 128B swizzle pattern (pattern repeats every 8 rows x 128 B)
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, p.nstages, p.nbuf, p.b_mn);
-    const uint32_t b_plane = conv_b_rows(p.BN, p.b_mn) * 128u;   // bytes of one B plane per stage
+    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, p.nstages, p.nbuf, p.b_mn, p.k32);
+    const uint32_t planes_ = p.nsplit == 3 ? 2u : 1u;
+    const uint32_t a_plane = L.a_bytes / planes_;                // bytes of one A / B plane per stage
+    const uint32_t b_plane = L.b_bytes / planes_;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
@@ -137,6 +141,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
 
     const int ntaps = p.kt * p.kh * p.kw;
     const int kiters = ntaps * p.kchunks;
+    const int kchunk_elems = p.k32 ? 32 : kChunkK;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (whole warp runs the loop)
@@ -148,42 +153,49 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
             const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
             const int n = m;
-            for (int tap = 0; tap < ntaps; ++tap) {
-                const int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
-                int qt, qh, qw, rt, rh, rw;
+            // taps in (dt, dh, dw) order with running counters: no integer division in the per-stage path (the producer
+            // warp's address arithmetic, not the TMA unit, paces short stages such as the folded Conv3d_1a)
+            int tap = 0;
+            for (int dt = 0; dt < p.kt; ++dt) {
+                int qt, rt;
                 split_parity(dt - p.pt, p.st, qt, rt);
-                split_parity(dh - p.ph, p.sh, qh, rh);
-                split_parity(dw - p.pw, p.sw, qw, rw);
-                const int mi = rt * 4 + rh * 2 + rw;
-                const CUtensorMap* mapA_hi = &maps.A_hi[mi];
-                const CUtensorMap* mapA_lo = &maps.A_lo[mi];
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (elect_one()) {
-                        unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
-                        unsigned char* sB = sA + L.a_bytes;
-                        mbar_expect_tx(&full_bar[stage], L.stage_bytes);
-                        const int c0 = kc * kChunkK;
-                        tma_load_5d(mapA_hi, &full_bar[stage], sA, c0, w0 + qw, h0 + qh, t0 + qt, n);
-                        if (!p.b_mn) {
-                            tma_load_3d(&mapB_hi, &full_bar[stage], sB, c0, nb * p.BN, tap);
-                            if (split) tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane, c0, nb * p.BN, tap);
-                        } else {
-                            // [64 K rows x 64 N] boxes of the flipped tap: N contiguous = MN-major B
-                            const int nbx = (p.BN + 63) / 64;
-                            for (int j = 0; j < nbx; ++j) {
-                                tma_load_3d(&mapB_hi, &full_bar[stage], sB + j * 8192, nb * p.BN + j * 64, c0, ntaps - 1 - tap);
-                                if (split)
-                                    tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane + j * 8192, nb * p.BN + j * 64, c0,
-                                                ntaps - 1 - tap);
+                for (int dh = 0; dh < p.kh; ++dh) {
+                    int qh, rh;
+                    split_parity(dh - p.ph, p.sh, qh, rh);
+                    for (int dw = 0; dw < p.kw; ++dw, ++tap) {
+                        int qw, rw;
+                        split_parity(dw - p.pw, p.sw, qw, rw);
+                        const int mi = rt * 4 + rh * 2 + rw;
+                        const CUtensorMap* mapA_hi = &maps.A_hi[mi];
+                        const CUtensorMap* mapA_lo = &maps.A_lo[mi];
+                        const int cw = w0 + qw, ch = h0 + qh, ct = t0 + qt;
+                        const int btap = p.b_mn ? ntaps - 1 - tap : tap;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (elect_one()) {
+                                unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
+                                unsigned char* sB = sA + L.a_bytes;
+                                mbar_expect_tx(&full_bar[stage], L.stage_bytes);
+                                const int c0 = kc * kchunk_elems;
+                                tma_load_5d(mapA_hi, &full_bar[stage], sA, c0, cw, ch, ct, n);
+                                if (!p.b_mn) {
+                                    tma_load_3d(&mapB_hi, &full_bar[stage], sB, c0, nb * p.BN, btap);
+                                    if (split) tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane, c0, nb * p.BN, btap);
+                                } else {
+                                    // [64 K rows x 64 N] boxes of the flipped tap: N contiguous = MN-major B
+                                    const int nbx = (p.BN + 63) / 64;
+                                    for (int j = 0; j < nbx; ++j) {
+                                        tma_load_3d(&mapB_hi, &full_bar[stage], sB + j * 8192, nb * p.BN + j * 64, c0, btap);
+                                        if (split)
+                                            tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane + j * 8192, nb * p.BN + j * 64, c0, btap);
+                                    }
+                                }
+                                if (split) tma_load_5d(mapA_lo, &full_bar[stage], sA + a_plane, c0, cw, ch, ct, n);
                             }
-                        }
-                        if (split) {
-                            tma_load_5d(mapA_lo, &full_bar[stage], sA + kATileBytes, c0, w0 + qw, h0 + qh, t0 + qt, n);
+                            __syncwarp();
+                            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                         }
                     }
-                    __syncwarp();
-                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -192,9 +204,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, 0, p.b_mn ? 1 : 0);
         // descriptor templates: everything but the start address.  K-major: 32 bytes per K=16 step inside the swizzled
         // row.  MN-major B (dgrad): 16 K rows = 2048 bytes per step, LBO = 8 KB between 64-wide N boxes, SBO = 1 KB.
-        const uint64_t tmpl_k = umma_smem_desc_sw128(0, 16, 1024);
+        // k32: 64-byte rows, SWIZZLE_64B, 8-row groups 512 bytes apart, two K=16 steps per stage.
+        const uint64_t tmpl_k = p.k32 ? umma_smem_desc(0, 16, 512, 4) : umma_smem_desc_sw128(0, 16, 1024);
         const uint64_t tmpl_b = p.b_mn ? umma_smem_desc_sw128(0, 8192, 1024) : tmpl_k;
         const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+        const int ksteps = p.k32 ? 2 : 4;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -207,12 +221,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
                 const uint32_t sB = sA + L.a_bytes;
                 const uint64_t a_hi0 = tmpl_k + (uint64_t)(sA >> 4);
-                const uint64_t a_lo0 = tmpl_k + (uint64_t)((sA + kATileBytes) >> 4);
+                const uint64_t a_lo0 = tmpl_k + (uint64_t)((sA + a_plane) >> 4);
                 const uint64_t b_hi0 = tmpl_b + (uint64_t)(sB >> 4);
                 const uint64_t b_lo0 = tmpl_b + (uint64_t)((sB + b_plane) >> 4);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if (k >= ksteps) break;
                         const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2);
                         const uint64_t b_hi = b_hi0 + (uint64_t)(k * b_step);
                         umma_f16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
@@ -405,7 +420,8 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
             p.BN = 64; p.n_blocks = (p.Cout + 63) / 64;
         }
     }
-    p.kchunks = (L.w_k + kChunkK - 1) / kChunkK;
+    const int chunk = p.k32 ? 32 : kChunkK;
+    p.kchunks = (L.w_k + chunk - 1) / chunk;
     p.store_bf16 = L.y_hi != nullptr;
     p.total_tiles = p.N * p.tilesT * p.tilesH * p.tilesW * p.n_blocks;
 
@@ -413,12 +429,12 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     // prefer (>= 3 stages, double-buffered staging), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
     int nst = 0, nbuf = p.store_bf16 ? 2 : 0;
     for (int s = kMaxStages; s >= 3 && !nst; --s)
-        if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn).total <= smem_cap) nst = s;
-    if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn).total <= smem_cap) nst = 2;
-    if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn).total <= smem_cap) { nst = 2; nbuf = 1; }
+        if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn, p.k32).total <= smem_cap) nst = s;
+    if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn, p.k32).total <= smem_cap) nst = 2;
+    if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn, p.k32).total <= smem_cap) { nst = 2; nbuf = 1; }
     if (!nst) { set_last_error_msg("conv: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
     p.nstages = nst; p.nbuf = nbuf;
-    const ConvSmem SL = conv_smem_layout(p.BN, p.nsplit, nst, nbuf, p.b_mn);
+    const ConvSmem SL = conv_smem_layout(p.BN, p.nsplit, nst, nbuf, p.b_mn, p.k32);
 
     int rc;
     const int ntaps = p.kt * p.kh * p.kw;
@@ -427,9 +443,10 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     const uint64_t bcol = p.b_mn ? (uint64_t)L.w_k : (uint64_t)p.Cout;
     const uint64_t bdims[3] = {brow, bcol, (uint64_t)ntaps};
     const uint64_t bst[2] = {brow * 2, brow * 2 * bcol};
-    const uint32_t bbox[3] = {64, p.b_mn ? 64u : (uint32_t)p.BN, 1};
-    if ((rc = make_tensor_map_bf16(&maps.B_hi, L.w_hi, 3, bdims, bst, bbox, 1))) return rc;
-    if (split && (rc = make_tensor_map_bf16(&maps.B_lo, L.w_lo, 3, bdims, bst, bbox, 1))) return rc;
+    const uint32_t bbox[3] = {(uint32_t)(p.k32 ? 32 : 64), p.b_mn ? 64u : (uint32_t)p.BN, 1};
+    const int bswz = p.k32 ? 2 : 1;                                   // 2 = SWIZZLE_64B (make_tensor_map_bf16)
+    if ((rc = make_tensor_map_bf16(&maps.B_hi, L.w_hi, 3, bdims, bst, bbox, bswz))) return rc;
+    if (split && (rc = make_tensor_map_bf16(&maps.B_lo, L.w_lo, 3, bdims, bst, bbox, bswz))) return rc;
     if (p.store_bf16) {
         const uint32_t obox[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
         const uint64_t odims[5] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.N};
@@ -520,17 +537,18 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
 }
 
 // Conv3d_1a_7x7 (AFSD/common/i3d_backbone.py:196-199): 7x7x7, stride 2, 3 input channels.
-// The clip is stored W-padded and channel-padded, [N,T,H,Wp,8] (otal_clip_ingest), so that the 7 W-taps x 8
-// channels of one (dt,dh) tap are 56 contiguous values: the A operand row of output column w' is the 64-element
-// window starting at padded column 2*w' (8th W-tap and channels 3..7 carry zero weights).  T and H use the
-// stride-2 parity views with TMA zero fill as padding; W padding is physical.
+// The clip is stored window-expanded, [N,T,H,W/2,8,4] (otal_clip_ingest): the 7 W-taps x 4 channel slots of one
+// (dt,dh) tap of output column w' are 28 contiguous values inside a 32-element (64-byte) window (8th W-tap and channel
+// 3 carry zero weights): K = 49 x 32 instead of 343 x 3 = 1029 useful (1.5x padding).  Operand rows are 64 bytes ->
+// SWIZZLE_64B TMA boxes and UMMA descriptors.  T and H use the stride-2 parity views with TMA zero fill as padding;
+// the W padding and the stride-2 window overlap are materialised by the ingest kernel so that TMA box rows are dense.
 int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d) { set_last_error_msg("conv1a: null descriptor"); return OTAL_ERR_BAD_ARG; }
     if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cout <= 0 || d->Cout % 8 || d->out_cstride % 8 || d->out_coff % 8) {
         set_last_error_msg("conv1a: bad dimension"); return OTAL_ERR_BAD_ARG;
     }
-    if (d->W % 2 || d->Wp < d->W + 6) { set_last_error_msg("conv1a: W must be even and Wp >= W + 6"); return OTAL_ERR_BAD_ARG; }
+    if (d->W % 2) { set_last_error_msg("conv1a: W must be even"); return OTAL_ERR_BAD_ARG; }
     if (d->tT * d->tH * d->tW != kTileM) { set_last_error_msg("conv1a: tile box must hold 128 positions"); return OTAL_ERR_BAD_ARG; }
     if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("conv1a: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
     const bool split = d->nsplit == 3;
@@ -539,7 +557,8 @@ int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
     }
     ConvLaunch L{};
     ConvParams& p = L.p;
-    p.N = d->N; p.Cin = 64; p.Cout = d->Cout;
+    p.N = d->N; p.Cin = 32; p.Cout = d->Cout;
+    p.k32 = 1;                                                  // 8 W taps x 4 channels = 32-element K chunks, SWIZZLE_64B
     p.kt = 7; p.kh = 7; p.kw = 1;
     // "same" padding of k=7, s=2 on an even extent: total 5, front 2 (i3d_backbone.py:45-69)
     p.pt = (d->T % 2 == 0) ? 2 : 3; p.ph = (d->H % 2 == 0) ? 2 : 3; p.pw = 0;
@@ -548,25 +567,25 @@ int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
     p.nsplit = d->nsplit; p.relu = d->relu; p.accumulate = 0;
     p.scale = d->scale; p.shift = d->shift; p.out_f32 = nullptr;
     p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
-    L.w_hi = d->w_hi; L.w_lo = d->w_lo; L.w_k = 64; L.y_hi = d->y_hi; L.y_lo = d->y_lo;
+    L.w_hi = d->w_hi; L.w_lo = d->w_lo; L.w_k = 32; L.y_hi = d->y_hi; L.y_lo = d->y_lo;
     L.To = (d->T + 1) / 2; L.Ho = (d->H + 1) / 2; L.Wo = d->W / 2;
 
     ConvMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
-    const uint64_t px = 8 * 2;                                  // bytes per padded pixel (8 channels)
-    const uint64_t sH_ = px * d->Wp, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
-    const uint32_t abox[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+    const uint64_t win = 32 * 2;                                // bytes per window (8 pixels x 4 channels)
+    const uint64_t sH_ = win * L.Wo, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
+    const uint32_t abox[5] = {32, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
     for (int rt = 0; rt < 2; ++rt) for (int rh = 0; rh < 2; ++rh) {
         const int eT = (d->T - rt + 1) / 2, eH = (d->H - rh + 1) / 2;
         if (eT <= 0 || eH <= 0) continue;
-        // dim0 = 64-element window, dim1 = output column (window origin advances 2 pixels = 16 elements)
-        const uint64_t adims[5] = {64, (uint64_t)L.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)p.N};
-        const uint64_t ast[4] = {2 * px, sH_ * 2, sT_ * 2, sN_};
-        const size_t off = ((size_t)rt * d->H + rh) * d->Wp * 8;
+        // dim0 = the 32-element window, dim1 = output column (dense: the clip is stored window-expanded)
+        const uint64_t adims[5] = {32, (uint64_t)L.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)p.N};
+        const uint64_t ast[4] = {win, sH_ * 2, sT_ * 2, sN_};
+        const size_t off = ((size_t)rt * d->H + rh) * L.Wo * 32;
         const int mi = rt * 4 + rh * 2;
-        if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 1))) return rc;
-        if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 2))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 2))) return rc;
     }
     return finish_and_launch(L, maps, stream);
 }

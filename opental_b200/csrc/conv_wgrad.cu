@@ -35,6 +35,7 @@ struct WgParams {
     int kt, kh, kw, pt, ph, pw, st, sh, sw;
     int tT, tH, tW, tilesT, tilesH, tilesW;
     int BN, n_blocks, m_blocks, ksplit, ktiles;   // ktiles = N * tilesT*tilesH*tilesW
+    int x32;                  // X operand rows are 32 elements = 64 bytes (folded Conv3d_1a), SWIZZLE_64B boxes of 4 KB
     int G, ngroups, cstride;  // taps per work item (they share the D tile in shared memory), number of tap groups, TMEM
                               // column stride between the accumulators of consecutive taps (BN rounded up to 32)
     int nsplit, nstages;
@@ -53,11 +54,12 @@ __device__ __forceinline__ void wg_split_parity(int d, int s, int& q, int& par) 
 }
 
 struct WgSmem { uint32_t a_bytes, b_bytes, tap_bytes, stage_bytes, bar_off, total; };
-__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages, int G) {
+__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages, int G, int x32 = 0) {
     WgSmem s;
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
+    const uint32_t xbox = x32 ? kWgBox / 2 : kWgBox;          // [64 positions x 32 | 64 channels]
     s.a_bytes = 2u * kWgBox * planes;                         // 128 rows of Cout = 2 boxes
-    s.tap_bytes = (uint32_t)((BN + 63) / 64) * kWgBox * planes;   // X boxes of ONE tap
+    s.tap_bytes = (uint32_t)((BN + 63) / 64) * xbox * planes;     // X boxes of ONE tap
     s.b_bytes = s.tap_bytes * (uint32_t)G;
     s.stage_bytes = s.a_bytes + s.b_bytes;
     s.bar_off = s.stage_bytes * (uint32_t)nstages;
@@ -69,7 +71,9 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages, p.G);
+    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages, p.G, p.x32);
+    const uint32_t xbox = p.x32 ? kWgBox / 2 : kWgBox;        // bytes of one X box
+    const uint32_t xstep = p.x32 ? 1024u : 2048u;             // bytes of 16 K rows of X
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + kWgMaxStages;
     uint64_t* tmem_full = empty_bar + kWgMaxStages;
@@ -136,32 +140,39 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             }
             const int m_valid = min(128, p.Cout - mb * 128);
             const int a_boxes = m_valid > 64 ? 2 : 1;     // rows 64..127 of a short block are never read back
-            const uint32_t tx = (uint32_t)(a_boxes + gsz * nboxes_b) * kWgBox * planes;
+            const uint32_t tx = ((uint32_t)a_boxes * kWgBox + (uint32_t)(gsz * nboxes_b) * xbox) * planes;
+            // K tile k -> (n, t, h, w) tile indices, advanced with running counters (no integer division per stage)
+            int iw, ih, it, n;
+            {
+                int m = k0;
+                iw = m % p.tilesW; m /= p.tilesW;
+                ih = m % p.tilesH; m /= p.tilesH;
+                it = m % p.tilesT; m /= p.tilesT;
+                n = m;
+            }
             for (int k = k0; k < k1; ++k) {
-                int m = k;
-                const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
-                const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
-                const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
-                const int n = m;
+                const int w0 = iw * p.tW, h0 = ih * p.tH, t0 = it * p.tT;
+                const int n_cur = n;
+                if (++iw == p.tilesW) { iw = 0; if (++ih == p.tilesH) { ih = 0; if (++it == p.tilesT) { it = 0; ++n; } } }
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
                     mbar_expect_tx(&full_bar[stage], tx);
                     for (int j = 0; j < a_boxes; ++j) {
-                        tma_load_5d(&maps.D_hi, &full_bar[stage], sA + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n);
+                        tma_load_5d(&maps.D_hi, &full_bar[stage], sA + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n_cur);
                         if (split)
-                            tma_load_5d(&maps.D_lo, &full_bar[stage], sA + 2 * kWgBox + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n);
+                            tma_load_5d(&maps.D_lo, &full_bar[stage], sA + 2 * kWgBox + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n_cur);
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (g < gsz) {
                             unsigned char* sB = sA + L.a_bytes + (size_t)g * L.tap_bytes;
                             for (int j = 0; j < nboxes_b; ++j) {
-                                tma_load_5d(&maps.X_hi[mi[g]], &full_bar[stage], sB + j * kWgBox, nb * p.BN + j * 64, w0 + qw[g],
-                                            h0 + qh[g], t0 + qt[g], n);
+                                tma_load_5d(&maps.X_hi[mi[g]], &full_bar[stage], sB + j * xbox, nb * p.BN + j * 64, w0 + qw[g],
+                                            h0 + qh[g], t0 + qt[g], n_cur);
                                 if (split)
-                                    tma_load_5d(&maps.X_lo[mi[g]], &full_bar[stage], sB + (nboxes_b + j) * kWgBox, nb * p.BN + j * 64,
-                                                w0 + qw[g], h0 + qh[g], t0 + qt[g], n);
+                                    tma_load_5d(&maps.X_lo[mi[g]], &full_bar[stage], sB + (nboxes_b + j) * xbox, nb * p.BN + j * 64,
+                                                w0 + qw[g], h0 + qh[g], t0 + qt[g], n_cur);
                             }
                         }
                     }
@@ -175,6 +186,8 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);   // both operands MN-major
         // descriptor template: 16 K rows = 2048 bytes per K step; LBO = distance between 64-channel boxes, SBO = 8 K rows
         const uint64_t tmpl = umma_smem_desc_sw128(0, kWgBox, 1024);
+        // X with 64-byte rows: MN-major SWIZZLE_64B, 32 contiguous elements per K row, 8-row groups 512 bytes apart
+        const uint64_t tmpl_x = p.x32 ? umma_smem_desc(0, kWgBox / 2, 512, 4) : tmpl;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -201,10 +214,10 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                             if (g < gsz) {
                                 const uint32_t sB = sA + L.a_bytes + (uint32_t)g * L.tap_bytes;
                                 const uint32_t dg = d_tmem + (uint32_t)(g * p.cstride);
-                                const uint64_t b_hi = tmpl + (uint64_t)((sB + ks * 2048) >> 4);
+                                const uint64_t b_hi = tmpl_x + (uint64_t)((sB + ks * xstep) >> 4);
                                 umma_f16(dg, a_hi, b_hi, idesc, accum);
                                 if (split) {
-                                    const uint64_t b_lo = tmpl + (uint64_t)((sB + nboxes_b * kWgBox + ks * 2048) >> 4);
+                                    const uint64_t b_lo = tmpl_x + (uint64_t)((sB + nboxes_b * xbox + ks * xstep) >> 4);
                                     umma_f16(dg, a_lo, b_hi, idesc, 1);
                                     umma_f16(dg, a_hi, b_lo, idesc, 1);
                                 }
@@ -334,10 +347,10 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     const uint32_t smem_cap = 227 * 1024 - 1024;
     int nst = 0;
     for (int s = kWgMaxStages; s >= 2 && !nst; --s)
-        if (wg_smem_layout(p.BN, p.nsplit, s, p.G).total <= smem_cap) nst = s;
+        if (wg_smem_layout(p.BN, p.nsplit, s, p.G, p.x32).total <= smem_cap) nst = s;
     if (!nst) { set_last_error_msg("wgrad: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
     p.nstages = nst;
-    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst, p.G);
+    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst, p.G, p.x32);
 
     int rc;
     const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
@@ -409,11 +422,11 @@ int otal_conv_wgrad(const otal_wgrad_desc* d, void* stream_) {
     return wg_finish_and_launch(p, maps, d->d_hi, d->d_lo, d->d_cstride, d->d_coff, stream);
 }
 
-// Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][64] fp32.
+// Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][32] fp32.
 int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d) { set_last_error_msg("conv1a_wgrad: null descriptor"); return OTAL_ERR_BAD_ARG; }
-    if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->W % 2 || d->Wp < d->W + 6 || d->Cout <= 0 || d->Cout % 8 ||
+    if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->W % 2 || d->Cout <= 0 || d->Cout % 8 ||
         d->d_cstride % 8 || d->d_coff % 8) {
         set_last_error_msg("conv1a_wgrad: bad dimension"); return OTAL_ERR_BAD_ARG;
     }
@@ -423,7 +436,8 @@ int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
     if (!d->x_hi || !d->d_hi || !d->dw || (split && (!d->x_lo || !d->d_lo))) { set_last_error_msg("conv1a_wgrad: null pointer"); return OTAL_ERR_BAD_ARG; }
 
     WgParams p{};
-    p.N = d->N; p.Cin = 64; p.Cout = d->Cout;
+    p.N = d->N; p.Cin = 32; p.Cout = d->Cout;
+    p.x32 = 1;
     p.To = (d->T + 1) / 2; p.Ho = (d->H + 1) / 2; p.Wo = d->W / 2;
     p.kt = 7; p.kh = 7; p.kw = 1;
     p.pt = (d->T % 2 == 0) ? 2 : 3; p.ph = (d->H % 2 == 0) ? 2 : 3; p.pw = 0;
@@ -434,18 +448,18 @@ int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
     WgMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
-    const uint64_t px = 8 * 2;
-    const uint64_t sH_ = px * d->Wp, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
-    const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
+    const uint64_t win = 32 * 2;                                // window-expanded clip: 64 bytes per output column
+    const uint64_t sH_ = win * p.Wo, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
+    const uint32_t box[5] = {32, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
     for (int rt = 0; rt < 2; ++rt) for (int rh = 0; rh < 2; ++rh) {
         const int eT = (d->T - rt + 1) / 2, eH = (d->H - rh + 1) / 2;
         if (eT <= 0 || eH <= 0) continue;
-        const uint64_t xdims[5] = {64, (uint64_t)p.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)d->N};
-        const uint64_t xst[4] = {2 * px, sH_ * 2, sT_ * 2, sN_};
-        const size_t off = ((size_t)rt * d->H + rh) * d->Wp * 8;
+        const uint64_t xdims[5] = {32, (uint64_t)p.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)d->N};
+        const uint64_t xst[4] = {win, sH_ * 2, sT_ * 2, sN_};
+        const size_t off = ((size_t)rt * d->H + rh) * p.Wo * 32;
         const int mi = rt * 4 + rh * 2;
-        if ((rc = make_tensor_map_bf16(&maps.X_hi[mi], d->x_hi + off, 5, xdims, xst, box, 1))) return rc;
-        if (split && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&maps.X_hi[mi], d->x_hi + off, 5, xdims, xst, box, 2))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 2))) return rc;
     }
     return wg_finish_and_launch(p, maps, d->d_hi, d->d_lo, d->d_cstride, d->d_coff, stream);
 }

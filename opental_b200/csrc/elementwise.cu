@@ -51,28 +51,34 @@ __global__ void ncdhw_to_ndhwc_split_kernel(const float* __restrict__ x, uint16_
 }
 
 
-// Clip ingest for Conv3d_1a: NCDHW fp32 [N,C,T,H,W] -> [N,T,H,Wp,8] bf16 planes; image column w lands at padded
-// column w + pad_left, every other element (pad columns, channels >= C) is zero.  One thread per padded pixel:
-// reads are coalesced along w per channel plane, the 16-byte pixel is written with one vector store per plane.
+// Clip ingest for Conv3d_1a: NCDHW fp32 [N,C,T,H,W] -> window-expanded [N,T,H,W/2,8,4] bf16 planes.  Window w' of a row
+// holds image columns 2*w' - 2 .. 2*w' + 5 (zero outside the image), 4 channel slots per pixel (zero for c >= C).
+// One thread per (window, pixel pair): reads are coalesced along w per channel plane, each thread writes 16 bytes
+// (2 pixels x 4 channels) per plane, a warp writes 512 contiguous bytes.
 __global__ void clip_ingest_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                   int N, int C, int T, int H, int W, int Wp, int pad_left) {
-    const long long total = (long long)N * T * H * Wp;
+                                   int N, int C, int T, int H, int W) {
+    const int Wo = W >> 1;
+    const long long total = (long long)N * T * H * Wo * 4;          // 4 pixel pairs per window
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long THW = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int wp = (int)(i % Wp);
-        const long long row = i / Wp;                 // (n*T + t)*H + h
-        const int w = wp - pad_left;
+        const int pp = (int)(i & 3);
+        const long long win = i >> 2;
+        const int wo = (int)(win % Wo);
+        const long long row = win / Wo;               // (n*T + t)*H + h
+        const long long n = row / ((long long)T * H);
+        const long long th = row - n * (long long)T * H;
         uint32_t h32[4] = {0, 0, 0, 0}, l32[4] = {0, 0, 0, 0};
-        if (w >= 0 && w < W) {
-            const long long n = row / ((long long)T * H);
-            const long long th = row - n * (long long)T * H;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int w = 2 * wo - 2 + 2 * pp + q;
+            if (w < 0 || w >= W) continue;
             const float* src = x + n * C * THW + th * W + w;
-            for (int c = 0; c < C && c < 8; ++c) {
+            for (int c = 0; c < C && c < 4; ++c) {
                 __nv_bfloat16 hb, lb;
                 split_bf16(src[c * THW], hb, lb);
-                h32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
-                l32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
+                h32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
+                l32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
             }
         }
         reinterpret_cast<uint4*>(hi)[i] = make_uint4(h32[0], h32[1], h32[2], h32[3]);
@@ -216,14 +222,13 @@ int otal_ncdhw_to_ndhwc_split(const float* x, uint16_t* hi, uint16_t* lo, int N,
     return OTAL_OK;
 }
 
-int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, int Wp,
-                     int pad_left, void* stream) {
-    if (N < 0 || C <= 0 || C > 8 || T <= 0 || H <= 0 || W <= 0 || pad_left < 0 || Wp < W + pad_left || !x || !hi) {
-        set_last_error_msg("clip_ingest: bad argument"); return OTAL_ERR_BAD_ARG;
+int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, void* stream) {
+    if (N < 0 || C <= 0 || C > 4 || T <= 0 || H <= 0 || W <= 0 || (W & 1) || !x || !hi) {
+        set_last_error_msg("clip_ingest: bad argument (C <= 4, W even)"); return OTAL_ERR_BAD_ARG;
     }
     if (N == 0) return OTAL_OK;
-    clip_ingest_kernel<<<grid_for((long long)N * T * H * Wp, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, hi, lo, N, C, T, H, W, Wp, pad_left);
+    clip_ingest_kernel<<<grid_for((long long)N * T * H * (W / 2) * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, hi, lo, N, C, T, H, W);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

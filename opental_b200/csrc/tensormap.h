@@ -6,6 +6,7 @@
 
 namespace otal {
 // bf16 tensor, `rank` dims innermost-first; strides[i] = byte stride of dim i+1; box = tile extents.
+// swizzle128: 0 = no swizzle, 1 = SWIZZLE_128B, 2 = SWIZZLE_64B.
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
 int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,

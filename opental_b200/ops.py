@@ -299,53 +299,49 @@ def conv_wgrad(x: Planes, d: Planes, dw: torch.Tensor, *, kernel: tuple[int, int
 # ----------------------------------------------------------------------------------------------------------
 # Conv3d_1a_7x7 (stride 2, 3 channels) in the folded layout
 # ----------------------------------------------------------------------------------------------------------
-CLIP_CPAD = 8
-CLIP_PAD_LEFT = 2
-
-
-def clip_padded_width(W: int) -> int:
-    return W + 8          # 2 zero columns left, 6 right (>= 4 needed by the 8-tap window)
+CLIP_CPAD = 4          # channel slots per pixel in the window-expanded clip
+CLIP_WIN = 8           # pixels per window (7 W taps + 1 zero-weight slot)
 
 
 def clip_ingest(x: torch.Tensor, with_lo: bool = True) -> Planes:
-    """NCDHW fp32 clip [N,3,T,H,W] -> [N,T,H,Wp,8] bf16 planes (W- and channel-padded), the input of conv1a_fwd."""
+    """NCDHW fp32 clip [N,3,T,H,W] -> window-expanded [N,T,H,W/2,32] bf16 planes, the input of conv1a_fwd."""
     _require_cuda(x)
     x = x.contiguous().float()
     N, C, T, H, W = x.shape
-    Wp = clip_padded_width(W)
-    hi = torch.empty((N, T, H, Wp, CLIP_CPAD), dtype=torch.bfloat16, device=x.device)
+    assert W % 2 == 0 and C <= CLIP_CPAD
+    hi = torch.empty((N, T, H, W // 2, CLIP_WIN * CLIP_CPAD), dtype=torch.bfloat16, device=x.device)
     lo = torch.empty_like(hi) if with_lo else None
-    _lib.call("otal_clip_ingest", x.data_ptr(), hi.data_ptr(), _ptr(lo), N, C, T, H, W, Wp, CLIP_PAD_LEFT, _stream())
+    _lib.call("otal_clip_ingest", x.data_ptr(), hi.data_ptr(), _ptr(lo), N, C, T, H, W, _stream())
     return Planes(hi, lo)
 
 
 def pack_conv1a_weight(w: torch.Tensor, with_lo: bool = True) -> Planes:
-    """[Cout, 3, 7, 7, 7] fp32 -> [49 (dt,dh), Cout, 64] planes, row element dw*8 + c (zero for dw == 7, c >= 3)."""
+    """[Cout, 3, 7, 7, 7] fp32 -> [49 (dt,dh), Cout, 32] planes, row element dw*4 + c (zero for dw == 7, c == 3)."""
     Cout, C, kt, kh, kw = w.shape
     assert (kt, kh, kw) == (7, 7, 7) and C <= CLIP_CPAD
     f = torch.zeros((kt, kh, Cout, 8, CLIP_CPAD), dtype=torch.float32, device=w.device)
     f[:, :, :, :kw, :C] = w.detach().float().permute(2, 3, 0, 4, 1)
-    return split_bf16(f.reshape(kt * kh, Cout, 64), with_lo)
+    return split_bf16(f.reshape(kt * kh, Cout, 8 * CLIP_CPAD), with_lo)
 
 
 def unpack_conv1a_wgrad(dw: torch.Tensor, C: int = 3) -> torch.Tensor:
-    """[49, Cout, 64] folded weight gradient -> [Cout, C, 7, 7, 7]."""
+    """[49, Cout, 32] folded weight gradient -> [Cout, C, 7, 7, 7]."""
     Cout = dw.shape[1]
     return dw.reshape(7, 7, Cout, 8, CLIP_CPAD)[:, :, :, :7, :C].permute(2, 4, 0, 1, 3).contiguous()
 
 
 def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shift: torch.Tensor | None,
                relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None) -> Planes:
-    N, T, H, Wp, C8 = x.hi.shape
+    N, T, H, Wo_, K_ = x.hi.shape
     taps, Cout, K = w.hi.shape
-    assert C8 == CLIP_CPAD and taps == 49 and K == 64
+    assert Wo_ == W // 2 and K_ == CLIP_WIN * CLIP_CPAD and taps == 49 and K == K_
     nsplit = 3 if (x.lo is not None and w.lo is not None) else 1
     To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
     if out is None:
         hi = torch.empty((N, To, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.hi.device)
         out = Planes(hi, torch.empty_like(hi) if nsplit == 3 else None)
     tT, tH, tW = pick_tile_box(To, Ho, Wo)
-    d = Conv1aDesc(N=N, T=T, H=H, W=W, Wp=Wp, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit, relu=int(relu),
+    d = Conv1aDesc(N=N, T=T, H=H, W=W, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit, relu=int(relu),
                    out_cstride=out.hi.shape[-1], out_coff=out_slice[0] if out_slice else 0,
                    x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                    w_hi=w.hi.data_ptr(), w_lo=_ptr(w.lo) if nsplit == 3 else None,
@@ -360,15 +356,15 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
 
 
 def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[int, int] | None = None) -> None:
-    """dw [49, Cout, 64] fp32 += folded weight gradient of Conv3d_1a."""
-    N, T, H, Wp, C8 = x.hi.shape
+    """dw [49, Cout, 32] fp32 += folded weight gradient of Conv3d_1a."""
+    N, T, H, Wo_, K_ = x.hi.shape
     taps, Cout, K = dw.shape
-    assert taps == 49 and K == 64 and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert Wo_ == W // 2 and taps == 49 and K == K_ == CLIP_WIN * CLIP_CPAD and dw.dtype == torch.float32 and dw.is_contiguous()
     nsplit = 3 if (x.lo is not None and d.lo is not None) else 1
     To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
     assert tuple(d.hi.shape[:4]) == (N, To, Ho, Wo)
     tT, tH, tW = pick_tile_box(To, Ho, Wo, 6)
-    desc = Conv1aWgradDesc(N=N, T=T, H=H, W=W, Wp=Wp, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit,
+    desc = Conv1aWgradDesc(N=N, T=T, H=H, W=W, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit,
                            d_cstride=d.hi.shape[-1], d_coff=d_slice[0] if d_slice else 0,
                            x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
                            d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())

@@ -144,11 +144,11 @@ def test_conv1a_wgrad():
     y = F.conv3d(O._pad3d(x, (7, 7, 7), (2, 2, 2)), w, stride=2)
     gy = torch.randn(y.shape, generator=g)
     (gw_ref,) = torch.autograd.grad(y, w, gy)
-    dw = torch.zeros(49, 64, 64, device="cuda")
+    dw = torch.zeros(49, 64, 32, device="cuda")
     ops.conv1a_wgrad(ops.clip_ingest(x.cuda()), to_planes(gy), dw, W)
     assert rel(ops.unpack_conv1a_wgrad(dw).cpu(), gw_ref) < TOL
     # the folded slots that carry no weight (8th W tap, channels 3..7) are not part of the parameter
-    assert dw.shape == (49, 64, 64)
+    assert dw.shape == (49, 64, 32)
 
 
 POOLS = [

@@ -56,7 +56,7 @@ w1 = ops.pack_conv1a_weight(torch.randn(64, 3, 7, 7, 7, device=dev) * 0.03)
 y1 = ops.conv1a_fwd(a, w1, 96, scale=torch.ones(64, device=dev), shift=torch.zeros(64, device=dev))
 order.append("conv_igemm_kernel  fwd   Conv3d_1a_7x7 (folded)")
 d1 = planes((B, 128, 48, 48, 64), relu=False)
-dw1 = torch.zeros(49, 64, 64, device=dev)
+dw1 = torch.zeros(49, 64, 32, device=dev)
 ops.conv1a_wgrad(a, d1, dw1, 96)
 order.append("conv_wgrad_kernel  wgrad Conv3d_1a_7x7 (folded)")
 del clip, a, d1
