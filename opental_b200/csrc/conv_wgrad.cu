@@ -35,7 +35,11 @@ struct WgParams {
     int kt, kh, kw, pt, ph, pw, st, sh, sw;
     int tT, tH, tW, tilesT, tilesH, tilesW;
     int BN, n_blocks, m_blocks, ksplit, ktiles;   // ktiles = N * tilesT*tilesH*tilesW
+    int BNs;                  // swap mode: MMA N = Cout rounded up to 16
     int x32;                  // X operand rows are 32 elements = 64 bytes (folded Conv3d_1a), SWIZZLE_64B boxes of 4 KB
+    int swap;                 // x32 only: the 4 taps' X tiles are the M operand (4 x 32 rows), D is the N operand (Cout <= 128
+                              // columns): one MMA covers 4 taps, so the D tile is read from shared memory once per 4 taps
+                              // instead of once per tap (the per-tap form is bound by those reads: SMEM 128 B/clk)
     int G, ngroups, cstride;  // taps per work item (they share the D tile in shared memory), number of tap groups, TMEM
                               // column stride between the accumulators of consecutive taps (BN rounded up to 32)
     int nsplit, nstages;
@@ -203,7 +207,27 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                 const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
                 const uint64_t a_hi0 = tmpl + (uint64_t)(sA >> 4);
                 const uint64_t a_lo0 = tmpl + (uint64_t)((sA + 2 * kWgBox) >> 4);
-                if (elect_one()) {
+                if (p.swap) {
+                    if (elect_one()) {
+                        // A = X tiles of the 4 taps (MN-major SW64, 32-row blocks LBO = tap_bytes apart), B = D tile
+                        const uint32_t sB = sA + L.a_bytes;
+                        const uint64_t tx_ = umma_smem_desc(0, L.tap_bytes, 512, 4);
+                        const uint32_t idesc_s = umma_idesc_bf16(128, p.BNs, 1, 1);
+#pragma unroll
+                        for (int ks = 0; ks < kWgKP / 16; ++ks) {
+                            const uint64_t xa_hi = tx_ + (uint64_t)((sB + ks * 1024) >> 4);
+                            const uint64_t xa_lo = tx_ + (uint64_t)((sB + xbox + ks * 1024) >> 4);
+                            const uint64_t d_hi = a_hi0 + (uint64_t)(ks * (2048 >> 4));
+                            const uint64_t d_lo = a_lo0 + (uint64_t)(ks * (2048 >> 4));
+                            umma_f16(d_tmem, xa_hi, d_hi, idesc_s, (k != k0 || ks != 0));
+                            if (split) {
+                                umma_f16(d_tmem, xa_lo, d_hi, idesc_s, 1);
+                                umma_f16(d_tmem, xa_hi, d_lo, idesc_s, 1);
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                    }
+                } else if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < kWgKP / 16; ++ks) {
                         const uint64_t a_hi = a_hi0 + (uint64_t)(ks * (2048 >> 4));
@@ -244,6 +268,25 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256 + ((uint32_t)(q * 32) << 16);
+            if (p.swap) {
+                // accumulator row = tap-in-group * 32 + folded input index j, column = output channel: for a fixed
+                // column the 32 lanes of a warp add to 32 consecutive floats of dW[tap][co][:]
+                if (q < gsz) {
+                    float* dst = p.dw + (size_t)(tap0 + q) * p.Cout * 32 + lane;
+                    for (int col0 = 0; col0 < p.Cout; col0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_acc + col0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.Cout) atomicAdd(dst + (size_t)(col0 + j) * 32, __uint_as_float(v[j]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             const int co = mb * 128 + row;
             for (int g = 0; g < gsz; ++g) {
                 float* dst = p.dw + ((size_t)(tap0 + g) * p.Cout + co) * p.Cin + nb * p.BN;
@@ -314,6 +357,8 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
         p.BN -= 64;
         p.n_blocks = (p.Cin + p.BN - 1) / p.BN;
     }
+    p.swap = (p.x32 && p.Cout <= 128 && p.Cout % 32 == 0 && p.Cin == 32) ? 1 : 0;
+    p.BNs = (p.Cout + 15) / 16 * 16;
     // taps per work item: as many accumulators as fit 256 TMEM columns (double buffered) and two pipeline stages of
     // shared memory (D tile + G X tiles, 16 KB per box pair in bf16x3)
     {
@@ -323,6 +368,7 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
         if (G > 4 / nbx) G = 4 / nbx;
         if (G > ntaps) G = ntaps;
         if (G < 1) G = 1;
+        if (p.swap) G = 4;                                           // 4 x 32 rows = one M = 128 operand
         p.G = G;
         p.ngroups = (ntaps + G - 1) / G;
     }
