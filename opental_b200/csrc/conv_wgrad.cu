@@ -63,7 +63,8 @@ __host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
     const uint32_t xbox = x32 ? kWgBox / 2 : kWgBox;          // [64 positions x 32 | 64 channels]
     s.a_bytes = 2u * kWgBox * planes;                         // 128 rows of Cout = 2 boxes
-    s.tap_bytes = (uint32_t)((BN + 63) / 64) * xbox * planes;     // X boxes of ONE tap
+    s.tap_bytes = (uint32_t)((BN + 63) / 64) * xbox * planes;     // X boxes of ONE tap (hi boxes of all taps come first,
+                                                                  // then the lo boxes: every plane is one run of boxes)
     s.b_bytes = s.tap_bytes * (uint32_t)G;
     s.stage_bytes = s.a_bytes + s.b_bytes;
     s.bar_off = s.stage_bytes * (uint32_t)nstages;
@@ -78,6 +79,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages, p.G, p.x32);
     const uint32_t xbox = p.x32 ? kWgBox / 2 : kWgBox;        // bytes of one X box
     const uint32_t xstep = p.x32 ? 1024u : 2048u;             // bytes of 16 K rows of X
+    const uint32_t lo_off = (uint32_t)(p.G * ((p.BN + 63) / 64)) * xbox;   // lo boxes follow the hi boxes of all G taps
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + kWgMaxStages;
     uint64_t* tmem_full = empty_bar + kWgMaxStages;
@@ -170,12 +172,12 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (g < gsz) {
-                            unsigned char* sB = sA + L.a_bytes + (size_t)g * L.tap_bytes;
+                            unsigned char* sB = sA + L.a_bytes + (size_t)(g * nboxes_b) * xbox;      // hi boxes of tap g
                             for (int j = 0; j < nboxes_b; ++j) {
                                 tma_load_5d(&maps.X_hi[mi[g]], &full_bar[stage], sB + j * xbox, nb * p.BN + j * 64, w0 + qw[g],
                                             h0 + qh[g], t0 + qt[g], n_cur);
                                 if (split)
-                                    tma_load_5d(&maps.X_lo[mi[g]], &full_bar[stage], sB + (nboxes_b + j) * xbox, nb * p.BN + j * 64,
+                                    tma_load_5d(&maps.X_lo[mi[g]], &full_bar[stage], sB + lo_off + j * xbox, nb * p.BN + j * 64,
                                                 w0 + qw[g], h0 + qh[g], t0 + qt[g], n_cur);
                             }
                         }
@@ -211,12 +213,12 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                     if (elect_one()) {
                         // A = X tiles of the 4 taps (MN-major SW64, 32-row blocks LBO = tap_bytes apart), B = D tile
                         const uint32_t sB = sA + L.a_bytes;
-                        const uint64_t tx_ = umma_smem_desc(0, L.tap_bytes, 512, 4);
+                        const uint64_t tx_ = umma_smem_desc(0, xbox, 512, 4);
                         const uint32_t idesc_s = umma_idesc_bf16(128, p.BNs, 1, 1);
 #pragma unroll
                         for (int ks = 0; ks < kWgKP / 16; ++ks) {
                             const uint64_t xa_hi = tx_ + (uint64_t)((sB + ks * 1024) >> 4);
-                            const uint64_t xa_lo = tx_ + (uint64_t)((sB + xbox + ks * 1024) >> 4);
+                            const uint64_t xa_lo = tx_ + (uint64_t)((sB + lo_off + ks * 1024) >> 4);
                             const uint64_t d_hi = a_hi0 + (uint64_t)(ks * (2048 >> 4));
                             const uint64_t d_lo = a_lo0 + (uint64_t)(ks * (2048 >> 4));
                             umma_f16(d_tmem, xa_hi, d_hi, idesc_s, (k != k0 || ks != 0));
@@ -228,24 +230,22 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                         umma_commit(&empty_bar[stage]);
                     }
                 } else if (elect_one()) {
+                    // ONE MMA per term covers all taps of the group: their X boxes sit side by side in shared memory, i.e.
+                    // they are consecutive 64-wide N blocks (LBO = one box) of an N = gsz * nboxes * 64 operand, and the
+                    // accumulator of tap g is the column range [g*cstride, g*cstride + BN).  The D tile is then read from
+                    // shared memory once per term instead of once per tap and term (these MMAs are SMEM-bandwidth-bound).
+                    const uint32_t sB = sA + L.a_bytes;
+                    const uint32_t idesc_g = umma_idesc_bf16(128, gsz * nboxes_b * 64, 1, 1);
 #pragma unroll
                     for (int ks = 0; ks < kWgKP / 16; ++ks) {
                         const uint64_t a_hi = a_hi0 + (uint64_t)(ks * (2048 >> 4));
                         const uint64_t a_lo = a_lo0 + (uint64_t)(ks * (2048 >> 4));
-                        const uint32_t accum = (k != k0 || ks != 0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (g < gsz) {
-                                const uint32_t sB = sA + L.a_bytes + (uint32_t)g * L.tap_bytes;
-                                const uint32_t dg = d_tmem + (uint32_t)(g * p.cstride);
-                                const uint64_t b_hi = tmpl_x + (uint64_t)((sB + ks * xstep) >> 4);
-                                umma_f16(dg, a_hi, b_hi, idesc, accum);
-                                if (split) {
-                                    const uint64_t b_lo = tmpl_x + (uint64_t)((sB + nboxes_b * xbox + ks * xstep) >> 4);
-                                    umma_f16(dg, a_lo, b_hi, idesc, 1);
-                                    umma_f16(dg, a_hi, b_lo, idesc, 1);
-                                }
-                            }
+                        const uint64_t b_hi = tmpl_x + (uint64_t)((sB + ks * xstep) >> 4);
+                        umma_f16(d_tmem, a_hi, b_hi, idesc_g, (k != k0 || ks != 0));
+                        if (split) {
+                            const uint64_t b_lo = tmpl_x + (uint64_t)((sB + lo_off + ks * xstep) >> 4);
+                            umma_f16(d_tmem, a_lo, b_hi, idesc_g, 1);
+                            umma_f16(d_tmem, a_hi, b_lo, idesc_g, 1);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -359,11 +359,12 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     }
     p.swap = (p.x32 && p.Cout <= 128 && p.Cout % 32 == 0 && p.Cin == 32) ? 1 : 0;
     p.BNs = (p.Cout + 15) / 16 * 16;
+    if (p.x32 && !p.swap) { set_last_error_msg("conv1a_wgrad: Cout must be a multiple of 32 and <= 128"); return OTAL_ERR_UNSUPPORTED; }
     // taps per work item: as many accumulators as fit 256 TMEM columns (double buffered) and two pipeline stages of
     // shared memory (D tile + G X tiles, 16 KB per box pair in bf16x3)
     {
         const int nbx = (p.BN + 63) / 64;
-        p.cstride = (p.BN + 31) / 32 * 32;
+        p.cstride = nbx * 64;                                        // one 64-wide N block per X box
         int G = 256 / p.cstride;
         if (G > 4 / nbx) G = 4 / nbx;
         if (G > ntaps) G = ntaps;
