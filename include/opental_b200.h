@@ -96,6 +96,13 @@ typedef struct otal_conv_desc {
     const float* scale; const float* shift;       /* [Cout] or NULL */
     uint16_t* y_hi; uint16_t* y_lo;               /* NULL = do not store bf16 planes */
     float* y_f32;                                 /* NULL = do not store fp32 */
+    /* Optional second K segment, 1x1 stride-1 convs only (Cin2 = 0: unused): y = [x | x2] . [w ; w2].  Used to compute the
+     * data gradient of several 1x1 convs that share their input (the b0 / b1a / b2a branches of an inception module,
+     * AFSD/common/i3d_backbone.py:116-121) in one pass instead of one read-modify-write pass per branch.
+     * x2: planes [N,T,H,W,in2_cstride], channels [in2_coff, in2_coff + Cin2); w2: [1][Cout][Cin2] (dgrad: [1][Cin2][Cout]). */
+    int Cin2, in2_cstride, in2_coff;
+    const uint16_t* x2_hi; const uint16_t* x2_lo;
+    const uint16_t* w2_hi; const uint16_t* w2_lo;
 } otal_conv_desc;
 
 OTAL_API int otal_conv_igemm_fwd(const otal_conv_desc* desc, void* stream);

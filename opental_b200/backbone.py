@@ -324,16 +324,25 @@ class I3DBackbone(nn.Module):
         g_x = torch.empty((*shape, x.hi.shape[-1]), dtype=torch.float32, device=dev)
         g_mid = torch.empty((*shape, mid.hi.shape[-1]), dtype=torch.float32, device=dev)
         g_pool = torch.empty((*shape, x.hi.shape[-1]), dtype=torch.float32, device=dev)
-        w1a = c["b1a"].cout
-        self._conv_bwd(c["b0"], x, d_y, g_x, d_slice=(0, c["b0"].cout))
+        w1a, w2a = c["b1a"].cout, c["b2a"].cout
+        self._conv_bwd(c["b0"], x, d_y, None, d_slice=(0, c["b0"].cout))                    # weight gradient only
         self._conv_bwd(c["b1b"], mid, d_y, g_mid, in_slice=(0, w1a), d_slice=(o1, c["b1b"].cout), gx_off=0)
-        self._conv_bwd(c["b2b"], mid, d_y, g_mid, in_slice=(w1a, c["b2a"].cout), d_slice=(o2, c["b2b"].cout), gx_off=w1a)
+        self._conv_bwd(c["b2b"], mid, d_y, g_mid, in_slice=(w1a, w2a), d_slice=(o2, c["b2b"].cout), gx_off=w1a)
         self._conv_bwd(c["b3b"], pooled, d_y, g_pool, d_slice=(o3, c["b3b"].cout))
-        del d_y
         sc_m = self._scale[c["b1a"].bn_off:c["b1a"].bn_off + mid.hi.shape[-1]]   # [b1a|b2a] contiguous by design
         d_m = ops.relu_bn_bwd_split(g_mid, mid, sc_m, with_lo=with_lo)
-        self._conv_bwd(c["b1a"], x, d_m, g_x, d_slice=(0, w1a), accumulate=True)
-        self._conv_bwd(c["b2a"], x, d_m, g_x, d_slice=(w1a, c["b2a"].cout), accumulate=True)
+        self._conv_bwd(c["b1a"], x, d_m, None, d_slice=(0, w1a))
+        self._conv_bwd(c["b2a"], x, d_m, None, d_slice=(w1a, w2a))
+        # data gradient of the three 1x1 convs that read x (b0, b1a, b2a) in ONE pass: K-concatenated
+        # [d_y(b0) | d_m] . [W_b0 ; W_b1a ; W_b2a] — g_x is written once instead of one write + two read-modify-writes
+        r1, r2 = c["b1a"], c["b2a"]
+        assert r1.w_off + r1.numel == r2.w_off          # b1a and b2a are adjacent in the flat weight buffer
+        sl = slice(r1.w_off, r2.w_off + r2.numel)
+        w12 = Planes(self._wp.hi[sl].view(1, w1a + w2a, r1.cin),
+                     self._wp.lo[sl].view(1, w1a + w2a, r1.cin) if self._wp.lo is not None else None)
+        ops.conv_igemm(d_y, self._w(c["b0"]), kernel=(1, 1, 1), pad_front=(0, 0, 0), in_slice=(0, c["b0"].cout), out_f32=g_x,
+                       out_slice=(0, c["b0"].cin), want_planes=False, dgrad=True, x2=d_m, w2=w12)
+        del d_y
         ops.maxpool_bwd(x, g_pool, g_x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)), argmax=parg)
         return g_x
 

@@ -57,6 +57,8 @@ struct ConvParams {
     int accumulate;  // fp32 destination: y += result (dgrad into a shared gradient buffer)
     int out_ncdhw;   // fp32 destination is channel-major [N, out_cstride, T, H, W] instead of channels-last
     int b_mn;        // dgrad mode: weights are read as [tap][K][N] (N contiguous, "MN-major" B) and taps are flipped
+    int kchunks2;    // second K segment (1x1 convs only): extra 64-channel chunks read through the A2 / B2 maps, i.e.
+                     // D = [x | x2] . [w ; w2] — the data gradients of several 1x1 convs that share their input, in ONE pass
     int k32;         // K chunk of 32 elements = 64-byte rows, SWIZZLE_64B operands (the folded Conv3d_1a: 8 W taps x 4 channels)
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
@@ -90,6 +92,7 @@ __host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nst
 struct alignas(64) ConvMaps {
     CUtensorMap A_hi[8], A_lo[8];
     CUtensorMap B_hi, B_lo, O_hi, O_lo;
+    CUtensorMap A2_hi, A2_lo, B2_hi, B2_lo;      // second K segment (kchunks2 > 0)
 };
 
 // d = tap offset - front pad along one dim with stride s: input index = s*o + d = s*(o + q) + par
@@ -140,7 +143,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     const uint32_t tmem_base = *tmem_ptr;
 
     const int ntaps = p.kt * p.kh * p.kw;
-    const int kiters = ntaps * p.kchunks;
+    const int kiters = ntaps * p.kchunks + p.kchunks2;
     const int kchunk_elems = p.k32 ? 32 : kChunkK;
 
     if (warp == 0) {
@@ -197,6 +200,29 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         }
                     }
                 }
+            }
+            for (int kc = 0; kc < p.kchunks2; ++kc) {          // second K segment (1x1, stride 1: no tap offsets)
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
+                    unsigned char* sB = sA + L.a_bytes;
+                    mbar_expect_tx(&full_bar[stage], L.stage_bytes);
+                    const int c0 = kc * kChunkK;
+                    tma_load_5d(&maps.A2_hi, &full_bar[stage], sA, c0, w0, h0, t0, n);
+                    if (!p.b_mn) {
+                        tma_load_3d(&maps.B2_hi, &full_bar[stage], sB, c0, nb * p.BN, 0);
+                        if (split) tma_load_3d(&maps.B2_lo, &full_bar[stage], sB + b_plane, c0, nb * p.BN, 0);
+                    } else {
+                        const int nbx = (p.BN + 63) / 64;
+                        for (int j = 0; j < nbx; ++j) {
+                            tma_load_3d(&maps.B2_hi, &full_bar[stage], sB + j * 8192, nb * p.BN + j * 64, c0, 0);
+                            if (split) tma_load_3d(&maps.B2_lo, &full_bar[stage], sB + b_plane + j * 8192, nb * p.BN + j * 64, c0, 0);
+                        }
+                    }
+                    if (split) tma_load_5d(&maps.A2_lo, &full_bar[stage], sA + a_plane, c0, w0, h0, t0, n);
+                }
+                __syncwarp();
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -390,6 +416,8 @@ struct ConvLaunch {
     const uint16_t *w_hi, *w_lo;      // [taps][Cout][KW] bf16 planes, KW = weight row width (Cin or 64 for conv1a);
                                       // dgrad (b_mn): [taps][K = w_k][N = Cout]
     int w_k;                          // reduction width in elements
+    const uint16_t *w2_hi = nullptr, *w2_lo = nullptr;   // second K segment weights (w2_k reduction elements), or null
+    int w2_k = 0;
     uint16_t *y_hi, *y_lo;
     int To, Ho, Wo;                   // output extent
 };
@@ -447,6 +475,14 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     const int bswz = p.k32 ? 2 : 1;                                   // 2 = SWIZZLE_64B (make_tensor_map_bf16)
     if ((rc = make_tensor_map_bf16(&maps.B_hi, L.w_hi, 3, bdims, bst, bbox, bswz))) return rc;
     if (split && (rc = make_tensor_map_bf16(&maps.B_lo, L.w_lo, 3, bdims, bst, bbox, bswz))) return rc;
+    if (L.w2_k > 0) {
+        const uint64_t brow2 = p.b_mn ? (uint64_t)p.Cout : (uint64_t)L.w2_k;
+        const uint64_t bcol2 = p.b_mn ? (uint64_t)L.w2_k : (uint64_t)p.Cout;
+        const uint64_t bdims2[3] = {brow2, bcol2, 1};
+        const uint64_t bst2[2] = {brow2 * 2, brow2 * 2 * bcol2};
+        if ((rc = make_tensor_map_bf16(&maps.B2_hi, L.w2_hi, 3, bdims2, bst2, bbox, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.B2_lo, L.w2_lo, 3, bdims2, bst2, bbox, 1))) return rc;
+    }
     if (p.store_bf16) {
         const uint32_t obox[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
         const uint64_t odims[5] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.N};
@@ -532,6 +568,21 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
         const int mi = rt * 4 + rh * 2 + rw;
         if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 1))) return rc;
         if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 1))) return rc;
+    }
+    if (d->Cin2 > 0) {
+        // second K segment: x2 [N,T,H,W,in2_cstride] planes (channels [in2_coff, in2_coff + Cin2)), w2 [1][Cout][Cin2]
+        // (dgrad: [1][Cin2][Cout]); 1x1 stride-1 only
+        if (d->kt * d->kh * d->kw != 1 || st != 1 || sh != 1 || sw != 1 || d->Cin2 % 8 || d->in2_cstride % 8 || d->in2_coff % 8 ||
+            !d->x2_hi || !d->w2_hi || (split && (!d->x2_lo || !d->w2_lo))) {
+            set_last_error_msg("conv: the second K segment needs a 1x1 stride-1 conv and complete x2 / w2 planes"); return OTAL_ERR_BAD_ARG;
+        }
+        p.kchunks2 = (d->Cin2 + kChunkK - 1) / kChunkK;
+        const uint64_t cs2 = (uint64_t)d->in2_cstride * 2;
+        const uint64_t adims[5] = {(uint64_t)d->Cin2, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->T, (uint64_t)p.N};
+        const uint64_t ast[4] = {cs2, cs2 * d->W, cs2 * d->W * d->H, cs2 * d->W * d->H * d->T};
+        if ((rc = make_tensor_map_bf16(&maps.A2_hi, d->x2_hi + d->in2_coff, 5, adims, ast, abox, 1))) return rc;
+        if (split && (rc = make_tensor_map_bf16(&maps.A2_lo, d->x2_lo + d->in2_coff, 5, adims, ast, abox, 1))) return rc;
+        L.w2_hi = d->w2_hi; L.w2_lo = d->w2_lo; L.w2_k = d->Cin2;
     }
     return finish_and_launch(L, maps, stream);
 }

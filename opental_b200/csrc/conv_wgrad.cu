@@ -301,10 +301,16 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                     }
                     tmem_ld_wait();
                     if (co < p.Cout) {
+                        // 16-byte vector reductions (red.global.add.v4.f32): Cin, BN and col0 are multiples of 4 and dW
+                        // blocks are 32-byte aligned, so groups of 4 columns are all-in or all-out and aligned
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < 32; j += 4) {
                             const int ci = nb * p.BN + col0 + j;
-                            if (col0 + j < p.BN && ci < p.Cin) atomicAdd(dst + col0 + j, __uint_as_float(v[j]));
+                            if (col0 + j < p.BN && ci < p.Cin)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + col0 + j),
+                                             "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                             "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                             : "memory");
                         }
                     }
                 }

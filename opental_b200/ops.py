@@ -206,7 +206,8 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                in_slice: tuple[int, int] | None = None, out: Planes | None = None,
                out_slice: tuple[int, int] | None = None, out_f32: torch.Tensor | None = None,
                want_planes: bool = True, tile: tuple[int, int, int] | None = None,
-               accumulate: bool = False, dgrad: bool = False, f32_ncdhw: bool = False) -> Planes | None:
+               accumulate: bool = False, dgrad: bool = False, f32_ncdhw: bool = False,
+               x2: Planes | None = None, w2: Planes | None = None, in2_slice: tuple[int, int] | None = None) -> Planes | None:
     """y = relu?(conv(x, w) * scale + shift).  x: NDHWC planes [N,T,H,W,Cx]; w: [taps,Cout,Cin] planes.
 
     in_slice = (offset, Cin) reads a channel slice of x; out/out_slice = write into a slice of an existing buffer.
@@ -256,13 +257,24 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                  y_hi=_ptr(out.hi) if out is not None else None,
                  y_lo=_ptr(out.lo) if (out is not None and nsplit == 3) else None,
                  y_f32=_ptr(out_f32))
+    flops2 = 0.0
+    if x2 is not None:
+        # second K segment (1x1 only): y = [x | x2] . [w ; w2]
+        assert w2 is not None and taps == 1 and tuple(x2.hi.shape[:4]) == (N, T, H, W)
+        c2 = w2.hi.shape[1] if dgrad else w2.hi.shape[2]
+        off2, used2 = in2_slice if in2_slice is not None else (0, x2.hi.shape[-1])
+        assert used2 == c2 and (w2.hi.shape[2] if dgrad else w2.hi.shape[1]) == Cout
+        d.Cin2, d.in2_cstride, d.in2_coff = c2, x2.hi.shape[-1], off2
+        d.x2_hi, d.x2_lo = x2.hi.data_ptr(), (_ptr(x2.lo) if nsplit == 3 else None)
+        d.w2_hi, d.w2_lo = w2.hi.data_ptr(), (_ptr(w2.lo) if nsplit == 3 else None)
+        flops2 = 2.0 * N * To * Ho * Wo * Cout * c2
     t0 = PROFILE.begin()
     if _lib.TRACE is not None:
         _lib.LABEL = (f"{'dgrad' if dgrad else 'fwd'} N{N} {T}x{H}x{W} Cin{Cin} Cout{Cout} k{kt}{kh}{kw} s{stride[0]}{stride[1]}{stride[2]} "
                       f"x{nsplit} tile{tT}x{tH}x{tW}{' f32' if out_f32 is not None else ''}{' acc' if accumulate else ''}",
-                      2.0 * N * To * Ho * Wo * Cout * Cin * taps)
+                      2.0 * N * To * Ho * Wo * Cout * Cin * taps + flops2)
     _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
-    PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps)
+    PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps + flops2)
     return out
 
 
