@@ -299,6 +299,17 @@ def run_native(args):
                    "executed_tflops": ach * hw, "executed_frac": ach * hw / peak_tf,
                    "note": f"achieved = algorithmic fp32-semantic conv FLOPs / event-timed kernel time; {args.precision} executes {hw:.0f}x "
                            f"those FLOPs on the bf16 pipe; peak = {peak_src}"}
+    try:      # DRAM traffic of the dominant kernel's largest launch, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+            ncu_traffic = json.load(fh)
+    except Exception:  # noqa: BLE001
+        ncu_traffic = {}
+    for k in roof:
+        t = ncu_traffic.get(k)
+        if t:
+            roof[k]["traffic"] = t["dram_bytes"]
+            roof[k]["traffic_note"] = (f"dram__bytes_read+write of one launch ({t['launch']}): {t['dram_bytes'] / 1e6:.0f} MB vs "
+                                       f"{t['algorithmic_bytes'] / 1e6:.0f} MB algorithmic; tensor pipe active {t['tensor_pipe_active_pct']}% (ncu)")
     big = [k for k in roof if "head" not in k]
     dominant = max(big, key=lambda k: roof[k]["ms_per_step"]) if big else None
 

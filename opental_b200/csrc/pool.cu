@@ -262,6 +262,116 @@ maxpool_bwd_argmax_kernel(const PoolParams p, const unsigned char* __restrict__ 
     }
 }
 
+// (3,3,3) / stride 1 (the b3a pool of every inception module): each input is needed by 27 windows, so the W-blocked
+// kernel above re-reads it ~13x from L2 (measured ~8 TB/s of L2 traffic, profiles/r01_pool_bench.txt).  Here one CTA
+// stages the integer keys of a (tT+2) x (tH+2) x (tW+2) halo tile for 64 channels in shared memory (each input is
+// fetched ~2.7x instead) and every thread scans its windows out of shared memory with two conflict-free 16-byte loads
+// per tap.  Shared layout per position: 256 bytes = [8 channel groups x 4 keys (channels 0-3)][8 groups x 4 keys (4-7)].
+struct PoolTile { int tT, tH, tW, tilesT, tilesH, tilesW, cchunks; };
+
+__global__ void __launch_bounds__(256)
+maxpool333_tiled_kernel(const PoolParams p, const PoolTile tl, unsigned char* __restrict__ argmax) {
+    extern __shared__ __align__(16) unsigned char pool_smem[];
+    uint4* keys = reinterpret_cast<uint4*>(pool_smem);                 // [halo positions][2 halves][8 cgs] x 16 B
+    constexpr uint32_t KEY_ZERO = 0x80008000u;
+    const int cgs = p.C >> 3;
+    int b = blockIdx.x;
+    const int cchunk = b % tl.cchunks; b /= tl.cchunks;
+    const int iw = b % tl.tilesW; b /= tl.tilesW;
+    const int ih = b % tl.tilesH; b /= tl.tilesH;
+    const int it = b % tl.tilesT;
+    const int n = b / tl.tilesT;
+    const int t0 = it * tl.tT, h0 = ih * tl.tH, w0 = iw * tl.tW;      // first output of the tile (= input coordinate)
+    const int eT = tl.tT + 2, eH = tl.tH + 2, eW = tl.tW + 2;
+    const int halo = eT * eH * eW;
+    // ---- stage keys: item = (halo position, channel group)
+    for (int i = threadIdx.x; i < halo * 8; i += blockDim.x) {
+        const int cgl = i & 7, hp = i >> 3;
+        const int cg = cchunk * 8 + cgl;
+        const int xw = hp % eW, xh = (hp / eW) % eH, xt = hp / (eW * eH);
+        const int t = t0 - 1 + xt, h = h0 - 1 + xh, w = w0 - 1 + xw;
+        uint4 k0 = make_uint4(KEY_ZERO, KEY_ZERO, KEY_ZERO, KEY_ZERO), k1 = k0;   // zero padding competes as 0
+        if (cg < cgs && t >= 0 && t < p.T && h >= 0 && h < p.H && w >= 0 && w < p.W) {
+            const size_t off = ((((size_t)n * p.T + t) * p.H + h) * p.W + w) * p.in_cstride + p.in_coff + cg * 8;
+            const uint4 hv = *reinterpret_cast<const uint4*>(p.x_hi + off);
+            uint4 lv = make_uint4(0, 0, 0, 0);
+            if (p.x_lo) lv = *reinterpret_cast<const uint4*>(p.x_lo + off);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+            uint32_t key[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t th = key_fwd2(hw[j]), tl_ = key_fwd2(lw[j]);
+                key[2 * j] = __byte_perm(tl_, th, 0x5410);
+                key[2 * j + 1] = __byte_perm(tl_, th, 0x7632);
+            }
+            k0 = make_uint4(key[0], key[1], key[2], key[3]);
+            k1 = make_uint4(key[4], key[5], key[6], key[7]);
+        }
+        keys[hp * 16 + cgl] = k0;
+        keys[hp * 16 + 8 + cgl] = k1;
+    }
+    __syncthreads();
+    // ---- scan: item = (output position of the tile, channel group)
+    const int nout = tl.tT * tl.tH * tl.tW;
+    for (int i = threadIdx.x; i < nout * 8; i += blockDim.x) {
+        const int cgl = i & 7, op = i >> 3;
+        const int cg = cchunk * 8 + cgl;
+        const int ow = op % tl.tW, oh = (op / tl.tW) % tl.tH, ot = op / (tl.tW * tl.tH);
+        const int to = t0 + ot, ho = h0 + oh, wo = w0 + ow;
+        if (cg >= cgs || to >= p.To || ho >= p.Ho || wo >= p.Wo) continue;
+        const bool pad = to == 0 || ho == 0 || wo == 0 || to + 1 >= p.T || ho + 1 >= p.H || wo + 1 >= p.W;
+        uint32_t best[8], arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = pad ? KEY_ZERO : 0u; arg[j] = 255u; }
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+                for (int dw = 0; dw < 3; ++dw) {
+                    const int hp = ((ot + dt) * eH + (oh + dh)) * eW + (ow + dw);
+                    const uint4 a = keys[hp * 16 + cgl], c = keys[hp * 16 + 8 + cgl];
+                    const uint32_t k[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                    const uint32_t code = (uint32_t)((dt * 3 + dh) * 3 + dw);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (k[j] > best[j]) { best[j] = k[j]; arg[j] = code; }
+                }
+        const long long opos = (((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo;
+        uint32_t oh_[4], ol_[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t ka = best[2 * j] ? best[2 * j] : KEY_ZERO, kb = best[2 * j + 1] ? best[2 * j + 1] : KEY_ZERO;
+            oh_[j] = key_inv2(__byte_perm(ka, kb, 0x7632));
+            ol_[j] = key_inv2(__byte_perm(ka, kb, 0x5410));
+        }
+        const size_t off = (size_t)opos * p.out_cstride + p.out_coff + cg * 8;
+        *reinterpret_cast<uint4*>(p.y_hi + off) = make_uint4(oh_[0], oh_[1], oh_[2], oh_[3]);
+        if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + off) = make_uint4(ol_[0], ol_[1], ol_[2], ol_[3]);
+        if (argmax) {
+            const uint32_t a0 = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+            const uint32_t a1 = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+            *reinterpret_cast<uint2*>(argmax + (size_t)opos * p.C + cg * 8) = make_uint2(a0, a1);
+        }
+    }
+}
+
+static int launch_pool333_tiled(const PoolParams& p, unsigned char* argmax, cudaStream_t s) {
+    PoolTile tl;
+    tl.tH = p.H < 6 ? p.H : 6; tl.tW = p.W < 6 ? p.W : 6; tl.tT = p.T < 4 ? p.T : 4;
+    tl.tilesT = (p.T + tl.tT - 1) / tl.tT; tl.tilesH = (p.H + tl.tH - 1) / tl.tH; tl.tilesW = (p.W + tl.tW - 1) / tl.tW;
+    tl.cchunks = ((p.C >> 3) + 7) / 8;
+    const size_t smem = (size_t)(tl.tT + 2) * (tl.tH + 2) * (tl.tW + 2) * 256;
+    static bool configured = false;
+    if (!configured) {
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(maxpool333_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
+    const long long blocks = (long long)p.N * tl.tilesT * tl.tilesH * tl.tilesW * tl.cchunks;
+    maxpool333_tiled_kernel<<<(unsigned)blocks, 256, smem, s>>>(p, tl, argmax);
+    return OTAL_OK;
+}
+
 template <int KT, int KH, int KW, int ST, int SH, int SW, int WB>
 static void launch_pool_fast(const PoolParams& p, unsigned char* argmax, cudaStream_t s) {
     const int wblocks = (p.Wo + WB - 1) / WB;
@@ -319,7 +429,8 @@ int otal_maxpool_fwd(const otal_pool_desc* d, void* stream) {
     };
     // WB = 2 measured best at batch 8 (profiles/r01_pool_bench.txt): these launches are bound by L2 re-reads of the
     // 27 window positions, WB = 4 shares more columns but halves the warps in flight
-    if (is(3, 3, 3, 1, 1, 1)) launch_pool_fast<3, 3, 3, 1, 1, 1, 2>(p, d->argmax, s);
+    if (is(3, 3, 3, 1, 1, 1) && p.pt == 1 && p.ph == 1 && p.pw == 1) { if ((rc = launch_pool333_tiled(p, d->argmax, s))) return rc; }
+    else if (is(3, 3, 3, 1, 1, 1)) launch_pool_fast<3, 3, 3, 1, 1, 1, 2>(p, d->argmax, s);
     else if (is(1, 3, 3, 1, 2, 2)) launch_pool_fast<1, 3, 3, 1, 2, 2, 2>(p, d->argmax, s);
     else if (is(3, 3, 3, 2, 2, 2)) launch_pool_fast<3, 3, 3, 2, 2, 2, 2>(p, d->argmax, s);
     else if (is(2, 2, 2, 2, 2, 2)) launch_pool_fast<2, 2, 2, 2, 2, 2, 2>(p, d->argmax, s);
