@@ -168,10 +168,12 @@ def run_native(args):
     tr = engine.Trainer(net, crit, lr=1e-5, weight_decay=1e-3)
     tr.broadcast_parameters(0)
 
-    # two distinct synthetic batches per rank, host (pinned) and device copies
+    # two distinct synthetic batches per rank, host (pinned) and device copies.  Clips travel in the dataset's storage
+    # format — uint8 frames [B,T,112,112,3] (AFSD/common/video2npy.py:61-74) — and are cropped to 96x96 and normalised
+    # to [-1,1] by the ingest kernel on the device (thumos_dataset.py:261-263), not by a CPU loader.
     def make_batch(j):
         idx = [rank * 1000 + j * B + i for i in range(B)]
-        clips = torch.stack([engine.normalise_clip(engine.synthetic_clip_u8(i, rank)) for i in idx])
+        clips = torch.stack([engine.synthetic_clip_u8(i, rank) for i in idx])
         tg = [engine.synthetic_targets(i, rank) for i in idx]
         sc = torch.stack([engine.synthetic_scores(t) for t in tg])
         from opental_b200.multisegment_loss import pad_targets
@@ -253,7 +255,7 @@ def run_native(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t)
         e2e = {"value": world * B * 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e, "api": "opental_b200.engine.Trainer.step on pinned host fp32 clips (prefetched H2D) + float(cost)"}
+               "ms_per_step": ms_e2e, "api": "opental_b200.engine.Trainer.step on pinned host uint8 frames [B,256,112,112,3] (H2D prefetched on a copy stream) + float(cost)"}
 
     # ---- per-kernel roofline: the same step enqueued eagerly with every tensor-core conv launch bracketed by CUDA events
     # on the launching stream (a graph replay cannot be bracketed per kernel); same process, same buffers, after the timed
@@ -328,7 +330,8 @@ def run_native(args):
         "config": {"workload": "THUMOS14 OpenTAL (configs/thumos14_opental_final.yaml --open_set) training step: BDNet fwd + MultiSegmentLoss(edl, "
                                "IBM, actionness) + boundary BCE + bwd + Adam; clips 3x256x96x96",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "precision": args.precision,
-                   "l2": "per-step inputs (226 MB of clips) and activations (GBs) exceed the 126 MB L2; two alternating batches",
+                   "input": "uint8 frames [B,256,112,112,3], centre crop 96 + normalisation in the ingest kernel",
+                   "l2": "per-step activations and gradients (several GB) exceed the 126 MB L2; two alternating input batches",
                    "ssl_pass": False, "cuda_graph": not args.no_graph},
         "clocks": clocks,
         "e2e": e2e,

@@ -123,6 +123,8 @@ class I3DBackbone(nn.Module):
         self._flat_dev = None
         self._anchor = None
         self.on_backward_start = None     # optional callback (the trainer overlaps the head's all-reduce here)
+        self.crop_size = 96               # uint8 input path: crop extent (config dataset.training.crop_size)
+        self.crop_offsets = None          # optional int32 [N,3] device tensor (row, column, mirror) per sample
         self.reset_parameters()
 
     # ------------------------------------------------------------------------------------------------ structure
@@ -268,12 +270,18 @@ class I3DBackbone(nn.Module):
 
     def forward_planes(self, x: torch.Tensor, saved: dict) -> dict:
         """Runs the whole backbone; `saved` receives every tensor the backward schedule needs."""
-        assert x.is_cuda and x.dim() == 5 and x.shape[1] == 3, "expected a CUDA clip batch [N,3,T,H,W]"
+        with_lo = self.precision == "bf16x3"
         self._ensure_flat(x.device)
         self._prepare()
-        with_lo = self.precision == "bf16x3"
-        W = x.shape[4]
-        a = ops.clip_ingest(x, with_lo)
+        if x.dtype == torch.uint8:
+            # the dataset's storage format: uint8 frames [N,T,Hs,Ws,3]; centre crop + normalisation happen in the ingest kernel
+            assert x.is_cuda and x.dim() == 5 and x.shape[4] == 3, "expected CUDA uint8 frames [N,T,Hs,Ws,3]"
+            W = self.crop_size
+            a = ops.clip_ingest_u8(x, W, self.crop_offsets, with_lo)
+        else:
+            assert x.is_cuda and x.dim() == 5 and x.shape[1] == 3, "expected a CUDA clip batch [N,3,T,H,W]"
+            W = x.shape[4]
+            a = ops.clip_ingest(x, with_lo)
         saved["clip"] = (a, W)
         r = self.convs["Conv3d_1a_7x7"]
         sc, sh = self._ss(r)

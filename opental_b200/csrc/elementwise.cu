@@ -182,6 +182,45 @@ static inline int grid_for(long long work_items, int threads) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// Same output as clip_ingest_kernel, straight from the dataset's storage format: uint8 [N,T,Hs,Ws,3] frames
+// (AFSD/common/video2npy.py:61-74), cropped to H x W at a per-sample offset, optionally mirrored along W, normalised as
+// (x / 255) * 2 - 1 (AFSD/common/thumos_dataset.py:261-263; _rn intrinsics in torch's operation order: bit-identical).
+// Replaces the CPU crop / flip / normalise of the data loader (videotransforms.py:30-124) and a 4x larger H2D copy.
+__global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, const int* __restrict__ crop, uint16_t* __restrict__ hi,
+                                      uint16_t* __restrict__ lo, int N, int T, int Hs, int Ws, int H, int W, int oh_def, int ow_def) {
+    const int Wo = W >> 1;
+    const long long total = (long long)N * T * H * Wo * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int pp = (int)(i & 3);
+        const long long win = i >> 2;
+        const int wo = (int)(win % Wo);
+        long long row = win / Wo;                     // (n*T + t)*H + h
+        const int h = (int)(row % H); row /= H;
+        const int t = (int)(row % T);
+        const int n = (int)(row / T);
+        const int oh = crop ? crop[3 * n] : oh_def, ow = crop ? crop[3 * n + 1] : ow_def, flip = crop ? crop[3 * n + 2] : 0;
+        uint32_t h32[4] = {0, 0, 0, 0}, l32[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int w = 2 * wo - 2 + 2 * pp + q;
+            if (w < 0 || w >= W) continue;
+            const int ws = ow + (flip ? W - 1 - w : w);
+            const unsigned char* src = px + ((((size_t)n * T + t) * Hs + (oh + h)) * Ws + ws) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)src[c], 255.f), 2.f), 1.f);
+                __nv_bfloat16 hb, lb;
+                split_bf16(v, hb, lb);
+                h32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
+                l32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
+            }
+        }
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h32[0], h32[1], h32[2], h32[3]);
+        if (lo) reinterpret_cast<uint4*>(lo)[i] = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+    }
+}
+
 }  // namespace otal
 
 using namespace otal;
@@ -272,3 +311,15 @@ int otal_ncl_to_nlc_split(const float* x, uint16_t* hi, uint16_t* lo, int B, int
 }
 
 }  // extern "C"
+
+extern "C" int otal_clip_ingest_u8(const unsigned char* px, const int* crop, uint16_t* hi, uint16_t* lo, int N, int T, int Hs,
+                                   int Ws, int H, int W, void* stream) {
+    if (N < 0 || T <= 0 || Hs <= 0 || Ws <= 0 || H <= 0 || W <= 0 || (W & 1) || H > Hs || W > Ws || !px || !hi) {
+        otal::set_last_error_msg("clip_ingest_u8: bad argument (W even, crop inside the frame)"); return OTAL_ERR_BAD_ARG;
+    }
+    if (N == 0) return OTAL_OK;
+    otal::clip_ingest_u8_kernel<<<otal::grid_for((long long)N * T * H * (W / 2) * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        px, crop, hi, lo, N, T, Hs, Ws, H, W, (Hs - H) / 2, (Ws - W) / 2);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}

@@ -327,6 +327,20 @@ def clip_ingest(x: torch.Tensor, with_lo: bool = True) -> Planes:
     return Planes(hi, lo)
 
 
+def clip_ingest_u8(px: torch.Tensor, crop: int = 96, offsets: torch.Tensor | None = None, with_lo: bool = True) -> Planes:
+    """uint8 frames [N,T,Hs,Ws,3] -> window-expanded planes of the normalised crop ((x/255)*2-1, bit-identical to torch).
+    offsets: optional int32 device tensor [N,3] = (row offset, column offset, mirror flag); default centre crop."""
+    _require_cuda(px)
+    assert px.dtype == torch.uint8 and px.dim() == 5 and px.shape[-1] == 3 and px.is_contiguous()
+    N, T, Hs, Ws, _ = px.shape
+    if offsets is not None:
+        assert offsets.dtype == torch.int32 and offsets.is_cuda and tuple(offsets.shape) == (N, 3) and offsets.is_contiguous()
+    hi = torch.empty((N, T, crop, crop // 2, CLIP_WIN * CLIP_CPAD), dtype=torch.bfloat16, device=px.device)
+    lo = torch.empty_like(hi) if with_lo else None
+    _lib.call("otal_clip_ingest_u8", px.data_ptr(), _ptr(offsets), hi.data_ptr(), _ptr(lo), N, T, Hs, Ws, crop, crop, _stream())
+    return Planes(hi, lo)
+
+
 def pack_conv1a_weight(w: torch.Tensor, with_lo: bool = True) -> Planes:
     """[Cout, 3, 7, 7, 7] fp32 -> [49 (dt,dh), Cout, 32] planes, row element dw*4 + c (zero for dw == 7, c == 3)."""
     Cout, C, kt, kh, kw = w.shape

@@ -309,3 +309,38 @@ def test_head_valid3d_conv():
     assert rel(xl.grad.permute(0, 4, 1, 2, 3).cpu(), gx_ref) < TOL
     assert rel(conv.weight.grad.cpu(), gw_ref) < TOL
     assert rel(conv.bias.grad.cpu(), gb_ref) < TOL
+
+
+def test_clip_ingest_u8_bit_exact():
+    """uint8 frames -> planes in one kernel == the data loader's crop / flip / (x/255)*2-1 followed by the fp32 ingest."""
+    from opental_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    N, T, Hs, Ws, crop = 3, 6, 28, 30, 24
+    px = torch.randint(0, 256, (N, T, Hs, Ws, 3), generator=g, dtype=torch.uint8)
+
+    def loader(px, oh, ow, flip):
+        x = px[:, oh:oh + crop, ow:ow + crop, :]
+        if flip:
+            x = x.flip(2)
+        return (x.permute(3, 0, 1, 2).float() / 255.0) * 2.0 - 1.0          # thumos_dataset.py:261-263
+
+    # centre crop, no mirroring (the default)
+    ref = ops.clip_ingest(torch.stack([loader(px[n], (Hs - crop) // 2, (Ws - crop) // 2, False) for n in range(N)]).cuda())
+    got = ops.clip_ingest_u8(px.cuda(), crop)
+    assert torch.equal(got.hi, ref.hi) and torch.equal(got.lo, ref.lo)
+    # per-sample random crop + mirror flag
+    offs = torch.tensor([[0, 0, 0], [4, 6, 1], [2, 3, 1]], dtype=torch.int32)
+    ref = ops.clip_ingest(torch.stack([loader(px[n], int(offs[n, 0]), int(offs[n, 1]), bool(offs[n, 2])) for n in range(N)]).cuda())
+    got = ops.clip_ingest_u8(px.cuda(), crop, offs.cuda())
+    assert torch.equal(got.hi, ref.hi) and torch.equal(got.lo, ref.lo)
+
+
+def test_backbone_accepts_uint8_frames():
+    from opental_b200 import engine
+    net, _ = engine.build_opental(epoch=1)
+    px = engine.synthetic_clip_u8(0, frames=64).unsqueeze(0).cuda()
+    x = engine.normalise_clip(px[0].cpu()).unsqueeze(0).cuda()
+    with torch.no_grad():
+        a = net.backbone(px)
+        b = net.backbone(x)
+    assert torch.equal(a["Mixed_5c"], b["Mixed_5c"]) and torch.equal(a["Mixed_4f"], b["Mixed_4f"])

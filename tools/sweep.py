@@ -1,0 +1,80 @@
+"""Clip-length x batch sweep (BASELINE.json configs[4]): training clips/s of one GPU for T in {128,256,512,1024} and
+B in {1,2,4,8,16}, with the per-point tensor-pipe roofline fraction (algorithmic conv FLOPs / measured bf16 peak).
+
+    python tools/sweep.py [--frames 128 256 512 1024] [--batches 1 2 4 8 16] > gpurun_out/sweep.txt
+
+Conv FLOPs scale linearly in T: backbone 0.638 GFLOP/frame forward; the head is sized for T/4 positions.
+Each point: CUDA-graph captured step, 2 warm-up + 5 timed replays, CUDA events."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from opental_b200 import engine  # noqa: E402
+from opental_b200.multisegment_loss import pad_targets  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, nargs="+", default=[128, 256, 512, 1024])
+    ap.add_argument("--batches", type=int, nargs="+", default=[1, 2, 4, 8, 16])
+    ap.add_argument("--precision", default="bf16x3")
+    args = ap.parse_args()
+    peak = 1398.1
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+    except Exception:  # noqa: BLE001
+        pass
+    dev = torch.device("cuda", 0)
+    print(f"# frames batch ms/step clips/s train_TFLOP/s(alg) frac_of_{peak:.0f}TF  peak_mem_GB   ({args.precision})")
+    for T in args.frames:
+        torch.manual_seed(0)
+        net, crit = engine.build_opental(device=dev, precision=args.precision, frame_num=T, epoch=11)
+        tr = engine.Trainer(net, crit)
+        # fwd + dgrad + wgrad conv FLOPs per clip, linear in T (466.45 GF at T = 256)
+        flop_clip = 466.45e9 * T / 256.0
+        for B in args.batches:
+            try:
+                torch.cuda.reset_peak_memory_stats()
+                clips = torch.rand(B, 3, T, 96, 96, device=dev) * 2 - 1
+                tg = [engine.synthetic_targets(i) for i in range(B)]
+                sc = torch.stack([engine.synthetic_scores(t, frames=T) for t in tg]).to(dev)
+                tp, tv = (t.to(dev) for t in pad_targets(tg, device="cpu"))
+                tr._graph = None
+                mode = "graph"
+                try:
+                    tr.capture(clips, (tp, tv), sc)
+                except Exception:  # noqa: BLE001   (B*priors > 4096: the loss takes the torch formulation, which synchronises)
+                    tr._graph = None
+                    mode = "eager"
+                    torch.cuda.synchronize()
+                for _ in range(2):
+                    tr.step(clips, (tp, tv), sc)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    tr.step(clips, (tp, tv), sc)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                tf = B * flop_clip / (ms * 1e-3) / 1e12
+                print(f"{T:6d} {B:5d} {ms:8.2f} {B * 1000.0 / ms:8.1f} {tf:10.1f} {tf / peak:8.3f} {torch.cuda.max_memory_allocated() / 2**30:8.1f}  {mode}",
+                      flush=True)
+            except Exception as ex:  # noqa: BLE001
+                print(f"{T:6d} {B:5d} failed: {repr(ex)[:200]}", flush=True)
+            finally:
+                tr._graph = None
+                tr._graph_out = None
+                tr._static = None
+                torch.cuda.empty_cache()
+        del tr, net, crit
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
