@@ -150,9 +150,72 @@ def model_cases():
     ns.restore_cuda()
 
 
+def anet_cases():
+    """ActivityNet flavour (configs/anet_opental.yaml --open_set): 768-frame clip, 150 classes, 189 priors, the
+    per-sample loss.  Run in its own process (`--anet`): the reference's config is a per-process global."""
+    ns = ref_loader.load_reference(config="configs/anet_opental.yaml", extra_args=("--open_set", "--split=0"), flavour="anet")
+    cfg = O.anet_config()
+    summary, arrays = {}, {}
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(8.0))      # x fpn stride 4..128 -> extents of 32..1024 frames
+    net = ns.BDNet(in_channels=3, training=False, frame_num=768, use_edl=True)
+    net.load_state_dict(sd)
+    net.train()
+    B = 2
+    x = torch.stack([O.synthetic_clip(i, frames=768) for i in range(B)])
+    targets = [O.synthetic_targets(i, num_classes=cfg.num_classes) for i in range(B)]
+    targets[1] = torch.cat([targets[1], torch.tensor([[0.40, 0.44, 17.0]])])          # a short third segment (level gating)
+    for epoch in (1, 11):
+        crit = ns.MultiSegmentLoss(cfg.num_classes, 0.5, 1.0, cls_loss_type="edl", edl_config=ns.config["training"]["edl_config"],
+                                   os_head=True)
+        crit.cls_loss.epoch = epoch
+        net.zero_grad()
+        out_r = net(x)
+        loss_r = crit([out_r[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors", "act", "prop_act")],
+                      [t.clone() for t in targets])
+        cost_r = loss_r[0] + 10 * loss_r[1] + loss_r[2] + 10 * loss_r[3] + loss_r[4] + loss_r[5] + loss_r[6]
+        cost_r.backward()
+        grads_r = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+
+        sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        state = O.LossState(epoch=epoch)
+        out_o = O.bdnet_forward(x, sdo, cfg, compat=True)
+        loss_o = O.multisegment_loss_anet(out_o, targets, state, cfg)
+        cost_o = loss_o[0] + 10 * loss_o[1] + loss_o[2] + 10 * loss_o[3] + loss_o[4] + loss_o[5] + loss_o[6]
+        cost_o.backward()
+        errs = {k: rel(out_o[k].detach(), out_r[k].detach()) for k in out_r if out_r[k] is not None}
+        lerrs = [abs(float(a) - float(b)) / max(abs(float(b)), 1e-6) for a, b in zip(loss_o, loss_r)]
+        gerrs = {k: rel(sdo[k].grad, g) for k, g in grads_r.items() if sdo[k].grad is not None}
+        missing = [k for k in grads_r if sdo[k].grad is None and grads_r[k].abs().max() > 0]
+        worst_out, worst_g = max(errs.values()), max(gerrs.values())
+        print(f"[anet epoch {epoch}] oracle vs reference: outputs {worst_out:.2e} losses {max(lerrs):.2e} grads {worst_g:.2e}"
+              f" (n={len(gerrs)}) missing={missing}  losses={[round(float(v), 4) for v in loss_r]}")
+        assert worst_out < TOL and max(lerrs) < 5e-5 and not missing, (errs, lerrs)
+        assert worst_g < 5e-2, sorted(gerrs.items(), key=lambda kv: -kv[1])[:5]
+        key = f"anet.e{epoch}"
+        summary[key] = dict(losses=[float(v) for v in loss_r], cost=float(cost_r), oracle_vs_ref_out=worst_out,
+                            oracle_vs_ref_grad=worst_g)
+        if epoch == 1:
+            for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "unct", "prop_unct", "priors"):
+                arrays[f"anet.{k}"] = out_r[k].detach().numpy()
+            for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop"):
+                arrays[f"anet.{k}.sample"] = out_r[k].detach().numpy()[:, ::8, ::8].copy()
+        fp = {}
+        for k, g in grads_r.items():
+            fp[k] = [float(g.sum()), float(g.abs().sum())]
+            arrays[f"{key}.grad.{k}"] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy().copy()
+        summary[key]["grad_fingerprint"] = fp
+    np.savez_compressed(os.path.join(GOLD, "model_anet_opental.npz"), **arrays)
+    with open(os.path.join(GOLD, "model_anet_opental.json"), "w") as fh:
+        json.dump(summary, fh, indent=1)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    bmp_cases()
-    model_cases()
+    if "--anet" in sys.argv:
+        anet_cases()
+    else:
+        bmp_cases()
+        model_cases()
     print("golden fixtures written to", GOLD)

@@ -71,6 +71,20 @@ class OracleConfig:
     # act_config (:50-52)
     act_weight: float = 0.0
     act_margin: float = 1.0
+    # 'thumos' (AFSD/thumos14) or 'anet' (AFSD/anet: single-source pyramid, loc x fpn stride, level-gated matching,
+    # per-sample loss normalisation, exp-form IBM weight)
+    variant: str = "thumos"
+    ibm_coeff: float = 10.0      # anet/cls_loss.py:99
+
+
+ANET_FPN_STRIDES = [4, 8, 16, 32, 64, 128]                                       # anet/BDNet.py:20
+ANET_BOUNDS = [[0, 30], [15, 60], [30, 120], [60, 240], [96, 768], [256, 768]]  # anet/multisegment_loss.py:69
+
+
+def anet_config() -> "OracleConfig":
+    """configs/anet_opental.yaml --open_set: 151 - 1 classes (os_head), 768-frame clips, feat_t = 768 // 8
+    (anet/BDNet.py:18-21), ActionnessLoss(weight=0.1) (anet/multisegment_loss.py:102)."""
+    return OracleConfig(num_classes=150, frame_num=768, feat_t=96, clip_length=768, act_weight=0.1, variant="anet")
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -91,12 +105,13 @@ def model_spec(cfg: OracleConfig) -> list[tuple[str, tuple[int, ...], str]]:
         out.append((prefix + "weight", (c,), "gn_w"))
         out.append((prefix + "bias", (c,), "gn_b"))
 
-    # pyramids (BDNet.py:129-168)
-    for i, (cin, k) in enumerate([(832, (1, 6, 6)), (1024, (1, 3, 3))]):
+    # pyramids (BDNet.py:129-168; anet/BDNet.py:130-155: one source, Mixed_5c)
+    sources = [(1024, (1, 3, 3))] if cfg.variant == "anet" else [(832, (1, 6, 6)), (1024, (1, 3, 3))]
+    for i, (cin, k) in enumerate(sources):
         out.append((f"{cp}pyramids.{i}.0.conv3d.weight", (HEAD_CH, cin, *k), "conv_w"))
         out.append((f"{cp}pyramids.{i}.0.conv3d.bias", (HEAD_CH,), "conv_b"))
         gn(f"{cp}pyramids.{i}.1.", HEAD_CH)
-    for i in range(2, NUM_LEVELS):
+    for i in range(len(sources), NUM_LEVELS):
         conv1d(f"{cp}pyramids.{i}.0.", HEAD_CH, HEAD_CH, 3)
         gn(f"{cp}pyramids.{i}.1.", HEAD_CH)
     for i in range(NUM_LEVELS):
@@ -388,10 +403,13 @@ def make_segments(loc, prior, t, frame_num):
 
 
 def level_priors(cfg: OracleConfig) -> list[torch.Tensor]:
-    """(c + 0.5)/t per level: BDNet.py:286-293."""
+    """(c + 0.5)/t per level: BDNet.py:286-293; ANet appends the level index: anet/BDNet.py:262-269."""
     out, t = [], cfg.feat_t
-    for _ in range(NUM_LEVELS):
-        out.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32))
+    for i in range(NUM_LEVELS):
+        if cfg.variant == "anet":
+            out.append(torch.tensor([[(c + 0.5) / t, i] for c in range(t)], dtype=torch.float32))
+        else:
+            out.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32))
         t //= 2
     return out
 
@@ -400,15 +418,22 @@ def coarse_pyramid(feats, sd, cfg: OracleConfig, compat=True, forced_segments=No
     """CoarsePyramid.forward: BDNet.py:295-432 (non-ssl path).  `forced_segments` (list of per-level
     (segments, frame_segments)) lets layer-wise parity tests bypass the discrete rounding hazard."""
     cp = "coarse_pyramid_detection."
-    B = feats["Mixed_4f"].shape[0]
+    B = feats["Mixed_5c"].shape[0]
     K = cfg.num_classes
-    x0 = gn_relu(head_unit3d_valid(feats["Mixed_4f"], sd, cp + "pyramids.0.0."), sd, cp + "pyramids.0.1.")
-    x0 = x0.squeeze(-1).squeeze(-1)
-    x1 = gn_relu(head_unit3d_valid(feats["Mixed_5c"], sd, cp + "pyramids.1.0."), sd, cp + "pyramids.1.1.")
-    x1 = x1.squeeze(-1).squeeze(-1)
-    levels = [x0 + F.interpolate(x1, x0.shape[2:], mode="nearest"), x1]
-    x = x1
-    for i in range(2, NUM_LEVELS):
+    anet = cfg.variant == "anet"
+    if anet:       # anet/BDNet.py:281-289: Mixed_5c only
+        B = feats["Mixed_5c"].shape[0]
+        x = gn_relu(head_unit3d_valid(feats["Mixed_5c"], sd, cp + "pyramids.0.0."), sd, cp + "pyramids.0.1.")
+        x = x.squeeze(-1).squeeze(-1)
+        levels, first = [x], 1
+    else:
+        x0 = gn_relu(head_unit3d_valid(feats["Mixed_4f"], sd, cp + "pyramids.0.0."), sd, cp + "pyramids.0.1.")
+        x0 = x0.squeeze(-1).squeeze(-1)
+        x1 = gn_relu(head_unit3d_valid(feats["Mixed_5c"], sd, cp + "pyramids.1.0."), sd, cp + "pyramids.1.1.")
+        x1 = x1.squeeze(-1).squeeze(-1)
+        levels, first = [x0 + F.interpolate(x1, x0.shape[2:], mode="nearest"), x1], 2
+        x = x1
+    for i in range(first, NUM_LEVELS):
         x = gn_relu(unit1d(x, sd, f"{cp}pyramids.{i}.0.", stride=2), sd, f"{cp}pyramids.{i}.1.")
         levels.append(x)
 
@@ -429,6 +454,8 @@ def coarse_pyramid(feats, sd, cfg: OracleConfig, compat=True, forced_segments=No
         t = feat.shape[2]
         loc = torch.exp(unit1d(lf, sd, cp + "loc_head.") * sd[f"{cp}loc_heads.{i}.scale"])     # ScaleExp BDNet.py:55-61
         loc = loc.view(B, 2, -1).permute(0, 2, 1).contiguous()
+        if anet:
+            loc = loc * ANET_FPN_STRIDES[i]                                                    # anet/BDNet.py:307-311
         locs.append(loc)
         confs.append(unit1d(cf, sd, cp + "conf_head.").view(B, K, -1).permute(0, 2, 1).contiguous())
         if cfg.os_head:
@@ -436,7 +463,7 @@ def coarse_pyramid(feats, sd, cfg: OracleConfig, compat=True, forced_segments=No
         if forced_segments is not None:
             segments, frame_segments = forced_segments[i]
         else:
-            segments, frame_segments = make_segments(loc, priors[i], t, cfg.frame_num)
+            segments, frame_segments = make_segments(loc, priors[i][:, :1], t, cfg.frame_num)
         segs.append((segments, frame_segments))
         lp, lp_ = proposal_branch(lf, frame, segments, frame_segments, sd, cp + "loc_proposal_branch.", compat)
         cpf, cp_ = proposal_branch(cf, frame, segments, frame_segments, sd, cp + "conf_proposal_branch.", compat)
@@ -623,6 +650,78 @@ def multisegment_loss(out, targets, state: LossState, cfg: OracleConfig):
     PN = max(int(ppos.sum()), 1)
     return (loss_l / N, loss_c / N, loss_prop_l / PN, loss_prop_c / PN + loss_iouc, loss_ct / N,
             loss_act / AN, loss_prop_act / PAN)
+
+
+def edl_loss_anet(logit, target, state: LossState, cfg: OracleConfig):
+    """EvidenceLoss of the ActivityNet flavour: same log loss, stateless exp-form IBM weight
+    1 / (||logit||_1 * exp(coeff * grad_norm) + 1e-10): anet/cls_loss.py:116-152, :225-232."""
+    K = cfg.num_classes
+    y = torch.eye(K, dtype=logit.dtype)[target]
+    alpha = torch.exp(torch.clamp(logit, -10, 10)) + 1
+    S = alpha.sum(1, keepdim=True)
+    per = (y * (torch.log(S) - torch.log(alpha))).sum(1)
+    if cfg.with_ibm and state.epoch >= cfg.ibm_start:
+        feat_norm = logit.abs().sum(1)            # NOT detached in the ANet flavour (anet/cls_loss.py:136, :229):
+        with torch.no_grad():                     # the weight back-propagates through ||logit||_1
+            a = alpha.detach()
+            u = K / a.sum(-1, keepdim=True)
+            gnorm = ((1 / a - u).abs() * y).sum(1)
+        w = 1.0 / (feat_norm * torch.exp(cfg.ibm_coeff * gnorm) + 1e-10)
+        per = w * per
+    return per.sum()
+
+
+def multisegment_loss_anet(out, targets, state: LossState, cfg: OracleConfig):
+    """ActivityNet MultiSegmentLoss.forward (cls_loss_type='edl', os_head): anet/multisegment_loss.py:106-301.
+    Per-sample loop; level-range gated matching (:156-166, bounds :69-83); refined positives need
+    IoU >= min(piou, best IoU among the positives) (:178-184); smooth-L1 refinement loss (:206); every term is
+    normalised per sample and averaged over the batch (:268-297)."""
+    loc, conf, ploc, pconf, center, priors = (out[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))
+    K, B, clip = cfg.num_classes, loc.shape[0], float(cfg.clip_length)
+    lb = torch.tensor([ANET_BOUNDS[int(l)][0] for l in priors[:, 1]], dtype=loc.dtype)[:, None]
+    rb = torch.tensor([ANET_BOUNDS[int(l)][1] for l in priors[:, 1]], dtype=loc.dtype)[:, None]
+    sums = [0.0] * 7
+    for b in range(B):
+        with torch.no_grad():
+            tr, lab = targets[b][:, :2].to(loc.dtype), targets[b][:, 2].long()
+            c = priors[:, 0]
+            left = (c[:, None] - tr[None, :, 0]) * clip
+            right = (tr[None, :, 1] - c[:, None]) * clip
+            max_dis = torch.max(left, right)
+            area = left + right
+            big = clip * 2
+            bad = (left < 0) | (right < 0) | (max_dis <= lb) | (max_dis > rb)
+            area = torch.where(bad, torch.full_like(area, big), area)
+            best, idx = area.min(1)
+            loc_t = torch.stack([(c - tr[idx, 0]) * clip, (tr[idx, 1] - c) * clip], 1)
+            conf_t = torch.where(best >= big, torch.zeros_like(lab[idx]), lab[idx])
+            iou = seg_iou(loc[b], loc_t)[0]
+            max_iou = iou[conf_t > 0].max() if (conf_t > 0).any() else torch.tensor(2.0)
+            thr = torch.minimum(torch.tensor(cfg.piou, dtype=iou.dtype), max_iou.to(iou.dtype))
+            prop_conf_t = torch.where(iou < thr, torch.zeros_like(conf_t), conf_t)
+            w = loc[b, :, 0] + loc[b, :, 1]
+            prop_loc_t = (loc_t - loc[b]) / (0.5 * w)[:, None]
+        pos, ppos = conf_t > 0, prop_conf_t > 0
+        zero = loc[b].sum() * 0
+        loss_l = seg_giou_loss(loc[b][pos], loc_t[pos]).sum() if pos.any() else zero
+        loss_prop_l = F.smooth_l1_loss(ploc[b][ppos], prop_loc_t[ppos], reduction="sum") if ppos.any() else zero
+        if pos.any():
+            pre = loc[b][pos]
+            cur = 0.5 * (pre[:, 0] + pre[:, 1]).unsqueeze(-1) * ploc[b][pos] + pre
+            q = seg_iou(cur, loc_t[pos])[0].clamp(min=0)
+            loss_ct = F.binary_cross_entropy_with_logits(center[b][pos].view(-1), q, reduction="sum")
+        else:
+            loss_ct = zero
+        loss_c = edl_loss_anet(conf[b][pos], conf_t[pos] - 1, state, cfg) if pos.any() else torch.tensor(0.0)
+        loss_act, AN = actionness_loss(out["act"][b].view(-1, 1), pos.float(), cfg)
+        loss_prop_c = edl_loss_anet(pconf[b][ppos], prop_conf_t[ppos] - 1, state, cfg) if ppos.any() else torch.tensor(0.0)
+        loss_iouc = iou_calibration(pconf[b], iou, cfg) if cfg.iou_aware else 0.0
+        loss_prop_act, PAN = actionness_loss(out["prop_act"][b].view(-1, 1), ppos.float(), cfg)
+        N, PN = max(int(pos.sum()), 1), max(int(ppos.sum()), 1)
+        terms = (loss_l / N, loss_c / N, loss_prop_l / PN, loss_prop_c / PN + loss_iouc, loss_ct / N, loss_act / AN,
+                 loss_prop_act / PAN)
+        sums = [s + t for s, t in zip(sums, terms)]
+    return tuple(s / B for s in sums)
 
 
 def boundary_bce(start, end, scores):

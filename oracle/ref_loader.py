@@ -88,8 +88,10 @@ def _fast_stub(oracle_mod, compat: bool):
 
 
 def load_reference(config="configs/thumos14_opental_final.yaml", extra_args=("--open_set", "--split=0", "--lw=1", "--cw=10",
-                   "--ctw=1", "--ssl=0.001", "--piou=0.5"), compat=True):
-    """Returns a namespace with the reference's BDNet module, MultiSegmentLoss class and config dict."""
+                   "--ctw=1", "--ssl=0.001", "--piou=0.5"), compat=True, flavour="thumos14"):
+    """Returns a namespace with the reference's BDNet module, MultiSegmentLoss class and config dict.
+    flavour: 'thumos14' or 'anet' (AFSD/<flavour>/BDNet.py, multisegment_loss.py).  The reference evaluates its config
+    once per process at import (AFSD/common/config.py:101): load ONE flavour per process."""
     import importlib
 
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -106,8 +108,8 @@ def load_reference(config="configs/thumos14_opental_final.yaml", extra_args=("--
     torch.Tensor.cuda = lambda self, *a, **k: self        # cls_loss.py:114 calls .cuda() unconditionally
     try:
         cwd = os.getcwd()
-        bdnet = importlib.import_module("AFSD.thumos14.BDNet")
-        msl = importlib.import_module("AFSD.thumos14.multisegment_loss")
+        bdnet = importlib.import_module(f"AFSD.{flavour}.BDNet")
+        msl = importlib.import_module(f"AFSD.{flavour}.multisegment_loss")
         cfg = importlib.import_module("AFSD.common.config").config
         os.chdir(cwd)
     finally:
