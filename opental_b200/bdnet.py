@@ -147,23 +147,38 @@ class _FramePoolFn(torch.autograd.Function):
         return total, None, None
 
 
-class CoarsePyramid(nn.Module):
-    """BDNet.py:117-432 (OpenTAL configuration: no RPL head, no transformer, dropout 0)."""
+ANET_FPN_STRIDES = (4, 8, 16, 32, 64, 128)      # AFSD/anet/BDNet.py:20
 
-    def __init__(self, feat_channels, num_classes, frame_num=256, os_head=False, precision="bf16x3", native_convs=True):
+
+class CoarsePyramid(nn.Module):
+    """BDNet.py:117-432 (OpenTAL configuration: no RPL head, no transformer, dropout 0).
+
+    variant='anet' is the ActivityNet flavour (AFSD/anet/BDNet.py:120-391): the pyramid starts from Mixed_5c alone
+    (:130-155, :281-289), feat_t = frame_num // 8 (:18-21), `loc` is multiplied by the level's FPN stride (:307-311) and
+    the priors carry the level index as a second column (:262-269)."""
+
+    def __init__(self, feat_channels, num_classes, frame_num=256, os_head=False, precision="bf16x3", native_convs=True,
+                 variant="thumos"):
         super().__init__()
+        assert variant in ("thumos", "anet")
         out_channels = CONV_CHANNELS
+        self.variant = variant
         self.num_classes = num_classes
         self.frame_num = frame_num
         self.os_head = os_head
         self.layer_num = LAYER_NUM
-        feat_t = frame_num // 4
-        s4, s5 = frame_num // 4, frame_num // 8      # temporal extents of Mixed_4f / Mixed_5c
-        assert feat_t == s4 and s5 * 2 == s4
         self.pyramids = nn.ModuleList()
-        self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[0], out_channels, [1, 6, 6]), out_channels))
-        self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[1], out_channels, [1, 3, 3]), out_channels))
-        for _ in range(2, LAYER_NUM):
+        if variant == "anet":
+            feat_t = frame_num // 8                  # temporal extent of Mixed_5c
+            self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[1], out_channels, [1, 3, 3]), out_channels))
+            n_src = 1
+        else:
+            feat_t = frame_num // 4                  # temporal extent of Mixed_4f; Mixed_5c has half of it
+            assert (frame_num // 8) * 2 == feat_t
+            self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[0], out_channels, [1, 6, 6]), out_channels))
+            self.pyramids.append(_unit_gn(Unit3DValid(feat_channels[1], out_channels, [1, 3, 3]), out_channels))
+            n_src = 2
+        for _ in range(n_src, LAYER_NUM):
             self.pyramids.append(_unit_gn(Unit1D(out_channels, out_channels, 3, stride=2), out_channels))
         self.loc_heads = nn.ModuleList([ScaleExp() for _ in range(LAYER_NUM)])
 
@@ -189,8 +204,11 @@ class CoarsePyramid(nn.Module):
         self.boundary_max_pooling = BoundaryMaxPooling()
         self.priors = []
         t = feat_t
-        for _ in range(LAYER_NUM):
-            self.priors.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32).view(-1, 1))
+        for i in range(LAYER_NUM):
+            if variant == "anet":
+                self.priors.append(torch.tensor([[(c + 0.5) / t, i] for c in range(t)], dtype=torch.float32).view(-1, 2))
+            else:
+                self.priors.append(torch.tensor([[(c + 0.5) / t] for c in range(t)], dtype=torch.float32).view(-1, 1))
             t = t // 2
         # Level-batched layouts.  The towers / heads / proposal branches share their weights across the 6 levels
         # (BDNet.py:333-412), so they run ONCE on all levels laid side by side along T:
@@ -227,14 +245,17 @@ class CoarsePyramid(nn.Module):
             offs = torch.tensor([o for (o, t) in self.cat_segments for _ in range(t)], dtype=torch.int32)
             lid = torch.tensor([i for i, t in enumerate(self.level_t) for _ in range(t)], dtype=torch.long)
             sep = torch.cat([torch.arange(o, o + t) for o, t in self.sep_segments])
-            self._tables[device] = dict(priors=[p.to(device) for p in self.priors],
-                                        prior=torch.cat(self.priors, 0).to(device), level_len=lens.to(device),
-                                        level_off=offs.to(device), level_id=lid.to(device), sep_idx=sep.to(device))
+            prior = torch.cat(self.priors, 0)
+            stride = torch.tensor([ANET_FPN_STRIDES[i] for i in lid.tolist()], dtype=torch.float32)
+            self._tables[device] = dict(priors=[p.to(device) for p in self.priors], prior=prior.to(device),
+                                        centre=prior[:, 0].contiguous().to(device), level_len=lens.to(device),
+                                        level_off=offs.to(device), level_id=lid.to(device), sep_idx=sep.to(device),
+                                        stride=stride.to(device))
         return self._tables[device]
 
     def _segments(self, loc, tb):
         """Window generation (no_grad, BDNet.py:355-384) for all levels: one native launch."""
-        _, seg_cat, frame_seg = ops.make_segments(loc, tb["prior"].view(-1), tb["level_len"], tb["level_off"], self.frame_num)
+        _, seg_cat, frame_seg = ops.make_segments(loc, tb["centre"], tb["level_len"], tb["level_off"], self.frame_num)
         return seg_cat, frame_seg
 
     def _forced(self, forced_segments):
@@ -248,23 +269,29 @@ class CoarsePyramid(nn.Module):
     def forward(self, feat_dict, ssl=False, get_feat=False, forced_segments=None):
         if get_feat:
             raise NotImplementedError("get_feat is an analysis-only path (SURVEY D10)")
-        x1, x2 = feat_dict["Mixed_4f"], feat_dict["Mixed_5c"]
+        x1, x2 = feat_dict.get("Mixed_4f"), feat_dict["Mixed_5c"]
         if self.conv_store is not None:
-            self.conv_store.prepare(x1.device)
-        B = x1.size(0)
+            self.conv_store.prepare(x2.device)
+        B = x2.size(0)
         K = self.num_classes
-        tb = self._tables_on(x1.device)
-        # ---- pyramid (BDNet.py:311-322) and frame-level feature (:324-331)
+        tb = self._tables_on(x2.device)
+        # ---- pyramid (BDNet.py:311-322; anet/BDNet.py:281-289) and frame-level feature (:324-331)
         feats = []
-        for i, conv in enumerate(self.pyramids):
-            if i == 0:
-                x = conv(x1)
-            elif i == 1:
-                x = conv(x2)
-                feats[-1] = feats[-1] + F.interpolate(x, feats[-1].shape[2:], mode="nearest")
-            else:
-                x = conv(x)
-            feats.append(x)
+        if self.variant == "anet":
+            x = None
+            for i, conv in enumerate(self.pyramids):
+                x = conv(x2) if i == 0 else conv(x)
+                feats.append(x)
+        else:
+            for i, conv in enumerate(self.pyramids):
+                if i == 0:
+                    x = conv(x1)
+                elif i == 1:
+                    x = conv(x2)
+                    feats[-1] = feats[-1] + F.interpolate(x, feats[-1].shape[2:], mode="nearest")
+                else:
+                    x = conv(x)
+                feats.append(x)
         frame = F.interpolate(feats[0].unsqueeze(-1), [self.frame_num, 1]).squeeze(-1)
         frame = self.deconv(frame).contiguous()
         start = frame[:, :256].permute(0, 2, 1).contiguous()
@@ -290,7 +317,10 @@ class CoarsePyramid(nn.Module):
             return y.permute(0, 2, 1).contiguous()
 
         scale = torch.cat([h.scale for h in self.loc_heads])[tb["level_id"]]            # ScaleExp of the prior's level
-        loc = to_out(torch.exp(self.loc_head(loc_feat).index_select(2, sep_idx) * scale))
+        loc = torch.exp(self.loc_head(loc_feat).index_select(2, sep_idx) * scale)
+        if self.variant == "anet":
+            loc = loc * tb["stride"]                                                        # anet/BDNet.py:307-311
+        loc = to_out(loc)
         conf = to_out(self.conf_head(conf_feat).index_select(2, sep_idx))
         act = to_out(self.actionness_head(conf_feat).index_select(2, sep_idx)) if self.os_head else None
 
@@ -350,7 +380,7 @@ class DirichletLayer(nn.Module):
 class BDNet(nn.Module):
     def __init__(self, in_channels=3, backbone_model=None, training=True, use_edl=False, use_rpl=False, *,
                  num_classes=21, os_head=False, frame_num=256, evidence="exp", dropout=0.0, precision="bf16x3",
-                 freeze_bn=True, freeze_bn_affine=True, native_head_convs=True):
+                 freeze_bn=True, freeze_bn_affine=True, native_head_convs=True, variant="thumos"):
         super().__init__()
         if use_rpl:
             raise NotImplementedError("the RPL head is a competing baseline, off in every OpenTAL config (SURVEY D10)")
@@ -362,8 +392,9 @@ class BDNet(nn.Module):
         torch.backends.cuda.matmul.allow_tf32 = False
         self.os_head = os_head
         self.num_classes = num_classes - 1 if os_head else num_classes       # BDNet.py:440
+        self.variant = variant
         self.coarse_pyramid_detection = CoarsePyramid([832, 1024], self.num_classes, frame_num, os_head, precision,
-                                                      native_head_convs)
+                                                      native_head_convs, variant)
         self.reset_params()
         self.backbone = I3DBackbone(in_channels, precision=precision, freeze_bn=freeze_bn,
                                     freeze_bn_affine=freeze_bn_affine)
@@ -406,6 +437,15 @@ class BDNet(nn.Module):
     def reset_params(self):
         for m in self.modules():
             self.weight_init(m)
+        if getattr(self, "variant", "thumos") == "anet":
+            # the ActivityNet flavour re-initialises the shared head convs with N(0, 0.01) (anet/BDNet.py:435-451)
+            cp = self.coarse_pyramid_detection
+            for mod in (cp.loc_tower, cp.conf_tower, cp.loc_head, cp.conf_head, cp.loc_proposal_branch, cp.conf_proposal_branch,
+                        cp.prop_loc_head, cp.prop_conf_head, cp.center_head):
+                for layer in mod.modules():
+                    if isinstance(layer, nn.Conv1d):
+                        nn.init.normal_(layer.weight, mean=0, std=0.01)
+                        nn.init.constant_(layer.bias, 0)
 
     def forward(self, x, proposals=None, ssl=False, get_feat=False, forced_segments=None):
         feat_dict = self.backbone(x)

@@ -132,7 +132,7 @@ class EvidenceLoss(nn.Module):
         M = logit.shape[0]
         if weight is None:
             weight = torch.ones(M, dtype=torch.bool, device=logit.device)
-        y = F.one_hot(target, self.num_cls).to(logit.dtype)
+        y = (target.unsqueeze(-1) == torch.arange(self.num_cls, device=logit.device)).to(logit.dtype)   # sync-free one-hot
         if self.soft_label:
             y = torch.where(y == 1, torch.full_like(y, 1 - self.soft_label), torch.full_like(y, self.soft_label / (self.num_cls - 1)))
         alpha = self.evidence_func(logit) + 1
@@ -146,7 +146,7 @@ class EvidenceLoss(nn.Module):
                 grad_norm = ((1 / a - unc).abs() * y).sum(dim=1)
                 grad_hat = grad_norm * feat_norm
                 bins = torch.ceil(grad_norm * self.num_bins).long()                 # 1..num_bins (0 if grad_norm == 0)
-                onehot = F.one_hot(bins.clamp(0, self.num_bins), self.num_bins + 1)[:, 1:].to(logit.dtype)
+                onehot = (bins.unsqueeze(-1) == torch.arange(1, self.num_bins + 1, device=logit.device)).to(logit.dtype)
                 onehot = onehot * weight.to(logit.dtype).unsqueeze(1)
                 cnt = onehot.sum(0)
                 mean = (onehot * grad_hat.unsqueeze(1)).sum(0) / cnt.clamp(min=1)
@@ -343,6 +343,119 @@ class MultiSegmentLoss(nn.Module):
             loss_act = loss_act / AN.clamp(min=1)
             loss_prop_act = loss_prop_act / PAN.clamp(min=1)
         return loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act
+
+
+ANET_BOUNDS = ((0, 30), (15, 60), (30, 120), (60, 240), (96, 768), (256, 768))   # anet/multisegment_loss.py:69
+
+
+class MultiSegmentLossANet(nn.Module):
+    """ActivityNet flavour of MultiSegmentLoss (AFSD/anet/multisegment_loss.py:86-301) with the reference's API:
+    `forward([loc, conf, prop_loc, prop_conf, center, priors, act, prop_act], targets)` -> the same 7-tuple.
+
+    Differences from the THUMOS14 loss, all reproduced: matching is gated by a per-level range of the larger of the two
+    boundary distances (`bounds`, :69-83, :156-166); refined positives need IoU >= min(piou, best IoU among the sample's
+    positives) (:178-184); the refinement loss is smooth-L1 (:206); every term is normalised PER SAMPLE and averaged
+    over the batch (:268-297); the IBM weight is the stateless exp form 1 / (||logit||_1 exp(10 g) + 1e-10), which
+    back-propagates through ||logit||_1 (anet/cls_loss.py:136, :229); ActionnessLoss(weight=0.1) (:102).
+    The reference loops over the batch in Python with boolean gathers; here every term is a fixed-shape masked
+    reduction along the prior axis — no host synchronisation."""
+
+    def __init__(self, num_classes, overlap_thresh, negpos_ratio, use_gpu=True, cls_loss_type="focal", edl_config=None,
+                 os_head=False, size_average=False, *, clip_length=768, act_weight=0.1, act_margin=1.0, ibm_coeff=10.0):
+        super().__init__()
+        if cls_loss_type != "edl" or not os_head or size_average:
+            raise NotImplementedError("the ActivityNet loss is implemented for the OpenTAL configuration (edl, os_head)")
+        self.num_classes, self.overlap_thresh, self.clip_length = num_classes, overlap_thresh, clip_length
+        self.cls_loss = EvidenceLoss(num_classes, edl_config)           # holds epoch / ibm_start like the reference
+        self.iou_aware = self.cls_loss.iou_aware
+        self.act_weight, self.act_margin, self.ibm_coeff = act_weight, act_margin, ibm_coeff
+        self.os_head = True
+
+    def _edl(self, logit, label, mask):
+        """Per-sample sum over the masked priors of the (IBM-weighted) log EDL loss.  logit [B,P,K]."""
+        K = self.num_classes
+        c = self.cls_loss
+        y = (label.unsqueeze(-1) == torch.arange(K, device=logit.device)).to(logit.dtype)     # one-hot without the
+        alpha = torch.exp(torch.clamp(logit, -10, 10)) + 1                                     # host sync of F.one_hot
+        S = alpha.sum(-1, keepdim=True)
+        per = (y * (torch.log(S) - torch.log(alpha))).sum(-1)
+        if c.with_ibm and c.epoch >= c.ibm_start:
+            feat_norm = logit.abs().sum(-1)                               # not detached (anet/cls_loss.py:136)
+            with torch.no_grad():
+                a = alpha.detach()
+                gnorm = ((1 / a - K / a.sum(-1, keepdim=True)).abs() * y).sum(-1)
+            per = per / (feat_norm * torch.exp(self.ibm_coeff * gnorm) + 1e-10)
+        return torch.where(mask, per, torch.zeros_like(per)).sum(1)
+
+    def _act(self, pred, pos):
+        """ActionnessLoss per sample (anet/cls_loss.py:256-296).  pred [B,P], pos [B,P] bool -> normalised loss [B]."""
+        neg = ~pos
+        npos, nneg = pos.sum(1), neg.sum(1)
+        top_m = torch.minimum(npos, nneg) - 1
+        use_top = top_m > 0
+        key = torch.where(neg, pred.detach(), torch.full_like(pred, float("inf")))
+        rank = key.argsort(dim=1).argsort(dim=1)
+        sel = torch.where(use_top[:, None], pos | (neg & (rank < top_m[:, None])), torch.ones_like(pos))
+        bce = F.binary_cross_entropy_with_logits(pred, pos.to(pred.dtype), reduction="none")
+        loss = torch.where(sel, bce, torch.zeros_like(bce)).sum(1)
+        neg_max = torch.where(neg, pred, torch.full_like(pred, -1e30)).max(1).values
+        pos_max = torch.where(pos, pred, torch.full_like(pred, -1e30)).max(1).values.detach()
+        rank_loss = torch.clamp(self.act_margin - neg_max + pos_max, min=0.0)
+        loss = loss + self.act_weight * torch.where(use_top, rank_loss, torch.zeros_like(rank_loss))
+        return loss / sel.sum(1).clamp(min=1)
+
+    def forward(self, predictions, targets, pre_locs=None):
+        loc, conf, ploc, pconf, center, priors, act, pact = predictions
+        B, P = loc.shape[:2]
+        K = self.num_classes
+        tgt, valid = pad_targets(targets, loc.device)
+        clip = float(self.clip_length)
+        with torch.no_grad():       # matching, anet/multisegment_loss.py:142-190
+            c = priors[:, 0].view(1, -1, 1)
+            lvl = priors[:, 1].long()
+            bounds = torch.tensor(ANET_BOUNDS, dtype=loc.dtype, device=loc.device)
+            lb, rb = bounds[lvl, 0].view(1, -1, 1), bounds[lvl, 1].view(1, -1, 1)
+            left = (c - tgt[:, None, :, 0]) * clip
+            right = (tgt[:, None, :, 1] - c) * clip
+            max_dis = torch.max(left, right)
+            big = clip * 2
+            area = left + right
+            bad = (left < 0) | (right < 0) | (max_dis <= lb) | (max_dis > rb)
+            area = torch.where(bad, torch.full_like(area, big), area)
+            area = torch.where(valid[:, None, :], area, torch.full_like(area, big * 2))
+            best, idx = area.min(dim=2)
+            cc = priors[:, 0].view(1, -1)
+            loc_t = torch.stack([(cc - tgt[:, :, 0].gather(1, idx)) * clip, (tgt[:, :, 1].gather(1, idx) - cc) * clip], dim=-1)
+            lab = tgt[:, :, 2].long().gather(1, idx)
+            conf_t = torch.where(best >= big, torch.zeros_like(lab), lab)
+            ld = loc.detach()
+            iou = _iou(ld, loc_t)[0]
+            pos = conf_t > 0
+            max_iou = torch.where(pos, iou, torch.full_like(iou, -1e30)).max(1).values
+            max_iou = torch.where(pos.any(1), max_iou, torch.full_like(max_iou, 2.0))
+            thr = torch.clamp(max_iou, max=self.overlap_thresh)                    # min(piou, max_iou)
+            prop_conf_t = torch.where(iou < thr[:, None], torch.zeros_like(conf_t), conf_t)
+            ppos = prop_conf_t > 0
+            prop_loc_t = (loc_t - ld) / (0.5 * (ld[..., 0] + ld[..., 1]).unsqueeze(-1))
+        zero = loc.new_zeros(())
+        N = pos.sum(1).clamp(min=1).to(loc.dtype)
+        PN = ppos.sum(1).clamp(min=1).to(loc.dtype)
+        loss_l = torch.where(pos, _giou_loss(loc, loc_t), zero).sum(1) / N
+        sl1 = F.smooth_l1_loss(ploc, prop_loc_t, reduction="none").sum(-1)
+        loss_prop_l = torch.where(ppos, sl1, zero).sum(1) / PN
+        cur = 0.5 * (loc[..., 0] + loc[..., 1]).unsqueeze(-1) * ploc + loc
+        q = _iou(cur, loc_t)[0].clamp(min=0)
+        ct = F.binary_cross_entropy_with_logits(center.reshape(B, P), q, reduction="none")
+        loss_ct = torch.where(pos, ct, zero).sum(1) / N
+        loss_c = self._edl(conf, conf_t - 1, pos) / N
+        loss_prop_c = self._edl(pconf, prop_conf_t - 1, ppos) / PN
+        if self.iou_aware:          # per-sample mean over ALL priors of the sample (anet/multisegment_loss.py:258-260)
+            io = torch.where(iou < 0, torch.full_like(iou, 1e-3), iou)
+            unc = K / (torch.exp(torch.clamp(pconf, -10, 10)) + 1).sum(-1)
+            loss_prop_c = loss_prop_c + (-io * torch.log(1 - unc) - (1 - io) * torch.log(unc)).mean(1)
+        loss_act = self._act(act.reshape(B, P), pos)
+        loss_prop_act = self._act(pact.reshape(B, P), ppos)
+        return tuple(t.mean() for t in (loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act))
 
 
 def calc_bce_loss(start, end, scores):

@@ -97,3 +97,41 @@ def test_focal_configuration():
     alpha = torch.where(conf_t.view(-1) == 0, torch.tensor(0.25), torch.tensor(0.75))
     want = (-(1 - p) ** 2 * alpha * p.log()).sum() / max(int((conf_t > 0).sum()), 1)
     assert abs(float(l[1]) - float(want)) < 1e-5 * abs(float(want))
+
+
+@pytest.mark.parametrize("B,epoch", [(1, 1), (2, 11), (3, 11)])
+def test_anet_loss_matches_oracle(B, epoch):
+    """ActivityNet flavour (per-sample normalisation, level-gated matching, smooth-L1, exp-form IBM) vs the oracle
+    restatement, which oracle/make_golden.py --anet pins to the reference's own AFSD/anet code."""
+    from opental_b200.multisegment_loss import MultiSegmentLossANet
+    cfg = O.anet_config()
+    g = torch.Generator().manual_seed(40 + B + epoch)
+    P, K = 189, cfg.num_classes
+    priors = torch.cat(O.level_priors(cfg), 0)
+    stride = torch.tensor([O.ANET_FPN_STRIDES[int(l)] for l in priors[:, 1]])
+    out = dict(loc=((torch.rand(B, P, 2, generator=g) * 6 + 0.5) * stride[None, :, None]).requires_grad_(True),
+               conf=torch.randn(B, P, K, generator=g).requires_grad_(True),
+               prop_loc=(0.3 * torch.randn(B, P, 2, generator=g)).requires_grad_(True),
+               prop_conf=torch.randn(B, P, K, generator=g).requires_grad_(True),
+               center=torch.randn(B, P, 1, generator=g).requires_grad_(True), priors=priors,
+               act=torch.randn(B, P, 1, generator=g).requires_grad_(True),
+               prop_act=torch.randn(B, P, 1, generator=g).requires_grad_(True))
+    targets = [O.synthetic_targets(i, num_classes=K) for i in range(B)]
+    if B >= 2:
+        targets[1] = torch.cat([targets[1], torch.tensor([[0.40, 0.44, 17.0]])])
+    if B >= 3:
+        targets[2] = torch.tensor([[1.2, 1.4, 3.0]])                 # no prior inside: no positives in this sample
+    ref = O.multisegment_loss_anet(out, targets, O.LossState(epoch=epoch), cfg)
+    crit = MultiSegmentLossANet(K, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True)
+    crit.cls_loss.epoch = epoch
+    keys = ("loc", "conf", "prop_loc", "prop_conf", "center", "priors", "act", "prop_act")
+    got = crit([out[k] for k in keys], targets)
+    for a, b in zip(got, ref):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (float(a), float(b))
+    gk = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
+    w = (1, 10, 1, 10, 1, 1, 1)
+    g_ref = torch.autograd.grad(sum(wi * li for wi, li in zip(w, ref)), [out[k] for k in gk], allow_unused=True)
+    g_got = torch.autograd.grad(sum(wi * li for wi, li in zip(w, got)), [out[k] for k in gk], allow_unused=True)
+    for k, a, b in zip(gk, g_got, g_ref):
+        b = torch.zeros_like(a) if b is None else b
+        assert torch.allclose(a, b, atol=2e-6, rtol=2e-4), (k, float((a - b).abs().max()))

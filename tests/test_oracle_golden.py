@@ -138,3 +138,26 @@ def test_empty_positive_case():
     losses = O.multisegment_loss(out, targets, O.LossState(epoch=11), cfg)
     assert float(losses[0]) == 0 and float(losses[1]) == 0 and float(losses[2]) == 0
     assert all(math.isfinite(float(v)) for v in losses)
+
+
+def test_anet_oracle_matches_reference_golden(golden_dir):
+    """ActivityNet flavour: the oracle's forward (2 clips x 768 frames) and per-sample loss reproduce the golden values the
+    reference's own AFSD/anet code produced (oracle/make_golden.py --anet)."""
+    arrays = np.load(os.path.join(golden_dir, "model_anet_opental.npz"))
+    with open(os.path.join(golden_dir, "model_anet_opental.json")) as fh:
+        summary = json.load(fh)
+    cfg = O.anet_config()
+    assert len(O.model_spec(cfg)) == 446 - 4 + 4      # one source conv instead of two, one more stride-2 level: same count
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(8.0))
+    x = torch.stack([O.synthetic_clip(i, frames=768) for i in range(2)])
+    targets = [O.synthetic_targets(i, num_classes=cfg.num_classes) for i in range(2)]
+    targets[1] = torch.cat([targets[1], torch.tensor([[0.40, 0.44, 17.0]])])
+    with torch.no_grad():
+        out = O.bdnet_forward(x, sd, cfg, compat=True)
+    for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "unct", "prop_unct", "priors"):
+        ref = torch.from_numpy(arrays[f"anet.{k}"])
+        assert float((out[k] - ref).abs().max() / ref.abs().max()) < 2e-5, k
+    for epoch in (1, 11):
+        losses = O.multisegment_loss_anet(out, targets, O.LossState(epoch=epoch), cfg)
+        for a, b in zip(losses, summary[f"anet.e{epoch}"]["losses"]):
+            assert abs(float(a) - b) <= 5e-5 * max(abs(b), 1.0), (epoch, float(a), b)
