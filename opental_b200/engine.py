@@ -154,8 +154,14 @@ class Trainer:
 
     def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor):
         out = self.net(clips)
-        losses = self.criterion(out, targets)
-        cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw)
+        anet = getattr(self.net, "variant", "thumos") == "anet"
+        if anet:      # the ActivityNet loss takes the list form (anet/train.py:168-172)
+            losses = self.criterion([out[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors", "act", "prop_act")],
+                                    targets)
+        else:
+            losses = self.criterion(out, targets)
+        cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw,
+                                     score_scale=8 if anet else 4)
         cost.backward()
         # detached: a caller holding a non-detached loss would keep this step's autograd graph (and its AccumulateGrad
         # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture
@@ -269,6 +275,17 @@ def synthetic_scores(targets: torch.Tensor, frames: int = 256) -> torch.Tensor:
 OPENTAL_EDL_CONFIG = dict(evidence="exp", loss_type="log", with_ibm=True, ibm_start=10, momentum=0.99, num_bins=50,
                           iou_aware=True)          # configs/thumos14_opental_final.yaml:38-49
 OPENTAL_ACT_CONFIG = dict(weight=0.0, margin=1.0)  # :50-52
+
+
+def build_opental_anet(device="cuda", precision="bf16x3", epoch=1):
+    """BDNet + MultiSegmentLoss as constructed for configs/anet_opental.yaml --open_set (768-frame clips, 150 classes)."""
+    from .multisegment_loss import MultiSegmentLossANet
+    net = BDNet(in_channels=3, training=True, use_edl=True, num_classes=151, os_head=True, frame_num=768, precision=precision,
+                variant="anet").to(device)
+    crit = MultiSegmentLossANet(150, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True).to(device)
+    crit.cls_loss.epoch = epoch
+    net.train()
+    return net, crit
 
 
 def build_opental(device="cuda", precision="bf16x3", frame_num=256, epoch=1):

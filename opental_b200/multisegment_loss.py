@@ -370,6 +370,7 @@ class MultiSegmentLossANet(nn.Module):
         self.iou_aware = self.cls_loss.iou_aware
         self.act_weight, self.act_margin, self.ibm_coeff = act_weight, act_margin, ibm_coeff
         self.os_head = True
+        self._bounds = {}
 
     def _edl(self, logit, label, mask):
         """Per-sample sum over the masked priors of the (IBM-weighted) log EDL loss.  logit [B,P,K]."""
@@ -413,7 +414,9 @@ class MultiSegmentLossANet(nn.Module):
         with torch.no_grad():       # matching, anet/multisegment_loss.py:142-190
             c = priors[:, 0].view(1, -1, 1)
             lvl = priors[:, 1].long()
-            bounds = torch.tensor(ANET_BOUNDS, dtype=loc.dtype, device=loc.device)
+            if loc.device not in self._bounds:      # cached: a host->device copy is not allowed inside a CUDA-graph capture
+                self._bounds[loc.device] = torch.tensor(ANET_BOUNDS, dtype=loc.dtype, device=loc.device)
+            bounds = self._bounds[loc.device]
             lb, rb = bounds[lvl, 0].view(1, -1, 1), bounds[lvl, 1].view(1, -1, 1)
             left = (c - tgt[:, None, :, 0]) * clip
             right = (tgt[:, None, :, 1] - c) * clip
@@ -466,11 +469,12 @@ def calc_bce_loss(start, end, scores):
             F.binary_cross_entropy(e.view(-1), scores[:, 1].contiguous().view(-1), reduction="mean"))
 
 
-def training_cost(output_dict, losses, scores, *, lw=1.0, cw=10.0, ctw=1.0, actw=1.0):
-    """Total cost of one (non-SSL) THUMOS14 training step (train.py:186-200, 226-235)."""
+def training_cost(output_dict, losses, scores, *, lw=1.0, cw=10.0, ctw=1.0, actw=1.0, score_scale=4):
+    """Total cost of one (non-SSL) training step (thumos14/train.py:186-200, 226-235; anet/train.py:168-190 with the
+    score maps down-sampled by 8 = score_scale)."""
     loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act = losses
     ls, le = calc_bce_loss(output_dict["start"], output_dict["end"], scores)
-    sc = F.interpolate(scores, scale_factor=1.0 / 4)
+    sc = F.interpolate(scores, scale_factor=1.0 / score_scale)
     a, b = calc_bce_loss(output_dict["start_loc_prop"], output_dict["end_loc_prop"], sc)
     c, d = calc_bce_loss(output_dict["start_conf_prop"], output_dict["end_conf_prop"], sc)
     ls = ls + 0.1 * (a + c)

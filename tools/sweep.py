@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--frames", type=int, nargs="+", default=[128, 256, 512, 1024])
     ap.add_argument("--batches", type=int, nargs="+", default=[1, 2, 4, 8, 16])
     ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--anet", action="store_true", help="ActivityNet flavour (configs/anet_opental.yaml): 768-frame clips, 150 classes")
     args = ap.parse_args()
     peak = 1398.1
     try:
@@ -31,9 +32,14 @@ def main():
         pass
     dev = torch.device("cuda", 0)
     print(f"# frames batch ms/step clips/s train_TFLOP/s(alg) frac_of_{peak:.0f}TF  peak_mem_GB   ({args.precision})")
+    if args.anet:
+        args.frames = [768]
     for T in args.frames:
         torch.manual_seed(0)
-        net, crit = engine.build_opental(device=dev, precision=args.precision, frame_num=T, epoch=11)
+        if args.anet:
+            net, crit = engine.build_opental_anet(device=dev, precision=args.precision, epoch=11)
+        else:
+            net, crit = engine.build_opental(device=dev, precision=args.precision, frame_num=T, epoch=11)
         tr = engine.Trainer(net, crit)
         # fwd + dgrad + wgrad conv FLOPs per clip, linear in T (466.45 GF at T = 256)
         flop_clip = 466.45e9 * T / 256.0
@@ -41,7 +47,7 @@ def main():
             try:
                 torch.cuda.reset_peak_memory_stats()
                 clips = torch.rand(B, 3, T, 96, 96, device=dev) * 2 - 1
-                tg = [engine.synthetic_targets(i) for i in range(B)]
+                tg = [engine.synthetic_targets(i, num_classes=150 if args.anet else 15) for i in range(B)]
                 sc = torch.stack([engine.synthetic_scores(t, frames=T) for t in tg]).to(dev)
                 tp, tv = (t.to(dev) for t in pad_targets(tg, device="cpu"))
                 tr._graph = None
