@@ -294,6 +294,16 @@ class CoarsePyramid(nn.Module):
                 feats.append(x)
         frame = F.interpolate(feats[0].unsqueeze(-1), [self.frame_num, 1]).squeeze(-1)
         frame = self.deconv(frame).contiguous()
+        if ssl:
+            # BDNet.py:397-400: the SSL / triplet pass only needs the frame-level feature and the boundary (lr_conv)
+            # features of level 0 — run the towers on that level alone
+            loc0, conf0 = feats[0], feats[0]
+            for blk in self.loc_tower:
+                loc0 = _conv_gn(blk, loc0)
+            for blk in self.conf_tower:
+                conf0 = _conv_gn(blk, conf0)
+            return [frame.clone(), _conv_gn(self.loc_proposal_branch.lr_conv, loc0),
+                    _conv_gn(self.conf_proposal_branch.lr_conv, conf0)]
         start = frame[:, :256].permute(0, 2, 1).contiguous()
         end = frame[:, 256:].permute(0, 2, 1).contiguous()
 
@@ -335,8 +345,6 @@ class CoarsePyramid(nn.Module):
         loc_prop, loc_lr = self.loc_proposal_branch(loc_cat, pooled_frame, segments, self.cat_segments)
         conf_prop, conf_lr = self.conf_proposal_branch(conf_cat, pooled_frame, segments, self.cat_segments)
         t0 = self.level_t[0]
-        if ssl:
-            return [frame.clone(), loc_lr[:, :, :t0].clone(), conf_lr[:, :, :t0].clone()]
         nd = loc_lr.size(1) // 2
         extra = dict(start_loc_prop=loc_lr[:, :nd, :t0].permute(0, 2, 1).contiguous(),
                      end_loc_prop=loc_lr[:, nd:, :t0].permute(0, 2, 1).contiguous(),

@@ -22,6 +22,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .bdnet import BDNet
@@ -94,9 +95,9 @@ def shard_indices(num_items: int, rank: int, world: int) -> range:
 
 class Trainer:
     def __init__(self, net: BDNet, criterion: MultiSegmentLoss, *, lr=1e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, process_group=None):
+                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, ssl_weight=0.001, process_group=None):
         self.net, self.criterion = net, criterion
-        self.lw, self.cw, self.ctw, self.actw = lw, cw, ctw, actw
+        self.lw, self.cw, self.ctw, self.actw, self.ssl_weight = lw, cw, ctw, actw, ssl_weight
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -152,7 +153,13 @@ class Trainer:
         for _, g in self.groups:
             g.zero_()
 
-    def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor):
+    @staticmethod
+    def triplet_loss(anchor, positive, negative):
+        """nn.TripletMarginLoss() per feature with weights (1, 0.1, 0.1): thumos14/train.py:174-184."""
+        weights = (1.0, 0.1, 0.1)
+        return torch.stack([F.triplet_margin_loss(anchor[i], positive[i], negative[i]) * weights[i] for i in range(3)]).sum(0)
+
+    def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None):
         out = self.net(clips)
         anet = getattr(self.net, "variant", "thumos") == "anet"
         if anet:      # the ActivityNet loss takes the list form (anet/train.py:168-172)
@@ -162,13 +169,18 @@ class Trainer:
             losses = self.criterion(out, targets)
         cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw,
                                      score_scale=8 if anet else 4)
+        if ssl_clips is not None:
+            # second forward on the cut-paste augmented clip + triplet loss on its boundary features
+            # (thumos14/train.py:237-242; BDNet.py:482-503); one backward for the sum
+            a, p, n = self.net(ssl_clips, proposals=ssl_targets, ssl=True)
+            cost = cost + self.ssl_weight * self.triplet_loss(a, p, n)
         cost.backward()
         # detached: a caller holding a non-detached loss would keep this step's autograd graph (and its AccumulateGrad
         # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture
         return cost.detach(), tuple(l.detach() if l is not None else None for l in losses), ls.detach(), le.detach()
 
     # ---------------------------------------------------------------------------------------------- CUDA graph
-    def capture(self, clips: torch.Tensor, targets, scores: torch.Tensor) -> None:
+    def capture(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None) -> None:
         """Capture zero_grad + forward + loss + backward for this input geometry into ONE CUDA graph.  The head and the
         loss are ~2500 small launches whose host-side enqueue cost (~75 ms per step at batch 8) exceeds the GPU work; a
         graph replay removes it.  Inputs are copied into static buffers before every replay; the gradient all-reduce and
@@ -177,10 +189,14 @@ class Trainer:
         import gc
         gc.collect()                                 # drop dead autograd graphs of earlier eager steps (see forward_backward)
         tgt, valid = pad_targets(targets, clips.device)
-        self._static = [torch.empty_like(t) for t in (clips, tgt, valid, scores)]
-        for d, s in zip(self._static, (clips, tgt, valid, scores)):
+        srcs = [clips, tgt, valid, scores]
+        if ssl_clips is not None:
+            srcs += [ssl_clips, torch.stack(list(ssl_targets)) if isinstance(ssl_targets, (list, tuple)) else ssl_targets]
+        self._static = [torch.empty_like(t) for t in srcs]
+        for d, s in zip(self._static, srcs):
             d.copy_(s)
-        c, t, v, sc = self._static
+        c, t, v, sc = self._static[:4]
+        ssl_args = (self._static[4], list(self._static[5].unbind(0))) if ssl_clips is not None else (None, None)
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())
         self._capturing = True
@@ -188,14 +204,14 @@ class Trainer:
             with torch.cuda.stream(stream):
                 for _ in range(2):                   # warm-up on the capture stream (lazy initialisations, allocator)
                     self.zero_grad()
-                    self.forward_backward(c, (t, v), sc)
+                    self.forward_backward(c, (t, v), sc, *ssl_args)
             torch.cuda.current_stream().wait_stream(stream)
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread may query events while this thread captures
             with torch.cuda.graph(self._graph, stream=stream, capture_error_mode="thread_local"):
                 self.zero_grad()
-                self._graph_out = self.forward_backward(c, (t, v), sc)
+                self._graph_out = self.forward_backward(c, (t, v), sc, *ssl_args)
         finally:
             self._capturing = False
         self._graph_epoch_flag = self._ibm_flag()
@@ -204,21 +220,26 @@ class Trainer:
         c = self.criterion.cls_loss
         return bool(getattr(c, "with_ibm", False) and c.epoch >= getattr(c, "ibm_start", 0))
 
-    def step(self, clips: torch.Tensor, targets, scores: torch.Tensor):
-        """clips [B,3,T,H,W] fp32 on the device, targets: list of [N_i,3] or padded (tensor, mask), scores [B,2,T]."""
+    def step(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None):
+        """clips [B,3,T,H,W] fp32 (or uint8 frames [B,T,Hs,Ws,3]) on the device, targets: list of [N_i,3] or padded
+        (tensor, mask), scores [B,2,T].  ssl_clips / ssl_targets: the cut-paste augmented clip and its [3,2] (anchor,
+        positive, negative) segments for the triplet pass (thumos14/train.py:237-242), or None."""
         if self._graph is not None:
             tgt, valid = pad_targets(targets, clips.device)
-            if (tuple(clips.shape) != tuple(self._static[0].shape) or tuple(tgt.shape) != tuple(self._static[1].shape)
+            srcs = [clips, tgt, valid, scores]
+            if ssl_clips is not None:
+                srcs += [ssl_clips, torch.stack(list(ssl_targets)) if isinstance(ssl_targets, (list, tuple)) else ssl_targets]
+            if (len(srcs) != len(self._static) or any(tuple(a.shape) != tuple(b.shape) for a, b in zip(srcs, self._static))
                     or self._ibm_flag() != self._graph_epoch_flag):
                 raise RuntimeError("captured training graph does not match this batch geometry / epoch: call capture() again")
-            for d, s in zip(self._static, (clips, tgt, valid, scores)):
+            for d, s in zip(self._static, srcs):
                 if d.data_ptr() != s.data_ptr():
                     d.copy_(s, non_blocking=True)
             self._graph.replay()
             cost, losses, ls, le = self._graph_out
         else:
             self.zero_grad()
-            cost, losses, ls, le = self.forward_backward(clips, targets, scores)
+            cost, losses, ls, le = self.forward_backward(clips, targets, scores, ssl_clips, ssl_targets)
         if self.world > 1:
             if not self._head_launched:
                 self._launch_head_allreduce()

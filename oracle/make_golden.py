@@ -210,11 +210,53 @@ def anet_cases():
     ns.restore_cuda()
 
 
+def ssl_cases():
+    """The SSL / triplet second pass of the THUMOS14 training step (train.py:174-184, 237-242; BDNet.py:482-503)."""
+    import torch.nn as nn
+    ns = ref_loader.load_reference()
+    cfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(32.0))
+    net = ns.BDNet(in_channels=3, training=False, use_edl=True)
+    net.load_state_dict(sd)
+    net.train()
+    x = O.synthetic_clip(1).unsqueeze(0)
+    proposals = [torch.tensor([[40.0, 90.0], [122.0, 172.0], [91.0, 121.0]])]      # anchor / positive / negative, frames
+    net.zero_grad()
+    a_r, p_r, n_r = net(x, proposals=proposals, ssl=True)
+    trip_r = torch.stack([nn.TripletMarginLoss()(a_r[i], p_r[i], n_r[i]) * w for i, w in enumerate((1, 0.1, 0.1))]).sum(0)
+    trip_r.backward()
+    grads_r = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    a_o, p_o, n_o = O.bdnet_forward_ssl(x, sdo, cfg, proposals, compat=True)
+    trip_o = O.triplet_loss(a_o, p_o, n_o)
+    trip_o.backward()
+    errs = [rel(o.detach(), r.detach()) for lo, lr in ((a_o, a_r), (p_o, p_r), (n_o, n_r)) for o, r in zip(lo, lr)]
+    gerrs = {k: rel(sdo[k].grad, g) for k, g in grads_r.items() if sdo[k].grad is not None and g.abs().max() > 0}
+    print(f"[ssl] oracle vs reference: features {max(errs):.2e} triplet {abs(float(trip_o) - float(trip_r)):.2e} "
+          f"grads {max(gerrs.values()):.2e} (n={len(gerrs)})  trip={float(trip_r):.5f}")
+    assert max(errs) < TOL and abs(float(trip_o) - float(trip_r)) < 1e-5 * max(1.0, abs(float(trip_r)))
+    assert max(gerrs.values()) < 5e-2
+    arrays = {}
+    for name, lst in (("anchor", a_r), ("positive", p_r), ("negative", n_r)):
+        for i, t in enumerate(lst):
+            arrays[f"ssl.{name}.{i}"] = t.detach().numpy()
+    fp = {}
+    for k, g in grads_r.items():
+        fp[k] = [float(g.sum()), float(g.abs().sum())]
+        arrays[f"ssl.grad.{k}"] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "model_thumos_ssl.npz"), **arrays)
+    with open(os.path.join(GOLD, "model_thumos_ssl.json"), "w") as fh:
+        json.dump(dict(triplet=float(trip_r), proposals=proposals[0].tolist(), grad_fingerprint=fp), fh, indent=1)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     if "--anet" in sys.argv:
         anet_cases()
+    elif "--ssl" in sys.argv:
+        ssl_cases()
     else:
         bmp_cases()
         model_cases()

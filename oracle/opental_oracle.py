@@ -414,7 +414,7 @@ def level_priors(cfg: OracleConfig) -> list[torch.Tensor]:
     return out
 
 
-def coarse_pyramid(feats, sd, cfg: OracleConfig, compat=True, forced_segments=None, return_segments=False):
+def coarse_pyramid(feats, sd, cfg: OracleConfig, compat=True, forced_segments=None, return_segments=False, ssl=False):
     """CoarsePyramid.forward: BDNet.py:295-432 (non-ssl path).  `forced_segments` (list of per-level
     (segments, frame_segments)) lets layer-wise parity tests bypass the discrete rounding hazard."""
     cp = "coarse_pyramid_detection."
@@ -467,6 +467,8 @@ def coarse_pyramid(feats, sd, cfg: OracleConfig, compat=True, forced_segments=No
         segs.append((segments, frame_segments))
         lp, lp_ = proposal_branch(lf, frame, segments, frame_segments, sd, cp + "loc_proposal_branch.", compat)
         cpf, cp_ = proposal_branch(cf, frame, segments, frame_segments, sd, cp + "conf_proposal_branch.", compat)
+        if i == 0 and ssl:      # BDNet.py:397-400: the frame-level feature and the two level-0 boundary features
+            return [frame.clone(), lp_.clone(), cp_.clone()]
         if i == 0:
             nd = lp_.shape[1] // 2
             extra = dict(start_loc_prop=lp_[:, :nd].permute(0, 2, 1).contiguous(),
@@ -504,6 +506,39 @@ def bdnet_forward(x, sd, cfg: OracleConfig, compat=True, forced_segments=None, r
         out["unct"] = dirichlet_uncertainty(out["conf"])
         out["prop_unct"] = dirichlet_uncertainty(out["prop_conf"])
     return (out, segs) if return_segments else out
+
+
+def bdnet_forward_ssl(x, sd, cfg: OracleConfig, proposals, compat=True):
+    """BDNet.forward(ssl=True): BDNet.py:482-503.  proposals: list with ONE tensor [3,2] of (start, end) frames — anchor,
+    positive and negative segment of the cut-paste augmentation (thumos_dataset.py:187-226).  Returns the three lists
+    (anchor, positive, negative), one entry per feature: frame level, loc branch, conf branch."""
+    feats = i3d_features(x, sd)
+    top = coarse_pyramid(feats, sd, cfg, compat, ssl=True)
+    dec = proposals[0].unsqueeze(0)
+    plen = dec[:, :, 1:] - dec[:, :, :1] + 1.0
+    inl = torch.clamp(plen / 4.0, min=1.0)
+    outl = torch.clamp(plen / 10.0, min=1.0)
+    fs = torch.cat([torch.round(dec[:, :, :1] - outl), torch.round(dec[:, :, :1] + inl),
+                    torch.round(dec[:, :, 1:] - inl), torch.round(dec[:, :, 1:] + outl)], dim=-1)
+    anchor, positive, negative = [], [], []
+    for i, scale in enumerate((1, 4, 4)):
+        seg = (fs / scale).expand(top[i].shape[0], -1, -1).contiguous()      # the reference indexes sample 0 for all (D11)
+        bound = boundary_max_pooling(top[i], seg, compat)
+        nd = bound.shape[1] // 2
+        anchor.append(bound[:, nd:, 0])
+        positive.append(bound[:, :nd, 1])
+        negative.append(bound[:, :nd, 2])
+    return anchor, positive, negative
+
+
+def triplet_loss(anchor, positive, negative):
+    """Sum of nn.TripletMarginLoss() (margin 1, p 2, eps 1e-6, mean) with weights (1, 0.1, 0.1): train.py:174-184."""
+    total = 0.0
+    for a, p, n, w in zip(anchor, positive, negative, (1.0, 0.1, 0.1)):
+        d_ap = (a - p + 1e-6).norm(dim=1)
+        d_an = (a - n + 1e-6).norm(dim=1)
+        total = total + w * torch.clamp(d_ap - d_an + 1.0, min=0).mean()
+    return total
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -136,3 +136,51 @@ def test_native_path_is_loaded():
     import inspect
     src = inspect.getsource(bb)
     assert "oracle" not in src.replace("no CPU fallback", "")
+
+
+def test_ssl_triplet_pass_matches_reference_golden(golden_dir):
+    """SSL second pass (BDNet.forward(ssl=True) + triplet loss, train.py:174-184, 237-242) vs the reference golden."""
+    from opental_b200 import engine
+    from opental_b200.prop_pooling import BoundaryMaxPoolingFunction
+    arrays = np.load(os.path.join(golden_dir, "model_thumos_ssl.npz"))
+    with open(os.path.join(golden_dir, "model_thumos_ssl.json")) as fh:
+        summary = json.load(fh)
+    net, crit = build(math.log(32.0), 1)
+    x = O.synthetic_clip(1).unsqueeze(0).cuda()
+    proposals = [torch.tensor(summary["proposals"]).cuda()]
+    a, p, n = net(x, proposals=proposals, ssl=True)
+    for name, lst in (("anchor", a), ("positive", p), ("negative", n)):
+        for i, t in enumerate(lst):
+            assert rel(t.detach().cpu(), torch.from_numpy(arrays[f"ssl.{name}.{i}"])) < 1e-3, (name, i)
+    trip = engine.Trainer.triplet_loss(a, p, n)
+    assert abs(float(trip) - summary["triplet"]) < 1e-3 * max(1.0, abs(summary["triplet"]))
+    net.backbone.flat_parameters()[1].zero_()
+    BoundaryMaxPoolingFunction.compat_tscale_bug = True        # golden gradients: reference kernel arithmetic (tscale = 3 here)
+    try:
+        trip.backward()
+    finally:
+        BoundaryMaxPoolingFunction.compat_tscale_bug = False
+    params = dict(net.named_parameters())
+    bad = {}
+    for k, (s, a_) in summary["grad_fingerprint"].items():
+        g = params[k].grad
+        if a_ > 0:
+            assert g is not None, k
+            e = abs(float(g.abs().sum()) - a_) / a_
+            if e > 5e-2:
+                bad[k] = e
+    assert not bad, bad
+
+
+def test_trainer_step_with_ssl_pass():
+    from opental_b200 import engine
+    net, crit = build(math.log(32.0), 11)
+    tr = engine.Trainer(net, crit, ssl_weight=0.001)
+    x = O.synthetic_clip(0).unsqueeze(0).cuda()
+    xs = O.synthetic_clip(1).unsqueeze(0).cuda()
+    tgt = [O.synthetic_targets(0, num_classes=15).cuda()]
+    sc = O.synthetic_scores(tgt[0].cpu()).unsqueeze(0).cuda()
+    prop = [torch.tensor([[40.0, 90.0], [122.0, 172.0], [91.0, 121.0]]).cuda()]
+    c0, *_ = tr.step(x, tgt, sc)
+    c1, *_ = tr.step(x, tgt, sc, ssl_clips=xs, ssl_targets=prop)
+    assert math.isfinite(float(c0)) and math.isfinite(float(c1)) and float(c1) != float(c0)

@@ -161,3 +161,21 @@ def test_anet_oracle_matches_reference_golden(golden_dir):
         losses = O.multisegment_loss_anet(out, targets, O.LossState(epoch=epoch), cfg)
         for a, b in zip(losses, summary[f"anet.e{epoch}"]["losses"]):
             assert abs(float(a) - b) <= 5e-5 * max(abs(b), 1.0), (epoch, float(a), b)
+
+
+def test_ssl_oracle_matches_reference_golden(golden_dir):
+    """SSL / triplet pass (BDNet.py:482-503, train.py:174-184): oracle vs the reference-generated golden values."""
+    arrays = np.load(os.path.join(golden_dir, "model_thumos_ssl.npz"))
+    with open(os.path.join(golden_dir, "model_thumos_ssl.json")) as fh:
+        summary = json.load(fh)
+    cfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(32.0))
+    x = O.synthetic_clip(1).unsqueeze(0)
+    proposals = [torch.tensor(summary["proposals"])]
+    with torch.no_grad():
+        a, p, n = O.bdnet_forward_ssl(x, sd, cfg, proposals, compat=True)
+    for name, lst in (("anchor", a), ("positive", p), ("negative", n)):
+        for i, t in enumerate(lst):
+            ref = torch.from_numpy(arrays[f"ssl.{name}.{i}"])
+            assert float((t - ref).abs().max() / ref.abs().max()) < 2e-5, (name, i)
+    assert abs(float(O.triplet_loss(a, p, n)) - summary["triplet"]) < 1e-5 * max(1.0, abs(summary["triplet"]))
