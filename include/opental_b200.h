@@ -290,6 +290,26 @@ OTAL_API int otal_make_segments(const float* loc, const float* prior, const int*
  * logit[m,k], -10, 10)) + 1).  logit [M,K] contiguous. */
 OTAL_API int otal_dirichlet_uncertainty(const float* logit, float* unct, long long M, int K, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Inference post-processing — replaces decode_predictions (AFSD/thumos14/test.py:112-140) and softnms_v2
+ * (AFSD/common/segment_utils.py:128-162, a Python loop on the CPU in the reference).
+ *
+ * otal_decode_scores: for B sliding-window clips, loc/prop_loc [B,P,2], conf/prop_conf [B,P,K] logits, center/act/
+ * prop_act [B,P] (act, prop_act NULL = closed-set head), prior [P] centres, offset [B] = first frame of each clip (or
+ * NULL).  segments [B,P,2] = refined (start, end) in seconds, scores [B,K,P] = mean Dirichlet probability of the two
+ * heads x sigmoid(center) x actionness, uncertainty [B,P] = mean of K / sum(alpha), actionness [B,P].
+ *
+ * otal_softnms: Gaussian soft-NMS per class.  segments [.., M, 2] (class c reads segments + c*seg_class_stride floats;
+ * stride 0 = all classes share one candidate list), scores [C,M] decayed IN PLACE (entries below score_threshold never
+ * take part: set filtered-out candidates to 0), keep [C,M] bytes = 1 for the kept candidates, count [C].
+ * ---------------------------------------------------------------------------------------------------------- */
+OTAL_API int otal_decode_scores(const float* loc, const float* prop_loc, const float* conf, const float* prop_conf,
+                                const float* center, const float* act, const float* prop_act, const float* prior,
+                                const float* offset, float* segments, float* scores, float* uncertainty, float* actionness,
+                                int B, int P, int K, float clip_length, float sample_fps, void* stream);
+OTAL_API int otal_softnms(const float* segments, long long seg_class_stride, float* scores, unsigned char* keep, int* count, int C,
+                          int M, float sigma, int top_k, float score_threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -624,3 +624,50 @@ def dirichlet_uncertainty(logit: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
     _lib.call("otal_dirichlet_uncertainty", x.data_ptr(), out.data_ptr(), x.numel() // K, K, _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# inference post-processing
+# ----------------------------------------------------------------------------------------------------------
+def decode_scores(out: dict, offsets: torch.Tensor | None, clip_length: float, sample_fps: float):
+    """decode_predictions (AFSD/thumos14/test.py:112-140) for every clip of a BDNet output dict.
+    Returns (segments [B,P,2] seconds, scores [B,K,P], uncertainty [B,P], actionness [B,P])."""
+    loc, conf = out["loc"].detach().contiguous(), out["conf"].detach().contiguous()
+    _require_cuda(loc, conf)
+    B, P, K = conf.shape
+    ploc, pconf = out["prop_loc"].detach().contiguous(), out["prop_conf"].detach().contiguous()
+    center = out["center"].detach().reshape(B, P).contiguous()
+    act = out.get("act")
+    pact = out.get("prop_act")
+    act = act.detach().reshape(B, P).contiguous() if act is not None else None
+    pact = pact.detach().reshape(B, P).contiguous() if pact is not None else None
+    prior = out["priors"][:, 0].contiguous()
+    if offsets is not None:
+        offsets = offsets.to(device=loc.device, dtype=torch.float32).contiguous()
+        assert offsets.numel() == B
+    dev = loc.device
+    seg = torch.empty(B, P, 2, dtype=torch.float32, device=dev)
+    scores = torch.empty(B, K, P, dtype=torch.float32, device=dev)
+    unct = torch.empty(B, P, dtype=torch.float32, device=dev)
+    actn = torch.empty(B, P, dtype=torch.float32, device=dev)
+    _lib.call("otal_decode_scores", loc.data_ptr(), ploc.data_ptr(), conf.data_ptr(), pconf.data_ptr(), center.data_ptr(), _ptr(act),
+              _ptr(pact), prior.data_ptr(), _ptr(offsets), seg.data_ptr(), scores.data_ptr(), unct.data_ptr(), actn.data_ptr(), B, P, K,
+              float(clip_length), float(sample_fps), _stream())
+    return seg, scores, unct, actn
+
+
+def softnms(segments: torch.Tensor, scores: torch.Tensor, sigma: float = 0.5, top_k: int = 1000, score_threshold: float = 0.001):
+    """Gaussian soft-NMS per class (softnms_v2, AFSD/common/segment_utils.py:128-162).  segments [M,2] (shared by all classes)
+    or [C,M,2]; scores [C,M] (entries below the threshold are ignored).  Returns (decayed scores [C,M], keep mask [C,M] bool,
+    count [C] int32); the input scores are not modified."""
+    _require_cuda(segments, scores)
+    scores = scores.detach().float().contiguous().clone()
+    segments = segments.detach().float().contiguous()
+    C, M = scores.shape
+    stride = 0 if segments.dim() == 2 else M * 2
+    assert segments.shape[-2:] == (M, 2)
+    keep = torch.empty(C, M, dtype=torch.uint8, device=scores.device)
+    count = torch.empty(C, dtype=torch.int32, device=scores.device)
+    _lib.call("otal_softnms", segments.data_ptr(), stride, scores.data_ptr(), keep.data_ptr(), count.data_ptr(), C, M, float(sigma),
+              int(top_k), float(score_threshold), _stream())
+    return scores, keep.bool(), count

@@ -250,6 +250,55 @@ def ssl_cases():
     ns.restore_cuda()
 
 
+def infer_cases():
+    """Inference post-processing (test.py:112-162, segment_utils.py:128-162): reference functions vs the oracle."""
+    import importlib
+    ns = ref_loader.load_reference()
+    ref_test = importlib.import_module("AFSD.thumos14.test")
+    ref_seg = importlib.import_module("AFSD.common.segment_utils")
+    cfg = O.OracleConfig()
+    g = torch.Generator().manual_seed(77)
+    P, K = 126, cfg.num_classes
+    out = dict(loc=torch.rand(1, P, 2, generator=g) * 40 + 1, conf=2 * torch.randn(1, P, K, generator=g),
+               prop_loc=0.3 * torch.randn(1, P, 2, generator=g), prop_conf=2 * torch.randn(1, P, K, generator=g),
+               center=torch.randn(1, P, 1, generator=g), priors=torch.cat(O.level_priors(cfg), 0),
+               act=2 * torch.randn(1, P, 1, generator=g), prop_act=2 * torch.randn(1, P, 1, generator=g))
+    out["unct"], out["prop_unct"] = O.dirichlet_uncertainty(out["conf"]), O.dirichlet_uncertainty(out["prop_conf"])
+    layer = ns.bdnet_module.DirichletLayer(evidence="exp", dim=-1)
+    loc, conf, ploc, pconf, center, priors, unct, punct, act, pact = ref_test.parse_output(out, use_edl=True, os_head=True)
+    seg_r, sc_r, un_r, ac_r = ref_test.decode_predictions(loc, ploc, priors, conf, pconf, unct, punct, act, pact, center, 384, 10.0,
+                                                          256, K, score_func=layer, use_edl=True, os_head=True)
+    seg_o, sc_o, un_o, ac_o = O.decode_predictions(out, 0, 384, 10.0, cfg)
+    for a, b in ((seg_o, seg_r), (sc_o, sc_r), (un_o, un_r), (ac_o, ac_r)):
+        assert rel(a, b) < 1e-6
+    arrays = dict(seg=seg_r.numpy(), scores=sc_r.numpy(), unct=un_r.numpy(), act=ac_r.numpy())
+    n_f = 0
+    for cl in range(K):
+        fr = ref_test.filtering(seg_r, sc_r[cl], un_r, ac_r, 0.001, use_edl=True, os_head=True)
+        fo = O.filter_candidates(seg_o, sc_o[cl], un_o, ac_o, 0.001)
+        assert (fr is None) == (fo is None)
+        if fr is not None:
+            assert torch.allclose(fr, fo, atol=1e-6)
+            n_f += fr.shape[0]
+    # soft-NMS cases: random candidates, a case with duplicates / ties, and one that hits top_k
+    for name, (n, top_k, sigma) in dict(a=(300, 1000, 0.5), b=(64, 10, 0.85), c=(5, 1000, 0.5), d=(1, 1000, 0.5)).items():
+        st = torch.rand(n, generator=g) * 100
+        cand = torch.stack([st, st + torch.rand(n, generator=g) * 30 + 0.5, torch.rand(n, generator=g), torch.rand(n, generator=g),
+                            torch.rand(n, generator=g)], -1)
+        if name == "b":
+            cand[10] = cand[3]                         # exact duplicate: first index wins the argmax
+        kept_r, cnt_r, mask_r = ref_seg.softnms_v2(cand.clone(), sigma=sigma, top_k=top_k, use_edl=True, os_head=True, get_mask=True)
+        kept_o, cnt_o, mask_o = O.softnms_v2(cand.clone(), sigma=sigma, top_k=top_k)
+        assert int(cnt_r) == cnt_o and torch.equal(mask_r, mask_o) and torch.allclose(kept_r, kept_o, atol=1e-7), name
+        arrays[f"nms.{name}.cand"] = cand.numpy()
+        arrays[f"nms.{name}.kept"] = kept_r.numpy()
+        arrays[f"nms.{name}.mask"] = mask_r.numpy()
+        arrays[f"nms.{name}.cfg"] = np.array([top_k, sigma])
+    print(f"[infer] decode / filtering ({n_f} candidates) / soft-NMS: oracle == reference")
+    np.savez_compressed(os.path.join(GOLD, "infer_cases.npz"), **arrays)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -257,6 +306,8 @@ if __name__ == "__main__":
         anet_cases()
     elif "--ssl" in sys.argv:
         ssl_cases()
+    elif "--infer" in sys.argv:
+        infer_cases()
     else:
         bmp_cases()
         model_cases()

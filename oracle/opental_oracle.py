@@ -779,3 +779,59 @@ def training_cost(out, targets, scores, state: LossState, cfg: OracleConfig, lw=
     cost = lw * l + cw * c + lw * pl + cw * pc + ctw * ct + ls + le + actw * act + actw * pact
     return cost, dict(loss_l=l, loss_c=c, loss_prop_l=pl, loss_prop_c=pc, loss_ct=ct, loss_start=ls, loss_end=le,
                       loss_act=act, loss_prop_act=pact)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# inference post-processing (AFSD/thumos14/test.py:112-200, AFSD/common/segment_utils.py:128-162)
+# ----------------------------------------------------------------------------------------------------------
+def decode_predictions(out, b, offset, sample_fps, cfg: OracleConfig):
+    """decode_predictions for clip `b` of an output dict (test.py:112-140) with the Dirichlet score function
+    (DirichletLayer.forward, BDNet.py:558-561: alpha / sum alpha) and the open-set head.
+    Returns (segments [P,2] seconds, scores [K,P], uncertainty [P], actionness [P])."""
+    loc, ploc, priors = out["loc"][b], out["prop_loc"][b], out["priors"]
+    w = loc[:, :1] + loc[:, 1:]
+    loc = 0.5 * w * ploc + loc
+    seg = torch.cat([priors[:, :1] * cfg.clip_length - loc[:, :1], priors[:, :1] * cfg.clip_length + loc[:, 1:]], dim=-1)
+    seg = seg.clamp(min=0, max=cfg.clip_length)
+    seg = (seg + offset) / sample_fps
+    unct = (dirichlet_uncertainty(out["conf"][b]) + dirichlet_uncertainty(out["prop_conf"][b])) / 2.0
+    actionness = (out["act"][b].squeeze(-1).sigmoid() + out["prop_act"][b].squeeze(-1).sigmoid()) / 2.0
+
+    def prob(logit):
+        alpha = torch.exp(torch.clamp(logit, -10, 10)) + 1
+        return alpha / alpha.sum(-1, keepdim=True)
+
+    conf = (prob(out["conf"][b]) + prob(out["prop_conf"][b])) / 2.0
+    conf = conf * out["center"][b].sigmoid() * actionness.unsqueeze(-1)
+    return seg, conf.view(-1, cfg.num_classes).transpose(1, 0).contiguous(), unct, actionness
+
+
+def filter_candidates(seg, score_cls, unct, actionness, conf_thresh):
+    """filtering (test.py:143-162), open-set head: rows (start, end, score, uncertainty, actionness) or None."""
+    m = (score_cls > conf_thresh) & (actionness > 0.5)
+    if not m.any():
+        return None
+    return torch.cat([seg[m], score_cls[m, None], unct[m, None], actionness[m, None]], -1)
+
+
+def softnms_v2(segments, sigma=0.5, top_k=1000, score_threshold=0.001):
+    """softnms_v2 (segment_utils.py:128-162).  segments [N, >=3] (start, end, score, ...).  Gaussian soft-NMS; NB the loop
+    stops when ONE candidate is left undone, so that last candidate is never kept.  Returns (kept rows, count, mask)."""
+    seg = segments.clone()
+    ts, te, sc = seg[:, 0], seg[:, 1], seg[:, 2]
+    done = torch.zeros_like(sc, dtype=torch.bool)
+    undone = sc >= score_threshold
+    while int(undone.sum()) > 1 and int(done.sum()) < top_k:
+        cand = undone.nonzero().view(-1)
+        idx = int(cand[sc[undone].argmax()])
+        undone[idx] = False
+        done[idx] = True
+        tt1 = ts[undone].clamp(min=float(ts[idx]))
+        tt2 = te[undone].clamp(max=float(te[idx]))
+        inter = (tt2 - tt1).clamp(min=0)
+        dur = te[undone] - ts[undone]
+        width = torch.clamp(te[idx] - ts[idx], min=1e-5)
+        iou = inter / (width + dur - inter)
+        sc[undone] = sc[undone] * torch.exp(-iou ** 2 / sigma)
+        undone[sc < score_threshold] = False
+    return seg[done], int(done.sum()), done

@@ -179,3 +179,22 @@ def test_ssl_oracle_matches_reference_golden(golden_dir):
             ref = torch.from_numpy(arrays[f"ssl.{name}.{i}"])
             assert float((t - ref).abs().max() / ref.abs().max()) < 2e-5, (name, i)
     assert abs(float(O.triplet_loss(a, p, n)) - summary["triplet"]) < 1e-5 * max(1.0, abs(summary["triplet"]))
+
+
+def test_inference_postprocessing_oracle_matches_reference_golden(golden_dir):
+    """decode_predictions / softnms_v2 restatements vs the values the reference's own functions produced."""
+    g = np.load(os.path.join(golden_dir, "infer_cases.npz"))
+    cfg = O.OracleConfig()
+    gen = torch.Generator().manual_seed(77)
+    P, K = 126, cfg.num_classes
+    out = dict(loc=torch.rand(1, P, 2, generator=gen) * 40 + 1, conf=2 * torch.randn(1, P, K, generator=gen),
+               prop_loc=0.3 * torch.randn(1, P, 2, generator=gen), prop_conf=2 * torch.randn(1, P, K, generator=gen),
+               center=torch.randn(1, P, 1, generator=gen), priors=torch.cat(O.level_priors(cfg), 0),
+               act=2 * torch.randn(1, P, 1, generator=gen), prop_act=2 * torch.randn(1, P, 1, generator=gen))
+    seg, scores, unct, act = O.decode_predictions(out, 0, 384, 10.0, cfg)
+    assert torch.allclose(seg, torch.from_numpy(g["seg"]), atol=1e-5) and torch.allclose(scores, torch.from_numpy(g["scores"]), atol=1e-7)
+    assert torch.allclose(unct, torch.from_numpy(g["unct"]), atol=1e-6) and torch.allclose(act, torch.from_numpy(g["act"]), atol=1e-6)
+    for name in "abcd":
+        cand = torch.from_numpy(g[f"nms.{name}.cand"])
+        kept, cnt, mask = O.softnms_v2(cand, sigma=float(g[f"nms.{name}.cfg"][1]), top_k=int(g[f"nms.{name}.cfg"][0]))
+        assert torch.equal(mask, torch.from_numpy(g[f"nms.{name}.mask"])) and torch.allclose(kept, torch.from_numpy(g[f"nms.{name}.kept"]), atol=1e-7)
