@@ -178,6 +178,13 @@ typedef struct otal_pool_desc {
 } otal_pool_desc;
 OTAL_API int otal_maxpool_fwd(const otal_pool_desc* desc, void* stream);
 OTAL_API int otal_maxpool_bwd(const otal_pool_desc* desc, void* stream);
+/* Pool backward fused with the ReLU / frozen-BN backward of the layer that produced the pool's input (gather form, for
+ * the stride-2 stage pools): d = (pool_bwd(g_out) [+ g_add]) * [x > 0] * scale[c], written as bf16 planes
+ * [N,T,H,W,d_cstride] at d_coff.  Needs desc->argmax (recorded by the forward), desc->g_out and desc->x_hi (the pool
+ * input = the producer's post-ReLU output); g_add: optional fp32 [N,T,H,W,add_cstride] gradient of another consumer. */
+OTAL_API int otal_maxpool_bwd_relu_bn_split(const otal_pool_desc* desc, const float* g_add, int add_cstride, int add_coff,
+                                            const float* scale, uint16_t* d_hi, uint16_t* d_lo, int d_cstride, int d_coff,
+                                            void* stream);
 
 /* Clip ingest for Conv3d_1a — replaces `clips.cuda()` + the first F.pad (AFSD/thumos14/train.py:165,
  * AFSD/common/i3d_backbone.py:59-79): NCDHW fp32 [N,C<=4,T,H,W] (W even) -> [N,T,H,W/2,8,4] bf16 planes: window w' holds

@@ -91,6 +91,8 @@ SIGNATURES = {
     "otal_maxpool_fwd": (c_int, [POINTER(PoolDesc), c_void_p]),
     "otal_maxpool_bwd": (c_int, [POINTER(PoolDesc), c_void_p]),
     "otal_clip_ingest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_maxpool_bwd_relu_bn_split": (c_int, [POINTER(PoolDesc), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                               c_void_p]),
     "otal_clip_ingest_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_relu_bn_bwd_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_void_p]),

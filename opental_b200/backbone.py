@@ -319,15 +319,22 @@ class I3DBackbone(nn.Module):
                            in_slice=d_slice, out_f32=g_x, out_slice=(gx_off, r.cin), want_planes=False, dgrad=True,
                            accumulate=accumulate)
 
-    def _mixed_bwd(self, name: str, saved: dict, g_y: torch.Tensor) -> torch.Tensor:
+    def _mixed_scale(self, name: str) -> torch.Tensor:
+        """Folded BN scales of the four concat branches [b0|b1b|b2b|b3b] of a Mixed block (contiguous by design)."""
+        c0 = self.convs[f"{name}.b0"]
+        ctot = sum(self.convs[f"{name}.{b}"].cout for b in ("b0", "b1b", "b2b", "b3b"))
+        return self._scale[c0.bn_off:c0.bn_off + ctot]
+
+    def _mixed_bwd(self, name: str, saved: dict, g_y: torch.Tensor | None, d_y: Planes | None = None) -> torch.Tensor:
+        """g_y: fp32 gradient w.r.t. the block output, or d_y: the already masked / scaled / split gradient planes
+        (produced by the fused pool backward of the stage pool that follows the block)."""
         c = {b: self.convs[f"{name}.{b}"] for b in BRANCHES}
         x, y, mid, pooled, parg = saved.pop(name)
         with_lo = self.precision == "bf16x3"
-        ctot = y.hi.shape[-1]
         o1, o2, o3 = c["b0"].cout, c["b0"].cout + c["b1b"].cout, c["b0"].cout + c["b1b"].cout + c["b2b"].cout
-        sc_y = self._scale[c["b0"].bn_off:c["b0"].bn_off + ctot]            # [b0|b1b|b2b|b3b] contiguous by design
-        d_y = ops.relu_bn_bwd_split(g_y, y, sc_y, with_lo=with_lo)
-        dev = g_y.device
+        if d_y is None:
+            d_y = ops.relu_bn_bwd_split(g_y, y, self._mixed_scale(name), with_lo=with_lo)
+        dev = d_y.hi.device
         shape = x.hi.shape[:4]
         g_x = torch.empty((*shape, x.hi.shape[-1]), dtype=torch.float32, device=dev)
         g_mid = torch.empty((*shape, mid.hi.shape[-1]), dtype=torch.float32, device=dev)
@@ -362,34 +369,45 @@ class I3DBackbone(nn.Module):
         x4f = saved["Mixed_4f"][1]
         x5c = saved["Mixed_5c"][1]
         g = g5.contiguous() if g5 is not None else torch.zeros(x5c.hi.shape, dtype=torch.float32, device=dev)
-        g4 = g4.contiguous().clone() if g4 is not None else torch.zeros(x4f.hi.shape, dtype=torch.float32, device=dev)
+        g4 = g4.contiguous() if g4 is not None else None          # added inside the fused backward of MaxPool3d_5a
+        # A stage pool's backward is fused with the ReLU / BN backward of the layer in front of it (gather kernel): it
+        # hands that layer its gradient planes `d_next` directly, no fp32 gradient of the pool input is materialised.
+        names = [e[0] for e in ENDPOINTS]
+        d_next = None
         for name, kind, arg in reversed(ENDPOINTS):
             if kind == "mixed":
-                if name == "Mixed_4f":
+                if name == "Mixed_4f" and d_next is None:
                     g = g4                                   # head gradient + pool5a routing, accumulated below
-                g = self._mixed_bwd(name, saved, g)
+                g = self._mixed_bwd(name, saved, g, d_next)
+                d_next = None
             elif kind == "pool":
                 x, _, parg = saved.pop(name)
-                if name == "MaxPool3d_5a_2x2":
-                    g_in = g4
+                prev_name, prev_kind, _ = ENDPOINTS[names.index(name) - 1]
+                if prev_kind == "mixed":
+                    sc = self._mixed_scale(prev_name)
                 else:
-                    g_in = torch.zeros(x.hi.shape, dtype=torch.float32, device=dev)
-                ops.maxpool_bwd(x, g, g_in, kernel=arg["k"], stride=arg["s"], pad_front=_pads(x.hi.shape[1:4], arg["k"], arg["s"]),
-                                argmax=parg)
-                g = g_in
+                    sc, _ = self._ss(self.convs[prev_name])
+                d_next = ops.maxpool_bwd_relu_bn_split(x, parg, g, sc, kernel=arg["k"], stride=arg["s"],
+                                                       pad_front=_pads(x.hi.shape[1:4], arg["k"], arg["s"]),
+                                                       g_add=g4 if name == "MaxPool3d_5a_2x2" else None, with_lo=with_lo)
+                g = None
             elif kind == "conv":
                 r = self.convs[name]
                 x, y = saved.pop(name)
-                sc, _ = self._ss(r)
-                d = ops.relu_bn_bwd_split(g, y, sc, with_lo=with_lo)
+                if d_next is None:
+                    sc, _ = self._ss(r)
+                    d_next = ops.relu_bn_bwd_split(g, y, sc, with_lo=with_lo)
+                d, d_next = d_next, None
                 g = torch.empty((*x.hi.shape[:4], r.cin), dtype=torch.float32, device=dev)
                 self._conv_bwd(r, x, d, g)
             else:  # conv1a: weight gradient only, the clip needs no gradient (train.py:165)
                 r = self.convs[name]
                 y = saved.pop(name)
                 a, W = saved.pop("clip")
-                sc, _ = self._ss(r)
-                d = ops.relu_bn_bwd_split(g, y, sc, with_lo=with_lo)
+                if d_next is None:
+                    sc, _ = self._ss(r)
+                    d_next = ops.relu_bn_bwd_split(g, y, sc, with_lo=with_lo)
+                d, d_next = d_next, None
                 dw = torch.zeros(49, r.cout, 8 * ops.CLIP_CPAD, dtype=torch.float32, device=dev)
                 ops.conv1a_wgrad(a, d, dw, W)
                 # packed layout of this block is [kt,kh,kw,Cout,Cin]; the parameter's .grad is its strided view

@@ -372,6 +372,82 @@ static int launch_pool333_tiled(const PoolParams& p, unsigned char* argmax, cuda
     return OTAL_OK;
 }
 
+// Backward of a pool FUSED with the ReLU / frozen-BN backward of the layer that produced the pool's input, as a gather:
+// every input position sums the gradients of the (few) windows whose recorded arg-max points at it, adds an optional
+// extra gradient (another consumer of the same tensor), applies d = g * [y > 0] * scale[c] and writes the bf16 (hi, lo)
+// planes the tensor-core dgrad / wgrad kernels read.  No atomics, no zero-initialised fp32 gradient buffer, no separate
+// relu_bn_bwd_split pass: the fp32 input gradient of the pool never touches HBM.  Used for the stride-2 stage pools
+// (<= 8 windows per input); the stride-1 inception pools (27 windows per input) keep the scatter form.
+struct PoolFuse {
+    const unsigned char* argmax;     // [N,To,Ho,Wo,C]
+    const float* g_add;              // optional fp32 [N,T,H,W,add_cstride] gradient to add (NULL = none)
+    int add_cstride, add_coff;
+    const uint16_t* y_hi;            // forward value of the pool input (ReLU mask), planes layout of x
+    const float* scale;              // [C] folded BN scale or NULL
+    uint16_t *d_hi, *d_lo;           // output planes [N,T,H,W,d_cstride]
+    int d_cstride, d_coff;
+};
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_gather_fused_kernel(const PoolParams p, const PoolFuse f) {
+    const int cgs = p.C >> 3;
+    const long long total = (long long)p.N * p.T * p.H * p.W * cgs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int cg = (int)(idx % cgs);
+        long long pos = idx / cgs;
+        const long long ipos = pos;
+        const int w = (int)(pos % p.W); pos /= p.W;
+        const int h = (int)(pos % p.H); pos /= p.H;
+        const int t = (int)(pos % p.T);
+        const int n = (int)(pos / p.T);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // windows (to, ho, wo) that contain this input: o*s - pad <= x <= o*s - pad + k - 1
+        const int to_lo = max(0, (t + p.pt - p.kt + p.st) / p.st), to_hi = min(p.To - 1, (t + p.pt) / p.st);
+        const int ho_lo = max(0, (h + p.ph - p.kh + p.sh) / p.sh), ho_hi = min(p.Ho - 1, (h + p.ph) / p.sh);
+        const int wo_lo = max(0, (w + p.pw - p.kw + p.sw) / p.sw), wo_hi = min(p.Wo - 1, (w + p.pw) / p.sw);
+        for (int to = to_lo; to <= to_hi; ++to)
+            for (int ho = ho_lo; ho <= ho_hi; ++ho)
+                for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                    const uint32_t code = (uint32_t)(((t - (to * p.st - p.pt)) * p.kh + (h - (ho * p.sh - p.ph))) * p.kw +
+                                                     (w - (wo * p.sw - p.pw)));
+                    const long long opos = (((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo;
+                    const uint2 a = *reinterpret_cast<const uint2*>(f.argmax + (size_t)opos * p.C + cg * 8);
+                    const float* g = p.g_out + (size_t)opos * p.gout_cstride + p.gout_coff + cg * 8;
+                    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+                    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t cj = ((j < 4 ? a.x : a.y) >> ((j & 3) * 8)) & 0xffu;
+                        if (cj == code) acc[j] += gv[j];
+                    }
+                }
+        if (f.g_add) {
+            const float* ga = f.g_add + (size_t)ipos * f.add_cstride + f.add_coff + cg * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(ga), a1 = *reinterpret_cast<const float4*>(ga + 4);
+            acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+            acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+        }
+        const uint4 yv = *reinterpret_cast<const uint4*>(f.y_hi + (size_t)ipos * p.in_cstride + p.in_coff + cg * 8);
+        const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        uint32_t ho_[4], lo_[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x0 = acc[2 * j], x1 = acc[2 * j + 1];
+            const uint32_t y0 = yw[j] & 0xffffu, y1 = yw[j] >> 16;
+            if (!(y0 != 0 && y0 < 0x8000u)) x0 = 0.f;             // y > 0 <=> sign clear and magnitude non-zero
+            if (!(y1 != 0 && y1 < 0x8000u)) x1 = 0.f;
+            if (f.scale) { x0 *= __ldg(f.scale + cg * 8 + 2 * j); x1 *= __ldg(f.scale + cg * 8 + 2 * j + 1); }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(x0, h0, l0); split_bf16(x1, h1, l1);
+            ho_[j] = pack_bf16x2(h0, h1); lo_[j] = pack_bf16x2(l0, l1);
+        }
+        const size_t off = (size_t)ipos * f.d_cstride + f.d_coff + cg * 8;
+        *reinterpret_cast<uint4*>(f.d_hi + off) = make_uint4(ho_[0], ho_[1], ho_[2], ho_[3]);
+        if (f.d_lo) *reinterpret_cast<uint4*>(f.d_lo + off) = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+    }
+}
+
 template <int KT, int KH, int KW, int ST, int SH, int SW, int WB>
 static void launch_pool_fast(const PoolParams& p, unsigned char* argmax, cudaStream_t s) {
     const int wblocks = (p.Wo + WB - 1) / WB;
@@ -448,6 +524,30 @@ int otal_maxpool_bwd(const otal_pool_desc* d, void* stream) {
     if (rc) return rc;
     if (d->argmax) maxpool_bwd_argmax_kernel<<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, d->argmax);
     else maxpool_kernel<true><<<pool_grid(p), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+
+int otal_maxpool_bwd_relu_bn_split(const otal_pool_desc* d, const float* g_add, int add_cstride, int add_coff, const float* scale,
+                                   uint16_t* d_hi, uint16_t* d_lo, int d_cstride, int d_coff, void* stream) {
+    if (!d || !d->argmax || !d->g_out || !d->x_hi || !d_hi || d_cstride % 8 || d_coff % 8 || (g_add && (add_cstride % 4 || add_coff % 4))) {
+        set_last_error_msg("maxpool_bwd_relu_bn_split: needs the recorded arg-max, g_out, the forward input planes and d planes");
+        return OTAL_ERR_BAD_ARG;
+    }
+    otal_pool_desc dd = *d;
+    float dummy = 0.f;
+    dd.g_in = &dummy;                       // fill_pool insists on a gradient destination; the fused kernel has none
+    PoolParams p{};
+    int rc = fill_pool(&dd, p, true);
+    if (rc) return rc;
+    PoolFuse f{};
+    f.argmax = d->argmax; f.g_add = g_add; f.add_cstride = add_cstride; f.add_coff = add_coff; f.y_hi = d->x_hi; f.scale = scale;
+    f.d_hi = d_hi; f.d_lo = d_lo; f.d_cstride = d_cstride; f.d_coff = d_coff;
+    const long long total = (long long)p.N * p.T * p.H * p.W * (p.C >> 3);
+    long long b = (total + 255) / 256;
+    const long long cap = 148LL * 16;
+    maxpool_bwd_gather_fused_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, f);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

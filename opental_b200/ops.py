@@ -474,6 +474,25 @@ def maxpool_bwd(x: Planes, g_out: torch.Tensor, g_in: torch.Tensor, *, kernel, s
     _lib.call("otal_maxpool_bwd", ctypes.byref(d), _stream())
 
 
+def maxpool_bwd_relu_bn_split(x: Planes, argmax: torch.Tensor, g_out: torch.Tensor, scale: torch.Tensor | None, *, kernel, stride,
+                              pad_front, g_add: torch.Tensor | None = None, with_lo: bool = True) -> Planes:
+    """d = (maxpool_bwd(g_out) [+ g_add]) * [x > 0] * scale as bf16 planes shaped like x — the pool backward fused with the
+    ReLU / frozen-BN backward of the layer that produced x (gather form: no atomics, no fp32 intermediate)."""
+    _require_cuda(x.hi, argmax, g_out)
+    d, oshape, C = _pool_desc(x, kernel, stride, pad_front, None)
+    assert tuple(g_out.shape[:4]) == oshape and g_out.dtype == torch.float32 and g_out.is_contiguous()
+    assert argmax.dtype == torch.uint8 and tuple(argmax.shape) == (*oshape, C) and C == x.hi.shape[-1]
+    d.gout_cstride, d.gout_coff, d.g_out, d.argmax = g_out.shape[-1], 0, g_out.data_ptr(), argmax.data_ptr()
+    if g_add is not None:
+        assert g_add.dtype == torch.float32 and g_add.is_contiguous() and tuple(g_add.shape) == tuple(x.hi.shape)
+    hi = torch.empty(x.hi.shape, dtype=torch.bfloat16, device=x.hi.device)
+    lo = torch.empty_like(hi) if with_lo else None
+    if _lib.TRACE is not None:
+        _lib.LABEL = (f"pool bwd+relu_bn {tuple(x.hi.shape)} k{kernel} s{stride}", 0.0)
+    _lib.call("otal_maxpool_bwd_relu_bn_split", ctypes.byref(d), _ptr(g_add), C, 0, _ptr(scale), hi.data_ptr(), _ptr(lo), C, 0, _stream())
+    return Planes(hi, lo)
+
+
 def relu_bn_bwd_split(g: torch.Tensor, y: Planes | None, scale: torch.Tensor | None, *, C: int | None = None,
                       g_slice=None, y_slice=None, relu: bool = True, with_lo: bool = True) -> Planes:
     """d = g * [y > 0] * scale  as bf16 planes [.., C] (dense)."""
