@@ -317,6 +317,15 @@ OTAL_API int otal_decode_scores(const float* loc, const float* prop_loc, const f
 OTAL_API int otal_softnms(const float* segments, long long seg_class_stride, float* scores, unsigned char* keep, int* count, int C,
                           int M, float sigma, int top_k, float score_threshold, void* stream);
 
+/* Boundary BCE of the training script — replaces calc_bce_loss (AFSD/thumos14/train.py:152-161; anet/train.py:134-143):
+ * loss = mean over rows r = (b, t) of BCE(mean_c tanh(x[b,t,c]), target[b*target_batch_stride + t]).  x [B,T,C] contiguous.
+ * forward writes the per-row losses row_loss [B*T] (their mean is the loss) and coef [B*T] for the backward;
+ * backward: grad_x = grad_loss[0] * coef[r] * (1 - tanh(x)^2). */
+OTAL_API int otal_boundary_bce_fwd(const float* x, const float* target, long long target_batch_stride, float* row_loss, float* coef,
+                                   int B, int T, int C, void* stream);
+OTAL_API int otal_boundary_bce_bwd(const float* x, const float* coef, const float* grad_loss, float* grad_x, int B, int T, int C,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,8 @@ SIGNATURES = {
     "otal_make_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                    c_void_p]),
     "otal_dirichlet_uncertainty": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "otal_boundary_bce_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "otal_boundary_bce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "otal_decode_scores": (c_int, [c_void_p] * 13 + [c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "otal_softnms": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_float, c_void_p]),
     "otal_ncdhw_to_ndhwc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -8,10 +8,15 @@ The reference reads num_classes / os_head / evidence / ... from a global config 
 (BDNet.py:12-18); here they are keyword arguments, and `BDNet.from_config(cfg_dict, ...)` maps the same yaml keys.
 
 Backbone: `I3DBackbone` (opental_b200/backbone.py) — every Unit3D, max-pool, their gradients and the concat are
-hand-written sm_100a kernels.  BoundaryMaxPooling: the native operator (opental_b200/prop_pooling.py).  The 1-D
-pyramid / towers / heads (CoarsePyramid, BDNet.py:117-432; 5 GFLOP of 168, launch-bound) currently run as torch ops
-on the same stream; the duplicated frame-level pooling of the two proposal branches (BDNet.py:109 called from :386
-and :388 with identical arguments) is computed once per level.
+hand-written sm_100a kernels.  Head (CoarsePyramid, BDNet.py:117-432): every Unit1D / head-side Unit3D runs on the same
+tensor-core implicit-GEMM kernels (headconv.py), GroupNorm+ReLU, window generation, BoundaryMaxPooling and the Dirichlet
+uncertainty are native kernels; torch only glues them (index_select / cat / exp / autograd bookkeeping).  Two structural
+changes against the reference's per-level Python loop, both value-preserving:
+  * the towers, heads and proposal branches share their weights across the 6 pyramid levels, so they run ONCE on all levels
+    laid side by side (123 -> 28 conv calls per forward);
+  * the duplicated frame-level pooling of the two proposal branches (BDNet.py:109 called from :386 and :388 with identical
+    arguments) is computed once.
+`variant='anet'` selects the ActivityNet flavour (AFSD/anet/BDNet.py).
 
 `use_rpl`, `get_feat`, the TransformerHead and dropout > 0 are baseline / ablation variants that are off in every
 OpenTAL config: NotImplementedError.

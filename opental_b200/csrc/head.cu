@@ -90,3 +90,65 @@ int otal_dirichlet_uncertainty(const float* logit, float* unct, long long M, int
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Boundary BCE of the training script — calc_bce_loss (AFSD/thumos14/train.py:152-161):
+//     s[r] = mean_c tanh(x[r, c]);   loss = mean_r BCE(s[r], t[r])          (F.binary_cross_entropy: logs clamped at -100)
+// for x = start / end maps [B, T, C] (rows r = (b, t), C contiguous) and t = the start / end score map of the clip.
+// One warp per row: coalesced reads, shuffle reduction.  The forward also stores coef[r] = dBCE/ds / (R * C) so that the
+// backward is one elementwise pass dx = g * coef[r] * (1 - tanh(x)^2).
+// ------------------------------------------------------------------------------------------------------------------
+namespace otal {
+
+__global__ void boundary_bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ target, long long t_bstride, int T,
+                                        float* __restrict__ row_loss, float* __restrict__ coef, int R, int C) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const float* xr = x + (size_t)row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += tanhf(xr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        s /= (float)C;
+        const int b = row / T, t = row - b * T;
+        const float y = target[(size_t)b * t_bstride + t];
+        const float l1 = fmaxf(logf(s), -100.f), l0 = fmaxf(logf(1.f - s), -100.f);
+        row_loss[row] = -(y * l1 + (1.f - y) * l0);
+        // torch's binary_cross_entropy backward: (s - y) / max(s (1 - s), 1e-12)
+        coef[row] = (s - y) / fmaxf(s * (1.f - s), 1e-12f) / ((float)R * (float)C);
+    }
+}
+
+__global__ void boundary_bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ coef, const float* __restrict__ g,
+                                        float* __restrict__ gx, long long n, int C) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float gv = g[0];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float th = tanhf(x[i]);
+        gx[i] = gv * coef[i / C] * (1.f - th * th);
+    }
+}
+
+}  // namespace otal
+
+extern "C" int otal_boundary_bce_fwd(const float* x, const float* target, long long target_batch_stride, float* row_loss,
+                                     float* coef, int B, int T, int C, void* stream) {
+    if (B <= 0 || T <= 0 || C <= 0 || !x || !target || !row_loss || !coef) { otal::set_last_error_msg("boundary_bce: bad argument"); return OTAL_ERR_BAD_ARG; }
+    const long long threads = (long long)B * T * 32;
+    otal::boundary_bce_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, target, target_batch_stride, T, row_loss, coef, B * T, C);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+extern "C" int otal_boundary_bce_bwd(const float* x, const float* coef, const float* grad_loss, float* grad_x, int B, int T, int C,
+                                     void* stream) {
+    if (B <= 0 || T <= 0 || C <= 0 || !x || !coef || !grad_loss || !grad_x) { otal::set_last_error_msg("boundary_bce: bad argument"); return OTAL_ERR_BAD_ARG; }
+    const long long n = (long long)B * T * C;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    otal::boundary_bce_bwd_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, coef, grad_loss, grad_x, n, C);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}

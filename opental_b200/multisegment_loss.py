@@ -462,7 +462,11 @@ class MultiSegmentLossANet(nn.Module):
 
 
 def calc_bce_loss(start, end, scores):
-    """tanh -> mean over channels -> BCE (AFSD/thumos14/train.py:152-161)."""
+    """tanh -> mean over channels -> BCE (AFSD/thumos14/train.py:152-161).  CUDA fp32 inputs take the fused kernel
+    (one launch per map forward, one backward); anything else the equivalent torch formulation."""
+    if start.is_cuda and start.dtype == torch.float32 and scores.dtype == torch.float32 and scores.stride(2) == 1:
+        from . import ops
+        return ops.boundary_bce(start, scores[:, 0]), ops.boundary_bce(end, scores[:, 1])
     s = torch.tanh(start).mean(-1)
     e = torch.tanh(end).mean(-1)
     return (F.binary_cross_entropy(s.view(-1), scores[:, 0].contiguous().view(-1), reduction="mean"),

@@ -690,3 +690,36 @@ def softnms(segments: torch.Tensor, scores: torch.Tensor, sigma: float = 0.5, to
     _lib.call("otal_softnms", segments.data_ptr(), stride, scores.data_ptr(), keep.data_ptr(), count.data_ptr(), C, M, float(sigma),
               int(top_k), float(score_threshold), _stream())
     return scores, keep.bool(), count
+
+
+# ----------------------------------------------------------------------------------------------------------
+# boundary BCE (calc_bce_loss of the training scripts)
+# ----------------------------------------------------------------------------------------------------------
+class _BoundaryBCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        """x [B,T,C] fp32; target [B,T] fp32 view with unit stride along T (a row of the [B,2,T] score maps)."""
+        _require_cuda(x, target)
+        x = x.contiguous()
+        B, T, C = x.shape
+        assert target.shape == (B, T) and target.stride(1) == 1 and target.dtype == torch.float32 and x.dtype == torch.float32
+        row_loss = torch.empty(B * T, dtype=torch.float32, device=x.device)
+        coef = torch.empty(B * T, dtype=torch.float32, device=x.device)
+        _lib.call("otal_boundary_bce_fwd", x.data_ptr(), target.data_ptr(), target.stride(0), row_loss.data_ptr(), coef.data_ptr(),
+                  B, T, C, _stream())
+        ctx.save_for_backward(x, coef)
+        return row_loss.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, coef = ctx.saved_tensors
+        B, T, C = x.shape
+        gx = torch.empty_like(x)
+        g = g.contiguous().float().reshape(1)
+        _lib.call("otal_boundary_bce_bwd", x.data_ptr(), coef.data_ptr(), g.data_ptr(), gx.data_ptr(), B, T, C, _stream())
+        return gx, None
+
+
+def boundary_bce(x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mean_{b,t} BCE(mean_c tanh(x[b,t,c]), target[b,t]) — calc_bce_loss (thumos14/train.py:152-161) for one map."""
+    return _BoundaryBCEFn.apply(x, target)

@@ -137,3 +137,21 @@ def test_fused_loss_is_deterministic_and_sync_free():
         vals.append(torch.cat([torch.stack(list(l))] + [x.reshape(-1) for x in g]))
     assert torch.equal(vals[0], vals[1])
     assert all(math.isfinite(v) for v in vals[0][:7].tolist())
+
+
+def test_boundary_bce_kernel_matches_torch():
+    """calc_bce_loss (train.py:152-161) fused kernel vs the torch formulation the oracle uses (oracle.boundary_bce)."""
+    from opental_b200.multisegment_loss import calc_bce_loss
+    g = torch.Generator().manual_seed(8)
+    for B, T, C in ((2, 256, 256), (3, 64, 512), (1, 768, 256)):
+        start = torch.randn(B, T, C, generator=g).relu()
+        end = torch.randn(B, T, C, generator=g).relu()
+        scores = (torch.rand(B, 2, T, generator=g) > 0.7).float()
+        sr, er = start.clone().requires_grad_(True), end.clone().requires_grad_(True)
+        ls_r, le_r = O.boundary_bce(sr, er, scores)
+        (ls_r + 2 * le_r).backward()
+        sd, ed = start.cuda().requires_grad_(True), end.cuda().requires_grad_(True)
+        ls, le = calc_bce_loss(sd, ed, scores.cuda())
+        (ls + 2 * le).backward()
+        assert abs(float(ls) - float(ls_r)) < 1e-5 * max(1.0, abs(float(ls_r))) and abs(float(le) - float(le_r)) < 1e-5 * max(1.0, abs(float(le_r)))
+        assert torch.allclose(sd.grad.cpu(), sr.grad, atol=1e-9, rtol=1e-4) and torch.allclose(ed.grad.cpu(), er.grad, atol=1e-9, rtol=1e-4)
