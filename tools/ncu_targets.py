@@ -1,7 +1,8 @@
 """One launch of every hot kernel at its batch-8 THUMOS14 shape, for `ncu --set full` captures (profiles/):
 
-    ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|maxpool|bmp_|msl_|gn_relu|relu_bn' \
-        -c 24 -o gpurun_out/r01_kernels python tools/ncu_targets.py
+    ncu --set full --clock-control none --import-source on \
+        -k regex:'conv_igemm|conv_wgrad|maxpool|bmp_|msl_|gn_relu|relu_bn|clip_ingest|decode_scores|softnms|boundary_bce' \
+        -c 48 -o gpurun_out/r01_kernels python tools/ncu_targets.py
 
 Prints the launch order so the report's IDs can be mapped back to layers."""
 import os
@@ -50,8 +51,9 @@ def conv_trio(name, shape, cin, cout, k):
 
 
 # Conv3d_1a_7x7 forward + weight gradient
-clip = torch.rand(B, 3, 256, 96, 96, device=dev) * 2 - 1
-a = ops.clip_ingest(clip)
+px = torch.randint(0, 256, (B, 256, 112, 112, 3), dtype=torch.uint8, device=dev)
+a = ops.clip_ingest_u8(px, 96)
+order.append("clip_ingest_u8_kernel  uint8 [B,256,112,112,3] -> window-expanded planes")
 w1 = ops.pack_conv1a_weight(torch.randn(64, 3, 7, 7, 7, device=dev) * 0.03)
 y1 = ops.conv1a_fwd(a, w1, 96, scale=torch.ones(64, device=dev), shift=torch.zeros(64, device=dev))
 order.append("conv_igemm_kernel  fwd   Conv3d_1a_7x7 (folded)")
@@ -59,7 +61,7 @@ d1 = planes((B, 128, 48, 48, 64), relu=False)
 dw1 = torch.zeros(49, 64, 32, device=dev)
 ops.conv1a_wgrad(a, d1, dw1, 96)
 order.append("conv_wgrad_kernel  wgrad Conv3d_1a_7x7 (folded)")
-del clip, a, d1
+del px, a, d1
 
 conv_trio("Conv3d_2c_3x3 64->192 @128x24x24", (128, 24, 24), 64, 192, (3, 3, 3))
 conv_trio("Mixed_3c.b1b 128->192 @128x12x12", (128, 12, 12), 128, 192, (3, 3, 3))
@@ -68,19 +70,20 @@ conv_trio("Mixed_4f.b1b 160->320 @64x6x6", (64, 6, 6), 160, 320, (3, 3, 3))
 
 # max pools
 x = planes((B, 128, 48, 48, 64))
-yp = ops.maxpool_fwd(x, kernel=(1, 3, 3), stride=(1, 2, 2), pad_front=_pads((128, 48, 48), (1, 3, 3), (1, 2, 2)))
-order.append("maxpool_kernel<0>  MaxPool3d_2a (1,3,3)/(1,2,2) @128x48x48x64")
+yp, arg2a = ops.maxpool_fwd(x, kernel=(1, 3, 3), stride=(1, 2, 2), pad_front=_pads((128, 48, 48), (1, 3, 3), (1, 2, 2)), save_argmax=True)
+order.append("maxpool_fwd_fast<1,3,3,1,2,2>  MaxPool3d_2a @128x48x48x64 (+arg-max)")
 g = torch.randn(B, 128, 24, 24, 64, device=dev)
-gi = torch.zeros(B, 128, 48, 48, 64, device=dev)
-ops.maxpool_bwd(x, g, gi, kernel=(1, 3, 3), stride=(1, 2, 2), pad_front=_pads((128, 48, 48), (1, 3, 3), (1, 2, 2)))
-order.append("maxpool_kernel<1>  MaxPool3d_2a backward")
+ops.maxpool_bwd_relu_bn_split(x, arg2a, g, torch.ones(64, device=dev), kernel=(1, 3, 3), stride=(1, 2, 2),
+                              pad_front=_pads((128, 48, 48), (1, 3, 3), (1, 2, 2)))
+order.append("maxpool_bwd_gather_fused  MaxPool3d_2a backward + ReLU/BN backward + split")
+del arg2a
 x = planes((B, 128, 12, 12, 256))
-ops.maxpool_fwd(x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=(1, 1, 1))
-order.append("maxpool_kernel<0>  Mixed_3c.b3a (3,3,3)/1 @128x12x12x256")
+_, arg3 = ops.maxpool_fwd(x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=(1, 1, 1), save_argmax=True)
+order.append("maxpool333_tiled  Mixed_3c.b3a (3,3,3)/1 @128x12x12x256 (+arg-max)")
 g = torch.randn(B, 128, 12, 12, 256, device=dev)
 gi = torch.zeros_like(g)
-ops.maxpool_bwd(x, g, gi, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=(1, 1, 1))
-order.append("maxpool_kernel<1>  Mixed_3c.b3a backward")
+ops.maxpool_bwd(x, g, gi, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=(1, 1, 1), argmax=arg3)
+order.append("maxpool_bwd_argmax  Mixed_3c.b3a backward (scatter)")
 yq = planes((B, 128, 12, 12, 256))
 ops.relu_bn_bwd_split(g, yq, torch.ones(256, device=dev))
 order.append("relu_bn_bwd_split  @128x12x12x256")
@@ -124,6 +127,19 @@ losses = crit(out, [synthetic_targets(i).cuda() for i in range(B)])
 order.append("msl_forward_kernel  B*P = %d" % (B * P))
 sum(losses).backward()
 order.append("msl_backward_kernel")
+# boundary BCE and inference post-processing
+from opental_b200.multisegment_loss import calc_bce_loss  # noqa: E402
+st = torch.randn(B, 256, 256, device=dev).relu().requires_grad_(True)
+en = torch.randn(B, 256, 256, device=dev).relu().requires_grad_(True)
+scm = (torch.rand(B, 2, 256, device=dev) > 0.7).float()
+ls, le = calc_bce_loss(st, en, scm)
+order.append("boundary_bce_fwd_kernel x2  [B,256,256]")
+(ls + le).backward()
+order.append("boundary_bce_bwd_kernel x2")
+seg, sco, un, ac = ops.decode_scores({k: v.detach() for k, v in out.items()}, torch.zeros(B), 256, 10.0)
+order.append("decode_scores_kernel  B*P = %d, K = 15" % (B * P))
+ops.softnms(seg.reshape(-1, 2), sco.permute(1, 0, 2).reshape(15, -1), sigma=0.5, top_k=200)
+order.append("softnms_kernel  15 classes x %d candidates, top_k 200" % (B * P))
 torch.cuda.synchronize()
 print("launch order of the profiled kernels:")
 for i, o_ in enumerate(order):
