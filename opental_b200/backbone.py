@@ -366,7 +366,6 @@ class I3DBackbone(nn.Module):
         self._bind_grads()
         with_lo = self.precision == "bf16x3"
         dev = self.flat_w.device
-        x4f = saved["Mixed_4f"][1]
         x5c = saved["Mixed_5c"][1]
         g = g5.contiguous() if g5 is not None else torch.zeros(x5c.hi.shape, dtype=torch.float32, device=dev)
         g4 = g4.contiguous() if g4 is not None else None          # added inside the fused backward of MaxPool3d_5a
@@ -376,8 +375,7 @@ class I3DBackbone(nn.Module):
         d_next = None
         for name, kind, arg in reversed(ENDPOINTS):
             if kind == "mixed":
-                if name == "Mixed_4f" and d_next is None:
-                    g = g4                                   # head gradient + pool5a routing, accumulated below
+                # (Mixed_4f: its gradient planes come from the fused MaxPool3d_5a backward, which already added g4)
                 g = self._mixed_bwd(name, saved, g, d_next)
                 d_next = None
             elif kind == "pool":

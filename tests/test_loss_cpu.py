@@ -8,7 +8,7 @@ import torch
 
 import opental_oracle as O
 from opental_b200.multisegment_loss import MultiSegmentLoss, training_cost
-from opental_b200.engine import OPENTAL_ACT_CONFIG, OPENTAL_EDL_CONFIG
+from opental_b200.engine import OPENTAL_EDL_CONFIG
 
 
 def fake_outputs(B, seed, loc_scale=30.0):

@@ -61,7 +61,6 @@ def test_backbone_endpoints_match_reference_golden(golden):
 @pytest.mark.parametrize("tag,shift", [("init", 0.0), ("biased", math.log(32.0))])
 def test_forward_loss_backward_match_reference_golden(golden, tag, shift):
     arrays, summary = golden
-    from opental_b200.multisegment_loss import training_cost
     net, crit = build(shift, 11)
     x = O.synthetic_clip(0).unsqueeze(0).cuda()
     targets = [O.synthetic_targets(0, num_classes=15).cuda()]
