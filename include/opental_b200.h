@@ -109,8 +109,8 @@ OTAL_API int otal_conv_igemm_fwd(const otal_conv_desc* desc, void* stream);
 
 /* Conv3d_1a_7x7: 7x7x7, stride 2, 3 input channels -> Cout, + folded BN + ReLU
  *   AFSD/common/i3d_backbone.py:196-199 (end point), :51-87 (Unit3D.forward incl. the (2,3) "same" padding)
- * x: the clip as written by otal_clip_ingest, [N,T,H,W/2,32] bf16 planes: for every output column w' the 8-pixel x
- * 4-channel window that starts 2 pixels left of image column 2*w' (zero outside the image, channel 3 zero).
+ * x: the clip as written by otal_clip_ingest, [N,T,H,W+8,4] bf16 planes (image column w at padded column w + 2, zero
+ * elsewhere, channel slot 3 zero): output column w' reads the 8-pixel x 4-slot window starting at padded column 2*w'.
  * w: [49 (dt,dh)][Cout][32] planes, element dw*4 + c of a row = W[co,c,dt,dh,dw] (zero for dw == 7 or c == 3).
  * y: [N,ceil(T/2),ceil(H/2),W/2,out_cstride] planes at channel offset out_coff. */
 typedef struct otal_conv1a_desc {
@@ -187,11 +187,9 @@ OTAL_API int otal_maxpool_bwd_relu_bn_split(const otal_pool_desc* desc, const fl
                                             void* stream);
 
 /* Clip ingest for Conv3d_1a — replaces `clips.cuda()` + the first F.pad (AFSD/thumos14/train.py:165,
- * AFSD/common/i3d_backbone.py:59-79): NCDHW fp32 [N,C<=4,T,H,W] (W even) -> [N,T,H,W/2,8,4] bf16 planes: window w' holds
- * image columns 2*w' - 2 .. 2*w' + 5 (the 7 W taps of the stride-2 conv with its "same" front padding of 2, plus one
- * zero-weight column), 4 channel slots per pixel, zero outside the image / for channels >= C.  The 4x expansion along
- * W makes every TMA box row of Conv3d_1a a dense 64-byte run (overlapping windows read through a strided tensor map
- * are bound by the TMA request rate, not by bytes).  lo may be NULL. */
+ * AFSD/common/i3d_backbone.py:59-79): NCDHW fp32 [N,C<=4,T,H,W] (W even) -> [N,T,H,W+8,4] bf16 planes: image column w at
+ * padded column w + 2 (the conv's "same" front padding of 2 plus room for the 8-pixel windows at the right edge), 4
+ * channel slots per pixel, zero outside the image / for channels >= C.  lo may be NULL. */
 OTAL_API int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, int T, int H, int W, void* stream);
 
 /* The same planes straight from the dataset's storage format — replaces the data loader's crop / flip / normalise

@@ -588,11 +588,12 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
 }
 
 // Conv3d_1a_7x7 (AFSD/common/i3d_backbone.py:196-199): 7x7x7, stride 2, 3 input channels.
-// The clip is stored window-expanded, [N,T,H,W/2,8,4] (otal_clip_ingest): the 7 W-taps x 4 channel slots of one
-// (dt,dh) tap of output column w' are 28 contiguous values inside a 32-element (64-byte) window (8th W-tap and channel
-// 3 carry zero weights): K = 49 x 32 instead of 343 x 3 = 1029 useful (1.5x padding).  Operand rows are 64 bytes ->
-// SWIZZLE_64B TMA boxes and UMMA descriptors.  T and H use the stride-2 parity views with TMA zero fill as padding;
-// the W padding and the stride-2 window overlap are materialised by the ingest kernel so that TMA box rows are dense.
+// The clip is stored W-padded with 4 channel slots per pixel, [N,T,H,W+8,4] (otal_clip_ingest): the 7 W-taps x 4 slots of
+// one (dt,dh) tap of output column w' are 28 contiguous values inside the 32-element (64-byte) window that starts at
+// padded column 2*w' (8th W-tap and channel 3 carry zero weights): K = 49 x 32 instead of 343 x 3 = 1029 useful (1.5x
+// padding).  Operand rows are 64 bytes -> SWIZZLE_64B TMA boxes and UMMA descriptors.  T and H use the stride-2 parity
+// views with TMA zero fill as padding; W padding is physical.  (A window-expanded copy of the clip — dense TMA rows —
+// was measured: same kernel time, 4x the clip traffic; the strided map is kept.)
 int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d) { set_last_error_msg("conv1a: null descriptor"); return OTAL_ERR_BAD_ARG; }
@@ -624,16 +625,18 @@ int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
     ConvMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
-    const uint64_t win = 32 * 2;                                // bytes per window (8 pixels x 4 channels)
-    const uint64_t sH_ = win * L.Wo, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
+    const uint64_t px = 4 * 2;                                  // bytes per padded pixel (4 channel slots)
+    const uint64_t Wp = (uint64_t)d->W + 8;                     // padded row: 2 zero pixels left, 6 right (otal_clip_ingest)
+    const uint64_t sH_ = px * Wp, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
     const uint32_t abox[5] = {32, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
     for (int rt = 0; rt < 2; ++rt) for (int rh = 0; rh < 2; ++rh) {
         const int eT = (d->T - rt + 1) / 2, eH = (d->H - rh + 1) / 2;
         if (eT <= 0 || eH <= 0) continue;
-        // dim0 = the 32-element window, dim1 = output column (dense: the clip is stored window-expanded)
+        // dim0 = the 32-element window, dim1 = output column: the window origin advances 2 pixels = 16 bytes, i.e. the
+        // windows of neighbouring columns overlap in memory (strided tensor map, nothing is duplicated in HBM)
         const uint64_t adims[5] = {32, (uint64_t)L.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)p.N};
-        const uint64_t ast[4] = {win, sH_ * 2, sT_ * 2, sN_};
-        const size_t off = ((size_t)rt * d->H + rh) * L.Wo * 32;
+        const uint64_t ast[4] = {2 * px, sH_ * 2, sT_ * 2, sN_};
+        const size_t off = ((size_t)rt * d->H + rh) * Wp * 4;
         const int mi = rt * 4 + rh * 2;
         if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 2))) return rc;
         if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 2))) return rc;

@@ -501,15 +501,16 @@ int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
     WgMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
-    const uint64_t win = 32 * 2;                                // window-expanded clip: 64 bytes per output column
-    const uint64_t sH_ = win * p.Wo, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
+    const uint64_t px = 4 * 2;                                  // bytes per padded pixel; rows are W + 8 pixels (otal_clip_ingest)
+    const uint64_t Wp = (uint64_t)d->W + 8;
+    const uint64_t sH_ = px * Wp, sT_ = sH_ * d->H, sN_ = sT_ * d->T;
     const uint32_t box[5] = {32, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
     for (int rt = 0; rt < 2; ++rt) for (int rh = 0; rh < 2; ++rh) {
         const int eT = (d->T - rt + 1) / 2, eH = (d->H - rh + 1) / 2;
         if (eT <= 0 || eH <= 0) continue;
         const uint64_t xdims[5] = {32, (uint64_t)p.Wo, (uint64_t)eH, (uint64_t)eT, (uint64_t)d->N};
-        const uint64_t xst[4] = {win, sH_ * 2, sT_ * 2, sN_};
-        const size_t off = ((size_t)rt * d->H + rh) * p.Wo * 32;
+        const uint64_t xst[4] = {2 * px, sH_ * 2, sT_ * 2, sN_};
+        const size_t off = ((size_t)rt * d->H + rh) * Wp * 4;
         const int mi = rt * 4 + rh * 2;
         if ((rc = make_tensor_map_bf16(&maps.X_hi[mi], d->x_hi + off, 5, xdims, xst, box, 2))) return rc;
         if (split && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 2))) return rc;

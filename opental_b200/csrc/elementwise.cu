@@ -51,38 +51,35 @@ __global__ void ncdhw_to_ndhwc_split_kernel(const float* __restrict__ x, uint16_
 }
 
 
-// Clip ingest for Conv3d_1a: NCDHW fp32 [N,C,T,H,W] -> window-expanded [N,T,H,W/2,8,4] bf16 planes.  Window w' of a row
-// holds image columns 2*w' - 2 .. 2*w' + 5 (zero outside the image), 4 channel slots per pixel (zero for c >= C).
-// One thread per (window, pixel pair): reads are coalesced along w per channel plane, each thread writes 16 bytes
-// (2 pixels x 4 channels) per plane, a warp writes 512 contiguous bytes.
+// Clip ingest for Conv3d_1a: NCDHW fp32 [N,C,T,H,W] -> [N,T,H,Wp,4] bf16 planes with Wp = W + 8: image column w lands at
+// padded column w + 2 (2 zero columns left, 6 right), 4 channel slots per pixel (zero for c >= C).  The 8-pixel x 4-slot
+// window of output column w' of the stride-2 conv is then the 32 contiguous elements starting at padded column 2*w'
+// (read by TMA through a strided tensor map: overlapping windows, no expansion in memory).  One thread per padded pixel:
+// reads are coalesced along w per channel plane, each thread writes 8 bytes per plane.
 __global__ void clip_ingest_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                    int N, int C, int T, int H, int W) {
-    const int Wo = W >> 1;
-    const long long total = (long long)N * T * H * Wo * 4;          // 4 pixel pairs per window
+    const int Wp = W + 8;
+    const long long total = (long long)N * T * H * Wp;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long THW = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int pp = (int)(i & 3);
-        const long long win = i >> 2;
-        const int wo = (int)(win % Wo);
-        const long long row = win / Wo;               // (n*T + t)*H + h
-        const long long n = row / ((long long)T * H);
-        const long long th = row - n * (long long)T * H;
-        uint32_t h32[4] = {0, 0, 0, 0}, l32[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int w = 2 * wo - 2 + 2 * pp + q;
-            if (w < 0 || w >= W) continue;
+        const int wp = (int)(i % Wp);
+        const long long row = i / Wp;                 // (n*T + t)*H + h
+        const int w = wp - 2;
+        uint32_t h32[2] = {0, 0}, l32[2] = {0, 0};
+        if (w >= 0 && w < W) {
+            const long long n = row / ((long long)T * H);
+            const long long th = row - n * (long long)T * H;
             const float* src = x + n * C * THW + th * W + w;
             for (int c = 0; c < C && c < 4; ++c) {
                 __nv_bfloat16 hb, lb;
                 split_bf16(src[c * THW], hb, lb);
-                h32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
-                l32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
+                h32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
+                l32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
             }
         }
-        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h32[0], h32[1], h32[2], h32[3]);
-        if (lo) reinterpret_cast<uint4*>(lo)[i] = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2(h32[0], h32[1]);
+        if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(l32[0], l32[1]);
     }
 }
 
@@ -188,23 +185,19 @@ static inline int grid_for(long long work_items, int threads) {
 // Replaces the CPU crop / flip / normalise of the data loader (videotransforms.py:30-124) and a 4x larger H2D copy.
 __global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, const int* __restrict__ crop, uint16_t* __restrict__ hi,
                                       uint16_t* __restrict__ lo, int N, int T, int Hs, int Ws, int H, int W, int oh_def, int ow_def) {
-    const int Wo = W >> 1;
-    const long long total = (long long)N * T * H * Wo * 4;
+    const int Wp = W + 8;
+    const long long total = (long long)N * T * H * Wp;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int pp = (int)(i & 3);
-        const long long win = i >> 2;
-        const int wo = (int)(win % Wo);
-        long long row = win / Wo;                     // (n*T + t)*H + h
+        const int wp = (int)(i % Wp);
+        long long row = i / Wp;                       // (n*T + t)*H + h
         const int h = (int)(row % H); row /= H;
         const int t = (int)(row % T);
         const int n = (int)(row / T);
-        const int oh = crop ? crop[3 * n] : oh_def, ow = crop ? crop[3 * n + 1] : ow_def, flip = crop ? crop[3 * n + 2] : 0;
-        uint32_t h32[4] = {0, 0, 0, 0}, l32[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int w = 2 * wo - 2 + 2 * pp + q;
-            if (w < 0 || w >= W) continue;
+        const int w = wp - 2;
+        uint32_t h32[2] = {0, 0}, l32[2] = {0, 0};
+        if (w >= 0 && w < W) {
+            const int oh = crop ? crop[3 * n] : oh_def, ow = crop ? crop[3 * n + 1] : ow_def, flip = crop ? crop[3 * n + 2] : 0;
             const int ws = ow + (flip ? W - 1 - w : w);
             const unsigned char* src = px + ((((size_t)n * T + t) * Hs + (oh + h)) * Ws + ws) * 3;
 #pragma unroll
@@ -212,12 +205,12 @@ __global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, cons
                 const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)src[c], 255.f), 2.f), 1.f);
                 __nv_bfloat16 hb, lb;
                 split_bf16(v, hb, lb);
-                h32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
-                l32[q * 2 + (c >> 1)] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
+                h32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(hb) << ((c & 1) * 16);
+                l32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(lb) << ((c & 1) * 16);
             }
         }
-        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h32[0], h32[1], h32[2], h32[3]);
-        if (lo) reinterpret_cast<uint4*>(lo)[i] = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2(h32[0], h32[1]);
+        if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(l32[0], l32[1]);
     }
 }
 
@@ -266,7 +259,7 @@ int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N, int C, i
         set_last_error_msg("clip_ingest: bad argument (C <= 4, W even)"); return OTAL_ERR_BAD_ARG;
     }
     if (N == 0) return OTAL_OK;
-    clip_ingest_kernel<<<grid_for((long long)N * T * H * (W / 2) * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    clip_ingest_kernel<<<grid_for((long long)N * T * H * (W + 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, hi, lo, N, C, T, H, W);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
@@ -318,7 +311,7 @@ extern "C" int otal_clip_ingest_u8(const unsigned char* px, const int* crop, uin
         otal::set_last_error_msg("clip_ingest_u8: bad argument (W even, crop inside the frame)"); return OTAL_ERR_BAD_ARG;
     }
     if (N == 0) return OTAL_OK;
-    otal::clip_ingest_u8_kernel<<<otal::grid_for((long long)N * T * H * (W / 2) * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    otal::clip_ingest_u8_kernel<<<otal::grid_for((long long)N * T * H * (W + 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         px, crop, hi, lo, N, T, Hs, Ws, H, W, (Hs - H) / 2, (Ws - W) / 2);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;

@@ -311,31 +311,32 @@ def conv_wgrad(x: Planes, d: Planes, dw: torch.Tensor, *, kernel: tuple[int, int
 # ----------------------------------------------------------------------------------------------------------
 # Conv3d_1a_7x7 (stride 2, 3 channels) in the folded layout
 # ----------------------------------------------------------------------------------------------------------
-CLIP_CPAD = 4          # channel slots per pixel in the window-expanded clip
+CLIP_CPAD = 4          # channel slots per pixel of the padded clip
 CLIP_WIN = 8           # pixels per window (7 W taps + 1 zero-weight slot)
+CLIP_WPAD = 8          # padded row = W + 8 pixels (2 left, 6 right)
 
 
 def clip_ingest(x: torch.Tensor, with_lo: bool = True) -> Planes:
-    """NCDHW fp32 clip [N,3,T,H,W] -> window-expanded [N,T,H,W/2,32] bf16 planes, the input of conv1a_fwd."""
+    """NCDHW fp32 clip [N,3,T,H,W] -> W-padded [N,T,H,W+8,4] bf16 planes, the input of conv1a_fwd."""
     _require_cuda(x)
     x = x.contiguous().float()
     N, C, T, H, W = x.shape
     assert W % 2 == 0 and C <= CLIP_CPAD
-    hi = torch.empty((N, T, H, W // 2, CLIP_WIN * CLIP_CPAD), dtype=torch.bfloat16, device=x.device)
+    hi = torch.empty((N, T, H, W + CLIP_WPAD, CLIP_CPAD), dtype=torch.bfloat16, device=x.device)
     lo = torch.empty_like(hi) if with_lo else None
     _lib.call("otal_clip_ingest", x.data_ptr(), hi.data_ptr(), _ptr(lo), N, C, T, H, W, _stream())
     return Planes(hi, lo)
 
 
 def clip_ingest_u8(px: torch.Tensor, crop: int = 96, offsets: torch.Tensor | None = None, with_lo: bool = True) -> Planes:
-    """uint8 frames [N,T,Hs,Ws,3] -> window-expanded planes of the normalised crop ((x/255)*2-1, bit-identical to torch).
+    """uint8 frames [N,T,Hs,Ws,3] -> W-padded planes [N,T,crop,crop+8,4] of the normalised crop ((x/255)*2-1, bit-identical).
     offsets: optional int32 device tensor [N,3] = (row offset, column offset, mirror flag); default centre crop."""
     _require_cuda(px)
     assert px.dtype == torch.uint8 and px.dim() == 5 and px.shape[-1] == 3 and px.is_contiguous()
     N, T, Hs, Ws, _ = px.shape
     if offsets is not None:
         assert offsets.dtype == torch.int32 and offsets.is_cuda and tuple(offsets.shape) == (N, 3) and offsets.is_contiguous()
-    hi = torch.empty((N, T, crop, crop // 2, CLIP_WIN * CLIP_CPAD), dtype=torch.bfloat16, device=px.device)
+    hi = torch.empty((N, T, crop, crop + CLIP_WPAD, CLIP_CPAD), dtype=torch.bfloat16, device=px.device)
     lo = torch.empty_like(hi) if with_lo else None
     _lib.call("otal_clip_ingest_u8", px.data_ptr(), _ptr(offsets), hi.data_ptr(), _ptr(lo), N, T, Hs, Ws, crop, crop, _stream())
     return Planes(hi, lo)
@@ -358,9 +359,9 @@ def unpack_conv1a_wgrad(dw: torch.Tensor, C: int = 3) -> torch.Tensor:
 
 def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shift: torch.Tensor | None,
                relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None) -> Planes:
-    N, T, H, Wo_, K_ = x.hi.shape
+    N, T, H, Wp_, C4 = x.hi.shape
     taps, Cout, K = w.hi.shape
-    assert Wo_ == W // 2 and K_ == CLIP_WIN * CLIP_CPAD and taps == 49 and K == K_
+    assert Wp_ == W + CLIP_WPAD and C4 == CLIP_CPAD and taps == 49 and K == CLIP_WIN * CLIP_CPAD
     nsplit = 3 if (x.lo is not None and w.lo is not None) else 1
     To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
     if out is None:
@@ -383,9 +384,10 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
 
 def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[int, int] | None = None) -> None:
     """dw [49, Cout, 32] fp32 += folded weight gradient of Conv3d_1a."""
-    N, T, H, Wo_, K_ = x.hi.shape
+    N, T, H, Wp_, C4 = x.hi.shape
     taps, Cout, K = dw.shape
-    assert Wo_ == W // 2 and taps == 49 and K == K_ == CLIP_WIN * CLIP_CPAD and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert Wp_ == W + CLIP_WPAD and C4 == CLIP_CPAD and taps == 49 and K == CLIP_WIN * CLIP_CPAD
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
     nsplit = 3 if (x.lo is not None and d.lo is not None) else 1
     To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
     assert tuple(d.hi.shape[:4]) == (N, To, Ho, Wo)

@@ -53,7 +53,7 @@ def conv_trio(name, shape, cin, cout, k):
 # Conv3d_1a_7x7 forward + weight gradient
 px = torch.randint(0, 256, (B, 256, 112, 112, 3), dtype=torch.uint8, device=dev)
 a = ops.clip_ingest_u8(px, 96)
-order.append("clip_ingest_u8_kernel  uint8 [B,256,112,112,3] -> window-expanded planes")
+order.append("clip_ingest_u8_kernel  uint8 [B,256,112,112,3] -> W-padded planes [B,256,96,104,4]")
 w1 = ops.pack_conv1a_weight(torch.randn(64, 3, 7, 7, 7, device=dev) * 0.03)
 y1 = ops.conv1a_fwd(a, w1, 96, scale=torch.ones(64, device=dev), shift=torch.zeros(64, device=dev))
 order.append("conv_igemm_kernel  fwd   Conv3d_1a_7x7 (folded)")
