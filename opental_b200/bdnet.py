@@ -424,13 +424,17 @@ class BDNet(nn.Module):
 
     @classmethod
     def from_config(cls, config: dict, **kw):
-        """Map the reference's yaml keys (AFSD/common/config.py, BDNet.py:12-18) to constructor arguments."""
+        """Map the reference's yaml keys (AFSD/common/config.py, BDNet.py:12-18) to constructor arguments; explicit
+        keyword arguments (the reference's own call `BDNet(in_channels=..., backbone_model=..., use_edl=...)`,
+        train.py:314) win over the config."""
         m = config.get("model", {})
-        return cls(in_channels=m.get("in_channels", 3), backbone_model=kw.pop("backbone_model", m.get("backbone_model")),
-                   num_classes=config["dataset"]["num_classes"], os_head=m.get("os_head", False),
-                   evidence=m.get("evidence", "exp"), dropout=m.get("dropout", 0.0),
-                   frame_num=config["dataset"]["training"]["clip_length"],
-                   freeze_bn=m.get("freeze_bn", True), freeze_bn_affine=m.get("freeze_bn_affine", True), **kw)
+        args = dict(in_channels=m.get("in_channels", 3), backbone_model=m.get("backbone_model"),
+                    num_classes=config["dataset"]["num_classes"], os_head=m.get("os_head", False),
+                    evidence=m.get("evidence", "exp"), dropout=m.get("dropout", 0.0),
+                    frame_num=config["dataset"]["training"]["clip_length"],
+                    freeze_bn=m.get("freeze_bn", True), freeze_bn_affine=m.get("freeze_bn_affine", True))
+        args.update(kw)
+        return cls(**args)
 
     def load_pretrained_weight(self, model_path):
         """I3D_BackBone.load_pretrained_weight (BDNet.py:35-37): Kinetics I3D state_dict, strict=False."""
