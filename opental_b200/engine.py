@@ -253,6 +253,38 @@ class Trainer:
         return cost, losses, ls, le
 
 
+    # ---------------------------------------------------------------------------------------------- bookkeeping
+    def grad_norm(self) -> torch.Tensor:
+        """`get_grad_norm` (thumos14/train.py:132-139): global L2 norm of the gradients of all trainable parameters, as a
+        0-dim device tensor (no synchronisation).  Three reductions over the flat buffers (their alignment padding is
+        zero) instead of 275 per-parameter norms.  After `step()` the buffers hold the rank-summed gradients; the 1/world
+        factor the Adam kernel applies is applied here too, so the value is the norm of the averaged gradient."""
+        sq = torch.stack([torch.linalg.vector_norm(g) ** 2 for _, g in self.groups]).sum()
+        return sq.sqrt() * self.reducer.grad_scale
+
+    def optimizer_state_dict(self) -> dict:
+        """The `torch.optim.Adam(net.parameters()).state_dict()` a reference run would hold at this point (train.py:115)."""
+        from . import checkpoint
+        return checkpoint.adam_state_dict(list(self.net.parameters()), self.groups, self.state, step=self.step_count,
+                                          lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd)
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        from . import checkpoint
+        self.step_count = checkpoint.load_adam_state_dict(sd, list(self.net.parameters()), self.groups, self.state)
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+
+    def save_checkpoint(self, epoch: int, checkpoint_path: str, train_state_path: str):
+        """`save_model` (train.py:106-118): model state_dict + {'optimizer', 'state'} in the reference's file layout."""
+        from . import checkpoint
+        return checkpoint.save(self, epoch, checkpoint_path, train_state_path)
+
+    def resume(self, resume_epoch: int, checkpoint_path: str, train_state_path: str) -> int:
+        """`resume_training` (train.py:121-131)."""
+        from . import checkpoint
+        return checkpoint.resume(self, resume_epoch, checkpoint_path, train_state_path)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # synthetic workload (SURVEY §8d conventions) — shared by bench.py, smoke() and the tests
 # ----------------------------------------------------------------------------------------------------------

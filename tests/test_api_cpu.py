@@ -58,3 +58,44 @@ def test_unsupported_variants_raise():
     from opental_b200.multisegment_loss import MultiSegmentLoss
     with pytest.raises(NotImplementedError):
         MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="rpl")
+
+
+def test_optimizer_state_interoperates_with_torch_adam():
+    """The flat Adam moment buffers <-> `torch.optim.Adam(net.parameters()).state_dict()` (the 'optimizer' entry of the
+    reference's training-state file, train.py:115), through the parameters' views into the flat buffers."""
+    from opental_b200 import checkpoint as ck
+    from opental_b200.bdnet import BDNet
+    from opental_b200.engine import FlatParams
+    net = BDNet(training=False, use_edl=True, num_classes=16, os_head=True)
+    net.train()
+    dev = torch.device("cpu")
+    bb, hc = net.backbone, net.coarse_pyramid_detection.conv_store
+    w, g = bb.flat_parameters(dev)
+    hc.ensure(dev)
+    skip = {id(p) for p in bb.parameters()} | {id(r.weight) for r in hc.recs}
+    head = FlatParams([p for p in net.parameters() if p.requires_grad and id(p) not in skip])
+    groups = [(w, g), (hc.flat_w, hc.flat_g), (head.w, head.g)]
+    gen = torch.Generator().manual_seed(0)
+    state = [dict(m=torch.randn(a.shape, generator=gen), v=torch.rand(a.shape, generator=gen)) for a, _ in groups]
+    params = list(net.parameters())
+    sd = ck.adam_state_dict(params, groups, state, step=7, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)
+    trainable = [i for i, p in enumerate(params) if p.requires_grad]
+    assert sorted(sd["state"]) == trainable and sum(params[i].numel() for i in trainable) == 44721259      # SURVEY §8e
+    opt = torch.optim.Adam(net.parameters(), lr=1.0)
+    opt.load_state_dict(sd)                                  # torch accepts it ...
+    back = opt.state_dict()
+    assert back["param_groups"][0]["lr"] == 1e-5 and back["param_groups"][0]["weight_decay"] == 1e-3
+    state2 = [dict(m=torch.zeros_like(a), v=torch.zeros_like(a)) for a, _ in groups]
+    assert ck.load_adam_state_dict(back, params, groups, state2) == 7      # ... and its own dict loads back losslessly
+    for i in trainable:
+        for key in ("m", "v"):
+            a = ck.moment_view(params[i], groups, [s[key] for s in state])
+            assert torch.equal(a, ck.moment_view(params[i], groups, [s[key] for s in state2]))
+            assert torch.equal(a, sd["state"][i]["exp_avg" if key == "m" else "exp_avg_sq"])
+    # torch 1.9 (the reference's pin) stores `step` as a python int
+    for ent in back["state"].values():
+        ent["step"] = 7
+    assert ck.load_adam_state_dict(back, params, groups, state2) == 7
+    with pytest.raises(ValueError):
+        bad = dict(state={}, param_groups=[dict(params=list(range(3)))])
+        ck.load_adam_state_dict(bad, params, groups, state2)
