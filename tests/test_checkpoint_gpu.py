@@ -37,8 +37,9 @@ def test_resume_is_bit_exact_and_matches_torch_adam(tmp_path):
     assert set(st) >= {"optimizer", "state"} and len(st["optimizer"]["state"]) == 161
 
     net2, crit2, tr2 = _trainer(1)
-    for w, _ in tr2.groups:
-        w.add_(0.01)                                        # make sure resume really overwrites
+    with torch.no_grad():
+        for p in net2.parameters():
+            p.add_(0.01)                                    # make sure resume really overwrites (views: padding untouched)
     assert tr2.resume(2, ckpt, state) == 3
     assert tr2.step_count == 2 and crit2.cls_loss.epoch == 11
     assert torch.equal(crit2.cls_loss.weight_accum, crit.cls_loss.weight_accum)
