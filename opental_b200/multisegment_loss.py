@@ -84,23 +84,42 @@ class FocalLoss_Ori(nn.Module):
 
 
 class EvidenceLoss(nn.Module):
-    """EDL classification loss, loss_type 'log' / 'digamma', evidence exp / relu / softplus, optional IBM
-    re-weighting and IoU-aware calibration (cls_loss.py:81-285).  The GHM / IB / focal-EDL / mse branches are ablations
-    outside the OpenTAL configs: NotImplementedError."""
+    """EDL classification loss with every branch of the reference (cls_loss.py:81-285): loss_type log / digamma / mse,
+    evidence exp / relu / softplus, soft labels, IoU-aware calibration, and the re-weighting branches in the
+    reference's precedence order focal > GHM > IB > IBM > plain (cls_loss.py:221-272).  All branches are written in
+    the masked, synchronisation-free form (`weight` marks the real rows; the reference gathers them with a boolean
+    mask and loops over bins with `.item()`), so they can be captured into the training graph.  The OpenTAL
+    configuration (log / exp / IBM) additionally has the fused CUDA kernel (MultiSegmentLoss._fused_ok)."""
 
     def __init__(self, num_cls, cfg, size_average=False):
         super().__init__()
         self.num_cls = num_cls
         self.loss_type = cfg["loss_type"]
         self.evidence = cfg["evidence"]
-        if self.loss_type not in ("log", "digamma"):
-            raise NotImplementedError(f"loss_type {self.loss_type}")
-        for k in ("with_focal", "with_ghm", "with_ibloss"):
-            if cfg.get(k, False):
-                raise NotImplementedError(f"{k} is an ablation branch outside the OpenTAL configs")
+        if self.loss_type not in ("log", "digamma", "mse"):
+            raise NotImplementedError(f"loss_type {self.loss_type}")          # cls_loss.py:177-178
+        self.with_focal = cfg.get("with_focal", False)
         self.soft_label = cfg.get("soft_label", 0.0)
         self.iou_aware = cfg.get("iou_aware", False)
+        self.with_ghm = cfg.get("with_ghm", False)
+        self.with_ibloss = cfg.get("with_ibloss", False)
         self.with_ibm = cfg.get("with_ibm", False)
+        if self.with_focal:
+            alpha = torch.ones(num_cls) * (1 - cfg["alpha"])
+            alpha[0] = cfg["alpha"]
+            self.register_buffer("alpha", alpha, persistent=False)
+            self.gamma = cfg["gamma"]
+        if self.with_ghm:
+            self.num_bins = cfg["num_bins"]
+            self.momentum = cfg["momentum"]
+            self.ghm_start = cfg.get("ghm_start", 0)
+            edges = [float(x) / self.num_bins for x in range(self.num_bins + 1)]
+            edges[-1] += 1e-6
+            self.register_buffer("edges", torch.tensor(edges, dtype=torch.float32), persistent=False)
+            # the reference keeps python floats (double precision): fp64 buffer
+            self.register_buffer("acc_sum", torch.zeros(self.num_bins, dtype=torch.float64))
+        if self.with_ibloss:
+            self.ib_start = cfg.get("ib_start", 10)
         if self.with_ibm:
             self.ibm_start = cfg.get("ibm_start", 0)
             self.num_bins = cfg.get("num_bins", 50)
@@ -124,30 +143,72 @@ class EvidenceLoss(nn.Module):
         reg = -ious * torch.log(1 - unc) - (1 - ious) * torch.log(unc)
         return reg.mean() if mean else reg.sum()
 
+    def _reduce(self, per, weight):
+        per = torch.where(weight, per, torch.zeros_like(per))
+        if self.size_average:
+            return per.sum() / weight.sum().clamp(min=1)
+        return per.sum()
+
     def forward(self, logit, target, weight=None):
         """logit [M,K]; target [M] in 0..K-1; weight [M] bool = which rows are real samples (masked formulation of the
         reference's boolean gather).  Returns the summed (or mean) loss."""
-        func = torch.log if self.loss_type == "log" else torch.digamma
         target = target.view(-1)
-        M = logit.shape[0]
+        M, K = logit.shape[0], self.num_cls
         if weight is None:
             weight = torch.ones(M, dtype=torch.bool, device=logit.device)
-        y = (target.unsqueeze(-1) == torch.arange(self.num_cls, device=logit.device)).to(logit.dtype)   # sync-free one-hot
+        wf = weight.to(logit.dtype)
+        y = (target.unsqueeze(-1) == torch.arange(K, device=logit.device)).to(logit.dtype)   # sync-free one-hot
         if self.soft_label:
-            y = torch.where(y == 1, torch.full_like(y, 1 - self.soft_label), torch.full_like(y, self.soft_label / (self.num_cls - 1)))
+            y = torch.where(y == 1, torch.full_like(y, 1 - self.soft_label), torch.full_like(y, self.soft_label / (K - 1)))
         alpha = self.evidence_func(logit) + 1
         S = alpha.sum(dim=1, keepdim=True)
-        per = (y * (func(S) - func(alpha))).sum(dim=1)
-        if self.with_ibm and self.epoch >= self.ibm_start:
+        if self.loss_type == "mse":                      # cls_loss.py:193-209: both terms carry 'loss' in their key
+            err = ((y - alpha / S) ** 2).sum(dim=1)
+            var = (alpha * (S - alpha) / (S * S * (S + 1))).sum(dim=1)
+            return self._reduce(err, weight) + self._reduce(var, weight)
+        func = torch.log if self.loss_type == "log" else torch.digamma
+        base = y * (func(S) - func(alpha))
+        if self.with_focal:                              # cls_loss.py:221-227 (the modulating factor is NOT detached)
+            pred = (alpha / S).max(dim=1).values
+            w = self.alpha.to(logit.device)[target.clamp(0, K - 1)] * torch.pow(1.0 - pred, self.gamma)
+            return self._reduce((base * w.unsqueeze(-1)).sum(dim=1), weight)
+        if self.with_ghm and self.epoch >= self.ghm_start:          # cls_loss.py:228-249
+            with torch.no_grad():
+                a = alpha.detach()
+                unc = K / a.sum(dim=-1, keepdim=True)
+                g = (1 / a - unc).abs() * y                                        # [M,K] gradient length
+                edges = self.edges.to(logit.device)
+                inb = (g.unsqueeze(-1) >= edges[:-1]) & (g.unsqueeze(-1) < edges[1:]) & weight.view(M, 1, 1)   # [M,K,bins]
+                cnt = inb.sum(dim=(0, 1)).to(torch.float64)
+                if self.momentum > 0:
+                    acc = torch.where(cnt > 0, self.momentum * self.acc_sum + (1 - self.momentum) * cnt, self.acc_sum)
+                    self.acc_sum.copy_(acc)
+                else:
+                    acc = cnt
+                per_bin = torch.where(cnt > 0, 1.0 / acc.clamp(min=1e-300), torch.zeros_like(acc)).to(logit.dtype)
+                n = (cnt > 0).sum()
+                w = (inb.to(logit.dtype) * per_bin).sum(dim=-1)                     # every element is in at most one bin
+                w = torch.where(n > 0, w / n.clamp(min=1).to(logit.dtype), w)
+            return self._reduce((base * w).sum(dim=1), weight)
+        per = base.sum(dim=1)
+        if self.with_ibloss and self.epoch >= self.ib_start:        # cls_loss.py:250-256
+            with torch.no_grad():
+                a = alpha.detach()
+                unc = K / a.sum(dim=-1, keepdim=True)
+                grad_norm = ((1 / a - unc).abs() * y).sum(dim=1)
+                # padding rows carry target -1 -> grad_norm 0 -> 1/0: keep inf out of the graph (inf * 0 = NaN in backward)
+                w = torch.where(weight, 1 / (grad_norm * logit.abs().sum(1)), torch.zeros_like(grad_norm))
+            per = w * per
+        elif self.with_ibm and self.epoch >= self.ibm_start:
             with torch.no_grad():       # cls_loss.py:257-270
                 feat_norm = logit.abs().sum(1)
                 a = alpha.detach()
-                unc = self.num_cls / a.sum(dim=-1, keepdim=True)
+                unc = K / a.sum(dim=-1, keepdim=True)
                 grad_norm = ((1 / a - unc).abs() * y).sum(dim=1)
                 grad_hat = grad_norm * feat_norm
                 bins = torch.ceil(grad_norm * self.num_bins).long()                 # 1..num_bins (0 if grad_norm == 0)
                 onehot = (bins.unsqueeze(-1) == torch.arange(1, self.num_bins + 1, device=logit.device)).to(logit.dtype)
-                onehot = onehot * weight.to(logit.dtype).unsqueeze(1)
+                onehot = onehot * wf.unsqueeze(1)
                 cnt = onehot.sum(0)
                 mean = (onehot * grad_hat.unsqueeze(1)).sum(0) / cnt.clamp(min=1)
                 if self.weight_accum.device != logit.device:
@@ -156,10 +217,7 @@ class EvidenceLoss(nn.Module):
                 self.weight_accum.copy_(acc)     # in place: the buffer keeps its address (CUDA-graph replays update it)
                 w = acc[(bins - 1) % self.num_bins]                                 # bin 0 -> index -1 (python wrap)
             per = w * per
-        per = torch.where(weight, per, torch.zeros_like(per))
-        if self.size_average:
-            return per.sum() / weight.sum().clamp(min=1)
-        return per.sum()
+        return self._reduce(per, weight)
 
 
 class ActionnessLoss(nn.Module):
@@ -269,12 +327,12 @@ class MultiSegmentLoss(nn.Module):
         return loc_t, conf_t, prop_loc_t, prop_conf_t, iou
 
     def _fused_ok(self, loc) -> bool:
-        """The single-CTA CUDA kernel covers the OpenTAL configuration; every other variant (focal, digamma, relu /
-        softplus evidence, soft labels, size_average, closed-set head) runs the masked torch formulation below."""
+        """The single-CTA CUDA kernel covers the OpenTAL configuration; every other variant (focal loss, digamma / mse,
+        relu / softplus evidence, soft labels, focal-EDL / GHM / IB re-weighting, size_average, closed-set head) runs the masked torch formulation below."""
         c = self.cls_loss
         return (self.fused and loc.is_cuda and loc.dtype == torch.float32 and self.cls_loss_type == "edl" and self.os_head
                 and not self.size_average and c.loss_type == "log" and c.evidence == "exp" and not c.soft_label
-                and loc.shape[0] * loc.shape[1] <= 4096)
+                and not (c.with_focal or c.with_ghm or c.with_ibloss) and loc.shape[0] * loc.shape[1] <= 4096)
 
     def forward(self, output_dict, targets, pre_locs=None):
         loc, conf, ploc, pconf, center, priors = (output_dict[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))

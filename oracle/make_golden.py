@@ -299,6 +299,56 @@ def infer_cases():
     ns.restore_cuda()
 
 
+def edl_cases():
+    """Every branch of EvidenceLoss (cls_loss.py:81-285) on seeded logits, called repeatedly so the stateful branches
+    (GHM acc_sum, IBM weight_accum) evolve: reference vs oracle, loss value and gradient."""
+    import importlib
+    ns = ref_loader.load_reference()
+    ref_cls = importlib.import_module("AFSD.thumos14.cls_loss")
+    K = 15
+    arrays = {}
+    for name, (cfg, epochs) in O.EDL_VARIANTS.items():
+        size_average = name.endswith("_mean")
+        ref = ref_cls.EvidenceLoss(K, dict(cfg), size_average=size_average)
+        st = O.EdlVariantState(cfg.get("num_bins", 50))
+        for call, epoch in enumerate(epochs):
+            logit, target = O.edl_inputs(name, call, K)
+            ref.epoch = st.epoch = epoch
+            lr = logit.clone().requires_grad_(True)
+            loss_r = ref(lr, target)
+            loss_r.backward()
+            lo = logit.clone().requires_grad_(True)
+            loss_o = O.evidence_loss_variant(lo, target, st, K, cfg, size_average=size_average)
+            loss_o.backward()
+            assert abs(float(loss_r) - float(loss_o)) <= TOL * max(1.0, abs(float(loss_r))), (name, call, float(loss_r), float(loss_o))
+            assert rel(lo.grad, lr.grad) < TOL, (name, call, rel(lo.grad, lr.grad))
+            arrays[f"{name}.{call}.loss"] = np.array(float(loss_r), dtype=np.float64)
+            arrays[f"{name}.{call}.grad"] = lr.grad.numpy().copy()
+        if cfg.get("with_ibm"):
+            assert torch.allclose(ref.weight_accum, st.weight_accum, atol=1e-7)
+            arrays[f"{name}.weight_accum"] = ref.weight_accum.numpy().copy()
+        if cfg.get("with_ghm") and cfg.get("momentum", 0) > 0:
+            assert np.allclose(ref.acc_sum, st.acc_sum, rtol=1e-12)
+            arrays[f"{name}.acc_sum"] = np.array(ref.acc_sum)
+        # the same configuration inside the whole MultiSegmentLoss (reference values only: the product's masked
+        # formulation is checked against them in tests/test_loss_cpu.py)
+        msl = ns.MultiSegmentLoss(K, 0.5, 1.0, use_gpu=False, cls_loss_type="edl", edl_config=dict(cfg, iou_aware=True), os_head=True,
+                                  act_config=dict(weight=0.1, margin=1.0))
+        msl.cls_loss.epoch = 11
+        for it in range(2):
+            out = {k: v.requires_grad_(True) for k, v in O.fake_head_outputs(3, 5 + it, K).items()}
+            out["priors"] = torch.cat(O.level_priors(O.OracleConfig()), 0)
+            losses = msl(out, [O.synthetic_targets(i, num_classes=K) for i in range(3)])
+            keys = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
+            grads = torch.autograd.grad(sum(w * l for w, l in zip((1, 10, 1, 10, 1, 1, 1), losses)), [out[k] for k in keys])
+            arrays[f"{name}.msl.{it}.losses"] = np.array([float(l) for l in losses])
+            for k, gk in zip(keys, grads):
+                arrays[f"{name}.msl.{it}.grad.{k}"] = gk.numpy().copy()
+        print(f"[edl] {name}: oracle == reference over {len(epochs)} calls")
+    np.savez_compressed(os.path.join(GOLD, "edl_variants.npz"), **arrays)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -308,6 +358,8 @@ if __name__ == "__main__":
         ssl_cases()
     elif "--infer" in sys.argv:
         infer_cases()
+    elif "--edl" in sys.argv:
+        edl_cases()
     else:
         bmp_cases()
         model_cases()

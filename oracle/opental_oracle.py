@@ -625,6 +625,117 @@ def edl_loss(logit, target, state: LossState, cfg: OracleConfig):
     return per.sum()
 
 
+class EdlVariantState:
+    """Mutable state of the ablation branches of EvidenceLoss (cls_loss.py:101-116): epoch, GHM `acc_sum` (python
+    floats), IBM `weight_accum`."""
+
+    def __init__(self, num_bins: int, epoch: int = 0):
+        self.epoch = epoch
+        self.acc_sum = [0.0] * num_bins
+        self.weight_accum = torch.ones(num_bins)
+
+
+def evidence_loss_variant(logit, target, state: EdlVariantState, num_cls: int, cfg: dict, size_average=False):
+    """EvidenceLoss.forward with EVERY branch of the reference (cls_loss.py:132-285): loss_type log / digamma / mse,
+    evidence exp / relu / softplus, soft labels, and the re-weighting branches in the reference's precedence order
+    focal (:221-227) > GHM (:228-249) > IB (:250-256) > IBM (:257-270) > plain (:272).  The OpenTAL configuration is the
+    IBM branch (`edl_loss` above); the others are the paper's ablations."""
+    K = num_cls
+    y = torch.eye(K, dtype=logit.dtype)[target.view(-1)]
+    soft = cfg.get("soft_label", 0.0)
+    ones = y == 1
+    y = torch.where(ones, torch.full_like(y, 1 - soft), torch.full_like(y, soft / (K - 1)))   # :149-150
+    ev = cfg["evidence"]
+    e = F.relu(logit) if ev == "relu" else torch.exp(torch.clamp(logit, -10, 10)) if ev == "exp" else F.softplus(logit)
+    alpha = e + 1
+    S = alpha.sum(1, keepdim=True)
+    red = (lambda v: v.mean()) if size_average else (lambda v: v.sum())
+    if cfg["loss_type"] == "mse":                                       # :193-209, 280-284: err + var, both 'loss' keys
+        err = ((y - alpha / S) ** 2).sum(1, keepdim=True)
+        var = (alpha * (S - alpha) / (S * S * (S + 1))).sum(1, keepdim=True)
+        return red(err) + red(var)
+    func = torch.log if cfg["loss_type"] == "log" else torch.digamma
+    base = y * (func(S) - func(alpha))
+    num_bins = cfg.get("num_bins", 50)
+    momentum = cfg.get("momentum", 0.99 if cfg.get("with_ibm") else 0.0)
+    if cfg.get("with_focal", False):
+        a_cls = torch.ones(K) * (1 - cfg["alpha"])
+        a_cls[0] = cfg["alpha"]
+        pred = (alpha / S).max(1).values                                # NOT detached in the reference (:224-226)
+        w = a_cls[target.view(-1)] * (1.0 - pred) ** cfg["gamma"]
+        per = (base * w.unsqueeze(-1)).sum(1)
+    elif cfg.get("with_ghm", False) and state.epoch >= cfg.get("ghm_start", 0):
+        a = alpha.detach()
+        u = K / a.sum(-1, keepdim=True)
+        g = (1 / a - u).abs() * y
+        edges = [float(x) / num_bins for x in range(num_bins + 1)]
+        edges[-1] += 1e-6
+        weights = torch.zeros_like(alpha)
+        n = 0
+        for i in range(num_bins):
+            inds = (g >= edges[i]) & (g < edges[i + 1])
+            cnt = int(inds.sum())
+            if cnt > 0:
+                if momentum > 0:
+                    state.acc_sum[i] = momentum * state.acc_sum[i] + (1 - momentum) * cnt
+                    weights[inds] = 1.0 / state.acc_sum[i]
+                else:
+                    weights[inds] = 1.0 / cnt
+                n += 1
+        if n > 0:
+            weights = weights / n
+        per = (base * weights).sum(1)
+    elif cfg.get("with_ibloss", False) and state.epoch >= cfg.get("ib_start", 10):
+        a = alpha.detach()
+        u = K / a.sum(-1, keepdim=True)
+        g = ((1 / a - u).abs() * y).sum(1)
+        per = base.sum(1) / (g * logit.detach().abs().sum(1))
+    elif cfg.get("with_ibm", False) and state.epoch >= cfg.get("ibm_start", 0):
+        a = alpha.detach()
+        u = K / a.sum(-1, keepdim=True)
+        g = ((1 / a - u).abs() * y).sum(1)
+        ghat = g * logit.detach().abs().sum(1)
+        bins = torch.ceil(g * num_bins).long()
+        for i in range(num_bins):
+            sel = bins == i + 1
+            if sel.any():
+                state.weight_accum[i] = momentum * state.weight_accum[i] + (1 - momentum) * ghat[sel].mean()
+        per = state.weight_accum[bins - 1] * base.sum(1)
+    else:
+        per = base.sum(1)
+    return red(per)
+
+
+EDL_VARIANTS = {
+    # name: (edl_config, epochs the two calls run at)            -- branches of cls_loss.py:212-278
+    "plain_log_exp": (dict(loss_type="log", evidence="exp"), (1, 2)),
+    "digamma_softplus": (dict(loss_type="digamma", evidence="softplus"), (1, 2)),
+    "mse_relu": (dict(loss_type="mse", evidence="relu"), (1, 2)),
+    "soft_label": (dict(loss_type="log", evidence="exp", soft_label=0.1), (1, 2)),
+    "focal": (dict(loss_type="log", evidence="exp", with_focal=True, alpha=0.25, gamma=2.0), (1, 2)),
+    "ghm_momentum": (dict(loss_type="log", evidence="exp", with_ghm=True, num_bins=30, momentum=0.75, ghm_start=2), (1, 2, 3)),
+    "ghm_plain": (dict(loss_type="log", evidence="exp", with_ghm=True, num_bins=10, momentum=0.0), (1, 2)),
+    "ibloss": (dict(loss_type="log", evidence="exp", with_ibloss=True, ib_start=2), (1, 2)),
+    "ibm": (dict(loss_type="log", evidence="exp", with_ibm=True, ibm_start=0, momentum=0.9, num_bins=50), (1, 2)),
+    "ibm_digamma_mean": (dict(loss_type="digamma", evidence="exp", with_ibm=True, ibm_start=0), (1, 2)),
+}
+
+
+def edl_inputs(name: str, call: int, K: int = 15, M: int = 96):
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) + call)
+    return 2.5 * torch.randn(M, K, generator=g), torch.randint(0, K, (M,), generator=g)
+
+
+def fake_head_outputs(B: int, seed: int, K: int = 15, P: int = 126, loc_scale: float = 30.0) -> dict:
+    """Seeded stand-in for the head outputs (loss-only fixtures)."""
+    g = torch.Generator().manual_seed(seed)
+    return dict(loc=(torch.rand(B, P, 2, generator=g) * loc_scale + 1), conf=2 * torch.randn(B, P, K, generator=g),
+                prop_loc=0.3 * torch.randn(B, P, 2, generator=g), prop_conf=2 * torch.randn(B, P, K, generator=g),
+                center=torch.randn(B, P, 1, generator=g), act=torch.randn(B, P, 1, generator=g),
+                prop_act=torch.randn(B, P, 1, generator=g))
+
+
 def iou_calibration(logit, ious, cfg: OracleConfig):
     """EvidenceLoss.iou_calib (mean): cls_loss.py:120-129."""
     ious = torch.where(ious < 0, torch.full_like(ious, 1e-3), ious)

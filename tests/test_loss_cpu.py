@@ -1,6 +1,7 @@
 """CPU: the product's fixed-shape, sync-free MultiSegmentLoss (opental_b200/multisegment_loss.py; plain torch ops, so it
 runs on CPU tensors too) against the oracle restatement of the reference loss, which itself is pinned to the
 reference-generated golden values (tests/test_oracle_golden.py).  Tolerance 1e-5 relative: only summation order differs."""
+import os
 import math
 
 import pytest
@@ -135,3 +136,75 @@ def test_anet_loss_matches_oracle(B, epoch):
     for k, a, b in zip(gk, g_got, g_ref):
         b = torch.zeros_like(a) if b is None else b
         assert torch.allclose(a, b, atol=2e-6, rtol=2e-4), (k, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("name", ["plain_log_exp", "digamma_softplus", "mse_relu", "soft_label", "focal", "ghm_momentum", "ghm_plain",
+                                  "ibloss", "ibm", "ibm_digamma_mean"])
+def test_evidence_loss_branches_match_reference_golden(name, golden_dir):
+    """Every EvidenceLoss branch (cls_loss.py:212-285): the masked / sync-free formulation of the product,
+    fed the real rows interleaved with padding rows, and the oracle's gather formulation, both against values the
+    reference produced (oracle/make_golden.py --edl).  Called repeatedly so the GHM / IBM state evolves."""
+    import numpy as np
+    from opental_b200.multisegment_loss import EvidenceLoss
+    variants, inputs = O.EDL_VARIANTS, O.edl_inputs
+    cfg, epochs = variants[name]
+    gold = np.load(os.path.join(golden_dir, "edl_variants.npz"))
+    K = 15
+    size_average = name.endswith("_mean")
+    crit = EvidenceLoss(K, dict(cfg), size_average=size_average)
+    st = O.EdlVariantState(cfg.get("num_bins", 50))
+    for call, epoch in enumerate(epochs):
+        logit, target = inputs(name, call, K)
+        want, want_g = float(gold[f"{name}.{call}.loss"]), torch.from_numpy(gold[f"{name}.{call}.grad"])
+        # oracle
+        st.epoch = epoch
+        lo = logit.clone().requires_grad_(True)
+        loss_o = O.evidence_loss_variant(lo, target, st, K, cfg, size_average=size_average)
+        loss_o.backward()
+        assert abs(float(loss_o) - want) <= 2e-5 * max(1.0, abs(want))
+        assert float((lo.grad - want_g).abs().max()) <= 2e-5 * float(want_g.abs().max())
+        # product: real rows at even positions, junk rows (masked out) at odd positions
+        M = logit.shape[0]
+        padded = torch.zeros(2 * M, K)
+        padded[0::2] = logit
+        padded[1::2] = 7.0 * torch.randn(M, K, generator=torch.Generator().manual_seed(call))
+        tgt = torch.full((2 * M,), -1, dtype=torch.long)     # as MultiSegmentLoss passes them: conf_t - 1 = -1 on padding
+        tgt[0::2] = target
+        mask = torch.zeros(2 * M, dtype=torch.bool)
+        mask[0::2] = True
+        padded.requires_grad_(True)
+        crit.epoch = epoch
+        loss_p = crit(padded, tgt, mask)
+        loss_p.backward()
+        assert abs(float(loss_p) - want) <= 2e-5 * max(1.0, abs(want)), (call, float(loss_p), want)
+        assert float((padded.grad[0::2] - want_g).abs().max()) <= 2e-5 * float(want_g.abs().max())
+        assert float(padded.grad[1::2].abs().max()) == 0.0
+    if cfg.get("with_ibm"):
+        assert torch.allclose(crit.weight_accum, torch.from_numpy(gold[f"{name}.weight_accum"]), atol=1e-6)
+    if cfg.get("with_ghm") and cfg.get("momentum", 0) > 0:
+        assert np.allclose(crit.acc_sum.numpy(), gold[f"{name}.acc_sum"], rtol=1e-12)
+        assert np.allclose(st.acc_sum, gold[f"{name}.acc_sum"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["mse_relu", "focal", "ghm_momentum", "ibloss", "digamma_softplus"])
+def test_multisegment_loss_with_ablation_branches_matches_reference_golden(name, golden_dir):
+    """The whole MultiSegmentLoss with an ablation edl_config (masked formulation; the fused kernel declines these)."""
+    import numpy as np
+    gold = np.load(os.path.join(golden_dir, "edl_variants.npz"))
+    cfg, _ = O.EDL_VARIANTS[name]
+    crit = MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=dict(cfg, iou_aware=True), os_head=True,
+                            act_config=dict(weight=0.1, margin=1.0))
+    crit.cls_loss.epoch = 11
+    keys = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
+    for it in range(2):
+        out = {k: v.requires_grad_(True) for k, v in O.fake_head_outputs(3, 5 + it).items()}
+        assert not crit._fused_ok(out["loc"])
+        out["priors"] = torch.cat(O.level_priors(O.OracleConfig()), 0)
+        losses = crit(out, [O.synthetic_targets(i, num_classes=15) for i in range(3)])
+        want = gold[f"{name}.msl.{it}.losses"]
+        for a, b in zip(losses, want):
+            assert abs(float(a) - b) <= 1e-5 * max(1.0, abs(b))
+        grads = torch.autograd.grad(sum(w * l for w, l in zip((1, 10, 1, 10, 1, 1, 1), losses)), [out[k] for k in keys])
+        for k, g in zip(keys, grads):
+            w = torch.from_numpy(gold[f"{name}.msl.{it}.grad.{k}"])
+            assert float((g - w).abs().max()) <= 2e-5 * max(float(w.abs().max()), 1e-6), k
