@@ -196,9 +196,12 @@ OTAL_API int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N,
  * (AFSD/common/thumos_dataset.py:239-275 `__getitem__`: videotransforms RandomCrop / RandomHorizontalFlip :30-124, then
  * `(x / 255.0) * 2.0 - 1.0` :261-263) and `clips.cuda()` (AFSD/thumos14/train.py:165) of a 4x larger fp32 tensor.
  * px: uint8 [N,T,Hs,Ws,3] frames (AFSD/common/video2npy.py:61-74); crop: device int32 [N,3] = (row offset, column offset,
- * mirror flag) per sample, or NULL for the centre crop without mirroring.  Normalisation is bit-identical to torch's. */
-OTAL_API int otal_clip_ingest_u8(const unsigned char* px, const int* crop, uint16_t* hi, uint16_t* lo, int N, int T, int Hs, int Ws,
-                                 int H, int W, void* stream);
+ * mirror flag) per sample, or NULL for the centre crop without mirroring.  Normalisation is bit-identical to torch's.
+ * frame_map: device int32 [N,T] or NULL (identity): output frame t is source frame frame_map[n*T+t] (clamped to [0,T)).
+ * This is the cut-paste augmentation of the SSL pass (`THUMOS_Dataset.augment_`, thumos_dataset.py:187-229: two temporal
+ * slice copies on a clone of the fp32 clip = a re-ordering of the clip's own frames), applied while the frames are read. */
+OTAL_API int otal_clip_ingest_u8(const unsigned char* px, const int* crop, const int* frame_map, uint16_t* hi, uint16_t* lo, int N,
+                                 int T, int Hs, int Ws, int H, int W, void* stream);
 
 /* Backward of relu(conv*scale+shift) w.r.t. the conv output, fused with the hi/lo split the tensor-core kernels read:
  * d = g * [y > 0] * scale[c]   (torch relu backward + frozen BatchNorm3d, AFSD/thumos14/BDNet.py:39-49).

@@ -93,7 +93,7 @@ SIGNATURES = {
     "otal_clip_ingest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_maxpool_bwd_relu_bn_split": (c_int, [POINTER(PoolDesc), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                c_void_p]),
-    "otal_clip_ingest_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_clip_ingest_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_relu_bn_bwd_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,

@@ -125,6 +125,7 @@ class I3DBackbone(nn.Module):
         self.on_backward_start = None     # optional callback (the trainer overlaps the head's all-reduce here)
         self.crop_size = 96               # uint8 input path: crop extent (config dataset.training.crop_size)
         self.crop_offsets = None          # optional int32 [N,3] device tensor (row, column, mirror) per sample
+        self.frame_map = None             # optional int32 [N,T] device tensor: temporal gather in the ingest kernel (SSL cut-paste)
         self.reset_parameters()
 
     # ------------------------------------------------------------------------------------------------ structure
@@ -277,7 +278,7 @@ class I3DBackbone(nn.Module):
             # the dataset's storage format: uint8 frames [N,T,Hs,Ws,3]; centre crop + normalisation happen in the ingest kernel
             assert x.is_cuda and x.dim() == 5 and x.shape[4] == 3, "expected CUDA uint8 frames [N,T,Hs,Ws,3]"
             W = self.crop_size
-            a = ops.clip_ingest_u8(x, W, self.crop_offsets, with_lo)
+            a = ops.clip_ingest_u8(x, W, self.crop_offsets, with_lo, frame_map=self.frame_map)
         else:
             assert x.is_cuda and x.dim() == 5 and x.shape[1] == 3, "expected a CUDA clip batch [N,3,T,H,W]"
             W = x.shape[4]

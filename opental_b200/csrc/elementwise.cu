@@ -183,7 +183,10 @@ static inline int grid_for(long long work_items, int threads) {
 // (AFSD/common/video2npy.py:61-74), cropped to H x W at a per-sample offset, optionally mirrored along W, normalised as
 // (x / 255) * 2 - 1 (AFSD/common/thumos_dataset.py:261-263; _rn intrinsics in torch's operation order: bit-identical).
 // Replaces the CPU crop / flip / normalise of the data loader (videotransforms.py:30-124) and a 4x larger H2D copy.
-__global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, const int* __restrict__ crop, uint16_t* __restrict__ hi,
+// frame_map (optional, [N,T]): output frame t reads source frame frame_map[n*T+t] — the SSL cut-paste augmentation
+// (thumos_dataset.py:187-229) is a re-ordering of the clip's own frames, so the augmented clip is never materialised.
+__global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, const int* __restrict__ crop,
+                                      const int* __restrict__ frame_map, uint16_t* __restrict__ hi,
                                       uint16_t* __restrict__ lo, int N, int T, int Hs, int Ws, int H, int W, int oh_def, int ow_def) {
     const int Wp = W + 8;
     const long long total = (long long)N * T * H * Wp;
@@ -199,7 +202,8 @@ __global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, cons
         if (w >= 0 && w < W) {
             const int oh = crop ? crop[3 * n] : oh_def, ow = crop ? crop[3 * n + 1] : ow_def, flip = crop ? crop[3 * n + 2] : 0;
             const int ws = ow + (flip ? W - 1 - w : w);
-            const unsigned char* src = px + ((((size_t)n * T + t) * Hs + (oh + h)) * Ws + ws) * 3;
+            const int ts = frame_map ? min(max(frame_map[n * T + t], 0), T - 1) : t;
+            const unsigned char* src = px + ((((size_t)n * T + ts) * Hs + (oh + h)) * Ws + ws) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)src[c], 255.f), 2.f), 1.f);
@@ -305,14 +309,14 @@ int otal_ncl_to_nlc_split(const float* x, uint16_t* hi, uint16_t* lo, int B, int
 
 }  // extern "C"
 
-extern "C" int otal_clip_ingest_u8(const unsigned char* px, const int* crop, uint16_t* hi, uint16_t* lo, int N, int T, int Hs,
-                                   int Ws, int H, int W, void* stream) {
+extern "C" int otal_clip_ingest_u8(const unsigned char* px, const int* crop, const int* frame_map, uint16_t* hi, uint16_t* lo,
+                                   int N, int T, int Hs, int Ws, int H, int W, void* stream) {
     if (N < 0 || T <= 0 || Hs <= 0 || Ws <= 0 || H <= 0 || W <= 0 || (W & 1) || H > Hs || W > Ws || !px || !hi) {
         otal::set_last_error_msg("clip_ingest_u8: bad argument (W even, crop inside the frame)"); return OTAL_ERR_BAD_ARG;
     }
     if (N == 0) return OTAL_OK;
     otal::clip_ingest_u8_kernel<<<otal::grid_for((long long)N * T * H * (W + 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        px, crop, hi, lo, N, T, Hs, Ws, H, W, (Hs - H) / 2, (Ws - W) / 2);
+        px, crop, frame_map, hi, lo, N, T, Hs, Ws, H, W, (Hs - H) / 2, (Ws - W) / 2);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

@@ -159,7 +159,8 @@ class Trainer:
         weights = (1.0, 0.1, 0.1)
         return torch.stack([F.triplet_margin_loss(anchor[i], positive[i], negative[i]) * weights[i] for i in range(3)]).sum(0)
 
-    def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None):
+    def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None,
+                         ssl_frame_map=None):
         out = self.net(clips)
         anet = getattr(self.net, "variant", "thumos") == "anet"
         if anet:      # the ActivityNet loss takes the list form (anet/train.py:168-172)
@@ -169,10 +170,19 @@ class Trainer:
             losses = self.criterion(out, targets)
         cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw,
                                      score_scale=8 if anet else 4)
-        if ssl_clips is not None:
+        if ssl_clips is not None or ssl_frame_map is not None:
             # second forward on the cut-paste augmented clip + triplet loss on its boundary features
-            # (thumos14/train.py:237-242; BDNet.py:482-503); one backward for the sum
-            a, p, n = self.net(ssl_clips, proposals=ssl_targets, ssl=True)
+            # (thumos14/train.py:237-242; BDNet.py:482-503); one backward for the sum.  With `ssl_frame_map` the augmented
+            # clip is not materialised: the ingest kernel re-reads the uint8 frames of `clips` through the map
+            # (opental_b200/augment.py).
+            bb = self.net.backbone
+            if ssl_frame_map is not None:
+                assert ssl_clips is None and clips.dtype == torch.uint8, "ssl_frame_map re-reads the uint8 frames of `clips`"
+                bb.frame_map, ssl_clips = ssl_frame_map, clips
+            try:
+                a, p, n = self.net(ssl_clips, proposals=ssl_targets, ssl=True)
+            finally:
+                bb.frame_map = None
             cost = cost + self.ssl_weight * self.triplet_loss(a, p, n)
         cost.backward()
         # detached: a caller holding a non-detached loss would keep this step's autograd graph (and its AccumulateGrad
@@ -180,7 +190,22 @@ class Trainer:
         return cost.detach(), tuple(l.detach() if l is not None else None for l in losses), ls.detach(), le.detach()
 
     # ---------------------------------------------------------------------------------------------- CUDA graph
-    def capture(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None) -> None:
+    @staticmethod
+    def _ssl_sources(ssl_clips, ssl_targets, ssl_frame_map) -> list:
+        if ssl_clips is None and ssl_frame_map is None:
+            return []
+        tg = torch.stack(list(ssl_targets)) if isinstance(ssl_targets, (list, tuple)) else ssl_targets
+        return [ssl_clips if ssl_clips is not None else ssl_frame_map, tg]
+
+    def _ssl_args(self, ssl_clips, ssl_frame_map) -> tuple:
+        """(ssl_clips, ssl_targets, ssl_frame_map) over the static buffers."""
+        if len(self._static) == 4:
+            return None, None, None
+        src, tg = self._static[4], list(self._static[5].unbind(0))
+        return (src, tg, None) if ssl_clips is not None else (None, tg, src)
+
+    def capture(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None,
+                ssl_frame_map=None) -> None:
         """Capture zero_grad + forward + loss + backward for this input geometry into ONE CUDA graph.  The head and the
         loss are ~2500 small launches whose host-side enqueue cost (~75 ms per step at batch 8) exceeds the GPU work; a
         graph replay removes it.  Inputs are copied into static buffers before every replay; the gradient all-reduce and
@@ -189,14 +214,12 @@ class Trainer:
         import gc
         gc.collect()                                 # drop dead autograd graphs of earlier eager steps (see forward_backward)
         tgt, valid = pad_targets(targets, clips.device)
-        srcs = [clips, tgt, valid, scores]
-        if ssl_clips is not None:
-            srcs += [ssl_clips, torch.stack(list(ssl_targets)) if isinstance(ssl_targets, (list, tuple)) else ssl_targets]
+        srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
         self._static = [torch.empty_like(t) for t in srcs]
         for d, s in zip(self._static, srcs):
             d.copy_(s)
         c, t, v, sc = self._static[:4]
-        ssl_args = (self._static[4], list(self._static[5].unbind(0))) if ssl_clips is not None else (None, None)
+        ssl_args = self._ssl_args(ssl_clips, ssl_frame_map)
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())
         self._capturing = True
@@ -220,16 +243,15 @@ class Trainer:
         c = self.criterion.cls_loss
         return bool(getattr(c, "with_ibm", False) and c.epoch >= getattr(c, "ibm_start", 0))
 
-    def step(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None):
+    def step(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None, ssl_frame_map=None):
         """clips [B,3,T,H,W] fp32 (or uint8 frames [B,T,Hs,Ws,3]) on the device, targets: list of [N_i,3] or padded
         (tensor, mask), scores [B,2,T].  ssl_clips / ssl_targets: the cut-paste augmented clip and its [3,2] (anchor,
-        positive, negative) segments for the triplet pass (thumos14/train.py:237-242), or None."""
+        positive, negative) segments for the triplet pass (thumos14/train.py:237-242), or None.  ssl_frame_map (int32
+        [B,T], from opental_b200.augment.cut_paste) replaces ssl_clips when `clips` are uint8 frames."""
         if self._graph is not None:
             tgt, valid = pad_targets(targets, clips.device)
-            srcs = [clips, tgt, valid, scores]
-            if ssl_clips is not None:
-                srcs += [ssl_clips, torch.stack(list(ssl_targets)) if isinstance(ssl_targets, (list, tuple)) else ssl_targets]
-            if (len(srcs) != len(self._static) or any(tuple(a.shape) != tuple(b.shape) for a, b in zip(srcs, self._static))
+            srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
+            if (len(srcs) != len(self._static) or any(tuple(a.shape) != tuple(b.shape) or a.dtype != b.dtype for a, b in zip(srcs, self._static))
                     or self._ibm_flag() != self._graph_epoch_flag):
                 raise RuntimeError("captured training graph does not match this batch geometry / epoch: call capture() again")
             for d, s in zip(self._static, srcs):
@@ -239,7 +261,7 @@ class Trainer:
             cost, losses, ls, le = self._graph_out
         else:
             self.zero_grad()
-            cost, losses, ls, le = self.forward_backward(clips, targets, scores, ssl_clips, ssl_targets)
+            cost, losses, ls, le = self.forward_backward(clips, targets, scores, ssl_clips, ssl_targets, ssl_frame_map)
         if self.world > 1:
             if not self._head_launched:
                 self._launch_head_allreduce()

@@ -328,17 +328,22 @@ def clip_ingest(x: torch.Tensor, with_lo: bool = True) -> Planes:
     return Planes(hi, lo)
 
 
-def clip_ingest_u8(px: torch.Tensor, crop: int = 96, offsets: torch.Tensor | None = None, with_lo: bool = True) -> Planes:
+def clip_ingest_u8(px: torch.Tensor, crop: int = 96, offsets: torch.Tensor | None = None, with_lo: bool = True,
+                   frame_map: torch.Tensor | None = None) -> Planes:
     """uint8 frames [N,T,Hs,Ws,3] -> W-padded planes [N,T,crop,crop+8,4] of the normalised crop ((x/255)*2-1, bit-identical).
-    offsets: optional int32 device tensor [N,3] = (row offset, column offset, mirror flag); default centre crop."""
+    offsets: optional int32 device tensor [N,3] = (row offset, column offset, mirror flag); default centre crop.
+    frame_map: optional int32 device tensor [N,T], output frame t <- source frame frame_map[n,t] (SSL cut-paste)."""
     _require_cuda(px)
     assert px.dtype == torch.uint8 and px.dim() == 5 and px.shape[-1] == 3 and px.is_contiguous()
     N, T, Hs, Ws, _ = px.shape
     if offsets is not None:
         assert offsets.dtype == torch.int32 and offsets.is_cuda and tuple(offsets.shape) == (N, 3) and offsets.is_contiguous()
+    if frame_map is not None:
+        assert frame_map.dtype == torch.int32 and frame_map.is_cuda and tuple(frame_map.shape) == (N, T) and frame_map.is_contiguous()
     hi = torch.empty((N, T, crop, crop + CLIP_WPAD, CLIP_CPAD), dtype=torch.bfloat16, device=px.device)
     lo = torch.empty_like(hi) if with_lo else None
-    _lib.call("otal_clip_ingest_u8", px.data_ptr(), _ptr(offsets), hi.data_ptr(), _ptr(lo), N, T, Hs, Ws, crop, crop, _stream())
+    _lib.call("otal_clip_ingest_u8", px.data_ptr(), _ptr(offsets), _ptr(frame_map), hi.data_ptr(), _ptr(lo), N, T, Hs, Ws, crop,
+              crop, _stream())
     return Planes(hi, lo)
 
 

@@ -349,6 +349,51 @@ def edl_cases():
     ns.restore_cuda()
 
 
+def augment_case_inputs(seed: int):
+    """Seeded annotation sets (frames) + threshold for the cut-paste fixtures."""
+    import random
+    r = random.Random(1000 + seed)
+    n = r.choice([1, 2, 2, 3])
+    cuts = sorted(r.sample(range(2, 254), 2 * n))
+    annos = [[cuts[2 * i], cuts[2 * i + 1], r.randint(1, 15)] for i in range(n)]
+    if seed % 5 == 0:
+        annos = [[a[0] + 0.5, a[1] + 0.25, a[2]] for a in annos]       # fractional boundaries (ceil / floor paths)
+    return annos, r.choice([3, 5, 8, 13, 21])
+
+
+def augment_cases():
+    """SSL cut-paste augmentation (thumos_dataset.py:172-237): the reference's own method run on a clip whose pixel value
+    is its frame index, so the augmented clip IS the frame map; same `random` seed on both sides."""
+    import importlib
+    import random
+    import types
+    ns = ref_loader.load_reference()
+    ds = importlib.import_module("AFSD.common.thumos_dataset")
+    from opental_b200 import augment as A
+    dummy = types.SimpleNamespace(clip_length=256)
+    dummy.get_bg = types.MethodType(ds.THUMOS_Dataset.get_bg, dummy)
+    dummy.augment_ = types.MethodType(ds.THUMOS_Dataset.augment_, dummy)
+    cases, n_ok = [], 0
+    clip = torch.arange(256, dtype=torch.float32).view(1, 256, 1, 1).expand(3, 256, 2, 2).contiguous()
+    for seed in range(60):
+        annos, th = augment_case_inputs(seed)
+        random.seed(seed)
+        new_input, new_annos, flag = ds.THUMOS_Dataset.augment(dummy, clip, [list(a) for a in annos], th, 1)
+        ref_map = new_input[0, :, 0, 0].long().tolist()
+        assert torch.equal(new_input, clip[:, ref_map])                 # it is a pure frame re-ordering
+        random.seed(seed)
+        fmap, got_annos, got_flag = A.cut_paste([list(a) for a in annos], th, 256, 1)
+        assert got_flag == flag and fmap.tolist() == ref_map, seed
+        assert [list(map(float, a)) for a in got_annos] == [list(map(float, a)) for a in new_annos], seed
+        n_ok += bool(flag)
+        cases.append(dict(seed=seed, annos=annos, th=th, flag=bool(flag), frame_map=ref_map,
+                          new_annos=[list(map(float, a)) for a in new_annos]))
+    print(f"[augment] 60 seeds ({n_ok} augmented): frame map == the reference's augmented clip")
+    with open(os.path.join(GOLD, "augment_cases.json"), "w") as fh:
+        json.dump(cases, fh)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -360,6 +405,9 @@ if __name__ == "__main__":
         infer_cases()
     elif "--edl" in sys.argv:
         edl_cases()
+    elif "--augment" in sys.argv:
+        sys.path.insert(0, ROOT)
+        augment_cases()
     else:
         bmp_cases()
         model_cases()

@@ -1,6 +1,7 @@
 """GPU parity of the backbone training kernels (through the C ABI) vs the CPU oracle's Unit3D / MaxPool3dSamePadding
 and torch autograd of the same fp32 ops: strided conv, folded Conv3d_1a, dgrad, wgrad, max-pool fwd/bwd, ReLU/BN
 backward split, fused Adam.  Tolerance 1e-4 relative (max-norm) in bf16x3 mode — inside BASELINE's 1e-3 budget."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -333,6 +334,30 @@ def test_clip_ingest_u8_bit_exact():
     ref = ops.clip_ingest(torch.stack([loader(px[n], int(offs[n, 0]), int(offs[n, 1]), bool(offs[n, 2])) for n in range(N)]).cuda())
     got = ops.clip_ingest_u8(px.cuda(), crop, offs.cuda())
     assert torch.equal(got.hi, ref.hi) and torch.equal(got.lo, ref.lo)
+
+
+def test_clip_ingest_u8_frame_map_is_a_temporal_gather():
+    """SSL cut-paste (thumos_dataset.py:187-229) as a frame map in the ingest kernel == the same ingest followed by an
+    index_select along time; together with crop offsets / mirroring; bit-exact."""
+    import random
+    from opental_b200 import augment, ops
+    g = torch.Generator().manual_seed(32)
+    N, T, Hs, Ws, crop = 3, 256, 20, 22, 16
+    px = torch.randint(0, 256, (N, T, Hs, Ws, 3), generator=g, dtype=torch.uint8).cuda()
+    offs = torch.tensor([[0, 0, 0], [4, 6, 1], [2, 3, 1]], dtype=torch.int32).cuda()
+    annos = [[[30, 120, 3], [170, 230, 7]], [[10, 20, 1]], [[60.5, 140.25, 2]]]
+    maps = [augment.cut_paste(a, 8, T, 1, rng=random.Random(i))[0] for i, a in enumerate(annos)]
+    assert (maps[1] == np.arange(T)).all() and (maps[0] != np.arange(T)).any() and (maps[2] != np.arange(T)).any()
+    fmap = torch.from_numpy(np.stack(maps)).cuda()
+    plain = ops.clip_ingest_u8(px, crop, offs)
+    got = ops.clip_ingest_u8(px, crop, offs, frame_map=fmap)
+    idx = fmap.long().view(N, T, 1, 1, 1).expand_as(plain.hi)
+    assert torch.equal(got.hi, plain.hi.gather(1, idx)) and torch.equal(got.lo, plain.lo.gather(1, idx))
+    # out-of-range entries are clamped (memory safety), never read outside the clip
+    bad = fmap.clone()
+    bad[0, 0], bad[0, 1] = -5, T + 7
+    got = ops.clip_ingest_u8(px, crop, offs, frame_map=bad)
+    assert torch.equal(got.hi[0, 0], plain.hi[0, 0]) and torch.equal(got.hi[0, 1], plain.hi[0, T - 1])
 
 
 def test_backbone_accepts_uint8_frames():

@@ -183,3 +183,30 @@ def test_trainer_step_with_ssl_pass():
     c0, *_ = tr.step(x, tgt, sc)
     c1, *_ = tr.step(x, tgt, sc, ssl_clips=xs, ssl_targets=prop)
     assert math.isfinite(float(c0)) and math.isfinite(float(c1)) and float(c1) != float(c0)
+
+
+def test_ssl_pass_through_frame_map_equals_materialised_clip():
+    """Trainer.step(..., ssl_frame_map=...) re-reads the uint8 frames through the cut-paste map inside the ingest kernel;
+    it must give the loss of the reference's data flow (augmented fp32 clip built on the host, thumos_dataset.py:264)."""
+    import random
+    from opental_b200 import augment, engine
+    px = engine.synthetic_clip_u8(0).unsqueeze(0)                                  # uint8 [1,256,112,112,3]
+    tgt = [engine.synthetic_targets(0).cuda()]
+    sc = engine.synthetic_scores(tgt[0].cpu()).unsqueeze(0).cuda()
+    annos = [[float(s) * 256, float(e) * 256, int(l)] for s, e, l in tgt[0].cpu().tolist()]
+    fmap, ssl_annos, flag = augment.cut_paste(annos, 8, 256, 1, rng=random.Random(3))
+    assert flag
+    prop = [torch.tensor(ssl_annos, dtype=torch.float32).cuda()]
+    costs = []
+    for mode in ("map", "materialised"):
+        net, crit = build(math.log(32.0), 11)
+        tr = engine.Trainer(net, crit, ssl_weight=0.001)
+        if mode == "map":
+            c, *_ = tr.step(px.cuda(), tgt, sc, ssl_targets=prop, ssl_frame_map=torch.from_numpy(fmap).unsqueeze(0).cuda())
+        else:
+            x = engine.normalise_clip(px[0]).unsqueeze(0)                          # centre crop + (x/255)*2-1, fp32 [1,3,256,96,96]
+            xs = x[:, :, torch.from_numpy(fmap).long()]                            # the reference's augmented clip
+            c, *_ = tr.step(x.cuda(), tgt, sc, ssl_clips=xs.cuda(), ssl_targets=prop)
+        costs.append(float(c))
+        assert net.backbone.frame_map is None                                      # reset after the SSL pass
+    assert abs(costs[0] - costs[1]) <= 1e-6 * abs(costs[1])      # identical planes in, deterministic forward
