@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ssl", action="store_true", help="add the self-supervised second pass (cut-paste clip through the frame map + "
+                    "triplet loss, train.py:237-242) to every step; the headline number is quoted without it (SURVEY §8d)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch from the host instead of replaying the captured step")
     return ap.parse_args()
 
@@ -182,14 +184,33 @@ def run_native(args):
         sc = torch.stack([engine.synthetic_scores(t) for t in tg])
         from opental_b200.multisegment_loss import pad_targets
         tp, tv = pad_targets(tg, device="cpu")
-        return clips.pin_memory(), tp.pin_memory(), tv.pin_memory(), sc.pin_memory()
+        out = [clips.pin_memory(), tp.pin_memory(), tv.pin_memory(), sc.pin_memory()]
+        if args.ssl:
+            # cut-paste plan per clip (thumos_dataset.py:187-237); th = 8 frames; re-draw until the attempt succeeds
+            import random
+            from opental_b200 import augment
+            maps, ssl_tg = [], []
+            for i, t in zip(idx, tg):
+                annos = [[float(a) * 256, float(b) * 256, int(c)] for a, b, c in t.tolist()]
+                rng, flag = random.Random(i), False
+                while not flag:
+                    fmap, new_annos, flag = augment.cut_paste(annos, 8, 256, 1, rng=rng)
+                maps.append(torch.from_numpy(fmap))
+                ssl_tg.append(torch.tensor(new_annos, dtype=torch.float32))
+            out += [torch.stack(maps).pin_memory(), torch.stack(ssl_tg).pin_memory()]
+        return tuple(out)
 
     host = [make_batch(j) for j in range(2)]
     devb = [tuple(t.to(dev) for t in hb) for hb in host]
 
-    def step_dev(j):
-        c, tp, tv, sc = devb[j % 2]
+    def run_step(batch):
+        c, tp, tv, sc = batch[:4]
+        if args.ssl:
+            return tr.step(c, (tp, tv), sc, ssl_targets=list(batch[5].unbind(0)), ssl_frame_map=batch[4])
         return tr.step(c, (tp, tv), sc)
+
+    def step_dev(j):
+        return run_step(devb[j % 2])
 
     def barrier():
         if world > 1:
@@ -199,7 +220,8 @@ def run_native(args):
     launches_per_graph = 0
     if not args.no_graph:
         n0 = _lib.launch_count()
-        tr.capture(devb[0][0], (devb[0][1], devb[0][2]), devb[0][3])
+        ssl_kw = dict(ssl_targets=list(devb[0][5].unbind(0)), ssl_frame_map=devb[0][4]) if args.ssl else {}
+        tr.capture(devb[0][0], (devb[0][1], devb[0][2]), devb[0][3], **ssl_kw)
         launches_per_graph = (_lib.launch_count() - n0) // 3          # capture() runs the step 3x (2 warm-ups + the capture)
     for j in range(args.warmup):
         step_dev(j)
@@ -248,8 +270,7 @@ def run_native(args):
             if j + 1 < args.steps:
                 prefetch(j + 1)
             torch.cuda.current_stream().wait_event(ready[j % 2])
-            c, tp, tv, sc = bufs[j % 2]
-            cost, losses, ls, le = tr.step(c, (tp, tv), sc)
+            cost, losses, ls, le = run_step(bufs[j % 2])
             consumed[j % 2].record()
             _ = float(cost)                                   # device -> host read of the step's result (4 bytes)
         barrier()
@@ -336,7 +357,7 @@ def run_native(args):
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "precision": args.precision,
                    "input": "uint8 frames [B,256,112,112,3], centre crop 96 + normalisation in the ingest kernel",
                    "l2": "per-step activations and gradients (several GB) exceed the 126 MB L2; two alternating input batches",
-                   "ssl_pass": False, "cuda_graph": not args.no_graph},
+                   "ssl_pass": bool(args.ssl), "cuda_graph": not args.no_graph},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
