@@ -27,6 +27,7 @@
 //              clips partial tiles.  Optionally also writes fp32 with plain stores.
 #include "common.cuh"
 #include "tensormap.h"
+#include <stdlib.h>
 
 namespace otal {
 
@@ -59,6 +60,10 @@ struct ConvParams {
     int b_mn;        // dgrad mode: weights are read as [tap][K][N] (N contiguous, "MN-major" B) and taps are flipped
     int kchunks2;    // second K segment (1x1 convs only): extra 64-channel chunks read through the A2 / B2 maps, i.e.
                      // D = [x | x2] . [w ; w2] — the data gradients of several 1x1 convs that share their input, in ONE pass
+    int ncat;        // bf16x3 with BN <= 128: B_lo sits right behind B_hi in shared memory, so ONE MMA of N = 2*BN computes
+                     // a_hi*[b_hi | b_lo] into columns [0,BN) and [BN,2BN) and a second one adds a_lo*b_hi to [0,BN): the A
+                     // tile is read from shared memory twice instead of three times per K step (these shapes are bound by the
+                     // 128 B/clk shared-memory operand bandwidth, not by the tensor pipe); the epilogue adds the two halves
     int k32;         // K chunk of 32 elements = 64-byte rows, SWIZZLE_64B operands (the folded Conv3d_1a: 8 W taps x 4 channels)
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
@@ -101,6 +106,7 @@ __device__ __forceinline__ void split_parity(int d, int s, int& q, int& par) {
     else { par = d & 1; q = (d - par) >> 1; }
 }
 
+template <bool NCAT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     const CUtensorMap& mapB_hi = maps.B_hi; const CUtensorMap& mapB_lo = maps.B_lo;
@@ -228,6 +234,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop)
         const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, 0, p.b_mn ? 1 : 0);
+        const uint32_t idesc_cat = umma_idesc_bf16(kTileM, 2 * p.BN, 0, p.b_mn ? 1 : 0);
         // descriptor templates: everything but the start address.  K-major: 32 bytes per K=16 step inside the swizzled
         // row.  MN-major B (dgrad): 16 K rows = 2048 bytes per step, LBO = 8 KB between 64-wide N boxes, SBO = 1 KB.
         // k32: 64-byte rows, SWIZZLE_64B, 8-row groups 512 bytes apart, two K=16 steps per stage.
@@ -256,6 +263,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         if (k >= ksteps) break;
                         const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2);
                         const uint64_t b_hi = b_hi0 + (uint64_t)(k * b_step);
+                        if constexpr (NCAT) {
+                            umma_f16(d_tmem, a_hi, b_hi, idesc_cat, (it | k) != 0);          // [a_hi*b_hi | a_hi*b_lo]
+                            umma_f16(d_tmem, a_lo0 + (uint64_t)(k * 2), b_hi, idesc, 1);       // += a_lo*b_hi
+                            continue;
+                        }
                         umma_f16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
                         if (split) {
                             umma_f16(d_tmem, a_lo0 + (uint64_t)(k * 2), b_hi, idesc, 1);
@@ -317,7 +329,15 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                     if (col0 >= p.BN) break;
                     uint32_t v[32];
                     tmem_ld32(t_acc + col0, v);
-                    tmem_ld_wait();
+                    if constexpr (NCAT) {                 // second half of the accumulator: the a_hi*b_lo products
+                        uint32_t v2[32];
+                        tmem_ld32(t_acc + p.BN + col0, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     const int cbase = nb * p.BN + col0;   // channel inside the slice
                     float f[32];
 #pragma unroll
@@ -448,6 +468,13 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
             p.BN = 64; p.n_blocks = (p.Cout + 63) / 64;
         }
     }
+    {
+        // N-concatenated hi|lo weights (see ConvParams::ncat): needs 2*BN accumulator columns and B_lo contiguous after B_hi
+        static const bool off = getenv("OTAL_NO_NCAT") != nullptr;
+        const uint32_t rowb = p.k32 ? 64u : 128u;
+        p.ncat = (!off && split && 2 * p.BN <= kAccStride && (conv_b_rows(p.BN, p.b_mn) * rowb) % 1024u == 0 &&
+                  (!p.b_mn || p.BN % 64 == 0)) ? 1 : 0;
+    }
     const int chunk = p.k32 ? 32 : kChunkK;
     p.kchunks = (L.w_k + chunk - 1) / chunk;
     p.store_bf16 = L.y_hi != nullptr;
@@ -495,12 +522,13 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     const size_t smem_bytes = SL.total + 1024;
     static bool configured = false;
     if (!configured) {
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024));
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    if (p.ncat) conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    else conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }
