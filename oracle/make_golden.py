@@ -394,6 +394,69 @@ def augment_cases():
     ns.restore_cuda()
 
 
+def closed_cfg():
+    return O.OracleConfig(num_classes=21, os_head=False, use_edl=False, with_ibm=False, iou_aware=False)
+
+
+def config1_clip():
+    """x = (randint(0,256,[1,3,256,96,96], seed 0).float()/255)*2-1."""
+    g = torch.Generator().manual_seed(0)
+    return (torch.randint(0, 256, [1, 3, 256, 96, 96], generator=g).float() / 255) * 2 - 1
+
+
+def closed_cases():
+    """BASELINE configs[0] / SURVEY §8d config 1: `configs/thumos14.yaml` (closed set: 21 classes incl. background, softmax
+    focal loss, no EDL, no actionness heads), `BDNet(in_channels=3, training=False).eval()` forward on the seed-0 clip; plus
+    one training step's losses and gradient fingerprints with MultiSegmentLoss(cls_loss_type='focal')."""
+    ns = ref_loader.load_reference(config="configs/thumos14.yaml", extra_args=())
+    cfg = closed_cfg()
+    x = config1_clip()
+    arrays, summary = {}, {}
+    for tag, shift in (("init", 0.0), ("biased", math.log(32.0))):
+        sd = O.synthetic_state_dict(cfg, loc_bias_shift=shift)
+        net = ns.BDNet(in_channels=3, training=False)
+        net.load_state_dict(sd)
+        net.eval()
+        with torch.no_grad():
+            out_r = net(x)
+            out_o = O.bdnet_forward(x, sd, cfg, compat=True)
+        assert out_r["act"] is None and out_r["prop_act"] is None and "unct" not in out_r
+        errs = {k: rel(out_o[k], out_r[k]) for k in out_r if out_r[k] is not None}
+        assert max(errs.values()) < TOL, errs
+        for k in ("loc", "conf", "prop_loc", "prop_conf", "center"):
+            arrays[f"{tag}.{k}"] = out_r[k].numpy()
+        for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop"):
+            arrays[f"{tag}.{k}.sample"] = out_r[k].numpy()[:, ::8, ::8].copy()
+        # training step with the focal loss
+        net.train()
+        targets = [O.synthetic_targets(0, num_classes=20)]
+        crit = ns.MultiSegmentLoss(21, 0.5, 1.0, use_gpu=False, cls_loss_type="focal")
+        net.zero_grad()
+        out_t = net(x)
+        loss_r = crit(out_t, [t.clone() for t in targets])
+        assert loss_r[5] is None and loss_r[6] is None
+        cost_r = loss_r[0] + 10 * loss_r[1] + loss_r[2] + 10 * loss_r[3] + loss_r[4]
+        cost_r.backward()
+        sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        out_ot = O.bdnet_forward(x, sdo, cfg, compat=True)
+        loss_o = O.multisegment_loss_closed(out_ot, targets, cfg)
+        (loss_o[0] + 10 * loss_o[1] + loss_o[2] + 10 * loss_o[3] + loss_o[4]).backward()
+        lerrs = [abs(float(a) - float(b)) / max(abs(float(b)), 1e-6) for a, b in zip(loss_o, loss_r[:5])]
+        grads_r = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        gerrs = {k: rel(sdo[k].grad, g) for k, g in grads_r.items() if sdo[k].grad is not None}
+        print(f"[closed {tag}] oracle vs reference: outputs {max(errs.values()):.2e} losses {max(lerrs):.2e} grads {max(gerrs.values()):.2e}")
+        assert max(lerrs) < 5e-5 and max(gerrs.values()) < 5e-2
+        fp = {}
+        for k, g in grads_r.items():
+            fp[k] = [float(g.sum()), float(g.abs().sum())]
+            arrays[f"{tag}.grad.{k}"] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy().copy()
+        summary[tag] = dict(losses=[float(v) for v in loss_r[:5]], cost=float(cost_r), grad_fingerprint=fp)
+    np.savez_compressed(os.path.join(GOLD, "model_thumos_closed.npz"), **arrays)
+    with open(os.path.join(GOLD, "model_thumos_closed.json"), "w") as fh:
+        json.dump(summary, fh, indent=1)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -405,6 +468,8 @@ if __name__ == "__main__":
         infer_cases()
     elif "--edl" in sys.argv:
         edl_cases()
+    elif "--closed" in sys.argv:
+        closed_cases()
     elif "--augment" in sys.argv:
         sys.path.insert(0, ROOT)
         augment_cases()

@@ -798,6 +798,40 @@ def multisegment_loss(out, targets, state: LossState, cfg: OracleConfig):
             loss_act / AN, loss_prop_act / PAN)
 
 
+def focal_loss_ori(prob, target, num_class: int, alpha: float = 0.25, gamma: float = 2.0, balance_index: int = 0):
+    """FocalLoss_Ori.forward, size_average=False (cls_loss.py:6-78): `prob` are softmax scores [N,K+1]; class
+    `balance_index` (background) gets weight alpha, every other class 1 - alpha; eps 1e-6 added to p_t."""
+    a = torch.ones(num_class, dtype=prob.dtype) * (1 - alpha)
+    a[balance_index] = alpha
+    pt = prob.gather(1, target.view(-1, 1)).view(-1) + 1e-6
+    return (-1 * torch.pow(1.0 - pt, gamma) * (a[target.view(-1)] * pt.log())).sum()
+
+
+def multisegment_loss_closed(out, targets, cfg: OracleConfig):
+    """MultiSegmentLoss.forward for the closed-set baseline (configs/thumos14.yaml: cls_loss_type='focal', no os_head, K+1
+    classes incl. background): multisegment_loss.py:92-259 with the focal branches (:193-195, :217-218) — every prior
+    contributes to the classification terms, background priors with label 0.  Returns the 5 losses (act terms are None)."""
+    loc, conf, ploc, pconf, center, priors = (out[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))
+    K1 = cfg.num_classes
+    loc_t, conf_t, prop_loc_t, prop_conf_t, _ = match_priors(loc, priors, targets, cfg)
+    pos, ppos = conf_t > 0, prop_conf_t > 0
+    zero = loc.sum() * 0
+    loss_l = seg_giou_loss(loc[pos], loc_t[pos]).sum() if pos.any() else zero
+    loss_prop_l = (ploc[ppos] - prop_loc_t[ppos]).abs().sum() if ppos.any() else zero
+    if pos.any():
+        pre = loc[pos]
+        cur = 0.5 * (pre[:, 0] + pre[:, 1]).unsqueeze(-1) * ploc[pos] + pre
+        q = seg_iou(cur, loc_t[pos])[0].clamp(min=0)
+        loss_ct = F.binary_cross_entropy_with_logits(center[pos].view(-1), q, reduction="sum")
+    else:
+        loss_ct = zero
+    loss_c = focal_loss_ori(F.softmax(conf.view(-1, K1), dim=1), conf_t.view(-1), K1)
+    loss_prop_c = focal_loss_ori(F.softmax(pconf.view(-1, K1), dim=1), prop_conf_t.view(-1), K1)
+    N = max(int(pos.sum()), 1)
+    PN = max(int(ppos.sum()), 1)
+    return loss_l / N, loss_c / N, loss_prop_l / PN, loss_prop_c / PN, loss_ct / N
+
+
 def edl_loss_anet(logit, target, state: LossState, cfg: OracleConfig):
     """EvidenceLoss of the ActivityNet flavour: same log loss, stateless exp-form IBM weight
     1 / (||logit||_1 * exp(coeff * grad_norm) + 1e-10): anet/cls_loss.py:116-152, :225-232."""

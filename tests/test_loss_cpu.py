@@ -208,3 +208,24 @@ def test_multisegment_loss_with_ablation_branches_matches_reference_golden(name,
         for k, g in zip(keys, grads):
             w = torch.from_numpy(gold[f"{name}.msl.{it}.grad.{k}"])
             assert float((g - w).abs().max()) <= 2e-5 * max(float(w.abs().max()), 1e-6), k
+
+
+@pytest.mark.parametrize("tag", ["init", "biased"])
+def test_closed_set_focal_loss_matches_reference_golden(tag, golden_dir):
+    """BASELINE configs[0] (configs/thumos14.yaml: focal, 21 classes incl. background, no actionness heads): the
+    reference's head outputs (golden) through the product's MultiSegmentLoss and the oracle's restatement -> the
+    reference's loss values."""
+    import json
+    import numpy as np
+    arrays = np.load(os.path.join(golden_dir, "model_thumos_closed.npz"))
+    with open(os.path.join(golden_dir, "model_thumos_closed.json")) as fh:
+        want = json.load(fh)[tag]["losses"]
+    cfg = O.OracleConfig(num_classes=21, os_head=False, use_edl=False)
+    out = {k: torch.from_numpy(arrays[f"{tag}.{k}"]) for k in ("loc", "conf", "prop_loc", "prop_conf", "center")}
+    out.update(priors=torch.cat(O.level_priors(cfg), 0), act=None, prop_act=None)
+    targets = [O.synthetic_targets(0, num_classes=20)]
+    got_o = O.multisegment_loss_closed(out, targets, cfg)
+    got_p = MultiSegmentLoss(21, 0.5, 1.0, cls_loss_type="focal")(out, targets)
+    assert got_p[5] is None and got_p[6] is None
+    for a, b, c in zip(got_o, got_p[:5], want):
+        assert abs(float(a) - c) <= 2e-5 * max(1.0, abs(c)) and abs(float(b) - c) <= 2e-5 * max(1.0, abs(c)), (float(a), float(b), c)

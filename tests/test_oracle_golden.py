@@ -198,3 +198,28 @@ def test_inference_postprocessing_oracle_matches_reference_golden(golden_dir):
         cand = torch.from_numpy(g[f"nms.{name}.cand"])
         kept, cnt, mask = O.softnms_v2(cand, sigma=float(g[f"nms.{name}.cfg"][1]), top_k=int(g[f"nms.{name}.cfg"][0]))
         assert torch.equal(mask, torch.from_numpy(g[f"nms.{name}.mask"])) and torch.allclose(kept, torch.from_numpy(g[f"nms.{name}.kept"]), atol=1e-7)
+
+
+def test_closed_set_config1_oracle_matches_reference_golden(golden_dir):
+    """BASELINE configs[0] / SURVEY §8d config 1 (`configs/thumos14.yaml`, closed set, eval forward on the seed-0 clip):
+    keys / shapes of §8(a9) and values the reference produced (oracle/make_golden.py --closed)."""
+    arrays = np.load(os.path.join(golden_dir, "model_thumos_closed.npz"))
+    cfg = O.OracleConfig(num_classes=21, os_head=False, use_edl=False)
+    spec = O.model_spec(cfg)
+    assert len(spec) == 442                              # no actionness heads: 446 - 2 x (weight, bias)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randint(0, 256, [1, 3, 256, 96, 96], generator=g).float() / 255) * 2 - 1
+    with torch.no_grad():
+        out = O.bdnet_forward(x, O.synthetic_state_dict(cfg), cfg, compat=True)
+    shapes = dict(loc=(1, 126, 2), conf=(1, 126, 21), prop_loc=(1, 126, 2), prop_conf=(1, 126, 21), center=(1, 126, 1),
+                  priors=(126, 1), start=(1, 256, 256), end=(1, 256, 256), start_loc_prop=(1, 64, 512), end_loc_prop=(1, 64, 512),
+                  start_conf_prop=(1, 64, 512), end_conf_prop=(1, 64, 512))
+    for k, s in shapes.items():
+        assert tuple(out[k].shape) == s, k
+    assert out["act"] is None and out["prop_act"] is None and "unct" not in out
+    for k in ("loc", "conf", "prop_loc", "prop_conf", "center"):
+        w = torch.from_numpy(arrays[f"init.{k}"])
+        assert float((out[k] - w).abs().max() / w.abs().max()) < 2e-5, k
+    for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop"):
+        w = torch.from_numpy(arrays[f"init.{k}.sample"])
+        assert float((out[k][:, ::8, ::8] - w).abs().max() / w.abs().max()) < 2e-5, k
