@@ -314,7 +314,14 @@ class I3DBackbone(nn.Module):
                   gx_off: int = 0, accumulate: bool = False) -> None:
         """wgrad into the flat gradient buffer + (optionally) dgrad into the fp32 buffer g_x."""
         pads = _pads(x.hi.shape[1:4], r.k)
-        ops.conv_wgrad(x, d, self._packed(self.flat_g, r), kernel=r.k, pad_front=pads, in_slice=in_slice, d_slice=d_slice)
+        if ops.OVERLAP_WGRAD:
+            # the weight gradient runs on the side stream next to the data gradients / elementwise kernels of the main
+            # stream (it fills their tails: every kernel here is persistent with one CTA per SM); the callers join before
+            # x / d can be released
+            with torch.cuda.stream(ops.fork()):
+                ops.conv_wgrad(x, d, self._packed(self.flat_g, r), kernel=r.k, pad_front=pads, in_slice=in_slice, d_slice=d_slice)
+        else:
+            ops.conv_wgrad(x, d, self._packed(self.flat_g, r), kernel=r.k, pad_front=pads, in_slice=in_slice, d_slice=d_slice)
         if g_x is not None:
             ops.conv_igemm(d, self._w(r), kernel=r.k, pad_front=tuple(kk - 1 - p for kk, p in zip(r.k, pads)),
                            in_slice=d_slice, out_f32=g_x, out_slice=(gx_off, r.cin), want_planes=False, dgrad=True,
@@ -358,6 +365,7 @@ class I3DBackbone(nn.Module):
                      self._wp.lo[sl].view(1, w1a + w2a, r1.cin) if self._wp.lo is not None else None)
         ops.conv_igemm(d_y, self._w(c["b0"]), kernel=(1, 1, 1), pad_front=(0, 0, 0), in_slice=(0, c["b0"].cout), out_f32=g_x,
                        out_slice=(0, c["b0"].cin), want_planes=False, dgrad=True, x2=d_m, w2=w12)
+        ops.join()               # all six weight gradients done: d_y / d_m / the saved activations may be released
         del d_y
         ops.maxpool_bwd(x, g_pool, g_x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)), argmax=parg)
         return g_x
@@ -399,6 +407,7 @@ class I3DBackbone(nn.Module):
                 d, d_next = d_next, None
                 g = torch.empty((*x.hi.shape[:4], r.cin), dtype=torch.float32, device=dev)
                 self._conv_bwd(r, x, d, g)
+                ops.join()
             else:  # conv1a: weight gradient only, the clip needs no gradient (train.py:165)
                 r = self.convs[name]
                 y = saved.pop(name)

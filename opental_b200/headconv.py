@@ -148,9 +148,18 @@ class _HeadConvFn(torch.autograd.Function):
         k = rec.taps
         gy = gy.contiguous()
         dp = ops.ncl_to_nlc_planes(gy, rec.cpad, with_lo=store.with_lo)
+        forked = False
         if rec.weight.requires_grad:
             store.bind_grads()
-            ops.conv_wgrad(xp, dp, store.block(store.flat_g, rec), kernel=(k, 1, 1), pad_front=(pf, 0, 0), stride=(stride, 1, 1))
+            if ops.OVERLAP_WGRAD and ctx.needs_input_grad[0]:
+                # weight gradient on the side stream, next to the data gradient (both are far smaller than the GPU)
+                forked = True
+                with torch.cuda.stream(ops.fork()):
+                    ops.conv_wgrad(xp, dp, store.block(store.flat_g, rec), kernel=(k, 1, 1), pad_front=(pf, 0, 0),
+                                   stride=(stride, 1, 1))
+            else:
+                ops.conv_wgrad(xp, dp, store.block(store.flat_g, rec), kernel=(k, 1, 1), pad_front=(pf, 0, 0), stride=(stride, 1, 1))
+        dp_w = dp                # keep the planes the side stream reads alive until the join
         gx = None
         if ctx.needs_input_grad[0]:
             if stride != 1:      # dgrad of a strided conv = stride-1 dgrad of the zero-upsampled gradient
@@ -164,6 +173,9 @@ class _HeadConvFn(torch.autograd.Function):
                 ops.conv_igemm(dp, store.w(rec), kernel=(1, 1, 1), pad_front=(0, 0, 0), out_f32=gx, want_planes=False, dgrad=True)
                 gx = gx.view(xshape)
         gb = gy.sum(dim=(0, 2)) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        if forked:
+            ops.join()
+        del dp_w
         return gx, None, gb, None, None, None
 
 

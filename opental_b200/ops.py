@@ -7,7 +7,11 @@ from __future__ import annotations
 import ctypes
 from dataclasses import dataclass
 
+import os
+
 import torch
+
+OVERLAP_WGRAD = os.environ.get("OTAL_NO_WGRAD_OVERLAP") is None      # see fork() / join() below
 
 from . import _lib
 from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, MslDesc, PoolDesc, WgradDesc
@@ -27,12 +31,17 @@ class KernelProfile:
 
         class _Ctx:
             def __enter__(self_):
+                global OVERLAP_WGRAD
                 prof.on = True
                 prof.records = []
+                # a kernel's roofline time is measured with the kernel running alone: no side-stream overlap while profiling
+                self_.overlap, OVERLAP_WGRAD = OVERLAP_WGRAD, False
                 return prof
 
             def __exit__(self_, *a):
+                global OVERLAP_WGRAD
                 prof.on = False
+                OVERLAP_WGRAD = self_.overlap
 
         return _Ctx()
 
@@ -74,6 +83,30 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fork / join: a layer's weight gradient does not depend on its data gradient.  `fork()` returns a side stream that has
+# waited for everything enqueued on the current stream so far; `join()` makes the current stream wait for it.  Callers
+# join before any tensor the side stream reads can be released (the caching allocator re-uses a block in stream order of
+# the stream it was allocated on).  Works under CUDA-graph capture (the side stream joins the capture through the event).
+# ----------------------------------------------------------------------------------------------------------
+_SIDE: dict = {}
+
+
+def fork() -> "torch.cuda.Stream":
+    dev = torch.cuda.current_device()
+    side = _SIDE.get(dev)
+    if side is None:
+        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    return side
+
+
+def join() -> None:
+    side = _SIDE.get(torch.cuda.current_device())
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
