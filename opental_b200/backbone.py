@@ -125,6 +125,7 @@ class I3DBackbone(nn.Module):
         self.on_backward_start = None     # optional callback (the trainer overlaps the head's all-reduce here)
         self.crop_size = 96               # uint8 input path: crop extent (config dataset.training.crop_size)
         self.crop_offsets = None          # optional int32 [N,3] device tensor (row, column, mirror) per sample
+        self._parked: list = []           # (event, tensors) of blocks whose side-stream weight gradients may still run
         self.frame_map = None             # optional int32 [N,T] device tensor: temporal gather in the ingest kernel (SSL cut-paste)
         self.reset_parameters()
 
@@ -365,10 +366,29 @@ class I3DBackbone(nn.Module):
                      self._wp.lo[sl].view(1, w1a + w2a, r1.cin) if self._wp.lo is not None else None)
         ops.conv_igemm(d_y, self._w(c["b0"]), kernel=(1, 1, 1), pad_front=(0, 0, 0), in_slice=(0, c["b0"].cout), out_f32=g_x,
                        out_slice=(0, c["b0"].cin), want_planes=False, dgrad=True, x2=d_m, w2=w12)
-        ops.join()               # all six weight gradients done: d_y / d_m / the saved activations may be released
-        del d_y
         ops.maxpool_bwd(x, g_pool, g_x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)), argmax=parg)
+        # the six weight gradients may still be running on the side stream: everything they read stays referenced until the
+        # main stream has waited for them (one block later, see _retire)
+        self._retire((x, y, mid, pooled, parg, d_y, d_m))
         return g_x
+
+    def _retire(self, tensors) -> None:
+        """Deferred join: the side stream's weight gradients of this block keep running under the main stream's next
+        kernels (stage-pool backward, ReLU/BN backward, the next block's data gradients).  The tensors they read are
+        parked with an event recorded behind them; the PREVIOUS block's entry is released once the main stream has
+        waited for its event — so at most two blocks of gradient planes are held beyond their natural lifetime."""
+        if not ops.OVERLAP_WGRAD:
+            return
+        ev = torch.cuda.Event()
+        ev.record(ops.side_stream())
+        self._parked.append((ev, tensors))
+        while len(self._parked) > 1:
+            old_ev, _ = self._parked.pop(0)
+            torch.cuda.current_stream().wait_event(old_ev)
+
+    def _retire_all(self) -> None:
+        ops.join()
+        self._parked.clear()
 
     def backward_planes(self, saved: dict, g4: torch.Tensor | None, g5: torch.Tensor | None) -> None:
         """Explicit backward schedule.  g4 / g5: fp32 NDHWC gradients w.r.t. Mixed_4f / Mixed_5c (or None)."""
@@ -407,7 +427,7 @@ class I3DBackbone(nn.Module):
                 d, d_next = d_next, None
                 g = torch.empty((*x.hi.shape[:4], r.cin), dtype=torch.float32, device=dev)
                 self._conv_bwd(r, x, d, g)
-                ops.join()
+                self._retire((x, y, d))
             else:  # conv1a: weight gradient only, the clip needs no gradient (train.py:165)
                 r = self.convs[name]
                 y = saved.pop(name)
@@ -420,6 +440,7 @@ class I3DBackbone(nn.Module):
                 ops.conv1a_wgrad(a, d, dw, W)
                 # packed layout of this block is [kt,kh,kw,Cout,Cin]; the parameter's .grad is its strided view
                 r.unit.conv3d.weight.grad.add_(ops.unpack_conv1a_wgrad(dw, r.cin))
+        self._retire_all()
 
 
 class _BackboneFn(torch.autograd.Function):

@@ -103,6 +103,14 @@ def fork() -> "torch.cuda.Stream":
     return side
 
 
+def side_stream() -> "torch.cuda.Stream":
+    dev = torch.cuda.current_device()
+    side = _SIDE.get(dev)
+    if side is None:
+        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return side
+
+
 def join() -> None:
     side = _SIDE.get(torch.cuda.current_device())
     if side is not None:
