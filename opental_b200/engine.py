@@ -19,6 +19,7 @@ per-rank, which differs from "the reference at batch 8*W on one GPU" exactly as 
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -335,16 +336,10 @@ def synthetic_targets(index: int, rank: int = 0, num_classes: int = 15) -> torch
 
 
 def synthetic_scores(targets: torch.Tensor, frames: int = 256) -> torch.Tensor:
-    """start/end score maps [2,T] (thumos_dataset.py:110-120)."""
-    scores = torch.zeros(2, frames)
-    for s, e, _ in targets.tolist():
-        s_f, e_f = s * frames, e * frames
-        half = max((e_f - s_f) / 10.0, 2.0)
-        for row, centre in ((0, s_f), (1, e_f)):
-            lo = max(int(round(centre - half)), 0)
-            hi = min(int(round(centre + half)), frames - 1)
-            scores[row, lo:hi + 1] = 1.0
-    return scores
+    """start/end score maps [2,T] of a clip's (normalised) targets — the loader's rule, thumos_dataset.py:109-120."""
+    from .windows import boundary_score_maps
+    start, end = boundary_score_maps([[s * frames, e * frames, l] for s, e, l in targets.tolist()], frames)
+    return torch.from_numpy(np.stack([start, end])).float()
 
 
 OPENTAL_EDL_CONFIG = dict(evidence="exp", loss_type="log", with_ibm=True, ibm_start=10, momentum=0.99, num_bins=50,

@@ -457,6 +457,49 @@ def closed_cases():
     ns.restore_cuda()
 
 
+def window_case_tables(seed: int):
+    """Synthetic video_infos / video_annos tables (sampled-frame units, fractional boundaries like the csv * ratio)."""
+    import random
+    r = random.Random(seed)
+    infos, annos = {}, {}
+    for v in range(6):
+        name = f"video_{seed}_{v}"
+        count = r.choice([120, 256, 300, 517, 1000, 1444])
+        infos[name] = dict(fps=30.0, sample_fps=10.0, count=count * 3, sample_count=count)
+        n = r.randint(1, 5)
+        segs = []
+        for _ in range(n):
+            s = r.uniform(0, count - 12)
+            segs.append([s, min(s + r.uniform(4, 180), count - 1.0), r.randint(1, 20)])
+        annos[name] = segs
+    return infos, annos
+
+
+def window_cases():
+    """Sliding-window index + start/end score maps: the reference's split_videos (thumos_dataset.py:69-130) vs
+    opental_b200.windows.split_videos on synthetic tables."""
+    import importlib
+    ns = ref_loader.load_reference()
+    ds = importlib.import_module("AFSD.common.thumos_dataset")
+    from opental_b200 import windows as Wn
+    out = []
+    for seed, (clip, stride) in enumerate([(256, 30), (256, 128), (128, 30), (512, 64)]):
+        infos, annos = window_case_tables(seed)
+        tl_r, th_r = ds.split_videos(infos, annos, clip, stride)
+        tl_o, th_o = Wn.split_videos(infos, annos, clip, stride)
+        assert th_r == th_o and len(tl_r) == len(tl_o) > 0, (seed, len(tl_r), len(tl_o))
+        for a, b in zip(tl_r, tl_o):
+            assert a["video_name"] == b["video_name"] and a["offset"] == b["offset"] and a["annos"] == b["annos"]
+            assert np.array_equal(a["start"], b["start"]) and np.array_equal(a["end"], b["end"])
+        out.append(dict(seed=seed, clip_length=clip, stride=stride, th=th_r, infos=infos, annos=annos,
+                        windows=[dict(video_name=w["video_name"], offset=int(w["offset"]), annos=[list(map(float, x)) for x in w["annos"]],
+                                      start=np.nonzero(w["start"])[0].tolist(), end=np.nonzero(w["end"])[0].tolist()) for w in tl_r]))
+        print(f"[windows] seed {seed}: {len(tl_r)} windows, th {sorted(th_r.values())}: identical")
+    with open(os.path.join(GOLD, "window_cases.json"), "w") as fh:
+        json.dump(out, fh)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -470,6 +513,9 @@ if __name__ == "__main__":
         edl_cases()
     elif "--closed" in sys.argv:
         closed_cases()
+    elif "--windows" in sys.argv:
+        sys.path.insert(0, ROOT)
+        window_cases()
     elif "--augment" in sys.argv:
         sys.path.insert(0, ROOT)
         augment_cases()

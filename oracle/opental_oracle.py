@@ -217,15 +217,15 @@ def synthetic_targets(index: int, rank: int = 0, num_classes: int = 15) -> torch
 
 
 def synthetic_scores(targets: torch.Tensor, frames: int = 256) -> torch.Tensor:
-    """start/end score maps [2,T]: ones within +-max(len/10, 1) frames of each boundary... restates the rule
-    at thumos_dataset.py:110-120 (annos in frames: start/end window half-width = max((end-start)/10, 2.0))."""
+    """start/end score maps [2,T]: ones inside a band of width d = max(len/10, 2) frames centred on each start / end
+    boundary, python rounding, clipped to the clip — the loader's rule at thumos_dataset.py:109-120."""
     scores = torch.zeros(2, frames)
     for s, e, _ in targets.tolist():
         s_f, e_f = s * frames, e * frames
-        half = max((e_f - s_f) / 10.0, 2.0)
+        d = max((e_f - s_f) / 10.0, 2.0)
         for row, centre in ((0, s_f), (1, e_f)):
-            lo = max(int(round(centre - half)), 0)
-            hi = min(int(round(centre + half)), frames - 1)
+            lo = min(max(int(round(centre - d / 2.0)), 0), frames - 1)
+            hi = min(max(int(round(centre + d / 2.0)), 0), frames - 1)
             scores[row, lo:hi + 1] = 1.0
     return scores
 
