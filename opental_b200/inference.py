@@ -60,3 +60,26 @@ def detect_video(net, frames: torch.Tensor, sample_fps: float, *, clip_length: i
         if m.any():
             result[cl] = torch.cat([seg_c[m], decayed_c[cl][m, None], unct_c[m, None], act_c[m, None]], -1)
     return result
+
+
+def to_proposal_list(result: dict, idx_to_class: dict, *, os_head: bool = True, use_edl: bool = True) -> list[dict]:
+    """The per-video list `get_video_detections` returns (test.py:182-200) from `detect_video`'s result: one dict per kept
+    detection with the keys the evaluation reads (`label`, `score`, `segment`, `uncertainty`, `actionness`), classes in
+    increasing index order, rows in descending score order (the order soft-NMS selects them in).  `idx_to_class` maps
+    1..K to names (`get_class_index_map`, thumos_dataset.py:13-21); with the open-set head the model's class c is c + 1."""
+    out = []
+    for cl in sorted(result):
+        rows = result[cl]
+        name = idx_to_class[cl + 1 if os_head else cl]
+        order = torch.argsort(rows[:, 2], descending=True, stable=True)
+        for r in rows[order].tolist():
+            if r[2] <= 0:
+                continue
+            out.append({"label": name, "score": float(r[2]), "segment": [float(r[0]), float(r[1])],
+                        "uncertainty": float(r[3]) if use_edl else 0.0, "actionness": float(r[4]) if os_head else 0.0})
+    return out
+
+
+def results_json(per_video: dict, version: str = "THUMOS14") -> dict:
+    """The file `test()` writes (test.py:253-255): {'version', 'results': {video: proposal list}, 'external_data'}."""
+    return {"version": version, "results": dict(per_video), "external_data": {}}

@@ -99,3 +99,18 @@ def test_optimizer_state_interoperates_with_torch_adam():
     with pytest.raises(ValueError):
         bad = dict(state={}, param_groups=[dict(params=list(range(3)))])
         ck.load_adam_state_dict(bad, params, groups, state2)
+
+
+def test_proposal_list_has_the_reference_format():
+    """inference.to_proposal_list: the dict layout of get_video_detections (test.py:182-200)."""
+    from opental_b200.inference import results_json, to_proposal_list
+    result = {2: torch.tensor([[1.0, 2.5, 0.3, 0.1, 0.9], [4.0, 6.0, 0.8, 0.2, 0.7]]), 0: torch.tensor([[0.5, 1.5, 0.6, 0.4, 0.95]])}
+    names = {i: f"class{i}" for i in range(1, 16)}
+    props = to_proposal_list(result, names)
+    assert [p["label"] for p in props] == ["class1", "class3", "class3"]              # model class c -> name of c + 1 (os_head)
+    assert [round(p["score"], 6) for p in props] == [0.6, 0.8, 0.3]                   # descending inside a class
+    assert props[1]["segment"] == [4.0, 6.0] and set(props[0]) == {"label", "score", "segment", "uncertainty", "actionness"}
+    closed = to_proposal_list({3: result[0]}, names, os_head=False, use_edl=False)
+    assert closed[0]["label"] == "class3" and closed[0]["uncertainty"] == 0.0 and closed[0]["actionness"] == 0.0
+    doc = results_json({"video_test_0000004": props})
+    assert doc["version"] == "THUMOS14" and list(doc["results"]) == ["video_test_0000004"] and doc["external_data"] == {}
