@@ -126,6 +126,7 @@ class Trainer:
         self.step_count = 0
         self._head_launched = False
         self._graph = None
+        self._graph_ssl = False
         self._static = None
         self._capturing = False
         bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
@@ -239,6 +240,12 @@ class Trainer:
         finally:
             self._capturing = False
         self._graph_epoch_flag = self._ibm_flag()
+        self._graph_ssl = ssl_clips is not None or ssl_frame_map is not None
+
+    def graph_matches(self, ssl: bool) -> bool:
+        """Is there a captured step graph for this flavour of batch (with / without the SSL pass) and the current epoch's
+        IBM switch?  (Batch geometry is checked by step() itself.)"""
+        return self._graph is not None and self._graph_ssl == bool(ssl) and self._ibm_flag() == self._graph_epoch_flag
 
     def _ibm_flag(self):
         c = self.criterion.cls_loss

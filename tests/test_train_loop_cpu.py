@@ -1,0 +1,89 @@
+"""CPU: the training driver's bookkeeping (opental_b200/train_loop.py; semantics of AFSD/thumos14/train.py:203-300, 370-380)
+with a recording stand-in for the Trainer (the real one needs a GPU: tests/test_model_gpu.py, test_checkpoint_gpu.py)."""
+import types
+
+import torch
+
+from opental_b200 import train_loop
+
+
+class FakeTrainer:
+    def __init__(self, ibm_start=3):
+        self.criterion = types.SimpleNamespace(cls_loss=types.SimpleNamespace(epoch=0, total_epoch=25, ibm_start=ibm_start))
+        self.calls, self.captures, self.saved, self.resumed = [], [], [], None
+        self._graph = None
+
+    def _flag(self):
+        return self.criterion.cls_loss.epoch >= self.criterion.cls_loss.ibm_start
+
+    def graph_matches(self, ssl):
+        return self._graph is not None and self._graph == (bool(ssl), self._flag())
+
+    def capture(self, clips, targets, scores, **kw):
+        self._graph = (bool(kw), self._flag())
+        self.captures.append((self.criterion.cls_loss.epoch, sorted(kw)))
+
+    def step(self, clips, targets, scores, **kw):
+        assert self._graph is None or self._graph == (bool(kw), self._flag())
+        self.calls.append((self.criterion.cls_loss.epoch, sorted(kw)))
+        v = float(len(self.calls))
+        t = torch.tensor
+        return t(v), (t(1.0), t(2.0), t(3.0), t(4.0), t(5.0), t(6.0), t(7.0)), t(0.5), t(0.25)
+
+    def grad_norm(self):
+        return torch.tensor(2.0)
+
+    def save_checkpoint(self, epoch, a, b):
+        self.saved.append((epoch, a, b))
+
+    def resume(self, epoch, a, b):
+        self.resumed = epoch
+        return epoch + 1
+
+
+def batch(flag, with_map=True):
+    b = dict(clips=torch.zeros(1), targets=[torch.zeros(1, 3)], scores=torch.zeros(1, 2, 4), flags=[flag, True],
+             ssl_targets=[torch.zeros(3, 2)])
+    if with_map:
+        b["ssl_frame_map"] = torch.zeros(1, 4, dtype=torch.int32)
+    return b
+
+
+def test_epoch_means_ssl_flag_and_recapture():
+    tr = FakeTrainer()
+    tr.criterion.cls_loss.epoch = 1
+    m = train_loop.run_one_epoch(tr, [batch(True), batch(True), batch(False), batch(True, with_map=False)], 1)
+    # SSL pass only when the FIRST sample's flag is set (train.py:237) and an augmented clip / frame map is present
+    assert [c[1] for c in tr.calls] == [["ssl_frame_map", "ssl_targets"]] * 2 + [[], []]
+    assert m["steps"] == 4 and m["ssl_steps"] == 2
+    assert len(tr.captures) == 2                                   # one per flavour, not one per step
+    assert m["cost"] == 2.5 and m["loc"] == 1.0 and m["prop_conf"] == 4.0 and m["start"] == 0.5 and m["end"] == 0.25
+    assert m["act"] == 6.0 and m["prop_act"] == 7.0 and m["grad_norm"] == 2.0
+    line = train_loop.summary_line(1, m)
+    assert line.startswith("Epoch-1 Train Loss: Total - 2.50000, loc - 1.00000, conf - 2.00000")
+
+
+def test_fit_sets_epochs_recaptures_on_ibm_switch_and_checkpoints_after_epoch_10(tmp_path):
+    tr = FakeTrainer(ibm_start=3)
+    logs = []
+    hist = train_loop.fit(tr, lambda e: [batch(False), batch(False)], max_epoch=12, checkpoint_path=str(tmp_path / "c"),
+                          train_state_path=str(tmp_path / "s"), log=logs.append)
+    assert [h["epoch"] for h in hist] == list(range(1, 13)) and len(logs) == 12
+    assert tr.criterion.cls_loss.total_epoch == 12
+    assert [c[0] for c in tr.calls] == [e for e in range(1, 13) for _ in range(2)]
+    assert [c[0] for c in tr.captures] == [1, 3]                    # first step, then when the IBM switch flips at epoch 3
+    assert [s[0] for s in tr.saved] == [11, 12]                     # `if training and epoch > 10: save_model` (train.py:291-293)
+
+
+def test_fit_resumes_from_the_reference_layout():
+    tr = FakeTrainer()
+    hist = train_loop.fit(tr, lambda e: [batch(False)], max_epoch=6, resume=4, checkpoint_path="c", train_state_path="s",
+                          use_graph=False, log=lambda s: None)
+    assert tr.resumed == 4 and [h["epoch"] for h in hist] == [5, 6] and not tr.captures
+
+
+def test_closed_set_losses_without_actionness_terms():
+    tr = FakeTrainer()
+    tr.step = lambda *a, **k: (torch.tensor(1.0), (torch.tensor(1.0),) * 5 + (None, None), torch.tensor(0.0), torch.tensor(0.0))
+    m = train_loop.run_one_epoch(tr, [batch(False)], 1, use_graph=False)
+    assert m["act"] == 0.0 and m["prop_act"] == 0.0
