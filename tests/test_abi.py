@@ -47,6 +47,14 @@ def test_bad_arguments_return_codes_without_gpu():
     assert lib.otal_bmp_forward_f32(None, None, None, 1, 4, 4, 2, None) == -1   # null pointers
     assert lib.otal_conv_igemm_fwd(None, None) == -1
     assert lib.otal_bmp_forward_f32(None, None, None, 0, 4, 4, 2, None) == 0    # empty batch is a no-op
+    # descriptor-taking entry points reject a null descriptor
+    for name in ("otal_conv_wgrad", "otal_conv1a_fwd", "otal_conv1a_wgrad", "otal_maxpool_fwd", "otal_msl_forward"):
+        assert getattr(lib, name)(None, None) == -1, name
+        assert "null descriptor" in _lib.last_error(), name
+    # uint8 ingest: odd crop width, crop larger than the frame, null source
+    for args in ((4096, None, None, 4096, None, 1, 4, 8, 8, 6, 5, None), (4096, None, None, 4096, None, 1, 4, 8, 8, 12, 6, None),
+                 (None, None, None, 4096, None, 1, 4, 8, 8, 6, 6, None)):
+        assert lib.otal_clip_ingest_u8(*args) == -1 and "clip_ingest_u8" in _lib.last_error()
 
 
 def test_product_path_fails_loudly_without_cuda():
