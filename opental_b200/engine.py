@@ -127,6 +127,7 @@ class Trainer:
         self._head_launched = False
         self._graph = None
         self._graph_ssl = False
+        self.target_slots = 8          # ground-truth slots per clip of a captured graph (more in a batch -> capture() again)
         self._static = None
         self._capturing = False
         bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
@@ -215,7 +216,7 @@ class Trainer:
         The graph bakes in `criterion.cls_loss.epoch >= ibm_start`: re-capture when the epoch crosses ibm_start."""
         import gc
         gc.collect()                                 # drop dead autograd graphs of earlier eager steps (see forward_backward)
-        tgt, valid = pad_targets(targets, clips.device)
+        tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
         srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
         self._static = [torch.empty_like(t) for t in srcs]
         for d, s in zip(self._static, srcs):
@@ -242,10 +243,20 @@ class Trainer:
         self._graph_epoch_flag = self._ibm_flag()
         self._graph_ssl = ssl_clips is not None or ssl_frame_map is not None
 
-    def graph_matches(self, ssl: bool) -> bool:
-        """Is there a captured step graph for this flavour of batch (with / without the SSL pass) and the current epoch's
-        IBM switch?  (Batch geometry is checked by step() itself.)"""
-        return self._graph is not None and self._graph_ssl == bool(ssl) and self._ibm_flag() == self._graph_epoch_flag
+    @staticmethod
+    def _max_segments(targets) -> int:
+        """Largest number of ground-truth segments of a sample (0 for an already padded (tensor, mask) pair: its geometry is
+        compared as is)."""
+        if isinstance(targets, (tuple, list)) and len(targets) == 2 and torch.is_tensor(targets[0]) and targets[0].dim() == 3:
+            return 0
+        return max(int(t.shape[0]) for t in targets)
+
+    def graph_matches(self, ssl: bool, targets=None) -> bool:
+        """Is there a captured step graph for this flavour of batch (with / without the SSL pass), the current epoch's IBM
+        switch and (when `targets` is given) enough ground-truth slots?  (Clip geometry is checked by step() itself.)"""
+        if self._graph is None or self._graph_ssl != bool(ssl) or self._ibm_flag() != self._graph_epoch_flag:
+            return False
+        return targets is None or self._max_segments(targets) <= self._static[1].shape[1]
 
     def _ibm_flag(self):
         c = self.criterion.cls_loss
@@ -257,7 +268,9 @@ class Trainer:
         positive, negative) segments for the triplet pass (thumos14/train.py:237-242), or None.  ssl_frame_map (int32
         [B,T], from opental_b200.augment.cut_paste) replaces ssl_clips when `clips` are uint8 frames."""
         if self._graph is not None:
-            tgt, valid = pad_targets(targets, clips.device)
+            if self._max_segments(targets) > self._static[1].shape[1]:
+                raise RuntimeError("captured training graph does not match this batch geometry / epoch: call capture() again")
+            tgt, valid = pad_targets(targets, clips.device, slots=self._static[1].shape[1])
             srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
             if (len(srcs) != len(self._static) or any(tuple(a.shape) != tuple(b.shape) or a.dtype != b.dtype for a, b in zip(srcs, self._static))
                     or self._ibm_flag() != self._graph_epoch_flag):

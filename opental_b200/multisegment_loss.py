@@ -36,12 +36,18 @@ def _giou_loss(pred, target):
     return 1.0 - (iou - (hull - union) / hull.clamp(min=_EPS))
 
 
-def pad_targets(targets, device=None):
-    """list of B tensors [N_i,3] (start, end, label; normalised) -> ([B,G,3] zero padded, [B,G] valid mask)."""
+def pad_targets(targets, device=None, slots=None):
+    """list of B tensors [N_i,3] (start, end, label; normalised) -> ([B,G,3] zero padded, [B,G] valid mask).
+    G = the largest N_i of the batch, or `slots` when given (a fixed geometry for a captured step graph; ValueError when a
+    sample has more segments than slots).  An already padded (tensor, mask) pair is returned as is."""
     if isinstance(targets, (tuple, list)) and len(targets) == 2 and torch.is_tensor(targets[0]) and targets[0].dim() == 3:
         return targets
     B = len(targets)
     G = max(1, max(int(t.shape[0]) for t in targets))
+    if slots is not None:
+        if G > slots:
+            raise ValueError(f"a sample has {G} ground-truth segments, the padded geometry has {slots} slots")
+        G = int(slots)
     device = device or targets[0].device
     padded = torch.zeros(B, G, 3, dtype=torch.float32)
     valid = torch.zeros(B, G, dtype=torch.bool)

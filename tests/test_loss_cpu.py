@@ -229,3 +229,23 @@ def test_closed_set_focal_loss_matches_reference_golden(tag, golden_dir):
     assert got_p[5] is None and got_p[6] is None
     for a, b, c in zip(got_o, got_p[:5], want):
         assert abs(float(a) - c) <= 2e-5 * max(1.0, abs(c)) and abs(float(b) - c) <= 2e-5 * max(1.0, abs(c)), (float(a), float(b), c)
+
+
+def test_pad_targets_fixed_slots():
+    from opental_b200.multisegment_loss import pad_targets
+    t = [torch.tensor([[0.1, 0.2, 3.0]]), torch.tensor([[0.3, 0.5, 1.0], [0.6, 0.9, 2.0]])]
+    p, v = pad_targets(t)
+    assert tuple(p.shape) == (2, 2, 3) and v.tolist() == [[True, False], [True, True]]
+    p8, v8 = pad_targets(t, slots=8)
+    assert tuple(p8.shape) == (2, 8, 3) and int(v8.sum()) == 3 and torch.equal(p8[:, :2], p)
+    assert pad_targets((p8, v8), slots=4)[0] is p8                    # an already padded pair passes through
+    with pytest.raises(ValueError):
+        pad_targets(t, slots=1)
+    # the loss does not depend on the number of (invalid) padding slots
+    out = {k: v_ for k, v_ in O.fake_head_outputs(2, 3).items()}
+    out["priors"] = torch.cat(O.level_priors(O.OracleConfig()), 0)
+    crit = MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True, act_config=dict(weight=0.1, margin=1.0))
+    crit.cls_loss.epoch = 1
+    a = crit(out, pad_targets(t))
+    b = crit(out, pad_targets(t, slots=8))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))

@@ -94,7 +94,7 @@ def main():
                 flags.append(flag)
                 offs.append([rng.randrange(112 - crop + 1), rng.randrange(112 - crop + 1), rng.randrange(2)])
             net.backbone.crop_offsets.copy_(torch.tensor(offs, dtype=torch.int32))
-            yield dict(clips=torch.stack(clips).to(dev), targets=[t.to(dev) for t in tgts], scores=torch.stack(scores).to(dev),
+            yield dict(clips=torch.stack(clips).to(dev), targets=tgts, scores=torch.stack(scores).to(dev),
                        flags=flags, ssl_targets=[t.to(dev) for t in ssl_t], ssl_frame_map=torch.stack(maps).to(dev))
 
     ck, st = os.path.join(args.out, "checkpoint"), os.path.join(args.out, "train_state")
