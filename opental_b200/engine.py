@@ -127,6 +127,7 @@ class Trainer:
         self._head_launched = False
         self._graph = None
         self._graph_ssl = False
+        self._graph_cache: dict = {}    # flavour (with / without the SSL pass) -> the captured graph that is not current
         self.target_slots = 8          # ground-truth slots per clip of a captured graph (more in a batch -> capture() again)
         self._static = None
         self._capturing = False
@@ -215,6 +216,7 @@ class Trainer:
         the Adam launches stay outside the graph (Adam's bias correction depends on the host step counter).
         The graph bakes in `criterion.cls_loss.epoch >= ibm_start`: re-capture when the epoch crosses ibm_start."""
         import gc
+        self._stash()                                # a graph of the other flavour stays available (select_graph)
         gc.collect()                                 # drop dead autograd graphs of earlier eager steps (see forward_backward)
         tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
         srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
@@ -257,6 +259,24 @@ class Trainer:
         if self._graph is None or self._graph_ssl != bool(ssl) or self._ibm_flag() != self._graph_epoch_flag:
             return False
         return targets is None or self._max_segments(targets) <= self._static[1].shape[1]
+
+    def _stash(self) -> None:
+        if self._graph is not None:
+            self._graph_cache[self._graph_ssl] = (self._graph, self._static, self._graph_out, self._graph_epoch_flag)
+
+    def select_graph(self, ssl: bool, targets=None) -> bool:
+        """Make a captured graph that fits this batch current (see graph_matches); False = the caller must capture().
+        One graph per flavour is kept, so batches alternating between with / without the SSL pass (train.py:237: only when
+        the first sample could be augmented) do not re-capture."""
+        if self.graph_matches(ssl, targets):
+            return True
+        ent = self._graph_cache.get(bool(ssl))
+        if ent is None or ent[3] != self._ibm_flag() or (targets is not None and self._max_segments(targets) > ent[1][1].shape[1]):
+            return False
+        self._stash()
+        self._graph, self._static, self._graph_out, self._graph_epoch_flag = ent
+        self._graph_ssl = bool(ssl)
+        return True
 
     def _ibm_flag(self):
         c = self.criterion.cls_loss

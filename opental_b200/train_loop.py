@@ -37,8 +37,8 @@ def run_one_epoch(trainer, batches: Iterable[dict], epoch: int, *, use_graph: bo
             kw = dict(ssl_targets=b["ssl_targets"], ssl_clips=b.get("ssl_clips"), ssl_frame_map=b.get("ssl_frame_map"))
             kw = {k: v for k, v in kw.items() if v is not None}
             n_ssl += 1
-        if use_graph and not trainer.graph_matches(ssl, b["targets"]):
-            # (re)capture: first iteration, the batch flavour changed (with / without the SSL pass), a clip has more
+        if use_graph and not trainer.select_graph(ssl, b["targets"]):
+            # capture: no graph of this flavour yet (one is kept per flavour), the batch flavour changed (with / without the SSL pass), a clip has more
             # ground-truth segments than the graph has slots, or the IBM switch flipped with the epoch.  Flavour changes are rare when most windows can be augmented.
             trainer.capture(b["clips"], b["targets"], b["scores"], **kw)
         cost, losses, ls, le = trainer.step(b["clips"], b["targets"], b["scores"], **kw)

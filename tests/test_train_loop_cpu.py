@@ -12,15 +12,21 @@ class FakeTrainer:
         self.criterion = types.SimpleNamespace(cls_loss=types.SimpleNamespace(epoch=0, total_epoch=25, ibm_start=ibm_start))
         self.calls, self.captures, self.saved, self.resumed = [], [], [], None
         self._graph = None
+        self.cache = set()
 
     def _flag(self):
         return self.criterion.cls_loss.epoch >= self.criterion.cls_loss.ibm_start
 
-    def graph_matches(self, ssl, targets=None):
-        return self._graph is not None and self._graph == (bool(ssl), self._flag())
+    def select_graph(self, ssl, targets=None):
+        key = (bool(ssl), self._flag())
+        if key in self.cache:
+            self._graph = key
+            return True
+        return False
 
     def capture(self, clips, targets, scores, **kw):
         self._graph = (bool(kw), self._flag())
+        self.cache.add(self._graph)
         self.captures.append((self.criterion.cls_loss.epoch, sorted(kw)))
 
     def step(self, clips, targets, scores, **kw):
@@ -52,11 +58,11 @@ def batch(flag, with_map=True):
 def test_epoch_means_ssl_flag_and_recapture():
     tr = FakeTrainer()
     tr.criterion.cls_loss.epoch = 1
-    m = train_loop.run_one_epoch(tr, [batch(True), batch(True), batch(False), batch(True, with_map=False)], 1)
+    m = train_loop.run_one_epoch(tr, [batch(True), batch(False), batch(True), batch(True, with_map=False)], 1)
     # SSL pass only when the FIRST sample's flag is set (train.py:237) and an augmented clip / frame map is present
-    assert [c[1] for c in tr.calls] == [["ssl_frame_map", "ssl_targets"]] * 2 + [[], []]
+    assert [c[1] for c in tr.calls] == [["ssl_frame_map", "ssl_targets"], [], ["ssl_frame_map", "ssl_targets"], []]
     assert m["steps"] == 4 and m["ssl_steps"] == 2
-    assert len(tr.captures) == 2                                   # one per flavour, not one per step
+    assert len(tr.captures) == 2                                   # one per flavour even when the flavours alternate
     assert m["cost"] == 2.5 and m["loc"] == 1.0 and m["prop_conf"] == 4.0 and m["start"] == 0.5 and m["end"] == 0.25
     assert m["act"] == 6.0 and m["prop_act"] == 7.0 and m["grad_norm"] == 2.0
     line = train_loop.summary_line(1, m)
