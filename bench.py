@@ -126,6 +126,21 @@ def cpu_training_steps(steps: int, warmup: int, batch: int = 1):
     return batch * 1000.0 / ms, ms, cores
 
 
+def host_info() -> dict:
+    """CPU model and torch version of the box the CPU numbers were taken on (SURVEY §8d 'CPU baseline timing')."""
+    import torch
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"cpu": model, "torch": torch.__version__}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,7 +155,7 @@ def run_reference(args):
                    "parallelism": f"dp{args.gpus}",
                    "reference_sample": "CPU restatement of the reference (oracle/, torch CPU fp32, all host cores); one step = forward + "
                                        "loss + backward of ONE clip (no optimizer), rank 0 only"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", **host_info(),
                          "sample": f"{steps} training steps of 1 clip after {warm} warm-up (forward + loss + backward, torch CPU fp32)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -343,7 +358,7 @@ def run_native(args):
     cpu_base = None
     if not args.no_cpu_baseline:
         v, cms, cores = cpu_training_steps(8, 1, batch=2)
-        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", **host_info(),
                     "sample": "8 training steps of 2 clips after 1 warm-up, ~10 s of CPU work (forward + loss + backward, torch CPU "
                               "fp32 restatement of the reference in oracle/, all host cores)",
                     "ms_per_step": cms}
