@@ -93,3 +93,41 @@ def test_closed_set_losses_without_actionness_terms():
     tr.step = lambda *a, **k: (torch.tensor(1.0), (torch.tensor(1.0),) * 5 + (None, None), torch.tensor(0.0), torch.tensor(0.0))
     m = train_loop.run_one_epoch(tr, [batch(False)], 1, use_graph=False)
     assert m["act"] == 0.0 and m["prop_act"] == 0.0
+
+
+def _fit_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from opental_b200 import train_loop as tl
+    from opental_b200.engine import shard_indices
+    tr = FakeTrainer()
+    logs = []
+    windows_ = list(range(10))                                       # 10 windows, batch 1 per rank: 5 steps per epoch per rank
+
+    def make_batches(epoch):
+        for i in shard_indices(len(windows_), rank, world):
+            yield batch(False)
+
+    hist = tl.fit(tr, make_batches, max_epoch=11, checkpoint_path=os.path.join(out_dir, "c"), train_state_path=os.path.join(out_dir, "s"),
+                  use_graph=False, log=logs.append)
+    torch.save(dict(saved=tr.saved, logs=len(logs), steps=[h["steps"] for h in hist]), os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fit_world_size_2_rank0_writes_checkpoints_and_logs(tmp_path):
+    """gloo, world size 2: every rank runs its shard of the epoch, only rank 0 logs and writes checkpoints."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_fit_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(2))
+    assert r0["steps"] == r1["steps"] == [5] * 11
+    assert [s[0] for s in r0["saved"]] == [11] and r1["saved"] == []
+    assert r0["logs"] == 11 and r1["logs"] == 0
