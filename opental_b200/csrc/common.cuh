@@ -18,6 +18,20 @@ namespace otal {
         if (_e != cudaSuccess) { otal::set_last_error(#expr, _e); return OTAL_ERR_CUDA; } \
     } while (0)
 
+// cudaFuncSetAttribute (opt-in dynamic shared memory) applies to the CURRENT device only: launch wrappers remember per
+// device whether a kernel has been configured, so a process that drives several GPUs configures each of them.
+struct OncePerDevice {
+    unsigned long long done = 0;
+    // true when the current device still needs the configuration; call mark() after it succeeded
+    bool need(int* dev_out) {
+        int d = 0;
+        cudaGetDevice(&d);
+        *dev_out = d;
+        return d < 0 || d >= 64 || !((done >> d) & 1ull);
+    }
+    void mark(int d) { if (d >= 0 && d < 64) done |= 1ull << d; }
+};
+
 void set_last_error(const char* what, cudaError_t e);
 void set_last_error_msg(const char* what);
 

@@ -520,11 +520,12 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     }
 
     const size_t smem_bytes = SL.total + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static OncePerDevice once;
+    int once_dev = 0;
+    if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        once.mark(once_dev);
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     if (p.ncat) conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);

@@ -413,10 +413,11 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     if ((rc = make_tensor_map_bf16(&maps.D_hi, d_hi + d_coff, 5, ddims, dst_, box, 1))) return rc;
     if (split && (rc = make_tensor_map_bf16(&maps.D_lo, d_lo + d_coff, 5, ddims, dst_, box, 1))) return rc;
 
-    static bool configured = false;
-    if (!configured) {
+    static OncePerDevice once;
+    int once_dev = 0;
+    if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        once.mark(once_dev);
     }
     const int grid = p.total_items < wg_num_sms() ? p.total_items : wg_num_sms();
     conv_wgrad_kernel<<<grid, kWgThreads, SL.total + 1024, stream>>>(maps, p);

@@ -156,11 +156,12 @@ static int gn_setup(int B, int C, int T, int G, int nseg, const int* seg_off, co
 }
 
 static int gn_configure() {
-    static bool configured = false;
-    if (!configured) {
+    static OncePerDevice once;
+    int once_dev = 0;
+    if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(gn_relu_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         OTAL_CUDA_TRY(cudaFuncSetAttribute(gn_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
-        configured = true;
+        once.mark(once_dev);
     }
     return OTAL_OK;
 }

@@ -493,10 +493,11 @@ int otal_msl_forward(const otal_msl_desc* d, void* stream_) {
     p.loc = d->loc; p.conf = d->conf; p.ploc = d->prop_loc; p.pconf = d->prop_conf; p.center = d->center;
     p.act = d->act; p.pact = d->prop_act; p.priors = d->priors; p.targets = d->targets; p.valid = d->valid;
     p.weight_accum = d->weight_accum; p.losses = d->losses; p.ws = d->workspace;
-    static bool configured = false;
-    if (!configured) {
+    static OncePerDevice once;
+    int once_dev = 0;
+    if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(msl_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        once.mark(once_dev);
     }
     msl_forward_kernel<<<1, kMslThreads, smem, stream>>>(p);
     OTAL_CUDA_TRY(cudaGetLastError());

@@ -362,10 +362,11 @@ static int launch_pool333_tiled(const PoolParams& p, unsigned char* argmax, cuda
     tl.tilesT = (p.T + tl.tT - 1) / tl.tT; tl.tilesH = (p.H + tl.tH - 1) / tl.tH; tl.tilesW = (p.W + tl.tW - 1) / tl.tW;
     tl.cchunks = ((p.C >> 3) + 7) / 8;
     const size_t smem = (size_t)(tl.tT + 2) * (tl.tH + 2) * (tl.tW + 2) * 256;
-    static bool configured = false;
-    if (!configured) {
+    static OncePerDevice once;
+    int once_dev = 0;
+    if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(maxpool333_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
+        once.mark(once_dev);
     }
     const long long blocks = (long long)p.N * tl.tilesT * tl.tilesH * tl.tilesW * tl.cchunks;
     maxpool333_tiled_kernel<<<(unsigned)blocks, 256, smem, s>>>(p, tl, argmax);

@@ -158,10 +158,11 @@ int otal_softnms(const float* segments, long long seg_class_stride, float* score
     }
     const size_t smem = (size_t)M * 5 + 16;
     if (smem > 200 * 1024) { set_last_error_msg("softnms: more than ~40000 candidates per class do not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
-    static bool configured = false;
-    if (!configured) {
+    static OncePerDevice once;
+    int once_dev = 0;
+    if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        once.mark(once_dev);
     }
     softnms_kernel<<<C, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(segments, seg_class_stride, scores, keep, count, M, sigma,
                                                                               top_k, score_threshold);
