@@ -500,6 +500,183 @@ def window_cases():
     ns.restore_cuda()
 
 
+def dataset_case_files(root: str, seed: int = 0, n_videos: int = 4):
+    """Writes a miniature THUMOS14 tree in the reference's file formats (thumos_dataset.py:13-56,133-141; video2npy.py:61-74)
+    and returns (info csv, annotation csv, class txt, npy dir).  Deterministic in `seed`: tests regenerate the same files."""
+    import random
+    r = random.Random(7000 + seed)
+    npy = os.path.join(root, "npy")
+    os.makedirs(npy, exist_ok=True)
+    origin = [7, 9, 12, 21, 22, 23, 24, 26, 31, 33, 36, 40, 45, 51, 68, 79, 85, 92, 93, 97]
+    with open(os.path.join(root, "classes.txt"), "w") as fh:
+        for i, o in enumerate(origin):
+            fh.write(f"{o} Class{i}\n")
+    info_rows, anno_rows = [], []
+    for v in range(n_videos):
+        name = f"video_test_{seed:02d}{v:03d}"
+        sample_count = r.choice([200, 300, 345, 410])
+        count = sample_count * 3 - r.randint(0, 2)
+        info_rows.append(f"{name},30.0,10.0,{count},{sample_count}")
+        t = r.uniform(20, 90)
+        while t + 60 < count:
+            length = r.uniform(70, 330)
+            end = min(t + length, count - 3.0)
+            oi = r.choice(origin)
+            anno_rows.append(f"{name},Class,{oi},{t / 30.0:.1f},{end / 30.0:.1f},{int(t)},{int(end)}")
+            t = end + r.uniform(60, 260)
+        g = torch.Generator().manual_seed(424242 + 1000 * seed + v)
+        np.save(os.path.join(npy, name + ".npy"), torch.randint(0, 256, (sample_count, 112, 112, 3), generator=g, dtype=torch.uint8).numpy())
+    info, anno = os.path.join(root, "info.csv"), os.path.join(root, "anno.csv")
+    with open(info, "w") as fh:
+        fh.write("video,fps,sample_fps,count,sample_count\n" + "\n".join(info_rows) + "\n")
+    with open(anno, "w") as fh:
+        fh.write("video,type,type_idx,start,end,startFrame,endFrame\n" + "\n".join(anno_rows) + "\n")
+    return info, anno, os.path.join(root, "classes.txt"), npy
+
+
+def dataset_cases():
+    """The training set end to end: csv / txt / npy parsing, window index and `THUMOS_Dataset.__getitem__` of the reference
+    (thumos_dataset.py:13-56,133-275) vs opental_b200.dataset on a miniature tree, same `random` seed on both sides.  The
+    reference returns fp32 clips; ours returns the uint8 window + (crop, mirror, frame map) — `host_clip` states what the
+    ingest kernel makes of them, and must equal the reference's clips bit for bit."""
+    import importlib
+    import random
+    import tempfile
+    import zlib
+    ns = ref_loader.load_reference()
+    ds = importlib.import_module("AFSD.common.thumos_dataset")
+    from opental_b200 import dataset as D
+    out = []
+    for seed, training in ((0, True), (1, True), (2, False)):
+        with tempfile.TemporaryDirectory() as root:
+            info, anno, cls, npy = dataset_case_files(root, seed)
+            vi_r = ds.get_video_info(info)
+            va_r = ds.get_video_anno(vi_r, anno, cls)
+            vi_o = D.get_video_info(info)
+            va_o = D.get_video_anno(vi_o, anno, cls)
+            assert {k: {a: float(b) for a, b in v.items()} for k, v in vi_r.items()} == \
+                   {k: {a: float(b) for a, b in v.items()} for k, v in vi_o.items()}
+            assert {k: [list(map(float, a)) for a in v] for k, v in va_r.items()} == \
+                   {k: [list(map(float, a)) for a in v] for k, v in va_o.items()}
+            assert ds.get_class_index_map(cls) == D.get_class_index_map(cls)
+            data_r = ds.load_video_data(vi_r, npy)
+            data_o = D.load_video_data(vi_o, npy)
+            ref = ds.THUMOS_Dataset(data_r, vi_r, va_r, clip_length=256, crop_size=96, stride=30, training=training)
+            ours = D.ThumosWindows(data_o, vi_o, va_o, clip_length=256, crop_size=96, stride=30, training=training)
+            assert len(ref) == len(ours) > 0
+            samples = []
+            for idx in range(0, len(ref), max(1, len(ref) // 6)):
+                random.seed(100 * seed + idx)
+                clip, target, scores, ssl_clip, ssl_target, flag = ref[idx]
+                s = ours.sample(idx, random.Random(100 * seed + idx))
+                mine = D.host_clip(s["frames"], s["crop"], 96)
+                mine_ssl = D.host_clip(s["frames"], s["crop"], 96, s["frame_map"])
+                assert torch.equal(mine, clip) and torch.equal(mine_ssl, ssl_clip), (seed, idx)
+                assert bool(flag) == s["flag"]
+                assert np.array_equal(np.asarray(target, dtype=np.float32), s["target"])
+                assert torch.equal(scores, torch.from_numpy(s["scores"]))
+                assert np.array_equal(np.asarray(ssl_target, dtype=np.float32)[:, :2], s["ssl_target"])
+                samples.append(dict(idx=idx, rng_seed=100 * seed + idx, crop=list(map(int, s["crop"])), flag=bool(flag),
+                                    target=np.asarray(target, dtype=np.float64).tolist(),
+                                    ssl_target=np.asarray(ssl_target, dtype=np.float64).tolist(),
+                                    frame_map_crc=zlib.crc32(np.asarray(s["frame_map"], dtype=np.int32).tobytes()),
+                                    clip_crc=zlib.crc32(clip.contiguous().numpy().tobytes()),
+                                    ssl_clip_crc=zlib.crc32(ssl_clip.contiguous().numpy().tobytes()),
+                                    scores_crc=zlib.crc32(scores.contiguous().numpy().tobytes())))
+            out.append(dict(seed=seed, training=training, n_windows=len(ref),
+                            video_infos={k: {a: float(b) for a, b in v.items()} for k, v in vi_r.items()},
+                            video_annos={k: [list(map(float, a)) for a in v] for k, v in va_r.items()}, samples=samples))
+            print(f"[dataset] seed {seed} (training={training}): {len(ref)} windows, {len(samples)} samples "
+                  f"({sum(x['flag'] for x in samples)} augmented): clips, ssl clips, targets, scores identical")
+    with open(os.path.join(GOLD, "dataset_cases.json"), "w") as fh:
+        json.dump(out, fh)
+    ns.restore_cuda()
+
+
+CONFIG_CASE_YAML = """dataset:
+  num_classes: 16
+  class_info_path: ./data/open/split_{id:d}/classes.txt
+  training:
+    video_info_path: ./data/open/train_info.csv
+    video_anno_path: ./data/open/split_{id:d}/train_anno.csv
+    video_data_path: ./data/train_npy/
+    clip_length: 256
+    clip_stride: 30
+    crop_size: 96
+  testing:
+    video_info_path: ./data/open/split_{id:d}/test_info.csv
+    video_anno_path: ./data/open/split_{id:d}/test_anno.csv
+    video_data_path: ./data/test_npy/
+    crop_size: 96
+    clip_length: 256
+    clip_stride: 128
+model:
+  in_channels: 3
+  freeze_bn: true
+  freeze_bn_affine: true
+  use_edl: true
+  evidence: exp
+  dropout: 0
+  os_head: true
+  backbone_model: ./weights/i3d.pt
+training:
+  batch_size: 1
+  learning_rate: 1e-5
+  weight_decay: 1e-3
+  max_epoch: 25
+  focal_loss: false
+  edl_loss: true
+  edl_config: {evidence: exp, loss_type: log, iou_aware: true, with_ibm: true, ibm_start: 10, momentum: 0.99, num_bins: 50}
+  act_config: {margin: 1.0, weight: 0}
+  checkpoint_path: ./ckpt/split_{id:d}/
+  random_seed: 2020
+testing:
+  conf_thresh: 0.01
+  top_k: 5000
+  nms_thresh: 0.5
+  nms_sigma: 0.5
+  checkpoint_path: ./ckpt/split_{id:d}/checkpoint-latest.ckpt
+  output_path: ./output/split_{id:d}
+  output_json: detection_results.json
+"""
+CONFIG_CASE_ARGVS = [
+    [],
+    ["--open_set", "--split=0", "--lw=1", "--cw=10", "--ctw=1", "--ssl=0.001", "--piou=0.5"],
+    ["--open_set", "--split=3", "--batch_size=8", "--learning_rate=2e-5", "--max_epoch=12", "--resume=4", "--ngpu=8"],
+    ["--checkpoint_path=/tmp/ck", "--seed=7", "--nms_sigma=0.4", "--top_k=100", "--fusion", "--ood_scoring=uncertainty",
+     "--output_json=out.json", "--exp_tag=x", "--weight_decay=0.01", "--actw=0.5", "--nms_thresh=0.6"],
+]
+
+
+def config_cases():
+    """The reference's own `get_config` (AFSD/common/config.py:5-98) vs opental_b200.config.get_config on a synthetic yaml
+    with the key structure of configs/thumos14_opental_final.yaml."""
+    import importlib
+    import tempfile
+    ns = ref_loader.load_reference()
+    ref_cfg = importlib.import_module("AFSD.common.config")
+    from opental_b200 import config as C
+    out = []
+    with tempfile.TemporaryDirectory() as root:
+        path = os.path.join(root, "cfg.yaml")
+        with open(path, "w") as fh:
+            fh.write(CONFIG_CASE_YAML)
+        for argv in CONFIG_CASE_ARGVS:
+            saved = sys.argv
+            sys.argv = ["ref", path, *argv]
+            try:
+                want = ref_cfg.get_config()
+            finally:
+                sys.argv = saved
+            got = C.get_config([path, *argv])
+            assert got == want, (argv, got, want)
+            out.append(dict(argv=argv, config=want))
+            print(f"[config] argv {argv}: identical")
+    with open(os.path.join(GOLD, "config_cases.json"), "w") as fh:
+        json.dump(dict(yaml=CONFIG_CASE_YAML, cases=out), fh)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -516,6 +693,12 @@ if __name__ == "__main__":
     elif "--windows" in sys.argv:
         sys.path.insert(0, ROOT)
         window_cases()
+    elif "--config" in sys.argv:
+        sys.path.insert(0, ROOT)
+        config_cases()
+    elif "--dataset" in sys.argv:
+        sys.path.insert(0, ROOT)
+        dataset_cases()
     elif "--augment" in sys.argv:
         sys.path.insert(0, ROOT)
         augment_cases()
