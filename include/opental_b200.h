@@ -126,6 +126,18 @@ typedef struct otal_conv1a_desc {
 } otal_conv1a_desc;
 OTAL_API int otal_conv1a_fwd(const otal_conv1a_desc* desc, void* stream);
 
+/* Conv3d_1a on the RAW uint8 clip — same reference lines as otal_conv1a_fwd plus the loader's normalisation
+ * (AFSD/common/thumos_dataset.py:261-263), which is folded into the epilogue instead of being applied to the input:
+ * x_hi = the plane of otal_clip_ingest_u8_raw (pixel values 0..255, exact in bf16; x_lo is ignored), w as above.
+ * With x = (2/255) u - 1 inside the image and zero padding of x outside it (i3d_backbone.py:59-79),
+ *   conv(x, W)[p, co] = (2/255) * conv(u zero-padded, W)[p, co] - sum over the taps that lie inside the image at p of W[co,.],
+ * so `scale` = bn_scale * 2/255 and `shift` is a TABLE [4][4][4][Cout] indexed by the border class of the output position
+ * along (T, H, W) — class of index o among n outputs: 1 if o == 0, 2 if o == n-2, 3 if o == n-1, else 0 — holding
+ * bn_shift - bn_scale * (sum of the in-bounds weights of that class).  Needs nsplit = 3, even T and H, extents >= 6.
+ * One tensor-core pass u * [w_hi | w_lo] instead of two, half the activation traffic, no activation rounding error.
+ * STAGED: built and argument-checked, enabled by OTAL_U8_CONV1A=1 (opental_b200/backbone.py), not yet measured on a GPU. */
+OTAL_API int otal_conv1a_fwd_u8(const otal_conv1a_desc* desc, void* stream);
+
 /* Weight gradient — replaces the weight part of torch's convolution_backward for Unit3D / Unit1D
  *   AFSD/common/i3d_backbone.py:82 (conv3d), AFSD/common/layers.py:211 (conv1d)
  * dw[tap][co][ci] += sum_{n,p} d[n,p,co] * x[n, s*p + tap - pad, ci]; x = saved conv input planes [N,T,H,W,x_cstride],
@@ -159,6 +171,18 @@ typedef struct otal_conv1a_wgrad_desc {
     float* dw;
 } otal_conv1a_wgrad_desc;
 OTAL_API int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* desc, void* stream);
+
+/* Weight gradient of Conv3d_1a against the raw uint8 clip (x_hi = plane of otal_clip_ingest_u8_raw, x_lo ignored, nsplit = 3,
+ * Cout = 64): dw[49][Cout][32] += sum_p D[p, co] * u[p + tap] in one tensor-core pass u * [D_hi | D_lo].  The gradient of the
+ * reference's conv is (2/255) * dw - R with R[co, tap] = sum of D over the positions where the tap lies inside the image,
+ * which the caller forms from otal_border_class_sums.  STAGED like otal_conv1a_fwd_u8. */
+OTAL_API int otal_conv1a_wgrad_u8(const otal_conv1a_wgrad_desc* desc, void* stream);
+
+/* sums[(ct*4+ch)*4+cw][c] += sum over the positions of border class (ct,ch,cw) of (d_hi + d_lo)[n,t,h,w,c] — d: NDHWC bf16
+ * planes [N,To,Ho,Wo,d_cstride], channels [d_coff, d_coff + C), C a power of two in 8..128; sums: fp32 [64][C], zeroed by the
+ * caller.  Classes as in otal_conv1a_fwd_u8.  d_lo may be NULL. */
+OTAL_API int otal_border_class_sums(const uint16_t* d_hi, const uint16_t* d_lo, float* sums, int N, int To, int Ho, int Wo, int C,
+                                    int d_cstride, int d_coff, void* stream);
 
 /* MaxPool3dSamePadding on NDHWC planes — replaces AFSD/common/layers.py:9-35 (zero pad + nn.MaxPool3d).
  * Output extent = ceil(input / stride); (pt,ph,pw) = front padding of the "same" rule; padding competes as 0.
@@ -202,6 +226,11 @@ OTAL_API int otal_clip_ingest(const float* x, uint16_t* hi, uint16_t* lo, int N,
  * slice copies on a clone of the fp32 clip = a re-ordering of the clip's own frames), applied while the frames are read. */
 OTAL_API int otal_clip_ingest_u8(const unsigned char* px, const int* crop, const int* frame_map, uint16_t* hi, uint16_t* lo, int N,
                                  int T, int Hs, int Ws, int H, int W, void* stream);
+
+/* The same crop / mirror / temporal gather, but the ONE output plane holds the pixel values 0..255 (exact in bf16) instead
+ * of the normalised clip: the input of otal_conv1a_fwd_u8 / otal_conv1a_wgrad_u8. */
+OTAL_API int otal_clip_ingest_u8_raw(const unsigned char* px, const int* crop, const int* frame_map, uint16_t* out, int N, int T,
+                                     int Hs, int Ws, int H, int W, void* stream);
 
 /* Backward of relu(conv*scale+shift) w.r.t. the conv output, fused with the hi/lo split the tensor-core kernels read:
  * d = g * [y > 0] * scale[c]   (torch relu backward + frozen BatchNorm3d, AFSD/thumos14/BDNet.py:39-49).

@@ -21,6 +21,7 @@ BatchNorm is frozen and in eval mode even while training (BDNet.py:39-49): only 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -127,6 +128,9 @@ class I3DBackbone(nn.Module):
         self.crop_offsets = None          # optional int32 [N,3] device tensor (row, column, mirror) per sample
         self._parked: list = []           # (event, tensors) of blocks whose side-stream weight gradients may still run
         self.frame_map = None             # optional int32 [N,T] device tensor: temporal gather in the ingest kernel (SSL cut-paste)
+        # STAGED (off by default, not yet validated on a GPU): Conv3d_1a fwd + wgrad on the raw uint8 pixel values — one exact
+        # bf16 plane, one tensor-core pass instead of 2 (fwd) / 3 (wgrad); ops.conv1a_u8_scale_shift / conv1a_u8_weight_grad
+        self.u8_conv1a = os.environ.get("OTAL_U8_CONV1A") == "1"
         self.reset_parameters()
 
     # ------------------------------------------------------------------------------------------------ structure
@@ -279,15 +283,19 @@ class I3DBackbone(nn.Module):
             # the dataset's storage format: uint8 frames [N,T,Hs,Ws,3]; centre crop + normalisation happen in the ingest kernel
             assert x.is_cuda and x.dim() == 5 and x.shape[4] == 3, "expected CUDA uint8 frames [N,T,Hs,Ws,3]"
             W = self.crop_size
-            a = ops.clip_ingest_u8(x, W, self.crop_offsets, with_lo, frame_map=self.frame_map)
+            u8 = bool(self.u8_conv1a and with_lo and x.shape[1] % 2 == 0 and x.shape[1] >= 6 and W >= 6)
+            a = ops.clip_ingest_u8(x, W, self.crop_offsets, with_lo, frame_map=self.frame_map, raw=u8)
         else:
             assert x.is_cuda and x.dim() == 5 and x.shape[1] == 3, "expected a CUDA clip batch [N,3,T,H,W]"
             W = x.shape[4]
+            u8 = False
             a = ops.clip_ingest(x, with_lo)
-        saved["clip"] = (a, W)
+        saved["clip"] = (a, W, u8)
         r = self.convs["Conv3d_1a_7x7"]
         sc, sh = self._ss(r)
-        cur = ops.conv1a_fwd(a, self._w1a, W, scale=sc, shift=sh, relu=True)
+        if u8:
+            sc, sh = ops.conv1a_u8_scale_shift(r.unit.conv3d.weight, sc, sh)
+        cur = ops.conv1a_fwd(a, self._w1a, W, scale=sc, shift=sh, relu=True, u8=u8)
         saved["Conv3d_1a_7x7"] = cur
         for name, kind, arg in ENDPOINTS[1:]:
             if kind == "pool":
@@ -431,15 +439,18 @@ class I3DBackbone(nn.Module):
             else:  # conv1a: weight gradient only, the clip needs no gradient (train.py:165)
                 r = self.convs[name]
                 y = saved.pop(name)
-                a, W = saved.pop("clip")
+                a, W, u8 = saved.pop("clip")
                 if d_next is None:
                     sc, _ = self._ss(r)
                     d_next = ops.relu_bn_bwd_split(g, y, sc, with_lo=with_lo)
                 d, d_next = d_next, None
                 dw = torch.zeros(49, r.cout, 8 * ops.CLIP_CPAD, dtype=torch.float32, device=dev)
-                ops.conv1a_wgrad(a, d, dw, W)
+                ops.conv1a_wgrad(a, d, dw, W, u8=u8)
                 # packed layout of this block is [kt,kh,kw,Cout,Cin]; the parameter's .grad is its strided view
-                r.unit.conv3d.weight.grad.add_(ops.unpack_conv1a_wgrad(dw, r.cin))
+                if u8:
+                    r.unit.conv3d.weight.grad.add_(ops.conv1a_u8_weight_grad(dw, ops.border_class_sums(d), r.cin))
+                else:
+                    r.unit.conv3d.weight.grad.add_(ops.unpack_conv1a_wgrad(dw, r.cin))
         self._retire_all()
 
 

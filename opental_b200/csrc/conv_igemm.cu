@@ -68,6 +68,11 @@ struct ConvParams {
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
     float* out_f32;      // optional NDHWC fp32 destination (nullptr = skip)
+    int a_single;    // U8 instantiation: the A operand is ONE exact bf16 plane (raw uint8 pixel values 0..255) while B and the
+                     // output keep hi/lo planes: a*[b_hi | b_lo] is ONE N-concatenated MMA per K step (needs ncat)
+    int shift_classes;  // U8: `shift` is a table [4*4*4 border classes][Cout]; class of an output index o along a dim of n
+                     // outputs = 1 (o == 0), 2 (o == n-2), 3 (o == n-1), else 0 — which taps of a 7-tap stride-2 window fall
+                     // outside the image, where the reference pads the NORMALISED clip with 0 and the raw clip holds 0 = -1
 };
 
 struct ConvSmem {
@@ -78,11 +83,12 @@ struct ConvSmem {
 
 __host__ __device__ inline uint32_t conv_b_rows(int BN, int b_mn) { return b_mn ? (uint32_t)((BN + 63) / 64) * 64u : (uint32_t)BN; }
 
-__host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nstages, int nbuf, int b_mn, int k32 = 0) {
+__host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nstages, int nbuf, int b_mn, int k32 = 0,
+                                                      int a_single = 0) {
     ConvSmem s;
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
     const uint32_t rowb = k32 ? 64u : 128u;                        // operand row pitch in shared memory
-    s.a_bytes = kTileM * rowb * planes;
+    s.a_bytes = kTileM * rowb * (a_single ? 1u : planes);
     s.b_bytes = ((conv_b_rows(BN, b_mn) * rowb + 1023u) & ~1023u) * planes;
     s.stage_bytes = s.a_bytes + s.b_bytes;
     s.staging_off = s.stage_bytes * (uint32_t)nstages;
@@ -106,17 +112,20 @@ __device__ __forceinline__ void split_parity(int d, int s, int& q, int& par) {
     else { par = d & 1; q = (d - par) >> 1; }
 }
 
-template <bool NCAT>
+// U8 (implies NCAT): single-plane A operand + border-class shift table, see ConvParams::a_single / shift_classes.  A separate
+// instantiation, so the code of the other two is unchanged by it.
+template <bool NCAT, bool U8 = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+    static_assert(NCAT || !U8, "the single-plane A operand needs the N-concatenated weight tile");
     const CUtensorMap& mapB_hi = maps.B_hi; const CUtensorMap& mapB_lo = maps.B_lo;
     const CUtensorMap& mapO_hi = maps.O_hi; const CUtensorMap& mapO_lo = maps.O_lo;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment is required by the 128B swizzle pattern (pattern repeats every 8 rows x 128 B)
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, p.nstages, p.nbuf, p.b_mn, p.k32);
+    const ConvSmem L = conv_smem_layout(p.BN, p.nsplit, p.nstages, p.nbuf, p.b_mn, p.k32, U8 ? 1 : 0);
     const uint32_t planes_ = p.nsplit == 3 ? 2u : 1u;
-    const uint32_t a_plane = L.a_bytes / planes_;                // bytes of one A / B plane per stage
+    const uint32_t a_plane = U8 ? L.a_bytes : L.a_bytes / planes_;   // bytes of one A / B plane per stage
     const uint32_t b_plane = L.b_bytes / planes_;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + kMaxStages;
@@ -134,7 +143,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.A_hi[0]);
         tma_prefetch_desc(&mapB_hi);
-        if (split) { tma_prefetch_desc(&maps.A_lo[0]); tma_prefetch_desc(&mapB_lo); }
+        if (split) { if (!U8) tma_prefetch_desc(&maps.A_lo[0]); tma_prefetch_desc(&mapB_lo); }
         if (p.store_bf16) { tma_prefetch_desc(&mapO_hi); if (split) tma_prefetch_desc(&mapO_lo); }
     }
     if (warp == 1 && lane == 0) {
@@ -199,7 +208,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                                             tma_load_3d(&mapB_lo, &full_bar[stage], sB + b_plane + j * 8192, nb * p.BN + j * 64, c0, btap);
                                     }
                                 }
-                                if (split) tma_load_5d(mapA_lo, &full_bar[stage], sA + a_plane, c0, cw, ch, ct, n);
+                                if (split && !U8) tma_load_5d(mapA_lo, &full_bar[stage], sA + a_plane, c0, cw, ch, ct, n);
                             }
                             __syncwarp();
                             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -265,7 +274,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         const uint64_t b_hi = b_hi0 + (uint64_t)(k * b_step);
                         if constexpr (NCAT) {
                             umma_f16(d_tmem, a_hi, b_hi, idesc_cat, (it | k) != 0);          // [a_hi*b_hi | a_hi*b_lo]
-                            umma_f16(d_tmem, a_lo0 + (uint64_t)(k * 2), b_hi, idesc, 1);       // += a_lo*b_hi
+                            if constexpr (!U8) umma_f16(d_tmem, a_lo0 + (uint64_t)(k * 2), b_hi, idesc, 1);   // += a_lo*b_hi
                             continue;
                         }
                         umma_f16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
@@ -302,6 +311,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             // position of this thread's row (for the optional fp32 store)
             const int rw = row % p.tW, rh = (row / p.tW) % p.tH, rt = row / (p.tW * p.tH);
             const bool row_ok = (w0 + rw < p.W) && (h0 + rh < p.H) && (t0 + rt < p.T);
+            int shift_off = 0;                       // U8: row of the border-class shift table for this position
+            if constexpr (U8) {
+                auto cls = [](int o, int n) { return o == 0 ? 1 : (o == n - 2 ? 2 : (o == n - 1 ? 3 : 0)); };
+                shift_off = ((cls(t0 + rt, p.T) * 4 + cls(h0 + rh, p.H)) * 4 + cls(w0 + rw, p.W)) * p.Cout;
+            }
             float* orow = nullptr;
             if (p.out_f32 && row_ok) {
                 const size_t pos = ((size_t)(t0 + rt) * p.H + (h0 + rh)) * p.W + (w0 + rw);
@@ -346,7 +360,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         float sc = 1.f, sh = 0.f;
                         if (c < p.Cout) {
                             if (p.scale) sc = __ldg(p.scale + c);
-                            if (p.shift) sh = __ldg(p.shift + c);
+                            if (p.shift) sh = __ldg(p.shift + shift_off + c);
                         }
                         float x = fmaf(__uint_as_float(v[j]), sc, sh);
                         if (p.relu) x = fmaxf(x, 0.f);
@@ -474,6 +488,11 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         const uint32_t rowb = p.k32 ? 64u : 128u;
         p.ncat = (!off && split && 2 * p.BN <= kAccStride && (conv_b_rows(p.BN, p.b_mn) * rowb) % 1024u == 0 &&
                   (!p.b_mn || p.BN % 64 == 0)) ? 1 : 0;
+        if (p.a_single) {
+            // the single-plane A operand exists only in the N-concatenated form (not switchable by OTAL_NO_NCAT)
+            p.ncat = (split && 2 * p.BN <= kAccStride && (conv_b_rows(p.BN, p.b_mn) * rowb) % 1024u == 0 && !p.b_mn) ? 1 : 0;
+            if (!p.ncat) { set_last_error_msg("conv (u8): needs bf16x3 weights and Cout <= 128"); return OTAL_ERR_UNSUPPORTED; }
+        }
     }
     const int chunk = p.k32 ? 32 : kChunkK;
     p.kchunks = (L.w_k + chunk - 1) / chunk;
@@ -484,12 +503,12 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     // prefer (>= 3 stages, double-buffered staging), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
     int nst = 0, nbuf = p.store_bf16 ? 2 : 0;
     for (int s = kMaxStages; s >= 3 && !nst; --s)
-        if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn, p.k32).total <= smem_cap) nst = s;
-    if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn, p.k32).total <= smem_cap) nst = 2;
-    if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn, p.k32).total <= smem_cap) { nst = 2; nbuf = 1; }
+        if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = s;
+    if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = 2;
+    if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) { nst = 2; nbuf = 1; }
     if (!nst) { set_last_error_msg("conv: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
     p.nstages = nst; p.nbuf = nbuf;
-    const ConvSmem SL = conv_smem_layout(p.BN, p.nsplit, nst, nbuf, p.b_mn, p.k32);
+    const ConvSmem SL = conv_smem_layout(p.BN, p.nsplit, nst, nbuf, p.b_mn, p.k32, p.a_single);
 
     int rc;
     const int ntaps = p.kt * p.kh * p.kw;
@@ -525,10 +544,13 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        auto* kernel_u8 = conv_igemm_kernel<true, true>;
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         once.mark(once_dev);
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    if (p.ncat) conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    if (p.a_single) conv_igemm_kernel<true, true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    else if (p.ncat) conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
     else conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
@@ -623,9 +645,15 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
 // padding).  Operand rows are 64 bytes -> SWIZZLE_64B TMA boxes and UMMA descriptors.  T and H use the stride-2 parity
 // views with TMA zero fill as padding; W padding is physical.  (A window-expanded copy of the clip — dense TMA rows —
 // was measured: same kernel time, 4x the clip traffic; the strided map is kept.)
-int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
+static int conv1a_fwd_impl(const otal_conv1a_desc* d, void* stream_, bool u8) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d) { set_last_error_msg("conv1a: null descriptor"); return OTAL_ERR_BAD_ARG; }
+    if (u8) {
+        // raw-pixel form: one exact A plane, hi/lo weights, per-border-class shift table (see otal_conv1a_fwd_u8)
+        if (d->nsplit != 3 || !d->shift || d->T % 2 || d->H % 2 || d->T < 6 || d->H < 6 || d->W < 6) {
+            set_last_error_msg("conv1a_u8: needs nsplit 3, a shift table, even T / H and extents >= 6"); return OTAL_ERR_BAD_ARG;
+        }
+    }
     if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cout <= 0 || d->Cout % 8 || d->out_cstride % 8 || d->out_coff % 8) {
         set_last_error_msg("conv1a: bad dimension"); return OTAL_ERR_BAD_ARG;
     }
@@ -633,13 +661,14 @@ int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
     if (d->tT * d->tH * d->tW != kTileM) { set_last_error_msg("conv1a: tile box must hold 128 positions"); return OTAL_ERR_BAD_ARG; }
     if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("conv1a: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
     const bool split = d->nsplit == 3;
-    if (!d->x_hi || !d->w_hi || (split && (!d->x_lo || !d->w_lo)) || !d->y_hi || (split && !d->y_lo)) {
+    if (!d->x_hi || !d->w_hi || (split && ((!u8 && !d->x_lo) || !d->w_lo)) || !d->y_hi || (split && !d->y_lo)) {
         set_last_error_msg("conv1a: null plane"); return OTAL_ERR_BAD_ARG;
     }
     ConvLaunch L{};
     ConvParams& p = L.p;
     p.N = d->N; p.Cin = 32; p.Cout = d->Cout;
     p.k32 = 1;                                                  // 8 W taps x 4 channels = 32-element K chunks, SWIZZLE_64B
+    p.a_single = u8 ? 1 : 0; p.shift_classes = u8 ? 1 : 0;
     p.kt = 7; p.kh = 7; p.kw = 1;
     // "same" padding of k=7, s=2 on an even extent: total 5, front 2 (i3d_backbone.py:45-69)
     p.pt = (d->T % 2 == 0) ? 2 : 3; p.ph = (d->H % 2 == 0) ? 2 : 3; p.pw = 0;
@@ -668,9 +697,20 @@ int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream_) {
         const size_t off = ((size_t)rt * d->H + rh) * Wp * 4;
         const int mi = rt * 4 + rh * 2;
         if ((rc = make_tensor_map_bf16(&maps.A_hi[mi], d->x_hi + off, 5, adims, ast, abox, 2))) return rc;
-        if (split && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 2))) return rc;
+        if (split && !u8 && (rc = make_tensor_map_bf16(&maps.A_lo[mi], d->x_lo + off, 5, adims, ast, abox, 2))) return rc;
     }
     return finish_and_launch(L, maps, stream);
 }
+
+int otal_conv1a_fwd(const otal_conv1a_desc* d, void* stream) { return conv1a_fwd_impl(d, stream, false); }
+
+// Conv3d_1a on the RAW uint8 clip (otal_clip_ingest_u8_raw: pixel values 0..255, exact in ONE bf16 plane; x_lo is ignored).
+// With x = (2/255) u - 1 inside the image and the reference's zero padding of x outside it,
+//   conv(x, W)[p, co] = (2/255) * sum_taps W * u_zero-padded  -  sum_{taps inside the image at p} W,
+// so the caller passes scale = bn_scale * 2/255 and `shift` = a table [4][4][4][Cout] over the border classes of the output
+// position (ConvParams::shift_classes; entry = bn_shift - bn_scale * sum of the in-bounds weights).  One tensor-core pass
+// (u * [w_hi | w_lo], N-concatenated) instead of the two of the bf16x3 form, and half the activation fill; at least as
+// accurate (the activation operand has no rounding error at all).
+int otal_conv1a_fwd_u8(const otal_conv1a_desc* d, void* stream) { return conv1a_fwd_impl(d, stream, true); }
 
 }  // extern "C"

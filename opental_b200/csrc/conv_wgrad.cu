@@ -44,6 +44,9 @@ struct WgParams {
                               // column stride between the accumulators of consecutive taps (BN rounded up to 32)
     int nsplit, nstages;
     int total_items;
+    int x_single;             // XS instantiation (swap mode, Cout == 64): X is ONE exact bf16 plane (raw uint8 pixels) and D keeps
+                              // hi/lo; the D_lo box sits right behind the D_hi box, so ONE MMA of N = 128 computes
+                              // X * [D_hi | D_lo] into accumulator columns [0,64) and [64,128), which the epilogue adds
     float* dw;
 };
 
@@ -58,12 +61,12 @@ __device__ __forceinline__ void wg_split_parity(int d, int s, int& q, int& par) 
 }
 
 struct WgSmem { uint32_t a_bytes, b_bytes, tap_bytes, stage_bytes, bar_off, total; };
-__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages, int G, int x32 = 0) {
+__host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages, int G, int x32 = 0, int x_single = 0) {
     WgSmem s;
     const uint32_t planes = nsplit == 3 ? 2u : 1u;
     const uint32_t xbox = x32 ? kWgBox / 2 : kWgBox;          // [64 positions x 32 | 64 channels]
     s.a_bytes = 2u * kWgBox * planes;                         // 128 rows of Cout = 2 boxes
-    s.tap_bytes = (uint32_t)((BN + 63) / 64) * xbox * planes;     // X boxes of ONE tap (hi boxes of all taps come first,
+    s.tap_bytes = (uint32_t)((BN + 63) / 64) * xbox * (x_single ? 1u : planes);   // X boxes of ONE tap (hi boxes of all taps come first,
                                                                   // then the lo boxes: every plane is one run of boxes)
     s.b_bytes = s.tap_bytes * (uint32_t)G;
     s.stage_bytes = s.a_bytes + s.b_bytes;
@@ -72,11 +75,13 @@ __host__ __device__ inline WgSmem wg_smem_layout(int BN, int nsplit, int nstages
     return s;
 }
 
+// XS: single-plane X operand (WgParams::x_single), swap mode only — a separate instantiation, the default one is unchanged.
+template <bool XS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages, p.G, p.x32);
+    const WgSmem L = wg_smem_layout(p.BN, p.nsplit, p.nstages, p.G, p.x32, XS ? 1 : 0);
     const uint32_t xbox = p.x32 ? kWgBox / 2 : kWgBox;        // bytes of one X box
     const uint32_t xstep = p.x32 ? 1024u : 2048u;             // bytes of 16 K rows of X
     const uint32_t lo_off = (uint32_t)(p.G * ((p.BN + 63) / 64)) * xbox;   // lo boxes follow the hi boxes of all G taps
@@ -146,7 +151,8 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             }
             const int m_valid = min(128, p.Cout - mb * 128);
             const int a_boxes = m_valid > 64 ? 2 : 1;     // rows 64..127 of a short block are never read back
-            const uint32_t tx = ((uint32_t)a_boxes * kWgBox + (uint32_t)(gsz * nboxes_b) * xbox) * planes;
+            const uint32_t tx = XS ? (uint32_t)a_boxes * kWgBox * planes + (uint32_t)(gsz * nboxes_b) * xbox
+                                   : ((uint32_t)a_boxes * kWgBox + (uint32_t)(gsz * nboxes_b) * xbox) * planes;
             // K tile k -> (n, t, h, w) tile indices, advanced with running counters (no integer division per stage)
             int iw, ih, it, n;
             {
@@ -166,8 +172,9 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                     mbar_expect_tx(&full_bar[stage], tx);
                     for (int j = 0; j < a_boxes; ++j) {
                         tma_load_5d(&maps.D_hi, &full_bar[stage], sA + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n_cur);
-                        if (split)
-                            tma_load_5d(&maps.D_lo, &full_bar[stage], sA + 2 * kWgBox + j * kWgBox, mb * 128 + j * 64, w0, h0, t0, n_cur);
+                        if (split)   // XS: D_lo is the second 64-wide N block of the [D_hi | D_lo] operand (a_boxes == 1)
+                            tma_load_5d(&maps.D_lo, &full_bar[stage], sA + (XS ? 1 : 2) * kWgBox + j * kWgBox, mb * 128 + j * 64, w0, h0,
+                                        t0, n_cur);
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -176,7 +183,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                             for (int j = 0; j < nboxes_b; ++j) {
                                 tma_load_5d(&maps.X_hi[mi[g]], &full_bar[stage], sB + j * xbox, nb * p.BN + j * 64, w0 + qw[g],
                                             h0 + qh[g], t0 + qt[g], n_cur);
-                                if (split)
+                                if (split && !XS)
                                     tma_load_5d(&maps.X_lo[mi[g]], &full_bar[stage], sB + lo_off + j * xbox, nb * p.BN + j * 64,
                                                 w0 + qw[g], h0 + qh[g], t0 + qt[g], n_cur);
                             }
@@ -221,6 +228,10 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                             const uint64_t xa_lo = tx_ + (uint64_t)((sB + lo_off + ks * 1024) >> 4);
                             const uint64_t d_hi = a_hi0 + (uint64_t)(ks * (2048 >> 4));
                             const uint64_t d_lo = a_lo0 + (uint64_t)(ks * (2048 >> 4));
+                            if constexpr (XS) {      // X * [D_hi | D_lo]: N = 2 * 64
+                                umma_f16(d_tmem, xa_hi, d_hi, umma_idesc_bf16(128, 128, 1, 1), (k != k0 || ks != 0));
+                                continue;
+                            }
                             umma_f16(d_tmem, xa_hi, d_hi, idesc_s, (k != k0 || ks != 0));
                             if (split) {
                                 umma_f16(d_tmem, xa_lo, d_hi, idesc_s, 1);
@@ -276,7 +287,15 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                     for (int col0 = 0; col0 < p.Cout; col0 += 32) {
                         uint32_t v[32];
                         tmem_ld32(t_acc + col0, v);
-                        tmem_ld_wait();
+                        if constexpr (XS) {                  // second accumulator half: the X * D_lo products
+                            uint32_t v2[32];
+                            tmem_ld32(t_acc + 64 + col0, v2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                        } else {
+                            tmem_ld_wait();
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (col0 + j < p.Cout) atomicAdd(dst + (size_t)(col0 + j) * 32, __uint_as_float(v[j]));
@@ -366,6 +385,9 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     p.swap = (p.x32 && p.Cout <= 128 && p.Cout % 32 == 0 && p.Cin == 32) ? 1 : 0;
     p.BNs = (p.Cout + 15) / 16 * 16;
     if (p.x32 && !p.swap) { set_last_error_msg("conv1a_wgrad: Cout must be a multiple of 32 and <= 128"); return OTAL_ERR_UNSUPPORTED; }
+    if (p.x_single && !(p.swap && split && p.Cout == 64)) {
+        set_last_error_msg("conv1a_wgrad_u8: needs nsplit 3 and Cout == 64"); return OTAL_ERR_UNSUPPORTED;
+    }
     // taps per work item: as many accumulators as fit 256 TMEM columns (double buffered) and two pipeline stages of
     // shared memory (D tile + G X tiles, 16 KB per box pair in bf16x3)
     {
@@ -400,10 +422,10 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     const uint32_t smem_cap = 227 * 1024 - 1024;
     int nst = 0;
     for (int s = kWgMaxStages; s >= 2 && !nst; --s)
-        if (wg_smem_layout(p.BN, p.nsplit, s, p.G, p.x32).total <= smem_cap) nst = s;
+        if (wg_smem_layout(p.BN, p.nsplit, s, p.G, p.x32, p.x_single).total <= smem_cap) nst = s;
     if (!nst) { set_last_error_msg("wgrad: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
     p.nstages = nst;
-    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst, p.G, p.x32);
+    const WgSmem SL = wg_smem_layout(p.BN, p.nsplit, nst, p.G, p.x32, p.x_single);
 
     int rc;
     const uint32_t box[5] = {64, (uint32_t)p.tW, (uint32_t)p.tH, (uint32_t)p.tT, 1};
@@ -416,11 +438,13 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     static OncePerDevice once;
     int once_dev = 0;
     if (once.need(&once_dev)) {
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         once.mark(once_dev);
     }
     const int grid = p.total_items < wg_num_sms() ? p.total_items : wg_num_sms();
-    conv_wgrad_kernel<<<grid, kWgThreads, SL.total + 1024, stream>>>(maps, p);
+    if (p.x_single) conv_wgrad_kernel<true><<<grid, kWgThreads, SL.total + 1024, stream>>>(maps, p);
+    else conv_wgrad_kernel<false><<<grid, kWgThreads, SL.total + 1024, stream>>>(maps, p);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }
@@ -477,9 +501,10 @@ int otal_conv_wgrad(const otal_wgrad_desc* d, void* stream_) {
 }
 
 // Weight gradient of Conv3d_1a_7x7 in the folded layout of otal_conv1a_fwd: dw is [49][Cout][32] fp32.
-int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
+static int conv1a_wgrad_impl(const otal_conv1a_wgrad_desc* d, void* stream_, bool u8) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!d) { set_last_error_msg("conv1a_wgrad: null descriptor"); return OTAL_ERR_BAD_ARG; }
+    if (u8 && d->nsplit != 3) { set_last_error_msg("conv1a_wgrad_u8: needs nsplit 3 (hi/lo output-gradient planes)"); return OTAL_ERR_BAD_ARG; }
     if (d->N <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->W % 2 || d->Cout <= 0 || d->Cout % 8 ||
         d->d_cstride % 8 || d->d_coff % 8) {
         set_last_error_msg("conv1a_wgrad: bad dimension"); return OTAL_ERR_BAD_ARG;
@@ -487,11 +512,12 @@ int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
     if (d->tT * d->tH * d->tW != kWgKP) { set_last_error_msg("conv1a_wgrad: K tile box must hold 64 positions"); return OTAL_ERR_BAD_ARG; }
     if (d->nsplit != 1 && d->nsplit != 3) { set_last_error_msg("conv1a_wgrad: nsplit must be 1 or 3"); return OTAL_ERR_BAD_ARG; }
     const bool split = d->nsplit == 3;
-    if (!d->x_hi || !d->d_hi || !d->dw || (split && (!d->x_lo || !d->d_lo))) { set_last_error_msg("conv1a_wgrad: null pointer"); return OTAL_ERR_BAD_ARG; }
+    if (!d->x_hi || !d->d_hi || !d->dw || (split && ((!u8 && !d->x_lo) || !d->d_lo))) { set_last_error_msg("conv1a_wgrad: null pointer"); return OTAL_ERR_BAD_ARG; }
 
     WgParams p{};
     p.N = d->N; p.Cin = 32; p.Cout = d->Cout;
     p.x32 = 1;
+    p.x_single = u8 ? 1 : 0;
     p.To = (d->T + 1) / 2; p.Ho = (d->H + 1) / 2; p.Wo = d->W / 2;
     p.kt = 7; p.kh = 7; p.kw = 1;
     p.pt = (d->T % 2 == 0) ? 2 : 3; p.ph = (d->H % 2 == 0) ? 2 : 3; p.pw = 0;
@@ -514,9 +540,17 @@ int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream_) {
         const size_t off = ((size_t)rt * d->H + rh) * Wp * 4;
         const int mi = rt * 4 + rh * 2;
         if ((rc = make_tensor_map_bf16(&maps.X_hi[mi], d->x_hi + off, 5, xdims, xst, box, 2))) return rc;
-        if (split && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 2))) return rc;
+        if (split && !u8 && (rc = make_tensor_map_bf16(&maps.X_lo[mi], d->x_lo + off, 5, xdims, xst, box, 2))) return rc;
     }
     return wg_finish_and_launch(p, maps, d->d_hi, d->d_lo, d->d_cstride, d->d_coff, stream);
 }
+
+int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* d, void* stream) { return conv1a_wgrad_impl(d, stream, false); }
+
+// Weight gradient of Conv3d_1a against the RAW uint8 clip (one exact bf16 plane, x_lo ignored): dw += sum_p D[p] * u[p + tap]
+// in ONE tensor-core pass (u * [D_hi | D_lo]) instead of three.  The caller turns it into the gradient of the reference's
+// conv on the normalised, zero-padded clip: dW = (2/255) * dw - (sum of D over the positions where the tap is inside the
+// image) — see otal_conv1a_fwd_u8 and otal_border_class_sums.
+int otal_conv1a_wgrad_u8(const otal_conv1a_wgrad_desc* d, void* stream) { return conv1a_wgrad_impl(d, stream, true); }
 
 }  // extern "C"

@@ -218,6 +218,90 @@ __global__ void clip_ingest_u8_kernel(const unsigned char* __restrict__ px, cons
     }
 }
 
+// The raw-pixel form of clip_ingest_u8_kernel: the same crop / mirror / temporal gather, but the plane holds the uint8 pixel
+// VALUES (0..255, exact in bf16) instead of the normalised clip; zero outside the image and in channel slot 3.  The
+// normalisation (x/255)*2-1 and the reference's zero padding of the normalised clip are folded into the scale / border-class
+// shift of otal_conv1a_fwd_u8, so one plane replaces two and the tensor core sees an operand without rounding error.
+__global__ void clip_ingest_u8_raw_kernel(const unsigned char* __restrict__ px, const int* __restrict__ crop,
+                                          const int* __restrict__ frame_map, uint16_t* __restrict__ out, int N, int T, int Hs, int Ws,
+                                          int H, int W, int oh_def, int ow_def) {
+    const int Wp = W + 8;
+    const long long total = (long long)N * T * H * Wp;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int wp = (int)(i % Wp);
+        long long row = i / Wp;                       // (n*T + t)*H + h
+        const int h = (int)(row % H); row /= H;
+        const int t = (int)(row % T);
+        const int n = (int)(row / T);
+        const int w = wp - 2;
+        uint32_t v32[2] = {0, 0};
+        if (w >= 0 && w < W) {
+            const int oh = crop ? crop[3 * n] : oh_def, ow = crop ? crop[3 * n + 1] : ow_def, flip = crop ? crop[3 * n + 2] : 0;
+            const int ws = ow + (flip ? W - 1 - w : w);
+            const int ts = frame_map ? min(max(frame_map[n * T + t], 0), T - 1) : t;
+            const unsigned char* src = px + ((((size_t)n * T + ts) * Hs + (oh + h)) * Ws + ws) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)src[c])) << ((c & 1) * 16);
+        }
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(v32[0], v32[1]);
+    }
+}
+
+// Sums of an NDHWC gradient (hi + lo planes) per border class of the position and per channel: sums[(ct*4+ch)*4+cw][c] +=
+// d[n,t,h,w,c], class of an index o along a dim of n outputs = 1 (o == 0), 2 (o == n-2), 3 (o == n-1), else 0 (the classes
+// of ConvParams::shift_classes).  From these 64 x C numbers the caller forms, for every tap of the 7x7x7 stride-2 conv, the
+// sum of d over the positions where the tap lies inside the image — the term that turns the raw-pixel weight gradient
+// (otal_conv1a_wgrad_u8) into the gradient of the conv on the normalised, zero-padded clip.  One pass over d: a block owns a
+// contiguous range of positions, interior positions accumulate in registers, border positions in a shared-memory table.
+__global__ void border_class_sums_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ sums,
+                                         long long npos, int To, int Ho, int Wo, int C, int cstride, int coff, long long chunk) {
+    extern __shared__ float bcs_tab[];               // [64][C]
+    for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) bcs_tab[i] = 0.f;
+    __syncthreads();
+    const int tpp = C >> 3;                          // threads per position (8 channels = 16 bytes each)
+    const int sub = threadIdx.x % tpp, slot = threadIdx.x / tpp, pslots = blockDim.x / tpp;
+    const long long p0 = (long long)blockIdx.x * chunk;
+    const long long p1 = p0 + chunk < npos ? p0 + chunk : npos;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    auto cls = [](int o, int n) { return o == 0 ? 1 : (o == n - 2 ? 2 : (o == n - 1 ? 3 : 0)); };
+    for (long long pos = p0 + slot; pos < p1; pos += pslots) {
+        const int w = (int)(pos % Wo);
+        long long r = pos / Wo;
+        const int h = (int)(r % Ho); r /= Ho;
+        const int t = (int)(r % To);
+        const int k = (cls(t, To) * 4 + cls(h, Ho)) * 4 + cls(w, Wo);
+        const size_t off = (size_t)pos * cstride + coff + sub * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(hi + off);
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (lo) b = *reinterpret_cast<const uint4*>(lo + off);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[2 * e] = __uint_as_float(aw[e] << 16) + __uint_as_float(bw[e] << 16);
+            v[2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + __uint_as_float(bw[e] & 0xffff0000u);
+        }
+        if (k == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&bcs_tab[k * C + sub * 8 + e], v[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&bcs_tab[sub * 8 + e], acc[e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) {
+        const float v = bcs_tab[i];
+        if (v != 0.f) atomicAdd(&sums[i], v);
+    }
+}
+
 }  // namespace otal
 
 using namespace otal;
@@ -317,6 +401,37 @@ extern "C" int otal_clip_ingest_u8(const unsigned char* px, const int* crop, con
     if (N == 0) return OTAL_OK;
     otal::clip_ingest_u8_kernel<<<otal::grid_for((long long)N * T * H * (W + 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         px, crop, frame_map, hi, lo, N, T, Hs, Ws, H, W, (Hs - H) / 2, (Ws - W) / 2);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+extern "C" int otal_clip_ingest_u8_raw(const unsigned char* px, const int* crop, const int* frame_map, uint16_t* out, int N, int T,
+                                       int Hs, int Ws, int H, int W, void* stream) {
+    if (N < 0 || T <= 0 || Hs <= 0 || Ws <= 0 || H <= 0 || W <= 0 || (W & 1) || H > Hs || W > Ws || !px || !out) {
+        otal::set_last_error_msg("clip_ingest_u8_raw: bad argument (W even, crop inside the frame)"); return OTAL_ERR_BAD_ARG;
+    }
+    if (N == 0) return OTAL_OK;
+    otal::clip_ingest_u8_raw_kernel<<<otal::grid_for((long long)N * T * H * (W + 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        px, crop, frame_map, out, N, T, Hs, Ws, H, W, (Hs - H) / 2, (Ws - W) / 2);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+extern "C" int otal_border_class_sums(const uint16_t* d_hi, const uint16_t* d_lo, float* sums, int N, int To, int Ho, int Wo, int C,
+                                      int d_cstride, int d_coff, void* stream) {
+    if (N < 0 || To < 3 || Ho < 3 || Wo < 3 || C < 8 || C > 128 || (C & (C - 1)) || d_cstride % 8 || d_coff % 8 || d_coff + C > d_cstride ||
+        !d_hi || !sums) {
+        otal::set_last_error_msg("border_class_sums: bad argument (C a power of two in 8..128, extents >= 3, 16-byte aligned slices)");
+        return OTAL_ERR_BAD_ARG;
+    }
+    if (N == 0) return OTAL_OK;
+    const long long npos = (long long)N * To * Ho * Wo;
+    long long blocks = 4LL * 148;
+    const long long pslots = 256 / (C >> 3);
+    if (blocks * pslots > npos) blocks = (npos + pslots - 1) / pslots;
+    const long long chunk = (npos + blocks - 1) / blocks;
+    otal::border_class_sums_kernel<<<(unsigned)blocks, 256, (size_t)64 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        d_hi, d_lo, sums, npos, To, Ho, Wo, C, d_cstride, d_coff, chunk);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

@@ -370,10 +370,11 @@ def clip_ingest(x: torch.Tensor, with_lo: bool = True) -> Planes:
 
 
 def clip_ingest_u8(px: torch.Tensor, crop: int = 96, offsets: torch.Tensor | None = None, with_lo: bool = True,
-                   frame_map: torch.Tensor | None = None) -> Planes:
+                   frame_map: torch.Tensor | None = None, raw: bool = False) -> Planes:
     """uint8 frames [N,T,Hs,Ws,3] -> W-padded planes [N,T,crop,crop+8,4] of the normalised crop ((x/255)*2-1, bit-identical).
     offsets: optional int32 device tensor [N,3] = (row offset, column offset, mirror flag); default centre crop.
-    frame_map: optional int32 device tensor [N,T], output frame t <- source frame frame_map[n,t] (SSL cut-paste)."""
+    frame_map: optional int32 device tensor [N,T], output frame t <- source frame frame_map[n,t] (SSL cut-paste).
+    raw: ONE plane holding the pixel values 0..255 (exact in bf16) — the operand of conv1a_fwd / conv1a_wgrad with u8=True."""
     _require_cuda(px)
     assert px.dtype == torch.uint8 and px.dim() == 5 and px.shape[-1] == 3 and px.is_contiguous()
     N, T, Hs, Ws, _ = px.shape
@@ -382,6 +383,10 @@ def clip_ingest_u8(px: torch.Tensor, crop: int = 96, offsets: torch.Tensor | Non
     if frame_map is not None:
         assert frame_map.dtype == torch.int32 and frame_map.is_cuda and tuple(frame_map.shape) == (N, T) and frame_map.is_contiguous()
     hi = torch.empty((N, T, crop, crop + CLIP_WPAD, CLIP_CPAD), dtype=torch.bfloat16, device=px.device)
+    if raw:
+        _lib.call("otal_clip_ingest_u8_raw", px.data_ptr(), _ptr(offsets), _ptr(frame_map), hi.data_ptr(), N, T, Hs, Ws, crop, crop,
+                  _stream())
+        return Planes(hi, None)
     lo = torch.empty_like(hi) if with_lo else None
     _lib.call("otal_clip_ingest_u8", px.data_ptr(), _ptr(offsets), _ptr(frame_map), hi.data_ptr(), _ptr(lo), N, T, Hs, Ws, crop,
               crop, _stream())
@@ -404,11 +409,14 @@ def unpack_conv1a_wgrad(dw: torch.Tensor, C: int = 3) -> torch.Tensor:
 
 
 def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shift: torch.Tensor | None,
-               relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None) -> Planes:
+               relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None, u8: bool = False) -> Planes:
+    """u8: x is the raw-pixel plane (clip_ingest_u8(raw=True)), scale / shift come from conv1a_u8_scale_shift."""
     N, T, H, Wp_, C4 = x.hi.shape
     taps, Cout, K = w.hi.shape
     assert Wp_ == W + CLIP_WPAD and C4 == CLIP_CPAD and taps == 49 and K == CLIP_WIN * CLIP_CPAD
-    nsplit = 3 if (x.lo is not None and w.lo is not None) else 1
+    nsplit = 3 if ((x.lo is not None or u8) and w.lo is not None) else 1
+    if u8:
+        assert nsplit == 3 and shift is not None and tuple(shift.shape) == (4, 4, 4, Cout) and shift.is_contiguous()
     To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
     if out is None:
         hi = torch.empty((N, To, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.hi.device)
@@ -416,37 +424,90 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
     tT, tH, tW = pick_tile_box(To, Ho, Wo)
     d = Conv1aDesc(N=N, T=T, H=H, W=W, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit, relu=int(relu),
                    out_cstride=out.hi.shape[-1], out_coff=out_slice[0] if out_slice else 0,
-                   x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
+                   x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 and not u8 else None,
                    w_hi=w.hi.data_ptr(), w_lo=_ptr(w.lo) if nsplit == 3 else None,
                    scale=_ptr(scale), shift=_ptr(shift), y_hi=out.hi.data_ptr(),
                    y_lo=_ptr(out.lo) if nsplit == 3 else None)
     t0 = PROFILE.begin()
     if _lib.TRACE is not None:
         _lib.LABEL = (f"conv1a fwd N{N} {T}x{H}x{W} Cout{Cout} x{nsplit}", 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
-    _lib.call("otal_conv1a_fwd", ctypes.byref(d), _stream())
+    _lib.call("otal_conv1a_fwd_u8" if u8 else "otal_conv1a_fwd", ctypes.byref(d), _stream())
     PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)   # algorithmic: 3 channels, 7^3 taps
     return out
 
 
-def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[int, int] | None = None) -> None:
-    """dw [49, Cout, 32] fp32 += folded weight gradient of Conv3d_1a."""
+def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[int, int] | None = None, u8: bool = False) -> None:
+    """dw [49, Cout, 32] fp32 += folded weight gradient of Conv3d_1a.  u8: x is the raw-pixel plane and dw receives the
+    gradient against the pixel values (conv1a_u8_weight_grad turns it into the gradient of the reference's conv)."""
     N, T, H, Wp_, C4 = x.hi.shape
     taps, Cout, K = dw.shape
     assert Wp_ == W + CLIP_WPAD and C4 == CLIP_CPAD and taps == 49 and K == CLIP_WIN * CLIP_CPAD
     assert dw.dtype == torch.float32 and dw.is_contiguous()
-    nsplit = 3 if (x.lo is not None and d.lo is not None) else 1
+    nsplit = 3 if ((x.lo is not None or u8) and d.lo is not None) else 1
+    assert not u8 or nsplit == 3
     To, Ho, Wo = -(-T // 2), -(-H // 2), W // 2
     assert tuple(d.hi.shape[:4]) == (N, To, Ho, Wo)
     tT, tH, tW = pick_tile_box(To, Ho, Wo, 6)
     desc = Conv1aWgradDesc(N=N, T=T, H=H, W=W, Cout=Cout, tT=tT, tH=tH, tW=tW, nsplit=nsplit,
                            d_cstride=d.hi.shape[-1], d_coff=d_slice[0] if d_slice else 0,
-                           x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 else None,
+                           x_hi=x.hi.data_ptr(), x_lo=_ptr(x.lo) if nsplit == 3 and not u8 else None,
                            d_hi=d.hi.data_ptr(), d_lo=_ptr(d.lo) if nsplit == 3 else None, dw=dw.data_ptr())
     t0 = PROFILE.begin()
     if _lib.TRACE is not None:
         _lib.LABEL = (f"conv1a wgrad N{N} {T}x{H}x{W} Cout{Cout} x{nsplit}", 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
-    _lib.call("otal_conv1a_wgrad", ctypes.byref(desc), _stream())
+    _lib.call("otal_conv1a_wgrad_u8" if u8 else "otal_conv1a_wgrad", ctypes.byref(desc), _stream())
     PROFILE.end("conv_wgrad_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
+
+
+# ---- Conv3d_1a on raw uint8 pixels: the host-side algebra around otal_conv1a_fwd_u8 / otal_conv1a_wgrad_u8 (pure torch on
+# [Cout,3,7,7,7]-sized tensors; device-agnostic so the CPU tests can pin it against F.conv3d) -------------------------------
+U8_SCALE = 2.0 / 255.0
+
+
+def border_class_masks(device=None) -> torch.Tensor:
+    """[4 classes, 7 taps] 0/1: which taps of a 7-tap, stride-2, front-pad-2 window lie inside an even-sized image for an
+    output index of class 0 (interior), 1 (o == 0: taps 0,1 outside), 2 (o == n-2: tap 6 outside), 3 (o == n-1: taps 4..6)."""
+    m = torch.ones(4, 7, device=device)
+    m[1, :2] = 0
+    m[2, 6:] = 0
+    m[3, 4:] = 0
+    return m
+
+
+def border_classes(n: int, device=None) -> torch.Tensor:
+    """Class of every output index 0..n-1 (n >= 3)."""
+    assert n >= 3
+    c = torch.zeros(n, dtype=torch.long, device=device)
+    c[0], c[n - 2], c[n - 1] = 1, 2, 3
+    return c
+
+
+def conv1a_u8_scale_shift(w: torch.Tensor, bn_scale: torch.Tensor, bn_shift: torch.Tensor):
+    """(scale [Cout], shift table [4,4,4,Cout]) for conv1a_fwd(u8=True).  With x = (2/255) u - 1 inside the image and the
+    reference's zero padding of x outside (i3d_backbone.py:59-79): bn(conv(x, W)) = bn_scale * (2/255) * conv(u, W)
+    + bn_shift - bn_scale * S_class, S_class = sum of W over the channels and the taps that are inside the image."""
+    m = border_class_masks(w.device).to(w.dtype)
+    ws = w.detach().sum(1)                                                        # [Cout,7,7,7]
+    s = torch.einsum("othw,at,bh,cw->abco", ws, m, m, m)                          # [4,4,4,Cout]
+    return bn_scale * U8_SCALE, (bn_shift - bn_scale * s).contiguous()
+
+
+def conv1a_u8_weight_grad(dw_raw: torch.Tensor, class_sums: torch.Tensor, C: int = 3) -> torch.Tensor:
+    """dW [Cout,C,7,7,7] of the reference's conv from the raw-pixel gradient dw_raw [49,Cout,32] (conv1a_wgrad(u8=True)) and
+    the border-class sums of the output gradient [4,4,4,Cout] (border_class_sums):
+    dW[co,ci,tap] = (2/255) * sum_p D[p,co] u[p+tap,ci] - sum_{p: tap inside the image} D[p,co]."""
+    m = border_class_masks(dw_raw.device).to(dw_raw.dtype)
+    r = torch.einsum("abco,at,bh,cw->othw", class_sums, m, m, m)                  # [Cout,7,7,7]
+    return unpack_conv1a_wgrad(dw_raw, C) * U8_SCALE - r[:, None]
+
+
+def border_class_sums(d: Planes, d_slice: tuple[int, int] | None = None) -> torch.Tensor:
+    """[4,4,4,C] fp32: sums of the NDHWC gradient planes d (hi + lo) over the positions of each border class."""
+    N, To, Ho, Wo, cs = d.hi.shape
+    coff, C = d_slice if d_slice else (0, cs)
+    out = torch.zeros((4, 4, 4, C), dtype=torch.float32, device=d.hi.device)
+    _lib.call("otal_border_class_sums", d.hi.data_ptr(), _ptr(d.lo), out.data_ptr(), N, To, Ho, Wo, C, cs, coff, _stream())
+    return out
 
 
 def ncl_to_nlc_planes(x: torch.Tensor, cpad: int | None = None, *, ttot: int | None = None, dilate: int = 1,

@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU call of round 2 (run through gpurun from the repo root):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r02_first_gpu_call.sh'
+# 1. the default GPU suite (code written after round 1's GPU budget ran out: Trainer graph cache / fixed target slots,
+#    per-device kernel configuration, dataset / config modules),
+# 2. the STAGED raw-uint8 Conv3d_1a kernels: opt-in tests, micro-benchmark, A/B of the whole step,
+# 3. ncu of the two conv1a forms, 4. the synthetic-dataset training run.
+# Everything lands in gpurun_out/r02_*.
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest default rc=$?" | tee -a gpurun_out/r02_pytest_gpu.log
+OTAL_STAGED=1 python -m pytest tests/test_conv1a_u8_gpu.py -q > gpurun_out/r02_pytest_staged.log 2>&1; echo "pytest staged rc=$?" | tee -a gpurun_out/r02_pytest_staged.log
+timeout 300 python tools/conv1a_bench.py > gpurun_out/r02_conv1a_bench.txt 2>&1; echo "conv1a_bench rc=$?"
+for flag in 0 1 0 1; do
+  OTAL_U8_CONV1A=$flag timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_u8_${flag}_$RANDOM.json 2> gpurun_out/r02_bench_err.log
+  echo "bench OTAL_U8_CONV1A=$flag rc=$?"
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|border_class|clip_ingest' -c 12 \
+  -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 900 python tools/train_synthetic.py --videos 6 --epochs 12 --batch 4 --ibm-start 3 --out gpurun_out/train_synth > gpurun_out/r02_train_synth.log 2>&1
+echo "train_synthetic rc=$?"
+tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_pytest_staged.log gpurun_out/r02_conv1a_bench.txt gpurun_out/r02_train_synth.log
