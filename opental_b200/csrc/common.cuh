@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include "../../include/opental_b200.h"
 
 namespace otal {
@@ -21,15 +22,16 @@ namespace otal {
 // cudaFuncSetAttribute (opt-in dynamic shared memory) applies to the CURRENT device only: launch wrappers remember per
 // device whether a kernel has been configured, so a process that drives several GPUs configures each of them.
 struct OncePerDevice {
-    unsigned long long done = 0;
-    // true when the current device still needs the configuration; call mark() after it succeeded
+    std::atomic<unsigned long long> done{0};
+    // true when the current device still needs the configuration; call mark() after it succeeded.  Two threads that race
+    // here both configure (idempotent) and both mark: the bit set is atomic, nothing is lost.
     bool need(int* dev_out) {
         int d = 0;
         cudaGetDevice(&d);
         *dev_out = d;
-        return d < 0 || d >= 64 || !((done >> d) & 1ull);
+        return d < 0 || d >= 64 || !((done.load(std::memory_order_acquire) >> d) & 1ull);
     }
-    void mark(int d) { if (d >= 0 && d < 64) done |= 1ull << d; }
+    void mark(int d) { if (d >= 0 && d < 64) done.fetch_or(1ull << d, std::memory_order_release); }
 };
 
 void set_last_error(const char* what, cudaError_t e);
