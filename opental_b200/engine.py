@@ -216,8 +216,12 @@ class Trainer:
         the Adam launches stay outside the graph (Adam's bias correction depends on the host step counter).
         The graph bakes in `criterion.cls_loss.epoch >= ibm_start`: re-capture when the epoch crosses ibm_start."""
         import gc
-        self._stash()                                # a graph of the other flavour stays available (select_graph)
-        gc.collect()                                 # drop dead autograd graphs of earlier eager steps (see forward_backward)
+        new_ssl = ssl_clips is not None or ssl_frame_map is not None
+        if self._graph is not None and self._graph_ssl != new_ssl:
+            self._stash()                            # a graph of the OTHER flavour stays available (select_graph)
+        self._graph_cache.pop(new_ssl, None)         # a stale graph of the flavour being captured (other IBM switch, fewer
+        self._graph = self._static = self._graph_out = None   # target slots) is released before the new one takes its memory
+        gc.collect()                                 # also drops dead autograd graphs of earlier eager steps (see forward_backward)
         tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
         srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
         self._static = [torch.empty_like(t) for t in srcs]

@@ -677,6 +677,136 @@ def config_cases():
     ns.restore_cuda()
 
 
+def anet_dataset_case_files(root: str, seed: int = 0, n_videos: int = 5, clip_length: int = 768):
+    """A miniature ActivityNet tree in the reference's formats (anet_dataset.py:32-105, 226-229): video_info json + npy."""
+    import random
+    r = random.Random(9000 + seed)
+    npy = os.path.join(root, "npy")
+    os.makedirs(npy, exist_ok=True)
+    info = {}
+    for v in range(n_videos):
+        name = f"v_{seed:02d}{v:03d}"
+        frame_num = clip_length if v != 1 else 700                       # one short video: the padding path
+        annos, t = [], r.uniform(10, 120)
+        while t + 80 < frame_num:
+            length = r.uniform(60, 330)
+            end = min(t + length, frame_num - 3.0)
+            annos.append(dict(start_frame=round(t, 2), end_frame=round(end, 2), label_id=r.randint(1, 150)))
+            t = end + r.uniform(60, 260)
+        if v == 2:
+            annos.append(dict(start_frame=50.0, end_frame=50.0, label_id=3))        # dropped: end <= start
+        info[name] = dict(subset="training" if v != 3 else "validation", frame_num=frame_num, annotations=annos)
+        if v != 4:                                                                  # video 4 has no npy file: skipped
+            g = torch.Generator().manual_seed(515151 + 1000 * seed + v)
+            np.save(os.path.join(npy, name + ".npy"), torch.randint(0, 256, (frame_num, 112, 112, 3), generator=g, dtype=torch.uint8).numpy())
+    path = os.path.join(root, "video_info.json")
+    with open(path, "w") as fh:
+        json.dump(info, fh)
+    return path, npy
+
+
+def anet_dataset_cases():
+    """`ANET_Dataset` of the reference (anet_dataset.py:127-257) vs opental_b200.anet_dataset on a miniature tree, same `random`
+    seed.  numpy >= 1.24 has no `np.float` (used at :232): aliased for the duration of the run (test infrastructure only)."""
+    import importlib
+    import random
+    import tempfile
+    import zlib
+    ns = ref_loader.load_reference()
+    ds = importlib.import_module("AFSD.common.anet_dataset")
+    from opental_b200 import anet_dataset as AD
+    from opental_b200 import dataset as D
+    if not hasattr(np, "float"):
+        np.float = float
+    out = []
+    for seed, training in ((0, True), (1, True), (2, False)):
+        with tempfile.TemporaryDirectory() as root:
+            info_path, npy = anet_dataset_case_files(root, seed)
+            subset = "training" if training else "validation"
+            ref = ds.ANET_Dataset(info_path, npy, 768, 96, 768, training=training)
+            ours = AD.AnetWindows(info_path, npy, 768, 96, training=training)
+            assert ds.get_video_info(info_path, subset) == AD.get_video_info(info_path, subset)
+            assert len(ref) == len(ours) > 0 and ref.th == ours.th
+            samples = []
+            for idx in range(len(ref)):
+                a, b = ref.training_list[idx], ours.training_list[idx]
+                assert a["video_name"] == b["video_name"] and a["annos"] == b["annos"] and a["frame_num"] == b["frame_num"]
+                for k in ("start", "end", "action"):
+                    assert np.array_equal(a[k], b[k]), (seed, idx, k)
+                random.seed(100 * seed + idx)
+                clip, target, scores, ssl_clip, ssl_target, flag = ref[idx]
+                s = ours.sample(idx, random.Random(100 * seed + idx))
+                mine = D.host_clip(s["frames"], s["crop"], 96)
+                mine_ssl = D.host_clip(s["frames"], s["crop"], 96, s["frame_map"])
+                n_real = a["frame_num"]                                             # beyond: the 127.5-vs-128 padding deviation
+                assert torch.equal(mine[:, :n_real], clip[:, :n_real]), (seed, idx)
+                if n_real == 768:
+                    assert torch.equal(mine_ssl, ssl_clip), (seed, idx)
+                else:
+                    assert float((mine[:, n_real:] - clip[:, n_real:]).abs().max()) <= 1.0 / 255 + 1e-6
+                assert bool(flag) == s["flag"]
+                assert np.array_equal(np.asarray(target, dtype=np.float32), s["target"])
+                assert torch.equal(scores, torch.from_numpy(s["scores"]))
+                assert np.array_equal(np.asarray(ssl_target, dtype=np.float32)[:, :2], s["ssl_target"])
+                samples.append(dict(idx=idx, rng_seed=100 * seed + idx, crop=list(map(int, s["crop"])), flag=bool(flag), frame_num=int(n_real),
+                                    target=np.asarray(target, dtype=np.float64).tolist(),
+                                    ssl_target=np.asarray(ssl_target, dtype=np.float64).tolist(),
+                                    frame_map_crc=zlib.crc32(np.asarray(s["frame_map"], dtype=np.int32).tobytes()),
+                                    clip_crc=zlib.crc32(clip[:, :n_real].contiguous().numpy().tobytes()),
+                                    ssl_clip_crc=zlib.crc32(ssl_clip.contiguous().numpy().tobytes()) if n_real == 768 else None,
+                                    scores_crc=zlib.crc32(scores.contiguous().numpy().tobytes())))
+            out.append(dict(seed=seed, training=training, n_windows=len(ref), th=ref.th, samples=samples))
+            print(f"[anet dataset] seed {seed} (training={training}): {len(ref)} windows ({sum(x['flag'] for x in samples)} augmented): identical")
+    with open(os.path.join(GOLD, "anet_dataset_cases.json"), "w") as fh:
+        json.dump(out, fh)
+    ns.restore_cuda()
+
+
+def augment_cases_anet():
+    """The ActivityNet variant of the cut-paste augmentation (anet_dataset.py:171-221: `>=` length test, RuntimeError of a
+    mis-sized slice assignment = not augmented) — the reference's own method on a frame-index clip, as augment_cases()."""
+    import importlib
+    import random
+    import types
+    ns = ref_loader.load_reference()
+    ds = importlib.import_module("AFSD.common.anet_dataset")
+    from opental_b200 import augment as A
+    dummy = types.SimpleNamespace(clip_length=256)
+    dummy.get_bg = types.MethodType(ds.ANET_Dataset.get_bg, dummy)
+    dummy.augment_ = types.MethodType(ds.ANET_Dataset.augment_, dummy)
+    clip = torch.arange(256, dtype=torch.float32).view(1, 256, 1, 1).expand(3, 256, 2, 2).contiguous()
+    cases, n_ok, n_crash = [], 0, 0
+    for seed in range(160):
+        annos, th = augment_case_inputs(seed)
+        if seed % 3 == 0:                                   # actions of exactly 2*th frames / pastes near the clip end
+            annos = [[a[0], a[0] + 2 * th, a[2]] for a in annos[:1]] + annos[1:]
+        random.seed(seed)
+        try:
+            new_input, new_annos, flag = ds.ANET_Dataset.augment(dummy, clip, [list(a) for a in annos], th, 1)
+        except IndexError:
+            # the reference itself crashes (random.choice of an empty range when an action is exactly 2*th long, :179-180);
+            # ours must raise the same error
+            random.seed(seed)
+            try:
+                A.cut_paste([list(a) for a in annos], th, 256, 1, variant="anet")
+                raise AssertionError(f"seed {seed}: the reference raised IndexError, ours did not")
+            except IndexError:
+                n_crash += 1
+            continue
+        ref_map = new_input[0, :, 0, 0].long().tolist()
+        random.seed(seed)
+        fmap, got_annos, got_flag = A.cut_paste([list(a) for a in annos], th, 256, 1, variant="anet")
+        assert got_flag == flag and fmap.tolist() == ref_map, seed
+        assert [list(map(float, a)) for a in got_annos] == [list(map(float, a)) for a in new_annos], seed
+        n_ok += bool(flag)
+        cases.append(dict(seed=seed, annos=annos, th=th, flag=bool(flag), frame_map=ref_map,
+                          new_annos=[list(map(float, a)) for a in new_annos]))
+    print(f"[augment anet] {len(cases)} cases ({n_ok} augmented, {n_crash} seeds where reference and ours both raise IndexError)")
+    with open(os.path.join(GOLD, "augment_cases_anet.json"), "w") as fh:
+        json.dump(cases, fh)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -693,6 +823,12 @@ if __name__ == "__main__":
     elif "--windows" in sys.argv:
         sys.path.insert(0, ROOT)
         window_cases()
+    elif "--augment-anet" in sys.argv:
+        sys.path.insert(0, ROOT)
+        augment_cases_anet()
+    elif "--anet-dataset" in sys.argv:
+        sys.path.insert(0, ROOT)
+        anet_dataset_cases()
     elif "--config" in sys.argv:
         sys.path.insert(0, ROOT)
         config_cases()
