@@ -531,16 +531,20 @@ def calc_bce_loss(start, end, scores):
     if start.is_cuda and start.dtype == torch.float32 and scores.dtype == torch.float32 and scores.stride(2) == 1:
         from . import ops
         return ops.boundary_bce(start, scores[:, 0]), ops.boundary_bce(end, scores[:, 1])
+    def bce(p, y):
+        # F.binary_cross_entropy's arithmetic (logs clamped at -100) without its target-range check: the ActivityNet maps hold
+        # class ids as targets, which torch 1.9 accepted and torch 2.x rejects on the CPU
+        return -(y * torch.log(p).clamp(min=-100.0) + (1.0 - y) * torch.log(1.0 - p).clamp(min=-100.0)).mean()
     s = torch.tanh(start).mean(-1)
     e = torch.tanh(end).mean(-1)
-    return (F.binary_cross_entropy(s.view(-1), scores[:, 0].contiguous().view(-1), reduction="mean"),
-            F.binary_cross_entropy(e.view(-1), scores[:, 1].contiguous().view(-1), reduction="mean"))
+    return bce(s.view(-1), scores[:, 0].contiguous().view(-1)), bce(e.view(-1), scores[:, 1].contiguous().view(-1))
 
 
 def training_cost(output_dict, losses, scores, *, lw=1.0, cw=10.0, ctw=1.0, actw=1.0, score_scale=4):
     """Total cost of one (non-SSL) training step (thumos14/train.py:186-200, 226-235; anet/train.py:168-190 with the
     score maps down-sampled by 8 = score_scale)."""
     loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act = losses
+    scores = scores[:, -2:]      # the ActivityNet loader's maps are (action, start, end): rows 1, 2 are used (anet/train.py:134-143)
     ls, le = calc_bce_loss(output_dict["start"], output_dict["end"], scores)
     sc = F.interpolate(scores, scale_factor=1.0 / score_scale)
     a, b = calc_bce_loss(output_dict["start_loc_prop"], output_dict["end_loc_prop"], sc)

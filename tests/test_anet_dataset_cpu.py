@@ -85,3 +85,39 @@ def test_anet_variant_accepts_actions_of_exactly_twice_the_threshold():
     assert A.cut_paste(annos, 8, 256, 1, rng=random.Random(0))[2] is False
     with pytest.raises(IndexError):
         A.cut_paste(annos, 8, 256, 1, rng=random.Random(0), variant="anet")
+
+
+def test_training_cost_reads_start_end_rows_of_the_three_row_score_maps():
+    """anet/train.py:134-143, 168-190: BCE targets are scores[:, 1] / scores[:, 2] (class ids, App. D7), down-sampled by 8 for the
+    proposal-level maps."""
+    import torch.nn.functional as F
+    from opental_b200.multisegment_loss import training_cost
+    g = torch.Generator().manual_seed(0)
+    B, T = 2, 64
+    out = {k: torch.rand(B, T if k in ("start", "end") else T // 8, 16, generator=g)          # post-ReLU features: tanh >= 0
+           for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop")}
+    scores = torch.zeros(B, 3, T)
+    scores[:, 0, 10:40] = 7.0
+    scores[:, 1, 8:13] = 7.0
+    scores[:, 2, 37:43] = 7.0
+    losses = tuple(torch.tensor(float(i + 1)) for i in range(7))
+    cost, ls, le = training_cost(out, losses, scores, score_scale=8)
+
+    def bce(x, y):          # F.binary_cross_entropy's formula; torch 2.x rejects targets > 1 on the CPU, torch 1.9 (the reference's) did not
+        p, y = torch.tanh(x).mean(-1).view(-1).double(), y.contiguous().view(-1).double()
+        return (-(y * torch.log(p).clamp(min=-100) + (1 - y) * torch.log(1 - p).clamp(min=-100)).mean()).float()
+    sc = F.interpolate(scores, scale_factor=1.0 / 8)
+    want_ls = bce(out["start"], scores[:, 1]) + 0.1 * (bce(out["start_loc_prop"], sc[:, 1]) + bce(out["start_conf_prop"], sc[:, 1]))
+    want_le = bce(out["end"], scores[:, 2]) + 0.1 * (bce(out["end_loc_prop"], sc[:, 2]) + bce(out["end_conf_prop"], sc[:, 2]))
+    assert torch.allclose(ls, want_ls, rtol=1e-5) and torch.allclose(le, want_le, rtol=1e-5)
+    # with {0,1} targets the formula is torch's own BCE
+    z = torch.rand(4, 9, 5, generator=g)
+    y01 = (torch.rand(4, 2, 9, generator=g) > 0.5).float()
+    from opental_b200.multisegment_loss import calc_bce_loss
+    a, b = calc_bce_loss(z, z * 0.5, y01)
+    assert torch.allclose(a, F.binary_cross_entropy(torch.tanh(z).mean(-1), y01[:, 0]), rtol=1e-6)
+    assert torch.allclose(b, F.binary_cross_entropy(torch.tanh(z * 0.5).mean(-1), y01[:, 1]), rtol=1e-6)
+    assert torch.allclose(cost, 1 * 1.0 + 10 * 2.0 + 1 * 3.0 + 10 * 4.0 + 1 * 5.0 + want_ls + want_le + 6.0 + 7.0)
+    # two-row (THUMOS14) maps are used as they are
+    c2, ls2, le2 = training_cost(out, losses, scores[:, 1:].contiguous(), score_scale=8)
+    assert torch.equal(ls2, ls) and torch.equal(le2, le)
