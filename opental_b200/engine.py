@@ -96,8 +96,11 @@ def shard_indices(num_items: int, rank: int, world: int) -> range:
 
 class Trainer:
     def __init__(self, net: BDNet, criterion: MultiSegmentLoss, *, lr=1e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, ssl_weight=0.001, process_group=None):
+                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, ssl_weight=0.001, process_group=None, backbone_lr_scale=1.0):
+        """backbone_lr_scale: learning rate of the backbone group relative to `lr` — anet/train.py:303-310 trains the backbone
+        at 0.1 x the head's rate; thumos14/train.py:321-323 uses one rate (1.0)."""
         self.net, self.criterion = net, criterion
+        self.backbone_lr_scale = float(backbone_lr_scale)
         self.lw, self.cw, self.ctw, self.actw, self.ssl_weight = lw, cw, ctw, actw, ssl_weight
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg = process_group
@@ -314,8 +317,9 @@ class Trainer:
             self.reducer.wait()
             self._head_launched = False
         self.step_count += 1
-        for (w, g), st in zip(self.groups, self.state):
-            ops.adam_step(w, g, st["m"], st["v"], lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
+        for gi, ((w, g), st) in enumerate(zip(self.groups, self.state)):      # group 0 = the backbone's flat buffer
+            lr = self.lr * self.backbone_lr_scale if gi == 0 else self.lr
+            ops.adam_step(w, g, st["m"], st["v"], lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
                           grad_scale=self.reducer.grad_scale, step=self.step_count)
         return cost, losses, ls, le
 
