@@ -57,6 +57,34 @@ def test_bad_arguments_return_codes_without_gpu():
         assert lib.otal_clip_ingest_u8(*args) == -1 and "clip_ingest_u8" in _lib.last_error()
 
 
+def test_staged_u8_entry_points_validate_arguments_without_gpu():
+    """otal_conv1a_fwd_u8 / otal_conv1a_wgrad_u8 / otal_clip_ingest_u8_raw / otal_border_class_sums: every rejection below
+    happens before the first CUDA call."""
+    from opental_b200 import _lib
+    lib = _lib.load()
+    for name in ("otal_conv1a_fwd_u8", "otal_conv1a_wgrad_u8"):
+        assert getattr(lib, name)(None, None) == -1 and "null descriptor" in _lib.last_error(), name
+    P = 4096        # never dereferenced
+    ok = dict(N=1, T=8, H=8, W=16, Cout=64, tT=4, tH=4, tW=8, nsplit=3, relu=1, out_cstride=64, out_coff=0, x_hi=P, x_lo=None,
+              w_hi=P, w_lo=P, scale=P, shift=P, y_hi=P, y_lo=P)
+    for bad, msg in ((dict(nsplit=1), "conv1a_u8"), (dict(shift=None), "conv1a_u8"), (dict(T=7), "conv1a_u8"), (dict(H=4), "conv1a_u8"),
+                     (dict(w_lo=None), "null plane"), (dict(tW=4), "128 positions")):
+        d = _lib.Conv1aDesc(**{**ok, **bad})
+        assert lib.otal_conv1a_fwd_u8(ctypes.byref(d), None) == -1 and msg in _lib.last_error(), (bad, _lib.last_error())
+    okw = dict(N=1, T=8, H=16, W=16, Cout=64, tT=1, tH=8, tW=8, nsplit=3, d_cstride=64, d_coff=0, x_hi=P, x_lo=None, d_hi=P, d_lo=P, dw=P)
+    for bad, msg in ((dict(nsplit=1), "conv1a_wgrad_u8"), (dict(d_lo=None), "null pointer"), (dict(tW=4), "64 positions")):
+        d = _lib.Conv1aWgradDesc(**{**okw, **bad})
+        assert lib.otal_conv1a_wgrad_u8(ctypes.byref(d), None) == -1 and msg in _lib.last_error(), (bad, _lib.last_error())
+    # raw ingest: odd crop width / null output;   class sums: C not a power of two, extent < 3, misaligned slice
+    assert lib.otal_clip_ingest_u8_raw(P, None, None, P, 1, 4, 8, 8, 6, 5, None) == -1 and "clip_ingest_u8_raw" in _lib.last_error()
+    assert lib.otal_clip_ingest_u8_raw(P, None, None, None, 1, 4, 8, 8, 6, 6, None) == -1
+    assert lib.otal_clip_ingest_u8_raw(P, None, None, P, 0, 4, 8, 8, 6, 6, None) == 0          # empty batch
+    for args in ((P, P, P, 1, 4, 4, 4, 48, 48, 0, None), (P, P, P, 1, 2, 4, 4, 64, 64, 0, None), (P, P, P, 1, 4, 4, 4, 64, 64, 4, None),
+                 (P, P, None, 1, 4, 4, 4, 64, 64, 0, None)):
+        assert lib.otal_border_class_sums(*args) == -1 and "border_class_sums" in _lib.last_error(), args
+    assert lib.otal_border_class_sums(P, None, P, 0, 4, 4, 4, 64, 64, 0, None) == 0
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
