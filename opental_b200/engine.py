@@ -219,11 +219,7 @@ class Trainer:
         the Adam launches stay outside the graph (Adam's bias correction depends on the host step counter).
         The graph bakes in `criterion.cls_loss.epoch >= ibm_start`: re-capture when the epoch crosses ibm_start."""
         import gc
-        new_ssl = ssl_clips is not None or ssl_frame_map is not None
-        if self._graph is not None and self._graph_ssl != new_ssl:
-            self._stash()                            # a graph of the OTHER flavour stays available (select_graph)
-        self._graph_cache.pop(new_ssl, None)         # a stale graph of the flavour being captured (other IBM switch, fewer
-        self._graph = self._static = self._graph_out = None   # target slots) is released before the new one takes its memory
+        self._release_for_capture(ssl_clips is not None or ssl_frame_map is not None)
         gc.collect()                                 # also drops dead autograd graphs of earlier eager steps (see forward_backward)
         tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
         srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
@@ -251,6 +247,15 @@ class Trainer:
             self._capturing = False
         self._graph_epoch_flag = self._ibm_flag()
         self._graph_ssl = ssl_clips is not None or ssl_frame_map is not None
+
+    def _release_for_capture(self, new_ssl: bool) -> None:
+        """Graph bookkeeping at the start of capture(): a current graph of the OTHER flavour is kept for select_graph; a graph
+        of the flavour being captured — current or cached, i.e. one with the other IBM switch or too few target slots — is
+        released before the new one takes its memory."""
+        if self._graph is not None and self._graph_ssl != new_ssl:
+            self._stash()
+        self._graph_cache.pop(new_ssl, None)
+        self._graph = self._static = self._graph_out = None
 
     @staticmethod
     def _max_segments(targets) -> int:

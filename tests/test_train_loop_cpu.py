@@ -131,3 +131,46 @@ def test_fit_world_size_2_rank0_writes_checkpoints_and_logs(tmp_path):
     assert r0["steps"] == r1["steps"] == [5] * 11
     assert [s[0] for s in r0["saved"]] == [11] and r1["saved"] == []
     assert r0["logs"] == 11 and r1["logs"] == 0
+
+
+def test_trainer_graph_cache_bookkeeping():
+    """Trainer.select_graph / graph_matches / _release_for_capture without a GPU: the methods only move (graph, static buffers,
+    outputs, IBM flag) tuples around, so stand-in objects are enough.  One graph per flavour (with / without the SSL pass);
+    a flavour's graph is dropped when it is re-captured; IBM switch and target slots gate the reuse."""
+    import types
+    from opental_b200.engine import Trainer
+    tr = Trainer.__new__(Trainer)
+    tr._graph, tr._graph_ssl, tr._graph_cache, tr._static, tr._graph_out, tr.target_slots = None, False, {}, None, None, 8
+    cls = types.SimpleNamespace(with_ibm=True, epoch=1, ibm_start=3)
+    tr.criterion = types.SimpleNamespace(cls_loss=cls)
+
+    def fake_capture(ssl, slots=8):                      # what capture() leaves behind
+        tr._release_for_capture(ssl)
+        tr._graph = object()
+        tr._static = [None, torch.zeros(2, slots, 3)] + ([None] * (4 if ssl else 2))
+        tr._graph_out, tr._graph_epoch_flag, tr._graph_ssl = ("out", ssl), tr._ibm_flag(), ssl
+        return tr._graph
+
+    tg2 = [torch.zeros(2, 3), torch.zeros(1, 3)]
+    tg9 = [torch.zeros(9, 3), torch.zeros(1, 3)]
+    assert not tr.select_graph(False, tg2)               # nothing captured yet
+    g_plain = fake_capture(False)
+    assert tr.select_graph(False, tg2) and tr._graph is g_plain
+    assert not tr.select_graph(True, tg2)                # other flavour: capture needed ...
+    g_ssl = fake_capture(True)
+    assert tr._graph is g_ssl and tr._graph_cache[False][0] is g_plain          # ... and the plain graph is kept
+    assert tr.select_graph(False, tg2) and tr._graph is g_plain and tr._graph_out == ("out", False)
+    assert tr._graph_cache[True][0] is g_ssl
+    assert tr.select_graph(True, tg2) and tr._graph is g_ssl                   # alternating batches: no re-capture
+    assert not tr.select_graph(True, tg9)                # 9 segments > 8 slots
+    assert tr.graph_matches(True, tg2) and not tr.graph_matches(True, tg9) and tr.graph_matches(True)
+    g_ssl9 = fake_capture(True, slots=9)
+    assert tr._graph is g_ssl9 and True not in tr._graph_cache                 # the 8-slot SSL graph is gone, not cached
+    assert tr.select_graph(True, tg9) and tr.select_graph(False, tg2) and tr._graph is g_plain
+    cls.epoch = 3                                        # the IBM switch flips: neither graph fits any more
+    assert not tr.select_graph(False, tg2) and not tr.select_graph(True, tg2)
+    g_plain_ibm = fake_capture(False)
+    assert tr._graph is g_plain_ibm and tr._graph_cache.get(False) is None     # stale plain graph released
+    assert tr._graph_cache[True][0] is g_ssl9 and not tr.select_graph(True, tg9)   # cached SSL graph has the old switch
+    # an already padded (tensor, mask) pair carries its own geometry: compared by step(), accepted here
+    assert tr.select_graph(False, (torch.zeros(2, 8, 3), torch.zeros(2, 8, dtype=torch.bool)))
