@@ -94,13 +94,56 @@ def shard_indices(num_items: int, rank: int, world: int) -> range:
     return range(rank * per, (rank + 1) * per)
 
 
+def global_normaliser_factors(counts: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """f = max(n_rank, 1) * world / max(sum over ranks of n_rank, 1), elementwise, for the raw counts (#positives, #refined
+    positives, #actionness samples ...) a rank's loss terms were normalised by.  `term_rank * f` summed over ranks and divided
+    by world — which is what the gradient all-reduce + the 1/world factor of the Adam kernel do — is the term normalised by the
+    BATCH-GLOBAL count, i.e. the reference's value at batch = world x per-rank batch (multisegment_loss.py:243-254).  One
+    all-reduce of a handful of floats."""
+    total = counts.clone()
+    if world > 1:
+        dist.all_reduce(total, group=group)
+    return counts.clamp(min=1) * float(world) / total.clamp(min=1)
+
+
+def globalise_losses(losses, stats: torch.Tensor, factors: torch.Tensor, iouc_live: torch.Tensor | None = None):
+    """Re-weight the 7 THUMOS14 loss terms of one rank from per-rank to batch-global normalisers.
+    stats = MultiSegmentLoss.last_stats (#pos, #refined pos, AN, PAN, loss_iouc), factors = global_normaliser_factors(stats[:4]).
+    loss_prop_c = A / PN + iouc mixes a count-normalised part with a plain mean over all priors (the IoU calibration, a mean of
+    per-rank means is already global): only A / PN is re-weighted.  With `iouc_live` (the calibration term recomputed with
+    autograd) the gradient is exact as well; without it the calibration term's gradient carries the factor f_PN (~1)."""
+    l, c, pl, pc, ct, act, pact = losses
+    fN, fPN, fAN, fPAN = factors.unbind(0)
+    iouc = stats[4].detach()
+    pc2 = pc * fPN + (1.0 - fPN) * (iouc_live if iouc_live is not None else iouc)
+    return (l * fN, c * fN, pl * fPN, pc2, ct * fN, act * fAN if act is not None else None,
+            pact * fPAN if pact is not None else None)
+
+
+def live_iou_calibration(crit, out, targets):
+    """The IoU-calibration term of loss_prop_c (multisegment_loss.py:233-238, cls_loss.py:120-129) recomputed with autograd —
+    the fused loss kernel only returns its value — so that globalise_losses can keep its gradient at weight 1.  None when the
+    loss has no such term."""
+    if not getattr(crit, "iou_aware", False):
+        return None
+    tgt, valid = pad_targets(targets, out["loc"].device)
+    iou = crit.match(out["loc"].detach(), out["priors"], tgt, valid)[4]
+    K = out["prop_conf"].shape[-1]
+    return crit.cls_loss.iou_calib(out["prop_conf"].reshape(-1, K), iou.t().reshape(-1), mean=True)
+
+
 class Trainer:
     def __init__(self, net: BDNet, criterion: MultiSegmentLoss, *, lr=1e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, ssl_weight=0.001, process_group=None, backbone_lr_scale=1.0):
+                 lw=1.0, cw=10.0, ctw=1.0, actw=1.0, ssl_weight=0.001, process_group=None, backbone_lr_scale=1.0,
+                 global_normalisers=False):
         """backbone_lr_scale: learning rate of the backbone group relative to `lr` — anet/train.py:303-310 trains the backbone
-        at 0.1 x the head's rate; thumos14/train.py:321-323 uses one rate (1.0)."""
+        at 0.1 x the head's rate; thumos14/train.py:321-323 uses one rate (1.0).
+        global_normalisers (THUMOS14 loss, world > 1; off by default): normalise the loss terms by the batch-GLOBAL counts of
+        positives instead of each rank's own — one all-reduce of 4 floats between the loss and the backward.
+        The actionness top-M selection and the IBM EMA stay per rank (§8e (2), (3))."""
         self.net, self.criterion = net, criterion
         self.backbone_lr_scale = float(backbone_lr_scale)
+        self.global_normalisers = bool(global_normalisers)
         self.lw, self.cw, self.ctw, self.actw, self.ssl_weight = lw, cw, ctw, actw, ssl_weight
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg = process_group
@@ -175,6 +218,8 @@ class Trainer:
                                     targets)
         else:
             losses = self.criterion(out, targets)
+            if self.global_normalisers and self.world > 1:
+                losses = self._globalise(out, losses, targets)
         cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw,
                                      score_scale=8 if anet else 4)
         if ssl_clips is not None or ssl_frame_map is not None:
@@ -195,6 +240,14 @@ class Trainer:
         # detached: a caller holding a non-detached loss would keep this step's autograd graph (and its AccumulateGrad
         # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture
         return cost.detach(), tuple(l.detach() if l is not None else None for l in losses), ls.detach(), le.detach()
+
+    def _globalise(self, out, losses, targets):
+        crit = self.criterion
+        stats = crit.last_stats.detach()
+        if stats.numel() >= 12:              # the fused kernel's 16-float vector: counts and loss_iouc sit at [7:12]
+            stats = stats[7:12]
+        factors = global_normaliser_factors(stats[:4].detach().clone(), self.world, self.pg)
+        return globalise_losses(losses, stats, factors, live_iou_calibration(crit, out, targets))
 
     # ---------------------------------------------------------------------------------------------- CUDA graph
     @staticmethod

@@ -356,7 +356,7 @@ class MultiSegmentLoss(nn.Module):
                        act_weight=float(self.act_loss.weight), act_margin=float(self.act_loss.margin))
             vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P), pact.reshape(B, P),
                                            priors, tgt, valid, c.weight_accum if c.with_ibm else None, cfg)
-            self.last_stats = stats        # N, PN, AN, PAN, loss_iouc at [7:12] (device; for logging)
+            self.last_stats = stats        # raw counts #pos, #refined pos, AN, PAN and loss_iouc at [7:12] (device; logging, engine._globalise)
             return tuple(vec.unbind(0))
         loc_t, conf_t, prop_loc_t, prop_conf_t, iou = self.match(loc.detach(), priors, tgt, valid)
         pos, ppos = conf_t > 0, prop_conf_t > 0
@@ -406,6 +406,10 @@ class MultiSegmentLoss(nn.Module):
         if self.os_head and not self.size_average:
             loss_act = loss_act / AN.clamp(min=1)
             loss_prop_act = loss_prop_act / PAN.clamp(min=1)
+        with torch.no_grad():          # the same five numbers the fused kernel reports (engine.globalise_losses reads them)
+            f = lambda v: torch.as_tensor(v, dtype=loc.dtype, device=loc.device).reshape(())   # noqa: E731
+            self.last_stats = torch.stack([f(pos.sum()), f(ppos.sum()), f(AN) if self.os_head else f(0.0),
+                                           f(PAN) if self.os_head else f(0.0), f(loss_iouc) if self.iou_aware else f(0.0)])
         return loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act
 
 

@@ -97,3 +97,102 @@ def test_bench_reference_arm_under_torchrun_world2():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "clips/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def _globalise_worker(rank, world, port, out_dir):
+    """Each rank: the THUMOS14 loss (torch formulation, CPU) on its half of a 4-clip batch, re-weighted to batch-global
+    normalisers; saves its terms and the gradients w.r.t. its own head outputs."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from opental_b200.engine import global_normaliser_factors, globalise_losses
+    out, targets, crit = _globalise_case()
+    sl = slice(2 * rank, 2 * rank + 2)
+    mine = {k: (v[sl].detach().clone().requires_grad_(True) if k != "priors" else v) for k, v in out.items()}
+    losses = crit(mine, targets[sl])
+    stats = crit.last_stats
+    factors = global_normaliser_factors(stats[:4].clone(), world)
+    g = globalise_losses(losses, stats, factors)
+    cost = g[0] + 10 * g[1] + g[2] + 10 * g[3] + g[4]
+    cost.backward()
+    torch.save(dict(terms=[float(t) for t in g[:5]], counts=stats[:2].tolist(), factors=factors.tolist(),
+                    grads={k: v.grad.clone() for k, v in mine.items() if k != "priors" and v.grad is not None}),
+               os.path.join(out_dir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _globalise_case():
+    import opental_oracle as O
+    from opental_b200.multisegment_loss import MultiSegmentLoss
+    g = torch.Generator().manual_seed(11)
+    B, P, K = 4, 126, 15
+    priors = O.make_priors() if hasattr(O, "make_priors") else None
+    if priors is None:
+        centers = torch.cat([(torch.arange(t) + 0.5) / t for t in (64, 32, 16, 8, 4, 2)])
+        priors = centers.view(-1, 1)
+    out = dict(loc=torch.rand(B, P, 2, generator=g) * 40 + 2, conf=torch.randn(B, P, K, generator=g),
+               prop_loc=torch.randn(B, P, 2, generator=g) * 0.1, prop_conf=torch.randn(B, P, K, generator=g),
+               center=torch.randn(B, P, 1, generator=g), act=torch.randn(B, P, 1, generator=g), prop_act=torch.randn(B, P, 1, generator=g),
+               priors=priors.float())
+    # very different numbers of positives per rank: clips 0, 1 carry short actions, clips 2, 3 long ones
+    targets = [torch.tensor([[0.10, 0.16, 3.0]]), torch.tensor([[0.70, 0.74, 5.0]]),
+               torch.tensor([[0.05, 0.60, 7.0], [0.62, 0.98, 2.0]]), torch.tensor([[0.20, 0.95, 9.0]])]
+    edl = dict(evidence="exp", loss_type="log", with_ibm=False, iou_aware=False, num_bins=50, momentum=0.99, ibm_start=10)
+    crit = MultiSegmentLoss(K, 0.5, 1.0, cls_loss_type="edl", edl_config=edl, os_head=True, act_config=dict(margin=1.0, weight=0))
+    crit.cls_loss.epoch = 1
+    crit.fused = False
+    return out, targets, crit
+
+
+def test_global_normalisers_reproduce_the_single_process_batch(tmp_path):
+    """with the per-rank terms re-weighted by max(n_r,1) * world / max(sum n_r,1), the mean over ranks of every
+    count-normalised loss term equals the term of the whole batch on one process, and each rank's input gradients are world x
+    the whole-batch gradients of its clips — so the summing all-reduce + Adam's 1/world give exactly the single-process update."""
+    world, port = 2, _free_port()
+    mp.spawn(_globalise_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f"g{k}.pt") for k in range(world)]
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    out, targets, crit = _globalise_case()
+    full = {k: (v.detach().clone().requires_grad_(True) if k != "priors" else v) for k, v in out.items()}
+    losses = crit(full, targets)
+    cost = losses[0] + 10 * losses[1] + losses[2] + 10 * losses[3] + losses[4]
+    cost.backward()
+    assert r[0]["counts"] != r[1]["counts"] and abs(r[0]["factors"][0] - 1.0) > 0.2          # the ranks really are unbalanced
+    for i in range(5):
+        got = sum(x["terms"][i] for x in r) / world
+        assert abs(got - float(losses[i])) <= 1e-5 * max(1.0, abs(float(losses[i]))), (i, got, float(losses[i]))
+    for k in ("loc", "conf", "prop_loc", "prop_conf", "center"):
+        for rank in range(world):
+            want = full[k].grad[2 * rank: 2 * rank + 2] * world
+            got = r[rank]["grads"][k]
+            assert torch.allclose(got, want, rtol=1e-4, atol=1e-7), (k, rank, float((got - want).abs().max()))
+    # without the re-weighting the per-rank mean is NOT the batch value (this is the documented default)
+    plain = [float(crit({k: (v[2 * q: 2 * q + 2] if k != "priors" else v) for k, v in out.items()}, targets[2 * q: 2 * q + 2])[0]) for q in range(2)]
+    assert abs(sum(plain) / 2 - float(losses[0])) > 1e-3
+
+
+def test_live_iou_calibration_is_the_term_inside_loss_prop_c():
+    """engine.live_iou_calibration == the loss's own calibration value (last_stats[4]); globalise_losses re-weights only the
+    count-normalised part of loss_prop_c and leaves the calibration term (value and gradient) at weight 1."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from opental_b200.engine import globalise_losses, live_iou_calibration
+    out, targets, crit = _globalise_case()
+    crit.iou_aware = crit.cls_loss.iou_aware = True
+    live = {k: (v.detach().clone().requires_grad_(True) if k != "priors" else v) for k, v in out.items()}
+    losses = crit(live, targets)
+    stats = crit.last_stats
+    iouc = live_iou_calibration(crit, live, targets)
+    assert float(stats[4]) > 0 and torch.allclose(iouc, stats[4], rtol=1e-6)
+    factors = torch.tensor([0.5, 2.0, 1.0, 1.0])
+    g = globalise_losses(losses, stats, factors, iouc)
+    a_over_pn = losses[3] - iouc
+    assert torch.allclose(g[3], a_over_pn * 2.0 + iouc, rtol=1e-6)
+    (gr,) = torch.autograd.grad(g[3], live["prop_conf"], retain_graph=True)
+    (ga,) = torch.autograd.grad(a_over_pn, live["prop_conf"], retain_graph=True)
+    (gi,) = torch.autograd.grad(iouc, live["prop_conf"], retain_graph=True)
+    assert torch.allclose(gr, 2.0 * ga + gi, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(g[0], losses[0] * 0.5) and torch.allclose(g[2], losses[2] * 2.0)
+    crit.iou_aware = False
+    assert live_iou_calibration(crit, live, targets) is None
