@@ -17,6 +17,11 @@ for flag in 0 1 0 1; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|border_class|clip_ingest' -c 12 \
   -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu rc=$?"
+# where the step goes now, per layer (event-timed eager pass), and a source-level look at the HBM-bound 1x1 convs, which run
+# at ~22 % of the copy roofline (profiles/r01_ncu_full_kernels_summary_v2.txt ids 8-10: Mixed_3c.b0 fwd / dgrad / wgrad)
+timeout 600 python tools/step_profile.py > gpurun_out/r02_step_profile.txt 2>&1; echo "step_profile rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm' -s 5 -c 2 \
+  -o gpurun_out/r02_conv1x1 python tools/ncu_targets.py > gpurun_out/r02_conv1x1_ncu.log 2>&1; echo "ncu 1x1 rc=$?"
 timeout 900 python tools/train_synthetic.py --videos 6 --epochs 12 --batch 4 --ibm-start 3 --out gpurun_out/train_synth > gpurun_out/r02_train_synth.log 2>&1
 echo "train_synthetic rc=$?"
 tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_pytest_staged.log gpurun_out/r02_conv1a_bench.txt gpurun_out/r02_train_synth.log
