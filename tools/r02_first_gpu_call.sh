@@ -17,6 +17,13 @@ for flag in 0 1 0 1; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|border_class|clip_ingest' -c 12 \
   -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu rc=$?"
+# pipeline-depth switch for the 2-stage shapes (3 stages + 1 staging buffer instead of 2 + 2)
+for flag in 0 1 0 1; do
+  if [ $flag = 1 ]; then export OTAL_CONV_PREFER_STAGES=1; else unset OTAL_CONV_PREFER_STAGES; fi
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_stages_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
+  echo "bench OTAL_CONV_PREFER_STAGES=$flag rc=$?"
+done
+unset OTAL_CONV_PREFER_STAGES
 # where the step goes now, per layer (event-timed eager pass), and a source-level look at the HBM-bound 1x1 convs, which run
 # at ~22 % of the copy roofline (profiles/r01_ncu_full_kernels_summary_v2.txt ids 8-10: Mixed_3c.b0 fwd / dgrad / wgrad)
 timeout 600 python tools/step_profile.py > gpurun_out/r02_step_profile.txt 2>&1; echo "step_profile rc=$?"
