@@ -483,6 +483,16 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         }
     }
     {
+        // STAGED switch (OTAL_CONV_1X1_BN64=1, default off, to be A/B-measured): 64-wide N blocks for the large 1x1 convs — a
+        // 48 KB stage instead of 64..96 KB, i.e. 3-4 loads in flight per SM; the second N block's A tile comes from L2 (tiles of
+        // one position block are consecutive, so they run side by side on neighbouring CTAs).  DESIGN §9.4.
+        static const bool bn64 = getenv("OTAL_CONV_1X1_BN64") != nullptr;
+        const int m_tiles = p.N * p.tilesT * p.tilesH * p.tilesW;
+        if (bn64 && p.kt * p.kh * p.kw == 1 && L.w2_k == 0 && p.BN > 64 && p.Cout % 64 == 0 && m_tiles >= 4 * num_sms()) {
+            p.BN = 64; p.n_blocks = p.Cout / 64;
+        }
+    }
+    {
         // N-concatenated hi|lo weights (see ConvParams::ncat): needs 2*BN accumulator columns and B_lo contiguous after B_hi
         static const bool off = getenv("OTAL_NO_NCAT") != nullptr;
         const uint32_t rowb = p.k32 ? 64u : 128u;
