@@ -22,6 +22,7 @@ import torch.distributed as dist  # noqa: E402
 
 from opental_b200 import anet_dataset as AD, config as C, dataset as D, engine, train_loop  # noqa: E402
 from opental_b200.bdnet import BDNet  # noqa: E402
+from opental_b200.loader import Prefetcher  # noqa: E402
 from opental_b200.multisegment_loss import MultiSegmentLossANet  # noqa: E402
 
 
@@ -29,6 +30,7 @@ def main(argv=None) -> int:
     parser = C.build_parser()
     parser.add_argument("--no_graph", action="store_true")
     parser.add_argument("--log_json", type=str, default=None)
+    parser.add_argument("--loader_threads", type=int, default=4)
     args = parser.parse_args(argv)
     cfg = C.get_config(argv, parser)
     tr_cfg, ds_cfg, model = cfg["training"], cfg["dataset"]["training"], cfg["model"]
@@ -58,9 +60,10 @@ def main(argv=None) -> int:
     net.backbone.crop_offsets = torch.zeros(batch, 3, dtype=torch.int32, device=dev)
 
     def make_batches(epoch):
-        for b in D.epoch_batches(ds, batch, epoch, rank=rank, world=world, device=dev, seed=seed, crop_offsets=net.backbone.crop_offsets):
-            b.pop("ssl_frame_map"), b.pop("ssl_targets")
-            yield b
+        # loader threads -> pinned ring -> copy stream (opental_b200/loader.py); the ingest kernel reads the crop / mirror
+        # decisions from the static tensor below, so a captured step graph sees every update
+        return Prefetcher(ds, batch, epoch, rank=rank, world=world, seed=seed, device=dev, workers=args.loader_threads,
+                          crop_offsets=net.backbone.crop_offsets, ssl=False)
 
     ck = tr_cfg["checkpoint_path"]
     st = os.path.join(ck, "training")

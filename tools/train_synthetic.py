@@ -1,6 +1,6 @@
 """End-to-end training on a synthetic dataset: the loader-side pieces (window index, score maps, cut-paste frame maps, random
 crop / mirror offsets) feeding `train_loop.fit` exactly as a THUMOS14 run would (AFSD/thumos14/train.py), on one or more
-GPUs.  A development / validation tool (the benchmark is bench.py):
+GPUs, through the product loader (opental_b200/dataset.py + loader.py).  A development / validation tool (the benchmark is bench.py):
 
     python tools/train_synthetic.py --videos 6 --epochs 12 --batch 4 --ibm-start 3 --out gpurun_out/train_synth
     torchrun --nproc-per-node 2 tools/train_synthetic.py ...
@@ -18,7 +18,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from opental_b200 import augment, engine, train_loop, windows  # noqa: E402
+from opental_b200 import dataset, engine, loader, train_loop  # noqa: E402
 
 
 def synthetic_dataset(n_videos: int, seed: int = 0):
@@ -36,7 +36,7 @@ def synthetic_dataset(n_videos: int, seed: int = 0):
             t += length + r.uniform(25, 90)
         annos[name] = segs or [[10.0, 80.0, 1]]
         g = torch.Generator().manual_seed(1000 + v)
-        data[name] = torch.randint(0, 256, (count, 112, 112, 3), generator=g, dtype=torch.uint8)
+        data[name] = torch.randint(0, 256, (count, 112, 112, 3), generator=g, dtype=torch.uint8).numpy()
     return infos, annos, data
 
 
@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--ibm-start", type=int, default=3)
     ap.add_argument("--resume", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--loader-threads", type=int, default=4)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "train_synth"))
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -57,9 +58,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     clip_length, crop = 256, 96
     infos, annos, data = synthetic_dataset(args.videos)
-    index, th = windows.split_videos(infos, annos, clip_length, stride=30)
+    ds = dataset.ThumosWindows(data, infos, annos, clip_length=clip_length, crop_size=crop, stride=30, training=True)
     if rank == 0:
-        print(f"{len(index)} windows from {args.videos} videos; cut-paste thresholds {sorted(th.values())}")
+        print(f"{len(ds)} windows from {args.videos} videos; cut-paste thresholds {sorted(ds.th.values())}")
 
     torch.manual_seed(0)
     net, crit = engine.build_opental(device=dev, epoch=1)
@@ -73,29 +74,9 @@ def main():
     tr.capture = lambda *a, **k: (captures.append((crit.cls_loss.epoch, sorted(k))), capture(*a, **k))[1]
 
     def make_batches(epoch):
-        rng = random.Random(100 * epoch)                       # the same shuffle on every rank, sharded below
-        order = list(range(len(index)))
-        rng.shuffle(order)
-        per_step = args.batch * world
-        for s in range(len(order) // per_step):                # drop_last=True (train.py:353)
-            mine = order[s * per_step + rank * args.batch: s * per_step + (rank + 1) * args.batch]
-            clips, tgts, scores, maps, ssl_t, flags, offs = [], [], [], [], [], [], []
-            for i in mine:
-                w = index[i]
-                frames = data[w["video_name"]][w["offset"]: w["offset"] + clip_length]
-                if frames.shape[0] < clip_length:               # zero padding of a short video (thumos_dataset.py:247-251)
-                    frames = torch.cat([frames, frames.new_zeros(clip_length - frames.shape[0], *frames.shape[1:])])
-                clips.append(frames)
-                tgts.append(torch.tensor(windows.annos_transform(w["annos"], clip_length), dtype=torch.float32))
-                scores.append(torch.from_numpy(np.stack([w["start"], w["end"]])).float())
-                fmap, new_annos, flag = augment.cut_paste(w["annos"], th[w["video_name"]], clip_length, 1, rng=rng)
-                maps.append(torch.from_numpy(fmap))
-                ssl_t.append(torch.tensor([a[:2] for a in new_annos][:3] if flag else [[0, 1], [1, 2], [2, 3]], dtype=torch.float32))
-                flags.append(flag)
-                offs.append([rng.randrange(112 - crop + 1), rng.randrange(112 - crop + 1), rng.randrange(2)])
-            net.backbone.crop_offsets.copy_(torch.tensor(offs, dtype=torch.int32))
-            yield dict(clips=torch.stack(clips).to(dev), targets=tgts, scores=torch.stack(scores).to(dev),
-                       flags=flags, ssl_targets=[t.to(dev) for t in ssl_t], ssl_frame_map=torch.stack(maps).to(dev))
+        # the product's loader: window index -> loader threads -> pinned ring -> copy stream (opental_b200/loader.py)
+        return loader.Prefetcher(ds, args.batch, epoch, rank=rank, world=world, seed=0, device=dev, workers=args.loader_threads,
+                                 crop_offsets=net.backbone.crop_offsets)
 
     ck, st = os.path.join(args.out, "checkpoint"), os.path.join(args.out, "train_state")
     hist = train_loop.fit(tr, make_batches, max_epoch=args.epochs, resume=args.resume, checkpoint_path=ck, train_state_path=st,

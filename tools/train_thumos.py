@@ -25,6 +25,7 @@ import torch.distributed as dist  # noqa: E402
 
 from opental_b200 import config as C, dataset as D, engine, train_loop  # noqa: E402
 from opental_b200.bdnet import BDNet  # noqa: E402
+from opental_b200.loader import Prefetcher  # noqa: E402
 from opental_b200.multisegment_loss import MultiSegmentLoss  # noqa: E402
 
 
@@ -33,6 +34,7 @@ def main(argv=None) -> int:
     parser.add_argument("--script_compat", action="store_true", help="cls_loss_type exactly as thumos14/train.py:27-31 computes it")
     parser.add_argument("--no_graph", action="store_true", help="eager steps instead of CUDA-graph replay")
     parser.add_argument("--log_json", type=str, default=None)
+    parser.add_argument("--loader_threads", type=int, default=4)
     args = parser.parse_args(argv)
     cfg = C.get_config(argv, parser)
     tr_cfg, ds_cfg = cfg["training"], cfg["dataset"]["training"]
@@ -68,10 +70,10 @@ def main(argv=None) -> int:
     ssl_on = tr_cfg["ssl"] > 0
 
     def make_batches(epoch):
-        for b in D.epoch_batches(ds, batch, epoch, rank=rank, world=world, device=dev, seed=seed, crop_offsets=net.backbone.crop_offsets):
-            if not ssl_on:
-                b.pop("ssl_frame_map"), b.pop("ssl_targets")
-            yield b
+        # loader threads -> pinned ring -> copy stream (opental_b200/loader.py); the ingest kernel reads the crop / mirror
+        # decisions from the static tensor below, so a captured step graph sees every update
+        return Prefetcher(ds, batch, epoch, rank=rank, world=world, seed=seed, device=dev, workers=args.loader_threads,
+                          crop_offsets=net.backbone.crop_offsets, ssl=ssl_on)
 
     ck = tr_cfg["checkpoint_path"]
     st = os.path.join(ck, "training")                                                    # train.py:37
