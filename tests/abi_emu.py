@@ -1,0 +1,328 @@
+"""A CPU stand-in for the BACKBONE entry points of libopental_b200.so  —  TEST INFRASTRUCTURE (never imported by the product).
+
+`install(monkeypatch)` replaces `opental_b200._lib.call` by a dispatcher that implements, with torch CPU ops on the host
+memory behind the raw pointers, what include/opental_b200.h says each entry point does (NDHWC bf16 hi/lo planes, channel
+slices of wider rows, tap-major weights, fused BN/ReLU epilogue, data-gradient mode, second K segment, arg-max recording
+pools, the fused pool / ReLU / BN backward, clip ingest, the folded Conv3d_1a and its staged raw-uint8 form).  With it the
+product's HOST code — opental_b200/backbone.py's forward and explicit backward schedule and the descriptor building in
+opental_b200/ops.py — runs on a CPU-only box and can be compared with the oracle's I3D (tests/test_backbone_emulated_cpu.py).
+Arithmetic: planes are read as hi + lo in fp32, the contraction runs in fp32 (torch), results are split back into planes —
+the accuracy class of the bf16x3 kernels.  Nothing here is a fallback: the product still raises without a CUDA device."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def _view(ptr, n: int, np_dtype) -> torch.Tensor | None:
+    """Flat torch view of n elements of host memory at `ptr` (shares storage)."""
+    if not ptr:
+        return None
+    ptr = ptr.value if isinstance(ptr, ctypes.c_void_p) else int(ptr)
+    buf = (ctypes.c_char * (n * np.dtype(np_dtype).itemsize)).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=np_dtype))
+
+
+def _bf16(ptr, n):          # bf16 plane as an int16 view; .view(torch.bfloat16) reinterprets
+    v = _view(ptr, n, np.int16)
+    return None if v is None else v.view(torch.bfloat16)
+
+
+def _load(hi_ptr, lo_ptr, shape, coff, C) -> torch.Tensor:
+    """fp32 [.., C] = (hi + lo)[..., coff:coff+C] of planes with rows of shape[-1] channels."""
+    n = int(np.prod(shape))
+    x = _bf16(hi_ptr, n).view(*shape)[..., coff:coff + C].float()
+    if lo_ptr:
+        x = x + _bf16(lo_ptr, n).view(*shape)[..., coff:coff + C].float()
+    return x
+
+
+def _store(x: torch.Tensor, hi_ptr, lo_ptr, shape, coff) -> None:
+    n = int(np.prod(shape))
+    C = x.shape[-1]
+    hi = x.bfloat16()
+    _bf16(hi_ptr, n).view(*shape)[..., coff:coff + C] = hi
+    if lo_ptr:
+        _bf16(lo_ptr, n).view(*shape)[..., coff:coff + C] = (x - hi.float()).bfloat16()
+
+
+def _out(n, s):
+    return -(-n // s)
+
+
+def _conv(x, w, stride, pad_front):
+    """x [N,T,H,W,Cin] fp32, w [Cout,Cin,kt,kh,kw]; output extent ceil(in / stride), implicit zero padding behind."""
+    xin = x.permute(0, 4, 1, 2, 3)
+    k = w.shape[2:]
+    pads = []
+    for dim in (2, 1, 0):                                           # F.pad order: W, H, T
+        n, s, kk, pf = xin.shape[2 + dim], stride[dim], k[dim], pad_front[dim]
+        back = max((_out(n, s) - 1) * s + kk - n - pf, 0)
+        pads += [pf, back]
+    y = F.conv3d(F.pad(xin, pads), w, stride=stride)
+    return y[:, :, :_out(x.shape[1], stride[0]), :_out(x.shape[2], stride[1]), :_out(x.shape[3], stride[2])].permute(0, 2, 3, 4, 1)
+
+
+class Emulator:
+    def __init__(self):
+        self.calls: dict[str, int] = {}
+
+    def __call__(self, name: str, *args) -> None:
+        self.calls[name] = self.calls.get(name, 0) + 1
+        fn = getattr(self, name, None)
+        if fn is None:
+            raise NotImplementedError(f"abi_emu: {name} is not emulated (backbone entry points only)")
+        fn(*args)
+
+    # ---------------------------------------------------------------------------------------------- layout kernels
+    def otal_split_bf16(self, x, hi, lo, n, stream):
+        v = _view(x, n, np.float32)
+        _store(v.view(n, 1), hi, lo, (n, 1), 0)
+
+    def otal_clip_ingest(self, x, hi, lo, N, C, T, H, W, stream):
+        v = _view(x, N * C * T * H * W, np.float32).view(N, C, T, H, W)
+        out = torch.zeros(N, T, H, W + 8, 4)
+        out[:, :, :, 2:W + 2, :C] = v.permute(0, 2, 3, 4, 1)
+        _store(out, hi, lo, (N, T, H, W + 8, 4), 0)
+
+    def _ingest_pixels(self, px, crop, fmap, N, T, Hs, Ws, H, W):
+        p = _view(px, N * T * Hs * Ws * 3, np.uint8).view(N, T, Hs, Ws, 3)
+        cr = _view(crop, N * 3, np.int32).view(N, 3) if crop else None
+        fm = _view(fmap, N * T, np.int32).view(N, T) if fmap else None
+        out = torch.zeros(N, T, H, W, 3)
+        for n in range(N):
+            oh, ow, flip = (int(v) for v in cr[n]) if cr is not None else ((Hs - H) // 2, (Ws - W) // 2, 0)
+            src = p[n] if fm is None else p[n][fm[n].long().clamp(0, T - 1)]
+            win = src[:, oh:oh + H, ow:ow + W, :].float()
+            out[n] = win.flip(2) if flip else win
+        return out
+
+    def otal_clip_ingest_u8(self, px, crop, fmap, hi, lo, N, T, Hs, Ws, H, W, stream):
+        u = self._ingest_pixels(px, crop, fmap, N, T, Hs, Ws, H, W)
+        out = torch.zeros(N, T, H, W + 8, 4)
+        out[:, :, :, 2:W + 2, :3] = (u / 255.0) * 2.0 - 1.0
+        _store(out, hi, lo, (N, T, H, W + 8, 4), 0)
+
+    def otal_clip_ingest_u8_raw(self, px, crop, fmap, out_ptr, N, T, Hs, Ws, H, W, stream):
+        out = torch.zeros(N, T, H, W + 8, 4)
+        out[:, :, :, 2:W + 2, :3] = self._ingest_pixels(px, crop, fmap, N, T, Hs, Ws, H, W)
+        _store(out, out_ptr, None, (N, T, H, W + 8, 4), 0)
+
+    # ---------------------------------------------------------------------------------------------- Conv3d_1a (folded)
+    @staticmethod
+    def _w1a(d, Cout):
+        """[Cout,3,7,7,7] from the folded planes [49][Cout][32] (element dw*4 + c)."""
+        w = _load(d.w_hi, d.w_lo, (49, Cout, 32), 0, 32).view(7, 7, Cout, 8, 4)
+        return w[:, :, :, :7, :3].permute(2, 4, 0, 1, 3).contiguous()
+
+    @staticmethod
+    def _classes(n):
+        c = torch.zeros(n, dtype=torch.long)
+        c[0], c[n - 2], c[n - 1] = 1, 2, 3
+        return c
+
+    def _conv1a_fwd(self, desc, u8):
+        d = desc._obj
+        N, T, H, W, Cout = d.N, d.T, d.H, d.W, d.Cout
+        x = _load(d.x_hi, None if u8 else d.x_lo, (N, T, H, W + 8, 4), 0, 4)[:, :, :, 2:W + 2, :3]
+        pf = tuple(2 if n % 2 == 0 else 3 for n in (T, H, W))
+        y = _conv(x, self._w1a(d, Cout), (2, 2, 2), pf)
+        To, Ho, Wo = y.shape[1:4]
+        sc = _view(d.scale, Cout, np.float32) if d.scale else torch.ones(Cout)
+        if u8:
+            tab = _view(d.shift, 64 * Cout, np.float32).view(4, 4, 4, Cout)
+            sh = tab[self._classes(To)][:, self._classes(Ho)][:, :, self._classes(Wo)]            # [To,Ho,Wo,Cout]
+        else:
+            sh = _view(d.shift, Cout, np.float32) if d.shift else torch.zeros(Cout)
+        y = y * sc + sh
+        if d.relu:
+            y = y.relu()
+        _store(y, d.y_hi, d.y_lo, (N, To, Ho, Wo, d.out_cstride), d.out_coff)
+
+    def otal_conv1a_fwd(self, desc, stream):
+        self._conv1a_fwd(desc, False)
+
+    def otal_conv1a_fwd_u8(self, desc, stream):
+        self._conv1a_fwd(desc, True)
+
+    def _conv1a_wgrad(self, desc, u8):
+        d = desc._obj
+        N, T, H, W, Cout = d.N, d.T, d.H, d.W, d.Cout
+        To, Ho, Wo = _out(T, 2), _out(H, 2), W // 2
+        x = _load(d.x_hi, None if u8 else d.x_lo, (N, T, H, W + 8, 4), 0, 4)[:, :, :, :, :]        # padded rows, 4 slots
+        g = _load(d.d_hi, d.d_lo, (N, To, Ho, Wo, d.d_cstride), d.d_coff, Cout)
+        # gradient against the folded weights: window of 8 pixels x 4 slots starting at padded column 2*w'
+        w = torch.zeros(Cout, 4, 7, 7, 8, requires_grad=True)
+        xin = x.permute(0, 4, 1, 2, 3)                                                            # [N,4,T,H,W+8]
+        pf_t, pf_h = (2 if T % 2 == 0 else 3), (2 if H % 2 == 0 else 3)
+        bt = max((To - 1) * 2 + 7 - T - pf_t, 0)
+        bh = max((Ho - 1) * 2 + 7 - H - pf_h, 0)
+        with torch.enable_grad():          # the product calls this from inside an autograd backward
+            y = F.conv3d(F.pad(xin, [0, 0, pf_h, bh, pf_t, bt]), w, stride=2)[:, :, :To, :Ho, :Wo]
+            (gw,) = torch.autograd.grad(y, w, g.permute(0, 4, 1, 2, 3))
+        dw = _view(d.dw, 49 * Cout * 32, np.float32).view(7, 7, Cout, 8, 4)
+        dw += gw.permute(2, 3, 0, 4, 1)
+
+    def otal_conv1a_wgrad(self, desc, stream):
+        self._conv1a_wgrad(desc, False)
+
+    def otal_conv1a_wgrad_u8(self, desc, stream):
+        self._conv1a_wgrad(desc, True)
+
+    def otal_border_class_sums(self, d_hi, d_lo, sums, N, To, Ho, Wo, C, cstride, coff, stream):
+        g = _load(d_hi, d_lo, (N, To, Ho, Wo, cstride), coff, C).sum(0)
+        out = _view(sums, 64 * C, np.float32).view(4, 4, 4, C)
+        ct, ch, cw = self._classes(To), self._classes(Ho), self._classes(Wo)
+        for a in range(4):
+            for b in range(4):
+                for c in range(4):
+                    sel = (ct == a)[:, None, None] & (ch == b)[None, :, None] & (cw == c)[None, None, :]
+                    if sel.any():
+                        out[a, b, c] += g[sel].sum(0)
+
+    # ---------------------------------------------------------------------------------------------- generic conv
+    def otal_conv_igemm_fwd(self, desc, stream):
+        d = desc._obj
+        N, T, H, W, Cin, Cout = d.N, d.T, d.H, d.W, d.Cin, d.Cout
+        k = (d.kt, d.kh, d.kw)
+        taps = k[0] * k[1] * k[2]
+        st = tuple(s or 1 for s in (d.sT, d.sH, d.sW))
+        x = _load(d.x_hi, d.x_lo if d.nsplit == 3 else None, (N, T, H, W, d.in_cstride), d.in_coff, Cin)
+        lo = d.w_lo if d.nsplit == 3 else None
+        if d.dgrad:
+            # w = FORWARD weights [taps][Cin (= fwd Cout)][Cout (= fwd Cin)], used transposed with flipped taps
+            wf = _load(d.w_hi, lo, (taps, Cin, Cout), 0, Cout).view(*k, Cin, Cout)
+            w = wf.flip(0, 1, 2).permute(4, 3, 0, 1, 2).contiguous()
+        else:
+            w = _load(d.w_hi, lo, (taps, Cout, Cin), 0, Cin).view(*k, Cout, Cin).permute(3, 4, 0, 1, 2).contiguous()
+        y = _conv(x, w, st, (d.pt, d.ph, d.pw))
+        if d.Cin2 > 0:
+            x2 = _load(d.x2_hi, d.x2_lo if d.nsplit == 3 else None, (N, T, H, W, d.in2_cstride), d.in2_coff, d.Cin2)
+            lo2 = d.w2_lo if d.nsplit == 3 else None
+            w2 = (_load(d.w2_hi, lo2, (1, d.Cin2, Cout), 0, Cout)[0].t() if d.dgrad else _load(d.w2_hi, lo2, (1, Cout, d.Cin2), 0, d.Cin2)[0])
+            y = y + x2 @ w2.t()
+        To, Ho, Wo = y.shape[1:4]
+        if d.scale:
+            y = y * _view(d.scale, Cout, np.float32)
+        if d.shift:
+            y = y + _view(d.shift, Cout, np.float32)
+        if d.relu:
+            y = y.relu()
+        if d.y_hi:
+            _store(y, d.y_hi, d.y_lo if d.nsplit == 3 else None, (N, To, Ho, Wo, d.out_cstride), d.out_coff)
+        if d.y_f32:
+            if d.y_f32_ncdhw:
+                dst = _view(d.y_f32, N * d.out_cstride * To * Ho * Wo, np.float32).view(N, d.out_cstride, To, Ho, Wo)
+                sl = dst[:, d.out_coff:d.out_coff + Cout]
+                yv = y.permute(0, 4, 1, 2, 3)
+            else:
+                dst = _view(d.y_f32, N * To * Ho * Wo * d.out_cstride, np.float32).view(N, To, Ho, Wo, d.out_cstride)
+                sl = dst[..., d.out_coff:d.out_coff + Cout]
+                yv = y
+            if d.accumulate:
+                sl += yv
+            else:
+                sl.copy_(yv)
+
+    def otal_conv_wgrad(self, desc, stream):
+        d = desc._obj
+        N, T, H, W, Cin, Cout = d.N, d.T, d.H, d.W, d.Cin, d.Cout
+        k = (d.kt, d.kh, d.kw)
+        st = tuple(s or 1 for s in (d.sT, d.sH, d.sW))
+        To, Ho, Wo = (_out(n, s) for n, s in zip((T, H, W), st))
+        split = d.nsplit == 3
+        x = _load(d.x_hi, d.x_lo if split else None, (N, T, H, W, d.x_cstride), d.x_coff, Cin)
+        g = _load(d.d_hi, d.d_lo if split else None, (N, To, Ho, Wo, d.d_cstride), d.d_coff, Cout)
+        w = torch.zeros(Cout, Cin, *k, requires_grad=True)
+        with torch.enable_grad():
+            (gw,) = torch.autograd.grad(_conv(x, w, st, (d.pt, d.ph, d.pw)), w, g)
+        dw = _view(d.dw, k[0] * k[1] * k[2] * Cout * Cin, np.float32).view(*k, Cout, Cin)
+        dw += gw.permute(2, 3, 4, 0, 1)
+
+    # ---------------------------------------------------------------------------------------------- pools, ReLU / BN backward
+    @staticmethod
+    def _pool_geometry(d):
+        k, s, pf = (d.kt, d.kh, d.kw), (d.st, d.sh, d.sw), (d.pt, d.ph, d.pw)
+        ext = (d.T, d.H, d.W)
+        out = tuple(_out(n, ss) for n, ss in zip(ext, s))
+        back = tuple(max((o - 1) * ss + kk - n - p, 0) for o, ss, kk, n, p in zip(out, s, k, ext, pf))
+        return k, s, pf, ext, out, back
+
+    def otal_maxpool_fwd(self, desc, stream):
+        d = desc._obj
+        k, s, pf, (T, H, W), (To, Ho, Wo), back = self._pool_geometry(d)
+        x = _load(d.x_hi, d.x_lo, (d.N, T, H, W, d.in_cstride), d.in_coff, d.C).permute(0, 4, 1, 2, 3)
+        xp = F.pad(x, [pf[2], back[2], pf[1], back[1], pf[0], back[0]])                 # zero padding competes as 0
+        y, idx = F.max_pool3d(xp, k, s, return_indices=True)
+        y, idx = y[:, :, :To, :Ho, :Wo], idx[:, :, :To, :Ho, :Wo]
+        _store(y.permute(0, 2, 3, 4, 1), d.y_hi, d.y_lo, (d.N, To, Ho, Wo, d.out_cstride), d.out_coff)
+        if d.argmax:
+            Hp, Wp = xp.shape[3], xp.shape[4]
+            it, ih, iw = idx // (Hp * Wp), (idx // Wp) % Hp, idx % Wp
+            ot = torch.arange(To).view(1, 1, -1, 1, 1) * s[0]
+            oh = torch.arange(Ho).view(1, 1, 1, -1, 1) * s[1]
+            ow = torch.arange(Wo).view(1, 1, 1, 1, -1) * s[2]
+            tap = ((it - ot) * k[1] + (ih - oh)) * k[2] + (iw - ow)                     # window-relative, < 27
+            _view(d.argmax, d.N * To * Ho * Wo * d.C, np.uint8).view(d.N, To, Ho, Wo, d.C).copy_(tap.permute(0, 2, 3, 4, 1).to(torch.uint8))
+
+    def _pool_scatter(self, d, g_out):
+        """fp32 [N,T,H,W,C]: g_out routed to the recorded arg-max positions (padding positions drop their gradient)."""
+        k, s, pf, (T, H, W), (To, Ho, Wo), back = self._pool_geometry(d)
+        assert d.argmax, "abi_emu: pool backward is emulated through the recorded arg-max only"
+        tap = _view(d.argmax, d.N * To * Ho * Wo * d.C, np.uint8).view(d.N, To, Ho, Wo, d.C).long()
+        dt, dh, dw = tap // (k[1] * k[2]), (tap // k[2]) % k[1], tap % k[2]
+        t = torch.arange(To).view(1, -1, 1, 1, 1) * s[0] + dt - pf[0]
+        h = torch.arange(Ho).view(1, 1, -1, 1, 1) * s[1] + dh - pf[1]
+        w = torch.arange(Wo).view(1, 1, 1, -1, 1) * s[2] + dw - pf[2]
+        ok = (t >= 0) & (t < T) & (h >= 0) & (h < H) & (w >= 0) & (w < W)
+        n = torch.arange(d.N).view(-1, 1, 1, 1, 1).expand_as(tap)
+        c = torch.arange(d.C).view(1, 1, 1, 1, -1).expand_as(tap)
+        flat = (((n * T + t) * H + h) * W + w) * d.C + c
+        out = torch.zeros(d.N * T * H * W * d.C)
+        out.index_add_(0, flat[ok], g_out[ok])
+        return out.view(d.N, T, H, W, d.C)
+
+    def otal_maxpool_bwd(self, desc, stream):
+        d = desc._obj
+        k, s, pf, (T, H, W), (To, Ho, Wo), back = self._pool_geometry(d)
+        g_out = _view(d.g_out, d.N * To * Ho * Wo * d.gout_cstride, np.float32).view(d.N, To, Ho, Wo, d.gout_cstride)
+        g_in = _view(d.g_in, d.N * T * H * W * d.gin_cstride, np.float32).view(d.N, T, H, W, d.gin_cstride)
+        g_in[..., d.gin_coff:d.gin_coff + d.C] += self._pool_scatter(d, g_out[..., d.gout_coff:d.gout_coff + d.C])
+
+    def otal_maxpool_bwd_relu_bn_split(self, desc, g_add, add_cstride, add_coff, scale, d_hi, d_lo, d_cstride, d_coff, stream):
+        d = desc._obj
+        k, s, pf, (T, H, W), (To, Ho, Wo), back = self._pool_geometry(d)
+        g_out = _view(d.g_out, d.N * To * Ho * Wo * d.gout_cstride, np.float32).view(d.N, To, Ho, Wo, d.gout_cstride)
+        g = self._pool_scatter(d, g_out[..., d.gout_coff:d.gout_coff + d.C])
+        if g_add:
+            g = g + _view(g_add, d.N * T * H * W * add_cstride, np.float32).view(d.N, T, H, W, add_cstride)[..., add_coff:add_coff + d.C]
+        x_hi = _bf16(d.x_hi, d.N * T * H * W * d.in_cstride).view(d.N, T, H, W, d.in_cstride)[..., d.in_coff:d.in_coff + d.C].float()
+        g = g * (x_hi > 0)
+        if scale:
+            g = g * _view(scale, d.C, np.float32)
+        _store(g, d_hi, d_lo, (d.N, T, H, W, d_cstride), d_coff)
+
+    def otal_relu_bn_bwd_split(self, g, y_hi, scale, d_hi, d_lo, npos, C, g_cstride, g_coff, y_cstride, y_coff, d_cstride, d_coff, relu, stream):
+        gv = _view(g, npos * g_cstride, np.float32).view(npos, g_cstride)[:, g_coff:g_coff + C]
+        out = gv.clone()
+        if relu and y_hi:
+            out = out * (_bf16(y_hi, npos * y_cstride).view(npos, y_cstride)[:, y_coff:y_coff + C].float() > 0)
+        if scale:
+            out = out * _view(scale, C, np.float32)
+        _store(out, d_hi, d_lo, (npos, d_cstride), d_coff)
+
+
+def install(monkeypatch) -> Emulator:
+    """Route every `_lib.call` to the emulator and let CPU tensors through the wrappers' CUDA guards (tests only)."""
+    from opental_b200 import _lib, ops
+    emu = Emulator()
+    monkeypatch.setattr(_lib, "call", emu)
+    monkeypatch.setattr(ops, "_require_cuda", lambda *t: None)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "OVERLAP_WGRAD", False)
+    monkeypatch.setattr(ops, "join", lambda: None)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    return emu
