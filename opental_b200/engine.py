@@ -148,8 +148,9 @@ class Trainer:
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        dev = next(net.coarse_pyramid_detection.parameters()).device
-        assert dev.type == "cuda", "the training step runs on a CUDA device (no CPU fallback)"
+        p0 = next(net.coarse_pyramid_detection.parameters())
+        dev = p0.device
+        ops._require_cuda(p0)          # RuntimeError on anything but a CUDA model: the training step has no CPU fallback
         self.device = dev
         bb = net.backbone
         self.bb_w, self.bb_g = bb.flat_parameters(dev)

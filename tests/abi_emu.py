@@ -1,4 +1,4 @@
-"""A CPU stand-in for the BACKBONE entry points of libopental_b200.so  —  TEST INFRASTRUCTURE (never imported by the product).
+"""A CPU stand-in for the training-path entry points of libopental_b200.so  —  TEST INFRASTRUCTURE (never imported by the product).
 
 `install(monkeypatch)` replaces `opental_b200._lib.call` by a dispatcher that implements, with torch CPU ops on the host
 memory behind the raw pointers, what include/opental_b200.h says each entry point does (NDHWC bf16 hi/lo planes, channel
@@ -74,7 +74,7 @@ class Emulator:
         self.calls[name] = self.calls.get(name, 0) + 1
         fn = getattr(self, name, None)
         if fn is None:
-            raise NotImplementedError(f"abi_emu: {name} is not emulated (backbone entry points only)")
+            raise NotImplementedError(f"abi_emu: {name} is not emulated")
         fn(*args)
 
     # ---------------------------------------------------------------------------------------------- layout kernels
@@ -315,6 +315,108 @@ class Emulator:
         _store(out, d_hi, d_lo, (npos, d_cstride), d_coff)
 
 
+    # ---------------------------------------------------------------------------------------------- detection head
+    def otal_ncl_to_nlc_split(self, x, hi, lo, B, C, T, Cpad, Ttot, dilate, offset, stream):
+        v = _view(x, B * C * T, np.float32).view(B, C, T).permute(0, 2, 1)                        # [B,T,C]
+        n = B * Ttot * Cpad
+        h = v.bfloat16()
+        pos = offset + torch.arange(T) * dilate
+        _bf16(hi, n).view(B, Ttot, Cpad)[:, pos, :C] = h
+        if lo:
+            _bf16(lo, n).view(B, Ttot, Cpad)[:, pos, :C] = (v - h.float()).bfloat16()
+
+    @staticmethod
+    def _segments(nseg, so, sl, T):
+        return [(int(so[i]), int(sl[i])) for i in range(nseg)] if nseg else [(0, T)]
+
+    def otal_groupnorm_relu_fwd(self, x, gamma, beta, y, mean, rstd, B, C, T, G, eps, relu, nseg, so, sl, stream):
+        xv = _view(x, B * C * T, np.float32).view(B, C, T)
+        yv = _view(y, B * C * T, np.float32).view(B, C, T)
+        ga, be = _view(gamma, C, np.float32), _view(beta, C, np.float32)
+        yv.zero_()
+        for off, ln in self._segments(nseg, so, sl, T):
+            out = F.group_norm(xv[:, :, off:off + ln], G, ga, be, eps)
+            yv[:, :, off:off + ln] = out.relu() if relu else out
+
+    def otal_groupnorm_relu_bwd(self, gy, x, gamma, beta, mean, rstd, gx, dgb, B, C, T, G, relu, nseg, so, sl, stream):
+        gyv = _view(gy, B * C * T, np.float32).view(B, C, T)
+        xv = _view(x, B * C * T, np.float32).view(B, C, T)
+        gxv = _view(gx, B * C * T, np.float32).view(B, C, T)
+        out = _view(dgb, B * 2 * C, np.float32).view(B, 2, C)
+        gxv.zero_(), out.zero_()
+        for b in range(B):                                      # per-sample partial sums of the parameter gradients
+            for off, ln in self._segments(nseg, so, sl, T):
+                with torch.enable_grad():
+                    xs = xv[b:b + 1, :, off:off + ln].clone().requires_grad_(True)
+                    ga = _view(gamma, C, np.float32).clone().requires_grad_(True)
+                    be = _view(beta, C, np.float32).clone().requires_grad_(True)
+                    o = F.group_norm(xs, G, ga, be, 1e-5)
+                    o = o.relu() if relu else o
+                    g1, g2, g3 = torch.autograd.grad(o, (xs, ga, be), gyv[b:b + 1, :, off:off + ln])
+                gxv[b:b + 1, :, off:off + ln] = g1
+                out[b, 0] += g2
+                out[b, 1] += g3
+
+    def otal_make_segments(self, loc, prior, level_len, level_off, seg_level, seg_concat, frame_seg, B, P, frame_num, stream):
+        lc = _view(loc, B * P * 2, np.float32).view(B, P, 2)
+        pri = _view(prior, P, np.float32).view(1, P, 1)
+        t = _view(level_len, P, np.int32).view(1, P, 1).float()
+        off = _view(level_off, P, np.int32).view(1, P, 1).float()
+        seg = lc / frame_num * t                                                                  # BDNet.py:355-384, all levels at once
+        centre = torch.round(pri * t - 0.5)
+        plen = seg[:, :, :1] + seg[:, :, 1:]
+        inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
+        ls, rs = centre - seg[:, :, :1], centre + seg[:, :, 1:]
+        segments = torch.cat([torch.round(ls - outl), torch.round(ls + inl), torch.round(rs - inl), torch.round(rs + outl)], -1)
+        if seg_level:
+            _view(seg_level, B * P * 4, np.float32).view(B, P, 4).copy_(segments)
+        clamped = torch.minimum(segments.trunc().clamp(min=0), t - 1) + off                       # kernel.cu:33-38 + level offset
+        _view(seg_concat, B * P * 4, np.float32).view(B, P, 4).copy_(clamped)
+        dl, dr = pri * frame_num - lc[:, :, :1], pri * frame_num + lc[:, :, 1:]
+        plen = dr - dl + 1.0
+        inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
+        fs = torch.cat([torch.round(dl - outl), torch.round(dl + inl), torch.round(dr - inl), torch.round(dr + outl)], -1)
+        _view(frame_seg, B * P * 4, np.float32).view(B, P, 4).copy_(fs)
+
+    def otal_dirichlet_uncertainty(self, logit, unct, M, K, stream):
+        x = _view(logit, M * K, np.float32).view(M, K)
+        _view(unct, M, np.float32).copy_(K / (torch.exp(torch.clamp(x, -10, 10)) + 1).sum(-1))
+
+    def otal_bmp_forward_f32(self, inp, seg, out, B, C, T, K, stream):
+        import opental_oracle as O
+        x = _view(inp, B * C * T, np.float32).view(B, C, T)
+        sg = _view(seg, B * K * 4, np.float32).view(B, K, 4)
+        _view(out, B * C * K, np.float32).view(B, C, K).copy_(O.boundary_max_pooling(x, sg, False))
+
+    def otal_bmp_backward_f32(self, gout, inp, seg, gin, B, C, T, K, compat, stream):
+        import opental_oracle as O
+        sg = _view(seg, B * K * 4, np.float32).view(B, K, 4)
+        with torch.enable_grad():
+            x = _view(inp, B * C * T, np.float32).view(B, C, T).clone().requires_grad_(True)
+            (g,) = torch.autograd.grad(O.boundary_max_pooling(x, sg, bool(compat)), x, _view(gout, B * C * K, np.float32).view(B, C, K))
+        _view(gin, B * C * T, np.float32).view(B, C, T).copy_(g)
+
+    def otal_boundary_bce_fwd(self, x, target, tstride, row_loss, coef, B, T, C, stream):
+        xv = _view(x, B * T * C, np.float32).view(B, T, C)
+        tg = torch.stack([_view(int(target) + 4 * b * int(tstride), T, np.float32) for b in range(B)])      # rows of the score maps
+        s = torch.tanh(xv).mean(-1)
+        loss = -(tg * torch.log(s).clamp(min=-100) + (1 - tg) * torch.log(1 - s).clamp(min=-100))
+        _view(row_loss, B * T, np.float32).copy_(loss.reshape(-1))
+        _view(coef, B * T, np.float32).copy_(((s - tg) / (s * (1 - s)).clamp(min=1e-12) / (B * T * C)).reshape(-1))
+
+    def otal_boundary_bce_bwd(self, x, coef, g, gx, B, T, C, stream):
+        xv = _view(x, B * T * C, np.float32).view(B * T, C)
+        th = torch.tanh(xv)
+        _view(gx, B * T * C, np.float32).view(B * T, C).copy_(_view(g, 1, np.float32) * _view(coef, B * T, np.float32).view(-1, 1) * (1 - th * th))
+
+    def otal_adam_step(self, p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step, stream):
+        pv, gv, mv, vv = (_view(t, n, np.float32) for t in (p, g, m, v))
+        gr = gv * grad_scale + wd * pv
+        mv.mul_(b1).add_(gr, alpha=1 - b1)
+        vv.mul_(b2).addcmul_(gr, gr, value=1 - b2)
+        pv.sub_(lr / (1 - b1 ** step) * mv / ((vv / (1 - b2 ** step)).sqrt() + eps))
+
+
 def install(monkeypatch) -> Emulator:
     """Route every `_lib.call` to the emulator and let CPU tensors through the wrappers' CUDA guards (tests only)."""
     from opental_b200 import _lib, ops
@@ -325,4 +427,6 @@ def install(monkeypatch) -> Emulator:
     monkeypatch.setattr(ops, "OVERLAP_WGRAD", False)
     monkeypatch.setattr(ops, "join", lambda: None)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    import contextlib
+    monkeypatch.setattr(torch.cuda, "device", lambda *_a, **_k: contextlib.nullcontext())
     return emu

@@ -1,0 +1,110 @@
+"""CPU: the WHOLE product model — opental_b200.bdnet.BDNet (native backbone + level-batched head), MultiSegmentLoss, the autograd
+glue between the native stages — run against the C-ABI emulation (tests/abi_emu.py) on the full-size synthetic clip and
+compared with the golden vectors produced by the reference's own code (tests/golden/model_thumos_opental.*): the CPU twin of
+tests/test_model_gpu.py::test_forward_loss_backward_match_reference_golden, same tolerances.  What it pins is the HOST code
+(layouts of the level-batched head, slices, pads, segment tables, backward schedules); the kernels are pinned on the GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import abi_emu
+import opental_oracle as O
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    arrays = np.load(os.path.join(golden_dir, "model_thumos_opental.npz"))
+    with open(os.path.join(golden_dir, "model_thumos_opental.json")) as fh:
+        return arrays, json.load(fh)
+
+
+def test_forward_loss_backward_match_reference_golden_on_the_emulated_abi(monkeypatch, golden):
+    from opental_b200 import engine
+    from opental_b200.prop_pooling import BoundaryMaxPoolingFunction
+    arrays, summary = golden
+    emu = abi_emu.install(monkeypatch)
+    tag = "init"
+    net, crit = engine.build_opental(device="cpu", epoch=11)
+    crit.fused = False                                   # the loss in its torch formulation (the fused kernel is GPU-only)
+    net.load_state_dict(O.synthetic_state_dict(O.OracleConfig()))
+    x = O.synthetic_clip(0).unsqueeze(0)
+    targets = [O.synthetic_targets(0, num_classes=15)]
+    out = net(x)
+    errs = {}
+    for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "unct", "prop_unct"):
+        errs[k] = rel(out[k].detach(), torch.from_numpy(arrays[f"{tag}.{k}"]))
+    for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop"):
+        errs[k] = rel(out[k].detach()[:, ::8, ::8], torch.from_numpy(arrays[f"{tag}.{k}.sample"]))
+    assert max(errs.values()) < 1e-3, errs
+    for epoch in (1, 11):
+        crit.cls_loss.epoch = epoch
+        crit.cls_loss.weight_accum = torch.ones(50)
+        losses = crit(out, targets)
+        for a, b in zip(losses, summary[f"{tag}.e{epoch}"]["losses"]):
+            assert abs(float(a) - b) <= 1e-3 * max(abs(b), 1.0), (epoch, float(a), b)
+    net.backbone.flat_parameters()[1].zero_()
+    cost = losses[0] + 10 * losses[1] + losses[2] + 10 * losses[3] + losses[4] + losses[5] + losses[6]
+    assert abs(float(cost) - summary[f"{tag}.e11"]["cost"]) < 1e-3 * abs(summary[f"{tag}.e11"]["cost"])
+    BoundaryMaxPoolingFunction.compat_tscale_bug = True        # the golden gradients come from the reference kernel
+    try:
+        cost.backward()
+    finally:
+        BoundaryMaxPoolingFunction.compat_tscale_bug = False
+    params = dict(net.named_parameters())
+    bad = {}
+    for k, (s, a) in summary[f"{tag}.e11"]["grad_fingerprint"].items():
+        g = params[k].grad
+        assert g is not None, k
+        if a > 0 and abs(float(g.abs().sum()) - a) / a > 5e-2:
+            bad[k] = abs(float(g.abs().sum()) - a) / a
+        smp = torch.from_numpy(arrays[f"{tag}.e11.grad.{k}"])
+        got = g.detach().reshape(-1)[:: max(1, g.numel() // 64)][:64]
+        if smp.abs().max() > 0 and rel(got, smp) > 0.2:
+            bad[k + ":sample"] = rel(got, smp)
+    assert not bad, bad
+    assert emu.calls["otal_conv_igemm_fwd"] > 80 and emu.calls["otal_groupnorm_relu_fwd"] >= 20 and emu.calls["otal_make_segments"] == 1
+
+
+def test_trainer_step_from_uint8_frames_on_the_emulated_abi(monkeypatch):
+    """engine.Trainer.step (eager): uint8 frames -> ingest -> model -> loss -> boundary BCE -> backward -> fused Adam, against the
+    oracle's whole training cost on the loader's normalised clip; then the same step through the STAGED raw-uint8 Conv3d_1a
+    path, which must give the same cost and the same update."""
+    from opental_b200 import engine
+    emu = abi_emu.install(monkeypatch)
+    torch.manual_seed(0)
+    cfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(cfg)
+    px = engine.synthetic_clip_u8(0).unsqueeze(0)
+    tg = [engine.synthetic_targets(0)]
+    sc = engine.synthetic_scores(tg[0]).unsqueeze(0)
+    out_ref = O.bdnet_forward(engine.normalise_clip(px[0]).unsqueeze(0), sd, cfg)
+    want, parts = O.training_cost(out_ref, tg, sc, O.LossState(epoch=1), cfg)
+
+    def one_step(u8):
+        net, crit = engine.build_opental(device="cpu", epoch=1)
+        crit.fused = False
+        net.load_state_dict(sd)
+        net.backbone.u8_conv1a = u8
+        tr = engine.Trainer(net, crit, lr=1e-3)
+        w_before = [w.clone() for w, _ in tr.groups]
+        cost, losses, ls, le = tr.step(px, tg, sc)
+        assert tr.step_count == 1 and all(torch.isfinite(w).all() for w, _ in tr.groups)
+        assert all(not torch.equal(a, w) for a, (w, _) in zip(w_before, tr.groups))                 # every group moved
+        return float(cost), float(ls), float(le), [w.clone() for w, _ in tr.groups], [g.clone() for _, g in tr.groups], float(tr.grad_norm())
+
+    cost, ls, le, w3, g3, n3 = one_step(False)
+    assert abs(cost - float(want)) <= 1e-3 * abs(float(want)), (cost, float(want))
+    assert abs(ls - float(parts["loss_start"])) <= 1e-3 and abs(le - float(parts["loss_end"])) <= 1e-3
+    assert emu.calls["otal_adam_step"] == 3 and emu.calls["otal_boundary_bce_fwd"] == 6 and emu.calls["otal_clip_ingest_u8"] == 1
+    cost8, ls8, le8, w8, g8, n8 = one_step(True)
+    assert emu.calls["otal_conv1a_fwd_u8"] == 1 and emu.calls["otal_conv1a_wgrad_u8"] == 1 and emu.calls["otal_clip_ingest_u8_raw"] == 1
+    assert abs(cost8 - cost) <= 1e-4 * abs(cost) and abs(n8 - n3) <= 5e-2 * n3
+    for a, b in zip(g8, g3):                       # gradients: the two paths differ only by rounding + its discrete flips
+        assert float((a - b).norm() / b.norm()) < 5e-2
