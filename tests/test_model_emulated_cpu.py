@@ -108,3 +108,43 @@ def test_trainer_step_from_uint8_frames_on_the_emulated_abi(monkeypatch):
     assert abs(cost8 - cost) <= 1e-4 * abs(cost) and abs(n8 - n3) <= 5e-2 * n3
     for a, b in zip(g8, g3):                       # gradients: the two paths differ only by rounding + its discrete flips
         assert float((a - b).norm() / b.norm()) < 5e-2
+
+
+def test_training_loop_from_dataset_files_on_the_emulated_abi(monkeypatch, tmp_path):
+    """The pieces a real run strings together — files in the reference's formats -> window index -> loader threads -> padded
+    batches -> train_loop.run_one_epoch -> Trainer.step with the self-supervised second pass through the frame map -> checkpoint
+    in the reference's layout -> resume — on two steps of batch 1 (eager: CUDA graphs need the GPU)."""
+    import itertools
+
+    import make_golden
+    from opental_b200 import dataset as D, engine, train_loop
+    from opental_b200.loader import Prefetcher
+    emu = abi_emu.install(monkeypatch)
+    info, anno, cls, npy = make_golden.dataset_case_files(str(tmp_path / "data"), seed=0, n_videos=2)
+    infos = D.get_video_info(info)
+    ds = D.ThumosWindows(D.load_video_data(infos, npy), infos, D.get_video_anno(infos, anno, cls), training=True)
+    torch.manual_seed(0)
+    net, crit = engine.build_opental(device="cpu", epoch=1)
+    crit.fused = False
+    net.load_state_dict(O.synthetic_state_dict(O.OracleConfig()))
+    tr = engine.Trainer(net, crit, lr=1e-5, weight_decay=1e-3, ssl_weight=0.001)
+    net.backbone.crop_offsets = torch.zeros(1, 3, dtype=torch.int32)
+    pf = Prefetcher(ds, 1, epoch=1, workers=2, crop_offsets=net.backbone.crop_offsets)
+    seen = []
+    m = train_loop.run_one_epoch(tr, itertools.islice(iter(pf), 2), epoch=1, use_graph=False,
+                                 on_step=lambda it, info_: seen.append((it, info_["ssl"], float(info_["cost"]))))
+    assert m["steps"] == 2 and len(seen) == 2 and all(np.isfinite(c) for _, _, c in seen) and np.isfinite(m["grad_norm"])
+    assert m["ssl_steps"] == sum(s for _, s, _ in seen)
+    if m["ssl_steps"]:
+        assert emu.calls["otal_clip_ingest_u8"] == 2 + m["ssl_steps"]                     # main pass + frame-map pass
+    assert set(train_loop.TERMS) <= set(m) and "Train Loss" in train_loop.summary_line(1, m)
+    ck, st = str(tmp_path / "ck"), str(tmp_path / "ck" / "training")
+    tr.save_checkpoint(1, ck, st)
+    assert os.path.exists(os.path.join(ck, "checkpoint-1.ckpt")) and os.path.lexists(os.path.join(ck, "checkpoint-latest.ckpt"))
+    net2, crit2 = engine.build_opental(device="cpu", epoch=1)
+    tr2 = engine.Trainer(net2, crit2)
+    assert tr2.resume(1, ck, st) == 2 and tr2.step_count == tr.step_count
+    for (a, _), (b, _) in zip(tr.groups, tr2.groups):
+        assert torch.equal(a, b)
+    for sa, sb in zip(tr.state, tr2.state):
+        assert torch.equal(sa["m"], sb["m"]) and torch.equal(sa["v"], sb["v"])
