@@ -82,6 +82,9 @@ class Emulator:
         v = _view(x, n, np.float32)
         _store(v.view(n, 1), hi, lo, (n, 1), 0)
 
+    def otal_merge_bf16(self, hi, lo, x, n, stream):
+        _view(x, n, np.float32).copy_(_load(hi, lo, (n, 1), 0, 1).view(n))
+
     def otal_clip_ingest(self, x, hi, lo, N, C, T, H, W, stream):
         v = _view(x, N * C * T * H * W, np.float32).view(N, C, T, H, W)
         out = torch.zeros(N, T, H, W + 8, 4)

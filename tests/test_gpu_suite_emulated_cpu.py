@@ -1,0 +1,81 @@
+"""CPU: selected `-m gpu` tests run UNCHANGED against the C-ABI emulation (tests/abi_emu.py).
+
+The GPU test modules move their data with `.cuda()`; here `.cuda()` is the identity, `engine.build_opental*` build on the CPU
+with the loss in its torch formulation, and every `_lib.call` lands in the emulator.  So the same assertions — golden vectors
+of the reference, same tolerances — check the product's host code on every CPU run: per-endpoint backbone features, the
+self-supervised (triplet) pass and its frame-map form, the closed-set and the ActivityNet flavours, checkpoint / resume.
+The kernels are what the real `-m gpu` run checks."""
+import functools
+import importlib
+import math
+
+import pytest
+import torch
+
+import abi_emu
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    from opental_b200 import engine
+    emu = abi_emu.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+    def on_cpu(build):
+        @functools.wraps(build)
+        def wrapper(*args, **kw):
+            kw["device"] = "cpu"
+            net, crit = build(*args, **kw)
+            if hasattr(crit, "fused"):
+                crit.fused = False              # the loss in its torch formulation: the single-CTA kernel is GPU-only
+            return net, crit
+        return wrapper
+
+    monkeypatch.setattr(engine, "build_opental", on_cpu(engine.build_opental))
+    monkeypatch.setattr(engine, "build_opental_anet", on_cpu(engine.build_opental_anet))
+    return emu
+
+
+def gpu_test(module: str, name: str):
+    fn = getattr(importlib.import_module(module), name)
+    return getattr(fn, "__wrapped__", fn)
+
+
+def golden_pair(golden_dir, stem):
+    import json
+    import os
+
+    import numpy as np
+    arrays = np.load(os.path.join(golden_dir, stem + ".npz"))
+    with open(os.path.join(golden_dir, stem + ".json")) as fh:
+        return arrays, json.load(fh)
+
+
+def test_backbone_endpoints(emulated, golden_dir):
+    gpu_test("test_model_gpu", "test_backbone_endpoints_match_reference_golden")(golden_pair(golden_dir, "model_thumos_opental"))
+
+
+def test_ssl_triplet_pass(emulated, golden_dir):
+    gpu_test("test_model_gpu", "test_ssl_triplet_pass_matches_reference_golden")(golden_dir)
+
+
+def test_ssl_pass_through_frame_map(emulated):
+    gpu_test("test_model_gpu", "test_ssl_pass_through_frame_map_equals_materialised_clip")()
+
+
+def test_closed_set_model(emulated, golden_dir):
+    gpu_test("test_model_closed_gpu", "test_closed_set_forward_focal_loss_backward_match_reference_golden")(golden_dir, "biased", math.log(32.0))
+
+
+def test_checkpoint_resume(emulated, tmp_path):
+    gpu_test("test_checkpoint_gpu", "test_resume_is_bit_exact_and_matches_torch_adam")(tmp_path)
+
+
+def test_activitynet_model(emulated, golden_dir):
+    gpu_test("test_model_anet_gpu", "test_anet_forward_loss_backward_match_reference_golden")(golden_dir)
+
+
+def test_head_with_forced_windows(emulated):
+    gpu_test("test_head_gpu", "test_head_forward_backward_matches_oracle_with_forced_windows")(2)
