@@ -412,6 +412,59 @@ class Emulator:
         th = torch.tanh(xv)
         _view(gx, B * T * C, np.float32).view(B * T, C).copy_(_view(g, 1, np.float32) * _view(coef, B * T, np.float32).view(-1, 1) * (1 - th * th))
 
+    def otal_msl_forward(self, desc, stream):
+        """The 7 losses by the ORACLE's restatement of the reference loss (independent of the product's torch formulation);
+        the unit gradients of each loss w.r.t. each head output are kept on the side, keyed by the workspace pointer."""
+        import opental_oracle as O
+        d = desc._obj
+        B, P, K, G = d.B, d.P, d.K, d.G
+        M = B * P
+        names = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
+        shapes = ((B, P, 2), (B, P, K), (B, P, 2), (B, P, K), (B, P, 1), (B, P, 1), (B, P, 1))
+        ptrs = (d.loc, d.conf, d.prop_loc, d.prop_conf, d.center, d.act, d.prop_act)
+        assert d.act and d.prop_act, "abi_emu: the fused loss is emulated for the os_head configuration"
+        with torch.enable_grad():
+            out = {n: _view(p_, int(np.prod(sh)), np.float32).view(*sh).clone().requires_grad_(True) for n, sh, p_ in zip(names, shapes, ptrs)}
+            pri = _view(d.priors, (P - 1) * d.prior_stride + 1, np.float32)[::d.prior_stride].view(P, 1)
+            tg = _view(d.targets, B * G * 3, np.float32).view(B, G, 3)
+            va = _view(d.valid, B * G, np.uint8).view(B, G).bool()
+            targets = [tg[b][va[b]] for b in range(B)]
+            cfg = O.OracleConfig(num_classes=K, clip_length=int(d.clip_length), piou=float(d.overlap_thresh), with_ibm=bool(d.use_ibm),
+                                 ibm_start=10, momentum=float(d.momentum), num_bins=max(int(d.num_bins), 1), iou_aware=bool(d.iou_aware),
+                                 act_weight=float(d.act_weight), act_margin=float(d.act_margin))
+            state = O.LossState(epoch=11 if d.use_ibm else 1)
+            wa = _view(d.weight_accum, d.num_bins, np.float32) if d.weight_accum and d.num_bins else None
+            if wa is not None:
+                state.weight_accum = wa.clone()
+            losses = O.multisegment_loss(dict(out, priors=pri), targets, state, cfg)
+            unit = [torch.autograd.grad(l, [out[n] for n in names], retain_graph=True, allow_unused=True) for l in losses]
+        if wa is not None:
+            wa.copy_(state.weight_accum)
+        lv = _view(d.losses, 16, np.float32)
+        lv.zero_()
+        for i, l in enumerate(losses):
+            lv[i] = float(l)
+        _, conf_t, _, prop_conf_t, iou_pred = O.match_priors(out["loc"].detach(), pri, targets, cfg)
+        pos, ppos = (conf_t > 0).view(-1), (prop_conf_t > 0).view(-1)
+        lv[7], lv[8] = float(pos.sum()), float(ppos.sum())
+        lv[9] = float(O.actionness_loss(out["act"].detach().view(-1, 1), pos.float(), cfg)[1])
+        lv[10] = float(O.actionness_loss(out["prop_act"].detach().view(-1, 1), ppos.float(), cfg)[1])
+        lv[11] = float(O.iou_calibration(out["prop_conf"].detach().view(-1, K), iou_pred.reshape(-1), cfg)) if d.iou_aware else 0.0
+        if not hasattr(self, "_msl"):
+            self._msl = {}
+        key = d.workspace.value if isinstance(d.workspace, ctypes.c_void_p) else int(d.workspace)
+        self._msl[key] = [[g if g is not None else torch.zeros(sh) for g, sh in zip(gs, shapes)] for gs in unit]
+
+    def otal_msl_backward(self, B, P, K, ws, grad_losses, g_loc, g_conf, g_ploc, g_pconf, g_center, g_act, g_pact, stream):
+        unit = self._msl[int(ws)]
+        gl = _view(grad_losses, 7, np.float32)
+        outs = (g_loc, g_conf, g_ploc, g_pconf, g_center, g_act, g_pact)
+        for j, ptr in enumerate(outs):
+            if not ptr:
+                continue
+            tot = sum(float(gl[i]) * unit[i][j] for i in range(7))
+            _view(ptr, tot.numel(), np.float32).copy_(tot.reshape(-1))
+
     def otal_adam_step(self, p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step, stream):
         pv, gv, mv, vv = (_view(t, n, np.float32) for t in (p, g, m, v))
         gr = gv * grad_scale + wd * pv

@@ -148,3 +148,31 @@ def test_training_loop_from_dataset_files_on_the_emulated_abi(monkeypatch, tmp_p
         assert torch.equal(a, b)
     for sa, sb in zip(tr.state, tr2.state):
         assert torch.equal(sa["m"], sb["m"]) and torch.equal(sa["v"], sb["v"])
+
+
+@pytest.mark.parametrize("epoch", [1, 11])
+def test_fused_loss_host_glue_against_the_torch_formulation(monkeypatch, epoch):
+    """MultiSegmentLoss through `_FusedMSLFn` (pad_targets, descriptor, stats, the 7-way backward scaling) with the fused entry
+    points emulated by the ORACLE's loss, against the product's own torch formulation: two independent statements of the
+    reference loss meeting at the autograd boundary — losses, input gradients and the IBM buffer."""
+    from opental_b200 import engine
+    abi_emu.install(monkeypatch)
+    out = dict(O.fake_head_outputs(2, seed=5), priors=torch.cat(O.level_priors(O.OracleConfig()), 0))
+    targets = [O.synthetic_targets(0), O.synthetic_targets(1)[:1]]
+    res = {}
+    for fused in (True, False):
+        _, crit = engine.build_opental(device="cpu", epoch=epoch)
+        crit.fused = fused
+        live = {k: (v.clone().requires_grad_(True) if k != "priors" else v) for k, v in out.items()}
+        losses = crit(live, targets)
+        cost = losses[0] + 10 * losses[1] + losses[2] + 10 * losses[3] + losses[4] + 0.5 * losses[5] + 2 * losses[6]
+        cost.backward()
+        res[fused] = ([float(l) for l in losses], {k: v.grad.clone() for k, v in live.items() if k != "priors"},
+                      crit.cls_loss.weight_accum.clone(), crit.last_stats.detach().clone())
+    for a, b in zip(res[True][0], res[False][0]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (a, b)
+    for k in res[False][1]:
+        assert float((res[True][1][k] - res[False][1][k]).abs().max()) <= 1e-4 * max(1e-6, float(res[False][1][k].abs().max())), k
+    assert torch.allclose(res[True][2], res[False][2], atol=1e-6)
+    st = res[True][3]
+    assert torch.allclose(st[7:12], res[False][3], rtol=1e-5, atol=1e-6)                  # #pos, #refined pos, AN, PAN, loss_iouc

@@ -12,6 +12,7 @@ Same yaml, same flags (opental_b200/config.py), same data files (opental_b200/da
   * no tensorboard (the per-epoch summary line is printed, `--log_json` appends the epoch means to a file).
 Not exercised by the GPU test-suite (it needs the dataset); its parts are: config / dataset / train_loop CPU tests and
 tools/train_synthetic.py."""
+import itertools
 import json
 import os
 import random
@@ -35,12 +36,15 @@ def main(argv=None) -> int:
     parser.add_argument("--no_graph", action="store_true", help="eager steps instead of CUDA-graph replay")
     parser.add_argument("--log_json", type=str, default=None)
     parser.add_argument("--loader_threads", type=int, default=4)
+    parser.add_argument("--steps_per_epoch", type=int, default=0, help="stop every epoch after this many steps (smoke runs)")
+    parser.add_argument("--device", type=str, default="cuda", help="'cuda' (the product has no CPU path; other values are for the test harness)")
     args = parser.parse_args(argv)
     cfg = C.get_config(argv, parser)
     tr_cfg, ds_cfg = cfg["training"], cfg["dataset"]["training"]
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+    dev = torch.device(args.device, local) if args.device == "cuda" else torch.device(args.device)
+    if dev.type == "cuda":
+        torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     seed = tr_cfg["random_seed"]
@@ -72,8 +76,9 @@ def main(argv=None) -> int:
     def make_batches(epoch):
         # loader threads -> pinned ring -> copy stream (opental_b200/loader.py); the ingest kernel reads the crop / mirror
         # decisions from the static tensor below, so a captured step graph sees every update
-        return Prefetcher(ds, batch, epoch, rank=rank, world=world, seed=seed, device=dev, workers=args.loader_threads,
-                          crop_offsets=net.backbone.crop_offsets, ssl=ssl_on)
+        pf = Prefetcher(ds, batch, epoch, rank=rank, world=world, seed=seed, device=dev, workers=args.loader_threads,
+                        crop_offsets=net.backbone.crop_offsets, ssl=ssl_on)
+        return itertools.islice(iter(pf), args.steps_per_epoch) if args.steps_per_epoch > 0 else pf
 
     ck = tr_cfg["checkpoint_path"]
     st = os.path.join(ck, "training")                                                    # train.py:37
@@ -85,7 +90,8 @@ def main(argv=None) -> int:
 
     hist = train_loop.fit(trainer, make_batches, max_epoch=tr_cfg["max_epoch"], resume=tr_cfg["resume"], checkpoint_path=ck,
                           train_state_path=st, use_graph=not args.no_graph, log=log)
-    torch.cuda.synchronize()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
     if rank == 0 and args.log_json:
         with open(args.log_json, "w") as fh:
             json.dump(hist, fh)
