@@ -465,6 +465,51 @@ class Emulator:
             tot = sum(float(gl[i]) * unit[i][j] for i in range(7))
             _view(ptr, tot.numel(), np.float32).copy_(tot.reshape(-1))
 
+    # ---------------------------------------------------------------------------------------------- inference post-processing
+    def otal_decode_scores(self, loc, ploc, conf, pconf, center, act, pact, prior, offset, seg, scores, unct, actn, B, P, K, clip_length,
+                           sample_fps, stream):
+        import opental_oracle as O
+        assert act and pact, "abi_emu: decode is emulated for the open-set head"
+        v = lambda p_, *sh: _view(p_, int(np.prod(sh)), np.float32).view(*sh)           # noqa: E731
+        out = dict(loc=v(loc, B, P, 2), prop_loc=v(ploc, B, P, 2), conf=v(conf, B, P, K), prop_conf=v(pconf, B, P, K),
+                   center=v(center, B, P, 1), act=v(act, B, P, 1), prop_act=v(pact, B, P, 1), priors=v(prior, P, 1))
+        offs = v(offset, B) if offset else torch.zeros(B)
+        cfg = O.OracleConfig(num_classes=K, clip_length=int(clip_length))
+        for b in range(B):
+            s_, sc_, u_, a_ = O.decode_predictions(out, b, float(offs[b]), sample_fps, cfg)
+            v(seg, B, P, 2)[b], v(scores, B, K, P)[b], v(unct, B, P)[b], v(actn, B, P)[b] = s_, sc_, u_, a_
+
+    def otal_softnms(self, segments, stride, scores, keep, count, C, M, sigma, top_k, thr, stream):
+        import opental_oracle as O
+        sc = _view(scores, C * M, np.float32).view(C, M)
+        kp = _view(keep, C * M, np.uint8).view(C, M)
+        ct = _view(count, C, np.int32)
+        for c in range(C):
+            sg = _view(int(segments) + 4 * c * int(stride), M * 2, np.float32).view(M, 2)
+            cand = torch.cat([sg, sc[c].clone().view(-1, 1)], -1)
+            # softnms_v2 decays a working copy in place; re-run it on a copy that exposes the decayed scores
+            work = cand.clone()
+            _, n, mask = self._softnms(work, sigma, top_k, thr)
+            sc[c], kp[c], ct[c] = work[:, 2], mask.to(torch.uint8), n
+
+    @staticmethod
+    def _softnms(seg, sigma, top_k, thr):
+        """O.softnms_v2 on `seg` itself (no clone), so that the caller sees the decayed scores."""
+        ts, te, sc = seg[:, 0], seg[:, 1], seg[:, 2]
+        done = torch.zeros_like(sc, dtype=torch.bool)
+        undone = sc >= thr
+        while int(undone.sum()) > 1 and int(done.sum()) < top_k:
+            cand = undone.nonzero().view(-1)
+            idx = int(cand[sc[undone].argmax()])
+            undone[idx] = False
+            done[idx] = True
+            tt1, tt2 = ts[undone].clamp(min=float(ts[idx])), te[undone].clamp(max=float(te[idx]))
+            inter = (tt2 - tt1).clamp(min=0)
+            iou = inter / (torch.clamp(te[idx] - ts[idx], min=1e-5) + (te[undone] - ts[undone]) - inter)
+            sc[undone] = sc[undone] * torch.exp(-iou ** 2 / sigma)
+            undone[sc < thr] = False
+        return seg[done], int(done.sum()), done
+
     def otal_adam_step(self, p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step, stream):
         pv, gv, mv, vv = (_view(t, n, np.float32) for t in (p, g, m, v))
         gr = gv * grad_scale + wd * pv

@@ -79,3 +79,14 @@ def test_activitynet_model(emulated, golden_dir):
 
 def test_head_with_forced_windows(emulated):
     gpu_test("test_head_gpu", "test_head_forward_backward_matches_oracle_with_forced_windows")(2)
+
+
+def test_inference_post_processing(emulated, golden_dir):
+    import numpy as np
+    import os
+    mod = importlib.import_module("test_infer_gpu")
+    golden = np.load(os.path.join(golden_dir, "infer_cases.npz"))
+    mod.test_decode_scores_matches_reference_golden.__wrapped__(golden) if hasattr(mod.test_decode_scores_matches_reference_golden, "__wrapped__") \
+        else mod.test_decode_scores_matches_reference_golden(golden)
+    mod.test_decode_scores_batch_matches_oracle()
+    mod.test_softnms_many_classes_matches_oracle()

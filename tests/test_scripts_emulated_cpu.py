@@ -114,3 +114,32 @@ def test_train_anet_script_smoke(monkeypatch, tmp_path, capsys):
     hist = json.loads(log.read_text())
     assert len(hist) == 1 and hist[0]["steps"] == 1 and hist[0]["cost"] == hist[0]["cost"]
     assert "videos;" in capsys.readouterr().out
+
+
+def test_test_thumos_script_smoke(monkeypatch, tmp_path, capsys):
+    """tools/test_thumos.py: checkpoint in the reference's layout -> sliding windows over every test video -> device-side decode
+    + soft-NMS (emulated by the oracle's restatements) -> detection json in the reference's layout."""
+    abi_emu.install(monkeypatch)
+    info, anno, cls, npy = make_golden.dataset_case_files(str(tmp_path / "data"), seed=2, n_videos=1)
+    sd = O.synthetic_state_dict(O.OracleConfig(num_classes=20), loc_bias_shift=3.4657)
+    os.makedirs(tmp_path / "ckpt_0")
+    torch.save(sd, tmp_path / "ckpt_0" / "checkpoint-3.ckpt")
+    os.symlink(tmp_path / "ckpt_0" / "checkpoint-3.ckpt", tmp_path / "ckpt_0" / "checkpoint-latest.ckpt")       # train.py:96-103
+    yaml_text = make_golden.CONFIG_CASE_YAML
+    for old, new in (("./data/open/split_{id:d}/test_info.csv", info), ("./data/open/split_{id:d}/test_anno.csv", anno),
+                     ("./data/open/split_{id:d}/classes.txt", cls), ("./data/test_npy/", npy), ("backbone_model: ./weights/i3d.pt", "backbone_model: null"),
+                     ("./ckpt/split_{id:d}/checkpoint-latest.ckpt", str(tmp_path / "ckpt_{id:d}" / "checkpoint-latest.ckpt")),
+                     ("./output/split_{id:d}", str(tmp_path / "out_{id:d}"))):
+        assert old in yaml_text, old
+        yaml_text = yaml_text.replace(old, new)
+    yaml_text = yaml_text.replace("num_classes: 16", "num_classes: 21").replace("conf_thresh: 0.01", "conf_thresh: 0.001").replace("top_k: 5000", "top_k: 50")
+    cfg_path = tmp_path / "cfg.yaml"
+    cfg_path.write_text(yaml_text)
+    assert load_tool("test_thumos").main([str(cfg_path), "--open_set", "--split=0", "--device=cpu"]) == 0
+    res = json.loads((tmp_path / "out_0" / "detection_results.json").read_text())
+    assert res["version"] == "THUMOS14" and res["external_data"] == {} and len(res["results"]) == 1
+    dets = next(iter(res["results"].values()))
+    assert isinstance(dets, list)
+    for d in dets:
+        assert set(d) == {"label", "score", "segment", "uncertainty", "actionness"} and d["label"].startswith("Class") and len(d["segment"]) == 2
+    assert "detections of 1 videos" in capsys.readouterr().out

@@ -20,12 +20,16 @@ from opental_b200.bdnet import BDNet  # noqa: E402
 
 
 def main(argv=None) -> int:
-    cfg = C.get_config(argv)
+    parser = C.build_parser()
+    parser.add_argument("--device", type=str, default="cuda", help="'cuda' (the product has no CPU path; other values are for the test harness)")
+    args = parser.parse_args(argv)
+    cfg = C.get_config(argv, parser)
     if cfg["testing"].get("fusion"):
         raise NotImplementedError("--fusion (RGB + optical-flow late fusion) is outside the OpenTAL hot path")
     te, ds, model = cfg["testing"], cfg["dataset"]["testing"], cfg["model"]
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    torch.cuda.set_device(dev)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if args.device == "cuda" else torch.device(args.device)
+    if dev.type == "cuda":
+        torch.cuda.set_device(dev)
     os_head, use_edl = bool(model.get("os_head", False)), bool(model.get("use_edl", False))
     net = BDNet.from_config(cfg, training=False, use_edl=use_edl, use_rpl=False, frame_num=ds["clip_length"]).to(dev)
     ckpt = te["checkpoint_path"]
