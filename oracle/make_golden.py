@@ -807,6 +807,38 @@ def augment_cases_anet():
     ns.restore_cuda()
 
 
+def anet_ssl_cases():
+    """The SSL / triplet second pass of the ActivityNet flavour (anet/BDNet.py:453-474, anet/train.py:159-166, 222-226): the
+    reference's own forward(ssl=True) + triplet loss + backward on the keyed synthetic weights and a 768-frame clip."""
+    import torch.nn as nn
+    ns = ref_loader.load_reference(config="configs/anet_opental.yaml", extra_args=("--open_set", "--split=0"), flavour="anet")
+    cfg = O.anet_config()
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(8.0))
+    net = ns.BDNet(in_channels=3, training=False, frame_num=768, use_edl=True)
+    net.load_state_dict(sd)
+    net.train()
+    x = O.synthetic_clip(1, frames=768).unsqueeze(0)
+    proposals = [torch.tensor([[120.0, 270.0], [366.0, 516.0], [273.0, 363.0]])]      # anchor / positive / negative, frames
+    net.zero_grad()
+    a_r, p_r, n_r = net(x, proposals=proposals, ssl=True)
+    trip_r = torch.stack([nn.TripletMarginLoss()(a_r[i], p_r[i], n_r[i]) * w for i, w in enumerate((1, 0.1, 0.1))]).sum(0)
+    trip_r.backward()
+    grads_r = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    arrays = {}
+    for name, lst in (("anchor", a_r), ("positive", p_r), ("negative", n_r)):
+        for i, t in enumerate(lst):
+            arrays[f"ssl.{name}.{i}"] = t.detach().numpy()
+    fp = {}
+    for k, g in grads_r.items():
+        fp[k] = [float(g.sum()), float(g.abs().sum())]
+        arrays[f"ssl.grad.{k}"] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy().copy()
+    print(f"[anet ssl] reference: triplet {float(trip_r):.5f}, {len(fp)} parameter gradients, feature shapes {[tuple(t.shape) for t in a_r]}")
+    np.savez_compressed(os.path.join(GOLD, "model_anet_ssl.npz"), **arrays)
+    with open(os.path.join(GOLD, "model_anet_ssl.json"), "w") as fh:
+        json.dump(dict(triplet=float(trip_r), proposals=proposals[0].tolist(), grad_fingerprint=fp), fh, indent=1)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -823,6 +855,8 @@ if __name__ == "__main__":
     elif "--windows" in sys.argv:
         sys.path.insert(0, ROOT)
         window_cases()
+    elif "--anet-ssl" in sys.argv:
+        anet_ssl_cases()
     elif "--augment-anet" in sys.argv:
         sys.path.insert(0, ROOT)
         augment_cases_anet()

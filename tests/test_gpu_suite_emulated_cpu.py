@@ -90,3 +90,7 @@ def test_inference_post_processing(emulated, golden_dir):
         else mod.test_decode_scores_matches_reference_golden(golden)
     mod.test_decode_scores_batch_matches_oracle()
     mod.test_softnms_many_classes_matches_oracle()
+
+
+def test_activitynet_ssl_triplet_pass(emulated, golden_dir):
+    gpu_test("test_model_anet_gpu", "test_anet_ssl_triplet_pass_matches_reference_golden")(golden_dir)

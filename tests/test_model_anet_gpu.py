@@ -68,3 +68,41 @@ def test_anet_forward_loss_backward_match_reference_golden(golden_dir):
             if e > 5e-2:
                 bad[k] = e
     assert not bad, bad
+
+
+@pytest.mark.skipif(os.environ.get("OTAL_STAGED") != "1", reason="written after round 1's GPU budget: passes against the C-ABI "
+                    "emulation on the CPU (tests/test_gpu_suite_emulated_cpu.py), first GPU run with OTAL_STAGED=1")
+def test_anet_ssl_triplet_pass_matches_reference_golden(golden_dir):
+    """SSL second pass of the ActivityNet flavour (anet/BDNet.py:453-474 + the triplet loss of anet/train.py:159-166) vs the
+    reference's own run (tests/golden/model_anet_ssl.*, oracle/make_golden.py --anet-ssl)."""
+    from opental_b200 import engine
+    from opental_b200.prop_pooling import BoundaryMaxPoolingFunction
+    arrays = np.load(os.path.join(golden_dir, "model_anet_ssl.npz"))
+    with open(os.path.join(golden_dir, "model_anet_ssl.json")) as fh:
+        summary = json.load(fh)
+    net, _ = engine.build_opental_anet(epoch=1)
+    net.load_state_dict(O.synthetic_state_dict(O.anet_config(), loc_bias_shift=math.log(8.0)))
+    x = O.synthetic_clip(1, frames=768).unsqueeze(0).cuda()
+    proposals = [torch.tensor(summary["proposals"]).cuda()]
+    a, p, n = net(x, proposals=proposals, ssl=True)
+    for name, lst in (("anchor", a), ("positive", p), ("negative", n)):
+        for i, t in enumerate(lst):
+            assert rel(t.detach().cpu(), torch.from_numpy(arrays[f"ssl.{name}.{i}"])) < 1e-3, (name, i)
+    trip = engine.Trainer.triplet_loss(a, p, n)
+    assert abs(float(trip) - summary["triplet"]) < 1e-3 * max(1.0, abs(summary["triplet"]))
+    net.backbone.flat_parameters()[1].zero_()
+    BoundaryMaxPoolingFunction.compat_tscale_bug = True        # golden gradients: the reference kernel's arithmetic
+    try:
+        trip.backward()
+    finally:
+        BoundaryMaxPoolingFunction.compat_tscale_bug = False
+    params = dict(net.named_parameters())
+    bad = {}
+    for k, (s, a_) in summary["grad_fingerprint"].items():
+        g = params[k].grad
+        if a_ > 0:
+            assert g is not None, k
+            e = abs(float(g.abs().sum()) - a_) / a_
+            if e > 5e-2:
+                bad[k] = e
+    assert not bad, bad

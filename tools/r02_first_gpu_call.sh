@@ -9,7 +9,7 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest default rc=$?" | tee -a gpurun_out/r02_pytest_gpu.log
-OTAL_STAGED=1 python -m pytest tests/test_conv1a_u8_gpu.py -q > gpurun_out/r02_pytest_staged.log 2>&1; echo "pytest staged rc=$?" | tee -a gpurun_out/r02_pytest_staged.log
+OTAL_STAGED=1 python -m pytest tests/test_conv1a_u8_gpu.py tests/test_model_anet_gpu.py -q > gpurun_out/r02_pytest_staged.log 2>&1; echo "pytest staged rc=$?" | tee -a gpurun_out/r02_pytest_staged.log
 timeout 300 python tools/conv1a_bench.py > gpurun_out/r02_conv1a_bench.txt 2>&1; echo "conv1a_bench rc=$?"
 for flag in 0 1 0 1; do
   OTAL_U8_CONV1A=$flag timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_u8_${flag}_$RANDOM.json 2> gpurun_out/r02_bench_err.log

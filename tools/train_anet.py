@@ -5,8 +5,8 @@
 
 Same yaml and flags (opental_b200/config.py), the reference's json / npy files (opental_b200/anet_dataset.py), the backbone at
 0.1 x the head's learning rate (train.py:303-310 -> Trainer(backbone_lr_scale=0.1)), score maps (action, start, end) holding
-class ids (App. D7).  The self-supervised second pass is OFF here (`--ssl_pass` is not offered): its ActivityNet flavour has
-not been pinned against the reference yet.  Checkpoints: model `state_dict` interoperates; the optimizer entry is written in
+class ids (App. D7), the self-supervised second pass through the cut-paste frame map when `--ssl` > 0 and the first sample of
+the batch could be augmented (anet/train.py:222-226; pinned by tests/golden/model_anet_ssl.*).  Checkpoints: model `state_dict` interoperates; the optimizer entry is written in
 the single-group layout of the THUMOS14 script (the reference's ActivityNet script uses two parameter groups).
 Not exercised by the GPU test-suite (needs the dataset); parts: tests/test_anet_dataset_cpu.py, tests/test_model_anet_gpu.py."""
 import itertools
@@ -53,7 +53,7 @@ def main(argv=None) -> int:
     crit = MultiSegmentLossANet(kw["num_classes"], kw["overlap_thresh"], 1.0, cls_loss_type=kw["cls_loss_type"],
                                 edl_config=kw["edl_config"], os_head=kw["os_head"], clip_length=clip_length).to(dev)
     trainer = engine.Trainer(net, crit, lr=tr_cfg["learning_rate"], weight_decay=tr_cfg["weight_decay"], lw=tr_cfg["lw"],
-                             cw=tr_cfg["cw"], ctw=tr_cfg["ctw"], actw=tr_cfg["actw"], backbone_lr_scale=0.1)
+                             cw=tr_cfg["cw"], ctw=tr_cfg["ctw"], actw=tr_cfg["actw"], ssl_weight=tr_cfg["ssl"], backbone_lr_scale=0.1)
     trainer.broadcast_parameters(0)
     ds = AD.AnetWindows(ds_cfg["video_info_path"], ds_cfg["video_mp4_path"], clip_length, ds_cfg["crop_size"], training=True,
                         binary_class=cfg["dataset"]["num_classes"] == 2)
@@ -67,7 +67,7 @@ def main(argv=None) -> int:
         # loader threads -> pinned ring -> copy stream (opental_b200/loader.py); the ingest kernel reads the crop / mirror
         # decisions from the static tensor below, so a captured step graph sees every update
         pf = Prefetcher(ds, batch, epoch, rank=rank, world=world, seed=seed, device=dev, workers=args.loader_threads,
-                        crop_offsets=net.backbone.crop_offsets, ssl=False)
+                        crop_offsets=net.backbone.crop_offsets, ssl=tr_cfg["ssl"] > 0)
         return itertools.islice(iter(pf), args.steps_per_epoch) if args.steps_per_epoch > 0 else pf
 
     ck = tr_cfg["checkpoint_path"]
