@@ -131,6 +131,10 @@ class I3DBackbone(nn.Module):
         # STAGED (off by default, not yet validated on a GPU): Conv3d_1a fwd + wgrad on the raw uint8 pixel values — one exact
         # bf16 plane, one tensor-core pass instead of 2 (fwd) / 3 (wgrad); ops.conv1a_u8_scale_shift / conv1a_u8_weight_grad
         self.u8_conv1a = os.environ.get("OTAL_U8_CONV1A") == "1"
+        # STAGED (off by default, to be A/B-measured): the two bottleneck 1x1 convs of an inception block (b1a, b2a: same input,
+        # adjacent weights / BN scales / outputs by construction) as ONE forward launch and ONE weight-gradient launch — b2a alone
+        # is a 16..48-channel conv, a launch-latency-bound sliver.  Host-side only: same kernels, same memory layout.
+        self.fuse_b12a = os.environ.get("OTAL_FUSE_B12A") == "1"
         self.reset_parameters()
 
     # ------------------------------------------------------------------------------------------------ structure
@@ -253,6 +257,14 @@ class I3DBackbone(nn.Module):
         ops.conv_igemm(x, self._w(r), kernel=r.k, pad_front=_pads(x.hi.shape[1:4], r.k), scale=sc, shift=sh, relu=True,
                        in_slice=in_slice, out=out, out_slice=(out_off, r.cout), out_f32=out_f32)
 
+    def _w12(self, c: dict) -> Planes:
+        """Weight planes of [b1a ; b2a] as ONE [1, w1a + w2a, Cin] operand (adjacent in the flat buffer by construction)."""
+        r1, r2 = c["b1a"], c["b2a"]
+        assert r1.w_off + r1.numel == r2.w_off and r1.bn_off + r1.cout == r2.bn_off and r1.cin == r2.cin
+        sl = slice(r1.w_off, r2.w_off + r2.numel)
+        return Planes(self._wp.hi[sl].view(1, r1.cout + r2.cout, r1.cin),
+                      self._wp.lo[sl].view(1, r1.cout + r2.cout, r1.cin) if self._wp.lo is not None else None)
+
     def _mixed(self, name: str, x: Planes, saved: dict, out_f32: bool = False) -> Planes:
         c = {b: self.convs[f"{name}.{b}"] for b in BRANCHES}
         shape = x.hi.shape[:4]
@@ -264,8 +276,14 @@ class I3DBackbone(nn.Module):
                                        save_argmax=True)
         o1, o2, o3 = c["b0"].cout, c["b0"].cout + c["b1b"].cout, c["b0"].cout + c["b1b"].cout + c["b2b"].cout
         self._conv(x, c["b0"], y, 0, out_f32=f32)
-        self._conv(x, c["b1a"], mid, 0)
-        self._conv(x, c["b2a"], mid, c["b1a"].cout)
+        if self.fuse_b12a:
+            r1, w12 = c["b1a"], self._w12(c)
+            n12 = w12.hi.shape[1]
+            ops.conv_igemm(x, w12, kernel=(1, 1, 1), pad_front=(0, 0, 0), scale=self._scale[r1.bn_off:r1.bn_off + n12],
+                           shift=self._shift[r1.bn_off:r1.bn_off + n12], relu=True, out=mid, out_slice=(0, n12))
+        else:
+            self._conv(x, c["b1a"], mid, 0)
+            self._conv(x, c["b2a"], mid, c["b1a"].cout)
         self._conv(mid, c["b1b"], y, o1, in_slice=(0, c["b1a"].cout), out_f32=f32)
         self._conv(mid, c["b2b"], y, o2, in_slice=(c["b1a"].cout, c["b2a"].cout), out_f32=f32)
         self._conv(pooled, c["b3b"], y, o3, out_f32=f32)
@@ -363,15 +381,20 @@ class I3DBackbone(nn.Module):
         self._conv_bwd(c["b3b"], pooled, d_y, g_pool, d_slice=(o3, c["b3b"].cout))
         sc_m = self._scale[c["b1a"].bn_off:c["b1a"].bn_off + mid.hi.shape[-1]]   # [b1a|b2a] contiguous by design
         d_m = ops.relu_bn_bwd_split(g_mid, mid, sc_m, with_lo=with_lo)
-        self._conv_bwd(c["b1a"], x, d_m, None, d_slice=(0, w1a))
-        self._conv_bwd(c["b2a"], x, d_m, None, d_slice=(w1a, w2a))
+        if self.fuse_b12a:
+            r1, r2 = c["b1a"], c["b2a"]
+            dw12 = self.flat_g[r1.w_off:r2.w_off + r2.numel].view(1, w1a + w2a, r1.cin)        # both gradient blocks, adjacent
+            if ops.OVERLAP_WGRAD:
+                with torch.cuda.stream(ops.fork()):
+                    ops.conv_wgrad(x, d_m, dw12, kernel=(1, 1, 1), pad_front=(0, 0, 0))
+            else:
+                ops.conv_wgrad(x, d_m, dw12, kernel=(1, 1, 1), pad_front=(0, 0, 0))
+        else:
+            self._conv_bwd(c["b1a"], x, d_m, None, d_slice=(0, w1a))
+            self._conv_bwd(c["b2a"], x, d_m, None, d_slice=(w1a, w2a))
         # data gradient of the three 1x1 convs that read x (b0, b1a, b2a) in ONE pass: K-concatenated
         # [d_y(b0) | d_m] . [W_b0 ; W_b1a ; W_b2a] — g_x is written once instead of one write + two read-modify-writes
-        r1, r2 = c["b1a"], c["b2a"]
-        assert r1.w_off + r1.numel == r2.w_off          # b1a and b2a are adjacent in the flat weight buffer
-        sl = slice(r1.w_off, r2.w_off + r2.numel)
-        w12 = Planes(self._wp.hi[sl].view(1, w1a + w2a, r1.cin),
-                     self._wp.lo[sl].view(1, w1a + w2a, r1.cin) if self._wp.lo is not None else None)
+        w12 = self._w12(c)
         ops.conv_igemm(d_y, self._w(c["b0"]), kernel=(1, 1, 1), pad_front=(0, 0, 0), in_slice=(0, c["b0"].cout), out_f32=g_x,
                        out_slice=(0, c["b0"].cin), want_planes=False, dgrad=True, x2=d_m, w2=w12)
         ops.maxpool_bwd(x, g_pool, g_x, kernel=(3, 3, 3), stride=(1, 1, 1), pad_front=_pads(shape[1:], (3, 3, 3)), argmax=parg)

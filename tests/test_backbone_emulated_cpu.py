@@ -104,3 +104,26 @@ def test_uint8_frames_default_path(monkeypatch):
     with torch.no_grad():
         a, b = net(px), net(x)
     assert rel(a["Mixed_5c"], b["Mixed_5c"]) < 1e-6 and emu.calls["otal_clip_ingest_u8"] == 1 and emu.calls["otal_clip_ingest"] == 1
+
+
+def test_staged_fused_bottleneck_convs_through_the_schedule(monkeypatch):
+    """OTAL_FUSE_B12A: b1a + b2a of every inception block as one forward and one weight-gradient launch — same results, 18 launches
+    fewer (9 forward, 9 weight gradient)."""
+    net, emu = build(monkeypatch)
+    net.fuse_b12a = True
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 3, 32, 64, 64, generator=g) * 2 - 1
+    g4, g5 = torch.randn(1, 832, 8, 4, 4, generator=g), torch.randn(1, 1024, 4, 2, 2, generator=g)
+    want, grads = oracle_run(x, g4, g5)
+    out = net(x)
+    net.flat_parameters()[1].zero_()
+    (out["Mixed_4f"] * g4).sum().add((out["Mixed_5c"] * g5).sum()).backward()
+    check(net, out, want, grads)
+    assert emu.calls["otal_conv_wgrad"] == 56 - 9
+    # forward launches: 56 generic convs without the switch, 47 with it
+    for flag, want_launches in ((False, 56), (True, 47)):
+        net.fuse_b12a = flag
+        before = emu.calls["otal_conv_igemm_fwd"]
+        with torch.no_grad():
+            net(x)
+        assert emu.calls["otal_conv_igemm_fwd"] - before == want_launches

@@ -31,6 +31,13 @@ for flag in 0 1 0 1; do
   echo "bench OTAL_CONV_1X1_BN64=$flag rc=$?"
 done
 unset OTAL_CONV_1X1_BN64
+# b1a + b2a of every inception block as one forward and one weight-gradient launch (host-side fusion, 18 launches fewer)
+for flag in 0 1 0 1; do
+  if [ $flag = 1 ]; then export OTAL_FUSE_B12A=1; else unset OTAL_FUSE_B12A; fi
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_fuse12_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
+  echo "bench OTAL_FUSE_B12A=$flag rc=$?"
+done
+unset OTAL_FUSE_B12A
 # where the step goes now, per layer (event-timed eager pass), and a source-level look at the HBM-bound 1x1 convs, which run
 # at ~22 % of the copy roofline (profiles/r01_ncu_full_kernels_summary_v2.txt ids 8-10: Mixed_3c.b0 fwd / dgrad / wgrad)
 timeout 600 python tools/step_profile.py > gpurun_out/r02_step_profile.txt 2>&1; echo "step_profile rc=$?"
