@@ -176,3 +176,32 @@ def test_fused_loss_host_glue_against_the_torch_formulation(monkeypatch, epoch):
     assert torch.allclose(res[True][2], res[False][2], atol=1e-6)
     st = res[True][3]
     assert torch.allclose(st[7:12], res[False][3], rtol=1e-5, atol=1e-6)                  # #pos, #refined pos, AN, PAN, loss_iouc
+
+
+def test_staged_uint8_path_with_the_ssl_frame_map(monkeypatch):
+    """The self-supervised second pass re-reads the uint8 frames through the cut-paste frame map; with the STAGED raw-uint8
+    Conv3d_1a path both passes go through otal_clip_ingest_u8_raw / otal_conv1a_*_u8 and the step's cost must not change."""
+    import random
+
+    from opental_b200 import augment, engine
+    emu = abi_emu.install(monkeypatch)
+    sd = O.synthetic_state_dict(O.OracleConfig(), loc_bias_shift=3.4657)
+    px = engine.synthetic_clip_u8(0).unsqueeze(0)
+    tg = [engine.synthetic_targets(0)]
+    sc = engine.synthetic_scores(tg[0]).unsqueeze(0)
+    annos = [[float(s) * 256, float(e) * 256, int(l)] for s, e, l in tg[0].tolist()]
+    fmap, ssl_annos, flag = augment.cut_paste(annos, 8, 256, 1, rng=random.Random(3))
+    assert flag
+    prop = [torch.tensor(ssl_annos, dtype=torch.float32)]
+    costs = {}
+    for u8 in (False, True):
+        net, crit = engine.build_opental(device="cpu", epoch=1)
+        crit.fused = False
+        net.load_state_dict(sd)
+        net.backbone.u8_conv1a = u8
+        tr = engine.Trainer(net, crit, ssl_weight=0.001)
+        c, *_ = tr.step(px, tg, sc, ssl_targets=prop, ssl_frame_map=torch.from_numpy(fmap).unsqueeze(0))
+        costs[u8] = float(c)
+        assert net.backbone.frame_map is None
+    assert emu.calls["otal_clip_ingest_u8_raw"] == 2 and emu.calls["otal_conv1a_wgrad_u8"] == 2 and emu.calls["otal_clip_ingest_u8"] == 2
+    assert abs(costs[True] - costs[False]) <= 1e-4 * abs(costs[False]), costs
