@@ -196,3 +196,32 @@ def test_live_iou_calibration_is_the_term_inside_loss_prop_c():
     assert torch.allclose(g[0], losses[0] * 0.5) and torch.allclose(g[2], losses[2] * 2.0)
     crit.iou_aware = False
     assert live_iou_calibration(crit, live, targets) is None
+
+
+def test_trainer_globalise_glue_with_the_fused_loss_stats(monkeypatch):
+    """Trainer._globalise on the FUSED loss's 16-float stats vector (counts + loss_iouc at [7:12]) — the fused entry points
+    emulated by the oracle's loss (tests/abi_emu.py) — in a 1-process gloo group with the world size forced to 2: every
+    count-normalised term doubles (n * 2 / n), the IoU-calibration term inside loss_prop_c keeps weight 1."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import abi_emu
+    from opental_b200.engine import Trainer, live_iou_calibration
+    abi_emu.install(monkeypatch)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        out, targets, crit = _globalise_case()
+        crit.fused = True
+        crit.iou_aware = crit.cls_loss.iou_aware = True
+        live = {k: (v.detach().clone().requires_grad_(True) if k != "priors" else v) for k, v in out.items()}
+        losses = crit(live, targets)
+        assert crit.last_stats.numel() == 16                                  # the fused path's vector
+        tr = Trainer.__new__(Trainer)
+        tr.criterion, tr.world, tr.pg = crit, 2, None
+        g = tr._globalise(live, losses, targets)
+        iouc = live_iou_calibration(crit, live, targets)
+        assert torch.allclose(iouc, crit.last_stats[11], rtol=1e-5)
+        for i in (0, 1, 2, 4, 5, 6):
+            assert torch.allclose(g[i], 2.0 * losses[i], rtol=1e-6), i
+        assert torch.allclose(g[3], 2.0 * (losses[3] - iouc) + iouc, rtol=1e-5)
+    finally:
+        dist.destroy_process_group()
