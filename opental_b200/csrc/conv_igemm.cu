@@ -515,12 +515,17 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     for (int s = kMaxStages; s >= 3 && !nst; --s)
         if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = s;
     {
-        // STAGED switch (OTAL_CONV_PREFER_STAGES=1, default off, to be A/B-measured): when two staging buffers leave room for
-        // only two pipeline stages (BN = 96..128 in bf16x3: 56-64 KB per stage), take THREE stages with ONE staging buffer
-        // instead — the HBM-bound 1x1 convs are latency-bound with two loads in flight
+        // STAGED switch (OTAL_CONV_PREFER_STAGES=1, default off, to be A/B-measured): pipeline depth before store overlap — when
+        // ONE staging buffer buys at least one more pipeline stage than two do (BN 64..128 in bf16x3: 48-64 KB per stage), take
+        // it.  The HBM-bound 1x1 convs run at ~22 % of DRAM bandwidth with every unit idle: the bytes a CTA has in flight (2
+        // stages = 64 KB of A) do not cover the DRAM latency of its 128-byte TMA rows.
         static const bool prefer_stages = getenv("OTAL_CONV_PREFER_STAGES") != nullptr;
-        if (prefer_stages && !nst && p.store_bf16 &&
-            conv_smem_layout(p.BN, p.nsplit, 3, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) { nst = 3; nbuf = 1; }
+        if (prefer_stages && p.store_bf16 && nst < kMaxStages) {
+            int s1 = 0;
+            for (int s = kMaxStages; s >= 3 && !s1; --s)
+                if (conv_smem_layout(p.BN, p.nsplit, s, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) s1 = s;
+            if (s1 > (nst ? nst : 2)) { nst = s1; nbuf = 1; }
+        }
     }
     if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = 2;
     if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) { nst = 2; nbuf = 1; }

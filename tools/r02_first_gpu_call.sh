@@ -31,6 +31,13 @@ for flag in 0 1 0 1; do
   echo "bench OTAL_CONV_1X1_BN64=$flag rc=$?"
 done
 unset OTAL_CONV_1X1_BN64
+# both launch-shape switches together: 64-wide N blocks + one staging buffer = 4 stages (128 KB of A) in flight per SM
+for flag in 0 1 0 1; do
+  if [ $flag = 1 ]; then export OTAL_CONV_1X1_BN64=1 OTAL_CONV_PREFER_STAGES=1; else unset OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES; fi
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_bn64stages_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
+  echo "bench BN64+PREFER_STAGES=$flag rc=$?"
+done
+unset OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES
 # b1a + b2a of every inception block as one forward and one weight-gradient launch (host-side fusion, 18 launches fewer)
 for flag in 0 1 0 1; do
   if [ $flag = 1 ]; then export OTAL_FUSE_B12A=1; else unset OTAL_FUSE_B12A; fi
