@@ -9,42 +9,22 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest default rc=$?" | tee -a gpurun_out/r02_pytest_gpu.log
-OTAL_STAGED=1 python -m pytest tests/test_conv1a_u8_gpu.py tests/test_model_anet_gpu.py -q > gpurun_out/r02_pytest_staged.log 2>&1; echo "pytest staged rc=$?" | tee -a gpurun_out/r02_pytest_staged.log
+OTAL_STAGED=1 timeout 300 python -m pytest tests/test_conv1a_u8_gpu.py tests/test_model_anet_gpu.py -q > gpurun_out/r02_pytest_staged.log 2>&1; echo "pytest staged rc=$?" | tee -a gpurun_out/r02_pytest_staged.log
 timeout 300 python tools/conv1a_bench.py > gpurun_out/r02_conv1a_bench.txt 2>&1; echo "conv1a_bench rc=$?"
-for flag in 0 1 0 1; do
-  OTAL_U8_CONV1A=$flag timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_u8_${flag}_$RANDOM.json 2> gpurun_out/r02_bench_err.log
-  echo "bench OTAL_U8_CONV1A=$flag rc=$?"
+# A/B of every staged switch: two interleaved passes over (baseline, each switch alone, the two launch-shape switches together);
+# `value` of each JSON line is the CUDA-event step time with resident inputs (no e2e leg, no CPU baseline: ~40 s per run)
+for pass in 1 2; do
+  for cfg in base OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 "OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES" OTAL_FUSE_B12A; do
+    unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A
+    if [ "$cfg" != base ]; then for v in $cfg; do export $v=1; done; fi
+    tag=$(echo "$cfg" | tr ' ' '+')
+    timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02_ab_${tag}_pass${pass}.json 2>> gpurun_out/r02_bench_err.log
+    echo "bench [$tag] pass $pass rc=$? $(python -c "import json,sys; print(json.load(open('gpurun_out/r02_ab_${tag}_pass${pass}.json'))['ms_per_step'])" 2>/dev/null) ms/step"
+  done
 done
+unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|border_class|clip_ingest' -c 12 \
-  -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu rc=$?"
-# pipeline-depth switch for the 2-stage shapes (3 stages + 1 staging buffer instead of 2 + 2)
-for flag in 0 1 0 1; do
-  if [ $flag = 1 ]; then export OTAL_CONV_PREFER_STAGES=1; else unset OTAL_CONV_PREFER_STAGES; fi
-  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_stages_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
-  echo "bench OTAL_CONV_PREFER_STAGES=$flag rc=$?"
-done
-unset OTAL_CONV_PREFER_STAGES
-# 64-wide N blocks for the large 1x1 convs (more loads in flight per SM)
-for flag in 0 1 0 1; do
-  if [ $flag = 1 ]; then export OTAL_CONV_1X1_BN64=1; else unset OTAL_CONV_1X1_BN64; fi
-  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_bn64_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
-  echo "bench OTAL_CONV_1X1_BN64=$flag rc=$?"
-done
-unset OTAL_CONV_1X1_BN64
-# both launch-shape switches together: 64-wide N blocks + one staging buffer = 4 stages (128 KB of A) in flight per SM
-for flag in 0 1 0 1; do
-  if [ $flag = 1 ]; then export OTAL_CONV_1X1_BN64=1 OTAL_CONV_PREFER_STAGES=1; else unset OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES; fi
-  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_bn64stages_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
-  echo "bench BN64+PREFER_STAGES=$flag rc=$?"
-done
-unset OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES
-# b1a + b2a of every inception block as one forward and one weight-gradient launch (host-side fusion, 18 launches fewer)
-for flag in 0 1 0 1; do
-  if [ $flag = 1 ]; then export OTAL_FUSE_B12A=1; else unset OTAL_FUSE_B12A; fi
-  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_fuse12_${flag}_$RANDOM.json 2>> gpurun_out/r02_bench_err.log
-  echo "bench OTAL_FUSE_B12A=$flag rc=$?"
-done
-unset OTAL_FUSE_B12A
+  -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu conv1a rc=$?"
 # where the step goes now, per layer (event-timed eager pass), and a source-level look at the HBM-bound 1x1 convs, which run
 # at ~22 % of the copy roofline (profiles/r01_ncu_full_kernels_summary_v2.txt ids 8-10: Mixed_3c.b0 fwd / dgrad / wgrad)
 timeout 600 python tools/step_profile.py > gpurun_out/r02_step_profile.txt 2>&1; echo "step_profile rc=$?"
