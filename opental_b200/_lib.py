@@ -32,7 +32,7 @@ class ConvDesc(Structure):
                       "sT", "sH", "sW", "nsplit", "relu", "accumulate", "dgrad", "y_f32_ncdhw",
                       "in_cstride", "in_coff", "out_cstride", "out_coff")
                 + _ptrs("x_hi", "x_lo", "w_hi", "w_lo", "scale", "shift", "y_hi", "y_lo", "y_f32")
-                + _ints("Cin2", "in2_cstride", "in2_coff") + _ptrs("x2_hi", "x2_lo", "w2_hi", "w2_lo"))
+                + _ints("Cin2", "in2_cstride", "in2_coff") + _ptrs("x2_hi", "x2_lo", "w2_hi", "w2_lo") + _ints("ksplit"))
 
 
 class Conv1aDesc(Structure):

@@ -70,6 +70,9 @@ struct ConvParams {
     float* out_f32;      // optional NDHWC fp32 destination (nullptr = skip)
     int a_single;    // U8 instantiation: the A operand is ONE exact bf16 plane (raw uint8 pixel values 0..255) while B and the
                      // output keep hi/lo planes: a*[b_hi | b_lo] is ONE N-concatenated MMA per K step (needs ncat)
+    int ksplit;      // KS instantiation: a tile's K iterations (taps x chunks) are split over `ksplit` CTAs, each adds its partial
+                     // sums to the fp32 destination with atomics (zeroed by the caller unless it accumulates); small problems
+                     // only — the 1-D head, where one CTA per tile streams 24..72 stages alone while half the SMs idle
     int shift_classes;  // U8: `shift` is a table [4*4*4 border classes][Cout]; class of an output index o along a dim of n
                      // outputs = 1 (o == 0), 2 (o == n-2), 3 (o == n-1), else 0 — which taps of a 7-tap stride-2 window fall
                      // outside the image, where the reference pads the NORMALISED clip with 0 and the raw clip holds 0 = -1
@@ -114,10 +117,12 @@ __device__ __forceinline__ void split_parity(int d, int s, int& q, int& par) {
 
 // U8 (implies NCAT): single-plane A operand + border-class shift table, see ConvParams::a_single / shift_classes.  A separate
 // instantiation, so the code of the other two is unchanged by it.
-template <bool NCAT, bool U8 = false>
+// KS: split-K over CTAs with an atomic fp32 epilogue (ConvParams::ksplit) — also a separate instantiation.
+template <bool NCAT, bool U8 = false, bool KS = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     static_assert(NCAT || !U8, "the single-plane A operand needs the N-concatenated weight tile");
+    static_assert(!(U8 && KS), "split-K is for the small fp32-output problems");
     const CUtensorMap& mapB_hi = maps.B_hi; const CUtensorMap& mapB_lo = maps.B_lo;
     const CUtensorMap& mapO_hi = maps.O_hi; const CUtensorMap& mapO_lo = maps.O_lo;
     extern __shared__ unsigned char smem_dyn[];
@@ -165,8 +170,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         // ------------------------------------------------------------------ TMA producer (whole warp runs the loop)
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nb = tile % p.n_blocks;
-            int m = tile / p.n_blocks;
+            int tdec = tile, it_lo = 0, it_hi = 0x7fffffff, it_cur = 0;
+            if constexpr (KS) {                       // K range of this CTA's share of the tile
+                const int ks = tdec % p.ksplit; tdec /= p.ksplit;
+                it_lo = kiters * ks / p.ksplit; it_hi = kiters * (ks + 1) / p.ksplit;
+            }
+            const int nb = tdec % p.n_blocks;
+            int m = tdec / p.n_blocks;
             const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
             const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
             const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
@@ -189,6 +199,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         const int cw = w0 + qw, ch = h0 + qh, ct = t0 + qt;
                         const int btap = p.b_mn ? ntaps - 1 - tap : tap;
                         for (int kc = 0; kc < p.kchunks; ++kc) {
+                            if constexpr (KS) {
+                                const int it = it_cur++;
+                                if (it < it_lo || it >= it_hi) continue;
+                            }
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (elect_one()) {
                                 unsigned char* sA = smem + (size_t)stage * L.stage_bytes;
@@ -257,7 +271,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
-            for (int it = 0; it < kiters; ++it) {
+            int n_it = kiters;
+            if constexpr (KS) {
+                const int ks = tile % p.ksplit;
+                n_it = kiters * (ks + 1) / p.ksplit - kiters * ks / p.ksplit;
+            }
+            for (int it = 0; it < n_it; ++it) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
@@ -302,8 +321,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nb = tile % p.n_blocks;
-            int m = tile / p.n_blocks;
+            int tdec = tile;
+            bool first_split = true;                  // the bias / shift is added by ONE of the K shares
+            if constexpr (KS) { first_split = (tdec % p.ksplit) == 0; tdec /= p.ksplit; }
+            const int nb = tdec % p.n_blocks;
+            int m = tdec / p.n_blocks;
             const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
             const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
             const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
@@ -360,7 +382,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         float sc = 1.f, sh = 0.f;
                         if (c < p.Cout) {
                             if (p.scale) sc = __ldg(p.scale + c);
-                            if (p.shift) sh = __ldg(p.shift + shift_off + c);
+                            if (p.shift && (!KS || first_split)) sh = __ldg(p.shift + shift_off + c);
                         }
                         float x = fmaf(__uint_as_float(v[j]), sc, sh);
                         if (p.relu) x = fmaxf(x, 0.f);
@@ -373,6 +395,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                             if (cbase + j < p.Cout) {
                                 float4* dst = reinterpret_cast<float4*>(orow + cbase + j);
                                 float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                                if constexpr (KS) {           // partial sums of the K shares meet in the destination
+                                    float* d1 = reinterpret_cast<float*>(dst);
+                                    atomicAdd(d1, v4.x); atomicAdd(d1 + 1, v4.y); atomicAdd(d1 + 2, v4.z); atomicAdd(d1 + 3, v4.w);
+                                    continue;
+                                }
                                 if (p.accumulate) { const float4 o = *dst; v4.x += o.x; v4.y += o.y; v4.z += o.z; v4.w += o.w; }
                                 *dst = v4;
                             }
@@ -383,6 +410,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         for (int j = 0; j < 32; ++j)
                             if (cbase + j < p.Cout) {
                                 float* dst = orow + (size_t)(cbase + j) * cs;
+                                if constexpr (KS) { atomicAdd(dst, f[j]); continue; }
                                 *dst = p.accumulate ? *dst + f[j] : f[j];
                             }
                     }
@@ -508,6 +536,18 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     p.kchunks = (L.w_k + chunk - 1) / chunk;
     p.store_bf16 = L.y_hi != nullptr;
     p.total_tiles = p.N * p.tilesT * p.tilesH * p.tilesW * p.n_blocks;
+    if (p.ksplit > 1) {
+        // split-K (STAGED): fp32 destination only, linear epilogue (bias allowed, no scale / ReLU), one K segment, N-concatenated form
+        const int kiters = p.kt * p.kh * p.kw * p.kchunks;
+        if (p.store_bf16 || !p.out_f32 || p.relu || p.scale || L.w2_k > 0 || !p.ncat || p.a_single || p.ksplit > 8 || kiters < 2 * p.ksplit) {
+            set_last_error_msg("conv: ksplit needs an fp32-only destination, no scale / ReLU / second K segment, bf16x3 with BN <= 128 and "
+                               ">= 2 K iterations per share");
+            return OTAL_ERR_UNSUPPORTED;
+        }
+        p.total_tiles *= p.ksplit;
+    } else {
+        p.ksplit = 1;
+    }
 
     const uint32_t smem_cap = 227 * 1024 - 1024;  // minus alignment slack
     // prefer (>= 3 stages, double-buffered staging), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
@@ -569,10 +609,13 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         auto* kernel_u8 = conv_igemm_kernel<true, true>;
         OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        auto* kernel_ks = conv_igemm_kernel<true, false, true>;
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         once.mark(once_dev);
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    if (p.a_single) conv_igemm_kernel<true, true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    if (p.ksplit > 1) conv_igemm_kernel<true, false, true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
+    else if (p.a_single) conv_igemm_kernel<true, true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
     else if (p.ncat) conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
     else conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);
     OTAL_CUDA_TRY(cudaGetLastError());
@@ -622,6 +665,7 @@ int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {
     p.out_ncdhw = d->y_f32_ncdhw ? 1 : 0;
     p.scale = d->scale; p.shift = d->shift; p.out_f32 = d->y_f32;
     p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+    p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
     L.w_hi = d->w_hi; L.w_lo = d->w_lo; L.w_k = d->Cin; L.y_hi = d->y_hi; L.y_lo = d->y_lo;
     L.To = (d->T + st - 1) / st; L.Ho = (d->H + sh - 1) / sh; L.Wo = (d->W + sw - 1) / sw;
 

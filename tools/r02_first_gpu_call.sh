@@ -14,15 +14,15 @@ timeout 300 python tools/conv1a_bench.py > gpurun_out/r02_conv1a_bench.txt 2>&1;
 # A/B of every staged switch: two interleaved passes over (baseline, each switch alone, the two launch-shape switches together);
 # `value` of each JSON line is the CUDA-event step time with resident inputs (no e2e leg, no CPU baseline: ~40 s per run)
 for pass in 1 2; do
-  for cfg in base OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 "OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES" OTAL_FUSE_B12A; do
-    unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A
+  for cfg in base OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 "OTAL_CONV_1X1_BN64 OTAL_CONV_PREFER_STAGES" OTAL_FUSE_B12A OTAL_CONV_KSPLIT; do
+    unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A OTAL_CONV_KSPLIT
     if [ "$cfg" != base ]; then for v in $cfg; do export $v=1; done; fi
     tag=$(echo "$cfg" | tr ' ' '+')
     timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02_ab_${tag}_pass${pass}.json 2>> gpurun_out/r02_bench_err.log
     echo "bench [$tag] pass $pass rc=$? $(python -c "import json,sys; print(json.load(open('gpurun_out/r02_ab_${tag}_pass${pass}.json'))['ms_per_step'])" 2>/dev/null) ms/step"
   done
 done
-unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A
+unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A OTAL_CONV_KSPLIT
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|border_class|clip_ingest' -c 12 \
   -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu conv1a rc=$?"
 # where the step goes now, per layer (event-timed eager pass), and a source-level look at the HBM-bound 1x1 convs, which run
