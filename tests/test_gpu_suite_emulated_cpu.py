@@ -3,7 +3,8 @@
 The GPU test modules move their data with `.cuda()`; here `.cuda()` is the identity, `engine.build_opental*` build on the CPU
 with the loss in its torch formulation, and every `_lib.call` lands in the emulator.  So the same assertions — golden vectors
 of the reference, same tolerances — check the product's host code on every CPU run: per-endpoint backbone features, the
-self-supervised (triplet) pass and its frame-map form, the closed-set and the ActivityNet flavours, checkpoint / resume.
+self-supervised (triplet) pass, the closed-set and the ActivityNet flavours, the head with forced windows, inference post-processing
+(the frame-map form of the SSL pass and checkpoint / resume are covered by tests/test_model_emulated_cpu.py).
 The kernels are what the real `-m gpu` run checks."""
 import functools
 import importlib
@@ -61,16 +62,10 @@ def test_ssl_triplet_pass(emulated, golden_dir):
     gpu_test("test_model_gpu", "test_ssl_triplet_pass_matches_reference_golden")(golden_dir)
 
 
-def test_ssl_pass_through_frame_map(emulated):
-    gpu_test("test_model_gpu", "test_ssl_pass_through_frame_map_equals_materialised_clip")()
-
-
 def test_closed_set_model(emulated, golden_dir):
     gpu_test("test_model_closed_gpu", "test_closed_set_forward_focal_loss_backward_match_reference_golden")(golden_dir, "biased", math.log(32.0))
 
 
-def test_checkpoint_resume(emulated, tmp_path):
-    gpu_test("test_checkpoint_gpu", "test_resume_is_bit_exact_and_matches_torch_adam")(tmp_path)
 
 
 def test_activitynet_model(emulated, golden_dir):
