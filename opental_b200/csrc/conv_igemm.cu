@@ -607,11 +607,18 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        auto* kernel_u8 = conv_igemm_kernel<true, true>;
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        auto* kernel_ks = conv_igemm_kernel<true, false, true>;
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         once.mark(once_dev);
+    }
+    if (p.a_single || p.ksplit > 1) {
+        // the staged instantiations are configured on their first use only: nothing about them can affect the default path
+        static OncePerDevice once_staged;
+        if (once_staged.need(&once_dev)) {
+            auto* kernel_u8 = conv_igemm_kernel<true, true>;
+            OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            auto* kernel_ks = conv_igemm_kernel<true, false, true>;
+            OTAL_CUDA_TRY(cudaFuncSetAttribute(kernel_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            once_staged.mark(once_dev);
+        }
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     if (p.ksplit > 1) conv_igemm_kernel<true, false, true><<<grid, kConvThreads, smem_bytes, stream>>>(maps, p);

@@ -439,8 +439,14 @@ static int wg_finish_and_launch(WgParams& p, WgMaps& maps, const uint16_t* d_hi,
     int once_dev = 0;
     if (once.need(&once_dev)) {
         OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         once.mark(once_dev);
+    }
+    if (p.x_single) {       // the staged instantiation is configured on its first use only
+        static OncePerDevice once_staged;
+        if (once_staged.need(&once_dev)) {
+            OTAL_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            once_staged.mark(once_dev);
+        }
     }
     const int grid = p.total_items < wg_num_sms() ? p.total_items : wg_num_sms();
     if (p.x_single) conv_wgrad_kernel<true><<<grid, kWgThreads, SL.total + 1024, stream>>>(maps, p);
