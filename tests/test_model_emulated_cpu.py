@@ -236,3 +236,19 @@ def test_staged_split_k_of_the_head_convs_keeps_the_model_outputs(monkeypatch, g
     assert ops._auto_ksplit(8, 136, 1, 1, (128, 1, 1), 512, 512, 3) == 1       # 16 tiles x 8 blocks = 128 CTAs: no room
     assert ops._auto_ksplit(1, 136, 1, 1, (128, 1, 1), 512, 512, 3) == 4       # 2 x 8 = 16 CTAs, 24 K iterations
     assert ops._auto_ksplit(1, 136, 1, 1, (128, 1, 1), 64, 512, 1) == 1        # a single K iteration cannot be split
+
+
+def test_single_pass_bf16_mode_host_path(monkeypatch, golden):
+    """precision='bf16' (one plane per tensor, `bench.py --precision bf16`): the same host code with `lo` planes absent; the
+    outputs land within the single-pass error class (~1e-2) of the reference goldens."""
+    from opental_b200 import engine
+    arrays, _ = golden
+    emu = abi_emu.install(monkeypatch)
+    net, crit = engine.build_opental(device="cpu", precision="bf16", epoch=1)
+    net.load_state_dict(O.synthetic_state_dict(O.OracleConfig()))
+    with torch.no_grad():
+        out = net(O.synthetic_clip(0).unsqueeze(0))
+    errs = {k: rel(out[k], torch.from_numpy(arrays[f"init.{k}"])) for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")}
+    # clearly not the bf16x3 accuracy class, clearly the right network: coarse heads ~1e-2, refined heads up to ~1e-1 (rounded
+    # proposal windows flip by a frame, SURVEY App. E2: 1.6e-2 .. 8e-2 for single-pass bf16)
+    assert all(1e-4 < errs[k] < 5e-2 for k in ("loc", "conf", "act")) and max(errs.values()) < 0.3, errs
