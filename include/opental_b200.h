@@ -35,6 +35,9 @@ extern "C" {
 
 OTAL_API const char* otal_last_error(void);
 OTAL_API int otal_abi_version(void);
+/* sizeof of a descriptor struct of this header by name ("otal_conv_desc", ...), 0 if unknown: a binding compares it with
+ * the size of its own mirror (opental_b200/_lib.py does at load time) so that a stale mirror fails loudly, not silently. */
+OTAL_API int otal_abi_sizeof(const char* name);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BoundaryMaxPooling — replaces boundary_max_pooling_cuda.forward / .backward

@@ -80,6 +80,7 @@ class MslDesc(Structure):
 SIGNATURES = {
     "otal_last_error": (c_char_p, []),
     "otal_abi_version": (c_int, []),
+    "otal_abi_sizeof": (c_int, [c_char_p]),
     "otal_bmp_forward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_bmp_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_bmp_forward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -123,6 +124,9 @@ SIGNATURES = {
     "otal_ncdhw_to_ndhwc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
+STRUCT_MIRRORS = {"otal_conv_desc": ConvDesc, "otal_conv1a_desc": Conv1aDesc, "otal_wgrad_desc": WgradDesc,
+                  "otal_conv1a_wgrad_desc": Conv1aWgradDesc, "otal_pool_desc": PoolDesc, "otal_msl_desc": MslDesc}
+
 _lib = None
 
 
@@ -142,6 +146,10 @@ def load() -> ctypes.CDLL:
             fn.argtypes = args
         if lib.otal_abi_version() != 1:
             raise RuntimeError("libopental_b200.so ABI version mismatch: rebuild the library")
+        for cname, mirror in STRUCT_MIRRORS.items():
+            if lib.otal_abi_sizeof(cname.encode()) != ctypes.sizeof(mirror):
+                raise RuntimeError(f"{cname}: the ctypes mirror ({ctypes.sizeof(mirror)} bytes) does not match the library "
+                                   f"({lib.otal_abi_sizeof(cname.encode())} bytes): rebuild the library or update _lib.py")
         _lib = lib
     return _lib
 

@@ -67,4 +67,16 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 extern "C" {
 const char* otal_last_error(void) { return otal::g_err; }
 int otal_abi_version(void) { return OTAL_ABI_VERSION; }
+
+// sizeof of a descriptor struct by name (0 = unknown): lets a binding check its mirror of the struct against this build.
+int otal_abi_sizeof(const char* name) {
+    if (!name) return 0;
+    if (!strcmp(name, "otal_conv_desc")) return (int)sizeof(otal_conv_desc);
+    if (!strcmp(name, "otal_conv1a_desc")) return (int)sizeof(otal_conv1a_desc);
+    if (!strcmp(name, "otal_wgrad_desc")) return (int)sizeof(otal_wgrad_desc);
+    if (!strcmp(name, "otal_conv1a_wgrad_desc")) return (int)sizeof(otal_conv1a_wgrad_desc);
+    if (!strcmp(name, "otal_pool_desc")) return (int)sizeof(otal_pool_desc);
+    if (!strcmp(name, "otal_msl_desc")) return (int)sizeof(otal_msl_desc);
+    return 0;
+}
 }

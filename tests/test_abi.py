@@ -38,6 +38,18 @@ def test_abi_version_and_error_string():
     assert isinstance(_lib.last_error(), str)
 
 
+def test_struct_mirrors_match_the_library():
+    """Every descriptor struct of the header has the size of its ctypes mirror (checked again at load time by _lib.load)."""
+    from opental_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "opental_b200.h")).read()
+    declared = sorted(set(re.findall(r"typedef struct (otal_\w+_desc)", header)))
+    assert declared == sorted(_lib.STRUCT_MIRRORS), (declared, sorted(_lib.STRUCT_MIRRORS))
+    for name, mirror in _lib.STRUCT_MIRRORS.items():
+        assert lib.otal_abi_sizeof(name.encode()) == ctypes.sizeof(mirror) > 0, name
+    assert lib.otal_abi_sizeof(b"no_such_struct") == 0 and lib.otal_abi_sizeof(None) == 0
+
+
 def test_bad_arguments_return_codes_without_gpu():
     # argument validation happens before any CUDA call, so it is testable on a CPU-only box
     from opental_b200 import _lib
