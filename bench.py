@@ -126,6 +126,27 @@ def cpu_training_steps(steps: int, warmup: int, batch: int = 1):
     return batch * 1000.0 / ms, ms, cores
 
 
+def cpu_forward_steps(steps: int = 3, warmup: int = 1, batch: int = 1):
+    """Forward-only counterpart of cpu_training_steps (the CPU baseline reports (i) forward and (ii) forward + loss
+    + backward): clips/s of `O.bdnet_forward` under no_grad, median of `steps` runs."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import opental_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(cfg)
+    x = torch.stack([O.synthetic_clip(i) for i in range(batch)])
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.bdnet_forward(x, sd, cfg, compat=True)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    return batch / times[len(times) // 2]
+
+
 def host_info() -> dict:
     """CPU model and torch version of the box the CPU numbers were taken on (SURVEY §8d 'CPU baseline timing')."""
     import torch
@@ -156,6 +177,7 @@ def run_reference(args):
                    "reference_sample": "CPU restatement of the reference (oracle/, torch CPU fp32, all host cores); one step = forward + "
                                        "loss + backward of ONE clip (no optimizer), rank 0 only"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", **host_info(),
+                         "forward_only_clips_per_s": cpu_forward_steps(3, 1, 1),
                          "sample": f"{steps} training steps of 1 clip after {warm} warm-up (forward + loss + backward, torch CPU fp32)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -359,6 +381,7 @@ def run_native(args):
     if not args.no_cpu_baseline:
         v, cms, cores = cpu_training_steps(8, 1, batch=2)
         cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", **host_info(),
+                    "forward_only_clips_per_s": cpu_forward_steps(3, 1, 1),
                     "sample": "8 training steps of 2 clips after 1 warm-up, ~10 s of CPU work (forward + loss + backward, torch CPU "
                               "fp32 restatement of the reference in oracle/, all host cores)",
                     "ms_per_step": cms}
