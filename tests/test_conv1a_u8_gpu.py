@@ -68,7 +68,7 @@ def test_conv1a_fwd_u8(shape):
     if H == W:
         a = ops.clip_ingest_u8(px.cuda(), W, raw=True)
     else:       # non-square: build the raw plane by hand (the ingest kernel crops squares)
-        hi = torch.zeros(N, T, H, W + 8, 4, dtype=torch.bfloat16, device="cuda")
+        hi = torch.zeros(N, T, H, W + 8, 4, dtype=torch.bfloat16).cuda()
         hi[:, :, :, 2:W + 2, :3] = px.cuda().to(torch.bfloat16)
         a = ops.Planes(hi, None)
     y = ops.conv1a_fwd(a, ops.pack_conv1a_weight(w), W, scale=sc, shift=tab, relu=True, u8=True)
@@ -105,7 +105,7 @@ def test_conv1a_wgrad_u8(shape):
     gy = torch.randn(y.shape, generator=g)
     (gw_ref,) = torch.autograd.grad(y, w, gy)
     d = ops.split_bf16(gy.permute(0, 2, 3, 4, 1).contiguous().cuda())
-    dw = torch.zeros(49, 64, 32, device="cuda")
+    dw = torch.zeros(49, 64, 32).cuda()
     ops.conv1a_wgrad(ops.clip_ingest_u8(px.cuda(), W, raw=True), d, dw, W, u8=True)
     got = ops.conv1a_u8_weight_grad(dw, ops.border_class_sums(d), 3)
     assert rel(got.cpu(), gw_ref) < TOL

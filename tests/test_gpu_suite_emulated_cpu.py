@@ -89,3 +89,15 @@ def test_inference_post_processing(emulated, golden_dir):
 
 def test_activitynet_ssl_triplet_pass(emulated, golden_dir):
     gpu_test("test_model_anet_gpu", "test_anet_ssl_triplet_pass_matches_reference_golden")(golden_dir)
+
+
+def test_staged_uint8_conv1a_gpu_tests_run_against_the_emulation(emulated):
+    """tests/test_conv1a_u8_gpu.py is the first thing the next GPU call runs: its own logic (shapes, helper calls, tolerances) is
+    checked here against the emulated entry points, so that a GPU minute is never spent on a broken test."""
+    mod = importlib.import_module("test_conv1a_u8_gpu")
+    mod.test_raw_ingest_is_exact()
+    for shape in [(1, 16, 24, 24), (2, 12, 16, 32), (1, 8, 8, 16)]:
+        mod.test_conv1a_fwd_u8(shape)
+    mod.test_border_class_sums()
+    for shape in [(2, 12, 16, 16), (1, 8, 16, 16)]:
+        mod.test_conv1a_wgrad_u8(shape)
