@@ -23,6 +23,7 @@ for pass in 1 2; do
   done
 done
 unset OTAL_U8_CONV1A OTAL_CONV_PREFER_STAGES OTAL_CONV_1X1_BN64 OTAL_FUSE_B12A OTAL_CONV_KSPLIT
+python tools/ab_summary.py gpurun_out > gpurun_out/r02_ab_summary.txt 2>&1; cat gpurun_out/r02_ab_summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv_wgrad|border_class|clip_ingest' -c 12 \
   -o gpurun_out/r02_conv1a python tools/conv1a_bench.py --ncu > gpurun_out/r02_conv1a_ncu.log 2>&1; echo "ncu conv1a rc=$?"
 # where the step goes now, per layer (event-timed eager pass), and a source-level look at the HBM-bound 1x1 convs, which run
