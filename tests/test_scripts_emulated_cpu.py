@@ -143,3 +143,13 @@ def test_test_thumos_script_smoke(monkeypatch, tmp_path, capsys):
     for d in dets:
         assert set(d) == {"label", "score", "segment", "uncertainty", "actionness"} and d["label"].startswith("Class") and len(d["segment"]) == 2
     assert "detections of 1 videos" in capsys.readouterr().out
+
+
+def test_train_synthetic_tool_smoke(monkeypatch, tmp_path, capsys):
+    """tools/train_synthetic.py — the first training run of the next GPU call — through the emulation: synthetic videos, window
+    index, loader threads, train_loop.fit with the SSL pass, the IBM switch and the capture bookkeeping (eager here)."""
+    abi_emu.install(monkeypatch)
+    rc = load_tool("train_synthetic").main(["--videos", "2", "--epochs", "2", "--batch", "1", "--ibm-start", "2", "--steps-per-epoch", "1",
+                                            "--no-graph", "--device", "cpu", "--loader-threads", "2", "--out", str(tmp_path / "out")])
+    text = capsys.readouterr().out
+    assert rc == 0 and "TRAIN_SYNTHETIC OK" in text and "windows from 2 videos" in text and "Epoch-2 Train Loss" in text

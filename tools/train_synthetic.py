@@ -8,6 +8,7 @@ GPUs, through the product loader (opental_b200/dataset.py + loader.py).  A devel
 Checks while it runs: losses finite, the step graph is re-captured only when the batch flavour / IBM switch changes,
 checkpoints appear after epoch 10 and `--resume E` continues from them, ranks stay bit-identical."""
 import argparse
+import itertools
 import os
 import random
 import sys
@@ -40,7 +41,7 @@ def synthetic_dataset(n_videos: int, seed: int = 0):
     return infos, annos, data
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--videos", type=int, default=6)
     ap.add_argument("--epochs", type=int, default=12)
@@ -49,11 +50,14 @@ def main():
     ap.add_argument("--resume", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--loader-threads", type=int, default=4)
+    ap.add_argument("--steps-per-epoch", type=int, default=0, help="stop every epoch after this many steps (smoke runs)")
+    ap.add_argument("--device", default="cuda", help="'cuda' (the product has no CPU path; other values are for the test harness)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "train_synth"))
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+    dev = torch.device("cuda", local) if args.device == "cuda" else torch.device(args.device)
+    if dev.type == "cuda":
+        torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     clip_length, crop = 256, 96
@@ -75,13 +79,15 @@ def main():
 
     def make_batches(epoch):
         # the product's loader: window index -> loader threads -> pinned ring -> copy stream (opental_b200/loader.py)
-        return loader.Prefetcher(ds, args.batch, epoch, rank=rank, world=world, seed=0, device=dev, workers=args.loader_threads,
-                                 crop_offsets=net.backbone.crop_offsets)
+        pf = loader.Prefetcher(ds, args.batch, epoch, rank=rank, world=world, seed=0, device=dev, workers=args.loader_threads,
+                               crop_offsets=net.backbone.crop_offsets)
+        return itertools.islice(iter(pf), args.steps_per_epoch) if args.steps_per_epoch > 0 else pf
 
     ck, st = os.path.join(args.out, "checkpoint"), os.path.join(args.out, "train_state")
     hist = train_loop.fit(tr, make_batches, max_epoch=args.epochs, resume=args.resume, checkpoint_path=ck, train_state_path=st,
                           use_graph=not args.no_graph)
-    torch.cuda.synchronize()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
     ok = all(np.isfinite(h["cost"]) for h in hist if h.get("steps"))
     if world > 1:
         chk = torch.stack([w.double().sum() for w, _ in tr.groups])
