@@ -839,10 +839,143 @@ def anet_ssl_cases():
     ns.restore_cuda()
 
 
+def batch8_cases():
+    """The BENCH configuration (BASELINE configs[1]/[2]: batch 8 per GPU) as a golden: reference BDNet forward +
+    MultiSegmentLoss (epoch 1 and 11) + backward on synthetic clips 0..7 — the whole-model path at B = 8 exercises the
+    `[P,B]`-vs-`[B,P]` IoU-calibration pairing (App. D) that B = 1 cannot.  `--batch8` (about a minute, ~25 GB)."""
+    ns = ref_loader.load_reference()
+    cfg = O.OracleConfig()
+    B = 8
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(32.0))
+    net = ns.BDNet(in_channels=3, training=False, use_edl=True)
+    net.load_state_dict(sd)
+    net.train()
+    x = torch.stack([O.synthetic_clip(i) for i in range(B)])
+    targets = [O.synthetic_targets(i, num_classes=cfg.num_classes) for i in range(B)]
+    targets[3] = targets[3][:1].clone()                                   # ragged: 1, 2 and 3 segments per clip
+    targets[5] = torch.cat([targets[5], torch.tensor([[0.42, 0.47, 3.0]])])
+    summary, arrays = dict(n_segments=[int(t.shape[0]) for t in targets]), {}
+    net.zero_grad()
+    out_r = net(x)
+    with torch.no_grad():
+        out_o = O.bdnet_forward(x, sd, cfg, compat=True)
+    errs = {k: rel(out_o[k].detach(), out_r[k].detach()) for k in out_r if out_r[k] is not None}
+    # Everything downstream of the proposal windows is a DISCONTINUOUS function of `loc` (BDNet.py:355-384 rounds the window
+    # ends to frames): with 8 x 126 x 4 window ends, a 3e-6 difference in `loc` moves one of them across an integer and the
+    # pooled maximum of that prior changes by ~5e-4 of the output range.  So: the coarse outputs at TOL, the refined ones
+    # row-wise — all but a handful of (clip, prior) rows at TOL.
+    refined = ("prop_loc", "prop_conf", "center", "prop_act", "prop_unct")
+    assert max(v for k, v in errs.items() if k not in refined) < TOL, errs
+    flipped = set()
+    for k in refined:
+        d = (out_o[k].detach() - out_r[k].detach()).abs().reshape(B, 126, -1).amax(-1) / out_r[k].detach().abs().max()
+        flipped |= {tuple(i) for i in (d > TOL).nonzero().tolist()}
+        assert errs[k] < 2e-3, errs
+    assert len(flipped) <= 4, flipped
+    summary["oracle_vs_ref_flipped_rows"] = sorted(flipped)
+    for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "unct", "prop_unct"):
+        arrays[f"b8.{k}"] = out_r[k].detach().numpy()
+    for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop"):
+        arrays[f"b8.{k}.sample"] = out_r[k].detach().numpy()[:, ::8, ::8].copy()
+    for epoch in (1, 11):
+        crit = ns.MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=ns.config["training"]["edl_config"],
+                                   os_head=True, act_config=ns.config["training"]["act_config"])
+        crit.cls_loss.epoch = epoch
+        loss_r = crit(out_r, [t.clone() for t in targets])
+        state = O.LossState(epoch=epoch)
+        loss_o = O.multisegment_loss({k: (v.detach() if torch.is_tensor(v) else v) for k, v in out_r.items()}, targets, state, cfg)
+        lerrs = [abs(float(a) - float(b)) / max(abs(float(b)), 1e-6) for a, b in zip(loss_o, loss_r)]
+        assert max(lerrs) < 5e-5, lerrs
+        assert torch.allclose(crit.cls_loss.weight_accum, state.weight_accum, atol=1e-6)
+        cost_r = loss_r[0] + 10 * loss_r[1] + loss_r[2] + 10 * loss_r[3] + loss_r[4] + loss_r[5] + loss_r[6]
+        summary[f"e{epoch}"] = dict(losses=[float(v) for v in loss_r], cost=float(cost_r))
+        arrays[f"b8.e{epoch}.weight_accum"] = crit.cls_loss.weight_accum.numpy().copy()
+    cost_r.backward()                                                     # epoch-11 cost
+    fp = {}
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad
+        fp[k] = [float(g.sum()), float(g.abs().sum())]
+        arrays[f"b8.e11.grad.{k}"] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy().copy()
+    summary["e11"]["grad_fingerprint"] = fp
+    print(f"[batch8] oracle vs reference outputs {max(errs.values()):.2e}; losses e1 {summary['e1']['losses']} e11 {summary['e11']['losses']}")
+    np.savez_compressed(os.path.join(GOLD, "model_thumos_b8.npz"), **arrays)
+    with open(os.path.join(GOLD, "model_thumos_b8.json"), "w") as fh:
+        json.dump(summary, fh, indent=1)
+    ns.restore_cuda()
+
+
+TRAJ_STEPS, TRAJ_LR, TRAJ_WD = 5, 1e-5, 1e-3
+
+
+def trajectory_cases():
+    """A 5-step training trajectory of the reference's own modules under `torch.optim.Adam(net.parameters(), lr,
+    weight_decay)` (thumos14/train.py:226-252, 321-323): batch of 2 clips, epoch 11 (IBM on: the 50-bin EMA evolves from step
+    to step), cost incl. the boundary BCE terms of forward_one_epoch (train.py:186-200, restated here because importing
+    train.py needs tensorboardX and creates directories).  lr = 1e-5, weight decay 1e-3 (the config's values): the cost falls 77.2 -> ~70 in five steps.  Stores cost / losses per step and the per-tensor |delta w| sums.  `--trajectory`."""
+    ns = ref_loader.load_reference()
+    cfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(cfg, loc_bias_shift=math.log(32.0))
+    net = ns.BDNet(in_channels=3, training=False, use_edl=True)
+    net.load_state_dict(sd)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=TRAJ_LR, weight_decay=TRAJ_WD)
+    crit = ns.MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=ns.config["training"]["edl_config"],
+                               os_head=True, act_config=ns.config["training"]["act_config"])
+    crit.cls_loss.epoch = 11
+    x = torch.stack([O.synthetic_clip(i) for i in range(2)])
+    targets = [O.synthetic_targets(i, num_classes=cfg.num_classes) for i in range(2)]
+    scores = torch.stack([O.synthetic_scores(t) for t in targets])
+    # the oracle runs the same trajectory (functional weights + its own Adam)
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "num_batches" not in k else v)
+           for k, v in sd.items()}
+    train_keys = [k for k, p in net.named_parameters() if p.requires_grad]
+    opt_o = torch.optim.Adam([sdo[k] for k in train_keys], lr=TRAJ_LR, weight_decay=TRAJ_WD)
+    state = O.LossState(epoch=11)
+    steps = []
+    for s in range(TRAJ_STEPS):
+        out = net(x)
+        l, c, pl, pc, ct, act, pact = crit(out, [t.clone() for t in targets])
+        ls, le = O.boundary_bce(out["start"], out["end"], scores)
+        sc4 = torch.nn.functional.interpolate(scores, scale_factor=1.0 / 4)
+        a, b = O.boundary_bce(out["start_loc_prop"], out["end_loc_prop"], sc4)
+        c2, d = O.boundary_bce(out["start_conf_prop"], out["end_conf_prop"], sc4)
+        ls = ls + 0.1 * (a + c2); le = le + 0.1 * (b + d)
+        cost = l + 10 * c + pl + 10 * pc + ct + ls + le + act + pact
+        opt.zero_grad()
+        cost.backward()
+        opt.step()
+        out_o = O.bdnet_forward(x, sdo, cfg, compat=True)
+        cost_o, parts = O.training_cost(out_o, targets, scores, state, cfg)
+        opt_o.zero_grad()
+        cost_o.backward()
+        opt_o.step()
+        e = abs(float(cost_o) - float(cost)) / abs(float(cost))
+        print(f"[trajectory] step {s}: reference cost {float(cost):.6f}  oracle {float(cost_o):.6f}  rel {e:.2e}")
+        # the trajectory is chaotic beyond a few steps (matching flips a prior when an IoU crosses 0.5, Adam's first steps are
+        # sign-like): two fp32 CPU implementations agree to < 1e-4 for three steps and drift to ~1e-3 afterwards.  The drift
+        # is recorded; tests allow max(1e-3, 3 x drift) at each step.
+        assert s > 2 or e < 2e-4, (s, float(cost), float(cost_o))
+        steps.append(dict(cost=float(cost), oracle_rel=e, losses=[float(v) for v in (l, c, pl, pc, ct, act, pact)], loss_start=float(ls),
+                          loss_end=float(le)))
+    delta = {k: float((p.detach() - sd[k]).abs().sum()) for k, p in net.named_parameters() if p.requires_grad}
+    arrays = {"weight_accum": crit.cls_loss.weight_accum.numpy().copy()}
+    with open(os.path.join(GOLD, "trajectory_thumos.json"), "w") as fh:
+        json.dump(dict(steps=steps, lr=TRAJ_LR, weight_decay=TRAJ_WD, delta_abs_sum=delta,
+                       delta_total=float(sum(delta.values()))), fh, indent=1)
+    np.savez_compressed(os.path.join(GOLD, "trajectory_thumos.npz"), **arrays)
+    ns.restore_cuda()
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    if "--anet" in sys.argv:
+    if "--batch8" in sys.argv:
+        batch8_cases()
+    elif "--trajectory" in sys.argv:
+        trajectory_cases()
+    elif "--anet" in sys.argv:
         anet_cases()
     elif "--ssl" in sys.argv:
         ssl_cases()
