@@ -396,8 +396,8 @@ def run_native(args):
                    "input": "uint8 frames [B,256,112,112,3], centre crop 96 + normalisation in the ingest kernel",
                    "l2": "per-step activations and gradients (several GB) exceed the 126 MB L2; two alternating input batches",
                    "ssl_pass": bool(args.ssl), "cuda_graph": not args.no_graph,
-                   "conv1a": "raw-uint8 form (OTAL_U8_CONV1A=1)" if os.environ.get("OTAL_U8_CONV1A") == "1" else "bf16x3 on the normalised clip",
-                   "staged_switches": sorted(k for k in ("OTAL_U8_CONV1A", "OTAL_CONV_PREFER_STAGES", "OTAL_CONV_1X1_BN64", "OTAL_FUSE_B12A", "OTAL_CONV_KSPLIT", "OTAL_NO_NCAT",
+                   "conv1a": "bf16x3 on the normalised clip (OTAL_U8_CONV1A=0)" if os.environ.get("OTAL_U8_CONV1A") == "0" else "raw uint8 pixels, one exact bf16 plane",
+                   "staged_switches": sorted(k for k in ("OTAL_U8_CONV1A", "OTAL_FUSE_B12A", "OTAL_CONV_KSPLIT", "OTAL_NO_NCAT",
                                                          "OTAL_NO_WGRAD_OVERLAP") if os.environ.get(k))},
         "clocks": clocks,
         "e2e": e2e,

@@ -123,18 +123,21 @@ class I3DBackbone(nn.Module):
         self._w_total, self._bn_total = w_off, bn_off
         self._flat_dev = None
         self._anchor = None
-        self.on_backward_start = None     # optional callback (the trainer overlaps the head's all-reduce here)
+        self.on_backward_start = None     # optional callback (the trainer overlaps the head's all-reduce here): fired when
+                                          # the LAST pending backbone backward of the step starts (see _BackboneFn)
+        self._pending_bwd = 0             # backbone forwards of this step whose backward has not started yet
         self.crop_size = 96               # uint8 input path: crop extent (config dataset.training.crop_size)
         self.crop_offsets = None          # optional int32 [N,3] device tensor (row, column, mirror) per sample
         self._parked: list = []           # (event, tensors) of blocks whose side-stream weight gradients may still run
         self.frame_map = None             # optional int32 [N,T] device tensor: temporal gather in the ingest kernel (SSL cut-paste)
-        # STAGED (off by default, not yet validated on a GPU): Conv3d_1a fwd + wgrad on the raw uint8 pixel values — one exact
-        # bf16 plane, one tensor-core pass instead of 2 (fwd) / 3 (wgrad); ops.conv1a_u8_scale_shift / conv1a_u8_weight_grad
-        self.u8_conv1a = os.environ.get("OTAL_U8_CONV1A") == "1"
-        # STAGED (off by default, to be A/B-measured): the two bottleneck 1x1 convs of an inception block (b1a, b2a: same input,
-        # adjacent weights / BN scales / outputs by construction) as ONE forward launch and ONE weight-gradient launch — b2a alone
-        # is a 16..48-channel conv, a launch-latency-bound sliver.  Host-side only: same kernels, same memory layout.
-        self.fuse_b12a = os.environ.get("OTAL_FUSE_B12A") == "1"
+        # Conv3d_1a fwd + wgrad on the raw uint8 pixel values (uint8 input only) — one exact bf16 plane, one tensor-core pass
+        # instead of 2 (fwd) / 3 (wgrad); ops.conv1a_u8_scale_shift / conv1a_u8_weight_grad.  Round-2 GPU A/B: 23.47 -> 22.99 ms
+        # per step, parity 9e-6 / 2.4e-5 vs the bf16x3 form (tests/test_conv1a_u8_gpu.py).  OTAL_U8_CONV1A=0 switches it off.
+        self.u8_conv1a = os.environ.get("OTAL_U8_CONV1A", "1") != "0"
+        # The two bottleneck 1x1 convs of an inception block (b1a, b2a: same input, adjacent weights / BN scales / outputs by
+        # construction) as ONE forward launch and ONE weight-gradient launch — b2a alone is a 16..48-channel conv, a
+        # launch-latency-bound sliver.  Host-side only: same kernels, same memory layout (-0.18 ms per step).  OTAL_FUSE_B12A=0: off.
+        self.fuse_b12a = os.environ.get("OTAL_FUSE_B12A", "1") != "0"
         self.reset_parameters()
 
     # ------------------------------------------------------------------------------------------------ structure
@@ -487,6 +490,8 @@ class _BackboneFn(torch.autograd.Function):
         out = net.forward_planes(x, saved)
         ctx.net = net
         ctx.saved = saved if any(ctx.needs_input_grad) else None
+        if ctx.saved is not None:
+            net._pending_bwd += 1
         f4, f5 = out["Mixed_4f"], out["Mixed_5c"]
         return f4, f5
 
@@ -498,7 +503,11 @@ class _BackboneFn(torch.autograd.Function):
         ctx.saved = None
         saved.pop("Mixed_4f.f32", None)
         saved.pop("Mixed_5c.f32", None)
-        if ctx.net.on_backward_start is not None:
-            ctx.net.on_backward_start()          # everything downstream of the backbone has its gradient by now
+        # A step with the SSL pass has TWO backbone nodes; autograd runs the later-created one (the SSL branch) first, while
+        # the main pass's head backward has not run yet.  Only when the last pending node starts has everything downstream
+        # of the backbone — both passes — accumulated its gradient.
+        ctx.net._pending_bwd = max(ctx.net._pending_bwd - 1, 0)
+        if ctx.net.on_backward_start is not None and ctx.net._pending_bwd == 0:
+            ctx.net.on_backward_start()
         ctx.net.backward_planes(saved, g4, g5)
         return None, None, None

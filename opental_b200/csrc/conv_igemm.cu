@@ -511,16 +511,6 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         }
     }
     {
-        // STAGED switch (OTAL_CONV_1X1_BN64=1, default off, to be A/B-measured): 64-wide N blocks for the large 1x1 convs — a
-        // 48 KB stage instead of 64..96 KB, i.e. 3-4 loads in flight per SM; the second N block's A tile comes from L2 (tiles of
-        // one position block are consecutive, so they run side by side on neighbouring CTAs).  DESIGN §9.4.
-        static const bool bn64 = getenv("OTAL_CONV_1X1_BN64") != nullptr;
-        const int m_tiles = p.N * p.tilesT * p.tilesH * p.tilesW;
-        if (bn64 && p.kt * p.kh * p.kw == 1 && L.w2_k == 0 && p.BN > 64 && p.Cout % 64 == 0 && m_tiles >= 4 * num_sms()) {
-            p.BN = 64; p.n_blocks = p.Cout / 64;
-        }
-    }
-    {
         // N-concatenated hi|lo weights (see ConvParams::ncat): needs 2*BN accumulator columns and B_lo contiguous after B_hi
         static const bool off = getenv("OTAL_NO_NCAT") != nullptr;
         const uint32_t rowb = p.k32 ? 64u : 128u;
@@ -554,19 +544,6 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     int nst = 0, nbuf = p.store_bf16 ? 2 : 0;
     for (int s = kMaxStages; s >= 3 && !nst; --s)
         if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = s;
-    {
-        // STAGED switch (OTAL_CONV_PREFER_STAGES=1, default off, to be A/B-measured): pipeline depth before store overlap — when
-        // ONE staging buffer buys at least one more pipeline stage than two do (BN 64..128 in bf16x3: 48-64 KB per stage), take
-        // it.  The HBM-bound 1x1 convs run at ~22 % of DRAM bandwidth with every unit idle: the bytes a CTA has in flight (2
-        // stages = 64 KB of A) do not cover the DRAM latency of its 128-byte TMA rows.
-        static const bool prefer_stages = getenv("OTAL_CONV_PREFER_STAGES") != nullptr;
-        if (prefer_stages && p.store_bf16 && nst < kMaxStages) {
-            int s1 = 0;
-            for (int s = kMaxStages; s >= 3 && !s1; --s)
-                if (conv_smem_layout(p.BN, p.nsplit, s, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) s1 = s;
-            if (s1 > (nst ? nst : 2)) { nst = s1; nbuf = 1; }
-        }
-    }
     if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = 2;
     if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) { nst = 2; nbuf = 1; }
     if (!nst) { set_last_error_msg("conv: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }

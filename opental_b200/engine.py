@@ -187,6 +187,8 @@ class Trainer:
             self._launch_head_allreduce()
 
     def _launch_head_allreduce(self) -> None:
+        if self._head_launched:                                # once per step, whoever asks first
+            return
         self.reducer.launch(range(1, len(self.groups)))        # head buffers: complete once the backbone backward starts
         self._head_launched = True
 
@@ -197,6 +199,7 @@ class Trainer:
 
     # ---------------------------------------------------------------------------------------------- one step
     def zero_grad(self) -> None:
+        self.net.backbone._pending_bwd = 0      # a forward without backward (evaluation) must not hold back the next step's hook
         self.net.backbone._bind_grads()
         if self.hc is not None:
             self.hc.bind_grads()

@@ -50,6 +50,10 @@ def detect_video(net, frames: torch.Tensor, sample_fps: float, *, clip_length: i
     ok = score > conf_thresh
     if out.get("act") is not None:
         ok = ok & (act > 0.5).unsqueeze(0)
+    else:
+        # closed set (no open-set head): class 0 is the background — the reference never filters / suppresses / reports it
+        # (`class_range = range(1, num_classes)`, test.py:208)
+        ok[0] = False
     score = torch.where(ok, score, torch.zeros_like(score))
     decayed, keep, _ = ops.softnms(seg, score, sigma=nms_sigma, top_k=top_k, score_threshold=0.001)
     keep = keep & ok

@@ -81,7 +81,9 @@ def test_pixel_values_are_exact_in_bf16():
     assert torch.equal(v.bfloat16().float(), v)
 
 
-def test_staged_path_is_off_by_default(monkeypatch):
-    monkeypatch.delenv("OTAL_U8_CONV1A", raising=False)
+def test_raw_uint8_path_is_the_default_and_switchable(monkeypatch):
     from opental_b200.backbone import I3DBackbone
+    monkeypatch.delenv("OTAL_U8_CONV1A", raising=False)
+    assert I3DBackbone().u8_conv1a is True
+    monkeypatch.setenv("OTAL_U8_CONV1A", "0")
     assert I3DBackbone().u8_conv1a is False

@@ -1,8 +1,6 @@
-"""GPU (opt-in): the STAGED raw-uint8 Conv3d_1a path — otal_clip_ingest_u8_raw, otal_conv1a_fwd_u8, otal_conv1a_wgrad_u8,
-otal_border_class_sums — vs the CPU oracle's Unit3D on the normalised clip and torch autograd.  These kernels were written
-after round 1's GPU budget was spent and have not run on a B200 yet; they are excluded from the default `-m gpu` run and
-enabled with OTAL_STAGED=1 (tools/r02_first_gpu_call.sh runs them first thing in round 2).  Same tolerance as the bf16x3
-path they replace (1e-4 relative, max-norm)."""
+"""GPU: the raw-uint8 Conv3d_1a path (the default for uint8 input since round 2) — otal_clip_ingest_u8_raw, otal_conv1a_fwd_u8,
+otal_conv1a_wgrad_u8, otal_border_class_sums — vs the CPU oracle's Unit3D on the normalised clip and torch autograd.  Same
+tolerance as the bf16x3 form it replaces (1e-4 relative, max-norm)."""
 import os
 
 import pytest
@@ -11,8 +9,7 @@ import torch.nn.functional as F
 
 import opental_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OTAL_STAGED") != "1", reason="staged kernels: set OTAL_STAGED=1")]
+pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 

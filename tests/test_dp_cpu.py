@@ -225,3 +225,52 @@ def test_trainer_globalise_glue_with_the_fused_loss_stats(monkeypatch):
         assert torch.allclose(g[3], 2.0 * (losses[3] - iouc) + iouc, rtol=1e-5)
     finally:
         dist.destroy_process_group()
+
+
+def test_head_allreduce_hook_fires_once_after_both_passes_of_an_ssl_step():
+    """a step with the SSL pass has two backbone autograd nodes; the SSL branch's node runs FIRST in the backward,
+    before the main pass's head has accumulated its gradients.  The hook that launches the head buffers' all-reduce must fire
+    once, when the LAST backbone backward starts — by then the head parameter's gradient holds both passes' contributions."""
+    from opental_b200 import backbone as bb_mod
+    net = bb_mod.I3DBackbone()
+    calls = []
+    head_w = torch.nn.Parameter(torch.tensor([2.0, -1.0]))
+
+    def fake_forward_planes(x, saved):
+        saved["x"] = x
+        f = x.sum() * torch.ones(1, 1, 1, 1, 2)
+        return {"Mixed_4f": f.clone(), "Mixed_5c": f.clone()}
+
+    net.forward_planes = fake_forward_planes
+    net.backward_planes = lambda saved, g4, g5: calls.append(("bb_bwd", None))
+    net._ensure_flat = lambda dev: None
+    net._anchor = torch.zeros(1, requires_grad=True)
+    net.on_backward_start = lambda: calls.append(("hook", None if head_w.grad is None else head_w.grad.clone()))
+
+    def head(feat):                       # stands for the pyramid + loss: linear in the head parameter
+        return (feat["Mixed_5c"].reshape(-1)[:2] * head_w).sum()
+
+    x_main, x_ssl = torch.full((1,), 3.0), torch.full((1,), 5.0)
+    cost = head(net(x_main)) + 0.5 * head(net(x_ssl))
+    assert net._pending_bwd == 2
+    cost.backward()
+    hooks = [c for c in calls if c[0] == "hook"]
+    assert len(hooks) == 1 and [c[0] for c in calls].count("bb_bwd") == 2
+    assert calls.index(hooks[0]) == 1                                  # after the first (SSL) backbone backward, before the last
+    assert torch.allclose(hooks[0][1], torch.full((2,), 3.0 + 0.5 * 5.0))          # both passes' head gradients are in
+    assert net._pending_bwd == 0
+    # single-pass step: fires at the one and only backbone backward
+    calls.clear(); head_w.grad = None
+    head(net(x_main)).backward()
+    assert [c[0] for c in calls] == ["hook", "bb_bwd"]
+
+
+def test_launch_head_allreduce_is_idempotent_within_a_step():
+    from opental_b200.engine import Trainer
+    tr = Trainer.__new__(Trainer)
+    launched = []
+    tr.reducer = type("R", (), {"launch": lambda self, which=None: launched.append(list(which))})()
+    tr.groups = [None, None, None]
+    tr._head_launched = False
+    tr._launch_head_allreduce(); tr._launch_head_allreduce()
+    assert launched == [[1, 2]]

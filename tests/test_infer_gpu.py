@@ -95,3 +95,20 @@ def test_detect_video_runs_end_to_end():
         assert rows.shape[1] == 5 and rows.shape[0] <= 100 and bool(torch.isfinite(rows).all())
         assert float(rows[:, :2].max()) <= 450 / 10.0 + 1e-3 and float(rows[:, :2].min()) >= 0.0
         assert bool((rows[:, 2] >= 0.001).all()) and bool((rows[:, 4] > 0.5).all())
+
+
+def test_closed_set_detect_video_never_reports_the_background_class():
+    """without the open-set head the reference iterates `range(1, num_classes)` (test.py:208): class 0 is the
+    background and never reaches filtering / soft-NMS / the proposal list, whose name map has no key 0."""
+    from opental_b200.bdnet import BDNet
+    from opental_b200.inference import detect_video, to_proposal_list
+    cfg = O.OracleConfig(num_classes=21, os_head=False, use_edl=False)
+    net = BDNet(in_channels=3, training=False, num_classes=21, os_head=False, use_edl=False).cuda()
+    net.load_state_dict(O.synthetic_state_dict(cfg, loc_bias_shift=3.4657))
+    net.eval()
+    frames = O.synthetic_clip(0).cuda()
+    res = detect_video(net, frames, sample_fps=10.0, conf_thresh=0.001, top_k=50)
+    assert res and 0 not in res and all(1 <= cl <= 20 for cl in res)
+    names = {i: f"class{i}" for i in range(1, 21)}                    # get_class_index_map: keys 1..K only
+    props = to_proposal_list(res, names, os_head=False, use_edl=False)
+    assert props and all(p["label"] in names.values() and p["actionness"] == 0.0 and p["uncertainty"] == 0.0 for p in props)

@@ -70,8 +70,6 @@ def test_anet_forward_loss_backward_match_reference_golden(golden_dir):
     assert not bad, bad
 
 
-@pytest.mark.skipif(os.environ.get("OTAL_STAGED") != "1", reason="written after round 1's GPU budget: passes against the C-ABI "
-                    "emulation on the CPU (tests/test_gpu_suite_emulated_cpu.py), first GPU run with OTAL_STAGED=1")
 def test_anet_ssl_triplet_pass_matches_reference_golden(golden_dir):
     """SSL second pass of the ActivityNet flavour (anet/BDNet.py:453-474 + the triplet loss of anet/train.py:159-166) vs the
     reference's own run (tests/golden/model_anet_ssl.*, oracle/make_golden.py --anet-ssl)."""

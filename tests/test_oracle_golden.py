@@ -223,3 +223,23 @@ def test_closed_set_config1_oracle_matches_reference_golden(golden_dir):
     for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop"):
         w = torch.from_numpy(arrays[f"init.{k}.sample"])
         assert float((out[k][:, ::8, ::8] - w).abs().max() / w.abs().max()) < 2e-5, k
+
+
+def test_batch8_loss_oracle_matches_reference_golden(golden_dir):
+    """The bench configuration (batch 8, ragged targets): the oracle's MultiSegmentLoss on the reference's own B = 8 head outputs
+    must give the reference's losses at epoch 1 and 11 — pins the `[P,B]`-vs-`[B,P]` IoU-calibration pairing for B > 1."""
+    arrays = np.load(os.path.join(golden_dir, "model_thumos_b8.npz"))
+    with open(os.path.join(golden_dir, "model_thumos_b8.json")) as fh:
+        summary = json.load(fh)
+    cfg = O.OracleConfig()
+    out = {k: torch.from_numpy(arrays[f"b8.{k}"]) for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")}
+    out["priors"] = torch.cat(O.level_priors(cfg), 0)
+    targets = [O.synthetic_targets(i, num_classes=15) for i in range(8)]
+    targets[3] = targets[3][:1].clone()
+    targets[5] = torch.cat([targets[5], torch.tensor([[0.42, 0.47, 3.0]])])
+    for epoch in (1, 11):
+        state = O.LossState(epoch=epoch)
+        losses = O.multisegment_loss(out, targets, state, cfg)
+        for a, b in zip(losses, summary[f"e{epoch}"]["losses"]):
+            assert abs(float(a) - b) <= 5e-5 * max(abs(b), 1.0), (epoch, float(a), b)
+        assert np.allclose(state.weight_accum.numpy(), arrays[f"b8.e{epoch}.weight_accum"], atol=1e-6)
