@@ -38,6 +38,21 @@ LAYER_NUM = 6        # BDNet.py:20
 CONV_CHANNELS = 512  # BDNet.py:21
 
 
+class _no_tf32:
+    """Scope for the (non-native) library convolutions of the head: they must not silently drop to TF32 (torch's default for
+    cuDNN convs) — single-pass TF32 alone costs ~1e-3 relative at the outputs, the whole error budget of the path.
+    Scoped, so that building a BDNet does not change the precision of anything else in the process."""
+
+    def __enter__(self):
+        self._saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self._saved
+        return False
+
+
 class Unit1D(nn.Module):
     """conv1d with TF-style "same" padding and bias, no activation (AFSD/common/layers.py:178-214)."""
 
@@ -55,7 +70,8 @@ class Unit1D(nn.Module):
         total = max(self._k - self._s, 0) if t % self._s == 0 else max(self._k - t % self._s, 0)
         if total:
             x = F.pad(x, [total // 2, total - total // 2])
-        return self.conv1d(x)
+        with _no_tf32():
+            return self.conv1d(x)
 
 
 class Unit3DValid(nn.Module):
@@ -73,7 +89,8 @@ class Unit3DValid(nn.Module):
         if self._native is not None:
             store, rec = self._native
             return head_conv(x.permute(0, 2, 3, 4, 1), self.conv3d.weight, self.conv3d.bias, store, rec, 1)
-        return self.conv3d(x).squeeze(-1).squeeze(-1)
+        with _no_tf32():
+            return self.conv3d(x).squeeze(-1).squeeze(-1)
 
 
 class GroupNormReLU(nn.GroupNorm):
@@ -399,10 +416,6 @@ class BDNet(nn.Module):
             raise NotImplementedError("the RPL head is a competing baseline, off in every OpenTAL config (SURVEY D10)")
         if dropout:
             raise NotImplementedError("dropout is 0 in every OpenTAL config (SURVEY D6)")
-        # The head's library convolutions must not silently drop to TF32 (torch's default for cuDNN convs): single-pass
-        # TF32 alone costs ~1e-3 relative at the outputs, the whole error budget of the path.
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
         self.os_head = os_head
         self.num_classes = num_classes - 1 if os_head else num_classes       # BDNet.py:440
         self.variant = variant

@@ -27,6 +27,11 @@ NVCC_FLAGS = [
 ]
 
 
+# developer builds: OTAL_BUILD_DEFINES="OTAL_TIMELINE" adds -D flags (the stamp changes with them, so the default build comes
+# back with a plain `python -m opental_b200.build`)
+NVCC_FLAGS += [f"-D{d}" for d in os.environ.get("OTAL_BUILD_DEFINES", "").split() if d]
+
+
 def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -251,6 +251,18 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     hi = __float2bfloat16_rn(x);
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// Two values at once with the packed conversion (F2FP.BF16.F32.PACK_AB, full rate — the scalar __float2bfloat16_rn compiles to
+// F2F.BF16.F32 on the quarter-rate conversion pipe): hi = {bf16(a) | bf16(b) << 16}, lo likewise for the residuals.  Same
+// round-to-nearest-even results as split_bf16.
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source operand -> upper half
+    return r;
+}
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = cvt_bf16x2(a, b);
+    lo = cvt_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }

@@ -73,10 +73,23 @@ struct ConvParams {
     int ksplit;      // KS instantiation: a tile's K iterations (taps x chunks) are split over `ksplit` CTAs, each adds its partial
                      // sums to the fp32 destination with atomics (zeroed by the caller unless it accumulates); small problems
                      // only — the 1-D head, where one CTA per tile streams 24..72 stages alone while half the SMs idle
+    unsigned long long* timeline;   // developer timeline buffer (OTAL_TIMELINE builds only), else nullptr
     int shift_classes;  // U8: `shift` is a table [4*4*4 border classes][Cout]; class of an output index o along a dim of n
                      // outputs = 1 (o == 0), 2 (o == n-2), 3 (o == n-1), else 0 — which taps of a 7-tap stride-2 window fall
                      // outside the image, where the reference pads the NORMALISED clip with 0 and the raw clip holds 0 = -1
 };
+
+// Developer timeline (compiled in only with -DOTAL_TIMELINE, see tools/conv_timeline.py): per CTA and tile, clock64() of the
+// pipeline events of each role.  g_timeline is set by otal_debug_set_timeline(); slots: 0 producer starts the tile, 1 first
+// stage issued, 2 last stage issued, 3 MMA got the first stage, 4 MMA committed the tile, 5 epilogue waits for the
+// accumulator, 6 got it, 7 first chunk stored, 8 accumulator released, 9 MMA waits for a free accumulator, 10 got it.
+#ifdef OTAL_TIMELINE
+#define OTAL_TL(tileno, slot) do { if (p.timeline && (tileno) < 16 && lane == 0) \
+    p.timeline[((size_t)blockIdx.x * 16 + (tileno)) * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+static unsigned long long* g_timeline = nullptr;
+#else
+#define OTAL_TL(tileno, slot) do { } while (0)
+#endif
 
 struct ConvSmem {
     // dynamic shared memory carve-up, all offsets relative to a 1024-byte aligned base
@@ -97,7 +110,7 @@ __host__ __device__ inline ConvSmem conv_smem_layout(int BN, int nsplit, int nst
     s.staging_off = s.stage_bytes * (uint32_t)nstages;
     uint32_t staging = (uint32_t)nbuf * planes * kATileBytes;      // nbuf (0, 1 or 2) buffers x planes x 16 KB
     s.bar_off = s.staging_off + staging;
-    s.total = s.bar_off + 256;
+    s.total = s.bar_off + 256 + 4096;      // barriers, then the epilogue's per-tile (scale, shift) table [2][256] float2
     return s;
 }
 
@@ -169,7 +182,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (whole warp runs the loop)
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int tl_n = 0, tl_first = 1;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl_n) {
+            OTAL_TL(tl_n, 0); tl_first = 1;
             int tdec = tile, it_lo = 0, it_hi = 0x7fffffff, it_cur = 0;
             if constexpr (KS) {                       // K range of this CTA's share of the tile
                 const int ks = tdec % p.ksplit; tdec /= p.ksplit;
@@ -225,11 +240,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                                 if (split && !U8) tma_load_5d(mapA_lo, &full_bar[stage], sA + a_plane, c0, cw, ch, ct, n);
                             }
                             __syncwarp();
+                            if (tl_first) { OTAL_TL(tl_n, 1); tl_first = 0; }
                             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
             }
+            if (p.kchunks2 == 0) OTAL_TL(tl_n, 2);
             for (int kc = 0; kc < p.kchunks2; ++kc) {          // second K segment (1x1, stride 1: no tap offsets)
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -253,6 +270,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 __syncwarp();
                 if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
+            if (p.kchunks2 != 0) OTAL_TL(tl_n, 2);
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop)
@@ -267,8 +285,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         const int ksteps = p.k32 ? 2 : 4;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int tl_n = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl_n) {
+            OTAL_TL(tl_n, 9);
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            OTAL_TL(tl_n, 10);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
             int n_it = kiters;
@@ -278,6 +299,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             }
             for (int it = 0; it < n_it; ++it) {
                 mbar_wait(&full_bar[stage], phase);
+                if (it == 0) OTAL_TL(tl_n, 3);
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + (size_t)stage * L.stage_bytes);
                 const uint32_t sB = sA + L.a_bytes;
@@ -309,90 +331,134 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             }
             if (elect_one()) umma_commit(&tmem_full[acc]);
             __syncwarp();
+            OTAL_TL(tl_n, 4);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (128 threads)
+        // One warp per scheduler does all of this, so the loop has to be short and free of long-latency dependent loads:
+        // the per-channel scale / shift of the tile's N block are staged in shared memory once per tile (ss), every launch
+        // parameter the loop reads lives in a register, conversions use the packed bf16x2 form.  (Round-2 timeline: the
+        // previous form — per-element __ldg of scale / shift behind branches, scalar conversions — took ~10 000 cycles per
+        // 64-column chunk and was THE bound of every 1x1 convolution.)
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;           // accumulator row = position inside the tile box
         const int et = threadIdx.x - 128;        // 0..127
         unsigned char* stg = smem + L.staging_off;
+        float2* ss = reinterpret_cast<float2*>(smem + L.bar_off + 256);       // [2][256] (scale, shift), by tile parity
         const uint32_t planes = split ? 2u : 1u;
+        const int BN = p.BN, Cout = p.Cout, n_blocks = p.n_blocks;
+        const int tW = p.tW, tH = p.tH, tT = p.tT, tilesW = p.tilesW, tilesH = p.tilesH, tilesT = p.tilesT;
+        const bool store_bf16 = p.store_bf16 != 0, ncdhw = p.out_ncdhw != 0, accumulate = p.accumulate != 0, two_buf = p.nbuf == 2;
+        const float* const scale_g = p.scale; const float* const shift_g = p.shift;
+        float* const out_f32 = p.out_f32;
+        const bool has_ss = (scale_g != nullptr) || (shift_g != nullptr && !U8);
+        const float relu_floor = p.relu ? 0.f : -3.402823466e38f;
+        const int nchunks = (BN + 63) / 64;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int tl_n = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl_n) {
             int tdec = tile;
             bool first_split = true;                  // the bias / shift is added by ONE of the K shares
             if constexpr (KS) { first_split = (tdec % p.ksplit) == 0; tdec /= p.ksplit; }
-            const int nb = tdec % p.n_blocks;
-            int m = tdec / p.n_blocks;
-            const int w0 = (m % p.tilesW) * p.tW; m /= p.tilesW;
-            const int h0 = (m % p.tilesH) * p.tH; m /= p.tilesH;
-            const int t0 = (m % p.tilesT) * p.tT; m /= p.tilesT;
+            const int nb = tdec % n_blocks;
+            int m = tdec / n_blocks;
+            const int w0 = (m % tilesW) * tW; m /= tilesW;
+            const int h0 = (m % tilesH) * tH; m /= tilesH;
+            const int t0 = (m % tilesT) * tT; m /= tilesT;
             const int n = m;
-            // position of this thread's row (for the optional fp32 store)
-            const int rw = row % p.tW, rh = (row / p.tW) % p.tH, rt = row / (p.tW * p.tH);
-            const bool row_ok = (w0 + rw < p.W) && (h0 + rh < p.H) && (t0 + rt < p.T);
-            int shift_off = 0;                       // U8: row of the border-class shift table for this position
-            if constexpr (U8) {
-                auto cls = [](int o, int n) { return o == 0 ? 1 : (o == n - 2 ? 2 : (o == n - 1 ? 3 : 0)); };
-                shift_off = ((cls(t0 + rt, p.T) * 4 + cls(h0 + rh, p.H)) * 4 + cls(w0 + rw, p.W)) * p.Cout;
+            float2* sst = ss + (tl_n & 1) * 256;
+            if (has_ss) {
+                // columns of this N block: (scale, shift), identity beyond Cout; the K shares other than the first add no shift
+                for (int c = et; c < BN; c += 128) {
+                    const int cg = nb * BN + c;
+                    float sc = 1.f, sh = 0.f;
+                    if (cg < Cout) {
+                        if (scale_g) sc = __ldg(scale_g + cg);
+                        if (shift_g && !U8 && (!KS || first_split)) sh = __ldg(shift_g + cg);
+                    }
+                    sst[c] = make_float2(sc, sh);
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
             }
             float* orow = nullptr;
-            if (p.out_f32 && row_ok) {
-                const size_t pos = ((size_t)(t0 + rt) * p.H + (h0 + rh)) * p.W + (w0 + rw);
-                if (p.out_ncdhw)   // element (n, c, pos): channel stride = T*H*W, consecutive rows -> consecutive addresses
-                    orow = p.out_f32 + ((size_t)n * p.out_cstride + p.out_coff) * ((size_t)p.T * p.H * p.W) + pos;
-                else
-                    orow = p.out_f32 + ((size_t)n * p.T * p.H * p.W + pos) * p.out_cstride + p.out_coff;
+            int shift_off = 0;                       // U8: row of the border-class shift table for this position
+            if (out_f32 != nullptr || U8) {
+                // position of this thread's row (fp32 store / border class)
+                const int rw = row % tW, rh = (row / tW) % tH, rt = row / (tW * tH);
+                const bool row_ok = (w0 + rw < p.W) && (h0 + rh < p.H) && (t0 + rt < p.T);
+                if constexpr (U8) {
+                    auto cls = [](int o, int n_) { return o == 0 ? 1 : (o == n_ - 2 ? 2 : (o == n_ - 1 ? 3 : 0)); };
+                    shift_off = ((cls(t0 + rt, p.T) * 4 + cls(h0 + rh, p.H)) * 4 + cls(w0 + rw, p.W)) * Cout;
+                }
+                if (out_f32 && row_ok) {
+                    const size_t pos = ((size_t)(t0 + rt) * p.H + (h0 + rh)) * p.W + (w0 + rw);
+                    if (ncdhw)   // element (n, c, pos): channel stride = T*H*W, consecutive rows -> consecutive addresses
+                        orow = out_f32 + ((size_t)n * p.out_cstride + p.out_coff) * ((size_t)p.T * p.H * p.W) + pos;
+                    else
+                        orow = out_f32 + ((size_t)n * p.T * p.H * p.W + pos) * p.out_cstride + p.out_coff;
+                }
             }
 
+            if (warp == 4) OTAL_TL(tl_n, 5);
             mbar_wait(&tmem_full[acc], acc_phase);
+            if (warp == 4) OTAL_TL(tl_n, 6);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
-            const int nchunks = (p.BN + 63) / 64;
             for (int ch = 0; ch < nchunks; ++ch) {
                 unsigned char* buf_hi = stg + (size_t)sbuf * planes * kATileBytes;
                 unsigned char* buf_lo = buf_hi + kATileBytes;
-                if (p.store_bf16) {
+                if (store_bf16) {
                     // the store that last read this staging buffer was committed nbuf chunks ago
-                    if (et == 0) { if (p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+                    if (et == 0) { if (two_buf) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int col0 = ch * 64 + half * 32;
-                    if (col0 >= p.BN) break;
+                    if (col0 >= BN) break;
                     uint32_t v[32];
                     tmem_ld32(t_acc + col0, v);
+                    float f[32];
                     if constexpr (NCAT) {                 // second half of the accumulator: the a_hi*b_lo products
                         uint32_t v2[32];
-                        tmem_ld32(t_acc + p.BN + col0, v2);
+                        tmem_ld32(t_acc + BN + col0, v2);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
                     } else {
                         tmem_ld_wait();
-                    }
-                    const int cbase = nb * p.BN + col0;   // channel inside the slice
-                    float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = cbase + j;
-                        float sc = 1.f, sh = 0.f;
-                        if (c < p.Cout) {
-                            if (p.scale) sc = __ldg(p.scale + c);
-                            if (p.shift && (!KS || first_split)) sh = __ldg(p.shift + shift_off + c);
-                        }
-                        float x = fmaf(__uint_as_float(v[j]), sc, sh);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        f[j] = x;
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     }
-                    if (orow && !p.out_ncdhw) {
+                    const int cbase = nb * BN + col0;     // channel inside the slice
+                    if (has_ss) {
+                        const float4* s4 = reinterpret_cast<const float4*>(sst + col0);      // 2 columns per 16-byte broadcast load
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float4 s2 = s4[j >> 1];
+                            f[j] = fmaf(f[j], s2.x, s2.y);
+                            f[j + 1] = fmaf(f[j + 1], s2.z, s2.w);
+                        }
+                    }
+                    if constexpr (U8) {
+                        // border-class shift table: rows differ between threads, channels beyond Cout do not exist (Cout % 8 == 0)
+                        const float4* tb = reinterpret_cast<const float4*>(shift_g + shift_off + cbase);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (cbase + j < Cout) {
+                                const float4 t4 = __ldg(tb + (j >> 2));
+                                f[j] += t4.x; f[j + 1] += t4.y; f[j + 2] += t4.z; f[j + 3] += t4.w;
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], relu_floor);
+                    if (orow && !ncdhw) {
                         // Cout, out_coff and out_cstride are multiples of 8: groups of 4 are all-in or all-out
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
-                            if (cbase + j < p.Cout) {
+                            if (cbase + j < Cout) {
                                 float4* dst = reinterpret_cast<float4*>(orow + cbase + j);
                                 float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                                 if constexpr (KS) {           // partial sums of the K shares meet in the destination
@@ -400,7 +466,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                                     atomicAdd(d1, v4.x); atomicAdd(d1 + 1, v4.y); atomicAdd(d1 + 2, v4.z); atomicAdd(d1 + 3, v4.w);
                                     continue;
                                 }
-                                if (p.accumulate) { const float4 o = *dst; v4.x += o.x; v4.y += o.y; v4.z += o.z; v4.w += o.w; }
+                                if (accumulate) { const float4 o = *dst; v4.x += o.x; v4.y += o.y; v4.z += o.z; v4.w += o.w; }
                                 *dst = v4;
                             }
                     } else if (orow) {
@@ -408,24 +474,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         const size_t cs = (size_t)p.T * p.H * p.W;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (cbase + j < p.Cout) {
+                            if (cbase + j < Cout) {
                                 float* dst = orow + (size_t)(cbase + j) * cs;
                                 if constexpr (KS) { atomicAdd(dst, f[j]); continue; }
-                                *dst = p.accumulate ? *dst + f[j] : f[j];
+                                *dst = accumulate ? *dst + f[j] : f[j];
                             }
                     }
-                    if (p.store_bf16) {
+                    if (store_bf16) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {          // 4 x 16-byte groups (8 channels each)
                             uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                __nv_bfloat16 h0b, l0b, h1b, l1b;
-                                split_bf16(f[g * 8 + e * 2], h0b, l0b);
-                                split_bf16(f[g * 8 + e * 2 + 1], h1b, l1b);
-                                hi[e] = pack_bf16x2(h0b, h1b);
-                                lo[e] = pack_bf16x2(l0b, l1b);
-                            }
+                            for (int e = 0; e < 4; ++e) split_bf16x2(f[g * 8 + e * 2], f[g * 8 + e * 2 + 1], hi[e], lo[e]);
                             const int j16 = half * 4 + g;                       // 16-byte chunk inside the 128-byte row
                             const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) << 4);
                             *reinterpret_cast<uint4*>(buf_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -433,24 +493,26 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                         }
                     }
                 }
-                if (p.store_bf16) {
+                if (store_bf16) {
                     fence_proxy_async_smem();
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et == 0) {
-                        const int cc = nb * p.BN + ch * 64;
+                        const int cc = nb * BN + ch * 64;
                         tma_store_5d(&mapO_hi, buf_hi, cc, w0, h0, t0, n);
                         if (split) tma_store_5d(&mapO_lo, buf_lo, cc, w0, h0, t0, n);
                         tma_store_commit();
                     }
-                    if (p.nbuf == 2) sbuf ^= 1;
+                    if (two_buf) sbuf ^= 1;
                 }
+                if (ch == 0 && warp == 4) OTAL_TL(tl_n, 7);
             }
             // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
+            if (warp == 4) OTAL_TL(tl_n, 8);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (p.store_bf16 && et == 0) tma_store_wait_all<0>();
+        if (store_bf16 && et == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -508,6 +570,15 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         }
         if (p.BN > 64 && p.BN % 64 != 0 && p.Cout > 64 && m_tiles * p.n_blocks < num_sms() / 2) {
             p.BN = 64; p.n_blocks = (p.Cout + 63) / 64;
+        }
+    }
+    {
+        // The widest tiles (BN > 128 in bf16x3: 96 KB per stage) leave no room for the epilogue's (scale, shift) table next to
+        // two stages and a staging buffer: such a launch runs as 128-wide N blocks instead (which also get the N-concatenated form).
+        const uint32_t cap = 227 * 1024 - 1024;
+        const int nb_try = L.y_hi != nullptr ? 1 : 0;
+        if (p.BN > 128 && conv_smem_layout(p.BN, p.nsplit, 2, nb_try, p.b_mn, p.k32, p.a_single).total > cap) {
+            p.BN = 128; p.n_blocks = (p.Cout + 127) / 128;
         }
     }
     {
@@ -578,6 +649,11 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
         if (split && (rc = make_tensor_map_bf16(&maps.O_lo, L.y_lo + p.out_coff, 5, odims, ost, obox, 1))) return rc;
     }
 
+#ifdef OTAL_TIMELINE
+    p.timeline = g_timeline;
+    fprintf(stderr, "otal timeline: BN %d n_blocks %d stages %d nbuf %d ncat %d kchunks %d taps %d tiles %d b_mn %d f32 %d\n", p.BN, p.n_blocks,
+            p.nstages, p.nbuf, p.ncat, p.kchunks, p.kt * p.kh * p.kw, p.total_tiles, p.b_mn, p.out_f32 != nullptr);
+#endif
     const size_t smem_bytes = SL.total + 1024;
     static OncePerDevice once;
     int once_dev = 0;
@@ -611,6 +687,11 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
 using namespace otal;
 
 extern "C" {
+
+#ifdef OTAL_TIMELINE
+// developer builds only: [grid][16 tiles][16 slots] of clock64() values, or nullptr to switch the recording off
+__attribute__((visibility("default"))) void otal_debug_set_timeline(unsigned long long* buf) { otal::g_timeline = buf; }
+#endif
 
 // See include/opental_b200.h for the contract.
 int otal_conv_igemm_fwd(const otal_conv_desc* d, void* stream_) {

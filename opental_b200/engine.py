@@ -288,11 +288,16 @@ class Trainer:
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())
         self._capturing = True
+        # the warm-ups are real passes over the live criterion: its stateful buffers (the IBM EMA `weight_accum`, GHM's
+        # `acc_sum`) must come out of capture() as they went in — the reference never makes these two extra updates
+        crit_state = [(b, b.detach().clone()) for b in self.criterion.buffers()]
         try:
             with torch.cuda.stream(stream):
                 for _ in range(2):                   # warm-up on the capture stream (lazy initialisations, allocator)
                     self.zero_grad()
                     self.forward_backward(c, (t, v), sc, *ssl_args)
+                for b, saved in crit_state:
+                    b.copy_(saved)
             torch.cuda.current_stream().wait_stream(stream)
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()

@@ -9,7 +9,7 @@
   cost step by step — eagerly and through the captured CUDA graph.
 
 Tolerances: outputs / losses 1e-3 relative (BASELINE.json); gradient fingerprints 5e-2 (discontinuous: ReLU / arg-max flips);
-trajectory cost max(1e-3, 3 x the drift recorded between the reference and its fp32 CPU restatement at that step)."""
+trajectory cost max(1e-3, 3 x the largest drift recorded between the reference and its fp32 CPU restatement up to that step)."""
 import json
 import math
 import os
@@ -117,7 +117,8 @@ def test_five_step_trajectory_follows_the_reference(golden_dir, graph):
             crit.cls_loss.weight_accum.copy_(acc0)             # capture() warm-ups touch the EMA (restored by the Trainer too)
         for s, want in enumerate(gold["steps"]):
             cost, losses, ls, le = tr.step(x, tg, sc)
-            tol = max(1e-3, 3 * want["oracle_rel"])
+            # once two implementations have bifurcated (a matching flip), every later step inherits the difference
+            tol = max(1e-3, 3 * max(w["oracle_rel"] for w in gold["steps"][:s + 1]))
             assert abs(float(cost) - want["cost"]) <= tol * abs(want["cost"]), (s, float(cost), want["cost"])
             if s < 3:
                 for a, b in zip(losses, want["losses"]):
