@@ -55,6 +55,37 @@ def build() -> str | None:
     return so_path()
 
 
+PY_OUT = os.path.join(OUT, "reference_src")
+# the Python modules of the hot path and the two configurations the bench runs
+PY_FILES = ("AFSD/common/config.py", "AFSD/common/i3d_backbone.py", "AFSD/common/layers.py", "AFSD/common/segment_utils.py",
+            "AFSD/prop_pooling/boundary_pooling_op.py", "AFSD/thumos14/BDNet.py", "AFSD/thumos14/multisegment_loss.py",
+            "AFSD/thumos14/cls_loss.py", "AFSD/anet/BDNet.py", "AFSD/anet/multisegment_loss.py", "AFSD/anet/cls_loss.py",
+            "configs/thumos14_opental_final.yaml", "configs/thumos14.yaml", "configs/anet_opental.yaml")
+
+
+def build_py() -> str | None:
+    """Place the reference's own Python modules of the hot path, byte for byte, under oracle/_ref/reference_src/ (git-ignored
+    build output that travels to the GPU box like the compiled checker) so that `bench.py --impl reference` and the
+    cpu_baseline leg can time the REFERENCE's code on the GPU box's host cores (`cpu_baseline.kind = "reference"`).  Returns the
+    directory, or None when neither /root/reference nor an earlier copy exists."""
+    import filecmp
+    import shutil
+    if not os.path.isdir(os.path.join(REF, "AFSD")):
+        return PY_OUT if os.path.isfile(os.path.join(PY_OUT, PY_FILES[5])) else None
+    for rel in PY_FILES:
+        src, dst = os.path.join(REF, rel), os.path.join(PY_OUT, rel)
+        if not os.path.isfile(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not (os.path.isfile(dst) and filecmp.cmp(src, dst, shallow=False)):
+            shutil.copyfile(src, dst)
+    for d in ("AFSD", "AFSD/common", "AFSD/prop_pooling", "AFSD/thumos14", "AFSD/anet"):
+        src = os.path.join(REF, d, "__init__.py")
+        if os.path.isfile(src):
+            shutil.copyfile(src, os.path.join(PY_OUT, d, "__init__.py"))
+    return PY_OUT
+
+
 def load_module():
     """Import the compiled reference extension (exposes forward / backward like the reference's module)."""
     import torch  # noqa: F401  (must be loaded first: the .so links against libtorch)
@@ -69,3 +100,4 @@ def load_module():
 
 if __name__ == "__main__":
     print(build())
+    print(build_py())

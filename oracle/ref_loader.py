@@ -13,6 +13,9 @@ import numpy as np
 import torch
 
 REF_ROOT = os.environ.get("OPENTAL_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "AFSD")):
+    # the GPU box has no /root/reference: the hot-path modules placed by oracle/build_ref.py:build_py()
+    REF_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_src")
 
 
 def kernel_emulation_forward(inp: torch.Tensor, seg: torch.Tensor) -> torch.Tensor:
@@ -97,8 +100,8 @@ def load_reference(config="configs/thumos14_opental_final.yaml", extra_args=("--
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import opental_oracle as oracle_mod
 
-    if not os.path.isdir(REF_ROOT):
-        raise RuntimeError(f"{REF_ROOT} not present: the reference can only be imported in the build container")
+    if not os.path.isdir(os.path.join(REF_ROOT, "AFSD")):
+        raise RuntimeError(f"{REF_ROOT} not present: run oracle/build_ref.py in the build container first")
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     argv = sys.argv
@@ -117,3 +120,29 @@ def load_reference(config="configs/thumos14_opental_final.yaml", extra_args=("--
     ns = types.SimpleNamespace(BDNet=bdnet.BDNet, bdnet_module=bdnet, MultiSegmentLoss=msl.MultiSegmentLoss,
                                config=cfg, restore_cuda=lambda: setattr(torch.Tensor, "cuda", cuda_orig))
     return ns
+
+
+def reference_training_cost(ns, net, crit, x, targets, scores, lw=1.0, cw=10.0, ctw=1.0, actw=1.0):
+    """Cost of one non-SSL training step of the reference's own modules: `forward_one_epoch` + the weighting of
+    `run_one_epoch` (thumos14/train.py:164-235), restated because importing train.py needs tensorboardX and creates
+    directories at import.  Returns (cost, 7 losses, loss_start, loss_end)."""
+    import torch.nn.functional as F
+
+    def bce(start, end, sc):
+        s = torch.tanh(start).mean(-1)
+        e = torch.tanh(end).mean(-1)
+        return (F.binary_cross_entropy(s.view(-1), sc[:, 0].contiguous().view(-1)),
+                F.binary_cross_entropy(e.view(-1), sc[:, 1].contiguous().view(-1)))
+
+    out = net(x)
+    l, c, pl, pc, ct, act, pact = crit(out, [t.clone() for t in targets])
+    ls, le = bce(out["start"], out["end"], scores)
+    sc4 = F.interpolate(scores, scale_factor=1.0 / 4)
+    a, b = bce(out["start_loc_prop"], out["end_loc_prop"], sc4)
+    c2, d = bce(out["start_conf_prop"], out["end_conf_prop"], sc4)
+    ls = ls + 0.1 * (a + c2)
+    le = le + 0.1 * (b + d)
+    cost = lw * l + cw * c + lw * pl + cw * pc + ctw * ct + ls + le
+    if act is not None:
+        cost = cost + actw * act + actw * pact
+    return cost, (l, c, pl, pc, ct, act, pact), ls, le

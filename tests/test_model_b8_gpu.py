@@ -127,7 +127,8 @@ def test_five_step_trajectory_follows_the_reference(golden_dir, graph):
     finally:
         BoundaryMaxPoolingFunction.compat_tscale_bug = False
     assert tr.step_count == len(gold["steps"])
-    assert np.allclose(crit.cls_loss.weight_accum.cpu().numpy(), w_acc, atol=2e-3)
+    # the 50-bin IBM EMA after five steps: a sample whose IoU sits on a bin edge moves a bin's EMA by (1 - momentum) x its weight
+    assert np.allclose(crit.cls_loss.weight_accum.cpu().numpy(), w_acc, atol=3e-2)
     # how far the parameters moved: Adam's first steps are ~lr per element per step, so the total |delta w| is a tight check of
     # the optimizer (bias correction, L2-in-gradient, step counter) even where single elements flip sign
     total = sum(float((p.detach() - w0[k]).abs().sum()) for k, p in net.named_parameters() if p.requires_grad)

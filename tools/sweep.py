@@ -45,7 +45,10 @@ def main():
         if rank == 0:
             print(line, flush=True)
 
-    say(f"# frames batch/GPU ms/step clips/s(job) train_TFLOP/s(alg, per GPU) frac_of_{peak:.0f}TF  peak_mem_GB   ({args.precision}, {world} GPU)")
+    import bench as B_
+    peaks = B_.load_peaks()
+    say(f"# frames batch/GPU ms/step clips/s(job) train_TFLOP/s(alg, per GPU) frac_of_{peak:.0f}TF  HBM_GB/s(alg lower bound) "
+        f"frac_of_{peaks.get('hbm_gbs', 6455.9):.0f}GB/s  peak_mem_GB   ({args.precision}, {world} GPU)")
     if args.anet:
         args.frames = [768]
     for T in args.frames:
@@ -90,7 +93,9 @@ def main():
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # the slowest rank's time
                 ms = float(t)
                 tf = B * flop_clip / (ms * 1e-3) / 1e12
-                say(f"{T:6d} {B:5d} {ms:8.2f} {world * B * 1000.0 / ms:8.1f} {tf:10.1f} {tf / peak:8.3f} {torch.cuda.max_memory_allocated() / 2**30:8.1f}  {mode}")
+                hbm = B_.hbm_estimate(dict(mode="train", frames=T), B, ms, peaks)
+                say(f"{T:6d} {B:5d} {ms:8.2f} {world * B * 1000.0 / ms:8.1f} {tf:10.1f} {tf / peak:8.3f} {hbm['achieved']:9.0f} {hbm['frac']:6.3f} "
+                    f"{torch.cuda.max_memory_allocated() / 2**30:8.1f}  {mode}")
             except Exception as ex:  # noqa: BLE001
                 print(f"[rank {rank}] {T:6d} {B:5d} failed: {repr(ex)[:200]}", flush=True)
             finally:
