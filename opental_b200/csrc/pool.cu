@@ -14,6 +14,7 @@
 // ATen's max_pool3d) and the fp32 gradient is added to the fp32 input-gradient buffer with red.global.add.f32.
 // Overlapping windows (k3 s1 / k3 s2) make the adds collide; sums have at most 27 terms.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace otal {
 
@@ -269,7 +270,7 @@ maxpool_bwd_argmax_kernel(const PoolParams p, const unsigned char* __restrict__ 
 // per tap.  Shared layout per position: 256 bytes = [8 channel groups x 4 keys (channels 0-3)][8 groups x 4 keys (4-7)].
 struct PoolTile { int tT, tH, tW, tilesT, tilesH, tilesW, cchunks; };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(320)
 maxpool333_tiled_kernel(const PoolParams p, const PoolTile tl, unsigned char* __restrict__ argmax) {
     extern __shared__ __align__(16) unsigned char pool_smem[];
     uint4* keys = reinterpret_cast<uint4*>(pool_smem);                 // [halo positions][2 halves][8 cgs] x 16 B
@@ -284,92 +285,141 @@ maxpool333_tiled_kernel(const PoolParams p, const PoolTile tl, unsigned char* __
     const int t0 = it * tl.tT, h0 = ih * tl.tH, w0 = iw * tl.tW;      // first output of the tile (= input coordinate)
     const int eT = tl.tT + 2, eH = tl.tH + 2, eW = tl.tW + 2;
     const int halo = eT * eH * eW;
-    // ---- stage keys: item = (halo position, channel group)
-    for (int i = threadIdx.x; i < halo * 8; i += blockDim.x) {
-        const int cgl = i & 7, hp = i >> 3;
-        const int cg = cchunk * 8 + cgl;
-        const int xw = hp % eW, xh = (hp / eW) % eH, xt = hp / (eW * eH);
-        const int t = t0 - 1 + xt, h = h0 - 1 + xh, w = w0 - 1 + xw;
-        uint4 k0 = make_uint4(KEY_ZERO, KEY_ZERO, KEY_ZERO, KEY_ZERO), k1 = k0;   // zero padding competes as 0
-        if (cg < cgs && t >= 0 && t < p.T && h >= 0 && h < p.H && w >= 0 && w < p.W) {
-            const size_t off = ((((size_t)n * p.T + t) * p.H + h) * p.W + w) * p.in_cstride + p.in_coff + cg * 8;
-            const uint4 hv = *reinterpret_cast<const uint4*>(p.x_hi + off);
-            uint4 lv = make_uint4(0, 0, 0, 0);
-            if (p.x_lo) lv = *reinterpret_cast<const uint4*>(p.x_lo + off);
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-            uint32_t key[8];
+    // ---- stage keys: item = (halo position, channel group).  Four items per thread and round, all loads issued before the
+    // first conversion: with 2 CTAs per SM the global-load latency of this phase is otherwise exposed once per item.
+    constexpr int kStageUnroll = 4;
+    for (int i0 = threadIdx.x; i0 < halo * 8; i0 += blockDim.x * kStageUnroll) {
+        uint4 hv[kStageUnroll], lv[kStageUnroll];
+        bool ok[kStageUnroll];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t th = key_fwd2(hw[j]), tl_ = key_fwd2(lw[j]);
-                key[2 * j] = __byte_perm(tl_, th, 0x5410);
-                key[2 * j + 1] = __byte_perm(tl_, th, 0x7632);
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int cgl = i & 7, hp = i >> 3;
+            const int cg = cchunk * 8 + cgl;
+            const int xw = hp % eW, xh = (hp / eW) % eH, xt = hp / (eW * eH);
+            const int t = t0 - 1 + xt, h = h0 - 1 + xh, w = w0 - 1 + xw;
+            ok[u] = i < halo * 8 && cg < cgs && t >= 0 && t < p.T && h >= 0 && h < p.H && w >= 0 && w < p.W;
+            hv[u] = make_uint4(0, 0, 0, 0); lv[u] = make_uint4(0, 0, 0, 0);
+            if (ok[u]) {
+                const size_t off = ((((size_t)n * p.T + t) * p.H + h) * p.W + w) * p.in_cstride + p.in_coff + cg * 8;
+                hv[u] = *reinterpret_cast<const uint4*>(p.x_hi + off);
+                if (p.x_lo) lv[u] = *reinterpret_cast<const uint4*>(p.x_lo + off);
             }
-            k0 = make_uint4(key[0], key[1], key[2], key[3]);
-            k1 = make_uint4(key[4], key[5], key[6], key[7]);
         }
-        keys[hp * 16 + cgl] = k0;
-        keys[hp * 16 + 8 + cgl] = k1;
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= halo * 8) break;
+            const int cgl = i & 7, hp = i >> 3;
+            uint4 k0 = make_uint4(KEY_ZERO, KEY_ZERO, KEY_ZERO, KEY_ZERO), k1 = k0;   // zero padding competes as 0
+            if (ok[u]) {
+                const uint32_t hw[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w}, lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+                uint32_t key[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t th = key_fwd2(hw[j]), tl_ = key_fwd2(lw[j]);
+                    key[2 * j] = __byte_perm(tl_, th, 0x5410);
+                    key[2 * j + 1] = __byte_perm(tl_, th, 0x7632);
+                }
+                k0 = make_uint4(key[0], key[1], key[2], key[3]);
+                k1 = make_uint4(key[4], key[5], key[6], key[7]);
+            }
+            keys[hp * 16 + cgl] = k0;
+            keys[hp * 16 + 8 + cgl] = k1;
+        }
     }
     __syncthreads();
-    // ---- scan: item = (output position of the tile, channel group)
-    const int nout = tl.tT * tl.tH * tl.tW;
-    for (int i = threadIdx.x; i < nout * 8; i += blockDim.x) {
+    // ---- scan: item = (output row/column of the tile, channel group); the thread walks along T.  The 3x3 maximum of every
+    // halo plane (first maximum in (dh, dw) order) is computed ONCE and merged over a sliding window of three planes, strict
+    // '>' in dt order: the same result as scanning the 27 taps in (dt, dh, dw) order — final key = max(init, taps), arg = first
+    // tap that attains it when it beats init — for (tT + 2) / tT x 9 taps per output instead of 27.
+    const int ncol = tl.tH * tl.tW;
+    for (int i = threadIdx.x; i < ncol * 8; i += blockDim.x) {
         const int cgl = i & 7, op = i >> 3;
         const int cg = cchunk * 8 + cgl;
-        const int ow = op % tl.tW, oh = (op / tl.tW) % tl.tH, ot = op / (tl.tW * tl.tH);
-        const int to = t0 + ot, ho = h0 + oh, wo = w0 + ow;
-        if (cg >= cgs || to >= p.To || ho >= p.Ho || wo >= p.Wo) continue;
-        const bool pad = to == 0 || ho == 0 || wo == 0 || to + 1 >= p.T || ho + 1 >= p.H || wo + 1 >= p.W;
-        uint32_t best[8], arg[8];
+        const int ow = op % tl.tW, oh = op / tl.tW;
+        const int ho = h0 + oh, wo = w0 + ow;
+        if (cg >= cgs || ho >= p.Ho || wo >= p.Wo) continue;
+        const bool pad_hw = ho == 0 || wo == 0 || ho + 1 >= p.H || wo + 1 >= p.W;
+        uint32_t pk[3][8];                       // plane maxima of the last three halo planes
+        uint32_t pa[3];                          // their in-plane arg (dh * 3 + dw), one nibble per channel
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = pad ? KEY_ZERO : 0u; arg[j] = 255u; }
+        for (int s_ = 0; s_ < 3; ++s_) { pa[s_] = 0;
 #pragma unroll
-        for (int dt = 0; dt < 3; ++dt)
+            for (int j = 0; j < 8; ++j) pk[s_][j] = 0; }
+        for (int xt = 0; xt < eT; ++xt) {
+            // shift the window and scan plane xt
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { pk[0][j] = pk[1][j]; pk[1][j] = pk[2][j]; }
+            pa[0] = pa[1]; pa[1] = pa[2];
+            uint32_t bk[8], ba[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { bk[j] = 0u; ba[j] = 0u; }
 #pragma unroll
             for (int dh = 0; dh < 3; ++dh)
 #pragma unroll
                 for (int dw = 0; dw < 3; ++dw) {
-                    const int hp = ((ot + dt) * eH + (oh + dh)) * eW + (ow + dw);
+                    const int hp = (xt * eH + (oh + dh)) * eW + (ow + dw);
                     const uint4 a = keys[hp * 16 + cgl], c = keys[hp * 16 + 8 + cgl];
                     const uint32_t k[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-                    const uint32_t code = (uint32_t)((dt * 3 + dh) * 3 + dw);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (k[j] > best[j]) { best[j] = k[j]; arg[j] = code; }
+                        if (k[j] > bk[j]) { bk[j] = k[j]; ba[j] = (uint32_t)(dh * 3 + dw); }
                 }
-        const long long opos = (((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo;
-        uint32_t oh_[4], ol_[4];
+            uint32_t packed = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t ka = best[2 * j] ? best[2 * j] : KEY_ZERO, kb = best[2 * j + 1] ? best[2 * j + 1] : KEY_ZERO;
-            oh_[j] = key_inv2(__byte_perm(ka, kb, 0x7632));
-            ol_[j] = key_inv2(__byte_perm(ka, kb, 0x5410));
-        }
-        const size_t off = (size_t)opos * p.out_cstride + p.out_coff + cg * 8;
-        *reinterpret_cast<uint4*>(p.y_hi + off) = make_uint4(oh_[0], oh_[1], oh_[2], oh_[3]);
-        if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + off) = make_uint4(ol_[0], ol_[1], ol_[2], ol_[3]);
-        if (argmax) {
-            const uint32_t a0 = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
-            const uint32_t a1 = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
-            *reinterpret_cast<uint2*>(argmax + (size_t)opos * p.C + cg * 8) = make_uint2(a0, a1);
+            for (int j = 0; j < 8; ++j) { pk[2][j] = bk[j]; packed |= ba[j] << (4 * j); }
+            pa[2] = packed;
+            const int ot = xt - 2;
+            if (ot < 0) continue;
+            const int to = t0 + ot;
+            if (to >= p.To) break;
+            const bool pad = pad_hw || to == 0 || to + 1 >= p.T;
+            uint32_t best[8], arg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { best[j] = pad ? KEY_ZERO : 0u; arg[j] = 255u; }
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (pk[dt][j] > best[j]) { best[j] = pk[dt][j]; arg[j] = (uint32_t)(dt * 9) + ((pa[dt] >> (4 * j)) & 0xfu); }
+            const long long opos = (((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo;
+            uint32_t oh_[4], ol_[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t ka = best[2 * j] ? best[2 * j] : KEY_ZERO, kb = best[2 * j + 1] ? best[2 * j + 1] : KEY_ZERO;
+                oh_[j] = key_inv2(__byte_perm(ka, kb, 0x7632));
+                ol_[j] = key_inv2(__byte_perm(ka, kb, 0x5410));
+            }
+            const size_t off = (size_t)opos * p.out_cstride + p.out_coff + cg * 8;
+            *reinterpret_cast<uint4*>(p.y_hi + off) = make_uint4(oh_[0], oh_[1], oh_[2], oh_[3]);
+            if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + off) = make_uint4(ol_[0], ol_[1], ol_[2], ol_[3]);
+            if (argmax) {
+                const uint32_t a0 = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+                const uint32_t a1 = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+                *reinterpret_cast<uint2*>(argmax + (size_t)opos * p.C + cg * 8) = make_uint2(a0, a1);
+            }
         }
     }
 }
 
 static int launch_pool333_tiled(const PoolParams& p, unsigned char* argmax, cudaStream_t s) {
     PoolTile tl;
-    tl.tH = p.H < 6 ? p.H : 6; tl.tW = p.W < 6 ? p.W : 6; tl.tT = p.T < 4 ? p.T : 4;
+    static const int tt_env = getenv("OTAL_POOL_TT") ? atoi(getenv("OTAL_POOL_TT")) : 4;      // developer A/B: T extent of a tile
+    tl.tH = p.H < 6 ? p.H : 6; tl.tW = p.W < 6 ? p.W : 6; tl.tT = p.T < tt_env ? p.T : tt_env;
     tl.tilesT = (p.T + tl.tT - 1) / tl.tT; tl.tilesH = (p.H + tl.tH - 1) / tl.tH; tl.tilesW = (p.W + tl.tW - 1) / tl.tW;
     tl.cchunks = ((p.C >> 3) + 7) / 8;
     const size_t smem = (size_t)(tl.tT + 2) * (tl.tH + 2) * (tl.tW + 2) * 256;
     static OncePerDevice once;
     int once_dev = 0;
     if (once.need(&once_dev)) {
-        OTAL_CUDA_TRY(cudaFuncSetAttribute(maxpool333_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        OTAL_CUDA_TRY(cudaFuncSetAttribute(maxpool333_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         once.mark(once_dev);
     }
     const long long blocks = (long long)p.N * tl.tilesT * tl.tilesH * tl.tilesW * tl.cchunks;
-    maxpool333_tiled_kernel<<<(unsigned)blocks, 256, smem, s>>>(p, tl, argmax);
+    if (smem > 200 * 1024) { set_last_error_msg("maxpool: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
+    const int threads = (tl.tH * tl.tW * 8 + 31) / 32 * 32;          // one scan item (output column, channel group) per thread
+    maxpool333_tiled_kernel<<<(unsigned)blocks, threads > 320 ? 320 : threads, smem, s>>>(p, tl, argmax);
     return OTAL_OK;
 }
 
