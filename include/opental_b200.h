@@ -143,8 +143,15 @@ OTAL_API int otal_conv1a_fwd(const otal_conv1a_desc* desc, void* stream);
  * along (T, H, W) — class of index o among n outputs: 1 if o == 0, 2 if o == n-2, 3 if o == n-1, else 0 — holding
  * bn_shift - bn_scale * (sum of the in-bounds weights of that class).  Needs nsplit = 3, even T and H, extents >= 6.
  * One tensor-core pass u * [w_hi | w_lo] instead of two, half the activation traffic, no activation rounding error.
- * STAGED: built and argument-checked, enabled by OTAL_U8_CONV1A=1 (opental_b200/backbone.py), not yet measured on a GPU. */
+ * Default for uint8 input since round 2 (OTAL_U8_CONV1A=0 in opental_b200/backbone.py switches back). */
 OTAL_API int otal_conv1a_fwd_u8(const otal_conv1a_desc* desc, void* stream);
+
+/* The same operator with a RESIDENT INPUT HALO (csrc/conv1a_halo.cu): a work unit = 256 positions of one output frame (two
+ * 16 x 8 tiles side by side); per dt ONE 37-row input box is loaded and the seven dh taps read it as shifted views, the seven
+ * [w_hi | w_lo] weight tiles of the dt arrive with it: 651 KB of L2 -> shared-memory fill per 256 positions instead of 1568 KB.
+ * Same arguments except: w_hi = the PACKED weights [49][2*Cout][32] (per tap the Cout w_hi rows, then the Cout w_lo rows),
+ * w_lo and x_lo ignored; Cout = 64, nsplit = 3, even T / H / W >= 6; tT/tH/tW are ignored (the tile is 1 x 16 x 8). */
+OTAL_API int otal_conv1a_fwd_u8_halo(const otal_conv1a_desc* desc, void* stream);
 
 /* Weight gradient — replaces the weight part of torch's convolution_backward for Unit3D / Unit1D
  *   AFSD/common/i3d_backbone.py:82 (conv3d), AFSD/common/layers.py:211 (conv1d)

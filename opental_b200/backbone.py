@@ -240,6 +240,7 @@ class I3DBackbone(nn.Module):
         self._shift = bb - bm * self._scale
         r = self.convs["Conv3d_1a_7x7"]
         self._w1a = ops.pack_conv1a_weight(r.unit.conv3d.weight, with_lo)
+        self._w1a_cat = ops.pack_conv1a_weight_cat(self._w1a) if (with_lo and self.u8_conv1a) else None
 
     def _w(self, r: _ConvRec) -> Planes:
         sl = slice(r.w_off, r.w_off + r.numel)
@@ -316,7 +317,7 @@ class I3DBackbone(nn.Module):
         sc, sh = self._ss(r)
         if u8:
             sc, sh = ops.conv1a_u8_scale_shift(r.unit.conv3d.weight, sc, sh)
-        cur = ops.conv1a_fwd(a, self._w1a, W, scale=sc, shift=sh, relu=True, u8=u8)
+        cur = ops.conv1a_fwd(a, self._w1a, W, scale=sc, shift=sh, relu=True, u8=u8, w_cat=self._w1a_cat if u8 else None)
         saved["Conv3d_1a_7x7"] = cur
         for name, kind, arg in ENDPOINTS[1:]:
             if kind == "pool":

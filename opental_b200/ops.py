@@ -437,9 +437,21 @@ def unpack_conv1a_wgrad(dw: torch.Tensor, C: int = 3) -> torch.Tensor:
     return dw.reshape(7, 7, Cout, 8, CLIP_CPAD)[:, :, :, :7, :C].permute(2, 4, 0, 1, 3).contiguous()
 
 
+# Conv3d_1a forward on raw pixels through the resident-halo kernel (csrc/conv1a_halo.cu); OTAL_CONV1A_HALO=0: the generic kernel
+CONV1A_HALO = os.environ.get("OTAL_CONV1A_HALO", "1") != "0"
+
+
+def pack_conv1a_weight_cat(w: Planes) -> torch.Tensor:
+    """[49, Cout, 32] hi / lo planes -> ONE bf16 tensor [49, 2*Cout, 32]: per tap the hi rows, then the lo rows (the
+    N-concatenated B operand of otal_conv1a_fwd_u8_halo as a single TMA box)."""
+    return torch.cat([w.hi, w.lo], dim=1).contiguous()
+
+
 def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shift: torch.Tensor | None,
-               relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None, u8: bool = False) -> Planes:
-    """u8: x is the raw-pixel plane (clip_ingest_u8(raw=True)), scale / shift come from conv1a_u8_scale_shift."""
+               relu: bool = True, out: Planes | None = None, out_slice: tuple[int, int] | None = None, u8: bool = False,
+               w_cat: torch.Tensor | None = None) -> Planes:
+    """u8: x is the raw-pixel plane (clip_ingest_u8(raw=True)), scale / shift come from conv1a_u8_scale_shift; with `w_cat`
+    (pack_conv1a_weight_cat) and 64 output channels the resident-halo kernel runs."""
     N, T, H, Wp_, C4 = x.hi.shape
     taps, Cout, K = w.hi.shape
     assert Wp_ == W + CLIP_WPAD and C4 == CLIP_CPAD and taps == 49 and K == CLIP_WIN * CLIP_CPAD
@@ -460,7 +472,12 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
     t0 = PROFILE.begin()
     if _lib.TRACE is not None:
         _lib.LABEL = (f"conv1a fwd N{N} {T}x{H}x{W} Cout{Cout} x{nsplit}", 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
-    _lib.call("otal_conv1a_fwd_u8" if u8 else "otal_conv1a_fwd", ctypes.byref(d), _stream())
+    if u8 and CONV1A_HALO and w_cat is not None and Cout == 64 and T % 2 == 0 and H % 2 == 0 and W % 2 == 0 and min(T, H, W) >= 6:
+        assert tuple(w_cat.shape) == (49, 2 * Cout, CLIP_WIN * CLIP_CPAD) and w_cat.dtype == torch.bfloat16 and w_cat.is_contiguous()
+        d.w_hi, d.w_lo = w_cat.data_ptr(), None
+        _lib.call("otal_conv1a_fwd_u8_halo", ctypes.byref(d), _stream())
+    else:
+        _lib.call("otal_conv1a_fwd_u8" if u8 else "otal_conv1a_fwd", ctypes.byref(d), _stream())
     PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)   # algorithmic: 3 channels, 7^3 taps
     return out
 

@@ -127,12 +127,12 @@ class Emulator:
         c[0], c[n - 2], c[n - 1] = 1, 2, 3
         return c
 
-    def _conv1a_fwd(self, desc, u8):
+    def _conv1a_fwd(self, desc, u8, w=None):
         d = desc._obj
         N, T, H, W, Cout = d.N, d.T, d.H, d.W, d.Cout
         x = _load(d.x_hi, None if u8 else d.x_lo, (N, T, H, W + 8, 4), 0, 4)[:, :, :, 2:W + 2, :3]
         pf = tuple(2 if n % 2 == 0 else 3 for n in (T, H, W))
-        y = _conv(x, self._w1a(d, Cout), (2, 2, 2), pf)
+        y = _conv(x, self._w1a(d, Cout) if w is None else w, (2, 2, 2), pf)
         To, Ho, Wo = y.shape[1:4]
         sc = _view(d.scale, Cout, np.float32) if d.scale else torch.ones(Cout)
         if u8:
@@ -150,6 +150,14 @@ class Emulator:
 
     def otal_conv1a_fwd_u8(self, desc, stream):
         self._conv1a_fwd(desc, True)
+
+    def otal_conv1a_fwd_u8_halo(self, desc, stream):
+        """Same operator; w_hi = packed [49][2*Cout][32] (hi rows, then lo rows per tap)."""
+        d = desc._obj
+        Cout = d.Cout
+        wc = _bf16(d.w_hi, 49 * 2 * Cout * 32).view(49, 2 * Cout, 32).float()
+        w = (wc[:, :Cout] + wc[:, Cout:]).view(7, 7, Cout, 8, 4)[:, :, :, :7, :3].permute(2, 4, 0, 1, 3).contiguous()
+        self._conv1a_fwd(desc, True, w=w)
 
     def _conv1a_wgrad(self, desc, u8):
         d = desc._obj

@@ -47,7 +47,7 @@ def test_raw_ingest_is_exact():
     assert torch.equal(got.hi.float().cpu(), want)
 
 
-@pytest.mark.parametrize("shape", [(1, 16, 24, 24), (2, 12, 16, 32), (1, 8, 8, 16)])
+@pytest.mark.parametrize("shape", [(1, 16, 24, 24), (2, 12, 16, 32), (1, 8, 8, 16), (1, 6, 96, 96), (1, 8, 64, 40)])
 def test_conv1a_fwd_u8(shape):
     from opental_b200 import ops
     N, T, H, W = shape
@@ -70,6 +70,12 @@ def test_conv1a_fwd_u8(shape):
         a = ops.Planes(hi, None)
     y = ops.conv1a_fwd(a, ops.pack_conv1a_weight(w), W, scale=sc, shift=tab, relu=True, u8=True)
     assert rel(y.float().permute(0, 4, 1, 2, 3).cpu(), ref) < TOL
+    # the resident-halo kernel (the default when the packed [hi | lo] weights are passed): same operator, same tolerance, and
+    # the same tensor-core products as the generic kernel in a different order (partial 16 x 8 tiles are clipped by TMA)
+    wp = ops.pack_conv1a_weight(w)
+    yh = ops.conv1a_fwd(a, wp, W, scale=sc, shift=tab, relu=True, u8=True, w_cat=ops.pack_conv1a_weight_cat(wp))
+    assert rel(yh.float().permute(0, 4, 1, 2, 3).cpu(), ref) < TOL
+    assert rel(yh.float().cpu(), y.float().cpu()) < 2e-5
     # and it agrees with the validated bf16x3 form on the normalised planes
     y3 = ops.conv1a_fwd(ops.clip_ingest(x.cuda()), ops.pack_conv1a_weight(w), W, scale=scale, shift=shift, relu=True)
     assert rel(y.float().cpu(), y3.float().cpu()) < TOL

@@ -61,12 +61,14 @@ reps = 11
 a3 = ops.clip_ingest_u8(px, 96)
 a8 = ops.clip_ingest_u8(px, 96, raw=True)
 sc8, tab8 = ops.conv1a_u8_scale_shift(w, scale, shift)
+wcat = ops.pack_conv1a_weight_cat(wp)
 dw = torch.zeros(49, 64, 32, device=dev)
 rows = [
     ("ingest  normalised hi+lo", lambda: ops.clip_ingest_u8(px, 96)),
     ("ingest  raw one plane   ", lambda: ops.clip_ingest_u8(px, 96, raw=True)),
     ("fwd     bf16x3          ", lambda: ops.conv1a_fwd(a3, wp, 96, scale=scale, shift=shift)),
     ("fwd     u8              ", lambda: ops.conv1a_fwd(a8, wp, 96, scale=sc8, shift=tab8, u8=True)),
+    ("fwd     u8 halo         ", lambda: ops.conv1a_fwd(a8, wp, 96, scale=sc8, shift=tab8, u8=True, w_cat=wcat)),
     ("wgrad   bf16x3          ", lambda: ops.conv1a_wgrad(a3, d, dw, 96)),
     ("wgrad   u8              ", lambda: ops.conv1a_wgrad(a8, d, dw, 96, u8=True)),
     ("class sums of dY        ", lambda: ops.border_class_sums(d)),
