@@ -475,7 +475,7 @@ class I3DBackbone(nn.Module):
                 ops.conv1a_wgrad(a, d, dw, W, u8=u8)
                 # packed layout of this block is [kt,kh,kw,Cout,Cin]; the parameter's .grad is its strided view
                 if u8:
-                    r.unit.conv3d.weight.grad.add_(ops.conv1a_u8_weight_grad(dw, ops.border_class_sums(d), r.cin))
+                    r.unit.conv3d.weight.grad.add_(ops.conv1a_u8_weight_grad(dw, None, r.cin))
                 else:
                     r.unit.conv3d.weight.grad.add_(ops.unpack_conv1a_wgrad(dw, r.cin))
         self._retire_all()

@@ -244,6 +244,10 @@ __global__ void clip_ingest_u8_raw_kernel(const unsigned char* __restrict__ px, 
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 v32[c >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)src[c])) << ((c & 1) * 16);
+            // channel slot 3 = 1.0 inside the image (0 in the padding): the forward weights of that slot are zero, and in the
+            // weight gradient its column is sum_p D[p] * [tap inside the image at p] — the term that turns the raw-pixel
+            // gradient into the gradient of the conv on the normalised, zero-padded clip (ops.conv1a_u8_weight_grad), for free
+            v32[1] |= 0x3F80u << 16;
         }
         reinterpret_cast<uint2*>(out)[i] = make_uint2(v32[0], v32[1]);
     }

@@ -538,12 +538,18 @@ def conv1a_u8_scale_shift(w: torch.Tensor, bn_scale: torch.Tensor, bn_shift: tor
     return bn_scale * U8_SCALE, (bn_shift - bn_scale * s).contiguous()
 
 
-def conv1a_u8_weight_grad(dw_raw: torch.Tensor, class_sums: torch.Tensor, C: int = 3) -> torch.Tensor:
-    """dW [Cout,C,7,7,7] of the reference's conv from the raw-pixel gradient dw_raw [49,Cout,32] (conv1a_wgrad(u8=True)) and
-    the border-class sums of the output gradient [4,4,4,Cout] (border_class_sums):
-    dW[co,ci,tap] = (2/255) * sum_p D[p,co] u[p+tap,ci] - sum_{p: tap inside the image} D[p,co]."""
-    m = border_class_masks(dw_raw.device).to(dw_raw.dtype)
-    r = torch.einsum("abco,at,bh,cw->othw", class_sums, m, m, m)                  # [Cout,7,7,7]
+def conv1a_u8_weight_grad(dw_raw: torch.Tensor, class_sums: torch.Tensor | None = None, C: int = 3) -> torch.Tensor:
+    """dW [Cout,C,7,7,7] of the reference's conv from the raw-pixel gradient dw_raw [49,Cout,32] (conv1a_wgrad(u8=True)):
+    dW[co,ci,tap] = (2/255) * sum_p D[p,co] u[p+tap,ci] - R[co,tap],   R[co,tap] = sum_{p: tap inside the image} D[p,co].
+    R comes for free: the raw plane carries 1.0 in channel slot 3 of every in-image pixel (otal_clip_ingest_u8_raw), so
+    R[co,(dt,dh,dw)] = dw_raw[dt*7+dh, co, dw*4+3].  With `class_sums` ([4,4,4,Cout], border_class_sums) R is formed from the
+    border-class sums of the output gradient instead (the round-1 form, kept for planes without the ones slot)."""
+    if class_sums is None:
+        Cout = dw_raw.shape[1]
+        r = dw_raw.reshape(7, 7, Cout, 8, CLIP_CPAD)[:, :, :, :7, 3].permute(2, 0, 1, 3)      # [Cout,7,7,7]
+    else:
+        m = border_class_masks(dw_raw.device).to(dw_raw.dtype)
+        r = torch.einsum("abco,at,bh,cw->othw", class_sums, m, m, m)              # [Cout,7,7,7]
     return unpack_conv1a_wgrad(dw_raw, C) * U8_SCALE - r[:, None]
 
 

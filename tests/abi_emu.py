@@ -112,6 +112,7 @@ class Emulator:
     def otal_clip_ingest_u8_raw(self, px, crop, fmap, out_ptr, N, T, Hs, Ws, H, W, stream):
         out = torch.zeros(N, T, H, W + 8, 4)
         out[:, :, :, 2:W + 2, :3] = self._ingest_pixels(px, crop, fmap, N, T, Hs, Ws, H, W)
+        out[:, :, :, 2:W + 2, 3] = 1.0                                   # the ones slot (in-image indicator)
         _store(out, out_ptr, None, (N, T, H, W + 8, 4), 0)
 
     # ---------------------------------------------------------------------------------------------- Conv3d_1a (folded)

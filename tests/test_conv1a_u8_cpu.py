@@ -74,6 +74,13 @@ def test_weight_gradient_identity(shape):
     got = ops.conv1a_u8_weight_grad(folded.reshape(49, cout, 32), sums, 3)
     assert got.shape == ref.shape
     assert float((got - ref).abs().max()) < 1e-11 * float(ref.abs().max())
+    # default form: R read from the ones slot (channel slot 3 = in-image indicator) of the folded gradient itself
+    ones = torch.zeros(1, 1, *u.shape[2:], dtype=torch.double); ones[...] = 1.0
+    wo = torch.zeros(cout, 1, 7, 7, 7, dtype=torch.double, requires_grad=True)
+    (r_ind,) = torch.autograd.grad(F.conv3d(F.pad(ones.expand(u.shape[0], 1, *u.shape[2:]), PAD), wo, stride=2), wo, d)
+    folded[:, :, :, :7, 3] = r_ind[:, 0].permute(1, 2, 0, 3)
+    got1 = ops.conv1a_u8_weight_grad(folded.reshape(49, cout, 32), None, 3)
+    assert float((got1 - ref).abs().max()) < 1e-11 * float(ref.abs().max())
 
 
 def test_pixel_values_are_exact_in_bf16():

@@ -44,6 +44,7 @@ def test_raw_ingest_is_exact():
         i, j, flip = (int(v) for v in offs[n])
         x = px[n, :, i:i + 16, j:j + 16, :].float()
         want[n, :, :, 2:18, :3] = x.flip(2) if flip else x
+        want[n, :, :, 2:18, 3] = 1.0            # the ones slot: in-image indicator (ops.conv1a_u8_weight_grad)
     assert torch.equal(got.hi.float().cpu(), want)
 
 
@@ -110,8 +111,10 @@ def test_conv1a_wgrad_u8(shape):
     d = ops.split_bf16(gy.permute(0, 2, 3, 4, 1).contiguous().cuda())
     dw = torch.zeros(49, 64, 32).cuda()
     ops.conv1a_wgrad(ops.clip_ingest_u8(px.cuda(), W, raw=True), d, dw, W, u8=True)
-    got = ops.conv1a_u8_weight_grad(dw, ops.border_class_sums(d), 3)
+    got = ops.conv1a_u8_weight_grad(dw, ops.border_class_sums(d), 3)          # R from the border-class sums (round-1 form)
     assert rel(got.cpu(), gw_ref) < TOL
+    got1 = ops.conv1a_u8_weight_grad(dw, None, 3)                             # R from the ones slot of the raw plane (default)
+    assert rel(got1.cpu(), gw_ref) < TOL
 
 
 def test_model_step_matches_the_bf16x3_path():

@@ -136,7 +136,8 @@ def test_training_loop_from_dataset_files_on_the_emulated_abi(monkeypatch, tmp_p
     assert m["steps"] == 2 and len(seen) == 2 and all(np.isfinite(c) for _, _, c in seen) and np.isfinite(m["grad_norm"])
     assert m["ssl_steps"] == sum(s for _, s, _ in seen)
     if m["ssl_steps"]:
-        assert emu.calls["otal_clip_ingest_u8"] == 2 + m["ssl_steps"]                     # main pass + frame-map pass
+        ingest = "otal_clip_ingest_u8_raw" if net.backbone.u8_conv1a else "otal_clip_ingest_u8"
+        assert emu.calls[ingest] == 2 + m["ssl_steps"]                                    # main pass + frame-map pass
     assert set(train_loop.TERMS) <= set(m) and "Train Loss" in train_loop.summary_line(1, m)
     ck, st = str(tmp_path / "ck"), str(tmp_path / "ck" / "training")
     tr.save_checkpoint(1, ck, st)
