@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the extra legs of the default run (ActivityNet config, "
+                    "clip length x batch sweep, inference protocol: BASELINE.json configs[3], configs[4])")
     ap.add_argument("--ssl", action="store_true", help="add the self-supervised second pass (cut-paste clip through the frame map + "
                     "triplet loss, train.py:237-242) to every step; the headline number is quoted without it (SURVEY §8d)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch from the host instead of replaying the captured step")
@@ -444,6 +446,145 @@ def load_peaks() -> dict:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, measured in the same run: configs[3] (ActivityNet) and configs[4] (clip length x batch)
+# ------------------------------------------------------------------------------------------------------------------
+def measure_point(tr, *, anet: bool, T: int, B: int, dev, world: int, rank: int, peaks: dict, steps: int = 5, warmup: int = 2) -> dict:
+    """One point of the sweep on an existing Trainer: a CUDA-graph captured training step at batch B of T-frame uint8 clips
+    resident in HBM, `warmup` + `steps` replays, CUDA events, MAX over ranks (barrier + synchronize on both sides); both
+    rooflines (algorithmic conv FLOPs vs the measured bf16 peak; algorithmic activation bytes vs the measured copy bandwidth)."""
+    import torch
+    import torch.distributed as dist
+
+    from opental_b200 import engine
+    from opental_b200.multisegment_loss import pad_targets
+    torch.cuda.reset_peak_memory_stats()
+    g = torch.Generator(device=dev).manual_seed(1000 * rank + B)
+    clips = torch.randint(0, 256, (B, T, 112, 112, 3), generator=g, dtype=torch.uint8, device=dev)     # i.i.d. pixels (SURVEY §8d)
+    tg = [engine.synthetic_targets(i, rank, num_classes=150 if anet else 15) for i in range(B)]
+    sc = torch.stack([engine.synthetic_scores(t, frames=T) for t in tg]).to(dev)
+    tp, tv = (t.to(dev) for t in pad_targets(tg, device="cpu"))
+    tr._graph = None
+    mode = "graph"
+    try:
+        tr.capture(clips, (tp, tv), sc)
+    except Exception:  # noqa: BLE001   (B x priors > 4096: the loss takes its torch formulation, which synchronises)
+        tr._graph = None
+        mode = "eager"
+        torch.cuda.synchronize()
+    try:
+        for _ in range(warmup):
+            tr.step(clips, (tp, tv), sc)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tr.step(clips, (tp, tv), sc)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    finally:
+        tr._graph = tr._graph_out = tr._static = None
+        tr._graph_cache.clear()
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    tf = B * FLOP_TRAIN_256 * T / 256.0 / (ms * 1e-3) / 1e12
+    hbm = hbm_estimate(dict(mode="train", frames=T), B, ms, peaks)
+    return {"frames": T, "batch_per_gpu": B, "ms_per_step": round(ms, 3), "clips_per_s": round(world * B * 1000.0 / ms, 2),
+            "tensor_tflops_per_gpu": round(tf, 1), "tensor_frac": round(tf / peak_tf, 4), "hbm_gbs": round(hbm["achieved"], 0),
+            "hbm_frac": round(hbm["frac"], 4), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1), "mode": mode}
+
+
+def other_configs(args, dev, world: int, rank: int, peaks: dict) -> dict:
+    """BASELINE.json configs[3] and configs[4] and the inference protocol on the SAME GPUs in the SAME run, a few steps each
+    (bounded: ~30 s), so that the driver's 1/2/4/8-GPU runs of the default command carry them.  Every rank takes part (the
+    training points contain the gradient all-reduce).  A failing point is reported as text and does not stop the line."""
+    import torch
+
+    from opental_b200 import engine
+    out = {"how": "each point: CUDA-graph captured training step, 2 warm-up + 5 timed replays, CUDA events, max over ranks; uint8 "
+                  "clips resident in HBM; clips_per_s is the whole job's; tensor_frac = algorithmic conv FLOPs / measured sustained "
+                  "bf16 peak, hbm_frac = algorithmic activation bytes / measured copy bandwidth (both per GPU)"}
+
+    def release():
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    # configs[3]: ActivityNet OpenTAL, 768-frame clips, 150 classes, per-sample loss, backbone at 0.1 x the head's rate
+    try:
+        torch.manual_seed(0)
+        net, crit = engine.build_opental_anet(device=dev, precision=args.precision, epoch=11)
+        tr = engine.Trainer(net, crit, lr=1e-5, weight_decay=1e-3, backbone_lr_scale=0.1)
+        tr.broadcast_parameters(0)
+        out["anet"] = {"workload": "ActivityNet OpenTAL (configs/anet_opental.yaml --open_set) training step; clips 3x768x96x96",
+                       **measure_point(tr, anet=True, T=768, B=args.batch, dev=dev, world=world, rank=rank, peaks=peaks)}
+        del tr, net, crit
+    except Exception as ex:  # noqa: BLE001
+        out["anet"] = {"error": repr(ex)[:200]}
+    release()
+    # configs[4]: clip length 128..1024 x batch 1..16
+    pts = []
+    for T in (128, 256, 512, 1024):
+        try:
+            torch.manual_seed(0)
+            net, crit = engine.build_opental(device=dev, precision=args.precision, frame_num=T, epoch=11)
+            tr = engine.Trainer(net, crit, lr=1e-5, weight_decay=1e-3)
+            tr.broadcast_parameters(0)
+            for B in (1, 2, 4, 8, 16):
+                try:
+                    pts.append(measure_point(tr, anet=False, T=T, B=B, dev=dev, world=world, rank=rank, peaks=peaks))
+                except Exception as ex:  # noqa: BLE001
+                    pts.append({"frames": T, "batch_per_gpu": B, "error": repr(ex)[:200]})
+                release()
+            del tr, net, crit
+        except Exception as ex:  # noqa: BLE001
+            pts.append({"frames": T, "error": repr(ex)[:200]})
+        release()
+    out["cliplen_batch_sweep"] = pts
+    # inference under the reference's only published protocol (AFSD/thumos14/BDNet.py:564-583) + batch-8 forward throughput
+    try:
+        torch.manual_seed(0)
+        net, _ = engine.build_opental(device=dev, precision=args.precision, frame_num=256, epoch=11)
+        net.eval()
+        with torch.no_grad():
+            x1 = torch.randn(1, 3, 256, 96, 96, device=dev)
+            for _ in range(2):
+                net(x1)
+            torch.cuda.synchronize()
+            t_run = 0.0
+            for _ in range(10):
+                torch.cuda.synchronize(); t0 = time.time()
+                net(x1)
+                torch.cuda.synchronize(); t_run += time.time() - t0
+            ms1 = t_run / 10 * 1e3
+            xb = torch.randint(0, 256, (args.batch, 256, 112, 112, 3), dtype=torch.uint8, device=dev)
+            for _ in range(2):
+                net(xb)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                net(xb)
+            e1.record()
+            torch.cuda.synchronize()
+            msb = e0.elapsed_time(e1) / 5
+        out["inference"] = {"reference_protocol_ms": round(ms1, 3), "infer_fps": round(1000.0 / ms1, 1),
+                            "protocol": "randn [1,3,256,96,96], 2 warm-ups, mean wall time of 10 synchronised eager forwards",
+                            "batch": args.batch, "forward_ms": round(msb, 3), "forward_clips_per_s_per_gpu": round(args.batch * 1000.0 / msb, 1),
+                            "forward_tensor_frac": round(args.batch * FLOP_FWD_256 / (msb * 1e-3) / 1e12 / (peaks.get("bf16_tflops_sustained") or 1400.0), 4),
+                            "note": "eager forwards (host-enqueued); `--mode infer` gives the graph-replayed number with its e2e leg"}
+        del net
+    except Exception as ex:  # noqa: BLE001
+        out["inference"] = {"error": repr(ex)[:200]}
+    release()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------------------------
 def run_native(args):
@@ -613,12 +754,21 @@ def run_native(args):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         in_sync = bool(torch.equal(hi, lo))
 
+    peaks = load_peaks()
+    others = None
+    default_run = not anet and T == 256 and not args.ssl and args.precision == "bf16x3" and not args.no_graph
+    if default_run and not args.no_other_configs:
+        # free the headline model first: the sweep's largest point (1024 frames x 16) wants ~43 GB
+        del graph, devb
+        tr._graph = tr._graph_out = tr._static = None
+        tr._graph_cache.clear()
+        others = other_configs(args, dev, world, rank, peaks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks.get("bf16_tflops_sustained") else "fallback 1.4 PFLOP/s sustained"
     roof = {}
@@ -673,6 +823,7 @@ def run_native(args):
         "model_tflops_per_gpu": value / world * wl["flop_clip"] / 1e12,
         "hbm": hbm_estimate(wl, B, ms, peaks),
         "cpu_baseline": cpu_base,
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -276,10 +276,18 @@ OTAL_API int otal_ncdhw_to_ndhwc_split(const float* x, uint16_t* hi, uint16_t* l
                               int Cpad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * MultiSegmentLoss (THUMOS14 OpenTAL configuration: cls_loss_type 'edl' with loss_type 'log', evidence 'exp', os_head)
- * — replaces MultiSegmentLoss.forward            AFSD/thumos14/multisegment_loss.py:92-259 (iou_loss :20-53)
+ * MultiSegmentLoss, three flavours (desc.flavour):
+ *  0  THUMOS14 OpenTAL (cls_loss_type 'edl' with loss_type 'log', evidence 'exp', os_head) — replaces
+ *            MultiSegmentLoss.forward                 AFSD/thumos14/multisegment_loss.py:92-259 (iou_loss :20-53)
  *            EvidenceLoss.forward/edl_loss/iou_calib  AFSD/thumos14/cls_loss.py:120-168, :212-278
  *            ActionnessLoss.forward                   AFSD/thumos14/cls_loss.py:299-339
+ *  1  ActivityNet OpenTAL — replaces MultiSegmentLoss.forward AFSD/anet/multisegment_loss.py:106-301 (level_bounds = its
+ *            `bounds` :69-83 as (left, right] per pyramid level, the level read from priors[p*prior_stride + 1]; per-sample
+ *            normalisation, smooth-L1, min(piou, max IoU) refinement threshold) and AFSD/anet/cls_loss.py:116-152, :225-232
+ *            (stateless IBM weight 1 / (||z||_1 exp(ibm_coeff g) + 1e-10); weight_accum unused)
+ *  2  THUMOS14 closed set (configs/thumos14.yaml: cls_loss_type 'focal', no os_head) — multisegment_loss.py:92-259 with
+ *            FocalLoss_Ori AFSD/thumos14/cls_loss.py:6-78 on the softmax of all priors (K counts the background class 0;
+ *            focal_alpha = weight of class 0, 1 - focal_alpha of the others; act / prop_act NULL; losses[5], [6] = 0)
  * and their autograd backward.  One single-CTA launch computes the 7 losses and the gradient of each loss w.r.t. each
  * head output ("unit gradients", stored in `workspace`); otal_msl_backward scales them by the 7 upstream gradients.
  *
@@ -304,6 +312,10 @@ typedef struct otal_msl_desc {
     float* weight_accum;
     float* losses;
     float* workspace;
+    int flavour;                 /* 0 THUMOS14 EDL, 1 ActivityNet EDL, 2 THUMOS14 closed-set focal */
+    float ibm_coeff;             /* flavour 1 */
+    float focal_alpha, focal_gamma;   /* flavour 2 */
+    float level_bounds[16];      /* flavour 1: (left, right) per pyramid level, up to 8 levels */
 } otal_msl_desc;
 OTAL_API long long otal_msl_workspace_floats(int B, int P, int K);
 OTAL_API int otal_msl_forward(const otal_msl_desc* desc, void* stream);

@@ -73,7 +73,9 @@ class MslDesc(Structure):
                 + [("momentum", c_float)] + _ints("iou_aware") + [("act_weight", c_float), ("act_margin", c_float)]
                 + _ints("prior_stride")
                 + _ptrs("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "priors", "targets", "valid",
-                        "weight_accum", "losses", "workspace"))
+                        "weight_accum", "losses", "workspace")
+                + _ints("flavour") + [("ibm_coeff", c_float), ("focal_alpha", c_float), ("focal_gamma", c_float),
+                                      ("level_bounds", c_float * 16)])
 
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/opental_b200.h.

@@ -77,6 +77,8 @@ class FocalLoss_Ori(nn.Module):
         else:
             a = alpha
         self.register_buffer("alpha", a, persistent=False)
+        # host copy of the (background, other classes) weights when alpha has that two-value form (the fused kernel's form)
+        self.alpha0 = float(alpha) if isinstance(alpha, (float, int)) and balance_index == 0 else None
         self.epoch, self.total_epoch = 0, 25
 
     def forward(self, prob, target, weight=None):
@@ -333,12 +335,17 @@ class MultiSegmentLoss(nn.Module):
         return loc_t, conf_t, prop_loc_t, prop_conf_t, iou
 
     def _fused_ok(self, loc) -> bool:
-        """The single-CTA CUDA kernel covers the OpenTAL configuration; every other variant (focal loss, digamma / mse,
-        relu / softplus evidence, soft labels, focal-EDL / GHM / IB re-weighting, size_average, closed-set head) runs the masked torch formulation below."""
+        """The single-CTA CUDA kernel covers the OpenTAL configuration (edl: log / exp, plain or IBM, os_head) and the closed-set
+        baseline (configs/thumos14.yaml: softmax focal loss, no os_head); the ablation variants (digamma / mse, relu / softplus
+        evidence, soft labels, focal-EDL / GHM / IB re-weighting, size_average) run the masked torch formulation below."""
         c = self.cls_loss
-        return (self.fused and loc.is_cuda and loc.dtype == torch.float32 and self.cls_loss_type == "edl" and self.os_head
-                and not self.size_average and c.loss_type == "log" and c.evidence == "exp" and not c.soft_label
-                and not (c.with_focal or c.with_ghm or c.with_ibloss) and loc.shape[0] * loc.shape[1] <= 4096)
+        if not (self.fused and loc.is_cuda and loc.dtype == torch.float32 and not self.size_average
+                and loc.shape[0] * loc.shape[1] <= 4096):
+            return False
+        if self.cls_loss_type == "focal":
+            return not self.os_head and c.alpha0 is not None and c.num_class < 1024
+        return (self.cls_loss_type == "edl" and self.os_head and c.loss_type == "log" and c.evidence == "exp" and not c.soft_label
+                and not (c.with_focal or c.with_ghm or c.with_ibloss))
 
     def forward(self, output_dict, targets, pre_locs=None):
         loc, conf, ploc, pconf, center, priors = (output_dict[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))
@@ -346,6 +353,14 @@ class MultiSegmentLoss(nn.Module):
         B, P = loc.shape[:2]
         K = self.num_classes
         tgt, valid = pad_targets(targets, loc.device)
+        if self._fused_ok(loc) and self.cls_loss_type == "focal":
+            from . import ops
+            cfg = dict(clip_length=float(self.clip_length), overlap_thresh=float(self.overlap_thresh), use_ibm=False, momentum=0.0,
+                       iou_aware=False, act_weight=0.0, act_margin=0.0, flavour=ops.MSL_FOCAL,
+                       focal_alpha=self.cls_loss.alpha0, focal_gamma=float(self.cls_loss.gamma))
+            vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), None, None, priors, tgt, valid, None, cfg)
+            self.last_stats = stats
+            return tuple(vec[:5].unbind(0)) + (None, None)
         if self._fused_ok(loc):
             c = self.cls_loss
             use_ibm = bool(c.with_ibm and c.epoch >= c.ibm_start)
@@ -439,6 +454,7 @@ class MultiSegmentLossANet(nn.Module):
         self.act_weight, self.act_margin, self.ibm_coeff = act_weight, act_margin, ibm_coeff
         self.os_head = True
         self._bounds = {}
+        self.fused = True       # the single-CTA CUDA kernel (csrc/msl.cu, flavour 1) when the inputs allow it
 
     def _edl(self, logit, label, mask):
         """Per-sample sum over the masked priors of the (IBM-weighted) log EDL loss.  logit [B,P,K]."""
@@ -479,6 +495,16 @@ class MultiSegmentLossANet(nn.Module):
         K = self.num_classes
         tgt, valid = pad_targets(targets, loc.device)
         clip = float(self.clip_length)
+        if self.fused and loc.is_cuda and loc.dtype == torch.float32 and B * P <= 4096 and B <= 64 and priors.dim() == 2:
+            from . import ops
+            c = self.cls_loss
+            cfg = dict(clip_length=clip, overlap_thresh=float(self.overlap_thresh), use_ibm=bool(c.with_ibm and c.epoch >= c.ibm_start),
+                       momentum=0.0, iou_aware=bool(self.iou_aware), act_weight=float(self.act_weight), act_margin=float(self.act_margin),
+                       flavour=ops.MSL_ANET, ibm_coeff=float(self.ibm_coeff), level_bounds=ANET_BOUNDS)
+            vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P), pact.reshape(B, P),
+                                           priors, tgt, valid, None, cfg)
+            self.last_stats = stats
+            return tuple(vec.unbind(0))
         with torch.no_grad():       # matching, anet/multisegment_loss.py:142-190
             c = priors[:, 0].view(1, -1, 1)
             lvl = priors[:, 1].long()

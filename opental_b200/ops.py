@@ -687,10 +687,16 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 # ----------------------------------------------------------------------------------------------------------
 # MultiSegmentLoss (single-CTA fused kernel)
 # ----------------------------------------------------------------------------------------------------------
+MSL_THUMOS, MSL_ANET, MSL_FOCAL = 0, 1, 2
+
+
 def msl_forward(loc, conf, prop_loc, prop_conf, center, act, prop_act, priors, targets, valid, weight_accum, *,
                 clip_length: float, overlap_thresh: float, use_ibm: bool, momentum: float, iou_aware: bool,
-                act_weight: float, act_margin: float) -> tuple[torch.Tensor, torch.Tensor]:
-    """All 7 losses (+ N, PN, AN, PAN, loss_iouc) and the unit-gradient workspace.  See include/opental_b200.h."""
+                act_weight: float, act_margin: float, flavour: int = MSL_THUMOS, ibm_coeff: float = 10.0,
+                focal_alpha: float = 0.25, focal_gamma: float = 2.0, level_bounds=()) -> tuple[torch.Tensor, torch.Tensor]:
+    """All 7 losses (+ N, PN, AN, PAN, loss_iouc) and the unit-gradient workspace.  See include/opental_b200.h.
+    flavour: MSL_THUMOS (OpenTAL EDL), MSL_ANET (per-sample ActivityNet loss; level_bounds = ((left, right), ...) per pyramid
+    level, priors [P,2] with the level in column 1) or MSL_FOCAL (closed-set softmax focal loss; act / prop_act None)."""
     _require_cuda(loc, conf, prop_loc, prop_conf, center, priors, targets, valid)
     B, P, K = conf.shape
     G = targets.shape[1]
@@ -708,7 +714,12 @@ def msl_forward(loc, conf, prop_loc, prop_conf, center, act, prop_act, priors, t
                 loc=ts[0].data_ptr(), conf=ts[1].data_ptr(), prop_loc=ts[2].data_ptr(), prop_conf=ts[3].data_ptr(),
                 center=ts[4].data_ptr(), act=_ptr(ts[5]), prop_act=_ptr(ts[6]), priors=priors.data_ptr(),
                 targets=targets.data_ptr(), valid=valid.data_ptr(), weight_accum=_ptr(weight_accum),
-                losses=losses.data_ptr(), workspace=ws.data_ptr())
+                losses=losses.data_ptr(), workspace=ws.data_ptr(), flavour=int(flavour), ibm_coeff=ibm_coeff,
+                focal_alpha=focal_alpha, focal_gamma=focal_gamma)
+    flat = [float(v) for pair in level_bounds for v in pair]
+    assert len(flat) <= 16, "msl: at most 8 pyramid levels"
+    for i, v in enumerate(flat):
+        d.level_bounds[i] = v
     _lib.call("otal_msl_forward", ctypes.byref(d), _stream())
     return losses, ws
 

@@ -425,19 +425,22 @@ class Emulator:
         _view(gx, B * T * C, np.float32).view(B * T, C).copy_(_view(g, 1, np.float32) * _view(coef, B * T, np.float32).view(-1, 1) * (1 - th * th))
 
     def otal_msl_forward(self, desc, stream):
-        """The 7 losses by the ORACLE's restatement of the reference loss (independent of the product's torch formulation);
-        the unit gradients of each loss w.r.t. each head output are kept on the side, keyed by the workspace pointer."""
+        """The 7 losses by the ORACLE's restatement of the reference loss (independent of the product's torch formulation) — the
+        THUMOS14 EDL, ActivityNet EDL or closed-set focal flavour; the unit gradients of each loss w.r.t. each head output are kept
+        on the side, keyed by the workspace pointer."""
         import opental_oracle as O
         d = desc._obj
         B, P, K, G = d.B, d.P, d.K, d.G
-        M = B * P
         names = ("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act")
         shapes = ((B, P, 2), (B, P, K), (B, P, 2), (B, P, K), (B, P, 1), (B, P, 1), (B, P, 1))
         ptrs = (d.loc, d.conf, d.prop_loc, d.prop_conf, d.center, d.act, d.prop_act)
-        assert d.act and d.prop_act, "abi_emu: the fused loss is emulated for the os_head configuration"
+        focal, anet = d.flavour == 2, d.flavour == 1
+        assert focal or (d.act and d.prop_act), "abi_emu: the EDL flavours of the fused loss are emulated for the os_head configuration"
         with torch.enable_grad():
-            out = {n: _view(p_, int(np.prod(sh)), np.float32).view(*sh).clone().requires_grad_(True) for n, sh, p_ in zip(names, shapes, ptrs)}
-            pri = _view(d.priors, (P - 1) * d.prior_stride + 1, np.float32)[::d.prior_stride].view(P, 1)
+            out = {n: (_view(p_, int(np.prod(sh)), np.float32).view(*sh).clone().requires_grad_(True) if p_ else None)
+                   for n, sh, p_ in zip(names, shapes, ptrs)}
+            ncol = 2 if anet else 1
+            pri = torch.stack([_view(d.priors, (P - 1) * d.prior_stride + ncol, np.float32)[c::d.prior_stride][:P] for c in range(ncol)], 1)
             tg = _view(d.targets, B * G * 3, np.float32).view(B, G, 3)
             va = _view(d.valid, B * G, np.uint8).view(B, G).bool()
             targets = [tg[b][va[b]] for b in range(B)]
@@ -445,23 +448,37 @@ class Emulator:
                                  ibm_start=10, momentum=float(d.momentum), num_bins=max(int(d.num_bins), 1), iou_aware=bool(d.iou_aware),
                                  act_weight=float(d.act_weight), act_margin=float(d.act_margin))
             state = O.LossState(epoch=11 if d.use_ibm else 1)
-            wa = _view(d.weight_accum, d.num_bins, np.float32) if d.weight_accum and d.num_bins else None
+            wa = _view(d.weight_accum, d.num_bins, np.float32) if d.weight_accum and d.num_bins and not anet else None
             if wa is not None:
                 state.weight_accum = wa.clone()
-            losses = O.multisegment_loss(dict(out, priors=pri), targets, state, cfg)
-            unit = [torch.autograd.grad(l, [out[n] for n in names], retain_graph=True, allow_unused=True) for l in losses]
+            if focal:
+                losses = O.multisegment_loss_closed(dict(out, priors=pri), targets, cfg)
+            elif anet:
+                cfg.ibm_coeff = float(d.ibm_coeff)
+                assert [float(v) for v in d.level_bounds[:12]] == [float(v) for pair in O.ANET_BOUNDS for v in pair]
+                losses = O.multisegment_loss_anet(dict(out, priors=pri), targets, state, cfg)
+            else:
+                losses = O.multisegment_loss(dict(out, priors=pri), targets, state, cfg)
+            live = [out[n] for n in names if out[n] is not None]
+            unit = []
+            for l in losses:
+                gs = iter(torch.autograd.grad(l, live, retain_graph=True, allow_unused=True) if torch.is_tensor(l) and l.requires_grad
+                          else [None] * len(live))
+                unit.append([next(gs) if out[n] is not None else None for n in names])
+            unit += [[None] * 7] * (7 - len(unit))
         if wa is not None:
             wa.copy_(state.weight_accum)
         lv = _view(d.losses, 16, np.float32)
         lv.zero_()
         for i, l in enumerate(losses):
             lv[i] = float(l)
-        _, conf_t, _, prop_conf_t, iou_pred = O.match_priors(out["loc"].detach(), pri, targets, cfg)
-        pos, ppos = (conf_t > 0).view(-1), (prop_conf_t > 0).view(-1)
-        lv[7], lv[8] = float(pos.sum()), float(ppos.sum())
-        lv[9] = float(O.actionness_loss(out["act"].detach().view(-1, 1), pos.float(), cfg)[1])
-        lv[10] = float(O.actionness_loss(out["prop_act"].detach().view(-1, 1), ppos.float(), cfg)[1])
-        lv[11] = float(O.iou_calibration(out["prop_conf"].detach().view(-1, K), iou_pred.reshape(-1), cfg)) if d.iou_aware else 0.0
+        if not focal and not anet:
+            _, conf_t, _, prop_conf_t, iou_pred = O.match_priors(out["loc"].detach(), pri, targets, cfg)
+            pos, ppos = (conf_t > 0).view(-1), (prop_conf_t > 0).view(-1)
+            lv[7], lv[8] = float(pos.sum()), float(ppos.sum())
+            lv[9] = float(O.actionness_loss(out["act"].detach().view(-1, 1), pos.float(), cfg)[1])
+            lv[10] = float(O.actionness_loss(out["prop_act"].detach().view(-1, 1), ppos.float(), cfg)[1])
+            lv[11] = float(O.iou_calibration(out["prop_conf"].detach().view(-1, K), iou_pred.reshape(-1), cfg)) if d.iou_aware else 0.0
         if not hasattr(self, "_msl"):
             self._msl = {}
         key = d.workspace.value if isinstance(d.workspace, ctypes.c_void_p) else int(d.workspace)

@@ -179,6 +179,44 @@ def test_fused_loss_host_glue_against_the_torch_formulation(monkeypatch, epoch):
     assert torch.allclose(st[7:12], res[False][3], rtol=1e-5, atol=1e-6)                  # #pos, #refined pos, AN, PAN, loss_iouc
 
 
+@pytest.mark.parametrize("flavour", ["anet", "focal"])
+def test_fused_loss_host_glue_other_flavours(monkeypatch, flavour):
+    """The ActivityNet and closed-set flavours through `_FusedMSLFn` (descriptor incl. flavour / level bounds / focal parameters,
+    act = None for the closed set, the 7-way backward) with the entry point emulated by the oracle's restatement of that
+    flavour, against the product's masked torch formulation."""
+    from opental_b200 import engine
+    from opental_b200.multisegment_loss import MultiSegmentLoss, MultiSegmentLossANet
+    emu = abi_emu.install(monkeypatch)
+    if flavour == "anet":
+        cfg = O.anet_config()
+        out = dict(O.fake_head_outputs(2, seed=6, K=150, P=189, loc_scale=60.0), priors=torch.cat(O.level_priors(cfg), 0))
+        targets = [O.synthetic_targets(0, num_classes=150), O.synthetic_targets(1, num_classes=150)[:1]]
+        make = lambda: MultiSegmentLossANet(150, 0.5, 1.0, cls_loss_type="edl", edl_config=engine.OPENTAL_EDL_CONFIG, os_head=True)  # noqa: E731
+        call = lambda crit, d: crit([d[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors", "act", "prop_act")], targets)  # noqa: E731
+    else:
+        out = dict(O.fake_head_outputs(2, seed=7, K=21), priors=torch.cat(O.level_priors(O.OracleConfig()), 0))
+        out.pop("act"); out.pop("prop_act")
+        targets = [O.synthetic_targets(0, num_classes=20), O.synthetic_targets(1, num_classes=20)[:1]]
+        make = lambda: MultiSegmentLoss(21, 0.5, 1.0, cls_loss_type="focal")  # noqa: E731
+        call = lambda crit, d: crit(d, targets)  # noqa: E731
+    res = {}
+    for fused in (True, False):
+        crit = make()
+        crit.cls_loss.epoch = 11
+        crit.fused = fused
+        live = {k: (v.clone().requires_grad_(True) if k != "priors" else v) for k, v in out.items()}
+        n0 = emu.calls.get("otal_msl_forward", 0)
+        losses = call(crit, live)
+        assert emu.calls.get("otal_msl_forward", 0) == n0 + (1 if fused else 0)
+        w = (1.0, 10.0, 1.0, 10.0, 1.0, 0.5, 2.0)
+        sum(wi * l for wi, l in zip(w, losses) if l is not None).backward()
+        res[fused] = ([float(l) for l in losses if l is not None], {k: v.grad.clone() for k, v in live.items() if k != "priors"})
+    for a, b in zip(res[True][0], res[False][0]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (a, b)
+    for k in res[False][1]:
+        assert float((res[True][1][k] - res[False][1][k]).abs().max()) <= 1e-4 * max(1e-6, float(res[False][1][k].abs().max())), k
+
+
 def test_staged_uint8_path_with_the_ssl_frame_map(monkeypatch):
     """The self-supervised second pass re-reads the uint8 frames through the cut-paste frame map; with the STAGED raw-uint8
     Conv3d_1a path both passes go through otal_clip_ingest_u8_raw / otal_conv1a_*_u8 and the step's cost must not change."""

@@ -155,3 +155,81 @@ def test_boundary_bce_kernel_matches_torch():
         (ls + 2 * le).backward()
         assert abs(float(ls) - float(ls_r)) < 1e-5 * max(1.0, abs(float(ls_r))) and abs(float(le) - float(le_r)) < 1e-5 * max(1.0, abs(float(le_r)))
         assert torch.allclose(sd.grad.cpu(), sr.grad, atol=1e-9, rtol=1e-4) and torch.allclose(ed.grad.cpu(), er.grad, atol=1e-9, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the other two flavours of the kernel: ActivityNet (per-sample normalisation, level-gated matching, smooth-L1, stateless IBM
+# weight with its gradient through ||z||_1) and the closed-set softmax focal loss of configs/thumos14.yaml
+# ---------------------------------------------------------------------------------------------------------------------
+def anet_outputs(B, seed, loc_scale=60.0):
+    cfg = O.anet_config()
+    P, K = sum(len(p) for p in O.level_priors(cfg)), cfg.num_classes
+    g = torch.Generator().manual_seed(seed)
+    out = dict(loc=(torch.rand(B, P, 2, generator=g) * loc_scale + 1), conf=2 * torch.randn(B, P, K, generator=g),
+               prop_loc=0.8 * torch.randn(B, P, 2, generator=g), prop_conf=2 * torch.randn(B, P, K, generator=g),
+               center=torch.randn(B, P, 1, generator=g), act=torch.randn(B, P, 1, generator=g),
+               prop_act=torch.randn(B, P, 1, generator=g))
+    return out, torch.cat(O.level_priors(cfg), 0), cfg
+
+
+@pytest.mark.parametrize("B,epoch", [(1, 1), (1, 11), (2, 11), (3, 1), (8, 11), (16, 11)])
+def test_fused_anet_loss_matches_oracle(B, epoch):
+    from opental_b200.multisegment_loss import MultiSegmentLossANet
+    out, priors, cfg = anet_outputs(B, seed=100 + 10 * B + epoch)
+    targets = [O.synthetic_targets(i, num_classes=cfg.num_classes) for i in range(B)]
+    if B >= 3:
+        targets[1] = targets[1][:1]
+        targets[2] = torch.tensor([[0.30, 0.34, 5.0]])               # a short action: only the fine levels' ranges admit it
+    ref_in = {k: v.clone().requires_grad_(True) for k, v in out.items()}
+    ref_in["priors"] = priors
+    ref = O.multisegment_loss_anet(ref_in, targets, O.LossState(epoch=epoch), cfg)
+    g_ref = torch.autograd.grad(sum(w * l for w, l in zip(W, ref)), [ref_in[k] for k in KEYS], allow_unused=True)
+    dev_in = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+    crit = MultiSegmentLossANet(cfg.num_classes, 0.5, 1.0, cls_loss_type="edl", edl_config=OPENTAL_EDL_CONFIG, os_head=True).cuda()
+    crit.cls_loss.epoch = epoch
+    from opental_b200 import _lib
+    n0 = _lib.LAUNCHES.get("otal_msl_forward", 0)
+    got = crit([dev_in[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center")] + [priors.cuda(), dev_in["act"], dev_in["prop_act"]],
+               [t.cuda() for t in targets])
+    assert _lib.LAUNCHES.get("otal_msl_forward", 0) == n0 + 1, "the ActivityNet loss must take the fused kernel"
+    g_got = torch.autograd.grad(sum(w * l for w, l in zip(W, got)), [dev_in[k] for k in KEYS], allow_unused=True)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (i, float(a), float(b))
+    for k, a, b in zip(KEYS, g_got, g_ref):
+        b = torch.zeros_like(a.cpu()) if b is None else b
+        assert torch.allclose(a.cpu(), b, atol=2e-6, rtol=1e-4), (k, float((a.cpu() - b).abs().max()))
+    # and the masked torch formulation (the fallback for B x P > 4096) agrees with the kernel
+    crit.fused = False
+    dev2 = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+    got2 = crit([dev2[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center")] + [priors.cuda(), dev2["act"], dev2["prop_act"]],
+                [t.cuda() for t in targets])
+    for a, b in zip(got, got2):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b)))
+
+
+@pytest.mark.parametrize("B", [1, 2, 8])
+def test_fused_closed_set_focal_loss_matches_oracle(B):
+    cfg = O.OracleConfig(num_classes=21)
+    P = 126
+    g = torch.Generator().manual_seed(300 + B)
+    out = dict(loc=(torch.rand(B, P, 2, generator=g) * 30 + 1), conf=2 * torch.randn(B, P, 21, generator=g),
+               prop_loc=0.3 * torch.randn(B, P, 2, generator=g), prop_conf=2 * torch.randn(B, P, 21, generator=g),
+               center=torch.randn(B, P, 1, generator=g))
+    priors = torch.cat(O.level_priors(cfg), 0)
+    targets = [O.synthetic_targets(i, num_classes=20) for i in range(B)]
+    keys = KEYS[:5]
+    ref_in = {k: v.clone().requires_grad_(True) for k, v in out.items()}
+    ref_in["priors"] = priors
+    ref = O.multisegment_loss_closed(ref_in, targets, cfg)
+    g_ref = torch.autograd.grad(sum(w * l for w, l in zip(W, ref)), [ref_in[k] for k in keys])
+    dev_in = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+    dev_in["priors"] = priors.cuda()
+    crit = MultiSegmentLoss(21, 0.5, 1.0, cls_loss_type="focal").cuda()
+    assert crit._fused_ok(dev_in["loc"])
+    got = crit(dev_in, [t.cuda() for t in targets])
+    assert got[5] is None and got[6] is None
+    g_got = torch.autograd.grad(sum(w * l for w, l in zip(W, got[:5])), [dev_in[k] for k in keys])
+    for i, (a, b) in enumerate(zip(got[:5], ref)):
+        assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (i, float(a), float(b))
+    for k, a, b in zip(keys, g_got, g_ref):
+        assert torch.allclose(a.cpu(), b, atol=2e-6, rtol=1e-4), (k, float((a.cpu() - b).abs().max()))

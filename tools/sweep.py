@@ -8,7 +8,8 @@ Under torchrun every rank runs the sweep on its own GPU with the gradient all-re
 the MAX over ranks (barrier + synchronize on both sides), clips/s is the whole job's, rank 0 prints.
 
 Conv FLOPs scale linearly in T: backbone 0.638 GFLOP/frame forward; the head is sized for T/4 positions.
-Each point: CUDA-graph captured step, 2 warm-up + 5 timed replays, CUDA events."""
+Each point (bench.measure_point, the same code as the `other_configs` legs of the default bench line): CUDA-graph captured step
+on uint8 clips resident in HBM, 2 warm-up + 5 timed replays, CUDA events."""
 import argparse
 import json
 import os
@@ -20,7 +21,6 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from opental_b200 import engine  # noqa: E402
-from opental_b200.multisegment_loss import pad_targets  # noqa: E402
 
 
 def main():
@@ -59,50 +59,14 @@ def main():
             net, crit = engine.build_opental(device=dev, precision=args.precision, frame_num=T, epoch=11)
         tr = engine.Trainer(net, crit)
         tr.broadcast_parameters(0)
-        # fwd + dgrad + wgrad conv FLOPs per clip, linear in T (466.45 GF at T = 256)
-        flop_clip = 466.45e9 * T / 256.0
         for B in args.batches:
             try:
-                torch.cuda.reset_peak_memory_stats()
-                torch.manual_seed(1000 * rank + B)
-                clips = torch.rand(B, 3, T, 96, 96, device=dev) * 2 - 1
-                tg = [engine.synthetic_targets(i, rank, num_classes=150 if args.anet else 15) for i in range(B)]
-                sc = torch.stack([engine.synthetic_scores(t, frames=T) for t in tg]).to(dev)
-                tp, tv = (t.to(dev) for t in pad_targets(tg, device="cpu"))
-                tr._graph = None
-                mode = "graph"
-                try:
-                    tr.capture(clips, (tp, tv), sc)
-                except Exception:  # noqa: BLE001   (B*priors > 4096: the loss takes the torch formulation, which synchronises)
-                    tr._graph = None
-                    mode = "eager"
-                    torch.cuda.synchronize()
-                for _ in range(2):
-                    tr.step(clips, (tp, tv), sc)
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    tr.step(clips, (tp, tv), sc)
-                e1.record()
-                torch.cuda.synchronize()
-                t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
-                if world > 1:
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # the slowest rank's time
-                ms = float(t)
-                tf = B * flop_clip / (ms * 1e-3) / 1e12
-                hbm = B_.hbm_estimate(dict(mode="train", frames=T), B, ms, peaks)
-                say(f"{T:6d} {B:5d} {ms:8.2f} {world * B * 1000.0 / ms:8.1f} {tf:10.1f} {tf / peak:8.3f} {hbm['achieved']:9.0f} {hbm['frac']:6.3f} "
-                    f"{torch.cuda.max_memory_allocated() / 2**30:8.1f}  {mode}")
+                r = B_.measure_point(tr, anet=args.anet, T=T, B=B, dev=dev, world=world, rank=rank, peaks=peaks)
+                say(f"{T:6d} {B:5d} {r['ms_per_step']:8.2f} {r['clips_per_s']:8.1f} {r['tensor_tflops_per_gpu']:10.1f} {r['tensor_frac']:8.3f} "
+                    f"{r['hbm_gbs']:9.0f} {r['hbm_frac']:6.3f} {r['peak_mem_gb']:8.1f}  {r['mode']}")
             except Exception as ex:  # noqa: BLE001
                 print(f"[rank {rank}] {T:6d} {B:5d} failed: {repr(ex)[:200]}", flush=True)
             finally:
-                tr._graph = None
-                tr._graph_out = None
-                tr._static = None
-                tr._graph_cache.clear()
                 torch.cuda.empty_cache()
         del tr, net, crit
         torch.cuda.empty_cache()
