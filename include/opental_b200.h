@@ -340,6 +340,27 @@ OTAL_API int otal_groupnorm_relu_bwd(const float* gy, const float* x, const floa
                                      const float* rstd, float* gx, float* dgamma_dbeta, int B, int C, int T, int groups,
                                      int relu, int nseg, const int* seg_off, const int* seg_len, void* stream);
 
+/* Extended GroupNorm + ReLU for the explicit head schedule: same arithmetic and segments as above, more destinations.
+ * forward (reads x, gamma, beta; writes mean, rstd): y [B,C,T] fp32 (may be NULL) and / or the result as channels-last bf16
+ *   planes p_hi / p_lo [B,T,p_cstride] at channel offset p_coff (p_lo may be NULL) — the operand layout of the tensor-core conv
+ *   that consumes it, or a slice of the concat buffer of ProposalBranch.forward (AFSD/thumos14/BDNet.py:111).
+ * backward (reads gy, x, gamma, beta, mean, rstd): gy element (b,c,t) at gy[b*gy_bstride + c*T + t] (gy_bstride = 0: C*T), i.e.
+ *   a channel slice of a wider gradient tensor; gx [B,C,T] fp32 (may be NULL) and / or channels-last planes d_hi / d_lo [B,T,C];
+ *   dgamma[c], dbeta[c] and (if not NULL) dbias[c] += sum over (b,t) of gx are ACCUMULATED atomically. */
+typedef struct otal_gn_desc {
+    int B, C, T, groups;
+    float eps;
+    int relu, nseg;
+    int seg_off[8], seg_len[8];
+    const float* x; const float* gamma; const float* beta;
+    float* mean; float* rstd;
+    float* y; uint16_t* p_hi; uint16_t* p_lo; int p_cstride, p_coff;          /* forward */
+    const float* gy; long long gy_bstride;                                      /* backward */
+    float* gx; uint16_t* d_hi; uint16_t* d_lo; float* dgamma; float* dbeta; float* dbias;
+} otal_gn_desc;
+OTAL_API int otal_groupnorm_relu_fwd_ex(const otal_gn_desc* desc, void* stream);
+OTAL_API int otal_groupnorm_relu_bwd_ex(const otal_gn_desc* desc, void* stream);
+
 /* Proposal window generation for all pyramid levels at once — replaces the no_grad block AFSD/thumos14/BDNet.py:355-384.
  * loc [B,P,2] (frames) over the P = sum of level lengths priors; per-prior tables prior [P] ((c+0.5)/t), level_len [P]
  * (t of the prior's level), level_off [P] (first column of that level in the level-concatenated feature).

@@ -25,13 +25,17 @@ def main():
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--syncs", action="store_true")
     ap.add_argument("--top", type=int, default=70)
+    ap.add_argument("--u8", action="store_true", help="uint8 frames as input (the bench's path: raw-pixel Conv3d_1a)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     net, crit = engine.build_opental(device=dev, precision=args.precision, epoch=11)
     tr = engine.Trainer(net, crit)
     B = args.batch
-    clips = torch.stack([engine.normalise_clip(engine.synthetic_clip_u8(i)) for i in range(B)]).to(dev)
+    if args.u8:
+        clips = torch.stack([engine.synthetic_clip_u8(i) for i in range(B)]).to(dev)
+    else:
+        clips = torch.stack([engine.normalise_clip(engine.synthetic_clip_u8(i)) for i in range(B)]).to(dev)
     tg = [engine.synthetic_targets(i) for i in range(B)]
     sc = torch.stack([engine.synthetic_scores(t) for t in tg]).to(dev)
     tp, tv = (t.to(dev) for t in pad_targets(tg, device="cpu"))
