@@ -402,8 +402,7 @@ def run_native_infer(args, wl, net, dev, world, rank, local):
             barrier()
         ksum = prof.summary()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
     peaks = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
@@ -433,8 +432,14 @@ def run_native_infer(args, wl, net, dev, world, rank, local):
         "cpu_baseline": None if args.no_cpu_baseline else cpu_baseline(wl),
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
+
+
+def shutdown(objs=()) -> None:
+    """Leave the process group without hanging (engine.shutdown_distributed); the JSON line is out by then."""
+    from opental_b200 import engine
+    sys.stdout.flush()
+    engine.shutdown_distributed(objs)
 
 
 def load_peaks() -> dict:
@@ -765,8 +770,7 @@ def run_native(args):
         others = other_configs(args, dev, world, rank, peaks)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown([tr])
         return
 
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
@@ -826,8 +830,7 @@ def run_native(args):
         "other_configs": others,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown([tr])
 
 
 def main():

@@ -259,6 +259,10 @@ OTAL_API int otal_relu_bn_bwd_split(const float* g, const uint16_t* y_hi, const 
  * AFSD/thumos14/train.py:321-323.  g is multiplied by grad_scale first (1/world_size after a summing all-reduce). */
 OTAL_API int otal_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                             float eps, float weight_decay, float grad_scale, int step, void* stream);
+/* The same update with the step counter t >= 1 read from DEVICE memory (step_dev[0], incremented by the caller beforehand): the
+ * launch can be captured into a CUDA graph together with the gradient all-reduce (bias corrections are computed on the device). */
+OTAL_API int otal_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                                float eps, float weight_decay, float grad_scale, const int* step_dev, void* stream);
 
 /* [B,C,T] fp32 (the reference's conv1d layout) -> channels-last bf16 planes [B,Ttot,Cpad]: element (b,c,t) lands at
  * position offset + t*dilate, channel c.  With dilate > 1 or Cpad > C the caller zero-fills the planes first (this is

@@ -78,6 +78,14 @@ class MslDesc(Structure):
                                       ("level_bounds", c_float * 16)])
 
 
+class GnDesc(Structure):
+    """Mirror of `otal_gn_desc`."""
+
+    _fields_ = (_ints("B", "C", "T", "groups") + [("eps", c_float)] + _ints("relu", "nseg") + [("seg_off", c_int * 8), ("seg_len", c_int * 8)]
+                + _ptrs("x", "gamma", "beta", "mean", "rstd", "y", "p_hi", "p_lo") + _ints("p_cstride", "p_coff")
+                + _ptrs("gy") + [("gy_bstride", c_longlong)] + _ptrs("gx", "d_hi", "d_lo", "dgamma", "dbeta", "dbias"))
+
+
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/opental_b200.h.
 SIGNATURES = {
     "otal_last_error": (c_char_p, []),
@@ -106,7 +114,11 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,
                                c_float, c_float, c_int, c_void_p]),
+    "otal_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,
+                                   c_float, c_float, c_void_p, c_void_p]),
     "otal_ncl_to_nlc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_groupnorm_relu_fwd_ex": (c_int, [POINTER(GnDesc), c_void_p]),
+    "otal_groupnorm_relu_bwd_ex": (c_int, [POINTER(GnDesc), c_void_p]),
     "otal_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_merge_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "otal_msl_workspace_floats": (c_longlong, [c_int, c_int, c_int]),
@@ -128,7 +140,8 @@ SIGNATURES = {
 }
 
 STRUCT_MIRRORS = {"otal_conv_desc": ConvDesc, "otal_conv1a_desc": Conv1aDesc, "otal_wgrad_desc": WgradDesc,
-                  "otal_conv1a_wgrad_desc": Conv1aWgradDesc, "otal_pool_desc": PoolDesc, "otal_msl_desc": MslDesc}
+                  "otal_conv1a_wgrad_desc": Conv1aWgradDesc, "otal_pool_desc": PoolDesc, "otal_msl_desc": MslDesc,
+                  "otal_gn_desc": GnDesc}
 
 _lib = None
 

@@ -125,6 +125,8 @@ class I3DBackbone(nn.Module):
         self._anchor = None
         self.on_backward_start = None     # optional callback (the trainer overlaps the head's all-reduce here): fired when
                                           # the LAST pending backbone backward of the step starts (see _BackboneFn)
+        self.on_deep_done = None          # optional callback: fired when the weight gradients of Mixed_4b..Mixed_5c (the bulk of the
+                                          # parameters: grad_split_offset() onwards in the flat buffer) are complete
         self._pending_bwd = 0             # backbone forwards of this step whose backward has not started yet
         self.crop_size = 96               # uint8 input path: crop extent (config dataset.training.crop_size)
         self.crop_offsets = None          # optional int32 [N,3] device tensor (row, column, mirror) per sample
@@ -139,6 +141,11 @@ class I3DBackbone(nn.Module):
         # launch-latency-bound sliver.  Host-side only: same kernels, same memory layout (-0.18 ms per step).  OTAL_FUSE_B12A=0: off.
         self.fuse_b12a = os.environ.get("OTAL_FUSE_B12A", "1") != "0"
         self.reset_parameters()
+
+    def grad_split_offset(self) -> int:
+        """Offset (elements) inside the flat weight / gradient buffer of the first parameter of Mixed_4b: everything from there on
+        is complete when `on_deep_done` fires (the buffer is laid out in forward order)."""
+        return min(r.w_off for name, r in self.convs.items() if name.startswith("Mixed_4b"))
 
     # ------------------------------------------------------------------------------------------------ structure
     def _add_unit(self, path: str, cin: int, cout: int, k) -> _ConvRec:
@@ -442,6 +449,9 @@ class I3DBackbone(nn.Module):
                 # (Mixed_4f: its gradient planes come from the fused MaxPool3d_5a backward, which already added g4)
                 g = self._mixed_bwd(name, saved, g, d_next)
                 d_next = None
+                if name == "Mixed_4b" and self.on_deep_done is not None and self._pending_bwd == 0:
+                    self._retire_all()           # joins the side stream: every weight gradient launched so far has been ordered
+                    self.on_deep_done()
             elif kind == "pool":
                 x, _, parg = saved.pop(name)
                 prev_name, prev_kind, _ = ENDPOINTS[names.index(name) - 1]

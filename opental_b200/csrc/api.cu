@@ -77,6 +77,7 @@ int otal_abi_sizeof(const char* name) {
     if (!strcmp(name, "otal_conv1a_wgrad_desc")) return (int)sizeof(otal_conv1a_wgrad_desc);
     if (!strcmp(name, "otal_pool_desc")) return (int)sizeof(otal_pool_desc);
     if (!strcmp(name, "otal_msl_desc")) return (int)sizeof(otal_msl_desc);
+    if (!strcmp(name, "otal_gn_desc")) return (int)sizeof(otal_gn_desc);
     return 0;
 }
 }

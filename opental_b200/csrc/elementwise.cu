@@ -144,6 +144,32 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// The same update with the step counter read from device memory: the launch can then be part of a captured CUDA graph (the bias
+// corrections of a host-side counter would be frozen into the graph).  The counter is incremented by the caller before the launch.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                                float wd, float grad_scale, const int* __restrict__ step) {
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)step[0];
+        s_bc[0] = (float)(1.0 - pow((double)beta1, t));
+        s_bc[1] = (float)(1.0 - pow((double)beta2, t));
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float step_size = lr / s_bc[0];
+    const float inv_sqrt_bc2 = rsqrtf(s_bc[1]);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pi = p[i];
+        float gi = g[i] * grad_scale + wd * pi;
+        float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
 // [B,C,T] fp32 -> channels-last planes [B,Ttot,Cpad]; thread = (b, t, 8-channel group).  Reads are strided by T
 // (tiny head tensors, L2 resident), writes are 16-byte vectors.
 __global__ void ncl_to_nlc_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
@@ -378,6 +404,16 @@ int otal_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                                              weight_decay, grad_scale, bc1, bc2);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}
+
+int otal_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, float grad_scale, const int* step_dev, void* stream) {
+    if (n < 0 || !step_dev || (n > 0 && (!p || !g || !m || !v))) { set_last_error_msg("adam_dev: bad argument"); return OTAL_ERR_BAD_ARG; }
+    if (n == 0) return OTAL_OK;
+    adam_dev_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                                 weight_decay, grad_scale, step_dev);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }

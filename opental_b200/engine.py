@@ -88,6 +88,28 @@ class GradReducer:
         self._work = []
 
 
+def shutdown_distributed(trainers=(), grace_s: float = 12.0) -> None:
+    """destroy_process_group() that cannot hang the launcher: a step graph that captured NCCL collectives holds references into
+    its communicator, so the trainers' graphs are released first; if the teardown stalls anyway a watchdog ends the process
+    (exit code 0: the work is done by the time this is called)."""
+    import gc
+    import os
+    import threading
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    timer = threading.Timer(grace_s, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    for tr in trainers:
+        tr._graph = tr._graph_out = tr._static = None
+        tr._graph_cache.clear()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.destroy_process_group()
+    timer.cancel()
+
+
 def shard_indices(num_items: int, rank: int, world: int) -> range:
     """Clip indices of `rank`: contiguous, disjoint, equal-sized shards (the remainder is dropped like drop_last)."""
     per = num_items // world
@@ -169,28 +191,64 @@ class Trainer:
         self.head = FlatParams(head)
         self.groups.append((self.head.w, self.head.g))
         self.state = [dict(m=torch.zeros_like(w), v=torch.zeros_like(w)) for w, _ in self.groups]
-        self.reducer = GradReducer([g for _, g in self.groups], process_group)
+        # Exchange buckets, in the order their gradients complete during the backward: the head's two buffers (complete when the
+        # backbone backward starts), the backbone's Mixed_4b..5c (89 % of its parameters; complete after Mixed_4b's backward), and
+        # the rest of the backbone at the end.  Each all-reduce is launched as soon as its bucket is complete and overlaps the
+        # remaining backward; the launches, the wait and the Adam update are part of the captured step graph.
+        split = bb.grad_split_offset()
+        self._buckets = [g for _, g in self.groups[1:]] + [self.bb_g[split:], self.bb_g[:split]]
+        self._n_head_buckets = len(self.groups) - 1
+        self.reducer = GradReducer(self._buckets, process_group)
         self.step_count = 0
-        self._head_launched = False
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # Adam's step counter, incremented on the device
+        self._head_launched = self._deep_launched = False
+        self._graph_updates = False       # does the current graph contain the all-reduce + Adam update?
         self._graph = None
         self._graph_ssl = False
         self._graph_cache: dict = {}    # flavour (with / without the SSL pass) -> the captured graph that is not current
         self.target_slots = 8          # ground-truth slots per clip of a captured graph (more in a batch -> capture() again)
+        self.graph_update = True       # capture the gradient exchange + Adam update into the step graph (False: they follow the replay)
         self._static = None
-        self._capturing = False
+        self._capturing = self._warming_up = False
         bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
+        bb.on_deep_done = self._on_backbone_deep_done if self.world > 1 else None
 
     # ---------------------------------------------------------------------------------------------- data parallel
+    def _comm_allowed(self) -> bool:
+        # the warm-up passes of capture() are real passes whose gradients are thrown away: no exchange, no update
+        return not self._warming_up
+
     def _on_backbone_backward(self) -> None:
-        # while a graph is being captured (or warmed up for capture) the all-reduce stays outside the graph
-        if not self._capturing and not torch.cuda.is_current_stream_capturing():
+        if self._comm_allowed():
             self._launch_head_allreduce()
+
+    def _on_backbone_deep_done(self) -> None:
+        if self._comm_allowed() and not self._deep_launched:
+            self._launch_head_allreduce()
+            self.reducer.launch([self._n_head_buckets])         # Mixed_4b..5c
+            self._deep_launched = True
 
     def _launch_head_allreduce(self) -> None:
         if self._head_launched:                                # once per step, whoever asks first
             return
-        self.reducer.launch(range(1, len(self.groups)))        # head buffers: complete once the backbone backward starts
+        self.reducer.launch(range(self._n_head_buckets))       # head buffers: complete once the backbone backward starts
         self._head_launched = True
+
+    def _finish_step(self) -> None:
+        """Everything after the backward: the buckets not exchanged yet, the wait, the step counter and the Adam launches.  Part of
+        the captured graph (NCCL collectives and the device-side step counter capture like any other launch)."""
+        if self.world > 1:
+            self._launch_head_allreduce()
+            if not self._deep_launched:
+                self.reducer.launch([self._n_head_buckets])
+            self.reducer.launch([self._n_head_buckets + 1])
+            self.reducer.wait()
+            self._head_launched = self._deep_launched = False
+        self._step_dev.add_(1)
+        for gi, ((w, g), st) in enumerate(zip(self.groups, self.state)):      # group 0 = the backbone's flat buffer
+            lr = self.lr * self.backbone_lr_scale if gi == 0 else self.lr
+            ops.adam_step(w, g, st["m"], st["v"], lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
+                          grad_scale=self.reducer.grad_scale, step_dev=self._step_dev)
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
@@ -291,13 +349,16 @@ class Trainer:
         # the warm-ups are real passes over the live criterion: its stateful buffers (the IBM EMA `weight_accum`, GHM's
         # `acc_sum`) must come out of capture() as they went in — the reference never makes these two extra updates
         crit_state = [(b, b.detach().clone()) for b in self.criterion.buffers()]
+        self._step_dev.fill_(self.step_count)        # the graph increments it from here (the host mirror follows in step())
         try:
+            self._warming_up = True
             with torch.cuda.stream(stream):
                 for _ in range(2):                   # warm-up on the capture stream (lazy initialisations, allocator)
                     self.zero_grad()
                     self.forward_backward(c, (t, v), sc, *ssl_args)
                 for b, saved in crit_state:
                     b.copy_(saved)
+            self._warming_up = False
             torch.cuda.current_stream().wait_stream(stream)
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
@@ -305,8 +366,12 @@ class Trainer:
             with torch.cuda.graph(self._graph, stream=stream, capture_error_mode="thread_local"):
                 self.zero_grad()
                 self._graph_out = self.forward_backward(c, (t, v), sc, *ssl_args)
+                if self.graph_update:
+                    self._finish_step()
         finally:
-            self._capturing = False
+            self._capturing = self._warming_up = False
+            self._head_launched = self._deep_launched = False
+        self._graph_updates = bool(self.graph_update)
         self._graph_epoch_flag = self._ibm_flag()
         self._graph_ssl = ssl_clips is not None or ssl_frame_map is not None
 
@@ -374,20 +439,13 @@ class Trainer:
                     d.copy_(s, non_blocking=True)
             self._graph.replay()
             cost, losses, ls, le = self._graph_out
+            if not self._graph_updates:
+                self._finish_step()
         else:
             self.zero_grad()
             cost, losses, ls, le = self.forward_backward(clips, targets, scores, ssl_clips, ssl_targets, ssl_frame_map)
-        if self.world > 1:
-            if not self._head_launched:
-                self._launch_head_allreduce()
-            self.reducer.launch([0])
-            self.reducer.wait()
-            self._head_launched = False
+            self._finish_step()
         self.step_count += 1
-        for gi, ((w, g), st) in enumerate(zip(self.groups, self.state)):      # group 0 = the backbone's flat buffer
-            lr = self.lr * self.backbone_lr_scale if gi == 0 else self.lr
-            ops.adam_step(w, g, st["m"], st["v"], lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
-                          grad_scale=self.reducer.grad_scale, step=self.step_count)
         return cost, losses, ls, le
 
 
@@ -411,6 +469,10 @@ class Trainer:
         self.step_count = checkpoint.load_adam_state_dict(sd, list(self.net.parameters()), self.groups, self.state)
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+        self._step_dev.fill_(self.step_count)
+        # a captured step graph has the optimizer's hyper-parameters baked into its Adam launches: capture again
+        self._graph = self._static = self._graph_out = None
+        self._graph_cache.clear()
 
     def save_checkpoint(self, epoch: int, checkpoint_path: str, train_state_path: str):
         """`save_model` (train.py:106-118): model state_dict + {'optimizer', 'state'} in the reference's file layout."""

@@ -675,11 +675,18 @@ def relu_bn_bwd_split(g: torch.Tensor, y: Planes | None, scale: torch.Tensor | N
 
 
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas=(0.9, 0.999),
-              eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, step: int = 1) -> None:
-    """In-place fused Adam (L2-in-gradient weight decay) over flat fp32 buffers."""
+              eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, step: int = 1,
+              step_dev: torch.Tensor | None = None) -> None:
+    """In-place fused Adam (L2-in-gradient weight decay) over flat fp32 buffers.  step_dev: int32 [1] device tensor holding the
+    step counter t >= 1 (then `step` is ignored): the launch can be captured into a CUDA graph."""
     _require_cuda(p, g, m, v)
     for t in (p, g, m, v):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    if step_dev is not None:
+        assert step_dev.dtype == torch.int32 and step_dev.device == p.device
+        _lib.call("otal_adam_step_dev", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1],
+                  eps, weight_decay, grad_scale, step_dev.data_ptr(), _stream())
+        return
     _lib.call("otal_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1],
               eps, weight_decay, grad_scale, step, _stream())
 

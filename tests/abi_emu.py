@@ -539,6 +539,9 @@ class Emulator:
             undone[sc < thr] = False
         return seg[done], int(done.sum()), done
 
+    def otal_adam_step_dev(self, p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step_dev, stream):
+        self.otal_adam_step(p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, int(_view(step_dev, 1, np.int32)[0]), stream)
+
     def otal_adam_step(self, p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step, stream):
         pv, gv, mv, vv = (_view(t, n, np.float32) for t in (p, g, m, v))
         gr = gv * grad_scale + wd * pv

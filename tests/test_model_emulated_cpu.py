@@ -102,7 +102,7 @@ def test_trainer_step_from_uint8_frames_on_the_emulated_abi(monkeypatch):
     cost, ls, le, w3, g3, n3 = one_step(False)
     assert abs(cost - float(want)) <= 1e-3 * abs(float(want)), (cost, float(want))
     assert abs(ls - float(parts["loss_start"])) <= 1e-3 and abs(le - float(parts["loss_end"])) <= 1e-3
-    assert emu.calls["otal_adam_step"] == 3 and emu.calls["otal_boundary_bce_fwd"] == 6 and emu.calls["otal_clip_ingest_u8"] == 1
+    assert emu.calls["otal_adam_step_dev"] == 3 and emu.calls["otal_boundary_bce_fwd"] == 6 and emu.calls["otal_clip_ingest_u8"] == 1
     cost8, ls8, le8, w8, g8, n8 = one_step(True)
     assert emu.calls["otal_conv1a_fwd_u8_halo"] == 1 and emu.calls["otal_conv1a_wgrad_u8"] == 1 and emu.calls["otal_clip_ingest_u8_raw"] == 1
     assert abs(cost8 - cost) <= 1e-4 * abs(cost) and abs(n8 - n3) <= 5e-2 * n3

@@ -70,8 +70,7 @@ def main():
                 torch.cuda.empty_cache()
         del tr, net, crit
         torch.cuda.empty_cache()
-    if world > 1:
-        dist.destroy_process_group()
+    B_.shutdown()
 
 
 if __name__ == "__main__":

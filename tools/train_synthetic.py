@@ -100,7 +100,7 @@ def main(argv=None):
         print(f"checkpoints: {sorted(os.listdir(ck)) if os.path.isdir(ck) else []}")
         print("TRAIN_SYNTHETIC", "OK" if ok else "FAILED")
     if world > 1:
-        dist.destroy_process_group()
+        engine.shutdown_distributed([tr])
     return 0 if ok else 1
 
 

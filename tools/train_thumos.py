@@ -96,7 +96,7 @@ def main(argv=None) -> int:
         with open(args.log_json, "w") as fh:
             json.dump(hist, fh)
     if world > 1:
-        dist.destroy_process_group()
+        engine.shutdown_distributed([trainer])
     return 0 if all(np.isfinite(h["cost"]) for h in hist if h.get("steps")) else 1
 
 
