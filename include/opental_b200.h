@@ -359,11 +359,57 @@ typedef struct otal_gn_desc {
     const float* x; const float* gamma; const float* beta;
     float* mean; float* rstd;
     float* y; uint16_t* p_hi; uint16_t* p_lo; int p_cstride, p_coff;          /* forward */
-    const float* gy; long long gy_bstride;                                      /* backward */
+    float* yt; int yt_off, yt_T;     /* forward: optional fp32 channels-last copy [B,yt_T,C] of the columns [yt_off, yt_off+yt_T) */
+    const float* gy; long long gy_bstride;                                      /* backward (gy may be NULL if gy2a / gy2b is given) */
+    const float* gy2a; const float* gy2b; int gy2_off, gy2_T;   /* backward: optional extra gradient, channels-last [B,gy2_T,C/2] per
+                                                                 * channel half, for the columns [gy2_off, gy2_off+gy2_T) */
     float* gx; uint16_t* d_hi; uint16_t* d_lo; float* dgamma; float* dbeta; float* dbias;
 } otal_gn_desc;
 OTAL_API int otal_groupnorm_relu_fwd_ex(const otal_gn_desc* desc, void* stream);
 OTAL_API int otal_groupnorm_relu_bwd_ex(const otal_gn_desc* desc, void* stream);
+
+/* Glue of the explicit head schedule: what CoarsePyramid.forward does with F.interpolate, +, torch.cat, index_select and permute
+ * between its convolutions (AFSD/thumos14/BDNet.py:311-331, :340-353, :399-412; AFSD/anet/BDNet.py:281-311) and the transposes of
+ * those steps in the backward.
+ * otal_rows_combine: dst[b,c,j] = sum over k < npairs of src[table[j][k][0]][b,c,table[j][k][1]] (source index -1 = no term);
+ *   sources [B,C,src_T[i]] fp32, `table` a DEVICE int32 array [Td][npairs][2]; the result goes to dst [B,C,Td] fp32 and / or
+ *   channels-last bf16 planes p_hi / p_lo [B,Td,C] (either destination may be NULL). */
+typedef struct otal_rows_desc {
+    int B, C, Td, npairs, nsrc;
+    const float* src[8];
+    int src_T[8];
+    const int* table;
+    float* dst; uint16_t* p_hi; uint16_t* p_lo;
+} otal_rows_desc;
+OTAL_API int otal_rows_combine(const otal_rows_desc* desc, void* stream);
+/* otal_head_gather_fwd: up to 4 head convolutions' raw outputs raw[k] [B,cpad[k],S] (S columns in the level-separated layout,
+ *   channels padded to cpad) -> out[k] [B,P,cout[k]], prior p read from column sep_idx[p] (DEVICE int32 [P]).  mode[k] = 1 applies
+ *   ScaleExp (BDNet.py:55-61, :341-346): exp(x * *scale[level_id[p]]) (* mult[p] if mult != NULL: anet/BDNet.py:307-311).
+ * otal_head_gather_bwd: gout[k] [B,P,cout[k]] (NULL = zero) -> the raw outputs' gradient as channels-last planes d_hi / d_lo
+ *   [B,S,cpad[k]] (zero in separator columns and padded channels; prior_of_col DEVICE int32 [S], -1 = separator); mode 1 reads the
+ *   forward's out[k] and raw[k] and accumulates *dscale[level] atomically. */
+typedef struct otal_headout_desc {
+    int B, S, P, n;
+    const int* sep_idx; const int* level_id; const float* mult;
+    const float* scale[8]; float* dscale[8];
+    const float* raw[4]; int cpad[4], cout[4], mode[4];
+    float* out[4]; const float* gout[4]; uint16_t* d_hi[4]; uint16_t* d_lo[4];
+    const float* bias[4];        /* [cout[k]] or NULL: added to raw before everything else (the conv's bias, when its padded output
+                                  * channels keep it out of the conv epilogue) */
+    float* dbias[4];             /* backward: its gradient, accumulated; or NULL */
+} otal_headout_desc;
+OTAL_API int otal_head_gather_fwd(const otal_headout_desc* desc, void* stream);
+OTAL_API int otal_head_gather_bwd(const otal_headout_desc* desc, const int* prior_of_col, void* stream);
+/* [B,C,T] fp32 (sample stride x_bstride elements, 0 = C*T) -> channels-last planes [B,T,cstride] at channel offset coff (a slice of
+ * the concat buffer of ProposalBranch.forward, BDNet.py:111).  C, cstride, coff multiples of 8.  lo may be NULL. */
+OTAL_API int otal_ncl_to_nlc_split_ex(const float* x, long long x_bstride, uint16_t* hi, uint16_t* lo, int B, int C, int T,
+                                      int cstride, int coff, void* stream);
+/* otal_boundary_bce_fwd / _bwd (below) on rows that are a channel slice of wider channels-last rows: row r starts at
+ * x + r * x_rstride (x_rstride >= C elements); grad_x is dense [B,T,C]. */
+OTAL_API int otal_boundary_bce_fwd_ex(const float* x, int x_rstride, const float* target, long long target_batch_stride,
+                                      float* row_loss, float* coef, int B, int T, int C, void* stream);
+OTAL_API int otal_boundary_bce_bwd_ex(const float* x, int x_rstride, const float* coef, const float* grad_loss, float* grad_x,
+                                      int B, int T, int C, void* stream);
 
 /* Proposal window generation for all pyramid levels at once — replaces the no_grad block AFSD/thumos14/BDNet.py:355-384.
  * loc [B,P,2] (frames) over the P = sum of level lengths priors; per-prior tables prior [P] ((c+0.5)/t), level_len [P]
@@ -374,6 +420,10 @@ OTAL_API int otal_groupnorm_relu_bwd_ex(const otal_gn_desc* desc, void* stream);
  *   frame_seg  [B,P,4]: the reference's `frame_segments` (frame units), bit-identical to torch */
 OTAL_API int otal_make_segments(const float* loc, const float* prior, const int* level_len, const int* level_off,
                                 float* seg_level, float* seg_concat, float* frame_seg, int B, int P, float frame_num, void* stream);
+/* The same windows written to rows out_row[p] of [B,S,4] arrays (DEVICE int32 [P]; the other rows are left untouched): the
+ * level-separated layout of the explicit head schedule, where level_off holds the levels' first columns in that layout. */
+OTAL_API int otal_make_segments_ex(const float* loc, const float* prior, const int* level_len, const int* level_off, const int* out_row,
+                                   int S, float* seg_concat, float* frame_seg, int B, int P, float frame_num, void* stream);
 
 /* DirichletLayer.compute_uncertainty, 'exp' evidence (AFSD/thumos14/BDNet.py:544-556): unct[m] = K / sum_k(exp(clamp(
  * logit[m,k], -10, 10)) + 1).  logit [M,K] contiguous. */

@@ -83,7 +83,24 @@ class GnDesc(Structure):
 
     _fields_ = (_ints("B", "C", "T", "groups") + [("eps", c_float)] + _ints("relu", "nseg") + [("seg_off", c_int * 8), ("seg_len", c_int * 8)]
                 + _ptrs("x", "gamma", "beta", "mean", "rstd", "y", "p_hi", "p_lo") + _ints("p_cstride", "p_coff")
-                + _ptrs("gy") + [("gy_bstride", c_longlong)] + _ptrs("gx", "d_hi", "d_lo", "dgamma", "dbeta", "dbias"))
+                + _ptrs("yt") + _ints("yt_off", "yt_T")
+                + _ptrs("gy") + [("gy_bstride", c_longlong)] + _ptrs("gy2a", "gy2b") + _ints("gy2_off", "gy2_T")
+                + _ptrs("gx", "d_hi", "d_lo", "dgamma", "dbeta", "dbias"))
+
+
+class RowsDesc(Structure):
+    """Mirror of `otal_rows_desc`."""
+
+    _fields_ = (_ints("B", "C", "Td", "npairs", "nsrc") + [("src", c_void_p * 8), ("src_T", c_int * 8)]
+                + _ptrs("table", "dst", "p_hi", "p_lo"))
+
+
+class HeadoutDesc(Structure):
+    """Mirror of `otal_headout_desc`."""
+
+    _fields_ = (_ints("B", "S", "P", "n") + _ptrs("sep_idx", "level_id", "mult") + [("scale", c_void_p * 8), ("dscale", c_void_p * 8),
+                ("raw", c_void_p * 4), ("cpad", c_int * 4), ("cout", c_int * 4), ("mode", c_int * 4), ("out", c_void_p * 4),
+                ("gout", c_void_p * 4), ("d_hi", c_void_p * 4), ("d_lo", c_void_p * 4), ("bias", c_void_p * 4), ("dbias", c_void_p * 4)])
 
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/opental_b200.h.
@@ -117,6 +134,12 @@ SIGNATURES = {
     "otal_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,
                                    c_float, c_float, c_void_p, c_void_p]),
     "otal_ncl_to_nlc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_rows_combine": (c_int, [POINTER(RowsDesc), c_void_p]),
+    "otal_head_gather_fwd": (c_int, [POINTER(HeadoutDesc), c_void_p]),
+    "otal_head_gather_bwd": (c_int, [POINTER(HeadoutDesc), c_void_p, c_void_p]),
+    "otal_ncl_to_nlc_split_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_boundary_bce_fwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "otal_boundary_bce_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "otal_groupnorm_relu_fwd_ex": (c_int, [POINTER(GnDesc), c_void_p]),
     "otal_groupnorm_relu_bwd_ex": (c_int, [POINTER(GnDesc), c_void_p]),
     "otal_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
@@ -131,6 +154,8 @@ SIGNATURES = {
                                         c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
     "otal_make_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                    c_void_p]),
+    "otal_make_segments_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float,
+                                      c_void_p]),
     "otal_dirichlet_uncertainty": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "otal_boundary_bce_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "otal_boundary_bce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -141,7 +166,7 @@ SIGNATURES = {
 
 STRUCT_MIRRORS = {"otal_conv_desc": ConvDesc, "otal_conv1a_desc": Conv1aDesc, "otal_wgrad_desc": WgradDesc,
                   "otal_conv1a_wgrad_desc": Conv1aWgradDesc, "otal_pool_desc": PoolDesc, "otal_msl_desc": MslDesc,
-                  "otal_gn_desc": GnDesc}
+                  "otal_gn_desc": GnDesc, "otal_rows_desc": RowsDesc, "otal_headout_desc": HeadoutDesc}
 
 _lib = None
 

@@ -248,6 +248,11 @@ class CoarsePyramid(nn.Module):
         cat_off = [sum(self.level_t[:i]) for i in range(LAYER_NUM)]
         self.cat_segments = tuple(zip(cat_off, self.level_t))
         self._tables = {}
+        # the explicit forward / backward schedule (head_schedule.py: one autograd node for the whole head); OTAL_HEAD_SCHEDULE=0
+        # selects the per-module autograd formulation below (the SSL / triplet pass always takes it)
+        import os
+        self.native_schedule = os.environ.get("OTAL_HEAD_SCHEDULE", "1") != "0"
+        self._anchors = {}
         # every head conv on the tensor-core kernels, weights re-homed into one packed flat buffer (headconv.py);
         # native_convs=False keeps torch's library convs (debugging aid, never selected implicitly)
         self.conv_store = None
@@ -275,6 +280,12 @@ class CoarsePyramid(nn.Module):
                                         stride=stride.to(device))
         return self._tables[device]
 
+    def _sched_anchor(self, device):
+        """A differentiable dummy input that makes autograd visit the head's single node even when the features need no gradient."""
+        if device not in self._anchors:
+            self._anchors[device] = torch.zeros(1, device=device, requires_grad=True)
+        return self._anchors[device]
+
     def _segments(self, loc, tb):
         """Window generation (no_grad, BDNet.py:355-384) for all levels: one native launch."""
         _, seg_cat, frame_seg = ops.make_segments(loc, tb["centre"], tb["level_len"], tb["level_off"], self.frame_num)
@@ -291,6 +302,9 @@ class CoarsePyramid(nn.Module):
     def forward(self, feat_dict, ssl=False, get_feat=False, forced_segments=None):
         if get_feat:
             raise NotImplementedError("get_feat is an analysis-only path (SURVEY D10)")
+        if self.native_schedule and self.conv_store is not None and not ssl:
+            from . import head_schedule
+            return head_schedule.run(self, feat_dict, forced_segments)
         x1, x2 = feat_dict.get("Mixed_4f"), feat_dict["Mixed_5c"]
         if self.conv_store is not None:
             self.conv_store.prepare(x2.device)

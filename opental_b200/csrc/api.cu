@@ -78,6 +78,8 @@ int otal_abi_sizeof(const char* name) {
     if (!strcmp(name, "otal_pool_desc")) return (int)sizeof(otal_pool_desc);
     if (!strcmp(name, "otal_msl_desc")) return (int)sizeof(otal_msl_desc);
     if (!strcmp(name, "otal_gn_desc")) return (int)sizeof(otal_gn_desc);
+    if (!strcmp(name, "otal_rows_desc")) return (int)sizeof(otal_rows_desc);
+    if (!strcmp(name, "otal_headout_desc")) return (int)sizeof(otal_headout_desc);
     return 0;
 }
 }

@@ -159,6 +159,8 @@ struct GnExFwd {
     uint16_t *p_hi, *p_lo;
     int C, T, G, relu, p_cstride, p_coff;
     float eps;
+    float* yt;            // optional fp32 channels-last copy [B, yt_T, C] of the columns [yt_off, yt_off + yt_T)
+    int yt_off, yt_T;
 };
 
 __global__ void __launch_bounds__(kGnThreads)
@@ -202,8 +204,14 @@ gn_relu_fwd_ex_kernel(const GnExFwd p, const GnSegs segs) {
         gn_smem[i] = v;
         if (p.y) p.y[base + i] = v;
     }
-    if (!p.p_hi) return;
+    if (!p.p_hi && !p.yt) return;
     __syncthreads();
+    if (p.yt)
+        for (int i = threadIdx.x; i < p.yt_T * cpg; i += kGnThreads) {
+            const int t = i / cpg, cl = i - t * cpg;
+            p.yt[((size_t)b * p.yt_T + t) * C + g * cpg + cl] = gn_smem[cl * T + p.yt_off + t];
+        }
+    if (!p.p_hi) return;
     // channels-last planes: thread = (t, channel pair)
     const int half = cpg >> 1;
     for (int i = threadIdx.x; i < T * half; i += kGnThreads) {
@@ -218,6 +226,10 @@ gn_relu_fwd_ex_kernel(const GnExFwd p, const GnSegs segs) {
 
 struct GnExBwd {
     const float *gy, *x, *gamma, *beta, *mean, *rstd;
+    // optional extra gradient in channels-last form for the columns [gy2_off, gy2_off + gy2_T): one [B, gy2_T, C/2] tensor per
+    // channel half (the start / end maps that the training script reads off this feature: BDNet.py:331, :392-395)
+    const float *gy2a, *gy2b;
+    int gy2_off, gy2_T;
     long long gy_bstride;
     float* gx;
     uint16_t *d_hi, *d_lo;
@@ -234,7 +246,7 @@ gn_relu_bwd_ex_kernel(const GnExBwd p, const GnSegs segs) {
     const int cpg = C / G, n = cpg * T;
     const size_t base = ((size_t)b * C + (size_t)g * cpg) * T;
     const float* xs = p.x + base;
-    const float* gs = p.gy + (size_t)b * p.gy_bstride + (size_t)g * cpg * T;
+    const float* gs = p.gy ? p.gy + (size_t)b * p.gy_bstride + (size_t)g * cpg * T : nullptr;
     float* sxh = gn_smem;
     float* sg = gn_smem + n;
     for (int i = threadIdx.x; i < n; i += kGnThreads) { sxh[i] = 0.f; sg[i] = 0.f; }
@@ -248,7 +260,13 @@ gn_relu_bwd_ex_kernel(const GnExBwd p, const GnSegs segs) {
             const int cl = i / len, idx = cl * T + off + i % len;
             const int c = g * cpg + cl;
             const float xh = (xs[idx] - mean) * rstd;
-            float gv = gs[idx];
+            float gv = p.gy ? gs[idx] : 0.f;
+            const int t = off + i % len, t2 = t - p.gy2_off;
+            if (t2 >= 0 && t2 < p.gy2_T) {
+                const int hc = C >> 1;
+                const float* extra = c < hc ? p.gy2a : p.gy2b;
+                if (extra) gv += extra[((size_t)b * p.gy2_T + t2) * hc + (c < hc ? c : c - hc)];
+            }
             if (p.relu && xh * p.gamma[c] + p.beta[c] <= 0.f) gv = 0.f;
             sxh[idx] = xh; sg[idx] = gv;
             const float dxh = gv * p.gamma[c];
@@ -373,7 +391,7 @@ int otal_groupnorm_relu_fwd_ex(const otal_gn_desc* d, void* stream_) {
     GnSegs segs{};
     int rc = gn_setup(d->B, d->C, d->T, d->groups, d->nseg, d->seg_off, d->seg_len, segs);
     if (rc) return rc;
-    if (!d->x || !d->gamma || !d->beta || !d->mean || !d->rstd || (!d->y && !d->p_hi)) { set_last_error_msg("groupnorm_ex: null pointer"); return OTAL_ERR_BAD_ARG; }
+    if (!d->x || !d->gamma || !d->beta || !d->mean || !d->rstd || (!d->y && !d->p_hi && !d->yt)) { set_last_error_msg("groupnorm_ex: null pointer"); return OTAL_ERR_BAD_ARG; }
     const int cpg = d->C / d->groups;
     if (d->p_hi && ((cpg & 1) || (d->p_coff & 1) || (d->p_cstride & 1) || d->p_coff + d->C > d->p_cstride)) {
         set_last_error_msg("groupnorm_ex: planes need an even group width and an even channel slice inside p_cstride"); return OTAL_ERR_BAD_ARG;
@@ -381,7 +399,9 @@ int otal_groupnorm_relu_fwd_ex(const otal_gn_desc* d, void* stream_) {
     const size_t n = (size_t)cpg * d->T;
     if (n * 4 > 96 * 1024) { set_last_error_msg("groupnorm_ex: (C/groups)*T exceeds the shared-memory staging (24576 values)"); return OTAL_ERR_UNSUPPORTED; }
     if ((rc = gn_configure())) return rc;
-    GnExFwd p{d->x, d->gamma, d->beta, d->y, d->mean, d->rstd, d->p_hi, d->p_lo, d->C, d->T, d->groups, d->relu, d->p_cstride, d->p_coff, d->eps};
+    if (d->yt && (d->yt_off < 0 || d->yt_T <= 0 || d->yt_off + d->yt_T > d->T)) { set_last_error_msg("groupnorm_ex: yt column range outside [0,T)"); return OTAL_ERR_BAD_ARG; }
+    GnExFwd p{d->x, d->gamma, d->beta, d->y, d->mean, d->rstd, d->p_hi, d->p_lo, d->C, d->T, d->groups, d->relu, d->p_cstride, d->p_coff, d->eps,
+              d->yt, d->yt_off, d->yt_T};
     gn_relu_fwd_ex_kernel<<<d->B * d->groups, kGnThreads, n * 4, stream>>>(p, segs);
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
@@ -393,15 +413,19 @@ int otal_groupnorm_relu_bwd_ex(const otal_gn_desc* d, void* stream_) {
     GnSegs segs{};
     int rc = gn_setup(d->B, d->C, d->T, d->groups, d->nseg, d->seg_off, d->seg_len, segs);
     if (rc) return rc;
-    if (!d->gy || !d->x || !d->gamma || !d->beta || !d->mean || !d->rstd || !d->dgamma || !d->dbeta || (!d->gx && !d->d_hi)) {
+    if ((!d->gy && !d->gy2a && !d->gy2b) || !d->x || !d->gamma || !d->beta || !d->mean || !d->rstd || !d->dgamma || !d->dbeta || (!d->gx && !d->d_hi)) {
         set_last_error_msg("groupnorm_ex backward: null pointer"); return OTAL_ERR_BAD_ARG;
+    }
+    if ((d->gy2a || d->gy2b) && (d->gy2_off < 0 || d->gy2_T <= 0 || d->gy2_off + d->gy2_T > d->T || (d->C & 1))) {
+        set_last_error_msg("groupnorm_ex backward: gy2 column range outside [0,T)"); return OTAL_ERR_BAD_ARG;
     }
     const int cpg = d->C / d->groups;
     if (d->d_hi && (cpg & 1)) { set_last_error_msg("groupnorm_ex backward: planes need an even group width"); return OTAL_ERR_BAD_ARG; }
     const size_t n = (size_t)cpg * d->T;
     if (n * 8 > 192 * 1024) { set_last_error_msg("groupnorm_ex backward: (C/groups)*T exceeds the shared-memory staging (24576 values)"); return OTAL_ERR_UNSUPPORTED; }
     if ((rc = gn_configure())) return rc;
-    GnExBwd p{d->gy, d->x, d->gamma, d->beta, d->mean, d->rstd, d->gy_bstride > 0 ? d->gy_bstride : (long long)d->C * d->T, d->gx,
+    GnExBwd p{d->gy, d->x, d->gamma, d->beta, d->mean, d->rstd, d->gy2a, d->gy2b, d->gy2_off, (d->gy2a || d->gy2b) ? d->gy2_T : 0,
+              d->gy_bstride > 0 ? d->gy_bstride : (long long)d->C * d->T, d->gx,
               d->d_hi, d->d_lo, d->dgamma, d->dbeta, d->dbias, d->C, d->T, d->groups, d->relu};
     gn_relu_bwd_ex_kernel<<<d->B * d->groups, kGnThreads, n * 8, stream>>>(p, segs);
     OTAL_CUDA_TRY(cudaGetLastError());

@@ -14,7 +14,7 @@ import torch
 OVERLAP_WGRAD = os.environ.get("OTAL_NO_WGRAD_OVERLAP") is None      # see fork() / join() below
 
 from . import _lib
-from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, MslDesc, PoolDesc, WgradDesc
+from ._lib import Conv1aDesc, Conv1aWgradDesc, ConvDesc, GnDesc, HeadoutDesc, MslDesc, PoolDesc, RowsDesc, WgradDesc
 
 
 class KernelProfile:
@@ -796,6 +796,153 @@ def groupnorm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     return _GroupNormReLUFn.apply(x, gamma, beta, groups, eps, relu, tuple(segments) if segments else None)
 
 
+def _gn_desc(x, gamma, beta, groups, eps, relu, segments, mean, rstd) -> "GnDesc":
+    B, C, T = x.shape
+    d = GnDesc(B=B, C=C, T=T, groups=groups, eps=eps, relu=int(relu), nseg=len(segments) if segments else 0,
+               x=x.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr())
+    for i, (o, l) in enumerate(segments or ()):
+        d.seg_off[i], d.seg_len[i] = int(o), int(l)
+    return d
+
+
+def groupnorm_relu_fwd_ex(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
+                          relu: bool = True, segments=None, want_y: bool = False, planes: Planes | None = None, planes_coff: int = 0,
+                          want_planes: bool = False, with_lo: bool = True, yt_range: tuple[int, int] | None = None):
+    """Extended GroupNorm + ReLU forward on x [B,C,T] fp32 (see otal_groupnorm_relu_fwd_ex).  Returns (y | None, planes | None,
+    yt | None, (mean, rstd)).  planes: an existing channels-last buffer [B,T,1,1,Ctot] to write at channel planes_coff, or
+    want_planes=True for a fresh [B,T,1,1,C] one; yt_range = (offset, length): fp32 channels-last copy [B,length,C] of those columns."""
+    _require_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, C, T = x.shape
+    ns = len(segments) if segments else 1
+    mean = torch.empty(B * groups * ns, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    d = _gn_desc(x, gamma, beta, groups, eps, relu, segments, mean, rstd)
+    y = torch.empty_like(x) if want_y else None
+    if planes is None and want_planes:
+        hi = torch.empty((B, T, 1, 1, C), dtype=torch.bfloat16, device=x.device)
+        planes = Planes(hi, torch.empty_like(hi) if with_lo else None)
+    yt = None
+    if yt_range is not None:
+        yt = torch.empty((B, yt_range[1], C), dtype=torch.float32, device=x.device)
+        d.yt, d.yt_off, d.yt_T = yt.data_ptr(), int(yt_range[0]), int(yt_range[1])
+    d.y = _ptr(y)
+    if planes is not None:
+        assert planes.hi.shape[0] == B and planes.hi.shape[1] == T
+        d.p_hi, d.p_lo, d.p_cstride, d.p_coff = planes.hi.data_ptr(), _ptr(planes.lo), planes.hi.shape[-1], int(planes_coff)
+    _lib.call("otal_groupnorm_relu_fwd_ex", ctypes.byref(d), _stream())
+    return y, planes, yt, (mean, rstd)
+
+
+def groupnorm_relu_bwd_ex(gy: torch.Tensor | None, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats, *,
+                          dgamma: torch.Tensor, dbeta: torch.Tensor, dbias: torch.Tensor | None, groups: int = 32, relu: bool = True,
+                          segments=None, gy_coff: int = 0, with_lo: bool = True, want_gx: bool = False,
+                          gy2=None, gy2_off: int = 0) -> tuple[Planes, torch.Tensor | None]:
+    """Extended GroupNorm + ReLU backward.  gy [B,Ctot,T] fp32, of which channels [gy_coff, gy_coff + C) are this layer's output
+    gradient (or None when only gy2 carries gradient); gy2 = (a, b): channels-last [B,T2,C/2] gradients of the two channel halves for
+    the columns [gy2_off, gy2_off + T2) (either may be None).  Accumulates into dgamma / dbeta / dbias [C]; returns (gx as
+    channels-last planes [B,T,1,1,C], gx fp32 [B,C,T] | None)."""
+    B, C, T = x.shape
+    mean, rstd = stats
+    d = _gn_desc(x, gamma, beta, groups, 0.0, relu, segments, mean, rstd)
+    if gy is not None:
+        assert gy.dtype == torch.float32 and gy.is_contiguous() and gy.shape[0] == B and gy.shape[2] == T
+        d.gy = gy.data_ptr() + 4 * gy_coff * T
+        d.gy_bstride = gy.shape[1] * T
+    if gy2 is not None:
+        a, b = gy2
+        t2 = (a if a is not None else b).shape[1]
+        for t in (a, b):
+            assert t is None or (t.is_contiguous() and tuple(t.shape) == (B, t2, C // 2) and t.dtype == torch.float32)
+        d.gy2a, d.gy2b, d.gy2_off, d.gy2_T = _ptr(a), _ptr(b), int(gy2_off), int(t2)
+    hi = torch.empty((B, T, 1, 1, C), dtype=torch.bfloat16, device=x.device)
+    planes = Planes(hi, torch.empty_like(hi) if with_lo else None)
+    gx = torch.empty_like(x) if want_gx else None
+    d.gx, d.d_hi, d.d_lo = _ptr(gx), hi.data_ptr(), _ptr(planes.lo)
+    d.dgamma, d.dbeta, d.dbias = dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dbias)
+    _lib.call("otal_groupnorm_relu_bwd_ex", ctypes.byref(d), _stream())
+    return planes, gx
+
+
+def rows_combine(srcs: list[torch.Tensor], table: torch.Tensor, *, want_f32: bool = False, want_planes: bool = False,
+                 with_lo: bool = True):
+    """dst[b,c,j] = sum_k srcs[table[j,k,0]][b,c,table[j,k,1]] (table: device int32 [Td,npairs,2], source -1 = no term).
+    Returns (dst fp32 [B,C,Td] | None, channels-last planes [B,Td,1,1,C] | None)."""
+    B, C = srcs[0].shape[:2]
+    Td, npairs = table.shape[:2]
+    assert table.dtype == torch.int32 and table.is_contiguous() and len(srcs) <= 8
+    d = RowsDesc(B=B, C=C, Td=Td, npairs=npairs, nsrc=len(srcs), table=table.data_ptr())
+    for i, t in enumerate(srcs):
+        assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape[:2]) == (B, C)
+        d.src[i], d.src_T[i] = t.data_ptr(), t.shape[2]
+    dst = torch.empty((B, C, Td), dtype=torch.float32, device=table.device) if want_f32 else None
+    planes = None
+    if want_planes:
+        hi = torch.empty((B, Td, 1, 1, C), dtype=torch.bfloat16, device=table.device)
+        planes = Planes(hi, torch.empty_like(hi) if with_lo else None)
+        d.p_hi, d.p_lo = hi.data_ptr(), _ptr(planes.lo)
+    d.dst = _ptr(dst)
+    _lib.call("otal_rows_combine", ctypes.byref(d), _stream())
+    return dst, planes
+
+
+def _headout_desc(raws, couts, modes, biases, sep_idx, level_id, mult, scales, S, P) -> "HeadoutDesc":
+    B = raws[0].shape[0]
+    d = HeadoutDesc(B=B, S=S, P=P, n=len(raws), sep_idx=sep_idx.data_ptr(), level_id=_ptr(level_id), mult=_ptr(mult))
+    for i, sc in enumerate(scales or ()):
+        d.scale[i] = sc.data_ptr()
+    for k, (r, co, m, bi) in enumerate(zip(raws, couts, modes, biases)):
+        assert r.dtype == torch.float32 and r.is_contiguous() and r.shape[0] == B and r.shape[2] == S
+        d.raw[k], d.cpad[k], d.cout[k], d.mode[k], d.bias[k] = r.data_ptr(), r.shape[1], int(co), int(m), _ptr(bi)
+    return d
+
+
+def head_gather_fwd(raws, couts, modes, biases, sep_idx, level_id=None, mult=None, scales=None) -> list[torch.Tensor]:
+    """Raw head conv outputs [B,cpad,S] (+ bias) -> the reference's [B,P,cout] tensors (see otal_head_gather_fwd)."""
+    B, S, P = raws[0].shape[0], raws[0].shape[2], sep_idx.numel()
+    d = _headout_desc(raws, couts, modes, biases, sep_idx, level_id, mult, scales, S, P)
+    outs = [torch.empty((B, P, co), dtype=torch.float32, device=raws[0].device) for co in couts]
+    for k, o in enumerate(outs):
+        d.out[k] = o.data_ptr()
+    _lib.call("otal_head_gather_fwd", ctypes.byref(d), _stream())
+    return outs
+
+
+def head_gather_bwd(raws, couts, modes, biases, dbiases, gouts, outs, sep_idx, prior_of_col, level_id=None, mult=None, scales=None,
+                    dscales=None, with_lo: bool = True) -> list[Planes]:
+    """Gradients of the [B,P,cout] outputs -> zero-padded channels-last planes [B,S,1,1,cpad] of the raw conv outputs' gradient;
+    bias gradients are accumulated into dbiases[k]; ScaleExp heads (mode 1) accumulate d scale into dscales[level]."""
+    B, S, P = raws[0].shape[0], raws[0].shape[2], sep_idx.numel()
+    d = _headout_desc(raws, couts, modes, biases, sep_idx, level_id, mult, scales, S, P)
+    for i, ds in enumerate(dscales or ()):
+        d.dscale[i] = ds.data_ptr()
+    for k, db in enumerate(dbiases):
+        d.dbias[k] = _ptr(db)
+    gouts = list(gouts)
+    res = []
+    for k, (g, o, r) in enumerate(zip(gouts, outs, raws)):
+        if g is not None:
+            g = g.contiguous()
+            assert g.dtype == torch.float32 and g.numel() == B * P * couts[k]
+            gouts[k] = g                          # keep the contiguous copy alive until the launch is enqueued
+        d.gout[k], d.out[k] = _ptr(g), _ptr(o)
+        hi = torch.empty((B, S, 1, 1, r.shape[1]), dtype=torch.bfloat16, device=r.device)
+        pl = Planes(hi, torch.empty_like(hi) if with_lo else None)
+        d.d_hi[k], d.d_lo[k] = hi.data_ptr(), _ptr(pl.lo)
+        res.append(pl)
+    _lib.call("otal_head_gather_bwd", ctypes.byref(d), prior_of_col.data_ptr(), _stream())
+    return res
+
+
+def ncl_to_nlc_into(x: torch.Tensor, planes: Planes, coff: int, x_coff: int = 0, C: int | None = None) -> None:
+    """Channels [x_coff, x_coff + C) of x [B,Ctot,T] fp32 -> channels [coff, coff + C) of the channels-last planes [B,T,1,1,Cdst]."""
+    B, Ctot, T = x.shape
+    C = Ctot - x_coff if C is None else C
+    assert x.dtype == torch.float32 and x.is_contiguous() and planes.hi.shape[0] == B and planes.hi.shape[1] == T
+    _lib.call("otal_ncl_to_nlc_split_ex", x.data_ptr() + 4 * x_coff * T, Ctot * T, planes.hi.data_ptr(), _ptr(planes.lo), B, C, T,
+              planes.hi.shape[-1], int(coff), _stream())
+
+
 # ----------------------------------------------------------------------------------------------------------
 # detection-head helpers
 # ----------------------------------------------------------------------------------------------------------
@@ -879,23 +1026,34 @@ class _BoundaryBCEFn(torch.autograd.Function):
     def forward(ctx, x, target):
         """x [B,T,C] fp32; target [B,T] fp32 view with unit stride along T (a row of the [B,2,T] score maps)."""
         _require_cuda(x, target)
-        x = x.contiguous()
         B, T, C = x.shape
+        # a channel slice of wider channels-last rows (the explicit head schedule hands out such views) is read in place
+        sliced = (not x.is_contiguous()) and x.stride(2) == 1 and x.stride(0) == T * x.stride(1) and x.stride(1) >= C
+        if not sliced:
+            x = x.contiguous()
         assert target.shape == (B, T) and target.stride(1) == 1 and target.dtype == torch.float32 and x.dtype == torch.float32
         row_loss = torch.empty(B * T, dtype=torch.float32, device=x.device)
         coef = torch.empty(B * T, dtype=torch.float32, device=x.device)
-        _lib.call("otal_boundary_bce_fwd", x.data_ptr(), target.data_ptr(), target.stride(0), row_loss.data_ptr(), coef.data_ptr(),
-                  B, T, C, _stream())
+        if sliced:
+            _lib.call("otal_boundary_bce_fwd_ex", x.data_ptr(), x.stride(1), target.data_ptr(), target.stride(0), row_loss.data_ptr(),
+                      coef.data_ptr(), B, T, C, _stream())
+        else:
+            _lib.call("otal_boundary_bce_fwd", x.data_ptr(), target.data_ptr(), target.stride(0), row_loss.data_ptr(), coef.data_ptr(),
+                      B, T, C, _stream())
         ctx.save_for_backward(x, coef)
+        ctx.sliced = sliced
         return row_loss.mean()
 
     @staticmethod
     def backward(ctx, g):
         x, coef = ctx.saved_tensors
         B, T, C = x.shape
-        gx = torch.empty_like(x)
+        gx = torch.empty((B, T, C), dtype=torch.float32, device=x.device)
         g = g.contiguous().float().reshape(1)
-        _lib.call("otal_boundary_bce_bwd", x.data_ptr(), coef.data_ptr(), g.data_ptr(), gx.data_ptr(), B, T, C, _stream())
+        if ctx.sliced:
+            _lib.call("otal_boundary_bce_bwd_ex", x.data_ptr(), x.stride(1), coef.data_ptr(), g.data_ptr(), gx.data_ptr(), B, T, C, _stream())
+        else:
+            _lib.call("otal_boundary_bce_bwd", x.data_ptr(), coef.data_ptr(), g.data_ptr(), gx.data_ptr(), B, T, C, _stream())
         return gx, None
 
 

@@ -372,6 +372,136 @@ class Emulator:
                 out[b, 0] += g2
                 out[b, 1] += g3
 
+    # ---------------------------------------------------------------------------------------------- explicit head schedule
+    def otal_groupnorm_relu_fwd_ex(self, desc, stream):
+        d = desc._obj
+        B, C, T, G = d.B, d.C, d.T, d.groups
+        xv = _view(d.x, B * C * T, np.float32).view(B, C, T)
+        ga, be = _view(d.gamma, C, np.float32), _view(d.beta, C, np.float32)
+        y = torch.zeros(B, C, T)
+        for off, ln in self._segments(d.nseg, d.seg_off, d.seg_len, T):
+            out = F.group_norm(xv[:, :, off:off + ln], G, ga, be, d.eps)
+            y[:, :, off:off + ln] = out.relu() if d.relu else out
+        if d.y:
+            _view(d.y, B * C * T, np.float32).view(B, C, T).copy_(y)
+        if d.p_hi:
+            _store(y.permute(0, 2, 1).contiguous(), d.p_hi, d.p_lo, (B, T, d.p_cstride), d.p_coff)
+        if d.yt:
+            _view(d.yt, B * d.yt_T * C, np.float32).view(B, d.yt_T, C).copy_(y[:, :, d.yt_off:d.yt_off + d.yt_T].permute(0, 2, 1))
+
+    def otal_groupnorm_relu_bwd_ex(self, desc, stream):
+        d = desc._obj
+        B, C, T, G = d.B, d.C, d.T, d.groups
+        xv = _view(d.x, B * C * T, np.float32).view(B, C, T)
+        gy = torch.zeros(B, C, T)
+        if d.gy:
+            base = d.gy.value if isinstance(d.gy, ctypes.c_void_p) else int(d.gy)
+            for b in range(B):
+                gy[b] = _view(base + 4 * b * d.gy_bstride, C * T, np.float32).view(C, T)
+        for ptr, lo in ((d.gy2a, 0), (d.gy2b, C // 2)):
+            if ptr:
+                gy[:, lo:lo + C // 2, d.gy2_off:d.gy2_off + d.gy2_T] += _view(ptr, B * d.gy2_T * (C // 2), np.float32).view(B, d.gy2_T, C // 2).permute(0, 2, 1)
+        gx = torch.zeros(B, C, T)
+        dga, dbe = _view(d.dgamma, C, np.float32), _view(d.dbeta, C, np.float32)
+        for off, ln in self._segments(d.nseg, d.seg_off, d.seg_len, T):
+            with torch.enable_grad():
+                xs = xv[:, :, off:off + ln].clone().requires_grad_(True)
+                ga = _view(d.gamma, C, np.float32).clone().requires_grad_(True)
+                be = _view(d.beta, C, np.float32).clone().requires_grad_(True)
+                o = F.group_norm(xs, G, ga, be, 1e-5)
+                o = o.relu() if d.relu else o
+                g1, g2, g3 = torch.autograd.grad(o, (xs, ga, be), gy[:, :, off:off + ln])
+            gx[:, :, off:off + ln] = g1
+            dga += g2
+            dbe += g3
+        if d.dbias:
+            _view(d.dbias, C, np.float32).add_(gx.sum(dim=(0, 2)))
+        if d.gx:
+            _view(d.gx, B * C * T, np.float32).view(B, C, T).copy_(gx)
+        if d.d_hi:
+            _store(gx.permute(0, 2, 1).contiguous(), d.d_hi, d.d_lo, (B, T, C), 0)
+
+    def otal_rows_combine(self, desc, stream):
+        d = desc._obj
+        B, C, Td, NP = d.B, d.C, d.Td, d.npairs
+        tab = _view(d.table, Td * NP * 2, np.int32).view(Td, NP, 2)
+        srcs = [_view(d.src[i], B * C * d.src_T[i], np.float32).view(B, C, d.src_T[i]) for i in range(d.nsrc)]
+        out = torch.zeros(B, C, Td)
+        for j in range(Td):
+            for k in range(NP):
+                si, col = int(tab[j, k, 0]), int(tab[j, k, 1])
+                if si >= 0:
+                    out[:, :, j] += srcs[si][:, :, col]
+        if d.dst:
+            _view(d.dst, B * C * Td, np.float32).view(B, C, Td).copy_(out)
+        if d.p_hi:
+            _store(out.permute(0, 2, 1).contiguous(), d.p_hi, d.p_lo, (B, Td, C), 0)
+
+    def _headout(self, d):
+        B, S, P = d.B, d.S, d.P
+        sep = _view(d.sep_idx, P, np.int32).long()
+        lvl = _view(d.level_id, P, np.int32).long() if d.level_id else None
+        mult = _view(d.mult, P, np.float32) if d.mult else None
+        return B, S, P, sep, lvl, mult
+
+    def otal_head_gather_fwd(self, desc, stream):
+        d = desc._obj
+        B, S, P, sep, lvl, mult = self._headout(d)
+        for k in range(d.n):
+            cp, co = d.cpad[k], d.cout[k]
+            raw = _view(d.raw[k], B * cp * S, np.float32).view(B, cp, S)
+            v = raw[:, :co, sep].permute(0, 2, 1)                                             # [B,P,co]
+            if d.bias[k]:
+                v = v + _view(d.bias[k], co, np.float32)
+            if d.mode[k] == 1:
+                sc = torch.stack([_view(d.scale[int(l)], 1, np.float32)[0] for l in lvl]).view(1, P, 1)
+                v = torch.exp(v * sc)
+                if mult is not None:
+                    v = v * mult.view(1, P, 1)
+            _view(d.out[k], B * P * co, np.float32).view(B, P, co).copy_(v)
+
+    def otal_head_gather_bwd(self, desc, prior_of_col, stream):
+        d = desc._obj
+        B, S, P, sep, lvl, mult = self._headout(d)
+        for k in range(d.n):
+            cp, co = d.cpad[k], d.cout[k]
+            g = _view(d.gout[k], B * P * co, np.float32).view(B, P, co).clone() if d.gout[k] else torch.zeros(B, P, co)
+            if d.mode[k] == 1:
+                raw = _view(d.raw[k], B * cp * S, np.float32).view(B, cp, S)[:, :co, sep].permute(0, 2, 1)
+                if d.bias[k]:
+                    raw = raw + _view(d.bias[k], co, np.float32)
+                out = _view(d.out[k], B * P * co, np.float32).view(B, P, co)
+                for l in range(int(lvl.max()) + 1):
+                    m = lvl == l
+                    _view(d.dscale[l], 1, np.float32).add_((g[:, m] * out[:, m] * raw[:, m]).sum())
+                sc = torch.stack([_view(d.scale[int(l)], 1, np.float32)[0] for l in lvl]).view(1, P, 1)
+                g = g * out * sc
+            if d.dbias[k]:
+                _view(d.dbias[k], co, np.float32).add_(g.sum(dim=(0, 1)))
+            full = torch.zeros(B, S, cp)
+            full[:, sep, :co] = g
+            _store(full, d.d_hi[k], d.d_lo[k], (B, S, cp), 0)
+
+    def otal_ncl_to_nlc_split_ex(self, x, x_bstride, hi, lo, B, C, T, cstride, coff, stream):
+        base = x.value if isinstance(x, ctypes.c_void_p) else int(x)
+        v = torch.stack([_view(base + 4 * b * x_bstride, C * T, np.float32).view(C, T) for b in range(B)]).permute(0, 2, 1).contiguous()
+        _store(v, hi, lo, (B, T, cstride), coff)
+
+    def otal_boundary_bce_fwd_ex(self, x, x_rstride, target, tstride, row_loss, coef, B, T, C, stream):
+        xv = _view(x, (B * T - 1) * x_rstride + C, np.float32)
+        rows = torch.stack([xv[r * x_rstride:r * x_rstride + C] for r in range(B * T)]).view(B, T, C)
+        tg = torch.stack([_view(int(target) + 4 * b * int(tstride), T, np.float32) for b in range(B)])
+        s = torch.tanh(rows).mean(-1)
+        loss = -(tg * torch.log(s).clamp(min=-100) + (1 - tg) * torch.log(1 - s).clamp(min=-100))
+        _view(row_loss, B * T, np.float32).copy_(loss.reshape(-1))
+        _view(coef, B * T, np.float32).copy_(((s - tg) / (s * (1 - s)).clamp(min=1e-12) / (B * T * C)).reshape(-1))
+
+    def otal_boundary_bce_bwd_ex(self, x, x_rstride, coef, g, gx, B, T, C, stream):
+        xv = _view(x, (B * T - 1) * x_rstride + C, np.float32)
+        rows = torch.stack([xv[r * x_rstride:r * x_rstride + C] for r in range(B * T)])
+        th = torch.tanh(rows)
+        _view(gx, B * T * C, np.float32).view(B * T, C).copy_(_view(g, 1, np.float32) * _view(coef, B * T, np.float32).view(-1, 1) * (1 - th * th))
+
     def otal_make_segments(self, loc, prior, level_len, level_off, seg_level, seg_concat, frame_seg, B, P, frame_num, stream):
         lc = _view(loc, B * P * 2, np.float32).view(B, P, 2)
         pri = _view(prior, P, np.float32).view(1, P, 1)
@@ -392,6 +522,13 @@ class Emulator:
         inl, outl = torch.clamp(plen / 4.0, min=1.0), torch.clamp(plen / 10.0, min=1.0)
         fs = torch.cat([torch.round(dl - outl), torch.round(dl + inl), torch.round(dr - inl), torch.round(dr + outl)], -1)
         _view(frame_seg, B * P * 4, np.float32).view(B, P, 4).copy_(fs)
+
+    def otal_make_segments_ex(self, loc, prior, level_len, level_off, out_row, S, seg_concat, frame_seg, B, P, frame_num, stream):
+        sc, fs = torch.zeros(B, P, 4), torch.zeros(B, P, 4)
+        self.otal_make_segments(loc, prior, level_len, level_off, None, sc.data_ptr(), fs.data_ptr(), B, P, frame_num, stream)
+        rows = _view(out_row, P, np.int32).long()
+        _view(seg_concat, B * S * 4, np.float32).view(B, S, 4)[:, rows] = sc
+        _view(frame_seg, B * S * 4, np.float32).view(B, S, 4)[:, rows] = fs
 
     def otal_dirichlet_uncertainty(self, logit, unct, M, K, stream):
         x = _view(logit, M * K, np.float32).view(M, K)
