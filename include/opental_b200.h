@@ -411,6 +411,10 @@ OTAL_API int otal_boundary_bce_fwd_ex(const float* x, int x_rstride, const float
 OTAL_API int otal_boundary_bce_bwd_ex(const float* x, int x_rstride, const float* coef, const float* grad_loss, float* grad_x,
                                       int B, int T, int C, void* stream);
 
+/* out[s] = mean of x[offsets[s] .. offsets[s+1]) for s < nseg <= 16 (offsets: HOST array of nseg + 1 element offsets), fixed
+ * summation order: the six boundary-BCE means of a training step (AFSD/thumos14/train.py:152-161, :186-200) in one launch. */
+OTAL_API int otal_segment_mean(const float* x, const long long* offsets_host, int nseg, float* out, void* stream);
+
 /* Proposal window generation for all pyramid levels at once — replaces the no_grad block AFSD/thumos14/BDNet.py:355-384.
  * loc [B,P,2] (frames) over the P = sum of level lengths priors; per-prior tables prior [P] ((c+0.5)/t), level_len [P]
  * (t of the prior's level), level_off [P] (first column of that level in the level-concatenated feature).

@@ -134,6 +134,7 @@ SIGNATURES = {
     "otal_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float,
                                    c_float, c_float, c_void_p, c_void_p]),
     "otal_ncl_to_nlc_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_segment_mean": (c_int, [c_void_p, POINTER(c_longlong), c_int, c_void_p, c_void_p]),
     "otal_rows_combine": (c_int, [POINTER(RowsDesc), c_void_p]),
     "otal_head_gather_fwd": (c_int, [POINTER(HeadoutDesc), c_void_p]),
     "otal_head_gather_bwd": (c_int, [POINTER(HeadoutDesc), c_void_p, c_void_p]),

@@ -447,3 +447,37 @@ extern "C" int otal_boundary_bce_bwd_ex(const float* x, int x_rstride, const flo
     OTAL_CUDA_TRY(cudaGetLastError());
     return OTAL_OK;
 }
+
+
+// out[s] = mean of x[off[s] .. off[s+1]) for nseg <= 16 segments, one CTA per segment, fixed summation order (deterministic): the
+// six boundary-BCE means of one training step in one launch (calc_bce_loss, AFSD/thumos14/train.py:152-161, x 6: :186-200)
+namespace otal {
+struct SegMeanParams { int n; long long off[17]; };
+__global__ void segment_mean_kernel(const float* __restrict__ x, float* __restrict__ out, const SegMeanParams p) {
+    __shared__ float red[32];
+    const int s = blockIdx.x;
+    const long long lo = p.off[s], hi = p.off[s + 1];
+    float a = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) a += x[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) out[s] = hi > lo ? t / (float)(hi - lo) : 0.f;
+    }
+}
+}  // namespace otal
+
+extern "C" int otal_segment_mean(const float* x, const long long* offsets_host, int nseg, float* out, void* stream) {
+    if (!x || !offsets_host || !out || nseg <= 0 || nseg > 16) { otal::set_last_error_msg("segment_mean: bad argument (1..16 segments)"); return OTAL_ERR_BAD_ARG; }
+    otal::SegMeanParams p{};
+    p.n = nseg;
+    for (int i = 0; i <= nseg; ++i) p.off[i] = offsets_host[i];
+    otal::segment_mean_kernel<<<nseg, 512, 0, static_cast<cudaStream_t>(stream)>>>(x, out, p);
+    OTAL_CUDA_TRY(cudaGetLastError());
+    return OTAL_OK;
+}

@@ -282,8 +282,9 @@ class Trainer:
             losses = self.criterion(out, targets)
             if self.global_normalisers and self.world > 1:
                 losses = self._globalise(out, losses, targets)
+                self.criterion.last_vec = None           # the re-weighted tuple is the loss now
         cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw,
-                                     score_scale=8 if anet else 4)
+                                     score_scale=8 if anet else 4, loss_vec=getattr(self.criterion, "last_vec", None))
         if ssl_clips is not None or ssl_frame_map is not None:
             # second forward on the cut-paste augmented clip + triplet loss on its boundary features
             # (thumos14/train.py:237-242; BDNet.py:482-503); one backward for the sum.  With `ssl_frame_map` the augmented

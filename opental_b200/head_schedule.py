@@ -84,6 +84,20 @@ def _tables(cp, device) -> dict:
     return out
 
 
+def _dilated(st: dict, g: torch.Tensor, T_in: int, with_lo: bool) -> Planes:
+    """The zero-upsampled output gradient of a stride-2 conv as channels-last planes [B,T_in,1,1,C] (its data gradient is the stride-1
+    data gradient of that): written into a cached buffer whose odd rows were zeroed once and are never touched again."""
+    from . import _lib
+    B, C, To = g.shape
+    key = ("dil", B, C, T_in)
+    if key not in st["seg_buf"]:
+        hi = torch.zeros((B, T_in, 1, 1, C), dtype=torch.bfloat16, device=g.device)
+        st["seg_buf"][key] = Planes(hi, torch.zeros_like(hi) if with_lo else None)
+    pl = st["seg_buf"][key]
+    _lib.call("otal_ncl_to_nlc_split", g.data_ptr(), pl.hi.data_ptr(), ops._ptr(pl.lo), B, C, To, C, T_in, 2, 0, ops._stream())
+    return pl
+
+
 def _grad(p: torch.Tensor) -> torch.Tensor:
     """The parameter's gradient buffer (the Trainer binds it to a flat buffer and zeroes it every step; allocated here otherwise)."""
     if p.grad is None:
@@ -427,7 +441,7 @@ def backward(c: _Ctx, grads: dict):
         else:
             dpl, gxf32 = _gn_bwd(c, f"pyr{i}", gn, d_p[i], unit, want_gx=True)
             T_in = pin[i].hi.shape[1]
-            dil = ops.ncl_to_nlc_planes(gxf32, unit._native[1].cpad, ttot=T_in, dilate=2, with_lo=c.with_lo)
+            dil = _dilated(st, gxf32, T_in, c.with_lo)
             _conv_bwd(c, pin[i], dpl, unit, stride=2, gx=d_p[i - 1], accumulate=True, dp_dgrad=dil)
     if c.forked:
         ops.join()

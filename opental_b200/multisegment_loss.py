@@ -353,13 +353,14 @@ class MultiSegmentLoss(nn.Module):
         B, P = loc.shape[:2]
         K = self.num_classes
         tgt, valid = pad_targets(targets, loc.device)
+        self.last_vec = None
         if self._fused_ok(loc) and self.cls_loss_type == "focal":
             from . import ops
             cfg = dict(clip_length=float(self.clip_length), overlap_thresh=float(self.overlap_thresh), use_ibm=False, momentum=0.0,
                        iou_aware=False, act_weight=0.0, act_margin=0.0, flavour=ops.MSL_FOCAL,
                        focal_alpha=self.cls_loss.alpha0, focal_gamma=float(self.cls_loss.gamma))
             vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), None, None, priors, tgt, valid, None, cfg)
-            self.last_stats = stats
+            self.last_stats, self.last_vec = stats, vec
             return tuple(vec[:5].unbind(0)) + (None, None)
         if self._fused_ok(loc):
             c = self.cls_loss
@@ -372,6 +373,7 @@ class MultiSegmentLoss(nn.Module):
             vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P), pact.reshape(B, P),
                                            priors, tgt, valid, c.weight_accum if c.with_ibm else None, cfg)
             self.last_stats = stats        # raw counts #pos, #refined pos, AN, PAN and loss_iouc at [7:12] (device; logging, engine._globalise)
+            self.last_vec = vec            # the 7 losses as one tensor (training_cost takes it instead of re-stacking the tuple)
             return tuple(vec.unbind(0))
         loc_t, conf_t, prop_loc_t, prop_conf_t, iou = self.match(loc.detach(), priors, tgt, valid)
         pos, ppos = conf_t > 0, prop_conf_t > 0
@@ -495,6 +497,7 @@ class MultiSegmentLossANet(nn.Module):
         K = self.num_classes
         tgt, valid = pad_targets(targets, loc.device)
         clip = float(self.clip_length)
+        self.last_vec = None
         if self.fused and loc.is_cuda and loc.dtype == torch.float32 and B * P <= 4096 and B <= 64 and priors.dim() == 2:
             from . import ops
             c = self.cls_loss
@@ -503,7 +506,7 @@ class MultiSegmentLossANet(nn.Module):
                        flavour=ops.MSL_ANET, ibm_coeff=float(self.ibm_coeff), level_bounds=ANET_BOUNDS)
             vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P), pact.reshape(B, P),
                                            priors, tgt, valid, None, cfg)
-            self.last_stats = stats
+            self.last_stats, self.last_vec = stats, vec
             return tuple(vec.unbind(0))
         with torch.no_grad():       # matching, anet/multisegment_loss.py:142-190
             c = priors[:, 0].view(1, -1, 1)
@@ -570,13 +573,41 @@ def calc_bce_loss(start, end, scores):
     return bce(s.view(-1), scores[:, 0].contiguous().view(-1)), bce(e.view(-1), scores[:, 1].contiguous().view(-1))
 
 
-def training_cost(output_dict, losses, scores, *, lw=1.0, cw=10.0, ctw=1.0, actw=1.0, score_scale=4):
+_COST_W: dict = {}
+
+
+def _cost_weights(device, lw, cw, ctw, actw):
+    """[13] weights of (loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act, the six boundary terms) in the total
+    cost, and the [6] weights of loss_start / loss_end (thumos14/train.py:186-200)."""
+    key = (device, lw, cw, ctw, actw)
+    if key not in _COST_W:
+        w = torch.tensor([lw, cw, lw, cw, ctw, actw, actw, 1.0, 1.0, 0.1, 0.1, 0.1, 0.1], dtype=torch.float32)
+        sel = torch.tensor([[1.0, 0.0, 0.1, 0.0, 0.1, 0.0], [0.0, 1.0, 0.0, 0.1, 0.0, 0.1]], dtype=torch.float32)
+        _COST_W[key] = (w.to(device), sel.to(device))
+    return _COST_W[key]
+
+
+def training_cost(output_dict, losses, scores, *, lw=1.0, cw=10.0, ctw=1.0, actw=1.0, score_scale=4, loss_vec=None):
     """Total cost of one (non-SSL) training step (thumos14/train.py:186-200, 226-235; anet/train.py:168-190 with the
-    score maps down-sampled by 8 = score_scale)."""
+    score maps down-sampled by 8 = score_scale).  On the GPU the six boundary terms are one fused op and the weighted sum is a dot
+    product with a cached weight vector (loss_vec: the criterion's [7] loss vector, when it has one, instead of re-stacking the tuple)."""
     loss_l, loss_c, loss_prop_l, loss_prop_c, loss_ct, loss_act, loss_prop_act = losses
     scores = scores[:, -2:]      # the ActivityNet loader's maps are (action, start, end): rows 1, 2 are used (anet/train.py:134-143)
-    ls, le = calc_bce_loss(output_dict["start"], output_dict["end"], scores)
     sc = F.interpolate(scores, scale_factor=1.0 / score_scale)
+    start = output_dict["start"]
+    if start.is_cuda and start.dtype == torch.float32 and scores.dtype == torch.float32 and scores.stride(2) == 1:
+        from . import ops
+        maps = [output_dict[k] for k in ("start", "end", "start_loc_prop", "end_loc_prop", "start_conf_prop", "end_conf_prop")]
+        tgs = [scores[:, 0], scores[:, 1], sc[:, 0], sc[:, 1], sc[:, 0], sc[:, 1]]
+        bce = ops.boundary_bce_multi(maps, tgs)
+        if loss_vec is None:
+            zero = loss_l.new_zeros(())
+            loss_vec = torch.stack([l if l is not None else zero for l in losses])
+        w, sel = _cost_weights(start.device, float(lw), float(cw), float(ctw), float(actw))
+        cost = torch.dot(torch.cat([loss_vec, bce]), w)
+        lse = sel @ bce.detach()
+        return cost, lse[0], lse[1]
+    ls, le = calc_bce_loss(output_dict["start"], output_dict["end"], scores)
     a, b = calc_bce_loss(output_dict["start_loc_prop"], output_dict["end_loc_prop"], sc)
     c, d = calc_bce_loss(output_dict["start_conf_prop"], output_dict["end_conf_prop"], sc)
     ls = ls + 0.1 * (a + c)

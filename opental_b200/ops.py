@@ -1057,6 +1057,57 @@ class _BoundaryBCEFn(torch.autograd.Function):
         return gx, None
 
 
+class _BoundaryBCEMultiFn(torch.autograd.Function):
+    """Several boundary maps at once: losses[i] = mean_{b,t} BCE(mean_c tanh(xs[i][b,t,c]), targets[i][b,t]).  One forward launch per
+    map into shared row buffers, ONE launch for all the means; the backward reads its upstream gradients straight from the
+    gradient vector (no per-map scalar tensors)."""
+
+    @staticmethod
+    def forward(ctx, n, *args):
+        xs, targets = list(args[:n]), list(args[n:])
+        _require_cuda(*xs, *targets)
+        dev = xs[0].device
+        rows = [x.shape[0] * x.shape[1] for x in xs]
+        offs = [0]
+        for r in rows:
+            offs.append(offs[-1] + r)
+        row_loss = torch.empty(offs[-1], dtype=torch.float32, device=dev)
+        coef = torch.empty(offs[-1], dtype=torch.float32, device=dev)
+        kept = []
+        for i, (x, tg) in enumerate(zip(xs, targets)):
+            B, T, C = x.shape
+            sliced = (not x.is_contiguous()) and x.stride(2) == 1 and x.stride(0) == T * x.stride(1) and x.stride(1) >= C
+            if not sliced:
+                x = x.contiguous()
+            assert tg.shape == (B, T) and tg.stride(1) == 1 and tg.dtype == torch.float32 and x.dtype == torch.float32
+            _lib.call("otal_boundary_bce_fwd_ex", x.data_ptr(), x.stride(1), tg.data_ptr(), tg.stride(0), row_loss.data_ptr() + 4 * offs[i],
+                      coef.data_ptr() + 4 * offs[i], B, T, C, _stream())
+            kept.append(x)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        arr = (ctypes.c_longlong * (n + 1))(*offs)
+        _lib.call("otal_segment_mean", row_loss.data_ptr(), arr, n, out.data_ptr(), _stream())
+        ctx.kept, ctx.coef, ctx.offs = kept, coef, offs
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().float()
+        grads = []
+        for i, x in enumerate(ctx.kept):
+            B, T, C = x.shape
+            gx = torch.empty((B, T, C), dtype=torch.float32, device=x.device)
+            _lib.call("otal_boundary_bce_bwd_ex", x.data_ptr(), x.stride(1), ctx.coef.data_ptr() + 4 * ctx.offs[i], g.data_ptr() + 4 * i,
+                      gx.data_ptr(), B, T, C, _stream())
+            grads.append(gx)
+        ctx.kept = None
+        return (None, *grads, *([None] * len(grads)))
+
+
+def boundary_bce_multi(xs: list[torch.Tensor], targets: list[torch.Tensor]) -> torch.Tensor:
+    """[len(xs)] vector of calc_bce_loss terms (thumos14/train.py:152-161), one per (map [B,T,C], target [B,T]) pair."""
+    return _BoundaryBCEMultiFn.apply(len(xs), *xs, *targets)
+
+
 def boundary_bce(x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """mean_{b,t} BCE(mean_c tanh(x[b,t,c]), target[b,t]) — calc_bce_loss (thumos14/train.py:152-161) for one map."""
     return _BoundaryBCEFn.apply(x, target)

@@ -496,6 +496,13 @@ class Emulator:
         _view(row_loss, B * T, np.float32).copy_(loss.reshape(-1))
         _view(coef, B * T, np.float32).copy_(((s - tg) / (s * (1 - s)).clamp(min=1e-12) / (B * T * C)).reshape(-1))
 
+    def otal_segment_mean(self, x, offsets, nseg, out, stream):
+        offs = [int(offsets[i]) for i in range(nseg + 1)]
+        xv = _view(x, offs[-1], np.float32)
+        ov = _view(out, nseg, np.float32)
+        for i in range(nseg):
+            ov[i] = xv[offs[i]:offs[i + 1]].mean() if offs[i + 1] > offs[i] else 0.0
+
     def otal_boundary_bce_bwd_ex(self, x, x_rstride, coef, g, gx, B, T, C, stream):
         xv = _view(x, (B * T - 1) * x_rstride + C, np.float32)
         rows = torch.stack([xv[r * x_rstride:r * x_rstride + C] for r in range(B * T)])
