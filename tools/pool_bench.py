@@ -28,6 +28,12 @@ for shape, C, k, s in SHAPES:
     t2 = timeit(lambda: ops.maxpool_bwd(x, g, gi, kernel=k, stride=s, pad_front=pads, argmax=arg))
     t3 = timeit(lambda: ops.maxpool_bwd(x, g, gi, kernel=k, stride=s, pad_front=pads))
     byt = (x.hi.numel() + y.hi.numel()) * 4
-    print(f"{shape} C{C} k{k} s{s}: fwd {t0:.3f} ms ({byt / t0 / 1e6:.0f} GB/s)  fwd+argmax {t1:.3f}  bwd(argmax) {t2:.3f}  bwd(recompute) {t3:.3f}")
+    extra = ""
+    if s != (1, 1, 1):      # stage pools: backward fused with the ReLU / BN backward of the producing layer (gather form)
+        sc = torch.rand(C, device="cuda") + 0.5
+        t4 = timeit(lambda: ops.maxpool_bwd_relu_bn_split(x, arg, g, sc, kernel=k, stride=s, pad_front=pads))
+        fb = x.hi.numel() * (4 + 2) + y.hi.numel() * (4 + 1)         # d planes written, y_hi read; pooled gradient + arg-max read
+        extra = f"  bwd fused+relu_bn {t4:.3f} ({fb / t4 / 1e6:.0f} GB/s)"
+    print(f"{shape} C{C} k{k} s{s}: fwd {t0:.3f} ms ({byt / t0 / 1e6:.0f} GB/s)  fwd+argmax {t1:.3f}  bwd(argmax) {t2:.3f}  bwd(recompute) {t3:.3f}{extra}")
     tot[0] += t0; tot[1] += t1; tot[2] += t2
 print("sum (one of each):", [round(t, 3) for t in tot], "WB", os.environ.get("OTAL_POOL_WB"))
