@@ -192,6 +192,10 @@ OTAL_API int otal_conv1a_wgrad(const otal_conv1a_wgrad_desc* desc, void* stream)
  * reference's conv is (2/255) * dw - R with R[co, tap] = sum of D over the positions where the tap lies inside the image,
  * which the caller forms from otal_border_class_sums.  STAGED like otal_conv1a_fwd_u8. */
 OTAL_API int otal_conv1a_wgrad_u8(const otal_conv1a_wgrad_desc* desc, void* stream);
+/* The same operator with a resident input halo (csrc/conv1a_wgrad_halo.cu): one 38-row input box per dt serves the seven dh taps as
+ * shifted MN-major operand views, a CTA accumulates a pair of dt over its share of the positions in TMEM and flushes once.  Same
+ * arguments and result (summation order differs); tT / tH / tW are ignored.  Even extents >= 6, Cout = 64. */
+OTAL_API int otal_conv1a_wgrad_u8_halo(const otal_conv1a_wgrad_desc* desc, void* stream);
 
 /* sums[(ct*4+ch)*4+cw][c] += sum over the positions of border class (ct,ch,cw) of (d_hi + d_lo)[n,t,h,w,c] — d: NDHWC bf16
  * planes [N,To,Ho,Wo,d_cstride], channels [d_coff, d_coff + C), C a power of two in 8..128; sums: fp32 [64][C], zeroed by the

@@ -117,6 +117,7 @@ SIGNATURES = {
     "otal_conv1a_fwd_u8": (c_int, [POINTER(Conv1aDesc), c_void_p]),
     "otal_conv1a_fwd_u8_halo": (c_int, [POINTER(Conv1aDesc), c_void_p]),
     "otal_conv1a_wgrad_u8": (c_int, [POINTER(Conv1aWgradDesc), c_void_p]),
+    "otal_conv1a_wgrad_u8_halo": (c_int, [POINTER(Conv1aWgradDesc), c_void_p]),
     "otal_clip_ingest_u8_raw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_border_class_sums": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_conv_wgrad": (c_int, [POINTER(WgradDesc), c_void_p]),

@@ -482,6 +482,10 @@ def conv1a_fwd(x: Planes, w: Planes, W: int, *, scale: torch.Tensor | None, shif
     return out
 
 
+# the resident-halo weight-gradient kernel of the raw-uint8 Conv3d_1a (csrc/conv1a_wgrad_halo.cu); OTAL_CONV1A_WGRAD_HALO=0: the generic one
+CONV1A_WGRAD_HALO = os.environ.get("OTAL_CONV1A_WGRAD_HALO", "1") != "0"
+
+
 def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[int, int] | None = None, u8: bool = False) -> None:
     """dw [49, Cout, 32] fp32 += folded weight gradient of Conv3d_1a.  u8: x is the raw-pixel plane and dw receives the
     gradient against the pixel values (conv1a_u8_weight_grad turns it into the gradient of the reference's conv)."""
@@ -501,7 +505,8 @@ def conv1a_wgrad(x: Planes, d: Planes, dw: torch.Tensor, W: int, d_slice: tuple[
     t0 = PROFILE.begin()
     if _lib.TRACE is not None:
         _lib.LABEL = (f"conv1a wgrad N{N} {T}x{H}x{W} Cout{Cout} x{nsplit}", 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
-    _lib.call("otal_conv1a_wgrad_u8" if u8 else "otal_conv1a_wgrad", ctypes.byref(desc), _stream())
+    halo = u8 and CONV1A_WGRAD_HALO and Cout == 64 and T % 2 == 0 and H % 2 == 0 and W % 2 == 0 and min(T, H, W) >= 6
+    _lib.call(("otal_conv1a_wgrad_u8_halo" if halo else "otal_conv1a_wgrad_u8") if u8 else "otal_conv1a_wgrad", ctypes.byref(desc), _stream())
     PROFILE.end("conv_wgrad_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * 3 * 343)
 
 

@@ -184,6 +184,9 @@ class Emulator:
     def otal_conv1a_wgrad_u8(self, desc, stream):
         self._conv1a_wgrad(desc, True)
 
+    def otal_conv1a_wgrad_u8_halo(self, desc, stream):
+        self._conv1a_wgrad(desc, True)
+
     def otal_border_class_sums(self, d_hi, d_lo, sums, N, To, Ho, Wo, C, cstride, coff, stream):
         g = _load(d_hi, d_lo, (N, To, Ho, Wo, cstride), coff, C).sum(0)
         out = _view(sums, 64 * C, np.float32).view(4, 4, 4, C)

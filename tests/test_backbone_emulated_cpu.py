@@ -91,7 +91,7 @@ def test_staged_uint8_conv1a_path_through_the_schedule(monkeypatch, flip):
     (out["Mixed_4f"] * g4).sum().add((out["Mixed_5c"] * g5).sum()).backward()
     check(net, out, want, grads)
     assert emu.calls["otal_clip_ingest_u8_raw"] == 1 and emu.calls["otal_conv1a_fwd_u8_halo"] == 1
-    assert emu.calls["otal_conv1a_wgrad_u8"] == 1 and "otal_border_class_sums" not in emu.calls     # R comes from the ones slot
+    assert emu.calls["otal_conv1a_wgrad_u8_halo"] == 1 and "otal_border_class_sums" not in emu.calls     # R comes from the ones slot
     assert "otal_conv1a_fwd" not in emu.calls and "otal_clip_ingest_u8" not in emu.calls
 
 

@@ -97,7 +97,7 @@ def test_border_class_sums():
                 assert float((got[a, b, c].double() - want).abs().max()) < 1e-4 * max(1.0, float(want.abs().max())), (a, b, c)
 
 
-@pytest.mark.parametrize("shape", [(2, 12, 16, 16), (1, 8, 16, 16)])
+@pytest.mark.parametrize("shape", [(2, 12, 16, 16), (1, 8, 16, 16), (1, 6, 96, 96), (1, 8, 24, 24)])
 def test_conv1a_wgrad_u8(shape):
     from opental_b200 import ops
     N, T, H, W = shape
@@ -115,6 +115,14 @@ def test_conv1a_wgrad_u8(shape):
     assert rel(got.cpu(), gw_ref) < TOL
     got1 = ops.conv1a_u8_weight_grad(dw, None, 3)                             # R from the ones slot of the raw plane (default)
     assert rel(got1.cpu(), gw_ref) < TOL
+    # both kernels: the resident-halo one (the default) and the generic one must agree (same products, different order)
+    dw2 = torch.zeros(49, 64, 32).cuda()
+    ops.CONV1A_WGRAD_HALO = not ops.CONV1A_WGRAD_HALO
+    try:
+        ops.conv1a_wgrad(ops.clip_ingest_u8(px.cuda(), W, raw=True), d, dw2, W, u8=True)
+    finally:
+        ops.CONV1A_WGRAD_HALO = not ops.CONV1A_WGRAD_HALO
+    assert rel(dw2.cpu(), dw.cpu()) < 2e-5
 
 
 def test_model_step_matches_the_bf16x3_path():

@@ -70,7 +70,8 @@ rows = [
     ("fwd     u8              ", lambda: ops.conv1a_fwd(a8, wp, 96, scale=sc8, shift=tab8, u8=True)),
     ("fwd     u8 halo         ", lambda: ops.conv1a_fwd(a8, wp, 96, scale=sc8, shift=tab8, u8=True, w_cat=wcat)),
     ("wgrad   bf16x3          ", lambda: ops.conv1a_wgrad(a3, d, dw, 96)),
-    ("wgrad   u8              ", lambda: ops.conv1a_wgrad(a8, d, dw, 96, u8=True)),
+    ("wgrad   u8 generic      ", lambda: (setattr(ops, "CONV1A_WGRAD_HALO", False), ops.conv1a_wgrad(a8, d, dw, 96, u8=True))),
+    ("wgrad   u8 halo         ", lambda: (setattr(ops, "CONV1A_WGRAD_HALO", True), ops.conv1a_wgrad(a8, d, dw, 96, u8=True))),
     ("class sums of dY        ", lambda: ops.border_class_sums(d)),
     ("host algebra (shift tab)", lambda: ops.conv1a_u8_scale_shift(w, scale, shift)),
 ]
