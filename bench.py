@@ -814,7 +814,7 @@ def run_native(args):
                    "l2": "per-step activations and gradients (several GB) exceed the 126 MB L2; two alternating input batches",
                    "ssl_pass": bool(args.ssl), "cuda_graph": not args.no_graph, **({"cuda_graph_note": graph_note} if graph_note else {}),
                    "conv1a": "bf16x3 on the normalised clip (OTAL_U8_CONV1A=0)" if os.environ.get("OTAL_U8_CONV1A") == "0" else "raw uint8 pixels, one exact bf16 plane",
-                   "staged_switches": sorted(k for k in ("OTAL_U8_CONV1A", "OTAL_FUSE_B12A", "OTAL_CONV_KSPLIT", "OTAL_NO_NCAT",
+                   "staged_switches": sorted(k for k in ("OTAL_U8_CONV1A", "OTAL_FUSE_B12A", "OTAL_HEAD_SCHEDULE", "OTAL_CONV1A_WGRAD_HALO", "OTAL_NO_NCAT",
                                                          "OTAL_NO_WGRAD_OVERLAP") if os.environ.get(k))},
         "clocks": clocks,
         "e2e": e2e,

@@ -106,10 +106,7 @@ typedef struct otal_conv_desc {
     int Cin2, in2_cstride, in2_coff;
     const uint16_t* x2_hi; const uint16_t* x2_lo;
     const uint16_t* w2_hi; const uint16_t* w2_lo;
-    /* STAGED (0 / 1 = off): split every tile's K iterations (taps x 64-channel chunks) over `ksplit` <= 8 CTAs that add their
-     * partial sums into y_f32 with float atomics — for the small problems of the 1-D head, where a handful of CTAs stream all
-     * of K alone while most SMs idle.  fp32 destination only (zeroed by the caller unless accumulate = 1), no scale / ReLU /
-     * second K segment, nsplit = 3 with Cout tiles <= 128; the bias (shift) is added by one share. */
+    /* must be 0 or 1 (a split-K experiment of round 1, withdrawn: the field stays so that the struct layout is unchanged) */
     int ksplit;
 } otal_conv_desc;
 

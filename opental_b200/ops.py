@@ -241,21 +241,6 @@ def _out_extent(size: int, stride: int) -> int:
     return -(-size // stride)
 
 
-# STAGED (off by default, to be A/B-measured): split-K for the small fp32-output convs of the 1-D head (otal_conv_desc.ksplit)
-KSPLIT = os.environ.get("OTAL_CONV_KSPLIT") == "1"
-
-
-def _auto_ksplit(N, To, Ho, Wo, tile, Cin, Cout, taps, sms: int = 148) -> int:
-    """K shares for a small problem: as many (<= 4) as keep the grid within the SM count, each with >= 4 K iterations."""
-    m_tiles = N * -(-To // tile[0]) * -(-Ho // tile[1]) * -(-Wo // tile[2])
-    ctas = m_tiles * -(-Cout // 64)                   # the launcher narrows N blocks to 64 for such problems
-    kiters = taps * -(-Cin // 64)
-    for ks in (4, 3, 2):
-        if ctas * ks <= sms and kiters >= 4 * ks:
-            return ks
-    return 1
-
-
 def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front: tuple[int, int, int],
                stride: tuple[int, int, int] = (1, 1, 1),
                scale: torch.Tensor | None = None, shift: torch.Tensor | None = None, relu: bool = False,
@@ -263,8 +248,7 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                out_slice: tuple[int, int] | None = None, out_f32: torch.Tensor | None = None,
                want_planes: bool = True, tile: tuple[int, int, int] | None = None,
                accumulate: bool = False, dgrad: bool = False, f32_ncdhw: bool = False,
-               x2: Planes | None = None, w2: Planes | None = None, in2_slice: tuple[int, int] | None = None,
-               ksplit: int | None = None) -> Planes | None:
+               x2: Planes | None = None, w2: Planes | None = None, in2_slice: tuple[int, int] | None = None) -> Planes | None:
     """y = relu?(conv(x, w) * scale + shift).  x: NDHWC planes [N,T,H,W,Cx]; w: [taps,Cout,Cin] planes.
 
     in_slice = (offset, Cin) reads a channel slice of x; out/out_slice = write into a slice of an existing buffer.
@@ -314,13 +298,6 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
                  y_hi=_ptr(out.hi) if out is not None else None,
                  y_lo=_ptr(out.lo) if (out is not None and nsplit == 3) else None,
                  y_f32=_ptr(out_f32))
-    if ksplit is None:
-        ksplit = _auto_ksplit(N, To, Ho, Wo, (tT, tH, tW), Cin, Cout, taps) if (
-            KSPLIT and out is None and out_f32 is not None and not relu and scale is None and x2 is None and nsplit == 3) else 1
-    if ksplit > 1:
-        d.ksplit = ksplit
-        if not accumulate:
-            out_f32.zero_()              # the K shares meet in the destination with atomics
     flops2 = 0.0
     if x2 is not None:
         # second K segment (1x1 only): y = [x | x2] . [w ; w2]
@@ -337,13 +314,7 @@ def conv_igemm(x: Planes, w: Planes, *, kernel: tuple[int, int, int], pad_front:
         _lib.LABEL = (f"{'dgrad' if dgrad else 'fwd'} N{N} {T}x{H}x{W} Cin{Cin} Cout{Cout} k{kt}{kh}{kw} s{stride[0]}{stride[1]}{stride[2]} "
                       f"x{nsplit} tile{tT}x{tH}x{tW}{' f32' if out_f32 is not None else ''}{' acc' if accumulate else ''}",
                       2.0 * N * To * Ho * Wo * Cout * Cin * taps + flops2)
-    try:
-        _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
-    except RuntimeError as e:
-        if d.ksplit <= 1 or "ksplit" not in str(e):
-            raise
-        d.ksplit = 0                      # the launcher's tile choice does not allow the split: plain launch (dst is zeroed or accumulates)
-        _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
+    _lib.call("otal_conv_igemm_fwd", ctypes.byref(d), _stream())
     PROFILE.end("conv_igemm_kernel", t0, 2.0 * N * To * Ho * Wo * Cout * Cin * taps + flops2)
     return out
 

@@ -205,9 +205,7 @@ class Emulator:
         k = (d.kt, d.kh, d.kw)
         taps = k[0] * k[1] * k[2]
         st = tuple(s or 1 for s in (d.sT, d.sH, d.sW))
-        if d.ksplit > 1:                                # the library's own argument rules for the split form
-            assert d.y_f32 and not d.y_hi and not d.relu and not d.scale and d.Cin2 == 0 and d.nsplit == 3 and d.ksplit <= 8
-            assert taps * -(-Cin // 64) >= 2 * d.ksplit
+        assert d.ksplit <= 1, "split-K was withdrawn (the library rejects it)"
         x = _load(d.x_hi, d.x_lo if d.nsplit == 3 else None, (N, T, H, W, d.in_cstride), d.in_coff, Cin)
         lo = d.w_lo if d.nsplit == 3 else None
         if d.dgrad:
@@ -240,7 +238,7 @@ class Emulator:
                 dst = _view(d.y_f32, N * To * Ho * Wo * d.out_cstride, np.float32).view(N, To, Ho, Wo, d.out_cstride)
                 sl = dst[..., d.out_coff:d.out_coff + Cout]
                 yv = y
-            if d.accumulate or d.ksplit > 1:          # split-K: the shares ADD into a destination the caller zeroed
+            if d.accumulate:
                 sl += yv
             else:
                 sl.copy_(yv)
