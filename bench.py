@@ -786,7 +786,7 @@ def run_native(args):
                    "note": f"achieved = algorithmic fp32-semantic conv FLOPs / event-timed kernel time; {args.precision} executes {hw:.0f}x "
                            f"those FLOPs on the bf16 pipe; peak = {peak_src}"}
     try:      # DRAM traffic of the dominant kernel's largest launch, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
             ncu_traffic = json.load(fh)
     except Exception:  # noqa: BLE001
         ncu_traffic = {}

@@ -68,8 +68,12 @@ conv1a_wgrad_halo_kernel(const __grid_constant__ WhMaps maps, const WhParams p) 
     }
     const int ndt = group == 3 ? 1 : 2;
     const int dt0 = 2 * group;
-    const int u_begin = (int)((long long)p.total_units * share / nshare);
-    const int u_end = (int)((long long)p.total_units * (share + 1) / nshare);
+    // units are dealt round-robin: at any time the CTAs of ALL groups work inside one moving window of the clip (a pair CTA
+    // takes twice as long per unit but owns half as many), so a D tile / input frame fetched from HBM by one group is an L2 hit
+    // for the others (contiguous shares re-read D from HBM for the odd group: 1.51 GB of DRAM reads against 0.77 GB of operands)
+    const int u_begin = share, u_step = nshare;
+    const int u_end = p.total_units;
+    const int n_units = share < p.total_units ? (p.total_units - share + nshare - 1) / nshare : 0;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&maps.X); tma_prefetch_desc(&maps.D_hi); tma_prefetch_desc(&maps.D_lo); }
     if (warp == 1 && lane == 0) {
@@ -95,7 +99,7 @@ conv1a_wgrad_halo_kernel(const __grid_constant__ WhMaps maps, const WhParams p) 
         // ------------------------------------------------------------------ TMA producer
         int stage = 0; uint32_t phase = 0;
         const uint32_t tx = (uint32_t)ndt * kWhXBytes + 2u * kWhDBytes;
-        for (int unit = u_begin; unit < u_end; ++unit) {
+        for (int unit = u_begin; unit < u_end; unit += u_step) {
             int n, to, h0, w0;
             decode(unit, n, to, h0, w0);
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -120,7 +124,7 @@ conv1a_wgrad_halo_kernel(const __grid_constant__ WhMaps maps, const WhParams p) 
         const uint64_t tmpl_d = umma_smem_desc_sw128(0, kWhDBytes, 1024);
         int stage = 0; uint32_t phase = 0;
         int in_chain = 0; uint32_t flush_phase = 0;
-        for (int unit = u_begin; unit < u_end; ++unit) {
+        for (int unit = u_begin; unit < u_end; unit += u_step) {
             if (in_chain == 0 && unit != u_begin) {            // the epilogue must have read the previous chain out of TMEM
                 mbar_wait(tmem_empty, flush_phase ^ 1);
                 tc_fence_after();
@@ -147,7 +151,7 @@ conv1a_wgrad_halo_kernel(const __grid_constant__ WhMaps maps, const WhParams p) 
             }
             __syncwarp();
             if (++stage == kWhStages) { stage = 0; phase ^= 1; }
-            if (++in_chain == kWhFlush || unit + 1 == u_end) {
+            if (++in_chain == kWhFlush || unit + u_step >= u_end) {
                 if (elect_one()) umma_commit(tmem_full);
                 __syncwarp();
                 in_chain = 0; flush_phase ^= 1;
@@ -156,7 +160,7 @@ conv1a_wgrad_halo_kernel(const __grid_constant__ WhMaps maps, const WhParams p) 
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue: one flush per accumulation chain
         const int q = warp & 3;                         // tap inside the M block: lanes = its 32 window elements
-        const int nflush = (u_end - u_begin + kWhFlush - 1) / kWhFlush;
+        const int nflush = (n_units + kWhFlush - 1) / kWhFlush;
         uint32_t fphase = 0;
         for (int f = 0; f < nflush; ++f) {
             mbar_wait(tmem_full, fphase);
