@@ -253,6 +253,7 @@ class CoarsePyramid(nn.Module):
         import os
         self.native_schedule = os.environ.get("OTAL_HEAD_SCHEDULE", "1") != "0"
         self._anchors = {}
+        self.two_streams = os.environ.get("OTAL_HEAD_ONE_STREAM") is None      # loc / conf halves of the schedule side by side
         # every head conv on the tensor-core kernels, weights re-homed into one packed flat buffer (headconv.py);
         # native_convs=False keeps torch's library convs (debugging aid, never selected implicitly)
         self.conv_store = None

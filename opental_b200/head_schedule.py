@@ -116,6 +116,8 @@ class _Ctx:
         self.store = cp.conv_store
         self.with_lo = self.store.with_lo
         self.sv: dict = {}
+        self.keep: list = []        # tensors a side stream reads: referenced until the stream has been joined
+        self.forked = False
 
 
 def _conv(c: _Ctx, xp: Planes, unit, stride: int = 1, conv3d: bool = False) -> torch.Tensor:
@@ -134,7 +136,8 @@ def _conv(c: _Ctx, xp: Planes, unit, stride: int = 1, conv3d: bool = False) -> t
 
 
 def _conv_bwd(c: _Ctx, xp: Planes, dp: Planes, unit, *, stride: int = 1, gx: torch.Tensor | None = None, accumulate: bool = False,
-              want_dgrad: bool = True, dp_dgrad: Planes | None = None, ndhwc_out: torch.Tensor | None = None) -> torch.Tensor | None:
+              want_dgrad: bool = True, want_wgrad: bool = True, dp_dgrad: Planes | None = None,
+              ndhwc_out: torch.Tensor | None = None) -> torch.Tensor | None:
     """Weight gradient (side stream) + data gradient of one head conv.  dp: the output gradient as channels-last planes.
     gx: fp32 [B,Cin,T] destination (allocated if None); accumulate = add to it.  dp_dgrad: the zero-upsampled gradient planes of a
     strided conv.  ndhwc_out: destination of a head-side Unit3D's data gradient ([B,T,1,1,Cin])."""
@@ -142,12 +145,13 @@ def _conv_bwd(c: _Ctx, xp: Planes, dp: Planes, unit, *, stride: int = 1, gx: tor
     T = xp.hi.shape[1]
     k = rec.taps
     pf = _same_pad_front(T, k, stride)
-    if rec.weight.requires_grad:
+    if rec.weight.requires_grad and want_wgrad:
         dw = store.block(store.flat_g, rec)
         if ops.OVERLAP_WGRAD:
             with torch.cuda.stream(ops.fork()):
                 ops.conv_wgrad(xp, dp, dw, kernel=(k, 1, 1), pad_front=(pf, 0, 0), stride=(stride, 1, 1))
             c.forked = True
+            c.keep.append((xp, dp))      # the caching allocator would hand a released block to the next main-stream allocation
         else:
             ops.conv_wgrad(xp, dp, dw, kernel=(k, 1, 1), pad_front=(pf, 0, 0), stride=(stride, 1, 1))
     if not want_dgrad:
@@ -226,11 +230,24 @@ def forward(cp, x1, x2, forced_segments, need_grad: bool):
     _, x_sep = ops.rows_combine(pf32, st["sep"], want_planes=True, with_lo=c.with_lo)
     _, frame_in = ops.rows_combine(pf32[:2] if thumos else pf32[:1], st["frame"], want_planes=True, with_lo=c.with_lo)
 
+    # Two independent halves run side by side (their kernels are far smaller than the GPU): the frame-level feature on the branch
+    # stream next to the towers / coarse heads / windows, then the conf proposal branch next to the loc one.
+    par = bool(getattr(cp, "two_streams", True)) and ops.OVERLAP_WGRAD
+
     # ---- frame-level feature (BDNet.py:324-331)
     dc = cp.deconv
-    _, d1, _ = _gn(c, _conv(c, frame_in, dc[0]), dc[1], "dc1")
-    _, d2, _ = _gn(c, _conv(c, d1, dc[3]), dc[4], "dc2")
-    frame, _, frame_t = _gn(c, _conv(c, d2, dc[6]), dc[7], "dc3", want_y=True, want_planes=False, yt_range=(0, cp.frame_num))
+
+    def frame_path():
+        _, d1_, _ = _gn(c, _conv(c, frame_in, dc[0]), dc[1], "dc1")
+        _, d2_, _ = _gn(c, _conv(c, d1_, dc[3]), dc[4], "dc2")
+        fr, _, fr_t = _gn(c, _conv(c, d2_, dc[6]), dc[7], "dc3", want_y=True, want_planes=False, yt_range=(0, cp.frame_num))
+        return d1_, d2_, fr, fr_t
+
+    if par:
+        with ops.parallel_branch():
+            d1, d2, frame, frame_t = frame_path()
+    else:
+        d1, d2, frame, frame_t = frame_path()
     half = frame.shape[1] // 2
     start, end = frame_t[:, :, :half], frame_t[:, :, half:]
 
@@ -268,6 +285,8 @@ def forward(cp, x1, x2, forced_segments, need_grad: bool):
         _lib.call("otal_make_segments_ex", loc.data_ptr(), tb["centre"].data_ptr(), tb["level_len"].data_ptr(),
                   st["level_off_sep"].data_ptr(), st["sep_idx"].data_ptr(), S, seg_sep.data_ptr(), fseg_sep.data_ptr(), B, P,
                   float(cp.frame_num), ops._stream())
+    if par:
+        ops.join_branch()                                                            # the frame-level feature is complete
     pooled = ops.bmp_forward(frame, fseg_sep)                                        # [B,512,S], shared by both branches (F5)
     hi = torch.empty((B, S, 1, 1, pooled.shape[1]), dtype=torch.bfloat16, device=dev)
     pooled_p = Planes(hi, torch.empty_like(hi) if c.with_lo else None)
@@ -290,8 +309,14 @@ def forward(cp, x1, x2, forced_segments, need_grad: bool):
             sv[tag + "cbuf"], sv[tag + "lr_y"] = cbuf, lr
         return out, lr_t
 
-    loc_prop, loc_lr_t = branch(cp.loc_proposal_branch, loc_feat, "lb")
-    conf_prop, conf_lr_t = branch(cp.conf_proposal_branch, conf_feat, "cb")
+    if par:
+        with ops.parallel_branch():
+            conf_prop, conf_lr_t = branch(cp.conf_proposal_branch, conf_feat, "cb")
+        loc_prop, loc_lr_t = branch(cp.loc_proposal_branch, loc_feat, "lb")
+        ops.join_branch()
+    else:
+        loc_prop, loc_lr_t = branch(cp.loc_proposal_branch, loc_feat, "lb")
+        conf_prop, conf_lr_t = branch(cp.conf_proposal_branch, conf_feat, "cb")
     nd = loc_lr_t.shape[2] // 2
 
     # ---- refined heads (BDNet.py:399-412)
@@ -351,34 +376,10 @@ def backward(c: _Ctx, grads: dict):
         d_prop[key] = _conv_bwd(c, feat, dpl, unit, gx=d_prop.get(key), accumulate=key in d_prop)
     d_loc_prop, d_conf_prop = d_prop[id(sv["loc_prop"])], d_prop[id(sv["conf_prop"])]
 
-    # ---- proposal branches
+    # ---- proposal branches and coarse heads: the conf half on the branch stream next to the loc half
+    par = bool(getattr(cp, "two_streams", True)) and ops.OVERLAP_WGRAD
     d_feat = {}
     d_pooled = None
-
-    def branch_bwd(br, tag, feat, d_out, g_start, g_end):
-        nonlocal d_pooled
-        cbuf = sv.pop(tag + "cbuf")
-        q = cbuf.hi.shape[-1] // 4
-        dpl, _ = _gn_bwd(c, tag + "pp", br.proposal_conv[1], d_out, br.proposal_conv[0])
-        d_cbuf = _conv_bwd(c, cbuf, dpl, br.proposal_conv[0])                               # [B,4q,S]
-        # roi part -> the shared pooled frame feature
-        dpl, _ = _gn_bwd(c, tag + "roi", br.roi_conv[1], d_cbuf, br.roi_conv[0], gy_coff=0)
-        d_pooled = _conv_bwd(c, sv["pooled_p"], dpl, br.roi_conv[0], gx=d_pooled, accumulate=d_pooled is not None)
-        # boundary part -> BoundaryMaxPooling backward -> lr_conv
-        lr = sv.pop(tag + "lr_y")
-        d_lr = ops.bmp_backward(d_cbuf[:, q:3 * q].contiguous(), lr, sv["seg_sep"], compat)
-        dpl, _ = _gn_bwd(c, tag + "lr", br.lr_conv[1], d_lr, br.lr_conv[0], gy2=(g_start, g_end) if (g_start is not None or g_end is not None) else None,
-                         gy2_off=segs[0][0])
-        key = id(feat)
-        d_feat[key] = _conv_bwd(c, feat, dpl, br.lr_conv[0], gx=d_feat.get(key), accumulate=key in d_feat)
-        # centre part
-        dpl, _ = _gn_bwd(c, tag + "cp", br.cur_point_conv[1], d_cbuf, br.cur_point_conv[0], gy_coff=3 * q)
-        d_feat[key] = _conv_bwd(c, feat, dpl, br.cur_point_conv[0], gx=d_feat[key], accumulate=True)
-
-    branch_bwd(cp.loc_proposal_branch, "lb", sv["loc_feat"], d_loc_prop, g("start_loc_prop"), g("end_loc_prop"))
-    branch_bwd(cp.conf_proposal_branch, "cb", sv["conf_feat"], d_conf_prop, g("start_conf_prop"), g("end_conf_prop"))
-
-    # ---- coarse heads
     heads, raws, outs = sv["heads"], sv["raws"], sv["outs"]
     hg = [g("loc"), g("conf")] + ([g("act")] if cp.os_head else [])
     scales = [h.scale.detach() for h in cp.loc_heads]
@@ -386,37 +387,83 @@ def backward(c: _Ctx, grads: dict):
                              [_grad(h[0].conv1d.bias) for h in heads], hg, outs, st["sep_idx"], st["prior_of_col"], st["level_id"],
                              tb["stride"] if cp.variant == "anet" else None, scales, [_grad(h.scale) for h in cp.loc_heads],
                              with_lo=c.with_lo)
-    for (unit, feat, _, _), dpl in zip(heads, hd):
+
+    def branch_bwd(br, tag, feat, d_out, g_start, g_end, defer_roi):
+        """One proposal branch + the coarse heads that read the same tower feature.  Returns the roi conv's output-gradient planes
+        when its data gradient (into the buffer both branches share) is left to the caller."""
+        nonlocal d_pooled
+        cbuf = sv.pop(tag + "cbuf")
+        q = cbuf.hi.shape[-1] // 4
+        dpl, _ = _gn_bwd(c, tag + "pp", br.proposal_conv[1], d_out, br.proposal_conv[0])
+        d_cbuf = _conv_bwd(c, cbuf, dpl, br.proposal_conv[0])                               # [B,4q,S]
+        # roi part -> the shared pooled frame feature
+        dpl_roi, _ = _gn_bwd(c, tag + "roi", br.roi_conv[1], d_cbuf, br.roi_conv[0], gy_coff=0)
+        if defer_roi:
+            _conv_bwd(c, sv["pooled_p"], dpl_roi, br.roi_conv[0], want_dgrad=False)
+        else:
+            d_pooled = _conv_bwd(c, sv["pooled_p"], dpl_roi, br.roi_conv[0], gx=d_pooled, accumulate=d_pooled is not None)
+        # boundary part -> BoundaryMaxPooling backward -> lr_conv
+        lr = sv.pop(tag + "lr_y")
+        d_lr = ops.bmp_backward(d_cbuf[:, q:3 * q].contiguous(), lr, sv["seg_sep"], compat)
+        dpl, _ = _gn_bwd(c, tag + "lr", br.lr_conv[1], d_lr, br.lr_conv[0], gy2=(g_start, g_end) if (g_start is not None or g_end is not None) else None,
+                         gy2_off=segs[0][0])
         key = id(feat)
-        d_feat[key] = _conv_bwd(c, feat, dpl, unit, gx=d_feat.get(key), accumulate=key in d_feat)
+        d_feat[key] = _conv_bwd(c, feat, dpl, br.lr_conv[0])
+        # centre part
+        dpl, _ = _gn_bwd(c, tag + "cp", br.cur_point_conv[1], d_cbuf, br.cur_point_conv[0], gy_coff=3 * q)
+        d_feat[key] = _conv_bwd(c, feat, dpl, br.cur_point_conv[0], gx=d_feat[key], accumulate=True)
+        # the coarse heads on this tower feature
+        for (unit, f, _, _), dp_head in zip(heads, hd):
+            if f is feat:
+                d_feat[key] = _conv_bwd(c, feat, dp_head, unit, gx=d_feat[key], accumulate=True)
+        c.keep.append((d_cbuf, d_lr, d_out))
+        return dpl_roi
 
-    # ---- frame-level pooling (shared) -> d frame
-    frame, fseg = sv["frame"], sv["fseg_sep"]
-    if not compat:
-        d_frame = ops.bmp_backward(d_pooled, frame, fseg, False)
-    else:       # the reference backward's tscale quirk depends on the per-level call shape (K = t of the level)
-        d_frame = None
-        for off, tl in segs:
-            gi = ops.bmp_backward(d_pooled[:, :, off:off + tl].contiguous(), frame, fseg[:, off:off + tl].contiguous(), True)
-            d_frame = gi if d_frame is None else d_frame + gi
+    if par:
+        with ops.parallel_branch():
+            roi_c = branch_bwd(cp.conf_proposal_branch, "cb", sv["conf_feat"], d_conf_prop, g("start_conf_prop"), g("end_conf_prop"), True)
+        branch_bwd(cp.loc_proposal_branch, "lb", sv["loc_feat"], d_loc_prop, g("start_loc_prop"), g("end_loc_prop"), False)
+        ops.join_branch()
+        d_pooled = _conv_bwd(c, sv["pooled_p"], roi_c, cp.conf_proposal_branch.roi_conv[0], gx=d_pooled, accumulate=True, want_wgrad=False)
+    else:
+        branch_bwd(cp.loc_proposal_branch, "lb", sv["loc_feat"], d_loc_prop, g("start_loc_prop"), g("end_loc_prop"), False)
+        branch_bwd(cp.conf_proposal_branch, "cb", sv["conf_feat"], d_conf_prop, g("start_conf_prop"), g("end_conf_prop"), False)
 
-    # ---- towers
+    # ---- frame-level feature on the branch stream (pooling backward, deconv chain), towers on the main stream
+    dc = cp.deconv
+    gs, ge = g("start"), g("end")
+
+    def frame_bwd():
+        frame, fseg = sv["frame"], sv["fseg_sep"]
+        if not compat:
+            d_frame = ops.bmp_backward(d_pooled, frame, fseg, False)
+        else:       # the reference backward's tscale quirk depends on the per-level call shape (K = t of the level)
+            d_frame = None
+            for off, tl in segs:
+                gi = ops.bmp_backward(d_pooled[:, :, off:off + tl].contiguous(), frame, fseg[:, off:off + tl].contiguous(), True)
+                d_frame = gi if d_frame is None else d_frame + gi
+        dpl, _ = _gn_bwd(c, "dc3", dc[7], d_frame, dc[6], gy2=(gs, ge) if (gs is not None or ge is not None) else None, gy2_off=0)
+        d_d2 = _conv_bwd(c, sv["d2"], dpl, dc[6])
+        dpl, _ = _gn_bwd(c, "dc2", dc[4], d_d2, dc[3])
+        d_d1 = _conv_bwd(c, sv["d1"], dpl, dc[3])
+        dpl, _ = _gn_bwd(c, "dc1", dc[1], d_d1, dc[0])
+        c.keep.append((d_frame, d_d2, d_d1))
+        return _conv_bwd(c, sv["frame_in"], dpl, dc[0])
+
+    if par:
+        with ops.parallel_branch():
+            d_frame_in = frame_bwd()
     d_x_sep = None
     for tw, tag, first, feat in ((cp.loc_tower, "lt", sv["lt1"], sv["loc_feat"]), (cp.conf_tower, "ct", sv["ct1"], sv["conf_feat"])):
         dpl, _ = _gn_bwd(c, tag + "2", tw[1][1], d_feat[id(feat)], tw[1][0])
         d_first = _conv_bwd(c, first, dpl, tw[1][0])
         dpl, _ = _gn_bwd(c, tag + "1", tw[0][1], d_first, tw[0][0])
         d_x_sep = _conv_bwd(c, sv["x_sep"], dpl, tw[0][0], gx=d_x_sep, accumulate=d_x_sep is not None)
-
-    # ---- deconv (frame-level feature)
-    dc = cp.deconv
-    gs, ge = g("start"), g("end")
-    dpl, _ = _gn_bwd(c, "dc3", dc[7], d_frame, dc[6], gy2=(gs, ge) if (gs is not None or ge is not None) else None, gy2_off=0)
-    d_d2 = _conv_bwd(c, sv["d2"], dpl, dc[6])
-    dpl, _ = _gn_bwd(c, "dc2", dc[4], d_d2, dc[3])
-    d_d1 = _conv_bwd(c, sv["d1"], dpl, dc[3])
-    dpl, _ = _gn_bwd(c, "dc1", dc[1], d_d1, dc[0])
-    d_frame_in = _conv_bwd(c, sv["frame_in"], dpl, dc[0])
+        c.keep.append(d_first)
+    if par:
+        ops.join_branch()
+    else:
+        d_frame_in = frame_bwd()
 
     # ---- pyramid: transposes of the sep layout / upsampling / top-down add, then the conv chain from the top level down
     pin = sv["pin"]
@@ -445,6 +492,7 @@ def backward(c: _Ctx, grads: dict):
             _conv_bwd(c, pin[i], dpl, unit, stride=2, gx=d_p[i - 1], accumulate=True, dp_dgrad=dil)
     if c.forked:
         ops.join()
+    c.keep.clear()
     sv.clear()
 
     def as_view(gx, shape):

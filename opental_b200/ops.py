@@ -117,6 +117,35 @@ def join() -> None:
         torch.cuda.current_stream().wait_stream(side)
 
 
+_SIDE2: dict = {}
+
+
+class parallel_branch:
+    """`with ops.parallel_branch():` runs the enclosed launches on a SECOND side stream that has waited for everything enqueued on the
+    current stream so far; `ops.join_branch()` makes the current stream wait for it.  For two independent halves of a schedule (the
+    loc / conf halves of the detection head): their kernels are far smaller than the GPU.  Same memory rule as fork / join: every
+    tensor the branch touches stays referenced until the join.  Captures into a CUDA graph as a parallel branch."""
+
+    def __enter__(self):
+        dev = torch.cuda.current_device()
+        side = _SIDE2.get(dev)
+        if side is None:
+            side = _SIDE2[dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        self._ctx = torch.cuda.stream(side)
+        self._ctx.__enter__()
+        return side
+
+    def __exit__(self, *exc):
+        return self._ctx.__exit__(*exc)
+
+
+def join_branch() -> None:
+    side = _SIDE2.get(torch.cuda.current_device())
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
+
+
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
