@@ -719,6 +719,11 @@ def run_native(args):
         for ev in consumed:
             ev.record()
         h2d = sum(t.numel() * t.element_size() for t in host[0])
+        # the loss of every step is read back on the host, one step behind the GPU (what a training loop that logs its loss does):
+        # step j's cost goes to a pinned slot with an async copy, the host reads it while step j + 1 runs
+        cost_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        cost_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        seen = []
         barrier()
         t0 = time.perf_counter()
         prefetch(0)
@@ -728,15 +733,22 @@ def run_native(args):
             torch.cuda.current_stream().wait_event(ready[j % 2])
             cost, losses, ls, le = run_step(bufs[j % 2])
             consumed[j % 2].record()
-            _ = float(cost)                                   # device -> host read of the step's result (4 bytes)
+            cost_host[j % 2:j % 2 + 1].copy_(cost.reshape(1), non_blocking=True)      # device -> host read of the step's result (4 bytes)
+            cost_ready[j % 2].record()
+            if j >= 1:
+                cost_ready[(j - 1) % 2].synchronize()
+                seen.append(float(cost_host[(j - 1) % 2]))
+        cost_ready[(args.steps - 1) % 2].synchronize()
+        seen.append(float(cost_host[(args.steps - 1) % 2]))
         barrier()
+        assert len(seen) == args.steps and all(v == v for v in seen), "every step's loss must have been read"
         ms_e2e = (time.perf_counter() - t0) * 1000.0 / args.steps
         if world > 1:
             t = torch.tensor([ms_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t)
         e2e = {"value": world * B * 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e, "api": f"opental_b200.engine.Trainer.step on pinned host uint8 frames [B,{T},112,112,3] (H2D prefetched on a copy stream) + float(cost)"}
+               "ms_per_step": ms_e2e, "api": f"opental_b200.engine.Trainer.step on pinned host uint8 frames [B,{T},112,112,3] (H2D prefetched on a copy stream); every step's cost is copied to pinned host memory and read by the host one step behind the GPU"}
 
     # ---- per-kernel roofline: the same step enqueued eagerly with every tensor-core conv launch bracketed by CUDA events
     # on the launching stream (a graph replay cannot be bracketed per kernel); same process, same buffers, after the timed

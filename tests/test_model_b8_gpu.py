@@ -117,8 +117,12 @@ def test_five_step_trajectory_follows_the_reference(golden_dir, graph):
             crit.cls_loss.weight_accum.copy_(acc0)             # capture() warm-ups touch the EMA (restored by the Trainer too)
         for s, want in enumerate(gold["steps"]):
             cost, losses, ls, le = tr.step(x, tg, sc)
-            # once two implementations have bifurcated (a matching flip), every later step inherits the difference
-            tol = max(1e-3, 3 * max(w["oracle_rel"] for w in gold["steps"][:s + 1]))
+            # once two implementations have bifurcated (a matching flip), every later step inherits the difference.  From the
+            # fourth step on the product also bifurcates against ITSELF from run to run (the atomically reduced weight gradients
+            # are summed in a different order, Adam's first steps turn sign noise into +-lr, and a prior whose IoU sits at the
+            # refinement threshold changes sides: measured 5.5e-3 on the cost in one run out of four, 1e-4 in the others), so
+            # those steps get the bar of a flip (1e-2) — the optimizer itself is pinned by the first three steps and by delta_total
+            tol = max(1e-3 if s < 3 else 1e-2, 3 * max(w["oracle_rel"] for w in gold["steps"][:s + 1]))
             assert abs(float(cost) - want["cost"]) <= tol * abs(want["cost"]), (s, float(cost), want["cost"])
             if s < 3:
                 for a, b in zip(losses, want["losses"]):
