@@ -321,6 +321,16 @@ typedef struct otal_msl_desc {
     float ibm_coeff;             /* flavour 1 */
     float focal_alpha, focal_gamma;   /* flavour 2 */
     float level_bounds[16];      /* flavour 1: (left, right) per pyramid level, up to 8 levels */
+    /* flavour 0, the re-weighting branches of EvidenceLoss.edl_loss (AFSD/thumos14/cls_loss.py:221-272; one at a time, in the
+     * reference's precedence focal > GHM > IB > IBM): 0 = use_ibm decides (IBM or none), 1 IBM, 2 IB (1 / (grad_norm feat_norm)),
+     * 3 focal-EDL (edl_focal_alpha = weight of class 0, edl_focal_gamma; the modulating factor is differentiated), 4 GHM
+     * (num_bins bins, momentum; ghm_acc_sum = the fp64 acc_sum state [num_bins], updated when momentum > 0).  The caller selects
+     * a branch only from its start epoch on (ghm_start, ib_start, ibm_start). */
+    int reweight;
+    int cls_all;                 /* flavour 0: 1 = no os_head (configs/ablations/thumos14_opental_noACT.yaml): every prior is a
+                                  * classification sample with class 0 = background (K counts it); act / prop_act NULL */
+    float edl_focal_alpha, edl_focal_gamma;
+    double* ghm_acc_sum;
 } otal_msl_desc;
 OTAL_API long long otal_msl_workspace_floats(int B, int P, int K);
 OTAL_API int otal_msl_forward(const otal_msl_desc* desc, void* stream);

@@ -75,7 +75,8 @@ class MslDesc(Structure):
                 + _ptrs("loc", "conf", "prop_loc", "prop_conf", "center", "act", "prop_act", "priors", "targets", "valid",
                         "weight_accum", "losses", "workspace")
                 + _ints("flavour") + [("ibm_coeff", c_float), ("focal_alpha", c_float), ("focal_gamma", c_float),
-                                      ("level_bounds", c_float * 16)])
+                                      ("level_bounds", c_float * 16)]
+                + _ints("reweight", "cls_all") + [("edl_focal_alpha", c_float), ("edl_focal_gamma", c_float)] + _ptrs("ghm_acc_sum"))
 
 
 class GnDesc(Structure):

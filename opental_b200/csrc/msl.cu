@@ -33,6 +33,7 @@ constexpr int kMslWarps = kMslThreads / 32;
 constexpr int kMslMaxBins = 256;
 constexpr int kMslMaxGroups = 64;
 enum { kMslThumos = 0, kMslAnet = 1, kMslFocal = 2 };
+enum { kRwNone = 0, kRwIbm = 1, kRwIb = 2, kRwFocal = 3, kRwGhm = 4 };
 
 struct MslParams {
     int B, P, K, G, M;
@@ -44,6 +45,10 @@ struct MslParams {
     float act_weight, act_margin;
     int prior_stride;
     float ibm_coeff, focal_alpha, focal_gamma;
+    int reweight;                // flavour 0 only: kRwNone / kRwIbm (binned EMA) / kRwIb / kRwFocal / kRwGhm (cls_loss.py:221-272)
+    int cls_all;                 // flavour 0 only: no os_head — every prior is a classification sample, class 0 = background
+    float edl_alpha0, edl_gamma; // focal-EDL: weight of class 0 (1 - alpha0 for the others), exponent
+    double* ghm_acc;             // GHM: fp64 per-bin EMA state (EvidenceLoss.acc_sum), updated when momentum > 0
     float bounds[16];            // flavour 1: (left, right] range of max(left, right) per pyramid level
     const float *loc, *conf, *ploc, *pconf, *center, *act, *pact, *priors, *targets;
     const unsigned char* valid;
@@ -158,14 +163,18 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x
 
 // EDL 'log' loss of one sample (cls_loss.py:212-216 with func = log, evidence = exp(clamp(.,-10,10))):
 // per = log S - log alpha_y; also the IBM statistics grad_norm = |1/alpha_y - K/S|, feat_norm = sum |z| (cls_loss.py:257-262)
-__device__ __forceinline__ void edl_terms(const float* z, int K, int y, float& per, float& S, float& alpha_y, float& gnorm, float& fnorm) {
+__device__ __forceinline__ void edl_terms(const float* z, int K, int y, float& per, float& S, float& alpha_y, float& gnorm, float& fnorm,
+                                          float* alpha_max = nullptr) {
     S = 0.f; fnorm = 0.f; alpha_y = 1.f;
+    float amax = 0.f;
     for (int k = 0; k < K; ++k) {
         const float zk = z[k];
         const float a = expf(fminf(fmaxf(zk, -10.f), 10.f)) + 1.f;
         S += a; fnorm += fabsf(zk);
+        amax = fmaxf(amax, a);
         if (k == y) alpha_y = a;
     }
+    if (alpha_max) *alpha_max = amax;
     per = logf(S) - logf(alpha_y);
     gnorm = fabsf(1.f / alpha_y - (float)K / S);
 }
@@ -215,6 +224,16 @@ __device__ __forceinline__ void match_prior(const MslParams& p, int b, int pr, f
     if (best >= maxn) label = 0;
 }
 
+// GHM bin of a gradient length g in [0, 1]: edges i / nb as fp32 (python: float(i) / nb -> float32 tensor), the last one + 1e-6
+// (cls_loss.py:105-108, :236-238)
+__device__ __forceinline__ int ghm_bin(float g, int nb) {
+    auto edge = [nb](int i) { return i == nb ? (float)(1.0 + 1e-6) : (float)((double)i / (double)nb); };
+    int i = min(max((int)(g * (float)nb), 0), nb - 1);
+    while (i > 0 && g < edge(i)) --i;
+    while (i < nb - 1 && g >= edge(i + 1)) ++i;
+    return i;
+}
+
 // s_meta: pos | ppos << 1 | label << 2 (10 bits) | (coarse IBM bin + 1) << 12 (9 bits) | (refined IBM bin + 1) << 21 (9 bits)
 __device__ __forceinline__ int meta_bin(int meta, int pass) { return ((meta >> (pass ? 21 : 12)) & 0x1ff) - 1; }
 
@@ -234,8 +253,9 @@ msl_forward_kernel(const MslParams p) {
     float* s_a = s_unc + M;                                  // [M] x 3 per-element loss terms on their way to the group sums
     float* s_b = s_a + M;
     float* s_c = s_b + M;
-    float* s_acc = s_c + M;                                  // [nb] IBM EMA
-    float* s_part = s_acc + kMslMaxBins;                     // [4 x 32] warp partials
+    float* s_acc = s_c + M;                                  // [nb] IBM EMA / GHM per-bin weight
+    double* s_accd = reinterpret_cast<double*>(s_acc + kMslMaxBins);   // [nb] GHM EMA (fp64 like the reference's python floats)
+    float* s_part = reinterpret_cast<float*>(s_accd + kMslMaxBins);    // [4 x 32] warp partials
     int* s_parti = reinterpret_cast<int*>(s_part + 4 * kMslWarps);   // [32]
     float* s_grp = reinterpret_cast<float*>(s_parti + kMslWarps);    // [12 x 64] per-group results
     int* s_grpi = reinterpret_cast<int*>(s_grp + 12 * kMslMaxGroups); // [2 x 64]
@@ -257,9 +277,14 @@ msl_forward_kernel(const MslParams p) {
 
     const int tid = threadIdx.x;
     const bool anet = p.flavour == kMslAnet, focal = p.flavour == kMslFocal;
-    const bool binned = p.use_ibm && !anet && !focal;        // the THUMOS14 IBM: 50-bin EMA state
-    if (binned)
+    const int rw = (anet || focal) ? kRwNone : p.reweight;
+    const bool ghm = rw == kRwGhm;
+    const bool binned = rw == kRwIbm || ghm;                 // batch-global bins: the THUMOS14 IBM (50-bin EMA state) or GHM
+    const bool cls_all = !anet && !focal && p.cls_all;
+    if (rw == kRwIbm)
         for (int i = tid; i < nb; i += blockDim.x) s_acc[i] = p.weight_accum[i];
+    if (ghm)
+        for (int i = tid; i < nb; i += blockDim.x) s_accd[i] = p.ghm_acc[i];
 
     // ------------------------------------------------------------------ phase A1: matching, IoU of the coarse prediction
     for (int j = tid; j < M; j += blockDim.x) {
@@ -358,19 +383,27 @@ msl_forward_kernel(const MslParams p) {
         } else {
             // EDL, unweighted; the THUMOS14 IBM weight needs the batch-global bins (phase B), the ActivityNet one is local:
             // w = 1 / (||z||_1 exp(c g) + 1e-10); s_gh_* then holds the weight and s_per_* the weighted loss
-            float per, S, ay, gn, fn;
-            edl_terms(p.conf + (size_t)j * K, K, label - 1, per, S, ay, gn, fn);
-            float wgt = 1.f;
-            if (anet && p.use_ibm) wgt = 1.f / (fn * expf(p.ibm_coeff * gn) + 1e-10f);
-            s_per_c[j] = pos ? per * (anet ? wgt : 1.f) : 0.f;
-            s_gh_c[j] = anet ? wgt : gn * fn;
-            if (binned) meta |= ((pos ? (int)ceilf(gn * (float)nb) : -1) + 1) << 12;
-            edl_terms(p.pconf + (size_t)j * K, K, plabel - 1, per, S, ay, gn, fn);
-            wgt = 1.f;
-            if (anet && p.use_ibm) wgt = 1.f / (fn * expf(p.ibm_coeff * gn) + 1e-10f);
-            s_per_p[j] = ppos ? per * (anet ? wgt : 1.f) : 0.f;
-            s_gh_p[j] = anet ? wgt : gn * fn;
-            if (binned) meta |= ((ppos ? (int)ceilf(gn * (float)nb) : -1) + 1) << 21;
+            float per, S, ay, gn, fn, amax;
+            auto local_weight = [&](int y, bool inc) {
+                if (anet && p.use_ibm) return 1.f / (fn * expf(p.ibm_coeff * gn) + 1e-10f);
+                if (rw == kRwIb) return inc ? 1.f / (gn * fn) : 0.f;                        // cls_loss.py:250-256
+                if (rw == kRwFocal) return (y == 0 ? p.edl_alpha0 : 1.f - p.edl_alpha0) * powf(1.f - amax / S, p.edl_gamma);   // :221-227
+                return 1.f;
+            };
+            const int yc = cls_all ? label : label - 1;
+            const bool inc_c = cls_all || pos;
+            edl_terms(p.conf + (size_t)j * K, K, yc, per, S, ay, gn, fn, &amax);
+            float wgt = local_weight(yc, inc_c);
+            s_per_c[j] = inc_c ? per * (binned ? 1.f : wgt) : 0.f;
+            s_gh_c[j] = binned ? (ghm ? gn : gn * fn) : wgt;
+            if (binned) meta |= ((inc_c ? (ghm ? ghm_bin(gn, nb) + 1 : (int)ceilf(gn * (float)nb)) : -1) + 1) << 12;
+            const int yp = cls_all ? plabel : plabel - 1;
+            const bool inc_p = cls_all || ppos;
+            edl_terms(p.pconf + (size_t)j * K, K, yp, per, S, ay, gn, fn, &amax);
+            wgt = local_weight(yp, inc_p);
+            s_per_p[j] = inc_p ? per * (binned ? 1.f : wgt) : 0.f;
+            s_gh_p[j] = binned ? (ghm ? gn : gn * fn) : wgt;
+            if (binned) meta |= ((inc_p ? (ghm ? ghm_bin(gn, nb) + 1 : (int)ceilf(gn * (float)nb)) : -1) + 1) << 21;
             s_unc[j] = (float)K / S;
         }
         s_meta[j] = meta;
@@ -395,7 +428,7 @@ msl_forward_kernel(const MslParams p) {
     // ------------------------------------------------------------------ phase B/C: THUMOS14 IBM per-bin EMA (cls_loss.py:263-268)
     // coarse call first, then the refined call sees the already updated buffer — the reference's call order.
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    if (binned) {
+    if (rw == kRwIbm) {
         for (int pass = 0; pass < 2; ++pass) {
             const float* gh = pass ? s_gh_p : s_gh_c;
             for (int i = warp; i < nb; i += nwarps) {
@@ -422,9 +455,50 @@ msl_forward_kernel(const MslParams p) {
             __syncthreads();
         }
         for (int i = tid; i < nb; i += blockDim.x) p.weight_accum[i] = s_acc[i];
-    } else if (!anet && !focal) {
-        for (int j = tid; j < M; j += blockDim.x) { s_gh_c[j] = 1.f; s_gh_p[j] = 1.f; }
-        __syncthreads();
+    } else if (ghm) {
+        // GHM (cls_loss.py:228-249): the [M,K] gradient lengths |1/alpha - K/S| * y are zero off the target class, so every
+        // included row puts K - 1 zeros into bin 0 and its target entry into ghm_bin(g); per-bin EMA of the COUNTS in fp64,
+        // weight = 1 / acc[bin] / (number of non-empty bins).  Coarse call first, the refined call sees the updated state.
+        int& s_nonempty = s_grpi[2 * kMslMaxGroups - 1];       // a spare slot of the per-group index table (GHM runs with one group)
+        for (int pass = 0; pass < 2; ++pass) {
+            const float n_inc = cls_all ? (float)M : (pass ? g_nppos[0] : g_npos[0]);
+            if (tid == 0) s_nonempty = 0;
+            __syncthreads();
+            for (int i = warp; i < nb; i += nwarps) {
+                float n = 0.f;
+                for (int j = lane; j < M; j += 32)
+                    if (meta_bin(s_meta[j], pass) == i + 1) n += 1.f;      // stored as ghm_bin + 1
+                n = warp_sum(n);
+                if (lane == 0) {
+                    const double cnt = (double)n + (i == 0 ? (double)(K - 1) * (double)n_inc : 0.0);
+                    float w = 0.f;
+                    if (cnt > 0.0) {
+                        const double acc = p.momentum > 0.f ? (double)p.momentum * s_accd[i] + (1.0 - (double)p.momentum) * cnt : cnt;
+                        if (p.momentum > 0.f) s_accd[i] = acc;
+                        w = (float)(1.0 / fmax(acc, 1e-300));
+                        atomicAdd(&s_nonempty, 1);
+                    }
+                    s_acc[i] = w;
+                }
+            }
+            __syncthreads();
+            float* per = pass ? s_per_p : s_per_c;
+            float* ghw = pass ? s_gh_p : s_gh_c;
+            const int ne = s_nonempty;
+            for (int j = tid; j < M; j += blockDim.x) {
+                float wgt = 0.f;
+                const int bin = meta_bin(s_meta[j], pass);
+                if (bin >= 0) {
+                    wgt = s_acc[bin - 1];
+                    if (ne > 0) wgt = wgt / (float)ne;
+                }
+                ghw[j] = wgt;
+                per[j] *= wgt;
+            }
+            __syncthreads();
+        }
+        if (p.momentum > 0.f)
+            for (int i = tid; i < nb; i += blockDim.x) p.ghm_acc[i] = s_accd[i];
     }
 
     // ------------------------------------------------------------------ phase D: actionness (cls_loss.py:299-339), per group
@@ -520,36 +594,44 @@ msl_forward_kernel(const MslParams p) {
         } else {
             // coarse EDL gradient: w/N * (1/S - [k == y]/alpha_y) * d alpha_k / d z_k  (+ the ActivityNet weight's own gradient
             // through ||z||_1: per * dw/dz_k = -per_weighted * w * exp(c g) * sign(z_k))
-            const float* z = p.conf + (size_t)j * K;
-            float* dz = d_conf + (size_t)j * K;
-            if (pos) {
-                float S = 0.f, ay = 1.f;
+            // one row: d/dz of  w * (log S - log alpha_y)  scaled by 1/norm, plus a per-row extra term on alpha (calibration)
+            auto row_grad = [&](const float* z, float* dz, int y, bool inc, float w, float per_w, float norm, float cal_alpha) {
+                float S = 0.f, ay = 1.f, amax = 0.f; int m = 0;
                 for (int k = 0; k < K; ++k) {
                     const float a = expf(fminf(fmaxf(z[k], -10.f), 10.f)) + 1.f;
-                    S += a; if (k == label - 1) ay = a;
+                    S += a; if (k == y) ay = a;
+                    if (a > amax) { amax = a; m = k; }
                 }
-                const float wgt = s_gh_c[j] / N;
-                float through_norm = 0.f;
-                if (anet && p.use_ibm) {
+                const float wn = inc ? w / norm : 0.f;
+                float through_norm = 0.f, fcoef = 0.f, pred = 0.f;
+                if (inc && anet && p.use_ibm) {        // the ActivityNet weight's own gradient through ||z||_1
                     const float gn = fabsf(1.f / ay - (float)K / S);
-                    through_norm = -(s_per_c[j] / N) * s_gh_c[j] * expf(p.ibm_coeff * gn);
+                    through_norm = -(per_w / norm) * w * expf(p.ibm_coeff * gn);
+                }
+                if (inc && rw == kRwFocal) {           // the modulating factor (1 - max_k alpha_k / S)^gamma is NOT detached (:221-227)
+                    pred = amax / S;
+                    const float a_cls = y == 0 ? p.edl_alpha0 : 1.f - p.edl_alpha0;
+                    fcoef = -((logf(S) - logf(ay)) / norm) * a_cls * p.edl_gamma * powf(1.f - pred, p.edl_gamma - 1.f) / S;
                 }
                 for (int k = 0; k < K; ++k) {
                     const float zk = z[k];
                     const float ev = expf(fminf(fmaxf(zk, -10.f), 10.f));
                     const float da = (zk >= -10.f && zk <= 10.f) ? ev : 0.f;
-                    float g = 1.f / S;
-                    if (k == label - 1) g -= 1.f / (ev + 1.f);
-                    dz[k] = wgt * g * da + through_norm * (zk > 0.f ? 1.f : (zk < 0.f ? -1.f : 0.f));
+                    float g = 0.f;
+                    if (inc) {
+                        g = 1.f / S;
+                        if (k == y) g -= 1.f / (ev + 1.f);
+                        g = g * wn + fcoef * ((k == m ? 1.f : 0.f) - pred);
+                    }
+                    g += cal_alpha / S;                                       // caller passes cal_g * (-unc): d unc / d alpha_k = -unc / S
+                    dz[k] = g * da + through_norm * (zk > 0.f ? 1.f : (zk < 0.f ? -1.f : 0.f));
                 }
-            } else {
-                for (int k = 0; k < K; ++k) dz[k] = 0.f;
-            }
+            };
+            // coarse: w/N * (1/S - [k == y]/alpha_y) * d alpha_k / d z_k (+ the weight's own gradient where it has one)
+            row_grad(p.conf + (size_t)j * K, d_conf + (size_t)j * K, cls_all ? label : label - 1, cls_all || pos, s_gh_c[j], s_per_c[j], N, 0.f);
             // refined EDL gradient + IoU-aware calibration over ALL priors (cls_loss.py:120-129, mean).  The THUMOS14 reference
             // flattens its [P,B] IoU buffer against [B*P] logits (multisegment_loss.py:116,146,236): element j pairs with the
             // IoU of prior j / B of sample j % B; the ActivityNet loss pairs them per sample (anet :258-260).
-            const float* zp = p.pconf + (size_t)j * K;
-            float* dzp = d_pconf + (size_t)j * K;
             float cal_g = 0.f;
             const float unc = s_unc[j];
             if (p.iou_aware) {
@@ -558,28 +640,9 @@ msl_forward_kernel(const MslParams p) {
                 cal = -iou * logf(1.f - unc) - (1.f - iou) * logf(unc);
                 cal_g = (iou / (1.f - unc) - (1.f - iou) / unc) * invM;      // d mean(reg) / d unc_j
             }
-            const float S = (float)K / unc;
-            const float wgt = ppos ? s_gh_p[j] / PN : 0.f;
             const int plabel = ppos ? label : 0;
-            float through_norm = 0.f;
-            if (anet && p.use_ibm && ppos) {
-                const float ay = expf(fminf(fmaxf(zp[plabel - 1], -10.f), 10.f)) + 1.f;
-                const float gn = fabsf(1.f / ay - (float)K / S);
-                through_norm = -(s_per_p[j] / PN) * s_gh_p[j] * expf(p.ibm_coeff * gn);
-            }
-            for (int k = 0; k < K; ++k) {
-                const float zk = zp[k];
-                const float ev = expf(fminf(fmaxf(zk, -10.f), 10.f));
-                const float da = (zk >= -10.f && zk <= 10.f) ? ev : 0.f;
-                float g = 0.f;
-                if (ppos) {
-                    g = 1.f / S;
-                    if (k == plabel - 1) g -= 1.f / (ev + 1.f);
-                    g *= wgt;
-                }
-                g += cal_g * (-unc / S);                                      // d unc / d alpha_k = -K / S^2
-                dzp[k] = g * da + through_norm * (zk > 0.f ? 1.f : (zk < 0.f ? -1.f : 0.f));
-            }
+            row_grad(p.pconf + (size_t)j * K, d_pconf + (size_t)j * K, cls_all ? plabel : plabel - 1, cls_all || ppos, s_gh_p[j], s_per_p[j], PN,
+                     cal_g * (-unc));
         }
         s_a[j] = cal;
     }
@@ -638,7 +701,7 @@ __global__ void msl_backward_kernel(const MslBwdParams p) {
 }
 
 static size_t msl_smem_bytes(int M) {
-    return (size_t)M * 12 * 4 + (kMslMaxBins + 4 * kMslWarps + kMslWarps + 12 * kMslMaxGroups + 2 * kMslMaxGroups) * 4;
+    return (size_t)M * 12 * 4 + (kMslMaxBins + 2 * kMslMaxBins + 4 * kMslWarps + kMslWarps + 12 * kMslMaxGroups + 2 * kMslMaxGroups) * 4 + 16;
 }
 
 }  // namespace otal
@@ -656,9 +719,18 @@ int otal_msl_forward(const otal_msl_desc* d, void* stream_) {
     if (!d->loc || !d->conf || !d->prop_loc || !d->prop_conf || !d->center || !d->priors || !d->targets || !d->valid ||
         !d->losses || !d->workspace) { set_last_error_msg("msl: null pointer"); return OTAL_ERR_BAD_ARG; }
     if (d->flavour < kMslThumos || d->flavour > kMslFocal) { set_last_error_msg("msl: flavour must be 0 (THUMOS14 EDL), 1 (ActivityNet EDL) or 2 (closed-set focal)"); return OTAL_ERR_BAD_ARG; }
-    const bool binned = d->use_ibm && d->flavour == kMslThumos;
-    if (binned && (!d->weight_accum || d->num_bins <= 0 || d->num_bins > kMslMaxBins)) {
+    // re-weighting branch of the THUMOS14 EDL loss: use_ibm (the round-1 field) means kRwIbm unless `reweight` names another
+    int rw = d->flavour == kMslThumos ? (d->reweight ? d->reweight : (d->use_ibm ? kRwIbm : kRwNone)) : kRwNone;
+    if (rw < kRwNone || rw > kRwGhm) { set_last_error_msg("msl: reweight must be 0..4"); return OTAL_ERR_BAD_ARG; }
+    const bool binned = rw == kRwIbm || rw == kRwGhm;
+    if (rw == kRwIbm && (!d->weight_accum || d->num_bins <= 0 || d->num_bins > kMslMaxBins)) {
         set_last_error_msg("msl: IBM needs weight_accum and 1..256 bins"); return OTAL_ERR_BAD_ARG;
+    }
+    if (rw == kRwGhm && (!d->ghm_acc_sum || d->num_bins <= 0 || d->num_bins > kMslMaxBins - 2)) {
+        set_last_error_msg("msl: GHM needs the fp64 acc_sum buffer and 1..254 bins"); return OTAL_ERR_BAD_ARG;
+    }
+    if (d->cls_all && (d->flavour != kMslThumos || d->act || d->prop_act)) {
+        set_last_error_msg("msl: cls_all (no os_head) is a THUMOS14 EDL option without actionness inputs"); return OTAL_ERR_BAD_ARG;
     }
     if (d->flavour == kMslFocal && (d->act || d->prop_act || d->iou_aware || d->use_ibm)) {
         set_last_error_msg("msl: the closed-set focal flavour has no actionness head, IBM or IoU calibration"); return OTAL_ERR_BAD_ARG;
@@ -682,6 +754,8 @@ int otal_msl_forward(const otal_msl_desc* d, void* stream_) {
     p.iou_aware = d->iou_aware; p.act_weight = d->act_weight; p.act_margin = d->act_margin;
     p.prior_stride = d->prior_stride > 0 ? d->prior_stride : 1;
     p.ibm_coeff = d->ibm_coeff; p.focal_alpha = d->focal_alpha; p.focal_gamma = d->focal_gamma;
+    p.reweight = rw; p.cls_all = d->cls_all ? 1 : 0; p.edl_alpha0 = d->edl_focal_alpha; p.edl_gamma = d->edl_focal_gamma;
+    p.ghm_acc = d->ghm_acc_sum;
     for (int i = 0; i < 16; ++i) p.bounds[i] = d->level_bounds[i];
     p.loc = d->loc; p.conf = d->conf; p.ploc = d->prop_loc; p.pconf = d->prop_conf; p.center = d->center;
     p.act = d->act; p.pact = d->prop_act; p.priors = d->priors; p.targets = d->targets; p.valid = d->valid;

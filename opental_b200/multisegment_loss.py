@@ -116,6 +116,7 @@ class EvidenceLoss(nn.Module):
             alpha = torch.ones(num_cls) * (1 - cfg["alpha"])
             alpha[0] = cfg["alpha"]
             self.register_buffer("alpha", alpha, persistent=False)
+            self.alpha0 = float(cfg["alpha"])          # host copy for the fused kernel
             self.gamma = cfg["gamma"]
         if self.with_ghm:
             self.num_bins = cfg["num_bins"]
@@ -336,16 +337,18 @@ class MultiSegmentLoss(nn.Module):
 
     def _fused_ok(self, loc) -> bool:
         """The single-CTA CUDA kernel covers the OpenTAL configuration (edl: log / exp, plain or IBM, os_head) and the closed-set
-        baseline (configs/thumos14.yaml: softmax focal loss, no os_head); the ablation variants (digamma / mse, relu / softplus
-        evidence, soft labels, focal-EDL / GHM / IB re-weighting, size_average) run the masked torch formulation below."""
+        baseline (configs/thumos14.yaml: softmax focal loss, no os_head) and the re-weighting ablations of configs/ablations
+        (focal-EDL, GHM, IB, no os_head); digamma / mse, relu / softplus evidence, soft labels and size_average run the masked
+        torch formulation below."""
         c = self.cls_loss
         if not (self.fused and loc.is_cuda and loc.dtype == torch.float32 and not self.size_average
                 and loc.shape[0] * loc.shape[1] <= 4096):
             return False
         if self.cls_loss_type == "focal":
             return not self.os_head and c.alpha0 is not None and c.num_class < 1024
-        return (self.cls_loss_type == "edl" and self.os_head and c.loss_type == "log" and c.evidence == "exp" and not c.soft_label
-                and not (c.with_focal or c.with_ghm or c.with_ibloss))
+        # edl: every branch a shipped config selects (configs/*.yaml, configs/ablations/*.yaml all use log / exp): plain, IBM, IB,
+        # focal-EDL, GHM, with or without os_head.  digamma / mse, relu / softplus and soft labels stay torch formulations.
+        return self.cls_loss_type == "edl" and c.loss_type == "log" and c.evidence == "exp" and not c.soft_label
 
     def forward(self, output_dict, targets, pre_locs=None):
         loc, conf, ploc, pconf, center, priors = (output_dict[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors"))
@@ -363,17 +366,34 @@ class MultiSegmentLoss(nn.Module):
             self.last_stats, self.last_vec = stats, vec
             return tuple(vec[:5].unbind(0)) + (None, None)
         if self._fused_ok(loc):
+            from . import ops
             c = self.cls_loss
-            use_ibm = bool(c.with_ibm and c.epoch >= c.ibm_start)
+            # the reference's precedence: focal > GHM > IB > IBM > plain (cls_loss.py:221-272), each from its start epoch on
+            rw, extra = ops.MSL_RW_NONE, {}
+            if c.with_focal:
+                rw, extra = ops.MSL_RW_FOCAL, dict(edl_focal_alpha=float(c.alpha0), edl_focal_gamma=float(c.gamma))
+            elif c.with_ghm and c.epoch >= c.ghm_start:
+                if c.acc_sum.device != loc.device:
+                    c.acc_sum = c.acc_sum.to(loc.device)
+                rw, extra = ops.MSL_RW_GHM, dict(ghm_acc_sum=c.acc_sum, num_bins=int(c.num_bins))
+            elif c.with_ibloss and c.epoch >= c.ib_start:
+                rw = ops.MSL_RW_IB
+            elif c.with_ibm and c.epoch >= c.ibm_start:
+                rw = ops.MSL_RW_IBM
             if c.with_ibm and c.weight_accum.device != loc.device:
                 c.weight_accum = c.weight_accum.to(loc.device)
-            cfg = dict(clip_length=float(self.clip_length), overlap_thresh=float(self.overlap_thresh), use_ibm=use_ibm,
-                       momentum=float(c.momentum) if c.with_ibm else 0.0, iou_aware=bool(self.iou_aware),
-                       act_weight=float(self.act_loss.weight), act_margin=float(self.act_loss.margin))
-            vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P), pact.reshape(B, P),
-                                           priors, tgt, valid, c.weight_accum if c.with_ibm else None, cfg)
+            mom = float(c.momentum) if (c.with_ibm or c.with_ghm) else 0.0
+            act_w, act_m = (float(self.act_loss.weight), float(self.act_loss.margin)) if self.os_head else (0.0, 0.0)
+            cfg = dict(clip_length=float(self.clip_length), overlap_thresh=float(self.overlap_thresh), use_ibm=rw == ops.MSL_RW_IBM,
+                       momentum=mom, iou_aware=bool(self.iou_aware), act_weight=act_w, act_margin=act_m, reweight=rw,
+                       cls_all=not self.os_head, **extra)
+            vec, stats = _FusedMSLFn.apply(loc, conf, ploc, pconf, center.reshape(B, P), act.reshape(B, P) if self.os_head else None,
+                                           pact.reshape(B, P) if self.os_head else None, priors, tgt, valid,
+                                           c.weight_accum if rw == ops.MSL_RW_IBM else None, cfg)
             self.last_stats = stats        # raw counts #pos, #refined pos, AN, PAN and loss_iouc at [7:12] (device; logging, engine._globalise)
             self.last_vec = vec            # the 7 losses as one tensor (training_cost takes it instead of re-stacking the tuple)
+            if not self.os_head:
+                return tuple(vec[:5].unbind(0)) + (None, None)
             return tuple(vec.unbind(0))
         loc_t, conf_t, prop_loc_t, prop_conf_t, iou = self.match(loc.detach(), priors, tgt, valid)
         pos, ppos = conf_t > 0, prop_conf_t > 0

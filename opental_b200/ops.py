@@ -700,15 +700,20 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 # MultiSegmentLoss (single-CTA fused kernel)
 # ----------------------------------------------------------------------------------------------------------
 MSL_THUMOS, MSL_ANET, MSL_FOCAL = 0, 1, 2
+MSL_RW_NONE, MSL_RW_IBM, MSL_RW_IB, MSL_RW_FOCAL, MSL_RW_GHM = 0, 1, 2, 3, 4
 
 
 def msl_forward(loc, conf, prop_loc, prop_conf, center, act, prop_act, priors, targets, valid, weight_accum, *,
                 clip_length: float, overlap_thresh: float, use_ibm: bool, momentum: float, iou_aware: bool,
                 act_weight: float, act_margin: float, flavour: int = MSL_THUMOS, ibm_coeff: float = 10.0,
-                focal_alpha: float = 0.25, focal_gamma: float = 2.0, level_bounds=()) -> tuple[torch.Tensor, torch.Tensor]:
+                focal_alpha: float = 0.25, focal_gamma: float = 2.0, level_bounds=(), reweight: int = 0, cls_all: bool = False,
+                edl_focal_alpha: float = 0.25, edl_focal_gamma: float = 2.0, ghm_acc_sum: torch.Tensor | None = None,
+                num_bins: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
     """All 7 losses (+ N, PN, AN, PAN, loss_iouc) and the unit-gradient workspace.  See include/opental_b200.h.
     flavour: MSL_THUMOS (OpenTAL EDL), MSL_ANET (per-sample ActivityNet loss; level_bounds = ((left, right), ...) per pyramid
-    level, priors [P,2] with the level in column 1) or MSL_FOCAL (closed-set softmax focal loss; act / prop_act None)."""
+    level, priors [P,2] with the level in column 1) or MSL_FOCAL (closed-set softmax focal loss; act / prop_act None).
+    reweight (MSL_THUMOS): MSL_RW_IBM / _IB / _FOCAL / _GHM select a re-weighting branch of EvidenceLoss (0: use_ibm decides);
+    ghm_acc_sum = the fp64 [num_bins] GHM state; cls_all = no os_head (every prior a classification sample, class 0 = background)."""
     _require_cuda(loc, conf, prop_loc, prop_conf, center, priors, targets, valid)
     B, P, K = conf.shape
     G = targets.shape[1]
@@ -721,13 +726,16 @@ def msl_forward(loc, conf, prop_loc, prop_conf, center, act, prop_act, priors, t
     losses = torch.empty(16, dtype=torch.float32, device=loc.device)
     ws = torch.empty(int(_lib.load().otal_msl_workspace_floats(B, P, K)), dtype=torch.float32, device=loc.device)
     d = MslDesc(B=B, P=P, K=K, G=G, clip_length=clip_length, overlap_thresh=overlap_thresh, use_ibm=int(use_ibm),
-                num_bins=weight_accum.numel() if weight_accum is not None else 0, momentum=momentum, iou_aware=int(iou_aware),
+                num_bins=(num_bins if num_bins is not None else (weight_accum.numel() if weight_accum is not None else 0)), momentum=momentum,
+                iou_aware=int(iou_aware),
                 act_weight=act_weight, act_margin=act_margin, prior_stride=priors.stride(0),
                 loc=ts[0].data_ptr(), conf=ts[1].data_ptr(), prop_loc=ts[2].data_ptr(), prop_conf=ts[3].data_ptr(),
                 center=ts[4].data_ptr(), act=_ptr(ts[5]), prop_act=_ptr(ts[6]), priors=priors.data_ptr(),
                 targets=targets.data_ptr(), valid=valid.data_ptr(), weight_accum=_ptr(weight_accum),
                 losses=losses.data_ptr(), workspace=ws.data_ptr(), flavour=int(flavour), ibm_coeff=ibm_coeff,
-                focal_alpha=focal_alpha, focal_gamma=focal_gamma)
+                focal_alpha=focal_alpha, focal_gamma=focal_gamma, reweight=int(reweight), cls_all=int(cls_all),
+                edl_focal_alpha=edl_focal_alpha, edl_focal_gamma=edl_focal_gamma, ghm_acc_sum=_ptr(ghm_acc_sum))
+    assert ghm_acc_sum is None or (ghm_acc_sum.dtype == torch.float64 and ghm_acc_sum.is_contiguous() and ghm_acc_sum.device == loc.device)
     flat = [float(v) for pair in level_bounds for v in pair]
     assert len(flat) <= 16, "msl: at most 8 pyramid levels"
     for i, v in enumerate(flat):

@@ -580,6 +580,7 @@ class Emulator:
         shapes = ((B, P, 2), (B, P, K), (B, P, 2), (B, P, K), (B, P, 1), (B, P, 1), (B, P, 1))
         ptrs = (d.loc, d.conf, d.prop_loc, d.prop_conf, d.center, d.act, d.prop_act)
         focal, anet = d.flavour == 2, d.flavour == 1
+        assert d.reweight in (0, 1) and not d.cls_all, "abi_emu: the ablation branches of the fused loss are GPU-tested only"
         assert focal or (d.act and d.prop_act), "abi_emu: the EDL flavours of the fused loss are emulated for the os_head configuration"
         with torch.enable_grad():
             out = {n: (_view(p_, int(np.prod(sh)), np.float32).view(*sh).clone().requires_grad_(True) if p_ else None)

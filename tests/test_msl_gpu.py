@@ -233,3 +233,67 @@ def test_fused_closed_set_focal_loss_matches_oracle(B):
         assert abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (i, float(a), float(b))
     for k, a, b in zip(keys, g_got, g_ref):
         assert torch.allclose(a.cpu(), b, atol=2e-6, rtol=1e-4), (k, float((a.cpu() - b).abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the re-weighting ablations of configs/ablations/*.yaml inside the fused kernel: focal-EDL, GHM (fp64 per-bin EMA state), IB —
+# against the REFERENCE's own losses and gradients (tests/golden/edl_variants.npz, generated by oracle/make_golden.py --edl from
+# the imported reference: two consecutive calls, so that the GHM state carries over) — and the no-os_head form against the
+# product's masked torch formulation (itself pinned to the reference on the CPU, tests/test_loss_cpu.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["focal", "ghm_momentum", "ibloss"])
+def test_fused_ablation_branches_match_reference_golden(name, golden_dir):
+    import os
+
+    import numpy as np
+    gold = np.load(os.path.join(golden_dir, "edl_variants.npz"))
+    cfg, _ = O.EDL_VARIANTS[name]
+    crit = MultiSegmentLoss(15, 0.5, 1.0, cls_loss_type="edl", edl_config=dict(cfg, iou_aware=True), os_head=True,
+                            act_config=dict(weight=0.1, margin=1.0)).cuda()
+    crit.cls_loss.epoch = 11
+    priors = torch.cat(O.level_priors(O.OracleConfig()), 0).cuda()
+    from opental_b200 import _lib
+    for it in range(2):
+        out = {k: v.cuda().requires_grad_(True) for k, v in O.fake_head_outputs(3, 5 + it).items()}
+        assert crit._fused_ok(out["loc"])
+        out["priors"] = priors
+        n0 = _lib.LAUNCHES.get("otal_msl_forward", 0)
+        losses = crit(out, [O.synthetic_targets(i, num_classes=15).cuda() for i in range(3)])
+        assert _lib.LAUNCHES.get("otal_msl_forward", 0) == n0 + 1
+        want = gold[f"{name}.msl.{it}.losses"]
+        for a, b in zip(losses, want):
+            assert abs(float(a) - b) <= 2e-5 * max(1.0, abs(b)), (name, it, float(a), b)
+        grads = torch.autograd.grad(sum(w * l for w, l in zip(W, losses)), [out[k] for k in KEYS])
+        for k, g in zip(KEYS, grads):
+            w = torch.from_numpy(gold[f"{name}.msl.{it}.grad.{k}"])
+            assert float((g.cpu() - w).abs().max()) <= 1e-4 * max(float(w.abs().max()), 1e-6), (name, it, k)
+
+
+@pytest.mark.parametrize("edl", [dict(), dict(with_ibm=True, ibm_start=0, momentum=0.9, num_bins=50), dict(with_ghm=True, num_bins=10, momentum=0.0)])
+def test_fused_loss_without_os_head_matches_the_torch_formulation(edl):
+    """configs/ablations/thumos14_opental_noACT.yaml: EDL over all priors with a background class, no actionness head."""
+    cfg = dict(loss_type="log", evidence="exp", iou_aware=True, **edl)
+    g = torch.Generator().manual_seed(41)
+    B, P, K = 3, 126, 16
+    base = dict(loc=(torch.rand(B, P, 2, generator=g) * 30 + 1), conf=2 * torch.randn(B, P, K, generator=g),
+                prop_loc=0.3 * torch.randn(B, P, 2, generator=g), prop_conf=2 * torch.randn(B, P, K, generator=g),
+                center=torch.randn(B, P, 1, generator=g))
+    priors = torch.cat(O.level_priors(O.OracleConfig()), 0).cuda()
+    targets = [O.synthetic_targets(i, num_classes=15).cuda() for i in range(B)]
+    keys = KEYS[:5]
+    res = {}
+    for fused in (True, False):
+        crit = MultiSegmentLoss(K, 0.5, 1.0, cls_loss_type="edl", edl_config=cfg, os_head=False).cuda()
+        crit.cls_loss.epoch = 11
+        crit.fused = fused
+        for it in range(2):                                  # two calls: the second sees the first one's state
+            out = {k: v.clone().cuda().requires_grad_(True) for k, v in base.items()}
+            out["priors"] = priors
+            losses = crit(out, targets)
+            assert losses[5] is None and losses[6] is None
+            grads = torch.autograd.grad(sum(w * l for w, l in zip(W, losses[:5])), [out[k] for k in keys])
+        res[fused] = ([float(l) for l in losses[:5]], [g_.cpu() for g_ in grads])
+    for a, b in zip(res[True][0], res[False][0]):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (a, b)
+    for k, a, b in zip(keys, res[True][1], res[False][1]):
+        assert float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-6), k
