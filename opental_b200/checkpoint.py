@@ -6,7 +6,9 @@ Our Trainer keeps its Adam moments in three flat fp32 buffers that mirror the fl
 `nn.Parameter` of the model is a (possibly strided) view into one of those parameter buffers — so the per-parameter
 moments are the SAME views taken on the moment buffers.  `adam_state_dict` / `load_adam_state_dict` translate between
 the two forms; parameter order and `requires_grad` flags are the reference's (tests/test_api_cpu.py), so the index-keyed
-`state` / `param_groups` of `torch.optim.Adam` line up and the files interoperate in both directions.
+`state` / `param_groups` of `torch.optim.Adam` line up and the files interoperate in both directions — in the layout the
+Trainer is configured for: one group (thumos14/train.py:321) or, with `backbone_lr_scale != 1`, the ActivityNet script's two groups
+numbered backbone-first (anet/train.py:304-311).
 
 Extras the reference loses on resume ride along under their own keys and are ignored by the reference's
 `resume_training`: the IBM `weight_accum` buffer, the loss epoch counters and the Trainer's step counter."""
@@ -35,34 +37,60 @@ def moment_view(p: torch.Tensor, groups, flat_moments) -> torch.Tensor:
     return torch.as_strided(flat_moments[gi], tuple(p.shape), tuple(p.stride()), off)
 
 
-def adam_state_dict(params, groups, state, *, step: int, lr, betas, eps, weight_decay) -> dict:
-    """`torch.optim.Adam(params).state_dict()`-compatible dict (train.py:115).  params: list(net.parameters())."""
+def _ordered(params, param_groups):
+    """The optimizer's parameter order: torch.optim.Adam numbers parameters group by group.  `param_groups` = None (one group,
+    `params` as given: thumos14/train.py:321) or [(parameters, lr), ...] (the ActivityNet script's two groups, backbone at
+    0.1 x the rate first, then coarse_pyramid_detection: anet/train.py:304-311)."""
+    if param_groups is None:
+        return list(params), None
+    ordered = [p for ps, _ in param_groups for p in ps]
+    if {id(p) for p in ordered} != {id(p) for p in params} or len(ordered) != len(params):
+        raise ValueError("param_groups must partition the model's parameters")
+    return ordered, [len(ps) for ps, _ in param_groups]
+
+
+def adam_state_dict(params, groups, state, *, step: int, lr, betas, eps, weight_decay, param_groups=None) -> dict:
+    """`torch.optim.Adam(...).state_dict()`-compatible dict (train.py:115).  params: list(net.parameters()); `param_groups`:
+    see _ordered (each group's own learning rate is written, `lr` is the single group's)."""
+    ordered, sizes = _ordered(params, param_groups)
     st = {}
     if step > 0:
-        for i, p in enumerate(params):
+        for i, p in enumerate(ordered):
             if not p.requires_grad:
                 continue                                     # torch keeps no state for parameters that never had a grad
             st[i] = dict(step=torch.tensor(float(step)),
                          exp_avg=moment_view(p, groups, [s["m"] for s in state]).detach().clone().contiguous(),
                          exp_avg_sq=moment_view(p, groups, [s["v"] for s in state]).detach().clone().contiguous())
-    group = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
-                 capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
-                 params=list(range(len(params))))
-    return dict(state=st, param_groups=[group])
+
+    def group(rate, idx):
+        return dict(lr=rate, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                    capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False, params=idx)
+    if sizes is None:
+        return dict(state=st, param_groups=[group(lr, list(range(len(ordered))))])
+    out, lo = [], 0
+    for n, (_, rate) in zip(sizes, param_groups):
+        out.append(group(rate, list(range(lo, lo + n))))
+        lo += n
+    return dict(state=st, param_groups=out)
 
 
-def load_adam_state_dict(sd: dict, params, groups, state) -> int:
+def load_adam_state_dict(sd: dict, params, groups, state, param_groups=None) -> int:
     """Copy a torch.optim.Adam state_dict (ours or the reference's; `step` an int as in torch 1.9 or a tensor) into the
-    flat moment buffers.  Returns the step count."""
-    idx = sd["param_groups"][0]["params"]
-    if len(idx) != len(params):
-        raise ValueError(f"optimizer state has {len(idx)} parameters, the model has {len(params)}")
+    flat moment buffers.  Returns the step count.  The file's group layout must be the Trainer's (one group, or the
+    ActivityNet script's two): the index -> parameter mapping depends on it."""
+    ordered, sizes = _ordered(params, param_groups)
+    have = [len(g["params"]) for g in sd["param_groups"]]
+    if have != (sizes if sizes is not None else [len(ordered)]):
+        raise ValueError(f"optimizer state has parameter groups of {have} parameters, this Trainer has "
+                         f"{sizes if sizes is not None else [len(ordered)]} (a single-rate THUMOS14 state and a two-rate "
+                         "ActivityNet state are not interchangeable)")
+    idx = [i for g in sd["param_groups"] for i in g["params"]]
     step = 0
     for s in state:
         s["m"].zero_()
         s["v"].zero_()
     for k, ent in sd["state"].items():
-        p = params[idx.index(k)]
+        p = ordered[idx.index(k)]
         if tuple(ent["exp_avg"].shape) != tuple(p.shape):
             raise ValueError(f"optimizer state {k}: shape {tuple(ent['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
         moment_view(p, groups, [s["m"] for s in state]).copy_(ent["exp_avg"])

@@ -203,6 +203,8 @@ class Trainer:
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # Adam's step counter, incremented on the device
         self._head_launched = self._deep_launched = False
         self._graph_updates = False       # does the current graph contain the all-reduce + Adam update?
+        self._nccl_captured = False       # has this Trainer captured NCCL work into a graph before? (see capture())
+        self._defer_comm = False          # a graph WITHOUT the exchange is being captured: the hooks must not launch it
         self._graph = None
         self._graph_ssl = False
         self._graph_cache: dict = {}    # flavour (with / without the SSL pass) -> the captured graph that is not current
@@ -215,8 +217,9 @@ class Trainer:
 
     # ---------------------------------------------------------------------------------------------- data parallel
     def _comm_allowed(self) -> bool:
-        # the warm-up passes of capture() are real passes whose gradients are thrown away: no exchange, no update
-        return not self._warming_up
+        # the warm-up passes of capture() are real passes whose gradients are thrown away: no exchange, no update; a graph that is
+        # captured without the exchange gets it from step() after the replay
+        return not self._warming_up and not self._defer_comm
 
     def _on_backbone_backward(self) -> None:
         if self._comm_allowed():
@@ -300,8 +303,11 @@ class Trainer:
                 bb.frame_map = None
             cost = cost + self.ssl_weight * self.triplet_loss(a, p, n)
         cost.backward()
-        # detached: a caller holding a non-detached loss would keep this step's autograd graph (and its AccumulateGrad
-        # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture
+        # Nothing non-detached may outlive this call: a live loss tensor keeps this step's autograd graph (and its AccumulateGrad
+        # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture ("dependency created
+        # on uncaptured work in another stream" inside backward()).  The criterion's `last_vec` is such a tensor.
+        if getattr(self.criterion, "last_vec", None) is not None:
+            self.criterion.last_vec = self.criterion.last_vec.detach()
         return cost.detach(), tuple(l.detach() if l is not None else None for l in losses), ls.detach(), le.detach()
 
     def _globalise(self, out, losses, targets):
@@ -337,6 +343,14 @@ class Trainer:
         import gc
         self._release_for_capture(ssl_clips is not None or ssl_frame_map is not None)
         gc.collect()                                 # also drops dead autograd graphs of earlier eager steps (see forward_backward)
+        # Data parallel: the FIRST graph a Trainer captures holds the gradient exchange and the Adam update.  Capturing NCCL work
+        # a second time on the same Trainer fails on this stack (torch 2.11 / NCCL 2.28: "dependency created on uncaptured work in
+        # another stream" inside backward(), whatever is done between the two captures — tools/probe/recapture_dp.py), so
+        # re-captures (the SSL flavour, the IBM switch, more target slots, the sweep's next batch size) keep the exchange and the
+        # update behind the replay, as in round 1.  Single-GPU graphs always contain the update.
+        import os
+        recapture_nccl = os.environ.get("OTAL_DP_RECAPTURE", "0") == "1"       # probe switch: capture the exchange again anyway
+        in_graph = bool(self.graph_update) and not (self.world > 1 and self._nccl_captured and not recapture_nccl)
         tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
         srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
         self._static = [torch.empty_like(t) for t in srcs]
@@ -344,7 +358,10 @@ class Trainer:
             d.copy_(s)
         c, t, v, sc = self._static[:4]
         ssl_args = self._ssl_args(ssl_clips, ssl_frame_map)
-        stream = torch.cuda.Stream()
+        # one capture stream per Trainer, reused by every re-capture (OTAL_CAP_STREAM=new: a fresh stream per capture, probe switch)
+        if getattr(self, "_cap_stream", None) is None or os.environ.get("OTAL_CAP_STREAM", "persist") == "new":
+            self._cap_stream = torch.cuda.Stream()
+        stream = self._cap_stream
         stream.wait_stream(torch.cuda.current_stream())
         self._capturing = True
         # the warm-ups are real passes over the live criterion: its stateful buffers (the IBM EMA `weight_accum`, GHM's
@@ -364,15 +381,17 @@ class Trainer:
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread may query events while this thread captures
+            self._defer_comm = not in_graph
             with torch.cuda.graph(self._graph, stream=stream, capture_error_mode="thread_local"):
                 self.zero_grad()
                 self._graph_out = self.forward_backward(c, (t, v), sc, *ssl_args)
-                if self.graph_update:
+                if in_graph:
                     self._finish_step()
         finally:
-            self._capturing = self._warming_up = False
+            self._capturing = self._warming_up = self._defer_comm = False
             self._head_launched = self._deep_launched = False
-        self._graph_updates = bool(self.graph_update)
+        self._graph_updates = in_graph
+        self._nccl_captured = self._nccl_captured or (in_graph and self.world > 1)
         self._graph_epoch_flag = self._ibm_flag()
         self._graph_ssl = ssl_clips is not None or ssl_frame_map is not None
 
@@ -402,7 +421,7 @@ class Trainer:
 
     def _stash(self) -> None:
         if self._graph is not None:
-            self._graph_cache[self._graph_ssl] = (self._graph, self._static, self._graph_out, self._graph_epoch_flag)
+            self._graph_cache[self._graph_ssl] = (self._graph, self._static, self._graph_out, self._graph_epoch_flag, self._graph_updates)
 
     def select_graph(self, ssl: bool, targets=None) -> bool:
         """Make a captured graph that fits this batch current (see graph_matches); False = the caller must capture().
@@ -414,7 +433,7 @@ class Trainer:
         if ent is None or ent[3] != self._ibm_flag() or (targets is not None and self._max_segments(targets) > ent[1][1].shape[1]):
             return False
         self._stash()
-        self._graph, self._static, self._graph_out, self._graph_epoch_flag = ent
+        self._graph, self._static, self._graph_out, self._graph_epoch_flag, self._graph_updates = ent
         self._graph_ssl = bool(ssl)
         return True
 
@@ -459,16 +478,26 @@ class Trainer:
         sq = torch.stack([torch.linalg.vector_norm(g) ** 2 for _, g in self.groups]).sum()
         return sq.sqrt() * self.reducer.grad_scale
 
+    def _param_groups(self):
+        """None for the single-rate optimizer (thumos14/train.py:321); the ActivityNet script's two groups — backbone at
+        backbone_lr_scale x the rate first, then the head (anet/train.py:304-311) — otherwise."""
+        if self.backbone_lr_scale == 1.0:
+            return None
+        return [(list(self.net.backbone.parameters()), self.lr * self.backbone_lr_scale),
+                (list(self.net.coarse_pyramid_detection.parameters()), self.lr)]
+
     def optimizer_state_dict(self) -> dict:
-        """The `torch.optim.Adam(net.parameters()).state_dict()` a reference run would hold at this point (train.py:115)."""
+        """The `torch.optim.Adam(...).state_dict()` a reference run would hold at this point (train.py:115)."""
         from . import checkpoint
         return checkpoint.adam_state_dict(list(self.net.parameters()), self.groups, self.state, step=self.step_count,
-                                          lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd)
+                                          lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
+                                          param_groups=self._param_groups())
 
     def load_optimizer_state_dict(self, sd: dict) -> None:
         from . import checkpoint
-        self.step_count = checkpoint.load_adam_state_dict(sd, list(self.net.parameters()), self.groups, self.state)
-        g = sd["param_groups"][0]
+        self.step_count = checkpoint.load_adam_state_dict(sd, list(self.net.parameters()), self.groups, self.state,
+                                                          param_groups=self._param_groups())
+        g = sd["param_groups"][-1]                  # the head's group carries the base rate
         self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
         self._step_dev.fill_(self.step_count)
         # a captured step graph has the optimizer's hyper-parameters baked into its Adam launches: capture again

@@ -101,6 +101,47 @@ def test_optimizer_state_interoperates_with_torch_adam():
         ck.load_adam_state_dict(bad, params, groups, state2)
 
 
+def test_two_rate_optimizer_state_matches_the_activitynet_layout():
+    """anet/train.py:304-311 builds Adam from two groups (backbone at 0.1 x the rate, then coarse_pyramid_detection): parameters
+    are numbered backbone-first, unlike net.parameters().  The state dict in that layout loads into such a torch optimizer and
+    comes back; a single-rate file is refused with a message instead of being mis-assigned."""
+    from opental_b200 import checkpoint as ck
+    from opental_b200.bdnet import BDNet
+    from opental_b200.engine import FlatParams
+    net = BDNet(training=False, use_edl=True, num_classes=16, os_head=True)
+    net.train()
+    dev = torch.device("cpu")
+    bb, hc = net.backbone, net.coarse_pyramid_detection.conv_store
+    w, g = bb.flat_parameters(dev)
+    hc.ensure(dev)
+    skip = {id(p) for p in bb.parameters()} | {id(r.weight) for r in hc.recs}
+    head = FlatParams([p for p in net.parameters() if p.requires_grad and id(p) not in skip])
+    groups = [(w, g), (hc.flat_w, hc.flat_g), (head.w, head.g)]
+    gen = torch.Generator().manual_seed(1)
+    state = [dict(m=torch.randn(a.shape, generator=gen), v=torch.rand(a.shape, generator=gen)) for a, _ in groups]
+    params = list(net.parameters())
+    pg = [(list(net.backbone.parameters()), 1e-6), (list(net.coarse_pyramid_detection.parameters()), 1e-5)]
+    sd = ck.adam_state_dict(params, groups, state, step=3, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, param_groups=pg)
+    assert [len(x["params"]) for x in sd["param_groups"]] == [len(pg[0][0]), len(pg[1][0])]
+    assert [x["lr"] for x in sd["param_groups"]] == [1e-6, 1e-5]
+    opt = torch.optim.Adam([{"params": net.backbone.parameters(), "lr": 1.0}, {"params": net.coarse_pyramid_detection.parameters(), "lr": 1.0}])
+    opt.load_state_dict(sd)
+    back = opt.state_dict()
+    # index 0 is the backbone's first parameter in this layout
+    first_bb = pg[0][0][0]
+    if first_bb.requires_grad:
+        assert torch.equal(back["state"][0]["exp_avg"], ck.moment_view(first_bb, groups, [s["m"] for s in state]))
+    state2 = [dict(m=torch.zeros_like(a), v=torch.zeros_like(a)) for a, _ in groups]
+    assert ck.load_adam_state_dict(back, params, groups, state2, param_groups=pg) == 3
+    for key in ("m", "v"):
+        for p in params:
+            if p.requires_grad:
+                assert torch.equal(ck.moment_view(p, groups, [s[key] for s in state]), ck.moment_view(p, groups, [s[key] for s in state2]))
+    one = ck.adam_state_dict(params, groups, state, step=3, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    with pytest.raises(ValueError, match="not interchangeable"):
+        ck.load_adam_state_dict(one, params, groups, state2, param_groups=pg)
+
+
 def test_proposal_list_has_the_reference_format():
     """inference.to_proposal_list: the dict layout of get_video_detections (test.py:182-200)."""
     from opental_b200.inference import results_json, to_proposal_list

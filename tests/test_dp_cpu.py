@@ -272,7 +272,7 @@ def test_launch_head_allreduce_is_idempotent_within_a_step():
     tr.reducer = type("R", (), {"launch": lambda self, which=None: launched.append(list(which))})()
     tr.groups = [None, None, None]
     tr._n_head_buckets = 2                      # exchange buckets: the head's two buffers first, then the backbone's two parts
-    tr._head_launched = tr._deep_launched = tr._warming_up = False
+    tr._head_launched = tr._deep_launched = tr._warming_up = tr._defer_comm = False
     tr._launch_head_allreduce(); tr._launch_head_allreduce()
     assert launched == [[0, 1]]
     # the deep-stage hook launches the head buckets if nobody has, then Mixed_4b..5c, once

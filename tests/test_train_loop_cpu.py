@@ -141,6 +141,7 @@ def test_trainer_graph_cache_bookkeeping():
     from opental_b200.engine import Trainer
     tr = Trainer.__new__(Trainer)
     tr._graph, tr._graph_ssl, tr._graph_cache, tr._static, tr._graph_out, tr.target_slots = None, False, {}, None, None, 8
+    tr._graph_updates = True                            # does the current graph contain the exchange + Adam (travels with the graph)
     cls = types.SimpleNamespace(with_ibm=True, epoch=1, ibm_start=3)
     tr.criterion = types.SimpleNamespace(cls_loss=cls)
 
