@@ -113,6 +113,30 @@ def test_trainer_step_from_uint8_frames_on_the_emulated_abi(monkeypatch):
         assert float((a - b).norm() / b.norm()) < 5e-2
 
 
+def test_nothing_with_an_autograd_graph_outlives_a_step(monkeypatch):
+    """After Trainer.step no tensor reachable from the Trainer / criterion may carry a grad_fn: a live loss tensor keeps the step's
+    autograd graph — and the AccumulateGrad nodes of the parameters, which remember the stream they were created on — alive, and a
+    later CUDA-graph capture on another stream then fails inside backward() (round 2: the criterion's `last_vec` did exactly that
+    and turned every re-capture of the clip-length x batch sweep into an eager fallback).  Checked with the fused loss glue, whose
+    loss vector is the tensor in question."""
+    from opental_b200 import engine
+    abi_emu.install(monkeypatch)
+    torch.manual_seed(0)
+    net, crit = engine.build_opental(device="cpu", epoch=11)
+    tr = engine.Trainer(net, crit, lr=1e-5)
+    px = engine.synthetic_clip_u8(0).unsqueeze(0)
+    tg = [engine.synthetic_targets(0)]
+    sc = engine.synthetic_scores(tg[0]).unsqueeze(0)
+    result = tr.step(px, tg, sc)
+    flat = [result[0], *[l for l in result[1] if l is not None], result[2], result[3]]
+    assert all(t.grad_fn is None for t in flat)
+    for owner in (crit, crit.cls_loss, tr):
+        for name, val in vars(owner).items():
+            if torch.is_tensor(val):
+                assert val.grad_fn is None, (type(owner).__name__, name)
+    assert crit.last_vec is not None and crit.last_vec.grad_fn is None            # the fused glue ran and its vector was detached
+
+
 def test_training_loop_from_dataset_files_on_the_emulated_abi(monkeypatch, tmp_path):
     """The pieces a real run strings together — files in the reference's formats -> window index -> loader threads -> padded
     batches -> train_loop.run_one_epoch -> Trainer.step with the self-supervised second pass through the frame map -> checkpoint
