@@ -59,6 +59,13 @@ OTAL_API int otal_bmp_forward_f64(const double* in, const double* seg, double* o
                          void* stream);
 OTAL_API int otal_bmp_backward_f64(const double* grad_out, const double* in, const double* seg, double* grad_in, int B,
                           int C, int T, int K, int compat_tscale_bug, void* stream);
+/* half precision (AT_DISPATCH_FLOATING_TYPES_AND_HALF, boundary_max_pooling_kernel.cu:96,128): raw IEEE binary16 bit patterns,
+ * segments half as well (truncated like the reference's static_cast<int>).  The backward sums a frame's contributions in fp32
+ * and rounds once (the reference's half atomicAdd rounds after every addition, in a run-dependent order). */
+OTAL_API int otal_bmp_forward_f16(const uint16_t* in, const uint16_t* seg, uint16_t* out, int B, int C, int T, int K,
+                         void* stream);
+OTAL_API int otal_bmp_backward_f16(const uint16_t* grad_out, const uint16_t* in, const uint16_t* seg, uint16_t* grad_in,
+                          int B, int C, int T, int K, int compat_tscale_bug, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (tcgen05 / TMA), stride 1 — replaces the per-layer chain

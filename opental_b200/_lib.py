@@ -113,6 +113,8 @@ SIGNATURES = {
     "otal_bmp_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_bmp_forward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_bmp_backward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_bmp_forward_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "otal_bmp_backward_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "otal_conv_igemm_fwd": (c_int, [POINTER(ConvDesc), c_void_p]),
     "otal_conv1a_fwd": (c_int, [POINTER(Conv1aDesc), c_void_p]),
     "otal_conv1a_fwd_u8": (c_int, [POINTER(Conv1aDesc), c_void_p]),

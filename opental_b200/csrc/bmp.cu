@@ -16,9 +16,22 @@
 // compat_tscale_bug=1 reproduces the reference backward's use of grad_output.size(2) (=K) as the time extent
 // for clamping *and* addressing (boundary_max_pooling_kernel.cu:121): rows are then K floats
 // apart in the flat input / grad_in buffers and the tail [B*C*K, B*C*T) of grad_in stays zero.
+//
+// Half precision (the reference dispatches AT_DISPATCH_FLOATING_TYPES_AND_HALF, boundary_max_pooling_kernel.cu:96,128): same
+// kernels on __half.  Segments are half as well (the reference casts them with static_cast<int>: truncation).  The backward sums
+// a frame's contributions in fp32 and rounds once — the reference's half atomicAdd rounds after every addition, in an order that
+// changes from run to run, so the two agree to a few half ulps of the partial sums, not bit for bit.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace otal {
+
+template <typename T> struct BmpAcc { using type = T; };
+template <> struct BmpAcc<__half> { using type = float; };
+template <typename A, typename T> __device__ __forceinline__ A bmp_to_acc(T v) { return static_cast<A>(v); }
+template <> __device__ __forceinline__ float bmp_to_acc<float, __half>(__half v) { return __half2float(v); }
+template <typename T, typename A> __device__ __forceinline__ T bmp_from_acc(A v) { return static_cast<T>(v); }
+template <> __device__ __forceinline__ __half bmp_from_acc<__half, float>(float v) { return __float2half_rn(v); }
 
 constexpr int kBmpThreads = 256;
 constexpr int kBmpSmemBudget = 40 * 1024;  // bytes for staged rows
@@ -29,6 +42,8 @@ template <>
 __device__ __forceinline__ int seg_to_int<float>(float v) { return __float2int_rz(v); }
 template <>
 __device__ __forceinline__ int seg_to_int<double>(double v) { return __double2int_rz(v); }
+template <>
+__device__ __forceinline__ int seg_to_int<__half>(__half v) { return __half2int_rz(v); }
 
 // Stage segments (clamped ints) for sample n: seg_s[k*4 + j]
 template <typename T>
@@ -119,10 +134,11 @@ bmp_backward_kernel(const T* __restrict__ gout, const T* __restrict__ in, const 
         const int row = i / tlen, t = i - row * tlen;
         const int* am = amax_s + row * K;
         const T* g = go_s + row * K;
-        T acc = T(0);
+        using A = typename BmpAcc<T>::type;
+        A acc = A(0);
         for (int k = 0; k < K; ++k)
-            if (am[k] == t) acc += g[k];
-        dst[i] = acc;
+            if (am[k] == t) acc += bmp_to_acc<A, T>(g[k]);
+        dst[i] = bmp_from_acc<T, A>(acc);
     }
 }
 
@@ -276,6 +292,22 @@ int otal_bmp_backward_f64(const double* gout, const double* in, const double* se
     if (rc) return rc;
     return bmp_backward_impl<double>(gout, in, seg, gin, B, C, T, K, compat_tscale_bug,
                                      static_cast<cudaStream_t>(stream));
+}
+
+/* half: pointers are the raw 16-bit patterns (IEEE binary16), C has no half type */
+int otal_bmp_forward_f16(const uint16_t* in, const uint16_t* seg, uint16_t* out, int B, int C, int T, int K, void* stream) {
+    int rc = check_bmp_args(in, seg, out, B, C, T, K);
+    if (rc) return rc;
+    return bmp_forward_impl<__half>(reinterpret_cast<const __half*>(in), reinterpret_cast<const __half*>(seg),
+                                    reinterpret_cast<__half*>(out), B, C, T, K, static_cast<cudaStream_t>(stream));
+}
+int otal_bmp_backward_f16(const uint16_t* gout, const uint16_t* in, const uint16_t* seg, uint16_t* gin, int B, int C, int T,
+                          int K, int compat_tscale_bug, void* stream) {
+    int rc = check_bmp_args(in, seg, gin, B, C, T, K);
+    if (rc) return rc;
+    return bmp_backward_impl<__half>(reinterpret_cast<const __half*>(gout), reinterpret_cast<const __half*>(in),
+                                     reinterpret_cast<const __half*>(seg), reinterpret_cast<__half*>(gin), B, C, T, K,
+                                     compat_tscale_bug, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

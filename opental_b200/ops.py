@@ -153,7 +153,7 @@ def _ptr(t: torch.Tensor | None) -> int | None:
 # ----------------------------------------------------------------------------------------------------------
 # BoundaryMaxPooling
 # ----------------------------------------------------------------------------------------------------------
-_BMP_SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
+_BMP_SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.float16: "f16"}      # the reference's dispatch set
 
 
 def _bmp_check(input: torch.Tensor, segments: torch.Tensor, *more: torch.Tensor) -> str:
@@ -164,7 +164,7 @@ def _bmp_check(input: torch.Tensor, segments: torch.Tensor, *more: torch.Tensor)
         if not t.is_contiguous():
             raise RuntimeError(f"{name} must be contiguous")
     if input.dtype not in _BMP_SUFFIX:
-        raise RuntimeError(f"boundary_max_pooling: unsupported dtype {input.dtype} (float32 / float64 only)")
+        raise RuntimeError(f"boundary_max_pooling: unsupported dtype {input.dtype} (float32 / float64 / float16, as the reference)")
     if segments.dtype != input.dtype:
         raise RuntimeError("segments must have the same dtype as input")
     if input.dim() != 3 or segments.dim() != 3 or segments.size(2) != 4:

@@ -104,6 +104,32 @@ def test_float64_and_nan(ops):
     assert not torch.isnan(out[0, 0, 0])        # NaN never wins the strict '>' unless it is the first element
 
 
+@pytest.mark.parametrize("shape", [(2, 1024, 64, 64), (2, 512, 256, 64), (3, 10, 37, 5)])
+def test_half_precision_dispatch(ops, shape):
+    """The reference dispatches AT_DISPATCH_FLOATING_TYPES_AND_HALF (boundary_max_pooling_kernel.cu:96,128): float16 input with
+    float16 segments (integers below 2048 are exact).  Forward: the maximum is an element of the row — bit-exact against the oracle
+    run on the same half values.  Backward: ours sums a frame's contributions in fp32 and rounds once (half ulp of the result);
+    the reference's own kernel rounds after every atomicAdd in a run-dependent order, so it is compared in norm."""
+    B, C, T, K = shape
+    inp, seg, gout = (t.half() for t in make_case(B, C, T, K, seed=3 + sum(shape)))
+    x = inp.float().requires_grad_(True)
+    y = O.boundary_max_pooling(x, seg.float(), False)
+    (gx,) = torch.autograd.grad(y, x, gout.float())
+    out = ops.bmp_forward(inp.cuda(), seg.cuda())
+    assert out.dtype == torch.float16 and torch.equal(out.cpu(), y.detach().half())
+    gi = ops.bmp_backward(gout.cuda(), inp.cuda(), seg.cuda(), False)
+    assert gi.dtype == torch.float16
+    assert torch.allclose(gi.float().cpu(), gx, rtol=1e-3, atol=1e-6)           # one rounding to half: 2^-11 relative
+    assert torch.equal(gi, ops.bmp_backward(gout.cuda(), inp.cuda(), seg.cuda(), False))      # deterministic
+    import build_ref
+    ref = build_ref.load_module()
+    if ref is not None and K <= T:
+        assert torch.equal(out, ref.forward(inp.cuda(), seg.cuda()))
+        want = ref.backward(gout.cuda(), inp.cuda(), seg.cuda()).float()
+        got = ops.bmp_backward(gout.cuda(), inp.cuda(), seg.cuda(), True).float()
+        assert float((got - want).norm() / want.norm().clamp(min=1e-6)) < 5e-3 and float((got - want).abs().max()) < 0.25
+
+
 def test_error_behaviour(ops):
     inp, seg, gout = (t.cuda() for t in make_case(2, 8, 16, 4, seed=5))
     with pytest.raises(RuntimeError, match="CUDA"):
