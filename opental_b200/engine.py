@@ -338,19 +338,17 @@ class Trainer:
         """Capture zero_grad + forward + loss + backward for this input geometry into ONE CUDA graph.  The head and the
         loss are ~2500 small launches whose host-side enqueue cost (~75 ms per step at batch 8) exceeds the GPU work; a
         graph replay removes it.  Inputs are copied into static buffers before every replay; the gradient all-reduce and
-        the Adam launches stay outside the graph (Adam's bias correction depends on the host step counter).
+        the Adam launches are part of the graph (`graph_update`; Adam reads its step counter from device memory).
         The graph bakes in `criterion.cls_loss.epoch >= ibm_start`: re-capture when the epoch crosses ibm_start."""
         import gc
         self._release_for_capture(ssl_clips is not None or ssl_frame_map is not None)
         gc.collect()                                 # also drops dead autograd graphs of earlier eager steps (see forward_backward)
-        # Data parallel: the FIRST graph a Trainer captures holds the gradient exchange and the Adam update.  Capturing NCCL work
-        # a second time on the same Trainer fails on this stack (torch 2.11 / NCCL 2.28: "dependency created on uncaptured work in
-        # another stream" inside backward(), whatever is done between the two captures — tools/probe/recapture_dp.py), so
-        # re-captures (the SSL flavour, the IBM switch, more target slots, the sweep's next batch size) keep the exchange and the
-        # update behind the replay, as in round 1.  Single-GPU graphs always contain the update.
+        # Data parallel: every captured graph holds the gradient exchange and the Adam update, re-captures included (2 GPUs:
+        # tools/probe/recapture_dp.py, profiles/r02_recapture_probe_n2.txt).  OTAL_DP_RECAPTURE=0 keeps the exchange and the update of
+        # a re-captured graph behind its replay instead (developer switch).  Single-GPU graphs always contain the update.
         import os
-        recapture_nccl = os.environ.get("OTAL_DP_RECAPTURE", "0") == "1"       # probe switch: capture the exchange again anyway
-        in_graph = bool(self.graph_update) and not (self.world > 1 and self._nccl_captured and not recapture_nccl)
+        behind = os.environ.get("OTAL_DP_RECAPTURE", "1") == "0" and self.world > 1 and self._nccl_captured
+        in_graph = bool(self.graph_update) and not behind
         tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
         srcs = [clips, tgt, valid, scores] + self._ssl_sources(ssl_clips, ssl_targets, ssl_frame_map)
         self._static = [torch.empty_like(t) for t in srcs]

@@ -25,9 +25,9 @@ for B in (1, 2, 4):
         for _ in range(3):
             cost, *_ = tr.step(clips, (tp, tv), sc)
         torch.cuda.synchronize()
-        print(rank, "B", B, "ok", float(cost), torch.cuda.memory_allocated() >> 20, "MiB", flush=True)
+        sys.stdout.write(f"{rank} B {B} ok {float(cost):.6f} {torch.cuda.memory_allocated() >> 20} MiB graph_updates {tr._graph_updates}\n"); sys.stdout.flush()
     except Exception:
-        print(rank, "B", B, "FAILED", flush=True)
+        sys.stdout.write(f"{rank} B {B} FAILED\n"); sys.stdout.flush()
         traceback.print_exc()
         break
     finally:
@@ -39,5 +39,5 @@ if world > 1:
     chk = torch.stack([w.double().sum() for w, _ in tr.groups])
     both = [torch.empty_like(chk) for _ in range(world)]
     dist.all_gather(both, chk)
-    print(rank, "params in sync:", all(bool((b == both[0]).all()) for b in both), "graph_updates", tr._graph_updates, flush=True)
+    sys.stdout.write(f"{rank} params in sync: {all(bool((b == both[0]).all()) for b in both)}\n"); sys.stdout.flush()
 engine.shutdown_distributed([tr])

@@ -1,18 +1,18 @@
 #!/bin/bash
-# 2 GPUs: re-capture of the data-parallel step graph on one Trainer — the fallback (exchange behind the replay) and the in-graph
-# re-capture; then the driver's launch line with every leg under the mode that passed
+# 2 GPUs: re-capture of the data-parallel step graph on one Trainer (in-graph exchange, the default, and the developer switch that
+# keeps it behind the replay), global normalisers under NCCL, then the driver's launch line with every leg
 set -u
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512"
-run() { echo "== $1"; shift; env "$@" timeout 150 $TR tools/probe/recapture_dp.py 2>&1 | grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax\|^$" | grep " B \|Error\|in sync" | head -12; }
+run() { echo "== $1"; shift; env "$@" timeout 150 $TR tools/probe/recapture_dp.py 2>&1 | grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax\|^$" | grep " B \|Error\|in sync" | sort | head -12; }
 {
-run fallback PROBE_MODE=destroy
-run recapture_in_graph OTAL_DP_RECAPTURE=1 PROBE_MODE=destroy
-} 2>&1 | tee gpurun_out/r02_recapture_probe2.txt
-MODE=0
-if [ "$(sed -n '/recapture_in_graph/,$p' gpurun_out/r02_recapture_probe2.txt | grep -c ' ok ')" = "6" ]; then MODE=1; fi
-echo "full bench with OTAL_DP_RECAPTURE=$MODE"
-( time OTAL_DP_RECAPTURE=$MODE timeout 500 $TR bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r02_full_bench_n2.json 2> gpurun_out/r02_full_bench_n2.err ) 2>&1 | tail -3
+run recapture_in_graph_default PROBE_MODE=destroy
+run exchange_behind_replay OTAL_DP_RECAPTURE=0 PROBE_MODE=destroy
+} 2>&1 | tee gpurun_out/r02_recapture_probe_n2.txt
+echo "== global normalisers under NCCL"
+timeout 200 python tools/probe/global_norm_nccl.py 2>&1 | grep -v "SyntaxWarning\|logit: softmax" | tail -3
+timeout 200 $TR tools/probe/global_norm_nccl.py 2>&1 | grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax\|^$" | tail -8 | tee gpurun_out/r02_global_norm_nccl.txt
+( time timeout 500 $TR bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r02_full_bench_n2.json 2> gpurun_out/r02_full_bench_n2.err ) 2>&1 | tail -3
 grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax" gpurun_out/r02_full_bench_n2.err | tail -5
 python - <<PY
 import json
