@@ -11,7 +11,7 @@ run exchange_behind_replay OTAL_DP_RECAPTURE=0 PROBE_MODE=destroy
 } 2>&1 | tee gpurun_out/r02_recapture_probe_n2.txt
 echo "== global normalisers under NCCL"
 timeout 200 python tools/probe/global_norm_nccl.py 2>&1 | grep -v "SyntaxWarning\|logit: softmax" | tail -3
-timeout 200 $TR tools/probe/global_norm_nccl.py 2>&1 | grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax\|^$" | tail -8 | tee gpurun_out/r02_global_norm_nccl.txt
+timeout 200 $TR tools/probe/global_norm_nccl.py 2>&1 | grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax\|^$" | tail -30 | tee gpurun_out/r02_global_norm_nccl.txt
 ( time timeout 500 $TR bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r02_full_bench_n2.json 2> gpurun_out/r02_full_bench_n2.err ) 2>&1 | tail -3
 grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax" gpurun_out/r02_full_bench_n2.err | tail -5
 python - <<PY
