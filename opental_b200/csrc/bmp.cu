@@ -34,6 +34,9 @@ template <typename T, typename A> __device__ __forceinline__ T bmp_from_acc(A v)
 template <> __device__ __forceinline__ __half bmp_from_acc<__half, float>(float v) { return __float2half_rn(v); }
 
 constexpr int kBmpThreads = 256;
+// bytes of the staged rows, rounded up so that the int / gradient arrays behind them stay aligned (half rows of odd length)
+template <typename T>
+__host__ __device__ inline size_t bmp_rows_bytes(int R, int tlen) { return ((size_t)R * tlen * sizeof(T) + 15) & ~(size_t)15; }
 constexpr int kBmpSmemBudget = 40 * 1024;  // bytes for staged rows
 
 template <typename T>
@@ -61,7 +64,7 @@ bmp_forward_kernel(const T* __restrict__ in, const T* __restrict__ seg, T* __res
                    int K, int R, int blocks_per_sample) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw);
-    int* seg_s = reinterpret_cast<int*>(smem_raw + (size_t)R * tlen * sizeof(T));
+    int* seg_s = reinterpret_cast<int*>(smem_raw + bmp_rows_bytes<T>(R, tlen));
 
     const int n = blockIdx.x / blocks_per_sample;
     const int c0 = (blockIdx.x % blocks_per_sample) * R;
@@ -96,7 +99,7 @@ bmp_backward_kernel(const T* __restrict__ gout, const T* __restrict__ in, const 
                     T* __restrict__ gin, int C, int tlen, int K, int R, int blocks_per_sample) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw);
-    int* seg_s = reinterpret_cast<int*>(smem_raw + (size_t)R * tlen * sizeof(T));
+    int* seg_s = reinterpret_cast<int*>(smem_raw + bmp_rows_bytes<T>(R, tlen));
     int* amax_s = seg_s + K * 4;                                   // [R*K]
     T* go_s = reinterpret_cast<T*>(amax_s + (size_t)R * K + ((R * K) & 1));  // [R*K], 8-byte aligned
 
@@ -192,7 +195,7 @@ __global__ void bmp_backward_direct_kernel(const T* __restrict__ gout, const T* 
 static int pick_rows(int tlen, int K, size_t elt, bool backward, int C) {
     // rows per CTA: as many as fit the staging budget, at most 32, at least 1; 0 = does not fit at all
     size_t per_row = (size_t)tlen * elt + (backward ? (size_t)K * (4 + elt) : 0);
-    size_t fixed = (size_t)K * 16 + 16;
+    size_t fixed = (size_t)K * 16 + 32;
     if (per_row + fixed > (size_t)kBmpSmemBudget) return 0;
     int r = (int)(((size_t)kBmpSmemBudget - fixed) / per_row);
     r = r > 32 ? 32 : r;
@@ -208,7 +211,7 @@ static int bmp_forward_impl(const T* in, const T* seg, T* out, int B, int C, int
     if (R > 0) {
         while (R > 1 && (long long)B * ((C + R - 1) / R) < 296) R = (R + 1) / 2;
         const int bps = (C + R - 1) / R;
-        size_t smem = (size_t)R * tlen * sizeof(T) + (size_t)K * 16;
+        size_t smem = bmp_rows_bytes<T>(R, tlen) + (size_t)K * 16;
         bmp_forward_kernel<T><<<B * bps, kBmpThreads, smem, s>>>(in, seg, out, C, tlen, K, R, bps);
     } else {
         long long total = (long long)B * C * K;
@@ -241,7 +244,7 @@ static int bmp_backward_impl(const T* gout, const T* in, const T* seg, T* gin, i
     if (R > 0) {
         while (R > 1 && (long long)B * ((C + R - 1) / R) < 296) R = (R + 1) / 2;
         const int bps = (C + R - 1) / R;
-        size_t smem = (size_t)R * tlen * sizeof(T) + (size_t)K * 16 + (size_t)(R * K + 1) * 4 +
+        size_t smem = bmp_rows_bytes<T>(R, tlen) + (size_t)K * 16 + (size_t)(R * K + 1) * 4 +
                       (size_t)R * K * sizeof(T) + 8;
         bmp_backward_kernel<T><<<B * bps, kBmpThreads, smem, s>>>(gout, in, seg, gin, C, tlen, K, R, bps);
     } else {

@@ -69,7 +69,7 @@ class GradReducer:
         self.buffers = buffers
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self._work = []
+        self._work: dict = {}             # bucket index -> the handle of its all-reduce in flight
 
     @property
     def grad_scale(self) -> float:
@@ -80,12 +80,14 @@ class GradReducer:
         if self.world == 1:
             return
         for i in (range(len(self.buffers)) if which is None else which):
-            self._work.append(dist.all_reduce(self.buffers[i], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            self._work[i] = dist.all_reduce(self.buffers[i], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
-    def wait(self) -> None:
-        for w in self._work:
-            w.wait()
-        self._work = []
+    def wait(self, which=None) -> None:
+        """Make the CURRENT stream wait for the all-reduces of the buckets in `which` (default: all in flight)."""
+        for i in (sorted(self._work) if which is None else which):
+            w = self._work.pop(i, None)
+            if w is not None:
+                w.wait()
 
 
 def shutdown_distributed(trainers=(), grace_s: float = 12.0) -> None:
@@ -212,8 +214,22 @@ class Trainer:
         self.graph_update = True       # capture the gradient exchange + Adam update into the step graph (False: they follow the replay)
         self._static = None
         self._capturing = self._warming_up = False
-        bb.on_backward_start = self._on_backbone_backward if self.world > 1 else None
-        bb.on_deep_done = self._on_backbone_deep_done if self.world > 1 else None
+        # Optimizer launches off the step's tail: a parameter range is updated as soon as its (exchanged) gradient is final — the
+        # head's two groups when the backbone backward starts (73 % of the parameters), Mixed_4b..5c when their bucket is back — on
+        # a side stream next to the remaining backward; only the first layers' update is left behind the last weight gradient.
+        # OFF by default: on one GPU it measures the same (17.28 / 17.28 / 17.25 / 17.25 ms, off / on / off / on,
+        # profiles/r02_early_adam_n1.txt — the update competes with the HBM-bound first kernels of the backbone backward for the
+        # same bandwidth it would use at the tail); OTAL_EARLY_ADAM=1 switches it on.
+        import os
+        self.early_update = os.environ.get("OTAL_EARLY_ADAM", "0") == "1"
+        self._early = False               # inside step() / the captured body: the hooks may launch optimizer work
+        self._updated: list = []          # (group, lo, hi) ranges already updated in this step
+        self._counted = False             # has the device-side step counter been advanced in this step?
+        self._opt_stream = None
+        self._bb_split = split
+        bb.on_backward_start = self._on_backbone_backward
+        bb.on_deep_done = self._on_backbone_deep_done if self.world > 1 else None      # (its join of the weight-gradient stream
+        #                                                                               is not worth an early update alone)
 
     # ---------------------------------------------------------------------------------------------- data parallel
     def _comm_allowed(self) -> bool:
@@ -223,13 +239,16 @@ class Trainer:
 
     def _on_backbone_backward(self) -> None:
         if self._comm_allowed():
-            self._launch_head_allreduce()
+            if self.world > 1:
+                self._launch_head_allreduce()
+            self._early_update("head")
 
     def _on_backbone_deep_done(self) -> None:
         if self._comm_allowed() and not self._deep_launched:
             self._launch_head_allreduce()
             self.reducer.launch([self._n_head_buckets])         # Mixed_4b..5c
             self._deep_launched = True
+            self._early_update("deep")
 
     def _launch_head_allreduce(self) -> None:
         if self._head_launched:                                # once per step, whoever asks first
@@ -237,21 +256,65 @@ class Trainer:
         self.reducer.launch(range(self._n_head_buckets))       # head buffers: complete once the backbone backward starts
         self._head_launched = True
 
+    def _adam(self, gi: int, lo: int = 0, hi: int | None = None) -> None:
+        (w, g), st = self.groups[gi], self.state[gi]
+        hi = w.numel() if hi is None else hi
+        if hi <= lo:
+            return
+        lr = self.lr * self.backbone_lr_scale if gi == 0 else self.lr         # group 0 = the backbone's flat buffer
+        ops.adam_step(w[lo:hi], g[lo:hi], st["m"][lo:hi], st["v"][lo:hi], lr=lr, betas=self.betas, eps=self.eps,
+                      weight_decay=self.wd, grad_scale=self.reducer.grad_scale, step_dev=self._step_dev)
+        self._updated.append((gi, lo, hi))
+
+    def _count_step(self) -> None:
+        if not self._counted:
+            self._step_dev.add_(1)
+            self._counted = True
+
+    def _early_update(self, which: str) -> None:
+        """Adam for the ranges whose gradients are final at this point of the backward, on the optimizer side stream (it waits for
+        everything enqueued so far and, data parallel, for the ranges' all-reduces; `_finish_step` joins it).  Only inside a
+        step: a bare forward_backward() leaves the weights alone."""
+        if not (self._early and self.early_update):
+            return
+        cuda = self.device.type == "cuda"
+        if cuda:
+            if self._opt_stream is None:
+                self._opt_stream = torch.cuda.Stream(self.device)
+            self._opt_stream.wait_stream(torch.cuda.current_stream())
+        import contextlib
+        with (torch.cuda.stream(self._opt_stream) if cuda else contextlib.nullcontext()):
+            if not any(gi > 0 for gi, _, _ in self._updated):              # the head's groups (also when "deep" comes first)
+                self.reducer.wait(range(self._n_head_buckets))
+                self._count_step()
+                for gi in range(1, len(self.groups)):
+                    self._adam(gi)
+            if which == "deep":
+                self.reducer.wait([self._n_head_buckets])
+                self._adam(0, self._bb_split, None)
+
     def _finish_step(self) -> None:
-        """Everything after the backward: the buckets not exchanged yet, the wait, the step counter and the Adam launches.  Part of
-        the captured graph (NCCL collectives and the device-side step counter capture like any other launch)."""
+        """Everything after the backward: the buckets not exchanged yet, the wait, the step counter and the Adam launches of the
+        ranges that were not updated during the backward.  Part of the captured graph (NCCL collectives and the device-side step
+        counter capture like any other launch)."""
         if self.world > 1:
             self._launch_head_allreduce()
             if not self._deep_launched:
                 self.reducer.launch([self._n_head_buckets])
             self.reducer.launch([self._n_head_buckets + 1])
+        if self._updated and self._opt_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._opt_stream)          # join: early updates (and the waits they made)
+        if self.world > 1:
             self.reducer.wait()
             self._head_launched = self._deep_launched = False
-        self._step_dev.add_(1)
-        for gi, ((w, g), st) in enumerate(zip(self.groups, self.state)):      # group 0 = the backbone's flat buffer
-            lr = self.lr * self.backbone_lr_scale if gi == 0 else self.lr
-            ops.adam_step(w, g, st["m"], st["v"], lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
-                          grad_scale=self.reducer.grad_scale, step_dev=self._step_dev)
+        self._count_step()
+        done = {gi: (lo, hi) for gi, lo, hi in self._updated}
+        for gi in range(len(self.groups)):
+            if gi not in done:
+                self._adam(gi)
+            else:                                           # the part of the group in front of the early range (backbone: first layers)
+                self._adam(gi, 0, done[gi][0])
+        self._updated, self._counted = [], False
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
@@ -382,11 +445,13 @@ class Trainer:
             self._defer_comm = not in_graph
             with torch.cuda.graph(self._graph, stream=stream, capture_error_mode="thread_local"):
                 self.zero_grad()
+                self._early = in_graph
                 self._graph_out = self.forward_backward(c, (t, v), sc, *ssl_args)
                 if in_graph:
                     self._finish_step()
         finally:
-            self._capturing = self._warming_up = self._defer_comm = False
+            self._capturing = self._warming_up = self._defer_comm = self._early = False
+            self._updated, self._counted = [], False
             self._head_launched = self._deep_launched = False
         self._graph_updates = in_graph
         self._nccl_captured = self._nccl_captured or (in_graph and self.world > 1)
@@ -461,7 +526,11 @@ class Trainer:
                 self._finish_step()
         else:
             self.zero_grad()
-            cost, losses, ls, le = self.forward_backward(clips, targets, scores, ssl_clips, ssl_targets, ssl_frame_map)
+            self._early, self._updated, self._counted = True, [], False
+            try:
+                cost, losses, ls, le = self.forward_backward(clips, targets, scores, ssl_clips, ssl_targets, ssl_frame_map)
+            finally:
+                self._early = False
             self._finish_step()
         self.step_count += 1
         return cost, losses, ls, le

@@ -273,9 +273,70 @@ def test_launch_head_allreduce_is_idempotent_within_a_step():
     tr.groups = [None, None, None]
     tr._n_head_buckets = 2                      # exchange buckets: the head's two buffers first, then the backbone's two parts
     tr._head_launched = tr._deep_launched = tr._warming_up = tr._defer_comm = False
+    tr._early, tr.early_update = False, True    # not inside a step: the hooks launch no optimizer work
     tr._launch_head_allreduce(); tr._launch_head_allreduce()
     assert launched == [[0, 1]]
     # the deep-stage hook launches the head buckets if nobody has, then Mixed_4b..5c, once
     launched.clear(); tr._head_launched = False
     tr._on_backbone_deep_done(); tr._on_backbone_deep_done()
     assert launched == [[0, 1], [2]]
+
+
+def test_early_optimizer_launches_cover_every_parameter_exactly_once(monkeypatch):
+    """Trainer._early_update / _finish_step bookkeeping (no GPU): whatever subset of the hooks fired during the backward — none
+    (a graph whose update follows the replay), the head hook only (one GPU), head + deep (data parallel) or deep first — the Adam
+    launches of one step partition every group exactly once, the step counter advances once, and buckets are waited for before
+    their ranges are updated."""
+    import types
+    from opental_b200 import engine
+    from opental_b200.engine import Trainer
+    events = []
+    monkeypatch.setattr(engine.ops, "adam_step", lambda w, g, m, v, **kw: events.append(("adam", w.data_ptr(), w.numel(), kw["lr"])))
+
+    def make(world):
+        tr = Trainer.__new__(Trainer)
+        tr.world, tr.device = world, torch.device("cpu")
+        tr.groups = [(torch.zeros(100), torch.zeros(100)), (torch.zeros(40), torch.zeros(40)), (torch.zeros(7), torch.zeros(7))]
+        tr.state = [dict(m=torch.zeros_like(w), v=torch.zeros_like(w)) for w, _ in tr.groups]
+        tr._bb_split, tr._n_head_buckets = 60, 2
+        tr.lr, tr.backbone_lr_scale, tr.betas, tr.eps, tr.wd = 1e-3, 0.1, (0.9, 0.999), 1e-8, 0.0
+        tr._step_dev = torch.zeros(1, dtype=torch.int32)
+        tr._head_launched = tr._deep_launched = tr._warming_up = tr._defer_comm = False
+        tr._early, tr.early_update, tr._updated, tr._counted, tr._opt_stream = True, True, [], False, None
+        tr.reducer = types.SimpleNamespace(grad_scale=1.0 / world,
+                                           launch=lambda which=None: events.append(("launch", list(which))),
+                                           wait=lambda which=None: events.append(("wait", None if which is None else list(which))))
+        return tr
+
+    def covered(tr):
+        out = {}
+        for e in events:
+            if e[0] == "adam":
+                gi = next(i for i, (w, _) in enumerate(tr.groups) if w.data_ptr() <= e[1] < w.data_ptr() + 4 * w.numel())
+                lo = (e[1] - tr.groups[gi][0].data_ptr()) // 4
+                out.setdefault(gi, []).append((lo, lo + e[2], e[3]))
+        return {gi: sorted(v) for gi, v in out.items()}
+
+    for world, hooks in ((1, ()), (1, ("head",)), (2, ("head", "deep")), (2, ("deep",)), (2, ())):
+        events.clear()
+        tr = make(world)
+        for h in hooks:
+            (tr._on_backbone_backward if h == "head" else tr._on_backbone_deep_done)()
+        tr._early = False
+        tr._finish_step()
+        cov = covered(tr)
+        assert [(lo, hi) for lo, hi, _ in cov[0]] in ([(0, 100)], [(0, 60), (60, 100)]), (world, hooks, cov)
+        assert [(lo, hi) for lo, hi, _ in cov[1]] == [(0, 40)] and [(lo, hi) for lo, hi, _ in cov[2]] == [(0, 7)]
+        assert all(abs(lr - 1e-4) < 1e-12 for _, _, lr in cov[0]) and cov[1][0][2] == 1e-3          # the backbone's own rate
+        assert int(tr._step_dev) == 1 and tr._updated == [] and tr._counted is False
+        if "deep" in hooks:                        # Mixed_4b..5c: updated early, after the wait for its bucket
+            i_wait = events.index(("wait", [2]))
+            i_adam = next(i for i, e in enumerate(events) if e[0] == "adam" and e[2] == 40 and e[1] == tr.groups[0][0].data_ptr() + 240)
+            assert i_wait < i_adam
+        if world > 1:                              # every bucket launched exactly once
+            assert sorted(b for e in events if e[0] == "launch" for b in e[1]) == [0, 1, 2, 3]
+    # outside a step (a bare forward_backward) the hooks leave the weights alone
+    events.clear()
+    tr = make(1); tr._early = False
+    tr._on_backbone_backward()
+    assert not any(e[0] == "adam" for e in events)
