@@ -3,7 +3,7 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514"
 ( time timeout 400 $TR bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r02_full_bench_n$N.json 2> gpurun_out/r02_full_bench_n$N.err ) 2>&1 | tail -3; echo "bench N=$N rc=$?"
 grep -v "^W1017\|OMP_NUM\|^\*\*\*\|SyntaxWarning\|logit: softmax" gpurun_out/r02_full_bench_n$N.err | tail -5
 python - <<PY
