@@ -65,6 +65,8 @@ struct ConvParams {
                      // tile is read from shared memory twice instead of three times per K step (these shapes are bound by the
                      // 128 B/clk shared-memory operand bandwidth, not by the tensor pipe); the epilogue adds the two halves
     int k32;         // K chunk of 32 elements = 64-byte rows, SWIZZLE_64B operands (the folded Conv3d_1a: 8 W taps x 4 channels)
+    int tail_ksteps;   // K = 16 steps the LAST chunk of a tap really holds (Cin = 144: 2 full chunks + 1 step instead of 4): the padded
+    int tail_ksteps2;  // part of a chunk is TMA zero fill in both operands, so its MMAs add exact zeros — not issued.  2: second K segment
     const float* scale;  // [Cout] or nullptr (=1)
     const float* shift;  // [Cout] or nullptr (=0)
     float* out_f32;      // optional NDHWC fp32 destination (nullptr = skip)
@@ -297,7 +299,15 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 const int ks = tile % p.ksplit;
                 n_it = kiters * (ks + 1) / p.ksplit - kiters * ks / p.ksplit;
             }
+            const int it_seg1 = kiters - p.kchunks2;       // iterations of the first K segment: taps x chunks, chunk fastest
+            int kc = 0;
             for (int it = 0; it < n_it; ++it) {
+                int ks_here = ksteps;                      // the last chunk of a tap / of the second segment may hold fewer K steps
+                if (it < it_seg1) {
+                    if (++kc == p.kchunks) { kc = 0; ks_here = p.tail_ksteps; }
+                } else if (it == n_it - 1) {
+                    ks_here = p.tail_ksteps2;
+                }
                 mbar_wait(&full_bar[stage], phase);
                 if (it == 0) OTAL_TL(tl_n, 3);
                 tc_fence_after();
@@ -310,7 +320,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (k >= ksteps) break;
+                        if (k >= ks_here) break;
                         const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2);
                         const uint64_t b_hi = b_hi0 + (uint64_t)(k * b_step);
                         if constexpr (NCAT) {
@@ -595,6 +605,9 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     }
     const int chunk = p.k32 ? 32 : kChunkK;
     p.kchunks = (L.w_k + chunk - 1) / chunk;
+    static const bool no_ktail = getenv("OTAL_NO_KTAIL") != nullptr;          // developer A/B: issue the zero K steps as before
+    p.tail_ksteps = no_ktail ? chunk / 16 : (L.w_k - (p.kchunks - 1) * chunk + 15) / 16;
+    p.tail_ksteps2 = (no_ktail || L.w2_k <= 0) ? kChunkK / 16 : (L.w2_k - (p.kchunks2 - 1) * kChunkK + 15) / 16;
     p.store_bf16 = L.y_hi != nullptr;
     p.total_tiles = p.N * p.tilesT * p.tilesH * p.tilesW * p.n_blocks;
     if (p.ksplit > 1) {
