@@ -619,10 +619,18 @@ static int finish_and_launch(ConvLaunch& L, ConvMaps& maps, cudaStream_t stream)
     p.ksplit = 1;
 
     const uint32_t smem_cap = 227 * 1024 - 1024;  // minus alignment slack
-    // prefer (>= 3 stages, double-buffered staging), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
+    // prefer (>= 3 stages, double-buffered staging), then (3 stages, 1 buffer), then (2 stages, 2 buffers), then (2 stages, 1 buffer)
     int nst = 0, nbuf = p.store_bf16 ? 2 : 0;
     for (int s = kMaxStages; s >= 3 && !nst; --s)
         if (conv_smem_layout(p.BN, p.nsplit, s, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = s;
+    {
+        // a third pipeline stage with ONE staging buffer before two stages with two (fits BN <= 112 in bf16x3): more operand bytes
+        // in flight for the HBM-bound 1x1 convs; 17.42 / 17.36 / 17.46 / 17.35 ms per step off / on / off / on
+        // (profiles/r02_prefer_stages_ab.txt).  OTAL_CONV_NO_PREFER_STAGES=1: the old order (developer A/B)
+        static const bool prefer_stages = getenv("OTAL_CONV_NO_PREFER_STAGES") == nullptr;
+        if (!nst && prefer_stages && p.store_bf16 &&
+            conv_smem_layout(p.BN, p.nsplit, 3, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) { nst = 3; nbuf = 1; }
+    }
     if (!nst && conv_smem_layout(p.BN, p.nsplit, 2, nbuf, p.b_mn, p.k32, p.a_single).total <= smem_cap) nst = 2;
     if (!nst && p.store_bf16 && conv_smem_layout(p.BN, p.nsplit, 2, 1, p.b_mn, p.k32, p.a_single).total <= smem_cap) { nst = 2; nbuf = 1; }
     if (!nst) { set_last_error_msg("conv: tile does not fit shared memory"); return OTAL_ERR_UNSUPPORTED; }
