@@ -297,6 +297,7 @@ class Trainer:
         """Everything after the backward: the buckets not exchanged yet, the wait, the step counter and the Adam launches of the
         ranges that were not updated during the backward.  Part of the captured graph (NCCL collectives and the device-side step
         counter capture like any other launch)."""
+        ops.nvtx_push("otal.exchange + adam")
         if self.world > 1:
             self._launch_head_allreduce()
             if not self._deep_launched:
@@ -315,6 +316,7 @@ class Trainer:
             else:                                           # the part of the group in front of the early range (backbone: first layers)
                 self._adam(gi, 0, done[gi][0])
         self._updated, self._counted = [], False
+        ops.nvtx_pop()
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
@@ -339,8 +341,13 @@ class Trainer:
 
     def forward_backward(self, clips: torch.Tensor, targets, scores: torch.Tensor, ssl_clips=None, ssl_targets=None,
                          ssl_frame_map=None):
-        out = self.net(clips)
+        ops.nvtx_push("otal.forward (backbone + head)")
+        try:
+            out = self.net(clips)
+        finally:
+            ops.nvtx_pop()
         anet = getattr(self.net, "variant", "thumos") == "anet"
+        ops.nvtx_push("otal.loss")
         if anet:      # the ActivityNet loss takes the list form (anet/train.py:168-172)
             losses = self.criterion([out[k] for k in ("loc", "conf", "prop_loc", "prop_conf", "center", "priors", "act", "prop_act")],
                                     targets)
@@ -351,6 +358,7 @@ class Trainer:
                 self.criterion.last_vec = None           # the re-weighted tuple is the loss now
         cost, ls, le = training_cost(out, losses, scores, lw=self.lw, cw=self.cw, ctw=self.ctw, actw=self.actw,
                                      score_scale=8 if anet else 4, loss_vec=getattr(self.criterion, "last_vec", None))
+        ops.nvtx_pop()
         if ssl_clips is not None or ssl_frame_map is not None:
             # second forward on the cut-paste augmented clip + triplet loss on its boundary features
             # (thumos14/train.py:237-242; BDNet.py:482-503); one backward for the sum.  With `ssl_frame_map` the augmented
@@ -365,7 +373,11 @@ class Trainer:
             finally:
                 bb.frame_map = None
             cost = cost + self.ssl_weight * self.triplet_loss(a, p, n)
-        cost.backward()
+        ops.nvtx_push("otal.backward (head + loss, backbone, gradient exchange hooks)")
+        try:
+            cost.backward()
+        finally:
+            ops.nvtx_pop()
         # Nothing non-detached may outlive this call: a live loss tensor keeps this step's autograd graph (and its AccumulateGrad
         # nodes, which remember the stream they were created on) alive, which breaks a later CUDA-graph capture ("dependency created
         # on uncaptured work in another stream" inside backward()).  The criterion's `last_vec` is such a tensor.

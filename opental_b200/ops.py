@@ -74,6 +74,20 @@ class KernelProfile:
 
 PROFILE = KernelProfile()
 
+# NVTX ranges around the stages of a step, for an Nsight Systems timeline of the EAGER path (a graph replay is one
+# node; tools/graph_timeline.py shows its inside).  Host-side markers only, off unless OTAL_NVTX=1.
+NVTX = os.environ.get("OTAL_NVTX", "0") == "1"
+
+
+def nvtx_push(name: str) -> None:
+    if NVTX and torch.cuda.is_available():
+        torch.cuda.nvtx.range_push(name)
+
+
+def nvtx_pop() -> None:
+    if NVTX and torch.cuda.is_available():
+        torch.cuda.nvtx.range_pop()
+
 
 def _require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:

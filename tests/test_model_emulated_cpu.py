@@ -127,7 +127,15 @@ def test_nothing_with_an_autograd_graph_outlives_a_step(monkeypatch):
     px = engine.synthetic_clip_u8(0).unsqueeze(0)
     tg = [engine.synthetic_targets(0)]
     sc = engine.synthetic_scores(tg[0]).unsqueeze(0)
+    marks = []                                   # the step's NVTX ranges (host-side markers, off unless OTAL_NVTX=1)
+    monkeypatch.setattr(engine.ops, "nvtx_push", lambda name: marks.append(name))
+    monkeypatch.setattr(engine.ops, "nvtx_pop", lambda: marks.append(None))
     result = tr.step(px, tg, sc)
+    depth = 0
+    for m in marks:
+        depth += 1 if m is not None else -1
+        assert depth >= 0
+    assert depth == 0 and [m.split(" ")[0] for m in marks if m] == ["otal.forward", "otal.loss", "otal.backward", "otal.exchange"]
     flat = [result[0], *[l for l in result[1] if l is not None], result[2], result[3]]
     assert all(t.grad_fn is None for t in flat)
     for owner in (crit, crit.cls_loss, tr):
