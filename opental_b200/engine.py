@@ -19,6 +19,9 @@ per-rank, which differs from "the reference at batch 8*W on one GPU" exactly as 
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -95,7 +98,6 @@ def shutdown_distributed(trainers=(), grace_s: float = 12.0) -> None:
     its communicator, so the trainers' graphs are released first; if the teardown stalls anyway a watchdog ends the process
     (exit code 0: the work is done by the time this is called)."""
     import gc
-    import os
     import threading
     if not (dist.is_available() and dist.is_initialized()):
         return
@@ -220,7 +222,6 @@ class Trainer:
         # OFF by default: on one GPU it measures the same (17.28 / 17.28 / 17.25 / 17.25 ms, off / on / off / on,
         # profiles/r02_early_adam_n1.txt — the update competes with the HBM-bound first kernels of the backbone backward for the
         # same bandwidth it would use at the tail); OTAL_EARLY_ADAM=1 switches it on.
-        import os
         self.early_update = os.environ.get("OTAL_EARLY_ADAM", "0") == "1"
         self._early = False               # inside step() / the captured body: the hooks may launch optimizer work
         self._updated: list = []          # (group, lo, hi) ranges already updated in this step
@@ -282,7 +283,6 @@ class Trainer:
             if self._opt_stream is None:
                 self._opt_stream = torch.cuda.Stream(self.device)
             self._opt_stream.wait_stream(torch.cuda.current_stream())
-        import contextlib
         with (torch.cuda.stream(self._opt_stream) if cuda else contextlib.nullcontext()):
             if not any(gi > 0 for gi, _, _ in self._updated):              # the head's groups (also when "deep" comes first)
                 self.reducer.wait(range(self._n_head_buckets))
@@ -421,7 +421,6 @@ class Trainer:
         # Data parallel: every captured graph holds the gradient exchange and the Adam update, re-captures included (2 GPUs:
         # tools/probe/recapture_dp.py, profiles/r02_recapture_probe_n2.txt).  OTAL_DP_RECAPTURE=0 keeps the exchange and the update of
         # a re-captured graph behind its replay instead (developer switch).  Single-GPU graphs always contain the update.
-        import os
         behind = os.environ.get("OTAL_DP_RECAPTURE", "1") == "0" and self.world > 1 and self._nccl_captured
         in_graph = bool(self.graph_update) and not behind
         tgt, valid = pad_targets(targets, clips.device, slots=max(self.target_slots, self._max_segments(targets)))
