@@ -106,3 +106,27 @@ def test_product_path_fails_loudly_without_cuda():
         ops.bmp_forward(torch.zeros(1, 2, 4), torch.zeros(1, 1, 4))
     with pytest.raises(RuntimeError):
         ops.split_bf16(torch.zeros(8))
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm may
+    import or execute anything under oracle/.  Static check over the product package (docstrings may cite oracle files)."""
+    import ast
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = {os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(root, "oracle", "*.py"))}
+    assert "opental_oracle" in names
+    offenders = []
+    for path in glob.glob(os.path.join(root, "opental_b200", "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            for m in mods:
+                if m.split(".")[0] in names or m.split(".")[0] == "oracle":
+                    offenders.append((os.path.relpath(path, root), m))
+    assert offenders == [], offenders
